@@ -1,0 +1,387 @@
+"""Problem descriptors for the reference examples on the hot path.
+
+Each builder restates what the corresponding `Problem` subclass of the reference
+constructs (dynamics, player costs, initial state) as the POD `ilqg_problem_desc`
+of include/ilqg.h.  Record order per player follows the reference's accumulation
+order (src/player_cost.cpp:194-215): state costs, control costs, state
+constraints, control constraints.
+
+  three_player_intersection  src/three_player_intersection_example.cpp:74-394
+  roundabout_merging         src/roundabout_merging_example.cpp:71-436,
+                             src/roundabout_lane_center.cpp:50-108
+  air_3d                     src/air_3d_example.cpp:62-141
+  two_player_point_mass_lq   test/test_lq_solver.cpp:143-177,227-248 (LQ-only)
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from . import _abi as abi
+
+F = np.float32
+
+
+class DescBuilder:
+    def __init__(self, num_time_steps: int = 100, time_step: float = 0.1):
+        self.d = abi.ProblemDesc()
+        self.d.num_time_steps = num_time_steps
+        self.d.time_step = time_step
+        self.d.initial_time = 0.0
+        self.d.num_players = 0
+        self.d.xdim = 0
+        self.d.num_subsystems = 0
+        self.d.num_costs = 0
+        self.d.num_polylines = 0
+        self.d.polyline_start[0] = 0
+        self._records: List[List[List[abi.CostDesc]]] = []  # [player][category] -> records
+
+    # dynamics ---------------------------------------------------------------
+    def add_player(self, udim: int, state_reg: float = 0.0, control_reg: float = 0.0,
+                   structure: int = abi.COST_SUM) -> int:
+        i = self.d.num_players
+        self.d.udim[i] = udim
+        self.d.state_regularization[i] = state_reg
+        self.d.control_regularization[i] = control_reg
+        self.d.cost_structure[i] = structure
+        self.d.num_players += 1
+        self._records.append([[], [], [], []])
+        return i
+
+    def add_subsystem(self, kind: int, xdim: int, first_player: int, params: Sequence[float] = ()):
+        s = self.d.subsystems[self.d.num_subsystems]
+        s.kind = kind
+        s.x_offset = self.d.xdim
+        s.first_player = first_player
+        for k, p in enumerate(params):
+            s.params[k] = p
+        self.d.xdim += xdim
+        self.d.num_subsystems += 1
+        return s.x_offset
+
+    # geometry ---------------------------------------------------------------
+    def add_polyline(self, points: Sequence[Tuple[float, float]]) -> int:
+        p = self.d.num_polylines
+        start = self.d.polyline_start[p]
+        assert len(points) >= 2 and start + len(points) <= abi.MAX_POLYLINE_POINTS
+        for k, (x, y) in enumerate(points):
+            self.d.polyline_points[start + k][0] = float(F(x))
+            self.d.polyline_points[start + k][1] = float(F(y))
+        self.d.polyline_start[p + 1] = start + len(points)
+        self.d.num_polylines += 1
+        return p
+
+    # costs ------------------------------------------------------------------
+    def _rec(self, player, category, kind, arg=-1, dims=(0,), weight=1.0, value=0.0, flag=0,
+             polyline=-1, is_equality=0):
+        r = abi.CostDesc()
+        r.kind, r.player, r.arg, r.is_equality = kind, player, arg, is_equality
+        for k in range(4):
+            r.dim[k] = dims[k] if k < len(dims) else 0
+        r.flag, r.polyline, r.weight, r.value = int(flag), polyline, weight, value
+        self._records[player][category].append(r)
+
+    def state_cost(self, player, kind, **kw):
+        self._rec(player, 0, kind, arg=-1, **kw)
+
+    def control_cost(self, player, control_of, kind, **kw):
+        self._rec(player, 1, kind, arg=control_of, **kw)
+
+    def state_constraint(self, player, kind, **kw):
+        self._rec(player, 2, kind, arg=-1, **kw)
+
+    def control_constraint(self, player, control_of, kind, **kw):
+        self._rec(player, 3, kind, arg=control_of, **kw)
+
+    def build(self) -> abi.ProblemDesc:
+        c = 0
+        for player_records in self._records:
+            for category in player_records:
+                for r in category:
+                    assert c < abi.MAX_COSTS
+                    self.d.costs[c] = r
+                    c += 1
+        self.d.num_costs = c
+        return self.d
+
+
+# --------------------------------------------------------------------------
+# ThreePlayerIntersectionExample, src/three_player_intersection_example.cpp
+# --------------------------------------------------------------------------
+def three_player_intersection(num_time_steps: int = 100, time_step: float = 0.1):
+    """Returns (desc, x0).  2x SinglePlayerCar6D + 1x SinglePlayerUnicycle4D, n = 16."""
+    b = DescBuilder(num_time_steps, time_step)
+    kInterAxleLength = 4.0
+    kStateReg, kControlReg = 1.0, 5.0
+    kOmegaCostWeight, kJerkCostWeight, kACostWeight = 0.1, 0.1, 0.1
+    kNominalVCostWeight, kLaneCostWeight, kMinProximity = 100.0, 25.0, 6.0
+    kP1NominalV, kP2NominalV, kP3NominalV = 8.0, 5.0, 1.5
+    kP1InitialX, kP2InitialX, kP3InitialX = -2.0, -10.0, -11.0
+    kP1InitialY, kP2InitialY, kP3InitialY = -30.0, 45.0, 16.0
+    kP1InitialHeading, kP2InitialHeading, kP3InitialHeading = math.pi / 2, -math.pi / 2, 0.0
+    kP1InitialSpeed, kP2InitialSpeed, kP3InitialSpeed = 4.0, 3.0, 1.25
+
+    for _ in range(3):  # :191-196
+        b.add_player(2, kStateReg, kControlReg)
+    o1 = b.add_subsystem(abi.DYN_CAR6D, 6, 0, [kInterAxleLength])  # :166-170
+    o2 = b.add_subsystem(abi.DYN_CAR6D, 6, 1, [kInterAxleLength])
+    o3 = b.add_subsystem(abi.DYN_UNICYCLE4D, 4, 2)
+    # index constants :133-163
+    kP1XIdx, kP1YIdx, kP1HeadingIdx, kP1VIdx = o1 + 0, o1 + 1, o1 + 2, o1 + 4
+    kP2XIdx, kP2YIdx, kP2HeadingIdx, kP2VIdx = o2 + 0, o2 + 1, o2 + 2, o2 + 4
+    kP3XIdx, kP3YIdx, kP3HeadingIdx, kP3VIdx = o3 + 0, o3 + 1, o3 + 2, o3 + 3
+
+    lane1 = b.add_polyline([(kP1InitialX, -1000.0), (kP1InitialX, 1000.0)])  # :201-209
+    lane2 = b.add_polyline([(kP2InitialX, 1000.0), (kP2InitialX, 18.0), (kP2InitialX + 0.5, 15.0),
+                            (kP2InitialX + 1.0, 14.0), (kP2InitialX + 3.0, 12.5),
+                            (kP2InitialX + 6.0, 12.0), (1000.0, 12.0)])
+    lane3 = b.add_polyline([(-1000.0, kP3InitialY), (1000.0, kP3InitialY)])
+
+    pos = [(kP1XIdx, kP1YIdx), (kP2XIdx, kP2YIdx), (kP3XIdx, kP3YIdx)]
+    vidx = [kP1VIdx, kP2VIdx, kP3VIdx]
+    nominal_v = [kP1NominalV, kP2NominalV, kP3NominalV]
+    lanes = [lane1, lane2, lane3]
+    for i in range(3):
+        b.state_cost(i, abi.COST_QUADRATIC_POLYLINE2, dims=pos[i], weight=kLaneCostWeight,
+                     polyline=lanes[i])  # :211-251
+        b.state_cost(i, abi.COST_QUADRATIC, dims=(vidx[i],), weight=kNominalVCostWeight,
+                     value=nominal_v[i])  # :254-287
+    # control costs :289-335 (P3's second control is acceleration)
+    b.control_cost(0, 0, abi.COST_QUADRATIC, dims=(0,), weight=kOmegaCostWeight, value=0.0)
+    b.control_cost(0, 0, abi.COST_QUADRATIC, dims=(1,), weight=kJerkCostWeight, value=0.0)
+    b.control_cost(1, 1, abi.COST_QUADRATIC, dims=(0,), weight=kOmegaCostWeight, value=0.0)
+    b.control_cost(1, 1, abi.COST_QUADRATIC, dims=(1,), weight=kJerkCostWeight, value=0.0)
+    b.control_cost(2, 2, abi.COST_QUADRATIC, dims=(0,), weight=kOmegaCostWeight, value=0.0)
+    b.control_cost(2, 2, abi.COST_QUADRATIC, dims=(1,), weight=kACostWeight, value=0.0)
+    # collision-avoidance constraints :363-394 (keep_within = !kKeepClose = false)
+    for i, others in ((0, (1, 2)), (1, (0, 2)), (2, (0, 1))):
+        for j in others:
+            b.state_constraint(i, abi.CONSTRAINT_PROXIMITY, dims=pos[i] + pos[j],
+                               value=kMinProximity, flag=0)
+
+    x0 = np.zeros(b.d.xdim, dtype=F)  # :172-185
+    x0[kP1XIdx], x0[kP1YIdx], x0[kP1HeadingIdx], x0[kP1VIdx] = (
+        kP1InitialX, kP1InitialY, kP1InitialHeading, kP1InitialSpeed)
+    x0[kP2XIdx], x0[kP2YIdx], x0[kP2HeadingIdx], x0[kP2VIdx] = (
+        kP2InitialX, kP2InitialY, kP2InitialHeading, kP2InitialSpeed)
+    x0[kP3XIdx], x0[kP3YIdx], x0[kP3HeadingIdx], x0[kP3VIdx] = (
+        kP3InitialX, kP3InitialY, kP3InitialHeading, kP3InitialSpeed)
+    return b.build(), x0
+
+
+def three_player_intersection_params(**overrides) -> abi.SolverParams:
+    """SolverParams as set by exec/three_player_intersection/main.cpp:109-120."""
+    base = dict(max_backtracking_steps=100, max_solver_iters=100,
+                unconstrained_solver_max_iters=10, linesearch=1,
+                expected_decrease_fraction=0.001, initial_alpha_scaling=0.1,
+                convergence_tolerance=1.0, geometric_mu_scaling=1.1,
+                geometric_mu_downscaling=0.5, geometric_lambda_downscaling=0.5)
+    base.update(overrides)
+    return abi.SolverParams.defaults(**base)
+
+
+def three_player_intersection_x0_batch(batch: int, seed: int) -> np.ndarray:
+    """SURVEY section 8d input #2: example x0 + positions U(-2,2) m, headings
+    U(-0.1,0.1) rad, speeds x U(0.8,1.2)."""
+    _, x0 = three_player_intersection()
+    rng = np.random.default_rng(seed)
+    out = np.tile(x0, (batch, 1)).astype(F)
+    pos = [0, 1, 6, 7, 12, 13]
+    head = [2, 8, 14]
+    spd = [4, 10, 15]
+    out[:, pos] += rng.uniform(-2.0, 2.0, size=(batch, len(pos))).astype(F)
+    out[:, head] += rng.uniform(-0.1, 0.1, size=(batch, len(head))).astype(F)
+    out[:, spd] *= rng.uniform(0.8, 1.2, size=(batch, len(spd))).astype(F)
+    return out
+
+
+# --------------------------------------------------------------------------
+# RoundaboutMergingExample
+# --------------------------------------------------------------------------
+def roundabout_lane_center(entrance_angle, exit_angle, distance_from_roundabout):
+    """RoundaboutLaneCenter, src/roundabout_lane_center.cpp:50-108 (fp32 arithmetic)."""
+    kR, kH = F(12.0), F(2.5)
+    ea, xa, dist = F(entrance_angle), F(exit_angle), F(distance_from_roundabout)
+    cos, sin = (lambda a: F(math.cos(float(a)))), (lambda a: F(math.sin(float(a))))
+    cx, cy = (kR + kH) * cos(ea), (kR + kH) * sin(ea)
+    first_angle = F(float(ea) - math.pi / 2)
+    fx, fy = cx + kH * cos(first_angle), cy + kH * sin(first_angle)
+    pts = [(fx + dist * cos(ea), fy + dist * sin(ea)), (fx, fy)]
+    for ii in range(1, 4):
+        ang = F(float(first_angle) - (math.pi / 2) * float(F(ii)) / 3)
+        pts.append((cx + kH * cos(ang), cy + kH * sin(ang)))
+    for ii in range(1, 11):
+        nxt = F(ea + (xa - ea) * F(ii) / F(10))
+        pts.append((kR * cos(nxt), kR * sin(nxt)))
+    pts.append((F(1e4) * cos(xa), F(1e4) * sin(xa)))
+    return [(float(x), float(y)) for x, y in pts]
+
+
+def roundabout_merging(num_time_steps: int = 100, time_step: float = 0.1):
+    """Returns (desc, x0).  4x SinglePlayerCar6D, n = 24, unconstrained."""
+    b = DescBuilder(num_time_steps, time_step)
+    kOmegaCostWeight, kACostWeight, kJerkCostWeight = 500.0, 50.0, 5.0
+    kMaxVCostWeight, kNominalVCostWeight = 1000.0, 10.0
+    kLaneCostWeight, kLaneBoundaryCostWeight = 25.0, 100.0
+    kMinProximity, kProximityCostWeight = 6.0, 100.0
+    kLaneHalfWidth, kMaxV, kMinV, kNominalV = 2.5, 12.0, 1.0, 10.0
+    dist = [25.0, 10.0, 25.0, 10.0]
+    speed = [3.0, 2.0, 3.0, 2.0]
+    kAngleOffset = F(math.pi / 2 * 0.5)  # static constexpr float
+    kWedgeSize = F(math.pi)
+    angles = [F(kAngleOffset), F(float(kAngleOffset) + 2.0 * math.pi / 4.0),
+              F(float(kAngleOffset) + 2.0 * 2.0 * math.pi / 4.0),
+              F(float(kAngleOffset) + 3.0 * 2.0 * math.pi / 4.0)]
+    offs = []
+    for i in range(4):
+        b.add_player(2, 0.0, 0.0)
+    for i in range(4):
+        offs.append(b.add_subsystem(abi.DYN_CAR6D, 6, i, [4.0]))
+    lanes, lane_pts = [], []
+    for i in range(4):
+        pts = roundabout_lane_center(angles[i], F(angles[i] + kWedgeSize), dist[i])
+        lane_pts.append(pts)
+        lanes.append(b.add_polyline(pts))
+    pos = [(o + 0, o + 1) for o in offs]
+    vidx = [o + 4 for o in offs]
+    kP1AIdx = offs[0] + 5
+    for i in range(4):
+        # lane costs :211-266
+        b.state_cost(i, abi.COST_QUADRATIC_POLYLINE2, dims=pos[i], weight=kLaneCostWeight,
+                     polyline=lanes[i])
+        b.state_cost(i, abi.COST_SEMIQUADRATIC_POLYLINE2, dims=pos[i],
+                     weight=kLaneBoundaryCostWeight, polyline=lanes[i], value=kLaneHalfWidth,
+                     flag=1)
+        b.state_cost(i, abi.COST_SEMIQUADRATIC_POLYLINE2, dims=pos[i],
+                     weight=kLaneBoundaryCostWeight, polyline=lanes[i], value=-kLaneHalfWidth,
+                     flag=0)
+    for i in range(4):
+        # speed costs :268-311
+        b.state_cost(i, abi.COST_SEMIQUADRATIC, dims=(vidx[i],), weight=kMaxVCostWeight,
+                     value=kMinV, flag=0)
+        b.state_cost(i, abi.COST_SEMIQUADRATIC, dims=(vidx[i],), weight=kMaxVCostWeight,
+                     value=kMaxV, flag=1)
+        b.state_cost(i, abi.COST_QUADRATIC, dims=(vidx[i],), weight=kNominalVCostWeight,
+                     value=kNominalV)
+    for i in range(4):
+        # acceleration cost: all four players index kP1AIdx (:342-353)
+        b.state_cost(i, abi.COST_QUADRATIC, dims=(kP1AIdx,), weight=kACostWeight, value=0.0)
+    for i in range(4):
+        b.control_cost(i, i, abi.COST_QUADRATIC, dims=(0,), weight=kOmegaCostWeight, value=0.0)
+        b.control_cost(i, i, abi.COST_QUADRATIC, dims=(1,), weight=kJerkCostWeight, value=0.0)
+    # proximity costs actually added (:385-434): p1:{p2,p4} p2:{p1,p3} p3:{p2,p4} p4:{p1,p3}
+    for i, others in ((0, (1, 3)), (1, (0, 2)), (2, (1, 3)), (3, (0, 2))):
+        for j in others:
+            b.state_cost(i, abi.COST_PROXIMITY, dims=pos[i] + pos[j],
+                         weight=kProximityCostWeight, value=kMinProximity)
+    # NB: the reference adds each player's state costs in source order lane(3), speed(3),
+    # accel(1), proximity(2); DescBuilder keeps per-player append order, which is that order.
+    x0 = np.zeros(b.d.xdim, dtype=F)  # :187-205
+    for i in range(4):
+        (ax, ay), (bx, by) = lane_pts[i][0], lane_pts[i][1]
+        x0[offs[i] + 0] = ax
+        x0[offs[i] + 1] = ay
+        x0[offs[i] + 2] = math.atan2(F(by) - F(ay), F(bx) - F(ax))  # LineSegment2::Heading
+        x0[offs[i] + 4] = speed[i]
+    return b.build(), x0
+
+
+def roundabout_x0_batch(batch: int, seed: int) -> np.ndarray:
+    """SURVEY section 8d input #3: each car U(0,10) m back along its first lane segment,
+    speed U(1,4)."""
+    desc, x0 = roundabout_merging()
+    rng = np.random.default_rng(seed)
+    out = np.tile(x0, (batch, 1)).astype(F)
+    back = rng.uniform(0.0, 10.0, size=(batch, 4)).astype(F)
+    spd = rng.uniform(1.0, 4.0, size=(batch, 4)).astype(F)
+    for i in range(4):
+        th = out[:, 6 * i + 2]
+        out[:, 6 * i + 0] -= back[:, i] * np.cos(th)
+        out[:, 6 * i + 1] -= back[:, i] * np.sin(th)
+        out[:, 6 * i + 4] = spd[:, i]
+    return out
+
+
+def roundabout_params(**overrides) -> abi.SolverParams:
+    """SolverParams of exec/roundabout_merging_example/main.cpp:72-75,108-113."""
+    base = dict(max_backtracking_steps=100, linesearch=1, expected_decrease_fraction=0.1,
+                initial_alpha_scaling=0.75, convergence_tolerance=0.01)
+    base.update(overrides)
+    return abi.SolverParams.defaults(**base)
+
+
+# --------------------------------------------------------------------------
+# Air3DExample
+# --------------------------------------------------------------------------
+def draw_circle(center, radius, num_segments):
+    """DrawCircle, src/draw_shapes.cpp:62-73."""
+    pts = [(center[0] + radius, center[1] + 0.0)]
+    for ii in range(num_segments):
+        angle = F(2.0 * math.pi * float(F(ii + 1)) / float(F(num_segments)))
+        pts.append((float(F(center[0]) + F(radius) * F(math.cos(float(angle)))),
+                    float(F(center[1]) + F(radius) * F(math.sin(float(angle))))))
+    return pts
+
+
+def air_3d(num_time_steps: int = 100, time_step: float = 0.1, rx0=4.0, ry0=3.0,
+           rtheta0=math.pi / 4.0, ve=1.0, vp=1.0):
+    """Returns (desc, x0). Two-player zero-sum-like pursuit-evasion, n = 3, m = (1,1)."""
+    b = DescBuilder(num_time_steps, time_step)
+    kOmegaCostWeight, kOmegaMax, kTargetRadius = 0.1, 1.0, 5.0
+    b.add_player(1, 0.0, 0.0, abi.COST_MAX)  # p1_cost.SetMaxOverTime() :139
+    b.add_player(1, 0.0, 0.0, abi.COST_MIN)  # p2_cost.SetMinOverTime() :140
+    b.add_subsystem(abi.DYN_AIR3D, 3, 0, [ve, vp])
+    circle = b.add_polyline(draw_circle((0.0, 0.0), kTargetRadius, 10))
+    # Polyline2SignedDistanceCost(circle, {rx,ry}, !kReach, "Target"): the bool lands in
+    # `float nominal` and the string literal in `bool oriented_same_as_polyline`:
+    # nominal = 0.0 (P1) / 1.0 (P2), oriented = true for both.
+    b.state_cost(0, abi.COST_POLYLINE2_SIGNED_DISTANCE, dims=(0, 1), polyline=circle, value=0.0,
+                 flag=1)
+    b.state_cost(1, abi.COST_POLYLINE2_SIGNED_DISTANCE, dims=(0, 1), polyline=circle, value=1.0,
+                 flag=1)
+    b.control_cost(0, 0, abi.COST_QUADRATIC, dims=(-1,), weight=kOmegaCostWeight, value=0.0)
+    b.control_cost(1, 1, abi.COST_QUADRATIC, dims=(-1,), weight=kOmegaCostWeight, value=0.0)
+    b.control_constraint(0, 0, abi.CONSTRAINT_SINGLE_DIMENSION, dims=(0,), value=kOmegaMax, flag=1)
+    b.control_constraint(0, 0, abi.CONSTRAINT_SINGLE_DIMENSION, dims=(0,), value=-kOmegaMax, flag=0)
+    b.control_constraint(1, 1, abi.CONSTRAINT_SINGLE_DIMENSION, dims=(0,), value=kOmegaMax, flag=1)
+    b.control_constraint(1, 1, abi.CONSTRAINT_SINGLE_DIMENSION, dims=(0,), value=-kOmegaMax, flag=0)
+    x0 = np.array([rx0, ry0, rtheta0], dtype=F)
+    return b.build(), x0
+
+
+def air_3d_params(**overrides) -> abi.SolverParams:
+    """SolverParams of exec/air_3d_example/main.cpp:75-78,111-118 (its two
+    regularization fields are dead)."""
+    base = dict(max_backtracking_steps=100, linesearch=1, expected_decrease_fraction=0.1,
+                initial_alpha_scaling=0.1, convergence_tolerance=0.01)
+    base.update(overrides)
+    return abi.SolverParams.defaults(**base)
+
+
+def air_3d_x0_grid(side: int = 128) -> np.ndarray:
+    """SURVEY section 8d input #4: side x side grid r_x,r_y in [-6,6], r_theta = pi/4."""
+    g = np.linspace(-6.0, 6.0, side, dtype=F)
+    rx, ry = np.meshgrid(g, g, indexing="ij")
+    out = np.stack([rx.ravel(), ry.ravel(), np.full(side * side, math.pi / 4.0, dtype=F)], axis=1)
+    r = np.hypot(out[:, 0], out[:, 1])
+    out[r < 0.5, 0] += 1.0  # exclude the origin neighbourhood
+    return out.astype(F)
+
+
+# --------------------------------------------------------------------------
+# LQ-only handle: the system of test/test_lq_solver.cpp
+# --------------------------------------------------------------------------
+def lq_only(num_time_steps: int, xdim: int, udims: Sequence[int],
+            cross_pairs: Sequence[Tuple[int, int]] = ()):
+    """Descriptor with no dynamics/costs: lin/quad are supplied with upload_lq.
+    cross_pairs lists extra (i, j) control blocks R_ij, i != j."""
+    b = DescBuilder(num_time_steps, 0.1)
+    for m in udims:
+        b.add_player(m)
+    b.d.xdim = xdim
+    for (i, j) in cross_pairs:
+        # a zero-weight control cost only declares that the (i,j) block exists
+        b.control_cost(i, j, abi.COST_QUADRATIC, dims=(-1,), weight=0.0, value=0.0)
+    return b.build()

@@ -1,0 +1,317 @@
+/*
+ * ilqg.h -- C ABI of the B200-native batched iLQ-games inner solver.
+ *
+ * This is the drop-in boundary for ONE hot path of HJReachability/ilqgames:
+ *   forward rollout -> per-timestep linearization -> per-timestep/per-player
+ *   quadraticization -> coupled backward Riccati Nash recursion (+ the Armijo
+ *   linesearch glue that decides how often the first two run).
+ *
+ * The reference has no FFI of its own: its boundary is
+ * the C++ virtual-class API.  Every entry point below therefore cites the
+ * reference member function whose body it replaces; the re-authored host
+ * classes (ILQSolver, LQFeedbackSolver, AugmentedLagrangianSolver) call these
+ * and nothing else.  All arguments are PODs / plain pointers + sizes; no torch,
+ * Eigen or C++ types cross this boundary; nothing throws or aborts across it.
+ *
+ * Two shared libraries implement this same header:
+ *   ilqgames_b200/lib/libilqg_b200.so   the product: sm_100a CUDA kernels
+ *   oracle/_build/libilqg_oracle.so     TEST INFRASTRUCTURE ONLY: the CPU
+ *                                       restatement of the reference algorithm
+ * (same symbols, loaded RTLD_LOCAL side by side by the parity tests).
+ *
+ * Host array layouts (all row-major, batch outermost, fp32 unless noted):
+ *   x0      [B][n]
+ *   xs      [B][T][n]             us     [B][T][M]   (M = sum of m_i, players
+ *                                                     concatenated in order)
+ *   Ps      [B][T][M][n]          alphas [B][T][M]   (rows of player i start at
+ *                                                     u-offset of player i)
+ *   A       [B][T][n][n]          Bs     [B][T][n][M]
+ *   Q       [B][T][N][n][n]       l      [B][T][N][n]
+ *   R       [B][T][rdim]          r      [B][T][udim_pairs]
+ *           (control-cost pairs (i,j) sorted by (i,j); pair p holds an
+ *            m_j x m_j row-major block at layout.pair_R_offset[p] and an m_j
+ *            vector at layout.pair_r_offset[p])
+ *   lambdas [B][num_constraints][T]      mu [B]
+ */
+#ifndef ILQG_H
+#define ILQG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------- limits --------------------------------- */
+#define ILQG_MAX_PLAYERS 4
+#define ILQG_MAX_SUBSYSTEMS 4
+#define ILQG_MAX_COSTS 64
+#define ILQG_MAX_POLYLINES 8
+#define ILQG_MAX_POLYLINE_POINTS 128
+#define ILQG_MAX_PAIRS 16 /* ILQG_MAX_PLAYERS^2 */
+#define ILQG_MAX_XDIM 24
+#define ILQG_MAX_UDIM 8   /* total control dimension M */
+#define ILQG_MAX_TIME_STEPS 512
+
+/* ------------------------------ error codes ----------------------------- */
+enum {
+  ILQG_OK = 0,
+  ILQG_ERR_INVALID_ARGUMENT = -1,
+  ILQG_ERR_UNSUPPORTED = -2,      /* descriptor outside the compiled envelope */
+  ILQG_ERR_CUDA = -3,             /* a CUDA runtime call failed               */
+  ILQG_ERR_NO_DEVICE = -4,        /* no sm_100 device / driver                */
+  ILQG_ERR_OUT_OF_MEMORY = -5,
+  ILQG_ERR_BAD_HANDLE = -6,
+  ILQG_ERR_SIZE_MISMATCH = -7     /* host buffer byte count is wrong          */
+};
+
+/* ----------------------------- descriptors ------------------------------ */
+
+/* Subsystem kinds.  Reference: include/ilqgames/dynamics/
+ *   single_player_car_6d.h:102-138, single_player_unicycle_4d.h:90-116,
+ *   air_3d.h:114-149. */
+enum {
+  ILQG_DYN_NONE = 0,       /* LQ-only handle: lin/quad come from ilqg_upload_lq */
+  ILQG_DYN_CAR6D = 1,      /* params[0] = inter-axle distance                  */
+  ILQG_DYN_UNICYCLE4D = 2,
+  ILQG_DYN_AIR3D = 3       /* params[0] = evader speed, params[1] = pursuer    */
+};
+
+typedef struct {
+  int32_t kind;
+  int32_t x_offset;      /* first state index of this subsystem             */
+  int32_t first_player;  /* index of the player owning its first control    */
+  int32_t reserved;
+  float params[4];
+} ilqg_subsystem_desc;
+
+/* Cost / constraint record kinds.  Reference: src/quadratic_cost.cpp:51-94,
+ * src/quadratic_polyline2_cost.cpp:52-126, src/proximity_cost.cpp:52-122,
+ * src/semiquadratic_cost.cpp:51-85, src/semiquadratic_polyline2_cost.cpp:52-142,
+ * src/polyline2_signed_distance_cost.cpp:52-121,
+ * src/proximity_constraint.cpp:56-116,
+ * include/ilqgames/constraint/single_dimension_constraint.h:68-96. */
+enum {
+  ILQG_COST_QUADRATIC = 1,                /* dim[0] (or -1 = all dims), weight, value=nominal */
+  ILQG_COST_QUADRATIC_POLYLINE2 = 2,      /* dim[0..1]=x,y idx, polyline, weight              */
+  ILQG_COST_PROXIMITY = 3,                /* dim[0..3]=x1,y1,x2,y2, weight, value=threshold   */
+  ILQG_COST_SEMIQUADRATIC = 4,            /* dim[0], weight, value=threshold, flag=oriented_right */
+  ILQG_COST_SEMIQUADRATIC_POLYLINE2 = 5,  /* dim[0..1], polyline, weight, value=threshold, flag=oriented_right */
+  ILQG_COST_POLYLINE2_SIGNED_DISTANCE = 6,/* dim[0..1], polyline, value=nominal, flag=oriented_same_as_polyline */
+  ILQG_CONSTRAINT_PROXIMITY = 7,          /* dim[0..3], value=threshold, flag=keep_within      */
+  ILQG_CONSTRAINT_SINGLE_DIMENSION = 8    /* dim[0], value=threshold, flag=keep_below          */
+};
+
+typedef struct {
+  int32_t kind;
+  int32_t player;      /* owner i: the PlayerCost this record was added to      */
+  int32_t arg;         /* -1: function of the state; j >= 0: of player j's control */
+  int32_t is_equality; /* constraints only (Constraint::is_equality_)          */
+  int32_t dim[4];
+  int32_t flag;
+  int32_t polyline;    /* index into the polyline table, or -1                  */
+  float weight;
+  float value;
+} ilqg_cost_desc;
+
+/* PlayerCost::CostStructure, include/ilqgames/cost/player_cost.h:105-111 */
+enum { ILQG_COST_SUM = 0, ILQG_COST_MAX = 1, ILQG_COST_MIN = 2 };
+
+typedef struct {
+  /* horizon: time::kNumTimeSteps / kTimeStep made run-time parameters
+   * (include/ilqgames/utils/types.h:133-143). */
+  int32_t num_time_steps;
+  int32_t num_players;
+  int32_t xdim;
+  int32_t udim[ILQG_MAX_PLAYERS];
+  double time_step;    /* Time is double on Linux (types.h:85)                   */
+  double initial_time; /* RelativeTimeTracker::initial_time_                    */
+
+  int32_t num_subsystems;
+  ilqg_subsystem_desc subsystems[ILQG_MAX_SUBSYSTEMS];
+
+  /* per player: PlayerCost(name, state_regularization, control_regularization)
+   * and its SUM/MAX/MIN structure (player_cost.h:63-70,105-111). */
+  float state_regularization[ILQG_MAX_PLAYERS];
+  float control_regularization[ILQG_MAX_PLAYERS];
+  int32_t cost_structure[ILQG_MAX_PLAYERS];
+
+  /* Cost records in the reference's accumulation order per player
+   * (src/player_cost.cpp:194-215): state costs, control costs, state
+   * constraints, control constraints. */
+  int32_t num_costs;
+  ilqg_cost_desc costs[ILQG_MAX_COSTS];
+
+  /* Polyline table: polyline p owns points[polyline_start[p] .. polyline_start[p+1]). */
+  int32_t num_polylines;
+  int32_t polyline_start[ILQG_MAX_POLYLINES + 1];
+  float polyline_points[ILQG_MAX_POLYLINE_POINTS][2];
+} ilqg_problem_desc;
+
+/* SolverParams, include/ilqgames/solver/solver_params.h:50-84 (the two dead
+ * regularization fields are omitted). */
+typedef struct {
+  float convergence_tolerance;
+  int32_t max_solver_iters;
+  int32_t linesearch;
+  float initial_alpha_scaling;
+  float geometric_alpha_scaling;
+  int32_t max_backtracking_steps;
+  float expected_decrease_fraction;
+  int32_t open_loop; /* must be 0: LQOpenLoopSolver is not on this path */
+  /* augmented Lagrangian outer loop */
+  int32_t unconstrained_solver_max_iters;
+  float geometric_mu_scaling;
+  float geometric_mu_downscaling;
+  float geometric_lambda_downscaling;
+  float constraint_error_tolerance;
+  /* additive (not in the reference): LQFeedbackSolver ctor's
+   * adaptive_regularization (lq_feedback_solver.h:73-75) and a benchmark switch
+   * that disables the HasConverged() exit so every instance runs max iters. */
+  int32_t adaptive_regularization;
+  int32_t disable_convergence_exit;
+} ilqg_solver_params;
+
+/* Shape / offset report so callers can size host buffers. */
+typedef struct {
+  int32_t batch, num_time_steps, num_players, xdim, total_udim;
+  int32_t udim[ILQG_MAX_PLAYERS];
+  int32_t u_offset[ILQG_MAX_PLAYERS];
+  int32_t num_pairs;                    /* control-cost pairs (i,j)          */
+  int32_t pair_player[ILQG_MAX_PAIRS];  /* i                                 */
+  int32_t pair_arg[ILQG_MAX_PAIRS];     /* j                                 */
+  int32_t pair_R_offset[ILQG_MAX_PAIRS];
+  int32_t pair_r_offset[ILQG_MAX_PAIRS];
+  int32_t R_floats;                     /* per (b,k): sum m_j^2 over pairs   */
+  int32_t r_floats;                     /* per (b,k): sum m_j  over pairs    */
+  int32_t num_constraints;
+  int32_t record_floats;                /* device LQ record size per (b,k)   */
+  int32_t lambda_index[ILQG_MAX_TIME_STEPS]; /* kk -> Constraint::TimeIndex */
+} ilqg_layout;
+
+/* Per-instance status word (replaces `has_converged` / `*success`,
+ * src/ilq_solver.cpp:95-96,146-155,168-171). */
+enum {
+  ILQG_STATUS_IDLE = 0,
+  ILQG_STATUS_RUNNING = 1,
+  ILQG_STATUS_CONVERGED = 2,         /* HasConverged() fired                    */
+  ILQG_STATUS_MAX_ITERS = 3,         /* hit max_solver_iters (success = true)   */
+  ILQG_STATUS_LINESEARCH_FAILED = 4, /* ModifyLQStrategies returned false       */
+  ILQG_STATUS_NONFINITE = 5
+};
+
+/* what to download / upload */
+enum {
+  ILQG_XS = 1, ILQG_US = 2, ILQG_PS = 3, ILQG_ALPHAS = 4,
+  ILQG_LIN_A = 5, ILQG_LIN_B = 6,
+  ILQG_QUAD_Q = 7, ILQG_QUAD_L = 8, ILQG_QUAD_R = 9, ILQG_QUAD_RGRAD = 10,
+  ILQG_DELTA_XS = 11,
+  ILQG_STATUS = 12,            /* int32 [B]                                   */
+  ILQG_ITERS = 13,             /* int32 [B] completed while-loop iterations   */
+  ILQG_MERIT = 14,             /* float [B] last_merit_function_value_        */
+  ILQG_TOTAL_COSTS = 15,       /* float [B][N]                                */
+  ILQG_LAMBDAS = 16, ILQG_MU = 17,
+  ILQG_EXPECTED_DECREASE = 18, /* float [B]                                   */
+  ILQG_STEP = 19,              /* float [B] accepted step size                */
+  ILQG_BACKTRACKS = 20,        /* int32 [B] cumulative rollouts in linesearch */
+  ILQG_TIME_OF_EXTREME = 21,   /* int32 [B][N]                                */
+  ILQG_X0 = 22,
+  ILQG_LQ_PS = 23, ILQG_LQ_ALPHAS = 24, /* raw LQ solution (before linesearch scaling) */
+  ILQG_MAX_CONSTRAINT_ERROR = 25 /* float [B], from ilqg_al_update            */
+};
+
+typedef struct ilqg_solver* ilqg_handle;
+
+/* ------------------------------ entry points ---------------------------- */
+
+/* Build the per-device slab for `batch` independent games described by `desc`.
+ * Replaces ILQSolver::ILQSolver (include/ilqgames/solver/ilq_solver.h:69-94)
+ * + LQFeedbackSolver::LQFeedbackSolver (lq_feedback_solver.h:73-115) +
+ * Problem::Initialize (solver/problem.h:66-73): zero operating point, zero
+ * strategies, lambda = 0, mu = 10, last merit = +inf.  `device` is the CUDA
+ * ordinal (ignored by the oracle). */
+int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
+                int batch, int device, ilqg_handle* out);
+int ilqg_destroy(ilqg_handle h);
+const char* ilqg_strerror(int code);
+/* sizeof() of the ABI structs as compiled (0: ilqg_problem_desc, 1:
+ * ilqg_solver_params, 2: ilqg_layout, 3: ilqg_cost_desc, 4: ilqg_subsystem_desc)
+ * so foreign-language bindings can verify their mirror of this header. */
+size_t ilqg_abi_struct_size(int which);
+int ilqg_get_layout(ilqg_handle h, ilqg_layout* out);
+
+/* Problem::ResetInitialState (problem.h:82-85), one x0 per instance. */
+int ilqg_upload_x0(ilqg_handle h, const float* x0, size_t bytes);
+
+/* Problem::OverwriteSolution (src/problem.cpp:188-194) from host arrays: sets
+ * the warm start every ilqg_solve_begin starts from (and the working iterate).
+ * Any pointer may be NULL (= zeros). */
+int ilqg_upload_warmstart(ilqg_handle h, const float* xs, const float* us,
+                          const float* Ps, const float* alphas);
+
+/* Generic upload of one per-instance array (ILQG_LAMBDAS, ILQG_MU, ILQG_MERIT,
+ * ILQG_TIME_OF_EXTREME ...): the reference's mutable statics made per-instance
+ * (Constraint::mu_ src/constraint.cpp:61, Constraint::lambdas_ constraint.h:138,
+ * ILQSolver::last_merit_function_value_ ilq_solver.h:189). */
+int ilqg_upload(ilqg_handle h, int what, const void* src, size_t bytes);
+
+/* Host-supplied LQ game: the arguments of LQFeedbackSolver::Solve
+ * (lq_feedback_solver.h:119-124).  Layouts as in the header comment. */
+int ilqg_upload_lq(ilqg_handle h, const float* A, const float* Bs,
+                   const float* Q, const float* l, const float* R,
+                   const float* r);
+
+/* ILQSolver::Solve prologue, src/ilq_solver.cpp:86-107: xs[0] <- x0, rollout
+ * under the current strategies (ILQSolver::CurrentOperatingPoint :174-206 with
+ * MultiPlayerDynamicalSystem::Integrate src/multi_player_dynamical_system.cpp:52-77),
+ * TotalCosts (:220-257); marks every instance RUNNING, iteration count 0. */
+int ilqg_solve_begin(ilqg_handle h);
+
+/* ILQSolver::ComputeLinearization (:437-455) + ComputeCostQuadraticization
+ * (:471-490) at the current operating point, fused; fills the LQ records. */
+int ilqg_linearize_quadraticize(ilqg_handle h);
+
+/* LQFeedbackSolver::Solve (src/lq_feedback_solver.cpp:71-244) on the current
+ * LQ records with x0 argument = 0 (x0 - xs[0], ilq_solver.cpp:140-143), plus
+ * ILQSolver::ExpectedDecrease (:364-398).  Result: ILQG_LQ_PS/ILQG_LQ_ALPHAS,
+ * ILQG_DELTA_XS, ILQG_EXPECTED_DECREASE. */
+int ilqg_lq_backward(ilqg_handle h);
+
+/* ILQSolver::ModifyLQStrategies (:289-348: alpha scaling, rollouts,
+ * MeritFunction :400-435, Armijo :350-362, HasConverged ilq_solver.h:126-130)
+ * followed by TotalCosts (:158).  Per instance. */
+int ilqg_linesearch(ilqg_handle h);
+
+/* Up to max_iters passes of the while loop src/ilq_solver.cpp:123-166 for every
+ * RUNNING instance (linearize_quadraticize, lq_backward, linesearch), entirely
+ * device-side.  iters_done (nullable; forces a sync) receives the largest
+ * per-instance iteration count. */
+int ilqg_iterate(ilqg_handle h, int max_iters, int* iters_done);
+
+/* One augmented-Lagrangian outer update, src/augmented_lagrangian_solver.cpp:
+ * 113-178: lambda <- max(0, lambda + mu g) with the TimeIndex quirk, mu scaling,
+ * per-instance failure down-scaling. max constraint error -> ILQG_MAX_CONSTRAINT_ERROR. */
+int ilqg_al_update(ilqg_handle h);
+
+/* Problem::OverwriteSolution(log->FinalOperatingPoint(), log->FinalStrategies())
+ * (src/problem.cpp:188-194, called at augmented_lagrangian_solver.cpp:151-154):
+ * the working iterate becomes the warm start of the next ilqg_solve_begin.
+ * only_successful != 0 skips instances whose last solve failed its linesearch. */
+int ilqg_overwrite_solution(ilqg_handle h, int only_successful);
+
+/* src/augmented_lagrangian_solver.cpp:165-178: for instances whose inner solve
+ * failed, lambda *= geometric_lambda_downscaling, mu *= geometric_mu_downscaling. */
+int ilqg_al_post_solve(ilqg_handle h);
+
+int ilqg_download(ilqg_handle h, int what, void* dst, size_t bytes);
+int ilqg_synchronize(ilqg_handle h);
+
+/* Launch accounting for bench.py ("gpu_launches"): number of kernels this
+ * handle has launched since creation (0 for the oracle). */
+int ilqg_kernel_launches(ilqg_handle h, long long* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ILQG_H */

@@ -1,0 +1,1707 @@
+// ===========================================================================
+// ilqg_oracle.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// CPU restatement of the reference algorithm (HJReachability/ilqgames) for the
+// one hot path this repository accelerates.  Only tests/, bench.py's
+// cpu_baseline / --impl reference legs and __graft_entry__.smoke() may load the
+// library built from this file; the product (ilqgames_b200/) never does.
+//
+// Parity pinning: the reference C++ cannot be built in this environment (no
+// Eigen3 / glog / gflags), so this restatement is pinned
+// against the reference's own tests instead, transcribed with file:line
+// citations in tests/test_oracle_pins.py:
+//   * geometry golden values     test/test_polyline2.cpp:52-125,
+//                                test/test_line_segment2.cpp:57-102
+//   * LQ solve known answer      test/test_lq_solver.cpp:292-317 (Lyapunov, 1e-4)
+//   * analytic derivatives vs finite differences
+//                                test/test_quadraticization.cpp:138-201,
+//                                test/test_linearization.cpp:142-196
+//   * player cost known answers  test/test_player_cost.cpp:84-122
+// The reference holds NO test of ILQSolver iterates / linesearch / AL loop, so
+// for those rows parity is pinned only by this restatement ("parity unpinned by
+// reference tests" -- see DESIGN.md).
+//
+// Every function cites the reference file:line it follows.  Scalars are `real`
+// (float by default = the reference's MatrixXf/VectorXf; build with
+// -DILQG_ORACLE_DOUBLE for an fp64 accuracy yardstick).  Expressions keep the
+// reference's literal types (double literals, float variables) so the C++
+// usual arithmetic conversions reproduce its mixed precision.
+// ===========================================================================
+#include "../include/ilqg.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#ifdef ILQG_ORACLE_DOUBLE
+typedef double real;
+#else
+typedef float real;
+#endif
+
+namespace {
+
+// include/ilqgames/utils/types.h:113-126
+constexpr float kSmallNumber = 1e-4;
+constexpr real kInfinity = std::numeric_limits<real>::infinity();
+constexpr float kDefaultMu = 10.0;
+
+// include/ilqgames/utils/types.h:152-165 (sgn)
+template <typename T>
+inline T sgn(T x) {
+  return (T(0) < x) - (x < T(0));
+}
+
+// ----------------------------- geometry ------------------------------------
+struct Point2 {
+  real x, y;
+};
+
+// include/ilqgames/geometry/line_segment2.h:52-62
+struct Segment {
+  Point2 p1, p2;
+  real length;
+  Point2 unit;
+};
+
+Segment MakeSegment(Point2 a, Point2 b) {
+  Segment s;
+  s.p1 = a;
+  s.p2 = b;
+  const real dx = a.x - b.x, dy = a.y - b.y;
+  s.length = std::sqrt(dx * dx + dy * dy);
+  s.unit.x = (b.x - a.x) / s.length;
+  s.unit.y = (b.y - a.y) / s.length;
+  return s;
+}
+
+// src/line_segment2.cpp:48-54
+bool SegmentSide(const Segment& s, Point2 q) {
+  const real rx = q.x - s.p1.x, ry = q.y - s.p1.y;
+  const real cross = rx * s.unit.y - s.unit.x * ry;
+  return cross > 0.0;
+}
+
+// src/line_segment2.cpp:56-100
+Point2 SegmentClosestPoint(const Segment& s, Point2 q, bool* is_endpoint,
+                           real* signed_sq) {
+  const real rx = q.x - s.p1.x, ry = q.y - s.p1.y;
+  const real dot = rx * s.unit.x + ry * s.unit.y;
+  const real cross = rx * s.unit.y - s.unit.x * ry;
+  const real cross_sign = sgn(cross);
+  if (dot < 0.0) {
+    *is_endpoint = true;
+    *signed_sq = cross_sign * (rx * rx + ry * ry);
+    return s.p1;
+  } else if (dot > s.length) {
+    *is_endpoint = true;
+    const real ex = q.x - s.p2.x, ey = q.y - s.p2.y;
+    *signed_sq = cross_sign * (ex * ex + ey * ey);
+    return s.p2;
+  }
+  *is_endpoint = false;
+  *signed_sq = cross_sign * cross * cross;
+  Point2 p;
+  p.x = s.p1.x + dot * s.unit.x;
+  p.y = s.p1.y + dot * s.unit.y;
+  return p;
+}
+
+struct Polyline {
+  std::vector<Segment> segs;  // src/polyline2.cpp:49-60
+};
+
+inline bool SamePointExact(Point2 a, Point2 b) { return a.x == b.x && a.y == b.y; }
+
+// src/polyline2.cpp:105-174
+Point2 PolylineClosestPoint(const Polyline& pl, Point2 q, bool* is_vertex,
+                            int* segment_idx_out, real* signed_sq_out,
+                            bool* is_endpoint) {
+  real closest_sq = kInfinity;
+  Point2 closest = {0, 0};
+  int segment_idx = 0;
+  bool vertex = false;
+  const int ns = (int)pl.segs.size();
+  for (int c = 0; c < ns; c++) {
+    const Segment& s = pl.segs[c];
+    bool seg_endpoint;
+    real cur_sq;
+    const Point2 cur = SegmentClosestPoint(s, q, &seg_endpoint, &cur_sq);
+    if (std::abs(cur_sq) < std::abs(closest_sq)) {
+      if (seg_endpoint && (c > 0 || SamePointExact(cur, s.p2)) &&
+          (c < ns - 1 || SamePointExact(cur, s.p1))) {
+        const Segment shortcut =
+            SamePointExact(cur, s.p1)
+                ? MakeSegment(pl.segs[c - 1].p1, s.p2)
+                : MakeSegment(s.p1, pl.segs[c + 1].p2);
+        cur_sq *= SegmentSide(shortcut, q) ? sgn(cur_sq) : -sgn(cur_sq);
+      }
+      closest_sq = cur_sq;
+      closest = cur;
+      vertex = seg_endpoint;
+      segment_idx = c;
+    }
+  }
+  if (is_vertex) *is_vertex = vertex;
+  if (segment_idx_out) *segment_idx_out = segment_idx;
+  if (signed_sq_out) *signed_sq_out = closest_sq;
+  if (is_endpoint) {
+    auto same = [](Point2 a, Point2 b) {
+      const real dx = a.x - b.x, dy = a.y - b.y;
+      return dx * dx + dy * dy < kSmallNumber;
+    };
+    *is_endpoint = same(closest, pl.segs.front().p1) || same(closest, pl.segs.back().p2);
+  }
+  return closest;
+}
+
+// ------------------------------ problem ------------------------------------
+struct Problem {
+  ilqg_problem_desc d;
+  ilqg_solver_params p;
+  int T, N, n, M;
+  int uoff[ILQG_MAX_PLAYERS + 1];
+  std::vector<Polyline> polylines;
+  // control-cost pairs (i,j) sorted by (i,j)
+  int num_pairs;
+  int pair_i[ILQG_MAX_PAIRS], pair_j[ILQG_MAX_PAIRS];
+  int pair_Roff[ILQG_MAX_PAIRS], pair_roff[ILQG_MAX_PAIRS];
+  int pair_of[ILQG_MAX_PLAYERS][ILQG_MAX_PLAYERS];
+  int R_floats, r_floats;
+  int num_constraints;
+  int constraint_slot[ILQG_MAX_COSTS];  // cost record -> lambda slot or -1
+  std::vector<int> lambda_index;         // kk -> TimeIndex
+};
+
+inline bool IsConstraintKind(int kind) {
+  return kind == ILQG_CONSTRAINT_PROXIMITY || kind == ILQG_CONSTRAINT_SINGLE_DIMENSION;
+}
+
+int BuildProblem(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
+                 Problem* pr) {
+  pr->d = *desc;
+  pr->p = *params;
+  const ilqg_problem_desc& d = pr->d;
+  if (d.num_time_steps < 2 || d.num_time_steps > ILQG_MAX_TIME_STEPS)
+    return ILQG_ERR_INVALID_ARGUMENT;
+  if (d.num_players < 1 || d.num_players > ILQG_MAX_PLAYERS) return ILQG_ERR_INVALID_ARGUMENT;
+  if (d.xdim < 1 || d.xdim > ILQG_MAX_XDIM) return ILQG_ERR_INVALID_ARGUMENT;
+  if (d.num_costs < 0 || d.num_costs > ILQG_MAX_COSTS) return ILQG_ERR_INVALID_ARGUMENT;
+  if (params->open_loop) return ILQG_ERR_UNSUPPORTED;
+  pr->T = d.num_time_steps;
+  pr->N = d.num_players;
+  pr->n = d.xdim;
+  pr->uoff[0] = 0;
+  for (int i = 0; i < pr->N; i++) {
+    if (d.udim[i] < 1) return ILQG_ERR_INVALID_ARGUMENT;
+    pr->uoff[i + 1] = pr->uoff[i] + d.udim[i];
+  }
+  pr->M = pr->uoff[pr->N];
+  if (pr->M > ILQG_MAX_UDIM) return ILQG_ERR_INVALID_ARGUMENT;
+
+  // polylines: src/polyline2.cpp:49-60
+  pr->polylines.clear();
+  for (int p = 0; p < d.num_polylines; p++) {
+    Polyline pl;
+    for (int q = d.polyline_start[p] + 1; q < d.polyline_start[p + 1]; q++) {
+      Point2 a = {(real)d.polyline_points[q - 1][0], (real)d.polyline_points[q - 1][1]};
+      Point2 b = {(real)d.polyline_points[q][0], (real)d.polyline_points[q][1]};
+      pl.segs.push_back(MakeSegment(a, b));
+    }
+    if (pl.segs.empty()) return ILQG_ERR_INVALID_ARGUMENT;
+    pr->polylines.push_back(pl);
+  }
+
+  // Control pairs: player i always owns an (i,i) block -- LQFeedbackSolver
+  // CHECKs it exists (src/lq_feedback_solver.cpp:139-141) -- plus any (i,j) a
+  // control cost / constraint names (src/player_cost.cpp:59-86).
+  bool has[ILQG_MAX_PLAYERS][ILQG_MAX_PLAYERS] = {};
+  for (int i = 0; i < pr->N; i++) has[i][i] = true;
+  for (int c = 0; c < d.num_costs; c++) {
+    const ilqg_cost_desc& cd = d.costs[c];
+    if (cd.player < 0 || cd.player >= pr->N || cd.arg >= pr->N) return ILQG_ERR_INVALID_ARGUMENT;
+    if (cd.arg >= 0) has[cd.player][cd.arg] = true;
+  }
+  pr->num_pairs = 0;
+  pr->R_floats = pr->r_floats = 0;
+  for (int i = 0; i < pr->N; i++)
+    for (int j = 0; j < pr->N; j++) {
+      pr->pair_of[i][j] = -1;
+      if (!has[i][j]) continue;
+      const int p = pr->num_pairs++;
+      pr->pair_of[i][j] = p;
+      pr->pair_i[p] = i;
+      pr->pair_j[p] = j;
+      pr->pair_Roff[p] = pr->R_floats;
+      pr->pair_roff[p] = pr->r_floats;
+      pr->R_floats += d.udim[j] * d.udim[j];
+      pr->r_floats += d.udim[j];
+    }
+
+  pr->num_constraints = 0;
+  for (int c = 0; c < d.num_costs; c++)
+    pr->constraint_slot[c] = IsConstraintKind(d.costs[c].kind) ? pr->num_constraints++ : -1;
+
+  // RelativeTimeTracker::RelativeTime / TimeIndex in double,
+  // include/ilqgames/utils/relative_time_tracker.h:63-72.
+  pr->lambda_index.resize(pr->T);
+  for (int kk = 0; kk < pr->T; kk++) {
+    const double t = static_cast<double>(kk) * d.time_step;
+    long idx = static_cast<long>(static_cast<size_t>((t - d.initial_time) / d.time_step));
+    idx = std::max(0L, std::min<long>(idx, pr->T - 1));
+    pr->lambda_index[kk] = (int)idx;
+  }
+  return ILQG_OK;
+}
+
+// ---------------------------- per-instance state ---------------------------
+struct Instance {
+  std::vector<real> x0;
+  // Problem::operating_point_ / strategies_ (problem.h:171-172): the warm start
+  // every Solve() begins from; only OverwriteSolution changes it.
+  std::vector<real> prob_xs, prob_us, prob_Ps, prob_alphas;
+  std::vector<real> xs, us;        // current operating point [T][n], [T][M]
+  std::vector<real> Ps, alphas;    // current strategies [T][M][n], [T][M]
+  std::vector<real> lqPs, lqAlphas;  // raw LQ solution
+  std::vector<real> A, B;          // [T][n][n], [T][n][M]
+  std::vector<real> Q, l, R, r;    // [T][N][n][n], [T][N][n], [T][R_floats], [T][r_floats]
+  std::vector<real> dxs;           // [T][n]
+  std::vector<real> lambdas;       // [ncon][T]
+  real mu;
+  real last_merit, expected_decrease, step;
+  std::vector<real> total_costs;
+  std::vector<int> time_of_extreme;  // used by quadraticization
+  int status, iters, backtracks;
+  real max_constraint_error;
+};
+
+// ------------------------------- dynamics ----------------------------------
+// xdot for all subsystems: src/concatenated_dynamical_system.cpp:69-84 and the
+// SinglePlayer*::Evaluate / Air3D::Evaluate bodies.
+void EvaluateDynamics(const Problem& pr, const real* x, const real* u, real* xdot) {
+  const ilqg_problem_desc& d = pr.d;
+  for (int s = 0; s < d.num_subsystems; s++) {
+    const ilqg_subsystem_desc& sd = d.subsystems[s];
+    const real* xs = x + sd.x_offset;
+    real* xd = xdot + sd.x_offset;
+    const real* us = u + pr.uoff[sd.first_player];
+    switch (sd.kind) {
+      case ILQG_DYN_CAR6D: {  // single_player_car_6d.h:102-113
+        const real L = sd.params[0];
+        xd[0] = xs[4] * std::cos(xs[2]);
+        xd[1] = xs[4] * std::sin(xs[2]);
+        xd[2] = (xs[4] / L) * std::tan(xs[3]);
+        xd[3] = us[0];
+        xd[4] = xs[5];
+        xd[5] = us[1];
+        break;
+      }
+      case ILQG_DYN_UNICYCLE4D: {  // single_player_unicycle_4d.h:90-99
+        xd[0] = xs[3] * std::cos(xs[2]);
+        xd[1] = xs[3] * std::sin(xs[2]);
+        xd[2] = us[0];
+        xd[3] = us[1];
+        break;
+      }
+      case ILQG_DYN_AIR3D: {  // air_3d.h:114-127
+        const real ve = sd.params[0], vp = sd.params[1];
+        const real u1 = us[0];
+        const real u2 = u[pr.uoff[sd.first_player + 1]];
+        xd[0] = -ve + vp * std::cos(xs[2]) + u1 * xs[1];
+        xd[1] = vp * std::sin(xs[2]) - u1 * xs[0];
+        xd[2] = u2 - u1;
+        break;
+      }
+      default:
+        break;
+    }
+  }
+}
+
+// MultiPlayerDynamicalSystem::Integrate, src/multi_player_dynamical_system.cpp:52-77.
+// RK4 with 2 substeps; the double `dt` narrows to the vector scalar type when it
+// multiplies a VectorXf (Eigen scalar promotion), as do the 0.5/2.0/6.0 literals.
+void Integrate(const Problem& pr, const real* x0, const real* u, real* xout) {
+  const int n = pr.n;
+  const double dt_d = pr.d.time_step / static_cast<double>(2);
+  const real dt = (real)dt_d;
+  real x[ILQG_MAX_XDIM], k1[ILQG_MAX_XDIM], k2[ILQG_MAX_XDIM], k3[ILQG_MAX_XDIM],
+      k4[ILQG_MAX_XDIM], tmp[ILQG_MAX_XDIM];
+  for (int a = 0; a < n; a++) x[a] = x0[a];
+  for (int sub = 0; sub < 2; sub++) {
+    EvaluateDynamics(pr, x, u, k1);
+    for (int a = 0; a < n; a++) { k1[a] = dt * k1[a]; tmp[a] = x[a] + (real)0.5 * k1[a]; }
+    EvaluateDynamics(pr, tmp, u, k2);
+    for (int a = 0; a < n; a++) { k2[a] = dt * k2[a]; tmp[a] = x[a] + (real)0.5 * k2[a]; }
+    EvaluateDynamics(pr, tmp, u, k3);
+    for (int a = 0; a < n; a++) { k3[a] = dt * k3[a]; tmp[a] = x[a] + k3[a]; }
+    EvaluateDynamics(pr, tmp, u, k4);
+    for (int a = 0; a < n; a++) {
+      k4[a] = dt * k4[a];
+      x[a] += (k1[a] + (real)2.0 * (k2[a] + k3[a]) + k4[a]) / (real)6.0;
+    }
+  }
+  for (int a = 0; a < n; a++) xout[a] = x[a];
+}
+
+// ConcatenatedDynamicalSystem::Linearize, src/concatenated_dynamical_system.cpp:86-107
+// + SinglePlayerCar6D::Linearize (single_player_car_6d.h:115-138),
+// SinglePlayerUnicycle4D::Linearize (single_player_unicycle_4d.h:101-116),
+// Air3D::Linearize (air_3d.h:129-149).  A = I (+ dt * df/dx), B = dt * df/du
+// (forward Euler).  `kTimeStep` is a double: products with it are
+// evaluated in double and narrowed on assignment.
+void Linearize(const Problem& pr, const real* x, const real* u, real* A, real* B) {
+  const int n = pr.n, M = pr.M;
+  const double kTimeStep = pr.d.time_step;
+  for (int a = 0; a < n * n; a++) A[a] = 0;
+  for (int a = 0; a < n; a++) A[a * n + a] = 1;
+  for (int a = 0; a < n * M; a++) B[a] = 0;
+  for (int s = 0; s < pr.d.num_subsystems; s++) {
+    const ilqg_subsystem_desc& sd = pr.d.subsystems[s];
+    const int o = sd.x_offset;
+    const real* xs = x + o;
+    const int uo = pr.uoff[sd.first_player];
+#define AA(r, c) A[(o + (r)) * n + (o + (c))]
+#define BB(r, c) B[(o + (r)) * M + (uo + (c))]
+    switch (sd.kind) {
+      case ILQG_DYN_CAR6D: {
+        const real L = sd.params[0];
+        const real ctheta = std::cos(xs[2]) * kTimeStep;
+        const real stheta = std::sin(xs[2]) * kTimeStep;
+        const real cphi = std::cos(xs[3]);
+        const real tphi = std::tan(xs[3]);
+        AA(0, 2) += -xs[4] * stheta;
+        AA(0, 4) += ctheta;
+        AA(1, 2) += xs[4] * ctheta;
+        AA(1, 4) += stheta;
+        AA(2, 3) += xs[4] * kTimeStep / (L * cphi * cphi);
+        AA(2, 4) += tphi * kTimeStep / L;
+        AA(4, 5) += kTimeStep;
+        BB(3, 0) = kTimeStep;
+        BB(5, 1) = kTimeStep;
+        break;
+      }
+      case ILQG_DYN_UNICYCLE4D: {
+        const real ctheta = std::cos(xs[2]) * kTimeStep;
+        const real stheta = std::sin(xs[2]) * kTimeStep;
+        AA(0, 2) += -xs[3] * stheta;
+        AA(0, 3) += ctheta;
+        AA(1, 2) += xs[3] * ctheta;
+        AA(1, 3) += stheta;
+        BB(2, 0) = kTimeStep;
+        BB(3, 1) = kTimeStep;
+        break;
+      }
+      case ILQG_DYN_AIR3D: {
+        const real vp = sd.params[1];
+        const real u1 = u[uo];
+        const int uo2 = pr.uoff[sd.first_player + 1];
+        const real ctheta = std::cos(xs[2]) * kTimeStep;
+        const real stheta = std::sin(xs[2]) * kTimeStep;
+        AA(0, 1) += u1 * kTimeStep;
+        AA(0, 2) -= vp * stheta;
+        AA(1, 0) -= u1 * kTimeStep;
+        AA(1, 2) += vp * ctheta;
+        BB(0, 0) = xs[1] * kTimeStep;
+        BB(1, 0) = -xs[0] * kTimeStep;
+        BB(2, 0) = -kTimeStep;
+        B[(o + 2) * M + uo2] = kTimeStep;
+        break;
+      }
+      default:
+        break;
+    }
+#undef AA
+#undef BB
+  }
+}
+
+// ------------------------------ costs --------------------------------------
+// Constraint::Mu, include/ilqgames/constraint/constraint.h:112-117
+inline real ConstraintMu(const ilqg_cost_desc& cd, real mu, real lambda, real g) {
+  if (!cd.is_equality && g <= kSmallNumber && std::abs(lambda) <= kSmallNumber) return 0.0;
+  return mu;
+}
+
+// Constraint::ModifyDerivatives, src/constraint.cpp:63-89
+void ModifyDerivatives(const ilqg_cost_desc& cd, real lambda, real mu_global, real g,
+                       real* dx, real* ddx, real* dy, real* ddy, real* dxdy) {
+  const real mu = ConstraintMu(cd, mu_global, lambda, g);
+  const real new_dx = lambda * *dx + mu * g * *dx;
+  const real new_ddx = lambda * *ddx + mu * (*dx * *dx + g * *ddx);
+  if (dy) {
+    const real new_dy = lambda * *dy + mu * g * *dy;
+    const real new_ddy = lambda * *ddy + mu * (*dy * *dy + g * *ddy);
+    const real new_dxdy = lambda * *dxdy + mu * (*dy * *dx + g * *dxdy);
+    *dy = new_dy;
+    *ddy = new_ddy;
+    *dxdy = new_dxdy;
+  }
+  *dx = new_dx;
+  *ddx = new_ddx;
+}
+
+// Cost::Evaluate for every record kind (value of the cost, or g(x) for constraints).
+real EvaluateRecord(const Problem& pr, const ilqg_cost_desc& cd, const real* in, int dim) {
+  const real weight_ = cd.weight;
+  switch (cd.kind) {
+    case ILQG_COST_QUADRATIC: {  // src/quadratic_cost.cpp:51-63
+      const real nominal_ = cd.value;
+      if (cd.dim[0] >= 0) {
+        const real delta = in[cd.dim[0]] - nominal_;
+        return 0.5 * weight_ * delta * delta;
+      }
+      real sq = 0;
+      for (int a = 0; a < dim; a++) sq += (in[a] - nominal_) * (in[a] - nominal_);
+      return 0.5 * weight_ * sq;
+    }
+    case ILQG_COST_QUADRATIC_POLYLINE2: {  // src/quadratic_polyline2_cost.cpp:52-69
+      real ssd;
+      bool is_endpoint;
+      PolylineClosestPoint(pr.polylines[cd.polyline], {in[cd.dim[0]], in[cd.dim[1]]}, nullptr,
+                           nullptr, &ssd, &is_endpoint);
+      if (is_endpoint) ssd = 0.0;
+      return 0.5 * weight_ * std::abs(ssd);
+    }
+    case ILQG_COST_PROXIMITY: {  // src/proximity_cost.cpp:52-62
+      const real threshold_ = cd.value;
+      const real threshold_sq_ = threshold_ * threshold_;
+      const real dx = in[cd.dim[0]] - in[cd.dim[2]];
+      const real dy = in[cd.dim[1]] - in[cd.dim[3]];
+      const real delta_sq = dx * dx + dy * dy;
+      if (delta_sq >= threshold_sq_) return 0.0;
+      const real gap = threshold_ - std::sqrt(delta_sq);
+      return 0.5 * weight_ * gap * gap;
+    }
+    case ILQG_COST_SEMIQUADRATIC: {  // src/semiquadratic_cost.cpp:51-59
+      const real diff = in[cd.dim[0]] - cd.value;
+      const bool oriented_right_ = cd.flag != 0;
+      if ((diff > 0.0 && oriented_right_) || (diff < 0.0 && !oriented_right_))
+        return 0.5 * weight_ * diff * diff;
+      return 0.0;
+    }
+    case ILQG_COST_SEMIQUADRATIC_POLYLINE2: {  // src/semiquadratic_polyline2_cost.cpp:52-73
+      const real threshold_ = cd.value;
+      const real signed_squared_threshold_ = sgn(threshold_) * threshold_ * threshold_;
+      const bool oriented_right_ = cd.flag != 0;
+      real ssd;
+      bool is_endpoint;
+      PolylineClosestPoint(pr.polylines[cd.polyline], {in[cd.dim[0]], in[cd.dim[1]]}, nullptr,
+                           nullptr, &ssd, &is_endpoint);
+      if (is_endpoint) return 0.0;
+      const bool active = (ssd > signed_squared_threshold_ && oriented_right_) ||
+                          (ssd < signed_squared_threshold_ && !oriented_right_);
+      if (!active) return 0.0;
+      const real signed_distance = sgn(ssd) * std::sqrt(std::abs(ssd));
+      const real diff = signed_distance - threshold_;
+      return 0.5 * weight_ * diff * diff;
+    }
+    case ILQG_COST_POLYLINE2_SIGNED_DISTANCE: {  // src/polyline2_signed_distance_cost.cpp:52-65
+      real ssd;
+      PolylineClosestPoint(pr.polylines[cd.polyline], {in[cd.dim[0]], in[cd.dim[1]]}, nullptr,
+                           nullptr, &ssd, nullptr);
+      if (!cd.flag) ssd *= -1.0;
+      return sgn(ssd) * std::sqrt(std::abs(ssd)) - cd.value;
+    }
+    case ILQG_CONSTRAINT_PROXIMITY: {  // src/proximity_constraint.cpp:56-62
+      const real dx = in[cd.dim[0]] - in[cd.dim[2]];
+      const real dy = in[cd.dim[1]] - in[cd.dim[3]];
+      const real value = std::hypot(dx, dy) - cd.value;
+      return cd.flag ? value : -value;
+    }
+    case ILQG_CONSTRAINT_SINGLE_DIMENSION: {  // single_dimension_constraint.h:68-70
+      return cd.flag ? in[cd.dim[0]] - cd.value : cd.value - in[cd.dim[0]];
+    }
+  }
+  return 0;
+}
+
+// Cost::Quadraticize for every record kind: accumulates into hess (dim x dim
+// row-major) and grad.  `lambda`, `mu` only matter for constraints.
+void QuadraticizeRecord(const Problem& pr, const ilqg_cost_desc& cd, const real* in, int dim,
+                        real lambda, real mu, real* hess, real* grad) {
+  const real weight_ = cd.weight;
+#define H(r, c) hess[(r) * dim + (c)]
+  switch (cd.kind) {
+    case ILQG_COST_QUADRATIC: {  // src/quadratic_cost.cpp:65-94
+      const real nominal_ = cd.value;
+      if (cd.dim[0] >= 0) {
+        const int d0 = cd.dim[0];
+        const real delta = in[d0] - nominal_;
+        const real dx = weight_ * delta;
+        const real ddx = weight_;
+        grad[d0] += dx;
+        H(d0, d0) += ddx;
+      } else {
+        for (int a = 0; a < dim; a++) {
+          grad[a] += weight_ * (in[a] - nominal_);
+          H(a, a) = H(a, a) + weight_;
+        }
+      }
+      break;
+    }
+    case ILQG_COST_QUADRATIC_POLYLINE2: {  // src/quadratic_polyline2_cost.cpp:71-126
+      const int xidx_ = cd.dim[0], yidx_ = cd.dim[1];
+      const Polyline& pl = pr.polylines[cd.polyline];
+      const Point2 cur = {in[xidx_], in[yidx_]};
+      bool is_vertex, is_endpoint;
+      int seg;
+      const Point2 closest = PolylineClosestPoint(pl, cur, &is_vertex, &seg, nullptr, &is_endpoint);
+      if (is_endpoint) return;
+      real ddx = weight_;
+      real ddy = weight_;
+      real dxdy = 0.0;
+      real dx = weight_ * (cur.x - closest.x);
+      real dy = weight_ * (cur.y - closest.y);
+      if (!is_vertex) {
+        const Segment& s = pl.segs[seg];
+        const real relx = cur.x - s.p1.x, rely = cur.y - s.p1.y;
+        ddx = weight_ * s.unit.y * s.unit.y;
+        ddy = weight_ * s.unit.x * s.unit.x;
+        dxdy = -weight_ * s.unit.x * s.unit.y;
+        const real w_cross = weight_ * (relx * s.unit.y - rely * s.unit.x);
+        dx = w_cross * s.unit.y;
+        dy = -w_cross * s.unit.x;
+      }
+      grad[xidx_] += dx;
+      grad[yidx_] += dy;
+      H(xidx_, xidx_) += ddx;
+      H(yidx_, yidx_) += ddy;
+      H(xidx_, yidx_) += dxdy;
+      H(yidx_, xidx_) += dxdy;
+      break;
+    }
+    case ILQG_COST_PROXIMITY: {  // src/proximity_cost.cpp:63-122
+      const int xidx1_ = cd.dim[0], yidx1_ = cd.dim[1], xidx2_ = cd.dim[2], yidx2_ = cd.dim[3];
+      const real threshold_ = cd.value;
+      const real threshold_sq_ = threshold_ * threshold_;
+      const real dx = in[xidx1_] - in[xidx2_];
+      const real dy = in[yidx1_] - in[yidx2_];
+      const real delta_sq = dx * dx + dy * dy;
+      if (delta_sq >= threshold_sq_) return;
+      const real delta = std::sqrt(delta_sq);
+      const real gap = threshold_ - delta;
+      const real weight_delta = weight_ / delta;
+      const real dx_delta = dx / delta;
+      const real dy_delta = dy / delta;
+      const real ddx1 = -weight_delta * gap * dx;
+      const real ddy1 = -weight_delta * gap * dy;
+      const real hess_x1x1 = weight_delta * (dx_delta * (gap * dx_delta + dx) - gap);
+      const real hess_y1y1 = weight_delta * (dy_delta * (gap * dy_delta + dy) - gap);
+      const real hess_x1y1 = weight_delta * (dx_delta * (gap * dy_delta + dy));
+      grad[xidx1_] += ddx1;
+      grad[xidx2_] -= ddx1;
+      grad[yidx1_] += ddy1;
+      grad[yidx2_] -= ddy1;
+      H(xidx1_, xidx1_) += hess_x1x1;
+      H(xidx1_, xidx2_) -= hess_x1x1;
+      H(xidx2_, xidx1_) -= hess_x1x1;
+      H(xidx2_, xidx2_) += hess_x1x1;
+      H(yidx1_, yidx1_) += hess_y1y1;
+      H(yidx1_, yidx2_) -= hess_y1y1;
+      H(yidx2_, yidx1_) -= hess_y1y1;
+      H(yidx2_, yidx2_) += hess_y1y1;
+      H(xidx1_, yidx1_) += hess_x1y1;
+      H(yidx1_, xidx1_) += hess_x1y1;
+      H(xidx1_, yidx2_) -= hess_x1y1;
+      H(yidx2_, xidx1_) -= hess_x1y1;
+      H(xidx2_, yidx1_) -= hess_x1y1;
+      H(yidx1_, xidx2_) -= hess_x1y1;
+      H(xidx2_, yidx2_) += hess_x1y1;
+      H(yidx2_, xidx2_) += hess_x1y1;
+      break;
+    }
+    case ILQG_COST_SEMIQUADRATIC: {  // src/semiquadratic_cost.cpp:63-85
+      const int d0 = cd.dim[0];
+      const bool oriented_right_ = cd.flag != 0;
+      const real diff = in[d0] - cd.value;
+      if ((diff < 0.0 && oriented_right_) || (diff > 0.0 && !oriented_right_)) return;
+      const real dx = weight_ * diff;
+      const real ddx = weight_;
+      grad[d0] += dx;
+      H(d0, d0) += ddx;
+      break;
+    }
+    case ILQG_COST_SEMIQUADRATIC_POLYLINE2: {  // src/semiquadratic_polyline2_cost.cpp:75-142
+      const int xidx_ = cd.dim[0], yidx_ = cd.dim[1];
+      const real threshold_ = cd.value;
+      const real signed_squared_threshold_ = sgn(threshold_) * threshold_ * threshold_;
+      const bool oriented_right_ = cd.flag != 0;
+      const Polyline& pl = pr.polylines[cd.polyline];
+      const Point2 cur = {in[xidx_], in[yidx_]};
+      real ssd;
+      bool is_vertex, is_endpoint;
+      int seg;
+      const Point2 closest = PolylineClosestPoint(pl, cur, &is_vertex, &seg, &ssd, &is_endpoint);
+      const bool active = (ssd > signed_squared_threshold_ && oriented_right_) ||
+                          (ssd < signed_squared_threshold_ && !oriented_right_);
+      if (!active) return;
+      if (is_endpoint) return;
+      real ddx = weight_;
+      real ddy = weight_;
+      real dxdy = 0.0;
+      real scaling = std::sqrt(std::abs(ssd));
+      scaling = (scaling - std::abs(threshold_)) / scaling;
+      real dx = weight_ * scaling * (cur.x - closest.x);
+      real dy = weight_ * scaling * (cur.y - closest.y);
+      if (!is_vertex) {
+        const Segment& s = pl.segs[seg];
+        const real relx = cur.x - s.p1.x, rely = cur.y - s.p1.y;
+        ddx = weight_ * s.unit.y * s.unit.y;
+        ddy = weight_ * s.unit.x * s.unit.x;
+        const real cross_term = -weight_ * s.unit.x * s.unit.y;
+        dxdy = cross_term;
+        const real w_cross = weight_ * (relx * s.unit.y - rely * s.unit.x - threshold_);
+        dx = w_cross * s.unit.y;
+        dy = -w_cross * s.unit.x;
+      }
+      grad[xidx_] += dx;
+      grad[yidx_] += dy;
+      H(xidx_, xidx_) += ddx;
+      H(yidx_, yidx_) += ddy;
+      H(xidx_, yidx_) += dxdy;
+      H(yidx_, xidx_) += dxdy;
+      break;
+    }
+    case ILQG_COST_POLYLINE2_SIGNED_DISTANCE: {  // src/polyline2_signed_distance_cost.cpp:67-121
+      const int xidx_ = cd.dim[0], yidx_ = cd.dim[1];
+      const Polyline& pl = pr.polylines[cd.polyline];
+      const Point2 cur = {in[xidx_], in[yidx_]};
+      bool is_vertex;
+      real ssd;
+      int seg;
+      const Point2 closest = PolylineClosestPoint(pl, cur, &is_vertex, &seg, &ssd, nullptr);
+      if (!cd.flag) ssd *= -1.0;
+      const real sign = sgn(ssd);
+      const real distance = std::sqrt(std::abs(ssd));
+      const real delta_x = cur.x - closest.x;
+      const real delta_y = cur.y - closest.y;
+      real dx = sign * delta_x / distance;
+      real dy = sign * delta_y / distance;
+      const real denom = ssd * distance;
+      real ddx = delta_y * delta_y / denom;
+      real ddy = delta_x * delta_x / denom;
+      real dxdy = -delta_x * delta_y / denom;
+      if (!is_vertex) {
+        const Segment& s = pl.segs[seg];
+        dx = s.unit.y;
+        dy = -s.unit.x;
+        ddx = 0.0;
+        ddy = 0.0;
+        dxdy = 0.0;
+      }
+      grad[xidx_] += dx;
+      grad[yidx_] += dy;
+      H(xidx_, xidx_) += ddx;
+      H(yidx_, yidx_) += ddy;
+      H(xidx_, yidx_) += dxdy;
+      H(yidx_, xidx_) += dxdy;
+      break;
+    }
+    case ILQG_CONSTRAINT_PROXIMITY: {  // src/proximity_constraint.cpp:64-116
+      const int xidx1_ = cd.dim[0], yidx1_ = cd.dim[1], xidx2_ = cd.dim[2], yidx2_ = cd.dim[3];
+      const real threshold_ = cd.value;
+      const real dx = in[xidx1_] - in[xidx2_];
+      const real dy = in[yidx1_] - in[yidx2_];
+      const real prox = std::hypot(dx, dy);
+      const real sign = (cd.flag) ? 1.0 : -1.0;
+      const real g = sign * (prox - threshold_);
+      const real rel_dx = dx / prox;
+      const real rel_dy = dy / prox;
+      real grad_x1 = sign * rel_dx;
+      real grad_y1 = sign * rel_dy;
+      real hess_x1x1 = sign * (1.0 - rel_dx * rel_dx) / prox;
+      real hess_y1y1 = sign * (1.0 - rel_dy * rel_dy) / prox;
+      real hess_x1y1 = -sign * rel_dx * rel_dy / prox;
+      ModifyDerivatives(cd, lambda, mu, g, &grad_x1, &hess_x1x1, &grad_y1, &hess_y1y1, &hess_x1y1);
+      grad[xidx1_] += grad_x1;
+      grad[xidx2_] -= grad_x1;
+      grad[yidx1_] += grad_y1;
+      grad[yidx2_] -= grad_y1;
+      H(xidx1_, xidx1_) += hess_x1x1;
+      H(xidx1_, xidx2_) -= hess_x1x1;
+      H(xidx2_, xidx1_) -= hess_x1x1;
+      H(xidx2_, xidx2_) += hess_x1x1;
+      H(yidx1_, yidx1_) += hess_y1y1;
+      H(yidx1_, yidx2_) -= hess_y1y1;
+      H(yidx2_, yidx1_) -= hess_y1y1;
+      H(yidx2_, yidx2_) += hess_y1y1;
+      H(xidx1_, yidx1_) += hess_x1y1;
+      H(xidx1_, yidx2_) -= hess_x1y1;
+      H(xidx2_, yidx1_) -= hess_x1y1;
+      H(xidx2_, yidx2_) += hess_x1y1;
+      H(yidx1_, xidx1_) += hess_x1y1;
+      H(yidx1_, xidx2_) -= hess_x1y1;
+      H(yidx2_, xidx1_) -= hess_x1y1;
+      H(yidx2_, xidx2_) += hess_x1y1;
+      break;
+    }
+    case ILQG_CONSTRAINT_SINGLE_DIMENSION: {  // single_dimension_constraint.h:74-96
+      const int dim_ = cd.dim[0];
+      const real sign = (cd.flag) ? 1.0 : -1.0;
+      const real x = in[dim_];
+      const real g = sign * (x - cd.value);
+      real dx = sign;
+      real ddx = 0.0;
+      ModifyDerivatives(cd, lambda, mu, g, &dx, &ddx, nullptr, nullptr, nullptr);
+      grad[dim_] += dx;
+      H(dim_, dim_) += ddx;
+      break;
+    }
+  }
+#undef H
+}
+
+// PlayerCost::Quadraticize / QuadraticizeControlCosts, src/player_cost.cpp:194-225,
+// as dispatched by ILQSolver::ComputeCostQuadraticization (src/ilq_solver.cpp:471-490).
+// Writes Q_i, l_i (all players) and R_p, r_p (all pairs) for time step kk.
+void QuadraticizeStep(const Problem& pr, const Instance& in, int kk, const real* x, const real* u,
+                      real* Q, real* l, real* R, real* r) {
+  const int n = pr.n, N = pr.N;
+  const ilqg_problem_desc& d = pr.d;
+  for (int i = 0; i < N; i++) {
+    real* Qi = Q + (size_t)i * n * n;
+    real* li = l + (size_t)i * n;
+    // QuadraticCostApproximation(xdim, state_regularization_): reg * I, zero grad.
+    for (int a = 0; a < n * n; a++) Qi[a] = 0;
+    for (int a = 0; a < n; a++) Qi[a * n + a] = d.state_regularization[i];
+    for (int a = 0; a < n; a++) li[a] = 0;
+  }
+  for (int p = 0; p < pr.num_pairs; p++) {
+    const int i = pr.pair_i[p], j = pr.pair_j[p], mj = d.udim[j];
+    real* Rp = R + pr.pair_Roff[p];
+    real* rp = r + pr.pair_roff[p];
+    for (int a = 0; a < mj * mj; a++) Rp[a] = 0;
+    for (int a = 0; a < mj; a++) rp[a] = 0;
+    // A control block only exists in the reference if some control cost or
+    // constraint names it (player_cost.cpp:70-80); it then starts at reg * I.
+    // The (i,i) block always exists in every in-scope example.
+    for (int a = 0; a < mj; a++) Rp[a * mj + a] = d.control_regularization[i];
+  }
+  for (int c = 0; c < d.num_costs; c++) {
+    const ilqg_cost_desc& cd = d.costs[c];
+    const int i = cd.player;
+    const bool full = d.cost_structure[i] == ILQG_COST_SUM || in.time_of_extreme[i] == kk;
+    const int slot = pr.constraint_slot[c];
+    const bool is_con = slot >= 0;
+    // QuadraticizeControlCosts keeps only control COSTS (no constraints).
+    if (!full && (cd.arg < 0 || is_con)) continue;
+    const real lambda = is_con ? in.lambdas[(size_t)slot * pr.T + pr.lambda_index[kk]] : (real)0;
+    if (cd.arg < 0) {
+      QuadraticizeRecord(pr, cd, x, n, lambda, in.mu, Q + (size_t)i * n * n, l + (size_t)i * n);
+    } else {
+      const int p = pr.pair_of[i][cd.arg];
+      QuadraticizeRecord(pr, cd, u + pr.uoff[cd.arg], d.udim[cd.arg], lambda, in.mu,
+                         R + pr.pair_Roff[p], r + pr.pair_roff[p]);
+    }
+  }
+}
+
+// PlayerCost::Evaluate(t, x, us), src/player_cost.cpp:128-144: state + control
+// COSTS only (no constraints).
+real EvaluatePlayerCost(const Problem& pr, int i, const real* x, const real* u) {
+  real total = 0.0;
+  const ilqg_problem_desc& d = pr.d;
+  for (int c = 0; c < d.num_costs; c++) {
+    const ilqg_cost_desc& cd = d.costs[c];
+    if (cd.player != i || pr.constraint_slot[c] >= 0) continue;
+    if (cd.arg < 0)
+      total += EvaluateRecord(pr, cd, x, pr.n);
+    else
+      total += EvaluateRecord(pr, cd, u + pr.uoff[cd.arg], d.udim[cd.arg]);
+  }
+  return total;
+}
+
+// ILQSolver::TotalCosts, src/ilq_solver.cpp:220-257
+void TotalCosts(const Problem& pr, Instance& in) {
+  const int T = pr.T, N = pr.N, n = pr.n, M = pr.M;
+  for (int i = 0; i < N; i++) {
+    const int cs = pr.d.cost_structure[i];
+    in.total_costs[i] = cs == ILQG_COST_SUM ? (real)0.0 : cs == ILQG_COST_MAX ? -kInfinity : kInfinity;
+  }
+  for (int kk = 0; kk < T; kk++)
+    for (int i = 0; i < N; i++) {
+      const real cur = EvaluatePlayerCost(pr, i, &in.xs[(size_t)kk * n], &in.us[(size_t)kk * M]);
+      const int cs = pr.d.cost_structure[i];
+      if (cs == ILQG_COST_SUM)
+        in.total_costs[i] += cur;
+      else if (cs == ILQG_COST_MAX && cur > in.total_costs[i]) {
+        in.total_costs[i] = cur;
+        in.time_of_extreme[i] = kk;
+      } else if (cs == ILQG_COST_MIN) {
+        if (cur < in.total_costs[i]) {
+          in.total_costs[i] = cur;
+          in.time_of_extreme[i] = kk;
+        }
+      }
+    }
+}
+
+// ILQSolver::CurrentOperatingPoint, src/ilq_solver.cpp:174-206 with
+// Strategy::operator(), include/ilqgames/utils/strategy.h:73-76.
+void Rollout(const Problem& pr, const real* last_xs, const real* last_us, const real* Ps,
+             const real* alphas, real* xs, real* us) {
+  const int T = pr.T, n = pr.n, M = pr.M;
+  real x[ILQG_MAX_XDIM], dx[ILQG_MAX_XDIM], xn[ILQG_MAX_XDIM];
+  for (int a = 0; a < n; a++) x[a] = last_xs[a];
+  for (int kk = 0; kk < T; kk++) {
+    for (int a = 0; a < n; a++) dx[a] = x[a] - last_xs[(size_t)kk * n + a];
+    for (int a = 0; a < n; a++) xs[(size_t)kk * n + a] = x[a];
+    for (int c = 0; c < M; c++) {
+      real acc = 0;
+      const real* Prow = Ps + ((size_t)kk * M + c) * n;
+      for (int a = 0; a < n; a++) acc += Prow[a] * dx[a];
+      us[(size_t)kk * M + c] = last_us[(size_t)kk * M + c] - acc - alphas[(size_t)kk * M + c];
+    }
+    if (kk < T - 1) {
+      Integrate(pr, x, &us[(size_t)kk * M], xn);
+      for (int a = 0; a < n; a++) x[a] = xn[a];
+    }
+  }
+}
+
+void LinearizeQuadraticize(const Problem& pr, Instance& in) {
+  const int T = pr.T, n = pr.n, M = pr.M, N = pr.N;
+  for (int kk = 0; kk < T; kk++) {
+    const real* x = &in.xs[(size_t)kk * n];
+    const real* u = &in.us[(size_t)kk * M];
+    Linearize(pr, x, u, &in.A[(size_t)kk * n * n], &in.B[(size_t)kk * n * M]);
+    QuadraticizeStep(pr, in, kk, x, u, &in.Q[(size_t)kk * N * n * n], &in.l[(size_t)kk * N * n],
+                     &in.R[(size_t)kk * pr.R_floats], &in.r[(size_t)kk * pr.r_floats]);
+  }
+}
+
+// ------------------------- Householder QR solve ----------------------------
+// Restates Eigen's HouseholderQR (householder_qr_inplace_unblocked +
+// MatrixBase::makeHouseholder + solve = Q^T b then back-substitution) as called
+// at src/lq_feedback_solver.cpp:180.  Eigen is an un-vendored, unpinned
+// dependency (cmake/Dependencies.cmake:5); this follows its published
+// algorithm, not its vectorised summation order.
+// Solves S X = Y in place: S is m x m (destroyed), Y is m x c (becomes X).
+void HouseholderQrSolve(real* S, int m, real* Y, int c) {
+  std::vector<real> tau(m);
+  for (int k = 0; k < m; k++) {
+    real tail_sq = 0;
+    for (int i = k + 1; i < m; i++) tail_sq += S[i * m + k] * S[i * m + k];
+    const real c0 = S[k * m + k];
+    real beta, t;
+    const real tol = std::numeric_limits<real>::min();
+    if (tail_sq <= tol) {
+      t = 0;
+      beta = c0;
+      for (int i = k + 1; i < m; i++) S[i * m + k] = 0;
+    } else {
+      beta = std::sqrt(c0 * c0 + tail_sq);
+      if (c0 >= 0) beta = -beta;
+      for (int i = k + 1; i < m; i++) S[i * m + k] /= (c0 - beta);
+      t = (beta - c0) / beta;
+    }
+    tau[k] = t;
+    S[k * m + k] = beta;
+    // apply H = I - tau v v^T (v = [1; essential]) to the remaining columns
+    for (int j = k + 1; j < m; j++) {
+      real w = S[k * m + j];
+      for (int i = k + 1; i < m; i++) w += S[i * m + k] * S[i * m + j];
+      w *= t;
+      S[k * m + j] -= w;
+      for (int i = k + 1; i < m; i++) S[i * m + j] -= S[i * m + k] * w;
+    }
+    // ... and to the right-hand sides (Q^T Y)
+    for (int j = 0; j < c; j++) {
+      real w = Y[k * c + j];
+      for (int i = k + 1; i < m; i++) w += S[i * m + k] * Y[i * c + j];
+      w *= t;
+      Y[k * c + j] -= w;
+      for (int i = k + 1; i < m; i++) Y[i * c + j] -= S[i * m + k] * w;
+    }
+  }
+  // back substitution with the upper triangle R
+  for (int j = 0; j < c; j++)
+    for (int i = m - 1; i >= 0; i--) {
+      real acc = Y[i * c + j];
+      for (int q = i + 1; q < m; q++) acc -= S[i * m + q] * Y[q * c + j];
+      Y[i * c + j] = acc / S[i * m + i];
+    }
+}
+
+// LQFeedbackSolver::Solve, src/lq_feedback_solver.cpp:71-244.
+// x0arg is the `x0` argument (ILQSolver passes x0 - xs[0], ilq_solver.cpp:140-143).
+void LQFeedbackSolve(const Problem& pr, Instance& in, const real* x0arg) {
+  const int T = pr.T, n = pr.n, M = pr.M, N = pr.N;
+  const ilqg_problem_desc& d = pr.d;
+  std::vector<real> Zs((size_t)T * N * n * n), zetas((size_t)T * N * n);
+  std::vector<real> S(M * M), Y(M * (n + 1)), F(n * n), beta(n), BiZi(ILQG_MAX_UDIM * n),
+      tmp(n * n), tmpv(n);
+  std::fill(in.lqPs.begin(), in.lqPs.end(), (real)0);  // Strategy ctor zero-fills (strategy.h:64-70)
+  std::fill(in.lqAlphas.begin(), in.lqAlphas.end(), (real)0);
+
+  auto Z = [&](int k, int i) { return &Zs[((size_t)k * N + i) * n * n]; };
+  auto zeta = [&](int k, int i) { return &zetas[((size_t)k * N + i) * n]; };
+
+  for (int i = 0; i < N; i++) {  // :102-105
+    std::memcpy(Z(T - 1, i), &in.Q[((size_t)(T - 1) * N + i) * n * n], sizeof(real) * n * n);
+    std::memcpy(zeta(T - 1, i), &in.l[((size_t)(T - 1) * N + i) * n], sizeof(real) * n);
+  }
+
+  for (int kk = T - 2; kk >= 0; kk--) {
+    const real* A = &in.A[(size_t)kk * n * n];
+    const real* B = &in.B[(size_t)kk * n * M];
+    const real* Rk = &in.R[(size_t)kk * pr.R_floats];
+    const real* rk = &in.r[(size_t)kk * pr.r_floats];
+    // :119-161 build S, Y
+    for (int i = 0; i < N; i++) {
+      const int mi = d.udim[i], ro = pr.uoff[i];
+      const real* Zi = Z(kk + 1, i);
+      const real* zi = zeta(kk + 1, i);
+      // BiZi = B_i^T Z_i  (mi x n)
+      for (int a = 0; a < mi; a++)
+        for (int c = 0; c < n; c++) {
+          real acc = 0;
+          for (int q = 0; q < n; q++) acc += B[q * M + ro + a] * Zi[q * n + c];
+          BiZi[a * n + c] = acc;
+        }
+      const int pii = pr.pair_of[i][i];
+      for (int j = 0; j < N; j++) {
+        const int mj = d.udim[j], co = pr.uoff[j];
+        for (int a = 0; a < mi; a++)
+          for (int c = 0; c < mj; c++) {
+            real acc = 0;
+            for (int q = 0; q < n; q++) acc += BiZi[a * n + q] * B[q * M + co + c];
+            if (i == j) acc = acc + Rk[pr.pair_Roff[pii] + a * mi + c];
+            S[(ro + a) * M + co + c] = acc;
+          }
+      }
+      for (int a = 0; a < mi; a++) {
+        for (int c = 0; c < n; c++) {
+          real acc = 0;
+          for (int q = 0; q < n; q++) acc += BiZi[a * n + q] * A[q * n + c];
+          Y[(ro + a) * (n + 1) + c] = acc;
+        }
+        real acc = 0;
+        for (int q = 0; q < n; q++) acc += B[q * M + ro + a] * zi[q];
+        Y[(ro + a) * (n + 1) + n] = acc + rk[pr.pair_roff[pii] + a];
+      }
+    }
+    // :163-176 Gershgorin (column-wise)
+    if (pr.p.adaptive_regularization) {
+      for (int c = 0; c < M; c++) {
+        real col1 = 0;
+        for (int a = 0; a < M; a++) col1 += std::abs(S[a * M + c]);
+        const real radius = col1 - std::abs(S[c * M + c]);
+        const real eval_lo = S[c * M + c] - radius;
+        constexpr float min_eval = 1e-3;
+        if (eval_lo < min_eval) S[c * M + c] += radius + min_eval;
+      }
+    }
+    // :180 X = S.householderQr().solve(Y)
+    HouseholderQrSolve(S.data(), M, Y.data(), n + 1);
+    real* Pk = &in.lqPs[(size_t)kk * M * n];
+    real* ak = &in.lqAlphas[(size_t)kk * M];
+    for (int a = 0; a < M; a++) {
+      for (int c = 0; c < n; c++) Pk[a * n + c] = Y[a * (n + 1) + c];
+      ak[a] = Y[a * (n + 1) + n];
+    }
+    // :189-194 F = A - sum B_i P_i ; beta = - sum B_i alpha_i
+    for (int a = 0; a < n; a++) {
+      for (int c = 0; c < n; c++) F[a * n + c] = A[a * n + c];
+      beta[a] = 0;
+    }
+    for (int i = 0; i < N; i++) {
+      const int mi = d.udim[i], ro = pr.uoff[i];
+      for (int a = 0; a < n; a++) {
+        for (int c = 0; c < n; c++) {
+          real acc = 0;
+          for (int q = 0; q < mi; q++) acc += B[a * M + ro + q] * Pk[(ro + q) * n + c];
+          F[a * n + c] -= acc;
+        }
+        real acc = 0;
+        for (int q = 0; q < mi; q++) acc += B[a * M + ro + q] * ak[ro + q];
+        beta[a] -= acc;
+      }
+    }
+    // :197-213 update Z, zeta
+    for (int i = 0; i < N; i++) {
+      const real* Zn = Z(kk + 1, i);
+      const real* zn = zeta(kk + 1, i);
+      real* Zc = Z(kk, i);
+      real* zc = zeta(kk, i);
+      const real* Qi = &in.Q[((size_t)kk * N + i) * n * n];
+      const real* li = &in.l[((size_t)kk * N + i) * n];
+      // zeta = F^T (zeta_next + Z_next beta) + l
+      for (int a = 0; a < n; a++) {
+        real acc = 0;
+        for (int q = 0; q < n; q++) acc += Zn[a * n + q] * beta[q];
+        tmpv[a] = zn[a] + acc;
+      }
+      for (int a = 0; a < n; a++) {
+        real acc = 0;
+        for (int q = 0; q < n; q++) acc += F[q * n + a] * tmpv[q];
+        zc[a] = acc + li[a];
+      }
+      // Z = (F^T Z_next) F + Q
+      for (int a = 0; a < n; a++)
+        for (int c = 0; c < n; c++) {
+          real acc = 0;
+          for (int q = 0; q < n; q++) acc += F[q * n + a] * Zn[q * n + c];
+          tmp[a * n + c] = acc;
+        }
+      for (int a = 0; a < n; a++)
+        for (int c = 0; c < n; c++) {
+          real acc = 0;
+          for (int q = 0; q < n; q++) acc += tmp[a * n + q] * F[q * n + c];
+          Zc[a * n + c] = acc + Qi[a * n + c];
+        }
+      // :206-212 control terms for every R_ij present
+      for (int j = 0; j < N; j++) {
+        const int p = pr.pair_of[i][j];
+        if (p < 0) continue;
+        const int mj = d.udim[j], co = pr.uoff[j];
+        const real* Rij = Rk + pr.pair_Roff[p];
+        const real* rij = rk + pr.pair_roff[p];
+        real v[ILQG_MAX_UDIM];
+        for (int a = 0; a < mj; a++) {
+          real acc = 0;
+          for (int q = 0; q < mj; q++) acc += Rij[a * mj + q] * ak[co + q];
+          v[a] = acc - rij[a];
+        }
+        for (int a = 0; a < n; a++) {
+          real acc = 0;
+          for (int q = 0; q < mj; q++) acc += Pk[(co + q) * n + a] * v[q];
+          zc[a] += acc;
+        }
+        real PtR[ILQG_MAX_XDIM * ILQG_MAX_UDIM];
+        for (int a = 0; a < n; a++)
+          for (int c = 0; c < mj; c++) {
+            real acc = 0;
+            for (int q = 0; q < mj; q++) acc += Pk[(co + q) * n + a] * Rij[q * mj + c];
+            PtR[a * mj + c] = acc;
+          }
+        for (int a = 0; a < n; a++)
+          for (int c = 0; c < n; c++) {
+            real acc = 0;
+            for (int q = 0; q < mj; q++) acc += PtR[a * mj + q] * Pk[(co + q) * n + c];
+            Zc[a * n + c] += acc;
+          }
+      }
+    }
+  }
+  // :217-241 forward pass for delta_xs (costates are unused downstream)
+  std::vector<real> xstar(x0arg, x0arg + n), last(n);
+  for (int kk = 0; kk < T; kk++) {
+    for (int a = 0; a < n; a++) in.dxs[(size_t)kk * n + a] = xstar[a];
+    const real* A = &in.A[(size_t)kk * n * n];
+    const real* B = &in.B[(size_t)kk * n * M];
+    last = xstar;
+    for (int a = 0; a < n; a++) {
+      real acc = 0;
+      for (int q = 0; q < n; q++) acc += A[a * n + q] * last[q];
+      xstar[a] = acc;
+    }
+    for (int i = 0; i < N; i++) {
+      const int mi = d.udim[i], ro = pr.uoff[i];
+      for (int a = 0; a < n; a++) {
+        real acc = 0;
+        for (int q = 0; q < mi; q++) acc += B[a * M + ro + q] * in.lqAlphas[(size_t)kk * M + ro + q];
+        xstar[a] -= acc;
+      }
+    }
+  }
+}
+
+// ILQSolver::ExpectedDecrease, src/ilq_solver.cpp:364-398 (as written)
+real ExpectedDecrease(const Problem& pr, const Instance& in) {
+  const int T = pr.T, n = pr.n, M = pr.M, N = pr.N;
+  real expected_decrease = 0.0;
+  for (int kk = 0; kk < T; kk++)
+    for (int i = 0; i < N; i++) {
+      const int mi = pr.d.udim[i], ro = pr.uoff[i], p = pr.pair_of[i][i];
+      const real* Rii = &in.R[(size_t)kk * pr.R_floats + pr.pair_Roff[p]];
+      const real* rii = &in.r[(size_t)kk * pr.r_floats + pr.pair_roff[p]];
+      const real* neg_ui = &in.lqAlphas[(size_t)kk * M + ro];
+      real acc = 0;  // (neg_ui^T * hess) * dLdu
+      for (int c = 0; c < mi; c++) {
+        real row = 0;
+        for (int a = 0; a < mi; a++) row += neg_ui[a] * Rii[a * mi + c];
+        acc += row * rii[c];
+      }
+      expected_decrease -= acc;
+      if (kk > 0) {
+        const real* Qi = &in.Q[((size_t)kk * N + i) * n * n];
+        const real* li = &in.l[((size_t)kk * N + i) * n];
+        const real* dx = &in.dxs[(size_t)kk * n];
+        real acc2 = 0;
+        for (int c = 0; c < n; c++) {
+          real row = 0;
+          for (int a = 0; a < n; a++) row += dx[a] * Qi[a * n + c];
+          acc2 += row * li[c];
+        }
+        expected_decrease -= acc2;
+      }
+    }
+  return expected_decrease;
+}
+
+// ILQSolver::MeritFunction, src/ilq_solver.cpp:400-435: requadraticize
+// at the candidate point, then 0.5 * sum_k sum_i (|r_ii|^2 + [k>0] |l_i|^2).
+real MeritFunction(const Problem& pr, Instance& in) {
+  const int T = pr.T, n = pr.n, M = pr.M, N = pr.N;
+  for (int kk = 0; kk < T; kk++)
+    QuadraticizeStep(pr, in, kk, &in.xs[(size_t)kk * n], &in.us[(size_t)kk * M],
+                     &in.Q[(size_t)kk * N * n * n], &in.l[(size_t)kk * N * n],
+                     &in.R[(size_t)kk * pr.R_floats], &in.r[(size_t)kk * pr.r_floats]);
+  real merit = 0.0;
+  for (int kk = 0; kk < T; kk++)
+    for (int i = 0; i < N; i++) {
+      const int mi = pr.d.udim[i], p = pr.pair_of[i][i];
+      const real* rii = &in.r[(size_t)kk * pr.r_floats + pr.pair_roff[p]];
+      real sq = 0;
+      for (int a = 0; a < mi; a++) sq += rii[a] * rii[a];
+      merit += sq;
+      if (kk > 0) {
+        const real* li = &in.l[((size_t)kk * N + i) * n];
+        real sq2 = 0;
+        for (int a = 0; a < n; a++) sq2 += li[a] * li[a];
+        merit += sq2;
+      }
+    }
+  return 0.5 * merit;
+}
+
+// ILQSolver::ModifyLQStrategies, src/ilq_solver.cpp:289-348 (+ CheckArmijoCondition
+// :350-362, HasConverged ilq_solver.h:126-130, ScaleAlphas :66-72).  Returns false
+// on linesearch failure.  On success the scaled LQ strategies become current.
+bool ModifyLQStrategies(const Problem& pr, Instance& in, bool* has_converged) {
+  const ilqg_solver_params& sp = pr.p;
+  in.expected_decrease = ExpectedDecrease(pr, in);
+  std::vector<real> Ps = in.lqPs, alphas = in.lqAlphas;
+  for (auto& a : alphas) a *= sp.initial_alpha_scaling;
+  const std::vector<real> last_xs = in.xs, last_us = in.us;
+  real current_stepsize = sp.initial_alpha_scaling;
+  Rollout(pr, last_xs.data(), last_us.data(), Ps.data(), alphas.data(), in.xs.data(), in.us.data());
+  in.backtracks++;
+  if (!sp.linesearch) {
+    in.Ps = Ps;
+    in.alphas = alphas;
+    in.step = current_stepsize;
+    return true;
+  }
+  for (int ii = 0; ii < sp.max_backtracking_steps; ii++) {
+    const real merit = MeritFunction(pr, in);
+    const real scaled_expected_decrease =
+        sp.expected_decrease_fraction * current_stepsize * in.expected_decrease;
+    if (in.last_merit - merit >= scaled_expected_decrease) {
+      *has_converged = (merit <= in.last_merit) &&
+                       std::abs(in.last_merit - merit) < sp.convergence_tolerance;
+      in.last_merit = merit;
+      in.Ps = Ps;
+      in.alphas = alphas;
+      in.step = current_stepsize;
+      return true;
+    }
+    for (auto& a : alphas) a *= sp.geometric_alpha_scaling;
+    current_stepsize *= sp.geometric_alpha_scaling;
+    Rollout(pr, last_xs.data(), last_us.data(), Ps.data(), alphas.data(), in.xs.data(),
+            in.us.data());
+    in.backtracks++;
+  }
+  // Failure: the log's final iterate is the last accepted one (ilq_solver.cpp:146-155).
+  in.xs = last_xs;
+  in.us = last_us;
+  return false;
+}
+
+}  // namespace
+
+// ============================== C ABI =======================================
+struct ilqg_solver {
+  Problem pr;
+  int batch;
+  std::vector<Instance> inst;
+};
+
+namespace {
+
+void InitInstance(const Problem& pr, Instance& in) {
+  const int T = pr.T, n = pr.n, M = pr.M, N = pr.N;
+  in.x0.assign(n, 0);
+  in.prob_xs.assign((size_t)T * n, 0);
+  in.prob_us.assign((size_t)T * M, 0);
+  in.prob_Ps.assign((size_t)T * M * n, 0);
+  in.prob_alphas.assign((size_t)T * M, 0);
+  in.xs.assign((size_t)T * n, 0);
+  in.us.assign((size_t)T * M, 0);
+  in.Ps.assign((size_t)T * M * n, 0);
+  in.alphas.assign((size_t)T * M, 0);
+  in.lqPs.assign((size_t)T * M * n, 0);
+  in.lqAlphas.assign((size_t)T * M, 0);
+  in.A.assign((size_t)T * n * n, 0);
+  in.B.assign((size_t)T * n * M, 0);
+  in.Q.assign((size_t)T * N * n * n, 0);
+  in.l.assign((size_t)T * N * n, 0);
+  in.R.assign((size_t)T * pr.R_floats, 0);
+  in.r.assign((size_t)T * pr.r_floats, 0);
+  in.dxs.assign((size_t)T * n, 0);
+  in.lambdas.assign((size_t)pr.num_constraints * T, 0);  // kDefaultLambda
+  in.mu = kDefaultMu;
+  in.last_merit = kInfinity;
+  in.expected_decrease = kInfinity;
+  in.step = 0;
+  in.total_costs.assign(N, 0);
+  in.time_of_extreme.assign(N, 0);
+  in.status = ILQG_STATUS_IDLE;
+  in.iters = 0;
+  in.backtracks = 0;
+  in.max_constraint_error = kInfinity;
+}
+
+template <typename Src>
+void CopyOut(const std::vector<Src>& v, float* dst) {
+  for (size_t a = 0; a < v.size(); a++) dst[a] = (float)v[a];
+}
+
+// One pass of the while loop src/ilq_solver.cpp:123-166 for one instance.
+void IterateOnce(const Problem& pr, Instance& in) {
+  if (in.status != ILQG_STATUS_RUNNING) return;
+  if (in.iters >= pr.p.max_solver_iters) {
+    in.status = ILQG_STATUS_MAX_ITERS;
+    return;
+  }
+  in.iters++;
+  LinearizeQuadraticize(pr, in);
+  std::vector<real> zero(pr.n, 0);
+  LQFeedbackSolve(pr, in, zero.data());
+  bool has_converged = false;
+  if (!ModifyLQStrategies(pr, in, &has_converged)) {
+    in.status = ILQG_STATUS_LINESEARCH_FAILED;
+    return;
+  }
+  TotalCosts(pr, in);
+  if (has_converged && !pr.p.disable_convergence_exit)
+    in.status = ILQG_STATUS_CONVERGED;
+  else if (in.iters >= pr.p.max_solver_iters)
+    in.status = ILQG_STATUS_MAX_ITERS;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params, int batch,
+                int /*device*/, ilqg_handle* out) {
+  if (!desc || !params || !out || batch < 1) return ILQG_ERR_INVALID_ARGUMENT;
+  ilqg_solver* s = new (std::nothrow) ilqg_solver;
+  if (!s) return ILQG_ERR_OUT_OF_MEMORY;
+  const int rc = BuildProblem(desc, params, &s->pr);
+  if (rc != ILQG_OK) {
+    delete s;
+    return rc;
+  }
+  s->batch = batch;
+  s->inst.resize(batch);
+  for (auto& in : s->inst) InitInstance(s->pr, in);
+  *out = s;
+  return ILQG_OK;
+}
+
+int ilqg_destroy(ilqg_handle h) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  delete h;
+  return ILQG_OK;
+}
+
+const char* ilqg_strerror(int code) {
+  switch (code) {
+    case ILQG_OK: return "ok";
+    case ILQG_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case ILQG_ERR_UNSUPPORTED: return "unsupported descriptor";
+    case ILQG_ERR_CUDA: return "CUDA error";
+    case ILQG_ERR_NO_DEVICE: return "no CUDA device";
+    case ILQG_ERR_OUT_OF_MEMORY: return "out of memory";
+    case ILQG_ERR_BAD_HANDLE: return "bad handle";
+    case ILQG_ERR_SIZE_MISMATCH: return "host buffer size mismatch";
+  }
+  return "unknown error";
+}
+
+size_t ilqg_abi_struct_size(int which) {
+  switch (which) {
+    case 0: return sizeof(ilqg_problem_desc);
+    case 1: return sizeof(ilqg_solver_params);
+    case 2: return sizeof(ilqg_layout);
+    case 3: return sizeof(ilqg_cost_desc);
+    case 4: return sizeof(ilqg_subsystem_desc);
+  }
+  return 0;
+}
+
+int ilqg_get_layout(ilqg_handle h, ilqg_layout* out) {
+  if (!h || !out) return ILQG_ERR_BAD_HANDLE;
+  const Problem& pr = h->pr;
+  std::memset(out, 0, sizeof(*out));
+  out->batch = h->batch;
+  out->num_time_steps = pr.T;
+  out->num_players = pr.N;
+  out->xdim = pr.n;
+  out->total_udim = pr.M;
+  for (int i = 0; i < pr.N; i++) {
+    out->udim[i] = pr.d.udim[i];
+    out->u_offset[i] = pr.uoff[i];
+  }
+  out->num_pairs = pr.num_pairs;
+  for (int p = 0; p < pr.num_pairs; p++) {
+    out->pair_player[p] = pr.pair_i[p];
+    out->pair_arg[p] = pr.pair_j[p];
+    out->pair_R_offset[p] = pr.pair_Roff[p];
+    out->pair_r_offset[p] = pr.pair_roff[p];
+  }
+  out->R_floats = pr.R_floats;
+  out->r_floats = pr.r_floats;
+  out->num_constraints = pr.num_constraints;
+  out->record_floats = 0;
+  for (int kk = 0; kk < pr.T; kk++) out->lambda_index[kk] = pr.lambda_index[kk];
+  return ILQG_OK;
+}
+
+int ilqg_upload_x0(ilqg_handle h, const float* x0, size_t bytes) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  const int n = h->pr.n;
+  if (bytes != sizeof(float) * (size_t)h->batch * n) return ILQG_ERR_SIZE_MISMATCH;
+  for (int b = 0; b < h->batch; b++)
+    for (int a = 0; a < n; a++) h->inst[b].x0[a] = x0[(size_t)b * n + a];
+  return ILQG_OK;
+}
+
+int ilqg_upload_warmstart(ilqg_handle h, const float* xs, const float* us, const float* Ps,
+                          const float* alphas) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  const Problem& pr = h->pr;
+  const size_t nx = (size_t)pr.T * pr.n, nu = (size_t)pr.T * pr.M, np = (size_t)pr.T * pr.M * pr.n;
+  for (int b = 0; b < h->batch; b++) {
+    Instance& in = h->inst[b];
+    for (size_t a = 0; a < nx; a++) in.prob_xs[a] = xs ? xs[b * nx + a] : 0.f;
+    for (size_t a = 0; a < nu; a++) in.prob_us[a] = us ? us[b * nu + a] : 0.f;
+    for (size_t a = 0; a < np; a++) in.prob_Ps[a] = Ps ? Ps[b * np + a] : 0.f;
+    for (size_t a = 0; a < nu; a++) in.prob_alphas[a] = alphas ? alphas[b * nu + a] : 0.f;
+    // the working copies follow so single-stage calls (linearize_quadraticize,
+    // lq_backward) see the uploaded point without a solve_begin
+    in.xs = in.prob_xs; in.us = in.prob_us; in.Ps = in.prob_Ps; in.alphas = in.prob_alphas;
+  }
+  return ILQG_OK;
+}
+
+int ilqg_upload(ilqg_handle h, int what, const void* src, size_t bytes) {
+  if (!h || !src) return ILQG_ERR_BAD_HANDLE;
+  const Problem& pr = h->pr;
+  const int B = h->batch;
+  const float* f = (const float*)src;
+  const int32_t* iv = (const int32_t*)src;
+  switch (what) {
+    case ILQG_LAMBDAS: {
+      const size_t per = (size_t)pr.num_constraints * pr.T;
+      if (bytes != sizeof(float) * per * B) return ILQG_ERR_SIZE_MISMATCH;
+      for (int b = 0; b < B; b++)
+        for (size_t a = 0; a < per; a++) h->inst[b].lambdas[a] = f[b * per + a];
+      return ILQG_OK;
+    }
+    case ILQG_MU:
+      if (bytes != sizeof(float) * B) return ILQG_ERR_SIZE_MISMATCH;
+      for (int b = 0; b < B; b++) h->inst[b].mu = f[b];
+      return ILQG_OK;
+    case ILQG_MERIT:
+      if (bytes != sizeof(float) * B) return ILQG_ERR_SIZE_MISMATCH;
+      for (int b = 0; b < B; b++) h->inst[b].last_merit = f[b];
+      return ILQG_OK;
+    case ILQG_TIME_OF_EXTREME:
+      if (bytes != sizeof(int32_t) * B * pr.N) return ILQG_ERR_SIZE_MISMATCH;
+      for (int b = 0; b < B; b++)
+        for (int i = 0; i < pr.N; i++) h->inst[b].time_of_extreme[i] = iv[b * pr.N + i];
+      return ILQG_OK;
+    case ILQG_X0:
+      return ilqg_upload_x0(h, f, bytes);
+  }
+  return ILQG_ERR_INVALID_ARGUMENT;
+}
+
+int ilqg_upload_lq(ilqg_handle h, const float* A, const float* Bs, const float* Q, const float* l,
+                   const float* R, const float* r) {
+  if (!h || !A || !Bs || !Q || !l || !R || !r) return ILQG_ERR_BAD_HANDLE;
+  const Problem& pr = h->pr;
+  const size_t T = pr.T, n = pr.n, M = pr.M, N = pr.N;
+  for (int b = 0; b < h->batch; b++) {
+    Instance& in = h->inst[b];
+    for (size_t a = 0; a < T * n * n; a++) in.A[a] = A[b * T * n * n + a];
+    for (size_t a = 0; a < T * n * M; a++) in.B[a] = Bs[b * T * n * M + a];
+    for (size_t a = 0; a < T * N * n * n; a++) in.Q[a] = Q[b * T * N * n * n + a];
+    for (size_t a = 0; a < T * N * n; a++) in.l[a] = l[b * T * N * n + a];
+    for (size_t a = 0; a < T * pr.R_floats; a++) in.R[a] = R[b * T * pr.R_floats + a];
+    for (size_t a = 0; a < T * pr.r_floats; a++) in.r[a] = r[b * T * pr.r_floats + a];
+  }
+  return ILQG_OK;
+}
+
+int ilqg_solve_begin(ilqg_handle h) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  const Problem& pr = h->pr;
+  for (auto& in : h->inst) {
+    // src/ilq_solver.cpp:86-107
+    std::vector<real> last_xs = in.prob_xs, last_us = in.prob_us;
+    for (int a = 0; a < pr.n; a++) last_xs[a] = in.x0[a];
+    in.Ps = in.prob_Ps;
+    in.alphas = in.prob_alphas;
+    Rollout(pr, last_xs.data(), last_us.data(), in.Ps.data(), in.alphas.data(), in.xs.data(),
+            in.us.data());
+    TotalCosts(pr, in);
+    in.status = ILQG_STATUS_RUNNING;
+    in.iters = 0;
+  }
+  return ILQG_OK;
+}
+
+int ilqg_linearize_quadraticize(ilqg_handle h) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  for (auto& in : h->inst) LinearizeQuadraticize(h->pr, in);
+  return ILQG_OK;
+}
+
+int ilqg_lq_backward(ilqg_handle h) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  std::vector<real> zero(h->pr.n, 0);
+  for (auto& in : h->inst) {
+    LQFeedbackSolve(h->pr, in, zero.data());
+    in.expected_decrease = ExpectedDecrease(h->pr, in);
+  }
+  return ILQG_OK;
+}
+
+int ilqg_linesearch(ilqg_handle h) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  for (auto& in : h->inst) {
+    bool conv = false;
+    if (!ModifyLQStrategies(h->pr, in, &conv)) {
+      in.status = ILQG_STATUS_LINESEARCH_FAILED;
+      continue;
+    }
+    TotalCosts(h->pr, in);
+    if (conv && !h->pr.p.disable_convergence_exit) in.status = ILQG_STATUS_CONVERGED;
+  }
+  return ILQG_OK;
+}
+
+int ilqg_iterate(ilqg_handle h, int max_iters, int* iters_done) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  int most = 0;
+  for (auto& in : h->inst) {
+    for (int it = 0; it < max_iters; it++) IterateOnce(h->pr, in);
+    most = std::max(most, in.iters);
+  }
+  if (iters_done) *iters_done = most;
+  return ILQG_OK;
+}
+
+// src/augmented_lagrangian_solver.cpp:113-178, per instance.
+int ilqg_al_update(ilqg_handle h) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  const Problem& pr = h->pr;
+  const ilqg_problem_desc& d = pr.d;
+  for (auto& in : h->inst) {
+    real max_err = -kInfinity;
+    // Outer loop over players then time (:116-139); constraints of one player in
+    // record order, state constraints before control constraints.
+    for (int i = 0; i < pr.N; i++)
+      for (int kk = 0; kk < pr.T; kk++) {
+        // t = op.t0 + kTimeStep * float(kk): same TimeIndex as RelativeTime(kk).
+        const int li = pr.lambda_index[kk];
+        for (int pass = 0; pass < 2; pass++)
+          for (int c = 0; c < d.num_costs; c++) {
+            const ilqg_cost_desc& cd = d.costs[c];
+            const int slot = pr.constraint_slot[c];
+            if (slot < 0 || cd.player != i) continue;
+            if ((pass == 0) != (cd.arg < 0)) continue;
+            const real g = cd.arg < 0
+                               ? EvaluateRecord(pr, cd, &in.xs[(size_t)kk * pr.n], pr.n)
+                               : EvaluateRecord(pr, cd, &in.us[(size_t)kk * pr.M + pr.uoff[cd.arg]],
+                                                d.udim[cd.arg]);
+            max_err = std::max(max_err, g);
+            // Constraint::IncrementLambda, constraint.h:98-102
+            real& lam = in.lambdas[(size_t)slot * pr.T + li];
+            const real new_lambda = lam + in.mu * g;
+            lam = cd.is_equality ? new_lambda : std::max((real)0.0f, new_lambda);
+          }
+      }
+    in.mu *= pr.p.geometric_mu_scaling;  // :143
+    in.max_constraint_error = max_err;
+  }
+  return ILQG_OK;
+}
+
+// Problem::OverwriteSolution(log->FinalOperatingPoint(), log->FinalStrategies()),
+// src/problem.cpp:188-194 as called at augmented_lagrangian_solver.cpp:151-154.
+int ilqg_overwrite_solution(ilqg_handle h, int only_successful) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  for (auto& in : h->inst) {
+    if (only_successful && in.status == ILQG_STATUS_LINESEARCH_FAILED) continue;
+    in.prob_xs = in.xs;
+    in.prob_us = in.us;
+    in.prob_Ps = in.Ps;
+    in.prob_alphas = in.alphas;
+  }
+  return ILQG_OK;
+}
+
+// src/augmented_lagrangian_solver.cpp:165-178: down-scale multipliers of the
+// instances whose inner solve failed.
+int ilqg_al_post_solve(ilqg_handle h) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  for (auto& in : h->inst) {
+    if (in.status != ILQG_STATUS_LINESEARCH_FAILED) continue;
+    for (auto& lam : in.lambdas) lam *= h->pr.p.geometric_lambda_downscaling;
+    in.mu *= h->pr.p.geometric_mu_downscaling;
+  }
+  return ILQG_OK;
+}
+
+int ilqg_download(ilqg_handle h, int what, void* dst, size_t bytes) {
+  if (!h || !dst) return ILQG_ERR_BAD_HANDLE;
+  const Problem& pr = h->pr;
+  const int B = h->batch;
+  float* f = (float*)dst;
+  int32_t* iv = (int32_t*)dst;
+  auto vec = [&](std::vector<real> Instance::*m) -> int {
+    const size_t per = (h->inst[0].*m).size();
+    if (bytes != sizeof(float) * per * B) return ILQG_ERR_SIZE_MISMATCH;
+    for (int b = 0; b < B; b++) CopyOut(h->inst[b].*m, f + b * per);
+    return ILQG_OK;
+  };
+  auto scal = [&](real Instance::*m) -> int {
+    if (bytes != sizeof(float) * B) return ILQG_ERR_SIZE_MISMATCH;
+    for (int b = 0; b < B; b++) f[b] = (float)(h->inst[b].*m);
+    return ILQG_OK;
+  };
+  auto iscal = [&](int Instance::*m) -> int {
+    if (bytes != sizeof(int32_t) * B) return ILQG_ERR_SIZE_MISMATCH;
+    for (int b = 0; b < B; b++) iv[b] = h->inst[b].*m;
+    return ILQG_OK;
+  };
+  switch (what) {
+    case ILQG_XS: return vec(&Instance::xs);
+    case ILQG_US: return vec(&Instance::us);
+    case ILQG_PS: return vec(&Instance::Ps);
+    case ILQG_ALPHAS: return vec(&Instance::alphas);
+    case ILQG_LQ_PS: return vec(&Instance::lqPs);
+    case ILQG_LQ_ALPHAS: return vec(&Instance::lqAlphas);
+    case ILQG_LIN_A: return vec(&Instance::A);
+    case ILQG_LIN_B: return vec(&Instance::B);
+    case ILQG_QUAD_Q: return vec(&Instance::Q);
+    case ILQG_QUAD_L: return vec(&Instance::l);
+    case ILQG_QUAD_R: return vec(&Instance::R);
+    case ILQG_QUAD_RGRAD: return vec(&Instance::r);
+    case ILQG_DELTA_XS: return vec(&Instance::dxs);
+    case ILQG_LAMBDAS: return vec(&Instance::lambdas);
+    case ILQG_TOTAL_COSTS: return vec(&Instance::total_costs);
+    case ILQG_X0: return vec(&Instance::x0);
+    case ILQG_MU: return scal(&Instance::mu);
+    case ILQG_MERIT: return scal(&Instance::last_merit);
+    case ILQG_EXPECTED_DECREASE: return scal(&Instance::expected_decrease);
+    case ILQG_STEP: return scal(&Instance::step);
+    case ILQG_MAX_CONSTRAINT_ERROR: return scal(&Instance::max_constraint_error);
+    case ILQG_STATUS: return iscal(&Instance::status);
+    case ILQG_ITERS: return iscal(&Instance::iters);
+    case ILQG_BACKTRACKS: return iscal(&Instance::backtracks);
+    case ILQG_TIME_OF_EXTREME:
+      if (bytes != sizeof(int32_t) * B * pr.N) return ILQG_ERR_SIZE_MISMATCH;
+      for (int b = 0; b < B; b++)
+        for (int i = 0; i < pr.N; i++) iv[b * pr.N + i] = h->inst[b].time_of_extreme[i];
+      return ILQG_OK;
+  }
+  return ILQG_ERR_INVALID_ARGUMENT;
+}
+
+int ilqg_synchronize(ilqg_handle h) { return h ? ILQG_OK : ILQG_ERR_BAD_HANDLE; }
+
+int ilqg_kernel_launches(ilqg_handle h, long long* out) {
+  if (!h || !out) return ILQG_ERR_BAD_HANDLE;
+  *out = 0;
+  return ILQG_OK;
+}
+
+// ----- extra oracle-only probes used by tests/test_oracle_pins.py ------------
+// Polyline2::ClosestPoint on polyline `p` of the handle's descriptor.
+int ilqg_oracle_polyline_closest_point(ilqg_handle h, int p, float qx, float qy, float* closest,
+                                       int* is_vertex, int* segment, float* signed_sq,
+                                       int* is_endpoint) {
+  if (!h || p < 0 || p >= (int)h->pr.polylines.size()) return ILQG_ERR_INVALID_ARGUMENT;
+  bool v, e;
+  int seg;
+  real ssd;
+  const Point2 c = PolylineClosestPoint(h->pr.polylines[p], {(real)qx, (real)qy}, &v, &seg, &ssd, &e);
+  closest[0] = (float)c.x;
+  closest[1] = (float)c.y;
+  *is_vertex = v;
+  *segment = seg;
+  *signed_sq = (float)ssd;
+  *is_endpoint = e;
+  return ILQG_OK;
+}
+
+// LineSegment2::ClosestPoint for the segment (ax,ay)-(bx,by).
+int ilqg_oracle_segment_closest_point(float ax, float ay, float bx, float by, float qx, float qy,
+                                      float* closest, int* is_endpoint, float* signed_sq) {
+  const Segment s = MakeSegment({(real)ax, (real)ay}, {(real)bx, (real)by});
+  if (!(s.length > kSmallNumber)) return ILQG_ERR_INVALID_ARGUMENT;  // CHECK_GT, line_segment2.h:61
+  bool e;
+  real ssd;
+  const Point2 c = SegmentClosestPoint(s, {(real)qx, (real)qy}, &e, &ssd);
+  closest[0] = (float)c.x;
+  closest[1] = (float)c.y;
+  *is_endpoint = e;
+  *signed_sq = (float)ssd;
+  return ILQG_OK;
+}
+
+// Evaluate record c (cost value, or g for constraints; with_al != 0 gives
+// Constraint::EvaluateAugmentedLagrangian, constraint.h:80-84) at one input.
+int ilqg_oracle_evaluate_record(ilqg_handle h, int c, const float* input, int dim, float lambda,
+                                float mu, int with_al, float* value) {
+  if (!h || c < 0 || c >= h->pr.d.num_costs) return ILQG_ERR_INVALID_ARGUMENT;
+  std::vector<real> in(input, input + dim);
+  const ilqg_cost_desc& cd = h->pr.d.costs[c];
+  const real g = EvaluateRecord(h->pr, cd, in.data(), dim);
+  if (with_al) {
+    const real m = ConstraintMu(cd, mu, lambda, g);
+    *value = (float)(lambda * g + 0.5 * m * g * g);
+  } else {
+    *value = (float)g;
+  }
+  return ILQG_OK;
+}
+
+// Quadraticize record c alone into zeroed hess/grad.
+int ilqg_oracle_quadraticize_record(ilqg_handle h, int c, const float* input, int dim,
+                                    float lambda, float mu, float* hess, float* grad) {
+  if (!h || c < 0 || c >= h->pr.d.num_costs) return ILQG_ERR_INVALID_ARGUMENT;
+  std::vector<real> in(input, input + dim), H((size_t)dim * dim, 0), g(dim, 0);
+  QuadraticizeRecord(h->pr, h->pr.d.costs[c], in.data(), dim, lambda, mu, H.data(), g.data());
+  for (int a = 0; a < dim * dim; a++) hess[a] = (float)H[a];
+  for (int a = 0; a < dim; a++) grad[a] = (float)g[a];
+  return ILQG_OK;
+}
+
+// xdot = f(x, u) and one Integrate() step, for the linearization FD checks.
+int ilqg_oracle_dynamics(ilqg_handle h, const float* x, const float* u, float* xdot, float* xnext) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  const Problem& pr = h->pr;
+  std::vector<real> xr(x, x + pr.n), ur(u, u + pr.M), xd(pr.n, 0), xn(pr.n, 0);
+  EvaluateDynamics(pr, xr.data(), ur.data(), xd.data());
+  Integrate(pr, xr.data(), ur.data(), xn.data());
+  for (int a = 0; a < pr.n; a++) {
+    xdot[a] = (float)xd[a];
+    xnext[a] = (float)xn[a];
+  }
+  return ILQG_OK;
+}
+
+}  // extern "C"
