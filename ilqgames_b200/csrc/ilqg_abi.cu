@@ -1,0 +1,750 @@
+// ilqg_abi.cu -- host side of the C ABI declared in include/ilqg.h: builds the device
+// descriptor, owns the per-device slab and launches the sm_100a kernels.  No CPU
+// implementation of the hot path lives here: without a CUDA device every entry point
+// that would compute returns ILQG_ERR_NO_DEVICE / ILQG_ERR_CUDA.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "ilqg_kernels.cuh"
+
+using namespace ilqg;
+
+struct ilqg_solver {
+  DevDesc d;
+  DevParams p;
+  ilqg_problem_desc host_desc;
+  ilqg_layout layout;
+  Slab s;
+  int device;
+  int B;
+  cudaStream_t stream;
+  std::vector<void*> allocs;
+  float* staging;
+  size_t staging_floats;
+  long long launches;
+  int dims_key;  // index into the dispatch table
+};
+
+namespace {
+
+#define CUDA_TRY(expr)                                                            \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      std::fprintf(stderr, "[ilqg_b200] %s failed: %s (%s:%d)\n", #expr,          \
+                   cudaGetErrorString(_e), __FILE__, __LINE__);                   \
+      return ILQG_ERR_CUDA;                                                       \
+    }                                                                             \
+  } while (0)
+
+inline bool IsConstraintKind(int kind) {
+  return kind == ILQG_CONSTRAINT_PROXIMITY || kind == ILQG_CONSTRAINT_SINGLE_DIMENSION;
+}
+
+int SubsystemXdim(int kind) {
+  return kind == ILQG_DYN_CAR6D ? 6 : kind == ILQG_DYN_UNICYCLE4D ? 4 : kind == ILQG_DYN_AIR3D ? 3 : 0;
+}
+
+// Host "problem compiler": ilqg_problem_desc -> DevDesc + ilqg_layout.
+int BuildDeviceDesc(const ilqg_problem_desc& h, DevDesc* d, ilqg_layout* lo, std::vector<int>* lidx) {
+  std::memset(d, 0, sizeof(*d));
+  std::memset(lo, 0, sizeof(*lo));
+  if (h.num_time_steps < 2 || h.num_time_steps > ILQG_MAX_TIME_STEPS) return ILQG_ERR_INVALID_ARGUMENT;
+  if (h.num_players < 1 || h.num_players > ILQG_MAX_PLAYERS) return ILQG_ERR_INVALID_ARGUMENT;
+  if (h.xdim < 1 || h.xdim > ILQG_MAX_XDIM) return ILQG_ERR_INVALID_ARGUMENT;
+  if (h.num_costs < 0 || h.num_costs > ILQG_MAX_COSTS) return ILQG_ERR_INVALID_ARGUMENT;
+  if (h.num_subsystems < 0 || h.num_subsystems > ILQG_MAX_SUBSYSTEMS) return ILQG_ERR_INVALID_ARGUMENT;
+  if (h.num_polylines < 0 || h.num_polylines > ILQG_MAX_POLYLINES) return ILQG_ERR_INVALID_ARGUMENT;
+  d->T = h.num_time_steps;
+  d->N = h.num_players;
+  d->n = h.xdim;
+  d->time_step = h.time_step;
+  d->uoff[0] = 0;
+  for (int i = 0; i < d->N; i++) {
+    if (h.udim[i] < 1) return ILQG_ERR_INVALID_ARGUMENT;
+    d->udim[i] = h.udim[i];
+    d->uoff[i + 1] = d->uoff[i] + h.udim[i];
+    d->state_reg[i] = h.state_regularization[i];
+    d->control_reg[i] = h.control_regularization[i];
+    d->cost_structure[i] = h.cost_structure[i];
+  }
+  d->M = d->uoff[d->N];
+  if (d->M > ILQG_MAX_UDIM) return ILQG_ERR_INVALID_ARGUMENT;
+
+  d->num_subsystems = h.num_subsystems;
+  for (int k = 0; k < h.num_subsystems; k++) {
+    const ilqg_subsystem_desc& hs = h.subsystems[k];
+    DevSubsystem& ds = d->sub[k];
+    const int xd = SubsystemXdim(hs.kind);
+    if (xd == 0 || hs.x_offset < 0 || hs.x_offset + xd > d->n) return ILQG_ERR_INVALID_ARGUMENT;
+    const int np = hs.kind == ILQG_DYN_AIR3D ? 2 : 1;
+    if (hs.first_player < 0 || hs.first_player + np > d->N) return ILQG_ERR_INVALID_ARGUMENT;
+    if (hs.kind != ILQG_DYN_AIR3D && d->udim[hs.first_player] != 2) return ILQG_ERR_INVALID_ARGUMENT;
+    ds.kind = hs.kind;
+    ds.x_offset = hs.x_offset;
+    ds.first_player = hs.first_player;
+    ds.u_offset = d->uoff[hs.first_player];
+    ds.u_offset2 = np == 2 ? d->uoff[hs.first_player + 1] : ds.u_offset + 1;
+    ds.p0 = hs.params[0];
+    ds.p1 = hs.params[1];
+  }
+
+  // polylines -> segments (Polyline2 ctor src/polyline2.cpp:49-60; LineSegment2 ctor
+  // line_segment2.h:55-62, fp32)
+  d->num_polylines = h.num_polylines;
+  int nseg = 0;
+  for (int p = 0; p < h.num_polylines; p++) {
+    d->seg_start[p] = nseg;
+    const int a = h.polyline_start[p], b = h.polyline_start[p + 1];
+    if (a < 0 || b > ILQG_MAX_POLYLINE_POINTS || b - a < 2) return ILQG_ERR_INVALID_ARGUMENT;
+    for (int q = a + 1; q < b; q++) {
+      DevSegment& sg = d->seg[nseg++];
+      sg.p1x = h.polyline_points[q - 1][0];
+      sg.p1y = h.polyline_points[q - 1][1];
+      sg.p2x = h.polyline_points[q][0];
+      sg.p2y = h.polyline_points[q][1];
+      const float dx = sg.p1x - sg.p2x, dy = sg.p1y - sg.p2y;
+      sg.length = std::sqrt(dx * dx + dy * dy);
+      if (!(sg.length > kSmallNumber)) return ILQG_ERR_INVALID_ARGUMENT;  // CHECK_GT line_segment2.h:61
+      sg.ux = (sg.p2x - sg.p1x) / sg.length;
+      sg.uy = (sg.p2y - sg.p1y) / sg.length;
+    }
+  }
+  d->seg_start[h.num_polylines] = nseg;
+
+  // control pairs (i,j) sorted by (i,j): (i,i) always (src/lq_feedback_solver.cpp:139-141)
+  bool has[ILQG_MAX_PLAYERS][ILQG_MAX_PLAYERS] = {};
+  for (int i = 0; i < d->N; i++) has[i][i] = true;
+  for (int c = 0; c < h.num_costs; c++) {
+    const ilqg_cost_desc& cd = h.costs[c];
+    if (cd.player < 0 || cd.player >= d->N || cd.arg >= d->N) return ILQG_ERR_INVALID_ARGUMENT;
+    if (cd.arg >= 0) has[cd.player][cd.arg] = true;
+  }
+  d->num_pairs = 0;
+  for (int i = 0; i < d->N; i++)
+    for (int j = 0; j < d->N; j++) {
+      d->pair_of[i][j] = -1;
+      if (!has[i][j]) continue;
+      const int p = d->num_pairs++;
+      d->pair_of[i][j] = p;
+      d->pair_i[p] = i;
+      d->pair_j[p] = j;
+      d->pair_Roff[p] = d->R_floats;
+      d->pair_roff[p] = d->r_floats;
+      d->R_floats += d->udim[j] * d->udim[j];
+      d->r_floats += d->udim[j];
+    }
+  if (d->r_floats > ILQG_MAX_UDIM * ILQG_MAX_PLAYERS) return ILQG_ERR_UNSUPPORTED;
+
+  // cost records, stably sorted by owner; lambda slots follow the host record order
+  int slot_of[ILQG_MAX_COSTS];
+  d->num_constraints = 0;
+  for (int c = 0; c < h.num_costs; c++)
+    slot_of[c] = IsConstraintKind(h.costs[c].kind) ? d->num_constraints++ : -1;
+  d->num_costs = 0;
+  for (int i = 0; i < d->N; i++) {
+    d->cost_begin[i] = d->num_costs;
+    for (int c = 0; c < h.num_costs; c++) {
+      const ilqg_cost_desc& cd = h.costs[c];
+      if (cd.player != i) continue;
+      if (cd.kind < ILQG_COST_QUADRATIC || cd.kind > ILQG_CONSTRAINT_SINGLE_DIMENSION)
+        return ILQG_ERR_UNSUPPORTED;
+      const int dim = cd.arg < 0 ? d->n : d->udim[cd.arg];
+      const bool needs_poly = cd.kind == ILQG_COST_QUADRATIC_POLYLINE2 ||
+                              cd.kind == ILQG_COST_SEMIQUADRATIC_POLYLINE2 ||
+                              cd.kind == ILQG_COST_POLYLINE2_SIGNED_DISTANCE;
+      if (needs_poly && (cd.polyline < 0 || cd.polyline >= h.num_polylines)) return ILQG_ERR_INVALID_ARGUMENT;
+      const int ndims = (cd.kind == ILQG_COST_PROXIMITY || cd.kind == ILQG_CONSTRAINT_PROXIMITY) ? 4
+                        : needs_poly ? 2 : 1;
+      for (int q = 0; q < ndims; q++) {
+        const bool all_dims_ok = cd.kind == ILQG_COST_QUADRATIC && q == 0 && cd.dim[0] < 0;
+        if (!all_dims_ok && (cd.dim[q] < 0 || cd.dim[q] >= dim)) return ILQG_ERR_INVALID_ARGUMENT;
+      }
+      DevCost& dc = d->cost[d->num_costs++];
+      dc.kind = cd.kind;
+      dc.player = cd.player;
+      dc.arg = cd.arg;
+      dc.is_equality = cd.is_equality;
+      dc.d0 = cd.dim[0];
+      dc.d1 = cd.dim[1];
+      dc.d2 = cd.dim[2];
+      dc.d3 = cd.dim[3];
+      dc.flag = cd.flag;
+      dc.polyline = cd.polyline;
+      dc.slot = slot_of[c];
+      dc.pair = cd.arg >= 0 ? d->pair_of[cd.player][cd.arg] : -1;
+      dc.weight = cd.weight;
+      dc.value = cd.value;
+    }
+  }
+  d->cost_begin[d->N] = d->num_costs;
+
+  // LQ record layout
+  const int n = d->n, M = d->M, N = d->N;
+  d->offA = 0;
+  d->offB = d->offA + n * n;
+  d->offQ = d->offB + n * M;
+  d->offl = d->offQ + N * n * n;
+  d->offR = d->offl + N * n;
+  d->offr = d->offR + d->R_floats;
+  d->rec = (d->offr + d->r_floats + 3) & ~3;
+
+  // kk -> Constraint::TimeIndex(RelativeTime(kk)) in double
+  // (include/ilqgames/utils/relative_time_tracker.h:63-72), SURVEY Q1
+  lidx->resize(d->T);
+  for (int kk = 0; kk < d->T; kk++) {
+    const double t = static_cast<double>(kk) * h.time_step;
+    long idx = static_cast<long>(static_cast<size_t>((t - h.initial_time) / h.time_step));
+    idx = std::max(0L, std::min<long>(idx, d->T - 1));
+    (*lidx)[kk] = (int)idx;
+  }
+
+  lo->num_time_steps = d->T;
+  lo->num_players = N;
+  lo->xdim = n;
+  lo->total_udim = M;
+  for (int i = 0; i < N; i++) {
+    lo->udim[i] = d->udim[i];
+    lo->u_offset[i] = d->uoff[i];
+  }
+  lo->num_pairs = d->num_pairs;
+  for (int p = 0; p < d->num_pairs; p++) {
+    lo->pair_player[p] = d->pair_i[p];
+    lo->pair_arg[p] = d->pair_j[p];
+    lo->pair_R_offset[p] = d->pair_Roff[p];
+    lo->pair_r_offset[p] = d->pair_roff[p];
+  }
+  lo->R_floats = d->R_floats;
+  lo->r_floats = d->r_floats;
+  lo->num_constraints = d->num_constraints;
+  lo->record_floats = d->rec;
+  for (int kk = 0; kk < d->T; kk++) lo->lambda_index[kk] = (*lidx)[kk];
+  return ILQG_OK;
+}
+
+// ------------------------- compiled dimension table -------------------------
+// (n, M, N) envelopes with a specialised backward kernel.
+struct DimsEntry {
+  int n, M, N;
+};
+constexpr DimsEntry kDims[] = {
+    {16, 6, 3},  // ThreePlayerIntersection: 2x Car6D + Unicycle4D
+    {24, 8, 4},  // RoundaboutMerging: 4x Car6D
+    {3, 2, 2},   // Air3D
+    {2, 2, 2},   // test/test_lq_solver.cpp point-mass LQ game
+    {12, 6, 3},  // BASELINE.json's "3x unicycle4d" variant
+};
+constexpr int kNumDims = sizeof(kDims) / sizeof(kDims[0]);
+
+constexpr int kLsLanes = 8;  // lanes per instance in k_linesearch / k_solve_begin
+
+template <typename K>
+int SetSmem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return ILQG_OK;
+}
+
+template <int NX, int MU, int NP>
+int LaunchBackward(ilqg_solver* h, int only_running) {
+  const size_t smem = sizeof(float) * KBWD_WARPS * (size_t)(BwdSmem<NX, MU, NP>::rec + h->d.rec);
+  int rc = SetSmem(k_lq_backward<NX, MU, NP>, smem);
+  if (rc != ILQG_OK) return rc;
+  const int blocks = (h->B + KBWD_WARPS - 1) / KBWD_WARPS;
+  k_lq_backward<NX, MU, NP><<<blocks, KBWD_WARPS * 32, smem, h->stream>>>(h->d, h->p, h->s, only_running);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ILQG_OK;
+}
+
+int DispatchBackward(ilqg_solver* h, int only_running) {
+  switch (h->dims_key) {
+    case 0: return LaunchBackward<16, 6, 3>(h, only_running);
+    case 1: return LaunchBackward<24, 8, 4>(h, only_running);
+    case 2: return LaunchBackward<3, 2, 2>(h, only_running);
+    case 3: return LaunchBackward<2, 2, 2>(h, only_running);
+    case 4: return LaunchBackward<12, 6, 3>(h, only_running);
+  }
+  return ILQG_ERR_UNSUPPORTED;
+}
+
+size_t LsSmemBytes(const ilqg_solver* h) {
+  const DevDesc& d = h->d;
+  const int per = ((2 * d.n + d.M + 3) & ~3) + ((d.T * 2 * d.N + 3) & ~3);
+  return sizeof(float) * (size_t)per * (KLS_THREADS / kLsLanes);
+}
+
+int LaunchLqRecords(ilqg_solver* h, int only_running) {
+  const DevDesc& d = h->d;
+  const size_t smem = sizeof(float) * KLQ_WARPS * (size_t)(d.rec + ((d.n + d.M + 3) & ~3));
+  int rc = SetSmem(k_linearize_quadraticize, smem);
+  if (rc != ILQG_OK) return rc;
+  const long long warps = (long long)h->B * d.T;
+  const int blocks = (int)((warps + KLQ_WARPS - 1) / KLQ_WARPS);
+  k_linearize_quadraticize<<<blocks, KLQ_WARPS * 32, smem, h->stream>>>(h->d, h->s, only_running);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ILQG_OK;
+}
+
+int LaunchLinesearch(ilqg_solver* h) {
+  const size_t smem = LsSmemBytes(h);
+  auto kern = k_linesearch<kLsLanes, ILQG_MAX_XDIM, ILQG_MAX_PLAYERS>;
+  int rc = SetSmem(kern, smem);
+  if (rc != ILQG_OK) return rc;
+  const int per_block = KLS_THREADS / kLsLanes;
+  kern<<<(h->B + per_block - 1) / per_block, KLS_THREADS, smem, h->stream>>>(h->d, h->p, h->s);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ILQG_OK;
+}
+
+int LaunchSolveBegin(ilqg_solver* h) {
+  const size_t smem = LsSmemBytes(h);
+  auto kern = k_solve_begin<kLsLanes, ILQG_MAX_XDIM, ILQG_MAX_PLAYERS>;
+  int rc = SetSmem(kern, smem);
+  if (rc != ILQG_OK) return rc;
+  const int per_block = KLS_THREADS / kLsLanes;
+  kern<<<(h->B + per_block - 1) / per_block, KLS_THREADS, smem, h->stream>>>(h->d, h->p, h->s);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ILQG_OK;
+}
+
+template <typename T>
+int DevAlloc(ilqg_solver* h, T** out, size_t count, bool zero = true) {
+  void* p = nullptr;
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    std::fprintf(stderr, "[ilqg_b200] cudaMalloc(%zu) failed: %s\n", bytes, cudaGetErrorString(e));
+    return ILQG_ERR_OUT_OF_MEMORY;
+  }
+  h->allocs.push_back(p);
+  if (zero) CUDA_TRY(cudaMemsetAsync(p, 0, bytes, h->stream));
+  *out = (T*)p;
+  return ILQG_OK;
+}
+
+int Fill(ilqg_solver* h, float* p, float v, size_t count) {
+  const int blocks = (int)std::min<size_t>((count + 255) / 256, 1024);
+  k_fill<<<blocks, 256, 0, h->stream>>>(p, v, count);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ILQG_OK;
+}
+
+int EnsureStaging(ilqg_solver* h, size_t floats) {
+  if (h->staging_floats >= floats) return ILQG_OK;
+  if (h->staging) cudaFree(h->staging);
+  h->staging = nullptr;
+  h->staging_floats = 0;
+  cudaError_t e = cudaMalloc((void**)&h->staging, floats * sizeof(float));
+  if (e != cudaSuccess) return ILQG_ERR_OUT_OF_MEMORY;
+  h->staging_floats = floats;
+  return ILQG_OK;
+}
+
+struct Guard {  // select the handle's device for the duration of a call
+  int prev;
+  bool ok;
+  explicit Guard(int dev) : prev(0), ok(true) {
+    if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+    if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    target = dev;
+  }
+  ~Guard() {
+    if (ok && prev != target) cudaSetDevice(prev);
+  }
+  int target;
+};
+
+#define ENTER(h)                              \
+  if (!(h)) return ILQG_ERR_BAD_HANDLE;       \
+  Guard _guard((h)->device);                  \
+  if (!_guard.ok) return ILQG_ERR_CUDA
+
+// download one parity-selected per-instance array through the staging buffer
+int DownloadParity(ilqg_solver* h, float* const src[2], const int* sel, int flip, size_t per, void* dst,
+                   size_t bytes) {
+  const size_t total = per * (size_t)h->B;
+  if (bytes != total * sizeof(float)) return ILQG_ERR_SIZE_MISMATCH;
+  int rc = EnsureStaging(h, total);
+  if (rc != ILQG_OK) return rc;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 4096);
+  k_gather_parity<<<blocks, 256, 0, h->stream>>>(h->staging, src[0], src[1], sel, flip, per, h->B);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(dst, h->staging, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return ILQG_OK;
+}
+
+int DownloadFlat(ilqg_solver* h, const void* src, size_t elem_bytes, size_t per, void* dst, size_t bytes) {
+  if (bytes != per * (size_t)h->B * elem_bytes) return ILQG_ERR_SIZE_MISMATCH;
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return ILQG_OK;
+}
+
+// one field of the LQ records, de-interleaved by the copy engine
+int DownloadRecordField(ilqg_solver* h, int off, int floats, void* dst, size_t bytes) {
+  const size_t rows = (size_t)h->B * h->d.T;
+  if (bytes != rows * floats * sizeof(float)) return ILQG_ERR_SIZE_MISMATCH;
+  if (floats == 0) return ILQG_OK;
+  CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)floats * sizeof(float), h->s.rec + off,
+                             (size_t)h->d.rec * sizeof(float), (size_t)floats * sizeof(float), rows,
+                             cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return ILQG_OK;
+}
+
+int UploadRecordField(ilqg_solver* h, int off, int floats, const float* src) {
+  const size_t rows = (size_t)h->B * h->d.T;
+  if (floats == 0) return ILQG_OK;
+  CUDA_TRY(cudaMemcpy2DAsync(h->s.rec + off, (size_t)h->d.rec * sizeof(float), src,
+                             (size_t)floats * sizeof(float), (size_t)floats * sizeof(float), rows,
+                             cudaMemcpyHostToDevice, h->stream));
+  return ILQG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t ilqg_abi_struct_size(int which) {
+  switch (which) {
+    case 0: return sizeof(ilqg_problem_desc);
+    case 1: return sizeof(ilqg_solver_params);
+    case 2: return sizeof(ilqg_layout);
+    case 3: return sizeof(ilqg_cost_desc);
+    case 4: return sizeof(ilqg_subsystem_desc);
+  }
+  return 0;
+}
+
+const char* ilqg_strerror(int code) {
+  switch (code) {
+    case ILQG_OK: return "ok";
+    case ILQG_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case ILQG_ERR_UNSUPPORTED: return "unsupported descriptor (no kernel compiled for these dimensions/kinds)";
+    case ILQG_ERR_CUDA: return "CUDA error";
+    case ILQG_ERR_NO_DEVICE: return "no CUDA device";
+    case ILQG_ERR_OUT_OF_MEMORY: return "out of memory";
+    case ILQG_ERR_BAD_HANDLE: return "bad handle";
+    case ILQG_ERR_SIZE_MISMATCH: return "host buffer size mismatch";
+  }
+  return "unknown error";
+}
+
+int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params, int batch, int device,
+                ilqg_handle* out) {
+  if (!desc || !params || !out || batch < 1) return ILQG_ERR_INVALID_ARGUMENT;
+  if (params->open_loop) return ILQG_ERR_UNSUPPORTED;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return ILQG_ERR_NO_DEVICE;
+  if (device < 0 || device >= ndev) return ILQG_ERR_INVALID_ARGUMENT;
+  ilqg_solver* h = new (std::nothrow) ilqg_solver();
+  if (!h) return ILQG_ERR_OUT_OF_MEMORY;
+  std::vector<int> lidx;
+  int rc = BuildDeviceDesc(*desc, &h->d, &h->layout, &lidx);
+  if (rc != ILQG_OK) {
+    delete h;
+    return rc;
+  }
+  h->dims_key = -1;
+  for (int k = 0; k < kNumDims; k++)
+    if (kDims[k].n == h->d.n && kDims[k].M == h->d.M && kDims[k].N == h->d.N) h->dims_key = k;
+  if (h->dims_key < 0) {
+    delete h;
+    return ILQG_ERR_UNSUPPORTED;
+  }
+  h->host_desc = *desc;
+  h->B = batch;
+  h->device = device;
+  h->layout.batch = batch;
+  h->staging = nullptr;
+  h->staging_floats = 0;
+  h->launches = 0;
+  DevParams& p = h->p;
+  p.convergence_tolerance = params->convergence_tolerance;
+  p.max_solver_iters = params->max_solver_iters;
+  p.linesearch = params->linesearch;
+  p.initial_alpha_scaling = params->initial_alpha_scaling;
+  p.geometric_alpha_scaling = params->geometric_alpha_scaling;
+  p.max_backtracking_steps = params->max_backtracking_steps;
+  p.expected_decrease_fraction = params->expected_decrease_fraction;
+  p.geometric_mu_scaling = params->geometric_mu_scaling;
+  p.geometric_mu_downscaling = params->geometric_mu_downscaling;
+  p.geometric_lambda_downscaling = params->geometric_lambda_downscaling;
+  p.adaptive_regularization = params->adaptive_regularization;
+  p.disable_convergence_exit = params->disable_convergence_exit;
+
+  Guard guard(device);
+  if (!guard.ok) {
+    delete h;
+    return ILQG_ERR_CUDA;
+  }
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return ILQG_ERR_CUDA;
+  }
+  const size_t B = batch, T = h->d.T, n = h->d.n, M = h->d.M, N = h->d.N;
+  Slab& s = h->s;
+  std::memset(&s, 0, sizeof(s));
+  s.B = batch;
+  auto fail = [&](int code) {
+    ilqg_destroy(h);
+    return code;
+  };
+#define ALLOC(ptr, count)                                          \
+  if ((rc = DevAlloc(h, &(ptr), (count))) != ILQG_OK) return fail(rc)
+  ALLOC(s.x0, B * n);
+  for (int k = 0; k < 2; k++) {
+    ALLOC(s.op_xs[k], B * T * n);
+    ALLOC(s.op_us[k], B * T * M);
+    ALLOC(s.st_P[k], B * T * M * n);
+    ALLOC(s.st_a[k], B * T * M);
+  }
+  ALLOC(s.prob_xs, B * T * n);
+  ALLOC(s.prob_us, B * T * M);
+  ALLOC(s.prob_P, B * T * M * n);
+  ALLOC(s.prob_a, B * T * M);
+  ALLOC(s.rec, B * T * (size_t)h->d.rec);
+  ALLOC(s.dxs, B * T * n);
+  ALLOC(s.lambdas, B * (size_t)h->d.num_constraints * T);
+  ALLOC(s.mu, B);
+  ALLOC(s.last_merit, B);
+  ALLOC(s.expected_decrease, B);
+  ALLOC(s.step, B);
+  ALLOC(s.total_costs, B * N);
+  ALLOC(s.max_con_err, B);
+  ALLOC(s.status, B);
+  ALLOC(s.iters, B);
+  ALLOC(s.backtracks, B);
+  ALLOC(s.te_quad, B * N);
+  ALLOC(s.te_new, B * N);
+  ALLOC(s.op_cur, B);
+  ALLOC(s.st_cur, B);
+  int* lidx_dev = nullptr;
+  ALLOC(lidx_dev, T);
+#undef ALLOC
+  s.lambda_index = lidx_dev;
+  if (cudaMemcpyAsync(lidx_dev, lidx.data(), T * sizeof(int), cudaMemcpyHostToDevice, h->stream) !=
+      cudaSuccess)
+    return fail(ILQG_ERR_CUDA);
+  // kDefaultMu = 10, last merit / expected decrease = +inf (types.h:125-126, ilq_solver.h:73-74)
+  if ((rc = Fill(h, s.mu, 10.0f, B)) != ILQG_OK) return fail(rc);
+  if ((rc = Fill(h, s.last_merit, INFINITY, B)) != ILQG_OK) return fail(rc);
+  if ((rc = Fill(h, s.expected_decrease, INFINITY, B)) != ILQG_OK) return fail(rc);
+  if ((rc = Fill(h, s.max_con_err, INFINITY, B)) != ILQG_OK) return fail(rc);
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(ILQG_ERR_CUDA);
+  *out = h;
+  return ILQG_OK;
+}
+
+int ilqg_destroy(ilqg_handle h) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  Guard guard(h->device);
+  if (h->stream) {
+    cudaStreamSynchronize(h->stream);
+    cudaStreamDestroy(h->stream);
+  }
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->staging) cudaFree(h->staging);
+  delete h;
+  return ILQG_OK;
+}
+
+int ilqg_get_layout(ilqg_handle h, ilqg_layout* out) {
+  if (!h || !out) return ILQG_ERR_BAD_HANDLE;
+  *out = h->layout;
+  return ILQG_OK;
+}
+
+int ilqg_upload_x0(ilqg_handle h, const float* x0, size_t bytes) {
+  ENTER(h);
+  if (!x0) return ILQG_ERR_INVALID_ARGUMENT;
+  if (bytes != sizeof(float) * (size_t)h->B * h->d.n) return ILQG_ERR_SIZE_MISMATCH;
+  CUDA_TRY(cudaMemcpyAsync(h->s.x0, x0, bytes, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));  // the host buffer may be pageable / reused
+  return ILQG_OK;
+}
+
+int ilqg_upload_warmstart(ilqg_handle h, const float* xs, const float* us, const float* Ps,
+                          const float* alphas) {
+  ENTER(h);
+  const size_t B = h->B, T = h->d.T, n = h->d.n, M = h->d.M;
+  struct Item {
+    float* dst;
+    const float* src;
+    size_t count;
+  } items[4] = {{h->s.prob_xs, xs, B * T * n}, {h->s.prob_us, us, B * T * M},
+                {h->s.prob_P, Ps, B * T * M * n}, {h->s.prob_a, alphas, B * T * M}};
+  for (const Item& it : items) {
+    if (it.src)
+      CUDA_TRY(cudaMemcpyAsync(it.dst, it.src, it.count * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    else
+      CUDA_TRY(cudaMemsetAsync(it.dst, 0, it.count * sizeof(float), h->stream));
+  }
+  k_prob_to_working<<<h->B, 256, 0, h->stream>>>(h->d, h->s);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return ILQG_OK;
+}
+
+int ilqg_upload(ilqg_handle h, int what, const void* src, size_t bytes) {
+  ENTER(h);
+  if (!src) return ILQG_ERR_INVALID_ARGUMENT;
+  const size_t B = h->B, T = h->d.T, N = h->d.N;
+  void* dst = nullptr;
+  size_t want = 0;
+  switch (what) {
+    case ILQG_LAMBDAS: dst = h->s.lambdas; want = sizeof(float) * B * h->d.num_constraints * T; break;
+    case ILQG_MU: dst = h->s.mu; want = sizeof(float) * B; break;
+    case ILQG_MERIT: dst = h->s.last_merit; want = sizeof(float) * B; break;
+    case ILQG_X0: dst = h->s.x0; want = sizeof(float) * B * h->d.n; break;
+    case ILQG_TIME_OF_EXTREME: {
+      if (bytes != sizeof(int) * B * N) return ILQG_ERR_SIZE_MISMATCH;
+      CUDA_TRY(cudaMemcpyAsync(h->s.te_new, src, bytes, cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(cudaMemcpyAsync(h->s.te_quad, src, bytes, cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
+      return ILQG_OK;
+    }
+    default: return ILQG_ERR_INVALID_ARGUMENT;
+  }
+  if (bytes != want) return ILQG_ERR_SIZE_MISMATCH;
+  if (want) CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return ILQG_OK;
+}
+
+int ilqg_upload_lq(ilqg_handle h, const float* A, const float* Bs, const float* Q, const float* l,
+                   const float* R, const float* r) {
+  ENTER(h);
+  if (!A || !Bs || !Q || !l || !R || !r) return ILQG_ERR_INVALID_ARGUMENT;
+  const DevDesc& d = h->d;
+  int rc;
+  if ((rc = UploadRecordField(h, d.offA, d.n * d.n, A)) != ILQG_OK) return rc;
+  if ((rc = UploadRecordField(h, d.offB, d.n * d.M, Bs)) != ILQG_OK) return rc;
+  if ((rc = UploadRecordField(h, d.offQ, d.N * d.n * d.n, Q)) != ILQG_OK) return rc;
+  if ((rc = UploadRecordField(h, d.offl, d.N * d.n, l)) != ILQG_OK) return rc;
+  if ((rc = UploadRecordField(h, d.offR, d.R_floats, R)) != ILQG_OK) return rc;
+  if ((rc = UploadRecordField(h, d.offr, d.r_floats, r)) != ILQG_OK) return rc;
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return ILQG_OK;
+}
+
+int ilqg_solve_begin(ilqg_handle h) {
+  ENTER(h);
+  return LaunchSolveBegin(h);
+}
+
+int ilqg_linearize_quadraticize(ilqg_handle h) {
+  ENTER(h);
+  return LaunchLqRecords(h, 0);
+}
+
+int ilqg_lq_backward(ilqg_handle h) {
+  ENTER(h);
+  return DispatchBackward(h, 0);
+}
+
+int ilqg_linesearch(ilqg_handle h) {
+  ENTER(h);
+  return LaunchLinesearch(h);
+}
+
+int ilqg_iterate(ilqg_handle h, int max_iters, int* iters_done) {
+  ENTER(h);
+  int rc;
+  for (int it = 0; it < max_iters; it++) {
+    if ((rc = LaunchLqRecords(h, 1)) != ILQG_OK) return rc;
+    if ((rc = DispatchBackward(h, 1)) != ILQG_OK) return rc;
+    if ((rc = LaunchLinesearch(h)) != ILQG_OK) return rc;
+  }
+  if (iters_done) {
+    std::vector<int> iters(h->B);
+    CUDA_TRY(cudaMemcpyAsync(iters.data(), h->s.iters, sizeof(int) * h->B, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    *iters_done = *std::max_element(iters.begin(), iters.end());
+  }
+  return ILQG_OK;
+}
+
+int ilqg_al_update(ilqg_handle h) {
+  ENTER(h);
+  k_al_update<<<h->B, ILQG_MAX_COSTS, 0, h->stream>>>(h->d, h->p, h->s);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ILQG_OK;
+}
+
+int ilqg_overwrite_solution(ilqg_handle h, int only_successful) {
+  ENTER(h);
+  k_overwrite_solution<<<h->B, 256, 0, h->stream>>>(h->d, h->s, only_successful);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ILQG_OK;
+}
+
+int ilqg_al_post_solve(ilqg_handle h) {
+  ENTER(h);
+  k_al_post_solve<<<h->B, 128, 0, h->stream>>>(h->d, h->p, h->s);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ILQG_OK;
+}
+
+int ilqg_download(ilqg_handle h, int what, void* dst, size_t bytes) {
+  ENTER(h);
+  if (!dst) return ILQG_ERR_INVALID_ARGUMENT;
+  const DevDesc& d = h->d;
+  const Slab& s = h->s;
+  const size_t T = d.T, n = d.n, M = d.M, N = d.N;
+  switch (what) {
+    case ILQG_XS: return DownloadParity(h, s.op_xs, s.op_cur, 0, T * n, dst, bytes);
+    case ILQG_US: return DownloadParity(h, s.op_us, s.op_cur, 0, T * M, dst, bytes);
+    case ILQG_PS: return DownloadParity(h, s.st_P, s.st_cur, 0, T * M * n, dst, bytes);
+    case ILQG_ALPHAS: return DownloadParity(h, s.st_a, s.st_cur, 0, T * M, dst, bytes);
+    case ILQG_LQ_PS: return DownloadParity(h, s.st_P, s.st_cur, 1, T * M * n, dst, bytes);
+    case ILQG_LQ_ALPHAS: return DownloadParity(h, s.st_a, s.st_cur, 1, T * M, dst, bytes);
+    case ILQG_LIN_A: return DownloadRecordField(h, d.offA, d.n * d.n, dst, bytes);
+    case ILQG_LIN_B: return DownloadRecordField(h, d.offB, d.n * d.M, dst, bytes);
+    case ILQG_QUAD_Q: return DownloadRecordField(h, d.offQ, d.N * d.n * d.n, dst, bytes);
+    case ILQG_QUAD_L: return DownloadRecordField(h, d.offl, d.N * d.n, dst, bytes);
+    case ILQG_QUAD_R: return DownloadRecordField(h, d.offR, d.R_floats, dst, bytes);
+    case ILQG_QUAD_RGRAD: return DownloadRecordField(h, d.offr, d.r_floats, dst, bytes);
+    case ILQG_DELTA_XS: return DownloadFlat(h, s.dxs, 4, T * n, dst, bytes);
+    case ILQG_LAMBDAS: return DownloadFlat(h, s.lambdas, 4, (size_t)d.num_constraints * T, dst, bytes);
+    case ILQG_TOTAL_COSTS: return DownloadFlat(h, s.total_costs, 4, N, dst, bytes);
+    case ILQG_X0: return DownloadFlat(h, s.x0, 4, n, dst, bytes);
+    case ILQG_MU: return DownloadFlat(h, s.mu, 4, 1, dst, bytes);
+    case ILQG_MERIT: return DownloadFlat(h, s.last_merit, 4, 1, dst, bytes);
+    case ILQG_EXPECTED_DECREASE: return DownloadFlat(h, s.expected_decrease, 4, 1, dst, bytes);
+    case ILQG_STEP: return DownloadFlat(h, s.step, 4, 1, dst, bytes);
+    case ILQG_MAX_CONSTRAINT_ERROR: return DownloadFlat(h, s.max_con_err, 4, 1, dst, bytes);
+    case ILQG_STATUS: return DownloadFlat(h, s.status, 4, 1, dst, bytes);
+    case ILQG_ITERS: return DownloadFlat(h, s.iters, 4, 1, dst, bytes);
+    case ILQG_BACKTRACKS: return DownloadFlat(h, s.backtracks, 4, 1, dst, bytes);
+    case ILQG_TIME_OF_EXTREME: return DownloadFlat(h, s.te_new, 4, N, dst, bytes);
+  }
+  return ILQG_ERR_INVALID_ARGUMENT;
+}
+
+int ilqg_synchronize(ilqg_handle h) {
+  ENTER(h);
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return ILQG_OK;
+}
+
+int ilqg_kernel_launches(ilqg_handle h, long long* out) {
+  if (!h || !out) return ILQG_ERR_BAD_HANDLE;
+  *out = h->launches;
+  return ILQG_OK;
+}
+
+}  // extern "C"

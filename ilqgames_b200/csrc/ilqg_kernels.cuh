@@ -1,0 +1,936 @@
+// ilqg_kernels.cuh -- the sm_100a kernels of the batched iLQ hot path.
+//
+//   k_linearize_quadraticize  K_lq : one warp per (instance, timestep) LQ record
+//   k_lq_backward             K_bwd: one warp per instance, coupled Riccati sweep with the
+//                                    running Z_i, zeta_i resident in shared memory, register-tiled
+//                                    F^T Z F, per-lane LU of the stacked S X = Y system,
+//                                    then the delta-x / expected-decrease forward sweep
+//   k_linesearch              K_ls : one G-lane tile per instance: rollout under the scaled
+//                                    strategies, gradient-only merit, Armijo, total costs
+//   k_solve_begin                    Solve() prologue (initial rollout + total costs)
+//
+// Data layout: instance-major slab; the LQ records [B][T][rec] hold
+// [A | B | Q_0..Q_{N-1} | l | R | r] contiguously so one (instance, timestep) is a single
+// 16-byte aligned chunk that a warp streams with 128-bit accesses.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "ilqg_device.cuh"
+
+namespace ilqg {
+namespace cg = cooperative_groups;
+
+struct Slab {
+  int B;
+  float* x0;                        // [B][n]
+  float* op_xs[2];                  // [B][T][n]   operating point double buffer
+  float* op_us[2];                  // [B][T][M]
+  float* st_P[2];                   // [B][T][M][n] strategies double buffer
+  float* st_a[2];                   // [B][T][M]
+  float *prob_xs, *prob_us, *prob_P, *prob_a;  // Problem's warm start
+  float* rec;                       // [B][T][rec]  LQ records
+  float* dxs;                       // [B][T][n]
+  float* lambdas;                   // [B][ncon][T]
+  float *mu, *last_merit, *expected_decrease, *step, *total_costs, *max_con_err;
+  int *status, *iters, *backtracks, *te_quad, *te_new, *op_cur, *st_cur;
+  const int* lambda_index;          // [T]  kk -> Constraint::TimeIndex
+};
+
+__device__ __forceinline__ int round4(int v) { return (v + 3) & ~3; }
+
+// ===========================================================================
+// K_lq: fused ComputeLinearization + ComputeCostQuadraticization
+// (src/ilq_solver.cpp:437-455, 471-490; PlayerCost::Quadraticize src/player_cost.cpp:194-225)
+// ===========================================================================
+constexpr int KLQ_WARPS = 4;
+
+__global__ void __launch_bounds__(KLQ_WARPS * 32)
+k_linearize_quadraticize(const __grid_constant__ DevDesc d, Slab s, int only_running) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * KLQ_WARPS + warp;
+  const int b = (int)(w / d.T), k = (int)(w % d.T);
+  if (b >= s.B) return;
+  if (only_running && s.status[b] != ILQG_STATUS_RUNNING) return;
+  const int n = d.n, M = d.M, N = d.N;
+  float* rec = smem + (size_t)warp * (d.rec + round4(n + M));
+  float* xu = rec + d.rec;
+  const int cur = s.op_cur[b];
+  const float* xs = s.op_xs[cur] + ((size_t)b * d.T + k) * n;
+  const float* us = s.op_us[cur] + ((size_t)b * d.T + k) * M;
+  for (int e = lane; e < n + M; e += 32) xu[e] = e < n ? xs[e] : us[e - n];
+  // LinearDynamicsApproximation ctor: A = I, B = 0 (linear_dynamics_approximation.h:65-70);
+  // QuadraticCostApproximation(xdim, state_reg): reg*I, zero grad (quadratic_cost_approximation.h:80-82)
+  for (int e = lane; e < d.rec; e += 32) rec[e] = 0.f;
+  __syncwarp();
+  for (int a = lane; a < n; a += 32) {
+    rec[d.offA + a * n + a] = 1.f;
+    for (int i = 0; i < N; i++) rec[d.offQ + (i * n + a) * n + a] = d.state_reg[i];
+  }
+  if (lane < d.num_pairs) {
+    const int mj = d.udim[d.pair_j[lane]];
+    for (int a = 0; a < mj; a++) rec[d.offR + d.pair_Roff[lane] + a * mj + a] = d.control_reg[d.pair_i[lane]];
+  }
+  __syncwarp();
+  const float* x = xu;
+  const float* u = xu + n;
+  if (lane < N) {
+    // player `lane`: its records in the reference's accumulation order
+    const int i = lane;
+    const bool full = d.cost_structure[i] == ILQG_COST_SUM || s.te_quad[(size_t)b * N + i] == k;
+    const float mu = s.mu[b];
+    for (int c = d.cost_begin[i]; c < d.cost_begin[i + 1]; c++) {
+      const DevCost& cd = d.cost[c];
+      const bool is_con = cd.slot >= 0;
+      if (!full && (cd.arg < 0 || is_con)) continue;  // QuadraticizeControlCosts
+      const float lambda =
+          is_con ? s.lambdas[((size_t)b * d.num_constraints + cd.slot) * d.T + s.lambda_index[k]] : 0.f;
+      if (cd.arg < 0)
+        quadraticize_record<true>(d, cd, x, n, lambda, mu, rec + d.offQ + i * n * n, n,
+                                  rec + d.offl + i * n);
+      else {
+        const int mj = d.udim[cd.arg];
+        quadraticize_record<true>(d, cd, u + d.uoff[cd.arg], mj, lambda, mu,
+                                  rec + d.offR + d.pair_Roff[cd.pair], mj,
+                                  rec + d.offr + d.pair_roff[cd.pair]);
+      }
+    }
+  } else if (lane - N < d.num_subsystems) {
+    subsystem_linearize(d, d.sub[lane - N], x, u, rec + d.offA, rec + d.offB);
+  }
+  __syncwarp();
+  float4* dst = reinterpret_cast<float4*>(s.rec + ((size_t)b * d.T + k) * d.rec);
+  const float4* src = reinterpret_cast<const float4*>(rec);
+  for (int e = lane; e < d.rec / 4; e += 32) dst[e] = src[e];
+}
+
+// ===========================================================================
+// small warp-level helpers
+// ===========================================================================
+__device__ __forceinline__ void warp_copy_f4(float* dst, const float* src, int floats, int lane) {
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  for (int e = lane; e < floats / 4; e += 32) d4[e] = __ldg(s4 + e);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// C tile of X^T Y for row-major NX x NX operands in shared memory.  Lane owns rows
+// [a0, a0+TR) x cols [c0, c0+TC) with TR = NX/8, TC = NX/4 (32 lanes cover the matrix).
+template <int NX>
+struct Tile {
+  static constexpr bool kTiled = (NX % 8 == 0) && NX >= 8;
+  static constexpr int TR = kTiled ? NX / 8 : 1;
+  static constexpr int TC = kTiled ? NX / 4 : 1;
+};
+
+template <int NX>
+__device__ __forceinline__ void mm_tn_tile(const float* __restrict__ X, const float* __restrict__ Y,
+                                           int a0, int c0, float (&acc)[Tile<NX>::TR][Tile<NX>::TC]) {
+  constexpr int TR = Tile<NX>::TR, TC = Tile<NX>::TC;
+#pragma unroll
+  for (int i = 0; i < TR; i++)
+#pragma unroll
+    for (int j = 0; j < TC; j++) acc[i][j] = 0.f;
+#pragma unroll 4
+  for (int q = 0; q < NX; q++) {
+    float xr[TR], yr[TC];
+#pragma unroll
+    for (int i = 0; i < TR; i++) xr[i] = X[q * NX + a0 + i];
+#pragma unroll
+    for (int j = 0; j < TC; j++) yr[j] = Y[q * NX + c0 + j];
+#pragma unroll
+    for (int i = 0; i < TR; i++)
+#pragma unroll
+      for (int j = 0; j < TC; j++) acc[i][j] = fmaf(xr[i], yr[j], acc[i][j]);
+  }
+}
+
+// ===========================================================================
+// K_bwd: LQFeedbackSolver::Solve (src/lq_feedback_solver.cpp:71-244) + ExpectedDecrease
+// (src/ilq_solver.cpp:364-398).  One warp per instance.
+// ===========================================================================
+constexpr int KBWD_WARPS = 4;
+
+template <int NX, int MU, int NP>
+struct BwdSmem {
+  static constexpr int Z = 0;
+  static constexpr int zeta = Z + ((NP * NX * NX + 3) & ~3);
+  static constexpr int F = zeta + ((NP * NX + 3) & ~3);
+  static constexpr int W = F + ((NX * NX + 3) & ~3);
+  static constexpr int BZ = W + ((NX * NX + 3) & ~3);
+  static constexpr int S = BZ + ((MU * NX + 3) & ~3);
+  static constexpr int Y = S + ((MU * MU + 3) & ~3);
+  static constexpr int beta = Y + ((MU * (NX + 1) + 3) & ~3);
+  static constexpr int tv = beta + ((NX + 3) & ~3);
+  static constexpr int rec = tv + ((NX + 3) & ~3);  // + d.rec (run time)
+};
+
+template <int NX, int MU, int NP>
+__global__ void __launch_bounds__(KBWD_WARPS * 32)
+k_lq_backward(const __grid_constant__ DevDesc d, const DevParams p, Slab s, int only_running) {
+  using L = BwdSmem<NX, MU, NP>;
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * KBWD_WARPS + warp;
+  if (b >= s.B) return;
+  if (only_running && s.status[b] != ILQG_STATUS_RUNNING) return;
+  const int T = d.T;
+  float* sm = smem + (size_t)warp * (L::rec + d.rec);
+  float* Z = sm + L::Z;
+  float* zeta = sm + L::zeta;
+  float* F = sm + L::F;
+  float* W = sm + L::W;
+  float* BZ = sm + L::BZ;
+  float* S = sm + L::S;
+  float* Y = sm + L::Y;
+  float* beta = sm + L::beta;
+  float* tv = sm + L::tv;
+  float* rec = sm + L::rec;
+  const float* A = rec + d.offA;
+  const float* Bm = rec + d.offB;
+  const float* Rk = rec + d.offR;
+  const float* rk = rec + d.offr;
+
+  // the quadraticization that follows this solve sees the newest extreme-time index
+  if (lane < NP) s.te_quad[(size_t)b * NP + lane] = s.te_new[(size_t)b * NP + lane];
+
+  const int cand = 1 - s.st_cur[b];
+  float* outP = s.st_P[cand] + (size_t)b * T * MU * NX;
+  float* outa = s.st_a[cand] + (size_t)b * T * MU;
+  const float* recb = s.rec + (size_t)b * T * d.rec;
+
+  // owner player and row offset of each stacked control row
+  int owner[MU], ro[MU];
+#pragma unroll
+  for (int c = 0; c < MU; c++) {
+    int o = 0;
+    for (int i = 1; i < NP; i++)
+      if (c >= d.uoff[i]) o = i;
+    owner[c] = o;
+    ro[c] = d.uoff[o];
+  }
+
+  // Z_i[T-1] = Q_i[T-1], zeta_i[T-1] = l_i[T-1]  (:102-105); strategy at T-1 stays zero
+  {
+    const float* last = recb + (size_t)(T - 1) * d.rec;
+    for (int e = lane; e < NP * NX * NX; e += 32) Z[e] = __ldg(last + d.offQ + e);
+    for (int e = lane; e < NP * NX; e += 32) zeta[e] = __ldg(last + d.offl + e);
+    for (int e = lane; e < MU * NX; e += 32) outP[(size_t)(T - 1) * MU * NX + e] = 0.f;
+    for (int e = lane; e < MU; e += 32) outa[(size_t)(T - 1) * MU + e] = 0.f;
+  }
+  __syncwarp();
+
+  constexpr int TR = Tile<NX>::TR, TC = Tile<NX>::TC;
+  const int a0 = (lane >> 2) * TR, c0 = (lane & 3) * TC;  // tiled path only
+
+  for (int kk = T - 2; kk >= 0; kk--) {
+    warp_copy_f4(rec, recb + (size_t)kk * d.rec, d.rec, lane);
+    __syncwarp();
+    // ---- BZ = B_i^T Z_i (:128) ----
+    for (int e = lane; e < MU * NX; e += 32) {
+      const int c = e / NX, col = e % NX;
+      int i = 0;
+#pragma unroll
+      for (int cc = 0; cc < MU; cc++)
+        if (cc == c) i = owner[cc];
+      const float* Zi = Z + i * NX * NX;
+      float acc = 0.f;
+#pragma unroll 4
+      for (int q = 0; q < NX; q++) acc = fmaf(Bm[q * MU + c], Zi[q * NX + col], acc);
+      BZ[e] = acc;
+    }
+    __syncwarp();
+    // ---- S (:131-149), Y (:152-157) ----
+    for (int e = lane; e < MU * MU + MU * (NX + 1); e += 32) {
+      if (e < MU * MU) {
+        const int c = e / MU, c2 = e % MU;
+        int i = 0, r0 = 0, i2 = 0;
+#pragma unroll
+        for (int cc = 0; cc < MU; cc++) {
+          if (cc == c) { i = owner[cc]; r0 = ro[cc]; }
+          if (cc == c2) i2 = owner[cc];
+        }
+        float acc = 0.f;
+#pragma unroll 4
+        for (int q = 0; q < NX; q++) acc = fmaf(BZ[c * NX + q], Bm[q * MU + c2], acc);
+        if (i == i2) {
+          const int pii = d.pair_of[i][i], mi = d.udim[i];
+          acc = acc + Rk[d.pair_Roff[pii] + (c - r0) * mi + (c2 - r0)];
+        }
+        S[e] = acc;
+      } else {
+        const int f = e - MU * MU;
+        const int c = f / (NX + 1), col = f % (NX + 1);
+        float acc = 0.f;
+        if (col < NX) {
+#pragma unroll 4
+          for (int q = 0; q < NX; q++) acc = fmaf(BZ[c * NX + q], A[q * NX + col], acc);
+        } else {
+          int i = 0, r0 = 0;
+#pragma unroll
+          for (int cc = 0; cc < MU; cc++)
+            if (cc == c) { i = owner[cc]; r0 = ro[cc]; }
+          const float* zi = zeta + i * NX;
+#pragma unroll 4
+          for (int q = 0; q < NX; q++) acc = fmaf(Bm[q * MU + c], zi[q], acc);
+          acc = acc + rk[d.pair_roff[d.pair_of[i][i]] + (c - r0)];
+        }
+        Y[f] = acc;
+      }
+    }
+    __syncwarp();
+    // ---- Gershgorin (:163-176) + solve S X = Y (:180) ----
+    // Every lane holds S in registers and eliminates redundantly; lane `col` owns RHS column
+    // `col` (NX state columns of P and the alpha column).  LU with partial pivoting replaces
+    // the reference's Householder QR (same solution up to rounding).
+    for (int col = lane; col < NX + 1; col += 32) {
+      float Sm[MU][MU], y[MU];
+#pragma unroll
+      for (int r = 0; r < MU; r++) {
+#pragma unroll
+        for (int c = 0; c < MU; c++) Sm[r][c] = S[r * MU + c];
+        y[r] = Y[r * (NX + 1) + col];
+      }
+      if (p.adaptive_regularization) {
+#pragma unroll
+        for (int c = 0; c < MU; c++) {
+          float col1 = 0.f;
+#pragma unroll
+          for (int r = 0; r < MU; r++) col1 += fabsf(Sm[r][c]);
+          const float radius = col1 - fabsf(Sm[c][c]);
+          const float eval_lo = Sm[c][c] - radius;
+          constexpr float min_eval = 1e-3;
+          if (eval_lo < min_eval) Sm[c][c] += radius + min_eval;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < MU; k++) {
+        int piv = k;
+        float best = fabsf(Sm[k][k]);
+#pragma unroll
+        for (int r = k + 1; r < MU; r++) {
+          const float v = fabsf(Sm[r][k]);
+          if (v > best) { best = v; piv = r; }
+        }
+#pragma unroll
+        for (int r = k + 1; r < MU; r++) {
+          if (piv == r) {
+#pragma unroll
+            for (int c = 0; c < MU; c++) { const float t = Sm[k][c]; Sm[k][c] = Sm[r][c]; Sm[r][c] = t; }
+            const float t = y[k]; y[k] = y[r]; y[r] = t;
+          }
+        }
+#pragma unroll
+        for (int r = k + 1; r < MU; r++) {
+          const float f = Sm[r][k] / Sm[k][k];
+#pragma unroll
+          for (int c = k + 1; c < MU; c++) Sm[r][c] = fmaf(-f, Sm[k][c], Sm[r][c]);
+          y[r] = fmaf(-f, y[k], y[r]);
+        }
+      }
+#pragma unroll
+      for (int r = MU - 1; r >= 0; r--) {
+        float acc = y[r];
+#pragma unroll
+        for (int c = r + 1; c < MU; c++) acc = fmaf(-Sm[r][c], y[c], acc);
+        y[r] = acc / Sm[r][r];
+      }
+#pragma unroll
+      for (int r = 0; r < MU; r++) {
+        Y[r * (NX + 1) + col] = y[r];  // X overwrites Y: rows = [P | alpha]
+        if (col < NX)
+          outP[((size_t)kk * MU + r) * NX + col] = y[r];
+        else
+          outa[(size_t)kk * MU + r] = y[r];
+      }
+    }
+    __syncwarp();
+    const float* X = Y;  // X[r*(NX+1)+c] = P[r][c]; X[r*(NX+1)+NX] = alpha[r]
+    // ---- F = A - sum B_i P_i ; beta = - sum B_i alpha_i (:189-194) ----
+    for (int e = lane; e < NX * NX + NX; e += 32) {
+      if (e < NX * NX) {
+        const int a = e / NX, c = e % NX;
+        float f = A[e];
+        // per-player subtraction, as F_ -= B_i * P_i
+        int i = 0;
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < MU; q++) {
+          if (owner[q] != i) { f -= acc; acc = 0.f; i = owner[q]; }
+          acc = fmaf(Bm[a * MU + q], X[q * (NX + 1) + c], acc);
+        }
+        f -= acc;
+        F[e] = f;
+      } else {
+        const int a = e - NX * NX;
+        float bsum = 0.f, acc = 0.f;
+        int i = 0;
+#pragma unroll
+        for (int q = 0; q < MU; q++) {
+          if (owner[q] != i) { bsum -= acc; acc = 0.f; i = owner[q]; }
+          acc = fmaf(Bm[a * MU + q], X[q * (NX + 1) + NX], acc);
+        }
+        bsum -= acc;
+        beta[a] = bsum;
+      }
+    }
+    __syncwarp();
+    // ---- Z_i, zeta_i update (:197-213) ----
+#pragma unroll 1
+    for (int i = 0; i < NP; i++) {
+      float* Zi = Z + i * NX * NX;
+      float* zi = zeta + i * NX;
+      const float* Qi = rec + d.offQ + i * NX * NX;
+      const float* li = rec + d.offl + i * NX;
+      // tv = zeta_next + Z_next beta
+      for (int a = lane; a < NX; a += 32) {
+        float acc = 0.f;
+#pragma unroll 4
+        for (int q = 0; q < NX; q++) acc = fmaf(Zi[a * NX + q], beta[q], acc);
+        tv[a] = zi[a] + acc;
+      }
+      __syncwarp();
+      // zeta = F^T tv + l  (+ control terms)
+      for (int a = lane; a < NX; a += 32) {
+        float acc = 0.f;
+#pragma unroll 4
+        for (int q = 0; q < NX; q++) acc = fmaf(F[q * NX + a], tv[q], acc);
+        float znew = acc + li[a];
+        for (int j = 0; j < NP; j++) {
+          const int pr = d.pair_of[i][j];
+          if (pr < 0) continue;
+          const int mj = d.udim[j], co = d.uoff[j];
+          const float* Rij = Rk + d.pair_Roff[pr];
+          const float* rij = rk + d.pair_roff[pr];
+          float t = 0.f;
+          for (int q = 0; q < mj; q++) {
+            float v = 0.f;
+            for (int q2 = 0; q2 < mj; q2++) v = fmaf(Rij[q * mj + q2], X[(co + q2) * (NX + 1) + NX], v);
+            v -= rij[q];
+            t = fmaf(X[(co + q) * (NX + 1) + a], v, t);
+          }
+          znew += t;
+        }
+        zi[a] = znew;
+      }
+      // Z = (F^T Z_next) F + Q (+ P_j^T R_ij P_j)
+      if constexpr (Tile<NX>::kTiled) {
+        float acc[TR][TC];
+        mm_tn_tile<NX>(F, Zi, a0, c0, acc);  // W = F^T Z   (tile rows a0.., cols c0..)
+        // store W transposed so the second product is again an X^T Y form
+#pragma unroll
+        for (int ii = 0; ii < TR; ii++)
+#pragma unroll
+          for (int jj = 0; jj < TC; jj++) W[(c0 + jj) * NX + a0 + ii] = acc[ii][jj];
+        __syncwarp();
+        mm_tn_tile<NX>(W, F, a0, c0, acc);   // (W^T)^T F = W F
+#pragma unroll
+        for (int ii = 0; ii < TR; ii++)
+#pragma unroll
+          for (int jj = 0; jj < TC; jj++) acc[ii][jj] = acc[ii][jj] + Qi[(a0 + ii) * NX + c0 + jj];
+        for (int j = 0; j < NP; j++) {
+          const int pr = d.pair_of[i][j];
+          if (pr < 0) continue;
+          const int mj = d.udim[j], co = d.uoff[j];
+          const float* Rij = Rk + d.pair_Roff[pr];
+#pragma unroll
+          for (int ii = 0; ii < TR; ii++)
+#pragma unroll
+            for (int jj = 0; jj < TC; jj++) {
+              float t = 0.f;
+              for (int q2 = 0; q2 < mj; q2++) {
+                float ptr = 0.f;  // (P_j^T R_ij)[a][q2]
+                for (int q = 0; q < mj; q++)
+                  ptr = fmaf(X[(co + q) * (NX + 1) + a0 + ii], Rij[q * mj + q2], ptr);
+                t = fmaf(ptr, X[(co + q2) * (NX + 1) + c0 + jj], t);
+              }
+              acc[ii][jj] += t;
+            }
+        }
+        __syncwarp();  // all lanes finished reading Zi (first product) before overwrite
+#pragma unroll
+        for (int ii = 0; ii < TR; ii++)
+#pragma unroll
+          for (int jj = 0; jj < TC; jj++) Zi[(a0 + ii) * NX + c0 + jj] = acc[ii][jj];
+      } else {
+        for (int e = lane; e < NX * NX; e += 32) {
+          const int a = e / NX, c = e % NX;
+          float acc = 0.f;
+          for (int q = 0; q < NX; q++) acc = fmaf(F[q * NX + a], Zi[q * NX + c], acc);
+          W[e] = acc;
+        }
+        __syncwarp();
+        float znew[(NX * NX + 31) / 32];
+        int cnt = 0;
+        for (int e = lane; e < NX * NX; e += 32, cnt++) {
+          const int a = e / NX, c = e % NX;
+          float acc = 0.f;
+          for (int q = 0; q < NX; q++) acc = fmaf(W[a * NX + q], F[q * NX + c], acc);
+          acc = acc + Qi[e];
+          for (int j = 0; j < NP; j++) {
+            const int pr = d.pair_of[i][j];
+            if (pr < 0) continue;
+            const int mj = d.udim[j], co = d.uoff[j];
+            const float* Rij = Rk + d.pair_Roff[pr];
+            float t = 0.f;
+            for (int q2 = 0; q2 < mj; q2++) {
+              float ptr = 0.f;
+              for (int q = 0; q < mj; q++) ptr = fmaf(X[(co + q) * (NX + 1) + a], Rij[q * mj + q2], ptr);
+              t = fmaf(ptr, X[(co + q2) * (NX + 1) + c], t);
+            }
+            acc += t;
+          }
+          znew[cnt] = acc;
+        }
+        __syncwarp();
+        cnt = 0;
+        for (int e = lane; e < NX * NX; e += 32, cnt++) Zi[e] = znew[cnt];
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- forward sweep: delta_xs (:217-241, x0 argument = 0) and ExpectedDecrease ----
+  float* dx = beta;  // reuse
+  float* dxn = tv;
+  for (int a = lane; a < NX; a += 32) dx[a] = 0.f;
+  float expected_decrease = 0.f;
+  float* dxs = s.dxs + (size_t)b * T * NX;
+  __syncwarp();
+  for (int kk = 0; kk < T; kk++) {
+    warp_copy_f4(rec, recb + (size_t)kk * d.rec, d.rec, lane);
+    for (int e = lane; e < MU; e += 32) S[e] = outa[(size_t)kk * MU + e];  // alpha_k
+    for (int a = lane; a < NX; a += 32) dxs[(size_t)kk * NX + a] = dx[a];
+    __syncwarp();
+    for (int i = 0; i < NP; i++) {
+      const int mi = d.udim[i], r0 = d.uoff[i], pii = d.pair_of[i][i];
+      const float* Rii = Rk + d.pair_Roff[pii];
+      const float* rii = rk + d.pair_roff[pii];
+      float t1 = 0.f;  // (alpha^T R_ii) r_ii, tiny: every lane computes it
+      for (int c = 0; c < mi; c++) {
+        float row = 0.f;
+        for (int a = 0; a < mi; a++) row = fmaf(S[r0 + a], Rii[a * mi + c], row);
+        t1 = fmaf(row, rii[c], t1);
+      }
+      expected_decrease -= t1;
+      if (kk > 0) {
+        const float* Qi = rec + d.offQ + i * NX * NX;
+        const float* li = rec + d.offl + i * NX;
+        float part = 0.f;
+        for (int c = lane; c < NX; c += 32) {
+          float row = 0.f;
+#pragma unroll 4
+          for (int a = 0; a < NX; a++) row = fmaf(dx[a], Qi[a * NX + c], row);
+          part = fmaf(row, li[c], part);
+        }
+        expected_decrease -= warp_sum(part);
+      }
+    }
+    // dx_next = A dx - sum_i B_i alpha_i   (no feedback term)
+    for (int a = lane; a < NX; a += 32) {
+      float acc = 0.f;
+#pragma unroll 4
+      for (int q = 0; q < NX; q++) acc = fmaf(A[a * NX + q], dx[q], acc);
+      int i = 0;
+      float pacc = 0.f;
+#pragma unroll
+      for (int q = 0; q < MU; q++) {
+        if (owner[q] != i) { acc -= pacc; pacc = 0.f; i = owner[q]; }
+        pacc = fmaf(Bm[a * MU + q], S[q], pacc);
+      }
+      acc -= pacc;
+      dxn[a] = acc;
+    }
+    __syncwarp();
+    for (int a = lane; a < NX; a += 32) dx[a] = dxn[a];
+    __syncwarp();
+  }
+  if (lane == 0) s.expected_decrease[b] = expected_decrease;
+}
+
+// ===========================================================================
+// K_ls and the Solve() prologue: tile-per-instance rollout, merit, Armijo, total costs
+// ===========================================================================
+template <int G>
+using TileG = cg::thread_block_tile<G>;
+
+// ILQSolver::CurrentOperatingPoint (src/ilq_solver.cpp:174-206) with Strategy::operator()
+// (strategy.h:73-76) and Integrate (multi_player_dynamical_system.cpp:52-77).
+// sm: x[n] | dx[n] | u[M].  alpha is scaled on the fly exactly as ScaleAlphas would have
+// (alpha * s0, then * rho nscale times).
+template <int G>
+__device__ void rollout(const TileG<G>& tile, const DevDesc& d, float* sm, const float* last_xs,
+                        const float* last_us, const float* x_start, const float* P,
+                        const float* alpha, bool scaled, float s0, float rho, int nscale,
+                        float* out_xs, float* out_us) {
+  const int n = d.n, M = d.M, T = d.T, t = tile.thread_rank();
+  float* x = sm;
+  float* dx = sm + n;
+  float* u = sm + 2 * n;
+  const float dt_half = (float)(d.time_step / 2.0);
+  for (int a = t; a < n; a += G) x[a] = x_start[a];
+  tile.sync();
+  for (int kk = 0; kk < T; kk++) {
+    for (int a = t; a < n; a += G) {
+      const float xv = x[a];
+      // last_operating_point.xs[0] was set to the start state (ilq_solver.cpp:88-89)
+      const float ref = kk == 0 ? x_start[a] : last_xs[(size_t)kk * n + a];
+      dx[a] = xv - ref;
+      out_xs[(size_t)kk * n + a] = xv;
+    }
+    tile.sync();
+    for (int c = t; c < M; c += G) {
+      const float* Prow = P + ((size_t)kk * M + c) * n;
+      float acc = 0.f;
+      for (int a = 0; a < n; a++) acc = fmaf(Prow[a], dx[a], acc);
+      float al = alpha[(size_t)kk * M + c];
+      if (scaled) {
+        al *= s0;
+        for (int j = 0; j < nscale; j++) al *= rho;
+      }
+      const float uv = last_us[(size_t)kk * M + c] - acc - al;
+      u[c] = uv;
+      out_us[(size_t)kk * M + c] = uv;
+    }
+    tile.sync();
+    if (kk < T - 1) {
+      for (int sidx = t; sidx < d.num_subsystems; sidx += G) {
+        const DevSubsystem& sub = d.sub[sidx];
+        const int xd = subsystem_xdim(sub.kind);
+        float xl[6];
+#pragma unroll
+        for (int a = 0; a < 6; a++) xl[a] = a < xd ? x[sub.x_offset + a] : 0.f;
+        const float u0 = u[sub.u_offset];
+        const float u1 = sub.kind == ILQG_DYN_AIR3D ? u[sub.u_offset2] : u[sub.u_offset + 1];
+        subsystem_integrate(sub, dt_half, xl, u0, u1);
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+          if (a < xd) x[sub.x_offset + a] = xl[a];
+      }
+    }
+    tile.sync();
+  }
+}
+
+// Per-timestep gradients of every player's cost (gradient half of PlayerCost::Quadraticize),
+// one thread per timestep; returns through terms[kk][2i] = |r_ii|^2, terms[kk][2i+1] = [kk>0]|l_i|^2
+// (ILQSolver::MeritFunction src/ilq_solver.cpp:400-435).
+template <int NXMAX, int NPMAX>
+__device__ void merit_terms_step(const DevDesc& d, const Slab& s, int b, int kk, const float* x,
+                                 const float* u, float* terms) {
+  float l[NPMAX * NXMAX];
+  float r[ILQG_MAX_UDIM * ILQG_MAX_PLAYERS];
+  const int n = d.n, N = d.N;
+  for (int e = 0; e < N * n; e++) l[e] = 0.f;
+  for (int e = 0; e < d.r_floats; e++) r[e] = 0.f;
+  const float mu = s.mu[b];
+  for (int i = 0; i < N; i++) {
+    const bool full = d.cost_structure[i] == ILQG_COST_SUM || s.te_quad[(size_t)b * N + i] == kk;
+    for (int c = d.cost_begin[i]; c < d.cost_begin[i + 1]; c++) {
+      const DevCost& cd = d.cost[c];
+      const bool is_con = cd.slot >= 0;
+      if (!full && (cd.arg < 0 || is_con)) continue;
+      const float lambda =
+          is_con ? s.lambdas[((size_t)b * d.num_constraints + cd.slot) * d.T + s.lambda_index[kk]] : 0.f;
+      if (cd.arg < 0)
+        quadraticize_record<false>(d, cd, x, n, lambda, mu, nullptr, 0, l + i * n);
+      else
+        quadraticize_record<false>(d, cd, u + d.uoff[cd.arg], d.udim[cd.arg], lambda, mu, nullptr, 0,
+                                   r + d.pair_roff[cd.pair]);
+    }
+  }
+  for (int i = 0; i < N; i++) {
+    const int pii = d.pair_of[i][i], mi = d.udim[i];
+    float sq = 0.f;
+    for (int a = 0; a < mi; a++) sq = fmaf(r[d.pair_roff[pii] + a], r[d.pair_roff[pii] + a], sq);
+    terms[kk * 2 * N + 2 * i] = sq;
+    float sq2 = 0.f;
+    if (kk > 0)
+      for (int a = 0; a < n; a++) sq2 = fmaf(l[i * n + a], l[i * n + a], sq2);
+    terms[kk * 2 * N + 2 * i + 1] = sq2;
+  }
+}
+
+template <int G, int NXMAX, int NPMAX>
+__device__ float merit_function(const TileG<G>& tile, const DevDesc& d, const Slab& s, int b,
+                                const float* xs, const float* us, float* terms) {
+  const int t = tile.thread_rank();
+  for (int kk = t; kk < d.T; kk += G)
+    merit_terms_step<NXMAX, NPMAX>(d, s, b, kk, xs + (size_t)kk * d.n, us + (size_t)kk * d.M, terms);
+  tile.sync();
+  float merit = 0.f;
+  if (t == 0) {
+    // single running fp32 accumulator in (k, i) order, as the reference
+    const int cnt = d.T * 2 * d.N;
+    for (int e = 0; e < cnt; e++) merit += terms[e];
+    merit = 0.5 * merit;
+  }
+  merit = tile.shfl(merit, 0);
+  tile.sync();
+  return merit;
+}
+
+// ILQSolver::TotalCosts, src/ilq_solver.cpp:220-257 (+ PlayerCost::Evaluate player_cost.cpp:128-144):
+// costs only, no constraints; first extreme wins (strict comparisons).
+template <int G>
+__device__ void total_costs(const TileG<G>& tile, const DevDesc& d, const Slab& s, int b,
+                            const float* xs, const float* us, float* vals) {
+  const int t = tile.thread_rank(), n = d.n, M = d.M, N = d.N;
+  for (int kk = t; kk < d.T; kk += G) {
+    const float* x = xs + (size_t)kk * n;
+    const float* u = us + (size_t)kk * M;
+    for (int i = 0; i < N; i++) {
+      float total = 0.f;
+      for (int c = d.cost_begin[i]; c < d.cost_begin[i + 1]; c++) {
+        const DevCost& cd = d.cost[c];
+        if (cd.slot >= 0) continue;
+        total += cd.arg < 0 ? evaluate_record(d, cd, x, n)
+                            : evaluate_record(d, cd, u + d.uoff[cd.arg], d.udim[cd.arg]);
+      }
+      vals[kk * N + i] = total;
+    }
+  }
+  tile.sync();
+  for (int i = t; i < N; i += G) {
+    const int cs = d.cost_structure[i];
+    float total = cs == ILQG_COST_SUM ? 0.f : cs == ILQG_COST_MAX ? -INFINITY : INFINITY;
+    int te = s.te_new[(size_t)b * N + i];
+    for (int kk = 0; kk < d.T; kk++) {
+      const float cur = vals[kk * N + i];
+      if (cs == ILQG_COST_SUM)
+        total += cur;
+      else if (cs == ILQG_COST_MAX && cur > total) {
+        total = cur;
+        te = kk;
+      } else if (cs == ILQG_COST_MIN && cur < total) {
+        total = cur;
+        te = kk;
+      }
+    }
+    s.total_costs[(size_t)b * N + i] = total;
+    s.te_new[(size_t)b * N + i] = te;
+  }
+  tile.sync();
+}
+
+template <int G>
+__device__ __forceinline__ float* tile_smem(float* smem, const DevDesc& d, int tile_in_block) {
+  const int per = round4(2 * d.n + d.M) + round4(d.T * 2 * d.N);
+  return smem + (size_t)tile_in_block * per;
+}
+
+constexpr int KLS_THREADS = 128;
+
+// ILQSolver::Solve prologue, src/ilq_solver.cpp:86-107.
+template <int G, int NXMAX, int NPMAX>
+__global__ void __launch_bounds__(KLS_THREADS)
+k_solve_begin(const __grid_constant__ DevDesc d, const DevParams p, Slab s) {
+  extern __shared__ __align__(16) float smem[];
+  cg::thread_block block = cg::this_thread_block();
+  TileG<G> tile = cg::tiled_partition<G>(block);
+  const int b = blockIdx.x * (KLS_THREADS / G) + tile.meta_group_rank();
+  if (b >= s.B) return;
+  float* sm = tile_smem<G>(smem, d, tile.meta_group_rank());
+  float* scratch = sm + round4(2 * d.n + d.M);
+  const int T = d.T, n = d.n, M = d.M, t = tile.thread_rank();
+  // current strategies <- problem strategies
+  float* P0 = s.st_P[0] + (size_t)b * T * M * n;
+  float* a0 = s.st_a[0] + (size_t)b * T * M;
+  const float* pP = s.prob_P + (size_t)b * T * M * n;
+  const float* pa = s.prob_a + (size_t)b * T * M;
+  for (int e = t; e < T * M * n; e += G) P0[e] = pP[e];
+  for (int e = t; e < T * M; e += G) a0[e] = pa[e];
+  tile.sync();
+  float* oxs = s.op_xs[0] + (size_t)b * T * n;
+  float* ous = s.op_us[0] + (size_t)b * T * M;
+  rollout<G>(tile, d, sm, s.prob_xs + (size_t)b * T * n, s.prob_us + (size_t)b * T * M,
+             s.x0 + (size_t)b * n, pP, pa, false, 1.f, 1.f, 0, oxs, ous);
+  total_costs<G>(tile, d, s, b, oxs, ous, scratch);
+  if (t == 0) {
+    s.op_cur[b] = 0;
+    s.st_cur[b] = 0;
+    s.iters[b] = 0;
+    s.status[b] = p.max_solver_iters > 0 ? ILQG_STATUS_RUNNING : ILQG_STATUS_MAX_ITERS;
+  }
+  for (int i = t; i < d.N; i += G) s.te_quad[(size_t)b * d.N + i] = s.te_new[(size_t)b * d.N + i];
+}
+
+// ILQSolver::ModifyLQStrategies (src/ilq_solver.cpp:289-348) + TotalCosts (:158) + loop exit
+// bookkeeping (:123-124, 168-171).
+template <int G, int NXMAX, int NPMAX>
+__global__ void __launch_bounds__(KLS_THREADS)
+k_linesearch(const __grid_constant__ DevDesc d, const DevParams p, Slab s) {
+  extern __shared__ __align__(16) float smem[];
+  cg::thread_block block = cg::this_thread_block();
+  TileG<G> tile = cg::tiled_partition<G>(block);
+  const int b = blockIdx.x * (KLS_THREADS / G) + tile.meta_group_rank();
+  if (b >= s.B) return;
+  if (s.status[b] != ILQG_STATUS_RUNNING) return;
+  float* sm = tile_smem<G>(smem, d, tile.meta_group_rank());
+  float* scratch = sm + round4(2 * d.n + d.M);
+  const int T = d.T, n = d.n, M = d.M, t = tile.thread_rank();
+  const int cur = s.op_cur[b], scur = s.st_cur[b];
+  const float* last_xs = s.op_xs[cur] + (size_t)b * T * n;
+  const float* last_us = s.op_us[cur] + (size_t)b * T * M;
+  float* cxs = s.op_xs[1 - cur] + (size_t)b * T * n;
+  float* cus = s.op_us[1 - cur] + (size_t)b * T * M;
+  const float* P = s.st_P[1 - scur] + (size_t)b * T * M * n;
+  float* alpha = s.st_a[1 - scur] + (size_t)b * T * M;
+  const float ed = s.expected_decrease[b];
+  const float lm = s.last_merit[b];
+  const float s0 = p.initial_alpha_scaling, rho = p.geometric_alpha_scaling;
+  float step = s0;
+  int nscale = 0, nroll = 1;
+  bool accept = false, converged = false;
+  float new_merit = lm;
+  rollout<G>(tile, d, sm, last_xs, last_us, last_xs, P, alpha, true, s0, rho, 0, cxs, cus);
+  if (!p.linesearch) {
+    accept = true;
+  } else {
+    for (int ii = 0; ii < p.max_backtracking_steps; ii++) {
+      const float merit = merit_function<G, NXMAX, NPMAX>(tile, d, s, b, cxs, cus, scratch);
+      // CheckArmijoCondition :350-362
+      const float scaled_expected_decrease = p.expected_decrease_fraction * step * ed;
+      if (lm - merit >= scaled_expected_decrease) {
+        accept = true;
+        converged = (merit <= lm) && fabsf(lm - merit) < p.convergence_tolerance;  // ilq_solver.h:126-130
+        new_merit = merit;
+        break;
+      }
+      nscale++;
+      step *= rho;
+      rollout<G>(tile, d, sm, last_xs, last_us, last_xs, P, alpha, true, s0, rho, nscale, cxs, cus);
+      nroll++;
+    }
+  }
+  if (accept) {
+    // the scaled LQ strategies become the current strategies
+    for (int e = t; e < T * M; e += G) {
+      float al = alpha[e] * s0;
+      for (int j = 0; j < nscale; j++) al *= rho;
+      alpha[e] = al;
+    }
+    tile.sync();
+    total_costs<G>(tile, d, s, b, cxs, cus, scratch);
+  }
+  if (t == 0) {
+    const int it = s.iters[b] + 1;
+    s.iters[b] = it;
+    s.backtracks[b] += nroll;
+    if (accept) {
+      s.op_cur[b] = 1 - cur;
+      s.st_cur[b] = 1 - scur;
+      s.last_merit[b] = new_merit;
+      s.step[b] = step;
+      if (converged && !p.disable_convergence_exit)
+        s.status[b] = ILQG_STATUS_CONVERGED;
+      else if (it >= p.max_solver_iters)
+        s.status[b] = ILQG_STATUS_MAX_ITERS;
+    } else {
+      s.status[b] = ILQG_STATUS_LINESEARCH_FAILED;  // the log's final iterate stays current
+    }
+  }
+}
+
+// ===========================================================================
+// small utility kernels
+// ===========================================================================
+// dst[b][e] = (sel[b] ^ flip ? src1 : src0)[b][e]
+__global__ void k_gather_parity(float* dst, const float* src0, const float* src1, const int* sel,
+                                int flip, size_t per, int B) {
+  const size_t total = per * (size_t)B;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(e / per);
+    dst[e] = ((sel[b] ^ flip) ? src1 : src0)[e];
+  }
+}
+
+// Problem::OverwriteSolution (src/problem.cpp:188-194): prob <- current, optionally only
+// for instances whose last solve did not fail.
+__global__ void k_overwrite_solution(const __grid_constant__ DevDesc d, Slab s, int only_successful) {
+  const int b = blockIdx.x;
+  if (only_successful && s.status[b] == ILQG_STATUS_LINESEARCH_FAILED) return;
+  const int T = d.T, n = d.n, M = d.M, cur = s.op_cur[b], scur = s.st_cur[b];
+  const size_t ox = (size_t)b * T * n, ou = (size_t)b * T * M, oP = (size_t)b * T * M * n;
+  for (int e = threadIdx.x; e < T * n; e += blockDim.x) s.prob_xs[ox + e] = s.op_xs[cur][ox + e];
+  for (int e = threadIdx.x; e < T * M; e += blockDim.x) {
+    s.prob_us[ou + e] = s.op_us[cur][ou + e];
+    s.prob_a[ou + e] = s.st_a[scur][ou + e];
+  }
+  for (int e = threadIdx.x; e < T * M * n; e += blockDim.x) s.prob_P[oP + e] = s.st_P[scur][oP + e];
+}
+
+// upload_warmstart mirrors the problem solution into the working buffers
+__global__ void k_prob_to_working(const __grid_constant__ DevDesc d, Slab s) {
+  const int b = blockIdx.x;
+  const int T = d.T, n = d.n, M = d.M;
+  const size_t ox = (size_t)b * T * n, ou = (size_t)b * T * M, oP = (size_t)b * T * M * n;
+  for (int e = threadIdx.x; e < T * n; e += blockDim.x) s.op_xs[0][ox + e] = s.prob_xs[ox + e];
+  for (int e = threadIdx.x; e < T * M; e += blockDim.x) {
+    s.op_us[0][ou + e] = s.prob_us[ou + e];
+    s.st_a[0][ou + e] = s.prob_a[ou + e];
+  }
+  for (int e = threadIdx.x; e < T * M * n; e += blockDim.x) s.st_P[0][oP + e] = s.prob_P[oP + e];
+  if (threadIdx.x == 0) {
+    s.op_cur[b] = 0;
+    s.st_cur[b] = 0;
+  }
+}
+
+// One augmented-Lagrangian multiplier sweep, src/augmented_lagrangian_solver.cpp:113-143,
+// one thread per (instance, constraint): lambda <- max(0, lambda + mu g) visiting kk in order
+// so the duplicated TimeIndex slots are incremented twice, exactly as the reference.
+__global__ void k_al_update(const __grid_constant__ DevDesc d, const DevParams p, Slab s) {
+  const int b = blockIdx.x;
+  __shared__ float smax[ILQG_MAX_COSTS];
+  const int cidx = threadIdx.x;
+  float max_err = -INFINITY;
+  if (cidx < d.num_costs && d.cost[cidx].slot >= 0) {
+    const DevCost& cd = d.cost[cidx];
+    const int cur = s.op_cur[b];
+    const float mu = s.mu[b];
+    float* lam = s.lambdas + ((size_t)b * d.num_constraints + cd.slot) * d.T;
+    for (int kk = 0; kk < d.T; kk++) {
+      const float* x = s.op_xs[cur] + ((size_t)b * d.T + kk) * d.n;
+      const float* u = s.op_us[cur] + ((size_t)b * d.T + kk) * d.M;
+      const float g = cd.arg < 0 ? evaluate_record(d, cd, x, d.n)
+                                 : evaluate_record(d, cd, u + d.uoff[cd.arg], d.udim[cd.arg]);
+      max_err = fmaxf(max_err, g);
+      const int li = s.lambda_index[kk];
+      const float new_lambda = lam[li] + mu * g;  // Constraint::IncrementLambda constraint.h:98-102
+      lam[li] = cd.is_equality ? new_lambda : fmaxf(0.0f, new_lambda);
+    }
+  }
+  if (cidx < ILQG_MAX_COSTS) smax[cidx] = max_err;
+  __syncthreads();
+  if (cidx == 0) {
+    float m = -INFINITY;
+    for (int c = 0; c < d.num_costs; c++) m = fmaxf(m, smax[c]);
+    s.max_con_err[b] = m;
+    s.mu[b] = s.mu[b] * p.geometric_mu_scaling;  // Constraint::ScaleMu :143
+  }
+}
+
+// src/augmented_lagrangian_solver.cpp:165-178
+__global__ void k_al_post_solve(const __grid_constant__ DevDesc d, const DevParams p, Slab s) {
+  const int b = blockIdx.x;
+  if (s.status[b] != ILQG_STATUS_LINESEARCH_FAILED) return;
+  const int cnt = d.num_constraints * d.T;
+  for (int e = threadIdx.x; e < cnt; e += blockDim.x)
+    s.lambdas[(size_t)b * cnt + e] *= p.geometric_lambda_downscaling;
+  if (threadIdx.x == 0) s.mu[b] *= p.geometric_mu_downscaling;
+}
+
+__global__ void k_fill(float* p, float v, size_t count) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < count;
+       e += (size_t)gridDim.x * blockDim.x)
+    p[e] = v;
+}
+
+}  // namespace ilqg

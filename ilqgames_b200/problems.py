@@ -289,17 +289,26 @@ def roundabout_merging(num_time_steps: int = 100, time_step: float = 0.1):
 
 
 def roundabout_x0_batch(batch: int, seed: int) -> np.ndarray:
-    """SURVEY section 8d input #3: each car U(0,10) m back along its first lane segment,
-    speed U(1,4)."""
+    """Synthetic initial states for RoundaboutMerging: each car U(0,8) m FORWARD along its
+    first lane segment (all first segments are >= 10 m long) with a lateral offset U(-1,1) m,
+    heading of the segment, speed U(1,4) m/s.
+
+    SURVEY section 8d proposed "U(0,10) m back along the first segment"; that puts every car
+    exactly on the axis behind the polyline's first point, where the reference's signed
+    distance is sgn(cross product ~ 0) * d^2 (src/line_segment2.cpp:56-100), i.e. decided by
+    rounding noise, so fp32 implementations legitimately disagree on which lane-boundary cost
+    is active.  The forward/lateral placement is well posed.
+    """
     desc, x0 = roundabout_merging()
     rng = np.random.default_rng(seed)
     out = np.tile(x0, (batch, 1)).astype(F)
-    back = rng.uniform(0.0, 10.0, size=(batch, 4)).astype(F)
+    fwd = rng.uniform(0.0, 8.0, size=(batch, 4)).astype(F)
+    lat = rng.uniform(-1.0, 1.0, size=(batch, 4)).astype(F)
     spd = rng.uniform(1.0, 4.0, size=(batch, 4)).astype(F)
     for i in range(4):
         th = out[:, 6 * i + 2]
-        out[:, 6 * i + 0] -= back[:, i] * np.cos(th)
-        out[:, 6 * i + 1] -= back[:, i] * np.sin(th)
+        out[:, 6 * i + 0] += fwd[:, i] * np.cos(th) - lat[:, i] * np.sin(th)
+        out[:, 6 * i + 1] += fwd[:, i] * np.sin(th) + lat[:, i] * np.cos(th)
         out[:, 6 * i + 4] = spd[:, i]
     return out
 

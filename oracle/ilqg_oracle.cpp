@@ -273,7 +273,12 @@ struct Instance {
   real mu;
   real last_merit, expected_decrease, step;
   std::vector<real> total_costs;
-  std::vector<int> time_of_extreme;  // used by quadraticization
+  // PlayerCost::time_of_extreme_cost_ (player_cost.h:151) seen from two places: TotalCosts
+  // writes te_new; quadraticization reads te_quad.  te_quad <- te_new right before each LQ
+  // solve, which reproduces the reference's ordering: the quadraticization an LQ solve
+  // consumes was computed inside the previous MeritFunction call, i.e. BEFORE the TotalCosts
+  // call that followed it (src/ilq_solver.cpp:146,158).
+  std::vector<int> te_quad, te_new;
   int status, iters, backtracks;
   real max_constraint_error;
 };
@@ -784,7 +789,7 @@ void QuadraticizeStep(const Problem& pr, const Instance& in, int kk, const real*
   for (int c = 0; c < d.num_costs; c++) {
     const ilqg_cost_desc& cd = d.costs[c];
     const int i = cd.player;
-    const bool full = d.cost_structure[i] == ILQG_COST_SUM || in.time_of_extreme[i] == kk;
+    const bool full = d.cost_structure[i] == ILQG_COST_SUM || in.te_quad[i] == kk;
     const int slot = pr.constraint_slot[c];
     const bool is_con = slot >= 0;
     // QuadraticizeControlCosts keeps only control COSTS (no constraints).
@@ -831,11 +836,11 @@ void TotalCosts(const Problem& pr, Instance& in) {
         in.total_costs[i] += cur;
       else if (cs == ILQG_COST_MAX && cur > in.total_costs[i]) {
         in.total_costs[i] = cur;
-        in.time_of_extreme[i] = kk;
+        in.te_new[i] = kk;
       } else if (cs == ILQG_COST_MIN) {
         if (cur < in.total_costs[i]) {
           in.total_costs[i] = cur;
-          in.time_of_extreme[i] = kk;
+          in.te_new[i] = kk;
         }
       }
     }
@@ -864,15 +869,21 @@ void Rollout(const Problem& pr, const real* last_xs, const real* last_us, const 
   }
 }
 
-void LinearizeQuadraticize(const Problem& pr, Instance& in) {
+// ILQSolver::ComputeLinearization, src/ilq_solver.cpp:437-455
+void LinearizeAll(const Problem& pr, Instance& in) {
+  const int T = pr.T, n = pr.n, M = pr.M;
+  for (int kk = 0; kk < T; kk++)
+    Linearize(pr, &in.xs[(size_t)kk * n], &in.us[(size_t)kk * M], &in.A[(size_t)kk * n * n],
+              &in.B[(size_t)kk * n * M]);
+}
+
+// ILQSolver::ComputeCostQuadraticization, src/ilq_solver.cpp:471-490
+void QuadraticizeAll(const Problem& pr, Instance& in) {
   const int T = pr.T, n = pr.n, M = pr.M, N = pr.N;
-  for (int kk = 0; kk < T; kk++) {
-    const real* x = &in.xs[(size_t)kk * n];
-    const real* u = &in.us[(size_t)kk * M];
-    Linearize(pr, x, u, &in.A[(size_t)kk * n * n], &in.B[(size_t)kk * n * M]);
-    QuadraticizeStep(pr, in, kk, x, u, &in.Q[(size_t)kk * N * n * n], &in.l[(size_t)kk * N * n],
+  for (int kk = 0; kk < T; kk++)
+    QuadraticizeStep(pr, in, kk, &in.xs[(size_t)kk * n], &in.us[(size_t)kk * M],
+                     &in.Q[(size_t)kk * N * n * n], &in.l[(size_t)kk * N * n],
                      &in.R[(size_t)kk * pr.R_floats], &in.r[(size_t)kk * pr.r_floats]);
-  }
 }
 
 // ------------------------- Householder QR solve ----------------------------
@@ -1148,11 +1159,8 @@ real ExpectedDecrease(const Problem& pr, const Instance& in) {
 // ILQSolver::MeritFunction, src/ilq_solver.cpp:400-435: requadraticize
 // at the candidate point, then 0.5 * sum_k sum_i (|r_ii|^2 + [k>0] |l_i|^2).
 real MeritFunction(const Problem& pr, Instance& in) {
-  const int T = pr.T, n = pr.n, M = pr.M, N = pr.N;
-  for (int kk = 0; kk < T; kk++)
-    QuadraticizeStep(pr, in, kk, &in.xs[(size_t)kk * n], &in.us[(size_t)kk * M],
-                     &in.Q[(size_t)kk * N * n * n], &in.l[(size_t)kk * N * n],
-                     &in.R[(size_t)kk * pr.R_floats], &in.r[(size_t)kk * pr.r_floats]);
+  const int T = pr.T, n = pr.n, N = pr.N;
+  QuadraticizeAll(pr, in);
   real merit = 0.0;
   for (int kk = 0; kk < T; kk++)
     for (int i = 0; i < N; i++) {
@@ -1251,7 +1259,8 @@ void InitInstance(const Problem& pr, Instance& in) {
   in.expected_decrease = kInfinity;
   in.step = 0;
   in.total_costs.assign(N, 0);
-  in.time_of_extreme.assign(N, 0);
+  in.te_quad.assign(N, 0);
+  in.te_new.assign(N, 0);
   in.status = ILQG_STATUS_IDLE;
   in.iters = 0;
   in.backtracks = 0;
@@ -1271,7 +1280,10 @@ void IterateOnce(const Problem& pr, Instance& in) {
     return;
   }
   in.iters++;
-  LinearizeQuadraticize(pr, in);
+  // Only the linearization is recomputed here; the quadraticization is the one the last
+  // MeritFunction call (or the Solve prologue) left behind (src/ilq_solver.cpp:116,136-143).
+  LinearizeAll(pr, in);
+  in.te_quad = in.te_new;
   std::vector<real> zero(pr.n, 0);
   LQFeedbackSolve(pr, in, zero.data());
   bool has_converged = false;
@@ -1418,7 +1430,8 @@ int ilqg_upload(ilqg_handle h, int what, const void* src, size_t bytes) {
     case ILQG_TIME_OF_EXTREME:
       if (bytes != sizeof(int32_t) * B * pr.N) return ILQG_ERR_SIZE_MISMATCH;
       for (int b = 0; b < B; b++)
-        for (int i = 0; i < pr.N; i++) h->inst[b].time_of_extreme[i] = iv[b * pr.N + i];
+        for (int i = 0; i < pr.N; i++)
+          h->inst[b].te_quad[i] = h->inst[b].te_new[i] = iv[b * pr.N + i];
       return ILQG_OK;
     case ILQG_X0:
       return ilqg_upload_x0(h, f, bytes);
@@ -1455,7 +1468,9 @@ int ilqg_solve_begin(ilqg_handle h) {
     Rollout(pr, last_xs.data(), last_us.data(), in.Ps.data(), in.alphas.data(), in.xs.data(),
             in.us.data());
     TotalCosts(pr, in);
-    in.status = ILQG_STATUS_RUNNING;
+    in.te_quad = in.te_new;
+    QuadraticizeAll(pr, in);  // src/ilq_solver.cpp:116
+    in.status = pr.p.max_solver_iters > 0 ? ILQG_STATUS_RUNNING : ILQG_STATUS_MAX_ITERS;
     in.iters = 0;
   }
   return ILQG_OK;
@@ -1463,7 +1478,10 @@ int ilqg_solve_begin(ilqg_handle h) {
 
 int ilqg_linearize_quadraticize(ilqg_handle h) {
   if (!h) return ILQG_ERR_BAD_HANDLE;
-  for (auto& in : h->inst) LinearizeQuadraticize(h->pr, in);
+  for (auto& in : h->inst) {
+    LinearizeAll(h->pr, in);
+    QuadraticizeAll(h->pr, in);
+  }
   return ILQG_OK;
 }
 
@@ -1471,6 +1489,7 @@ int ilqg_lq_backward(ilqg_handle h) {
   if (!h) return ILQG_ERR_BAD_HANDLE;
   std::vector<real> zero(h->pr.n, 0);
   for (auto& in : h->inst) {
+    in.te_quad = in.te_new;
     LQFeedbackSolve(h->pr, in, zero.data());
     in.expected_decrease = ExpectedDecrease(h->pr, in);
   }
@@ -1480,13 +1499,18 @@ int ilqg_lq_backward(ilqg_handle h) {
 int ilqg_linesearch(ilqg_handle h) {
   if (!h) return ILQG_ERR_BAD_HANDLE;
   for (auto& in : h->inst) {
+    if (in.status != ILQG_STATUS_RUNNING) continue;
+    in.iters++;  // the stage sequence LQ -> backward -> linesearch is one loop pass
     bool conv = false;
     if (!ModifyLQStrategies(h->pr, in, &conv)) {
       in.status = ILQG_STATUS_LINESEARCH_FAILED;
       continue;
     }
     TotalCosts(h->pr, in);
-    if (conv && !h->pr.p.disable_convergence_exit) in.status = ILQG_STATUS_CONVERGED;
+    if (conv && !h->pr.p.disable_convergence_exit)
+      in.status = ILQG_STATUS_CONVERGED;
+    else if (in.iters >= h->pr.p.max_solver_iters)
+      in.status = ILQG_STATUS_MAX_ITERS;
   }
   return ILQG_OK;
 }
@@ -1614,7 +1638,7 @@ int ilqg_download(ilqg_handle h, int what, void* dst, size_t bytes) {
     case ILQG_TIME_OF_EXTREME:
       if (bytes != sizeof(int32_t) * B * pr.N) return ILQG_ERR_SIZE_MISMATCH;
       for (int b = 0; b < B; b++)
-        for (int i = 0; i < pr.N; i++) iv[b * pr.N + i] = h->inst[b].time_of_extreme[i];
+        for (int i = 0; i < pr.N; i++) iv[b * pr.N + i] = h->inst[b].te_new[i];
       return ILQG_OK;
   }
   return ILQG_ERR_INVALID_ARGUMENT;
