@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- iLQ iterations/s on a batch of ThreePlayerIntersection games (T = 100).
+
+Contract (see the task prompt): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
+line; for N > 1 it is launched under torch.distributed.run, one rank per GPU.
+
+  step        one benchmark solve of the whole per-GPU batch: Solve() prologue + 10 iLQ
+              iterations (linearize+quadraticize, backward Riccati, linesearch) from the zero
+              warm start, lambda = 0, mu = 10, convergence exit disabled
+  value       completed instance-iterations / second, all ranks, inputs resident in HBM,
+              CUDA-event timed on the launch stream, max over ranks
+  e2e         same metric through the C ABI with HOST buffers: per step the initial states go
+              pinned-host -> device and trajectories + status come back device -> pinned-host
+  roofline    dominant kernel: algorithmic bytes per launch / mean launch duration (CUDA events)
+  cpu_baseline  the CPU oracle (restatement of the reference's Eigen path) on a bounded sample
+
+`--impl reference` times the reference algorithm's CPU path instead (the oracle port, all host
+cores) on the same workload/metric; no GPU code runs in that arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+ITERS_PER_SOLVE = 10
+ORACLE_LIB = os.path.join(REPO, "oracle", "_build", "libilqg_oracle.so")
+
+
+def workload(batch: int, seed: int):
+    from ilqgames_b200 import problems
+    desc, _ = problems.three_player_intersection()
+    params = problems.three_player_intersection_params(max_solver_iters=ITERS_PER_SOLVE,
+                                                       disable_convergence_exit=1)
+    x0 = problems.three_player_intersection_x0_batch(batch, seed)
+    return desc, params, x0
+
+
+def algorithmic_bytes(layout) -> dict:
+    """Per instance-iteration algorithmic bytes of each kernel (SURVEY.md section 8d byte model,
+    DESIGN.md section 5): fp32 slab terms of the dense-record design."""
+    T, n, M, N = layout.num_time_steps, layout.xdim, layout.total_udim, layout.num_players
+    op = T * (n + M)
+    AB = T * (n * n + n * M)
+    QR = T * (N * (n * n + n) + layout.R_floats + layout.r_floats)
+    Ql = T * N * (n * n + n)
+    Pa = T * (M * n + M)
+    dx = T * n
+    return {
+        "linearize_quadraticize": 4 * (op + AB + QR),
+        "lq_backward": 4 * ((AB + QR + Pa) + (AB + Ql + Pa + dx)),
+        "linesearch_per_rollout": 4 * (2 * op + Pa),
+    }
+
+
+# ------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for k, nm in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------- CPU arm
+def _oracle_worker(args):
+    x0, iters = args
+    from ilqgames_b200 import _abi as abi
+    desc, params, _ = workload(1, 0)
+    lib = abi.Library(ORACLE_LIB)
+    h = abi.Handle(lib, desc, params, x0.shape[0])
+    h.upload_x0(x0)
+    t = time.perf_counter()
+    h.reset(h.RESET_SOLVER)
+    h.solve_begin()
+    h.iterate(iters)
+    dt = time.perf_counter() - t
+    done = int(h.download(abi.ITERS).sum())
+    rolls = int(h.download(abi.BACKTRACKS).sum())
+    h.close()
+    return dt, done, rolls
+
+
+def cpu_single_core(x0_sample):
+    dt, done, rolls = _oracle_worker((x0_sample, ITERS_PER_SOLVE))
+    return done / dt, done, rolls, dt
+
+
+def run_reference(args):
+    """--impl reference: the CPU path (oracle port of the reference's Eigen algorithm) on all host
+    cores; each step is a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_worker = 8
+    _, _, x0 = workload(args.batch, args.seed)
+    sample = x0[: min(args.batch, cores * per_worker)]
+    chunks = [c for c in np.array_split(sample, cores) if len(c)]
+    ctx = mp.get_context("fork")
+    times = []
+    done_total = 0
+    with ctx.Pool(len(chunks)) as pool:
+        for step in range(args.warmup + args.steps):
+            t = time.perf_counter()
+            res = pool.map(_oracle_worker, [(c, ITERS_PER_SOLVE) for c in chunks])
+            dt = time.perf_counter() - t
+            if step >= args.warmup:
+                times.append(dt)
+                done_total += sum(r[1] for r in res)
+    total = sum(times)
+    value = done_total / total
+    line = {
+        "impl": "reference", "metric": "ilq_instance_iterations_per_second", "value": value,
+        "unit": "instance-iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ThreePlayerIntersection n=16 m=(2,2,2) T=100, 10 iLQ iterations/solve, "
+                               "lambda=0 mu=10, convergence exit disabled", "batch_per_gpu": args.batch,
+                   "seed": args.seed},
+        "cpu_baseline": {"value": value, "unit": "instance-iterations/s", "cores": len(chunks), "kind": "port",
+                         "sample": f"first {len(sample)} instances of the batch x {ITERS_PER_SOLVE} iterations per step, "
+                                   f"{len(chunks)} processes; oracle port because the reference's Eigen build is "
+                                   "impossible here (no Eigen3/glog/gflags)"},
+        "e2e": {"value": value, "unit": "instance-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from ilqgames_b200 import _abi as abi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference "
+                         "for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # each rank owns a contiguous slice of the global batch: independent games, no hot-path
+    # collective; seed differs per rank
+    desc, params, x0 = workload(args.batch, args.seed + rank)
+    lib = abi.product_library()
+    h = abi.Handle(lib, desc, params, args.batch, local)
+    # a non-default torch stream so torch.cuda.Event and the library's launches share it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    h.set_stream(stream.cuda_stream)
+    h.upload_x0(x0)
+    bytes_model = algorithmic_bytes(h.layout)
+
+    def solve():
+        h.reset(h.RESET_SOLVER)  # a fresh ILQSolver per solve (last merit = +inf)
+        h.solve_begin()
+        h.iterate(ITERS_PER_SOLVE)
+
+    # ---- device-resident timing ------------------------------------------------------
+    for _ in range(args.warmup):
+        solve()
+    barrier()
+    launches0 = h.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            solve()
+        ev1.record(stream)
+        barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = h.kernel_launches() - launches0
+    iters = h.download(abi.ITERS)
+    rollouts = h.download(abi.BACKTRACKS)  # cumulative over all solves since creation
+    status = h.download(abi.STATUS)
+    done_per_step = int(iters.sum())
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([done_per_step], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    max_ms = float(t.item())
+    total_done_per_step = int(cnt.item())
+    value = total_done_per_step * args.steps / (max_ms * 1e-3)
+
+    # ---- per-kernel profile pass (not part of the timed region above) ----------------
+    h.profile(True)
+    prof_steps = max(1, min(args.steps, 3))
+    roll_before = int(h.download(abi.BACKTRACKS).sum())
+    for _ in range(prof_steps):
+        solve()
+    prof = h.profile_read()
+    h.profile(False)
+    roll_per_step = (int(h.download(abi.BACKTRACKS).sum()) - roll_before) / prof_steps
+    kern = {}
+    for name, (ms, n) in prof.items():
+        if n:
+            kern[name] = {"ms_per_launch": ms / n, "launches_per_step": n / prof_steps, "ms_per_step": ms / prof_steps}
+    inst_iters_per_launch = done_per_step / ITERS_PER_SOLVE
+    per_kernel_bytes = {
+        "linearize_quadraticize": bytes_model["linearize_quadraticize"] * inst_iters_per_launch,
+        "lq_backward": bytes_model["lq_backward"] * inst_iters_per_launch,
+        "linesearch": bytes_model["linesearch_per_rollout"] * roll_per_step / ITERS_PER_SOLVE,
+    }
+    hot = [k for k in ("linearize_quadraticize", "lq_backward", "linesearch") if k in kern]
+    dominant = max(hot, key=lambda k: kern[k]["ms_per_step"])
+    peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = per_kernel_bytes[dominant] / (kern[dominant]["ms_per_launch"] * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(REPO, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dominant)
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": per_kernel_bytes[dominant],
+                "kernels": {k: dict(v, algorithmic_GBps=per_kernel_bytes[k] / (v["ms_per_launch"] * 1e-3) / 1e9
+                                    if k in per_kernel_bytes else None) for k, v in kern.items()}}
+
+    # ---- end to end through the C ABI with host buffers ------------------------------
+    pin_x0 = torch.from_numpy(x0).pin_memory()
+    lo = h.layout
+    pin_xs = torch.empty((args.batch, lo.num_time_steps, lo.xdim), dtype=torch.float32).pin_memory()
+    pin_us = torch.empty((args.batch, lo.num_time_steps, lo.total_udim), dtype=torch.float32).pin_memory()
+    pin_status = torch.empty((args.batch,), dtype=torch.int32).pin_memory()
+    pin_iters = torch.empty((args.batch,), dtype=torch.int32).pin_memory()
+    h2d = pin_x0.numel() * 4
+    d2h = (pin_xs.numel() + pin_us.numel()) * 4 + (pin_status.numel() + pin_iters.numel()) * 4
+
+    def e2e_step():
+        h.upload_x0_ptr(pin_x0.data_ptr(), h2d)
+        solve()
+        h.download_ptr(abi.XS, pin_xs.data_ptr(), pin_xs.numel() * 4)
+        h.download_ptr(abi.US, pin_us.data_ptr(), pin_us.numel() * 4)
+        h.download_ptr(abi.STATUS, pin_status.data_ptr(), pin_status.numel() * 4)
+        h.download_ptr(abi.ITERS, pin_iters.data_ptr(), pin_iters.numel() * 4)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_done = int(pin_iters.sum().item())
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    ce = torch.tensor([e2e_done], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ce, op=dist.ReduceOp.SUM)
+    e2e_value = int(ce.item()) * e2e_steps / float(te.item())
+
+    # ---- gather of converged trajectories over NCCL (off the hot path, reported apart) ----
+    gather_ms = None
+    if world > 1:
+        dev_xs = pin_xs.cuda(non_blocking=True)
+        out = torch.empty((world,) + tuple(dev_xs.shape), dtype=dev_xs.dtype, device="cuda")
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        dist.all_gather_into_tensor(out.view(-1), dev_xs.view(-1))
+        g1.record()
+        torch.cuda.synchronize()
+        gather_ms = g0.elapsed_time(g1)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample = x0[: min(args.batch, args.cpu_sample)]
+        v, done, rolls, dt = cpu_single_core(sample)
+        cpu = {"value": v, "unit": "instance-iterations/s", "cores": 1, "kind": "port",
+               "sample": f"first {len(sample)} instances of the same batch, {ITERS_PER_SOLVE} iterations each, "
+                         f"{dt:.1f} s on one host core (of {os.cpu_count()}); oracle port of the reference's "
+                         "Eigen path (reference itself not buildable: no Eigen3/glog/gflags)"}
+
+    if rank == 0:
+        hist = np.bincount(status, minlength=6).tolist()
+        line = {
+            "metric": "ilq_instance_iterations_per_second", "value": value, "unit": "instance-iterations/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "batch 4096 ThreePlayerIntersection (2x car6d + unicycle4d, n=16, m=(2,2,2)), "
+                                   "T=100, 10 iLQ iterations/solve, lambda=0 mu=10, convergence exit disabled"
+                       if args.batch == 4096 else f"batch {args.batch} ThreePlayerIntersection T=100",
+                       "batch_per_gpu": args.batch, "global_batch": args.batch * world, "iterations_per_step": ITERS_PER_SOLVE,
+                       "instance_iterations_per_step": total_done_per_step, "mean_rollouts_per_iteration": roll_per_step / max(done_per_step, 1),
+                       "status_histogram_rank0": hist, "l2": "working set per step (LQ records ~1.9 GB) exceeds the 126 MB L2",
+                       "parallelism": f"dp{world} (independent games, no hot-path collective)", "seed": args.seed},
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": "instance-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "gather_ms": gather_ms,
+        }
+        print(json.dumps(line))
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="instances per GPU")
+    ap.add_argument("--seed", type=int, default=4096)
+    ap.add_argument("--cpu-sample", type=int, default=256)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

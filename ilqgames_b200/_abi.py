@@ -110,7 +110,8 @@ ABI_SYMBOLS = [
     "ilqg_upload_x0", "ilqg_upload_warmstart", "ilqg_upload", "ilqg_upload_lq",
     "ilqg_solve_begin", "ilqg_linearize_quadraticize", "ilqg_lq_backward", "ilqg_linesearch",
     "ilqg_iterate", "ilqg_al_update", "ilqg_overwrite_solution", "ilqg_al_post_solve",
-    "ilqg_download", "ilqg_synchronize", "ilqg_kernel_launches",
+    "ilqg_download", "ilqg_synchronize", "ilqg_kernel_launches", "ilqg_set_stream",
+    "ilqg_profile", "ilqg_profile_read", "ilqg_reset",
 ]
 
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -152,6 +153,11 @@ class Library:
         L.ilqg_overwrite_solution.argtypes = [vp, C.c_int]
         L.ilqg_download.argtypes = [vp, C.c_int, vp, C.c_size_t]
         L.ilqg_kernel_launches.argtypes = [vp, C.POINTER(C.c_longlong)]
+        L.ilqg_set_stream.argtypes = [vp, vp]
+        L.ilqg_reset.argtypes = [vp, C.c_int]
+        L.ilqg_profile.argtypes = [vp, C.c_int]
+        L.ilqg_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double),
+                                        C.POINTER(C.c_longlong)]
         for name in ABI_SYMBOLS:
             if name not in ("ilqg_strerror", "ilqg_abi_struct_size"):
                 getattr(L, name).restype = C.c_int
@@ -274,6 +280,13 @@ class Handle:
                        f"download({what})")
         return out
 
+    def upload_x0_ptr(self, ptr: int, nbytes: int):
+        self.lib.check(self.lib.lib.ilqg_upload_x0(self._h, C.c_void_p(ptr), nbytes), "upload_x0")
+
+    def download_ptr(self, what: int, ptr: int, nbytes: int):
+        self.lib.check(self.lib.lib.ilqg_download(self._h, what, C.c_void_p(ptr), nbytes),
+                       f"download({what})")
+
     # -- hot path ---------------------------------------------------------------
     def solve_begin(self):
         self.lib.check(self.lib.lib.ilqg_solve_begin(self._h), "solve_begin")
@@ -307,6 +320,30 @@ class Handle:
 
     def synchronize(self):
         self.lib.check(self.lib.lib.ilqg_synchronize(self._h), "synchronize")
+
+    RESET_SOLVER, RESET_MULTIPLIERS, RESET_SOLUTION = 1, 2, 4
+
+    def reset(self, mask: int = 1):
+        self.lib.check(self.lib.lib.ilqg_reset(self._h, mask), "reset")
+
+    def set_stream(self, cuda_stream: int):
+        """cuda_stream: a cudaStream_t as an integer (e.g. torch.cuda.current_stream().cuda_stream)."""
+        self.lib.check(self.lib.lib.ilqg_set_stream(self._h, C.c_void_p(cuda_stream)), "set_stream")
+
+    def profile(self, enable: bool):
+        self.lib.check(self.lib.lib.ilqg_profile(self._h, int(enable)), "profile")
+
+    KERNEL_NAMES = ("linearize_quadraticize", "lq_backward", "linesearch", "solve_begin")
+
+    def profile_read(self):
+        """{kernel name: (total_ms, launches)} since profile(True)."""
+        out = {}
+        for k, name in enumerate(self.KERNEL_NAMES):
+            ms, n = C.c_double(0), C.c_longlong(0)
+            self.lib.check(self.lib.lib.ilqg_profile_read(self._h, k, C.byref(ms), C.byref(n)),
+                           "profile_read")
+            out[name] = (ms.value, n.value)
+        return out
 
     def kernel_launches(self) -> int:
         out = C.c_longlong(0)

@@ -8,7 +8,7 @@
 #include <new>
 #include <vector>
 
-#include "ilqg_kernels.cuh"
+#include "ilqg_linesearch.cuh"
 
 using namespace ilqg;
 
@@ -18,10 +18,19 @@ struct ilqg_solver {
   ilqg_problem_desc host_desc;
   ilqg_layout layout;
   Slab s;
+  LsScratch ls;
+  int ls_blocks_max;
   int device;
   int B;
-  cudaStream_t stream;
+  cudaStream_t stream;      // the stream work is issued on
+  cudaStream_t own_stream;  // created with the handle
   std::vector<void*> allocs;
+  // per-kernel event timing (ilqg_profile)
+  bool profiling;
+  struct Sample { cudaEvent_t a, b; int kind; };
+  std::vector<Sample> samples;
+  double prof_ms[4];
+  long long prof_n[4];
   float* staging;
   size_t staging_floats;
   long long launches;
@@ -239,7 +248,25 @@ constexpr DimsEntry kDims[] = {
 };
 constexpr int kNumDims = sizeof(kDims) / sizeof(kDims[0]);
 
-constexpr int kLsLanes = 8;  // lanes per instance in k_linesearch / k_solve_begin
+
+struct ProfScope {  // brackets one launch with events when profiling is on
+  ilqg_solver* h;
+  cudaEvent_t a, b;
+  int kind;
+  bool on;
+  ProfScope(ilqg_solver* hh, int k) : h(hh), a(nullptr), b(nullptr), kind(k), on(hh->profiling) {
+    if (on) {
+      on = cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess;
+      if (on) cudaEventRecord(a, h->stream);
+    }
+  }
+  ~ProfScope() {
+    if (on) {
+      cudaEventRecord(b, h->stream);
+      h->samples.push_back({a, b, kind});
+    }
+  }
+};
 
 template <typename K>
 int SetSmem(K kernel, size_t bytes) {
@@ -253,27 +280,46 @@ int LaunchBackward(ilqg_solver* h, int only_running) {
   int rc = SetSmem(k_lq_backward<NX, MU, NP>, smem);
   if (rc != ILQG_OK) return rc;
   const int blocks = (h->B + KBWD_WARPS - 1) / KBWD_WARPS;
+  ProfScope prof(h, 1);
   k_lq_backward<NX, MU, NP><<<blocks, KBWD_WARPS * 32, smem, h->stream>>>(h->d, h->p, h->s, only_running);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   return ILQG_OK;
 }
 
-int DispatchBackward(ilqg_solver* h, int only_running) {
-  switch (h->dims_key) {
-    case 0: return LaunchBackward<16, 6, 3>(h, only_running);
-    case 1: return LaunchBackward<24, 8, 4>(h, only_running);
-    case 2: return LaunchBackward<3, 2, 2>(h, only_running);
-    case 3: return LaunchBackward<2, 2, 2>(h, only_running);
-    case 4: return LaunchBackward<12, 6, 3>(h, only_running);
-  }
-  return ILQG_ERR_UNSUPPORTED;
+template <int NX, int MU, int NP>
+int LaunchBackwardHw(ilqg_solver* h, int only_running) {
+  const size_t per_inst = HwSmem<NX, MU, NP>::lrr + (h->d.rec - h->d.offl);
+  const size_t smem = sizeof(float) * KHW_WARPS * 2 * per_inst;
+  int rc = SetSmem(k_lq_backward_hw<NX, MU, NP>, smem);
+  if (rc != ILQG_OK) return rc;
+  const int per_block = KHW_WARPS * 2;
+  ProfScope prof(h, 1);
+  k_lq_backward_hw<NX, MU, NP><<<(h->B + per_block - 1) / per_block, KHW_WARPS * 32, smem, h->stream>>>(
+      h->d, h->p, h->s, only_running);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ILQG_OK;
 }
 
-size_t LsSmemBytes(const ilqg_solver* h) {
-  const DevDesc& d = h->d;
-  const int per = ((2 * d.n + d.M + 3) & ~3) + ((d.T * 2 * d.N + 3) & ~3);
-  return sizeof(float) * (size_t)per * (KLS_THREADS / kLsLanes);
+// with_dxs: also produce ILQG_DELTA_XS (an optional output of LQFeedbackSolver::Solve that the
+// iLQ loop itself never reads once ExpectedDecrease is fused into the backward sweep)
+int DispatchBackward(ilqg_solver* h, int only_running, bool with_dxs) {
+  int rc = ILQG_ERR_UNSUPPORTED;
+  bool hw = true;
+  switch (h->dims_key) {
+    case 0: rc = LaunchBackwardHw<16, 6, 3>(h, only_running); break;
+    case 1: rc = LaunchBackwardHw<24, 8, 4>(h, only_running); break;
+    case 2: rc = LaunchBackward<3, 2, 2>(h, only_running); hw = false; break;
+    case 3: rc = LaunchBackward<2, 2, 2>(h, only_running); hw = false; break;
+    case 4: rc = LaunchBackwardHw<12, 6, 3>(h, only_running); break;
+  }
+  if (rc == ILQG_OK && hw && with_dxs) {
+    k_delta_xs<<<(h->B + 3) / 4, 128, sizeof(float) * 4 * 2 * ILQG_MAX_XDIM, h->stream>>>(h->d, h->s);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  return rc;
 }
 
 int LaunchLqRecords(ilqg_solver* h, int only_running) {
@@ -283,34 +329,71 @@ int LaunchLqRecords(ilqg_solver* h, int only_running) {
   if (rc != ILQG_OK) return rc;
   const long long warps = (long long)h->B * d.T;
   const int blocks = (int)((warps + KLQ_WARPS - 1) / KLQ_WARPS);
+  ProfScope prof(h, 0);
   k_linearize_quadraticize<<<blocks, KLQ_WARPS * 32, smem, h->stream>>>(h->d, h->s, only_running);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   return ILQG_OK;
 }
 
-int LaunchLinesearch(ilqg_solver* h) {
-  const size_t smem = LsSmemBytes(h);
-  auto kern = k_linesearch<kLsLanes, ILQG_MAX_XDIM, ILQG_MAX_PLAYERS>;
-  int rc = SetSmem(kern, smem);
+int LaunchLsEval(ilqg_solver* h, int mode, int jbase, int jcount, long long items, int prof_kind) {
+  const DevDesc& d = h->d;
+  const size_t smem = sizeof(float) * (size_t)ls_smem_floats(d.n, d.M, d.N);
+  int rc = SetSmem(k_ls_eval, smem);
   if (rc != ILQG_OK) return rc;
-  const int per_block = KLS_THREADS / kLsLanes;
-  kern<<<(h->B + per_block - 1) / per_block, KLS_THREADS, smem, h->stream>>>(h->d, h->p, h->s);
+  const int blocks = (int)((items + 31) / 32);
+  if (blocks <= 0) return ILQG_OK;
+  if (blocks > h->ls_blocks_max) return ILQG_ERR_INVALID_ARGUMENT;
+  const int threads = (d.num_subsystems + d.N) * 32;
+  ProfScope prof(h, prof_kind);
+  k_ls_eval<<<blocks, threads, smem, h->stream>>>(h->d, h->p, h->s, h->ls, mode, jbase, jcount);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   return ILQG_OK;
 }
 
-int LaunchSolveBegin(ilqg_solver* h) {
-  const size_t smem = LsSmemBytes(h);
-  auto kern = k_solve_begin<kLsLanes, ILQG_MAX_XDIM, ILQG_MAX_PLAYERS>;
-  int rc = SetSmem(kern, smem);
-  if (rc != ILQG_OK) return rc;
-  const int per_block = KLS_THREADS / kLsLanes;
-  kern<<<(h->B + per_block - 1) / per_block, KLS_THREADS, smem, h->stream>>>(h->d, h->p, h->s);
+// ILQSolver::ModifyLQStrategies as the speculative A/B/C pipeline (ilqg_linesearch.cuh)
+int LaunchLinesearch(ilqg_solver* h) {
+  const int B = h->B, JA = h->ls.JA, max_bt = h->p.max_backtracking_steps;
+  int rc;
+  ProfScope prof(h, 2);
+  const bool was = h->profiling;
+  h->profiling = false;  // one sample for the whole pipeline
+  auto done = [&](int code) {
+    h->profiling = was;
+    return code;
+  };
+  CUDA_TRY(cudaMemsetAsync(h->ls.counts, 0, 2 * sizeof(int), h->stream));
+  if ((rc = LaunchLsEval(h, LS_MODE_A, 0, JA, (long long)B * JA, 2)) != ILQG_OK) return done(rc);
+  const int dec_blocks = (B + KDEC_WARPS - 1) / KDEC_WARPS;
+  k_ls_decide_a<<<dec_blocks, KDEC_WARPS * 32, 0, h->stream>>>(h->d, h->p, h->s, h->ls);
   h->launches++;
-  CUDA_TRY(cudaGetLastError());
-  return ILQG_OK;
+  if (h->p.linesearch && max_bt > JA) {
+    const int jcount = max_bt - JA;
+    if ((rc = LaunchLsEval(h, LS_MODE_B, JA, jcount, (long long)B * jcount, 2)) != ILQG_OK) return done(rc);
+    k_ls_decide_b<<<(B + 127) / 128, 128, 0, h->stream>>>(h->d, h->p, h->s, h->ls, JA, jcount);
+    h->launches++;
+    if ((rc = LaunchLsEval(h, LS_MODE_C, 0, 1, B, 2)) != ILQG_OK) return done(rc);
+    k_ls_finalize_c<<<dec_blocks, KDEC_WARPS * 32, 0, h->stream>>>(h->d, h->p, h->s, h->ls);
+    h->launches++;
+  }
+  if (cudaGetLastError() != cudaSuccess) return done(ILQG_ERR_CUDA);
+  return done(ILQG_OK);
+}
+
+int LaunchSolveBegin(ilqg_solver* h) {
+  int rc;
+  ProfScope prof(h, 3);
+  const bool was = h->profiling;
+  h->profiling = false;
+  rc = LaunchLsEval(h, LS_MODE_BEGIN, 0, 1, h->B, 3);
+  if (rc == ILQG_OK) {
+    k_begin_finalize<<<(h->B + KDEC_WARPS - 1) / KDEC_WARPS, KDEC_WARPS * 32, 0, h->stream>>>(h->d, h->p, h->s, h->ls);
+    h->launches++;
+    if (cudaGetLastError() != cudaSuccess) rc = ILQG_ERR_CUDA;
+  }
+  h->profiling = was;
+  return rc;
 }
 
 template <typename T>
@@ -443,16 +526,22 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
                 ilqg_handle* out) {
   if (!desc || !params || !out || batch < 1) return ILQG_ERR_INVALID_ARGUMENT;
   if (params->open_loop) return ILQG_ERR_UNSUPPORTED;
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return ILQG_ERR_NO_DEVICE;
-  if (device < 0 || device >= ndev) return ILQG_ERR_INVALID_ARGUMENT;
   ilqg_solver* h = new (std::nothrow) ilqg_solver();
   if (!h) return ILQG_ERR_OUT_OF_MEMORY;
   std::vector<int> lidx;
-  int rc = BuildDeviceDesc(*desc, &h->d, &h->layout, &lidx);
+  int rc = BuildDeviceDesc(*desc, &h->d, &h->layout, &lidx);  // descriptor errors first
   if (rc != ILQG_OK) {
     delete h;
     return rc;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    delete h;
+    return ILQG_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= ndev) {
+    delete h;
+    return ILQG_ERR_INVALID_ARGUMENT;
   }
   h->dims_key = -1;
   for (int k = 0; k < kNumDims; k++)
@@ -468,6 +557,10 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
   h->staging = nullptr;
   h->staging_floats = 0;
   h->launches = 0;
+  h->profiling = false;
+  h->stream = nullptr;
+  h->own_stream = nullptr;
+  for (int k = 0; k < 4; k++) { h->prof_ms[k] = 0; h->prof_n[k] = 0; }
   DevParams& p = h->p;
   p.convergence_tolerance = params->convergence_tolerance;
   p.max_solver_iters = params->max_solver_iters;
@@ -487,10 +580,11 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
     delete h;
     return ILQG_ERR_CUDA;
   }
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
     return ILQG_ERR_CUDA;
   }
+  h->stream = h->own_stream;
   const size_t B = batch, T = h->d.T, n = h->d.n, M = h->d.M, N = h->d.N;
   Slab& s = h->s;
   std::memset(&s, 0, sizeof(s));
@@ -530,6 +624,31 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
   ALLOC(s.st_cur, B);
   int* lidx_dev = nullptr;
   ALLOC(lidx_dev, T);
+  {
+    // linesearch scratch (ilqg_linesearch.cuh): JA speculative candidates per instance in phase A
+    LsScratch& ls = h->ls;
+    std::memset(&ls, 0, sizeof(ls));
+    const int max_bt = std::max(1, params->max_backtracking_steps);
+    int JA = (int)std::max<size_t>(1, std::min<size_t>(8, 32768 / B));
+    if (!params->linesearch) JA = 1;
+    JA = std::min(JA, max_bt);
+    ls.JA = JA;
+    const size_t per = (size_t)std::max(std::max(JA, max_bt - JA), 1);
+    const size_t blocks_max = (B * per + 31) / 32;
+    h->ls_blocks_max = (int)blocks_max;
+#define ALLOCNZ(ptr, count)                                               \
+  if ((rc = DevAlloc(h, &(ptr), (count), false)) != ILQG_OK) return fail(rc)
+    ALLOCNZ(ls.traj_xs, B * JA * T * n);
+    ALLOCNZ(ls.traj_us, B * JA * T * M);
+    ALLOCNZ(ls.terms, blocks_max * T * 2 * N * 32);
+    ALLOCNZ(ls.vals, blocks_max * T * N * 32);
+    ALLOCNZ(ls.merit, blocks_max * 32);
+#undef ALLOCNZ
+    ALLOC(ls.pending, B);
+    ALLOC(ls.commit, B);
+    ALLOC(ls.accept_j, B);
+    ALLOC(ls.counts, 2);
+  }
 #undef ALLOC
   s.lambda_index = lidx_dev;
   if (cudaMemcpyAsync(lidx_dev, lidx.data(), T * sizeof(int), cudaMemcpyHostToDevice, h->stream) !=
@@ -548,9 +667,11 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
 int ilqg_destroy(ilqg_handle h) {
   if (!h) return ILQG_ERR_BAD_HANDLE;
   Guard guard(h->device);
-  if (h->stream) {
-    cudaStreamSynchronize(h->stream);
-    cudaStreamDestroy(h->stream);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  for (auto& sm : h->samples) {
+    cudaEventDestroy(sm.a);
+    cudaEventDestroy(sm.b);
   }
   for (void* p : h->allocs) cudaFree(p);
   if (h->staging) cudaFree(h->staging);
@@ -650,7 +771,7 @@ int ilqg_linearize_quadraticize(ilqg_handle h) {
 
 int ilqg_lq_backward(ilqg_handle h) {
   ENTER(h);
-  return DispatchBackward(h, 0);
+  return DispatchBackward(h, 0, true);
 }
 
 int ilqg_linesearch(ilqg_handle h) {
@@ -663,7 +784,7 @@ int ilqg_iterate(ilqg_handle h, int max_iters, int* iters_done) {
   int rc;
   for (int it = 0; it < max_iters; it++) {
     if ((rc = LaunchLqRecords(h, 1)) != ILQG_OK) return rc;
-    if ((rc = DispatchBackward(h, 1)) != ILQG_OK) return rc;
+    if ((rc = DispatchBackward(h, 1, false)) != ILQG_OK) return rc;
     if ((rc = LaunchLinesearch(h)) != ILQG_OK) return rc;
   }
   if (iters_done) {
@@ -738,6 +859,72 @@ int ilqg_download(ilqg_handle h, int what, void* dst, size_t bytes) {
 int ilqg_synchronize(ilqg_handle h) {
   ENTER(h);
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return ILQG_OK;
+}
+
+int ilqg_reset(ilqg_handle h, int mask) {
+  ENTER(h);
+  int rc;
+  const size_t B = h->B, T = h->d.T, n = h->d.n, M = h->d.M;
+  Slab& s = h->s;
+  if (mask & ILQG_RESET_SOLVER) {
+    if ((rc = Fill(h, s.last_merit, INFINITY, B)) != ILQG_OK) return rc;
+    if ((rc = Fill(h, s.expected_decrease, INFINITY, B)) != ILQG_OK) return rc;
+  }
+  if (mask & ILQG_RESET_MULTIPLIERS) {
+    CUDA_TRY(cudaMemsetAsync(s.lambdas, 0, sizeof(float) * std::max<size_t>(B * h->d.num_constraints * T, 1), h->stream));
+    if ((rc = Fill(h, s.mu, 10.0f, B)) != ILQG_OK) return rc;
+  }
+  if (mask & ILQG_RESET_SOLUTION) {
+    CUDA_TRY(cudaMemsetAsync(s.prob_xs, 0, sizeof(float) * B * T * n, h->stream));
+    CUDA_TRY(cudaMemsetAsync(s.prob_us, 0, sizeof(float) * B * T * M, h->stream));
+    CUDA_TRY(cudaMemsetAsync(s.prob_P, 0, sizeof(float) * B * T * M * n, h->stream));
+    CUDA_TRY(cudaMemsetAsync(s.prob_a, 0, sizeof(float) * B * T * M, h->stream));
+    k_prob_to_working<<<h->B, 256, 0, h->stream>>>(h->d, h->s);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  return ILQG_OK;
+}
+
+int ilqg_set_stream(ilqg_handle h, void* cuda_stream) {
+  ENTER(h);
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return ILQG_OK;
+}
+
+static int DrainSamples(ilqg_solver* h) {
+  for (auto& sm : h->samples) {
+    CUDA_TRY(cudaEventSynchronize(sm.b));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, sm.a, sm.b));
+    h->prof_ms[sm.kind] += ms;
+    h->prof_n[sm.kind] += 1;
+    cudaEventDestroy(sm.a);
+    cudaEventDestroy(sm.b);
+  }
+  h->samples.clear();
+  return ILQG_OK;
+}
+
+int ilqg_profile(ilqg_handle h, int enable) {
+  ENTER(h);
+  int rc = DrainSamples(h);
+  if (rc != ILQG_OK) return rc;
+  if (enable)
+    for (int k = 0; k < 4; k++) { h->prof_ms[k] = 0; h->prof_n[k] = 0; }
+  h->profiling = enable != 0;
+  return ILQG_OK;
+}
+
+int ilqg_profile_read(ilqg_handle h, int kernel, double* total_ms, long long* launches) {
+  ENTER(h);
+  if (kernel < 0 || kernel > 3 || !total_ms || !launches) return ILQG_ERR_INVALID_ARGUMENT;
+  int rc = DrainSamples(h);
+  if (rc != ILQG_OK) return rc;
+  *total_ms = h->prof_ms[kernel];
+  *launches = h->prof_n[kernel];
   return ILQG_OK;
 }
 

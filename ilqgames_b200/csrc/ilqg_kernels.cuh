@@ -5,9 +5,7 @@
 //                                    running Z_i, zeta_i resident in shared memory, register-tiled
 //                                    F^T Z F, per-lane LU of the stacked S X = Y system,
 //                                    then the delta-x / expected-decrease forward sweep
-//   k_linesearch              K_ls : one G-lane tile per instance: rollout under the scaled
-//                                    strategies, gradient-only merit, Armijo, total costs
-//   k_solve_begin                    Solve() prologue (initial rollout + total costs)
+//   (K_ls, the linesearch / rollout pipeline, lives in ilqg_linesearch.cuh)
 //
 // Data layout: instance-major slab; the LQ records [B][T][rec] hold
 // [A | B | Q_0..Q_{N-1} | l | R | r] contiguously so one (instance, timestep) is a single
@@ -551,290 +549,6 @@ k_lq_backward(const __grid_constant__ DevDesc d, const DevParams p, Slab s, int 
     __syncwarp();
   }
   if (lane == 0) s.expected_decrease[b] = expected_decrease;
-}
-
-// ===========================================================================
-// K_ls and the Solve() prologue: tile-per-instance rollout, merit, Armijo, total costs
-// ===========================================================================
-template <int G>
-using TileG = cg::thread_block_tile<G>;
-
-// ILQSolver::CurrentOperatingPoint (src/ilq_solver.cpp:174-206) with Strategy::operator()
-// (strategy.h:73-76) and Integrate (multi_player_dynamical_system.cpp:52-77).
-// sm: x[n] | dx[n] | u[M].  alpha is scaled on the fly exactly as ScaleAlphas would have
-// (alpha * s0, then * rho nscale times).
-template <int G>
-__device__ void rollout(const TileG<G>& tile, const DevDesc& d, float* sm, const float* last_xs,
-                        const float* last_us, const float* x_start, const float* P,
-                        const float* alpha, bool scaled, float s0, float rho, int nscale,
-                        float* out_xs, float* out_us) {
-  const int n = d.n, M = d.M, T = d.T, t = tile.thread_rank();
-  float* x = sm;
-  float* dx = sm + n;
-  float* u = sm + 2 * n;
-  const float dt_half = (float)(d.time_step / 2.0);
-  for (int a = t; a < n; a += G) x[a] = x_start[a];
-  tile.sync();
-  for (int kk = 0; kk < T; kk++) {
-    for (int a = t; a < n; a += G) {
-      const float xv = x[a];
-      // last_operating_point.xs[0] was set to the start state (ilq_solver.cpp:88-89)
-      const float ref = kk == 0 ? x_start[a] : last_xs[(size_t)kk * n + a];
-      dx[a] = xv - ref;
-      out_xs[(size_t)kk * n + a] = xv;
-    }
-    tile.sync();
-    for (int c = t; c < M; c += G) {
-      const float* Prow = P + ((size_t)kk * M + c) * n;
-      float acc = 0.f;
-      for (int a = 0; a < n; a++) acc = fmaf(Prow[a], dx[a], acc);
-      float al = alpha[(size_t)kk * M + c];
-      if (scaled) {
-        al *= s0;
-        for (int j = 0; j < nscale; j++) al *= rho;
-      }
-      const float uv = last_us[(size_t)kk * M + c] - acc - al;
-      u[c] = uv;
-      out_us[(size_t)kk * M + c] = uv;
-    }
-    tile.sync();
-    if (kk < T - 1) {
-      for (int sidx = t; sidx < d.num_subsystems; sidx += G) {
-        const DevSubsystem& sub = d.sub[sidx];
-        const int xd = subsystem_xdim(sub.kind);
-        float xl[6];
-#pragma unroll
-        for (int a = 0; a < 6; a++) xl[a] = a < xd ? x[sub.x_offset + a] : 0.f;
-        const float u0 = u[sub.u_offset];
-        const float u1 = sub.kind == ILQG_DYN_AIR3D ? u[sub.u_offset2] : u[sub.u_offset + 1];
-        subsystem_integrate(sub, dt_half, xl, u0, u1);
-#pragma unroll
-        for (int a = 0; a < 6; a++)
-          if (a < xd) x[sub.x_offset + a] = xl[a];
-      }
-    }
-    tile.sync();
-  }
-}
-
-// Per-timestep gradients of every player's cost (gradient half of PlayerCost::Quadraticize),
-// one thread per timestep; returns through terms[kk][2i] = |r_ii|^2, terms[kk][2i+1] = [kk>0]|l_i|^2
-// (ILQSolver::MeritFunction src/ilq_solver.cpp:400-435).
-template <int NXMAX, int NPMAX>
-__device__ void merit_terms_step(const DevDesc& d, const Slab& s, int b, int kk, const float* x,
-                                 const float* u, float* terms) {
-  float l[NPMAX * NXMAX];
-  float r[ILQG_MAX_UDIM * ILQG_MAX_PLAYERS];
-  const int n = d.n, N = d.N;
-  for (int e = 0; e < N * n; e++) l[e] = 0.f;
-  for (int e = 0; e < d.r_floats; e++) r[e] = 0.f;
-  const float mu = s.mu[b];
-  for (int i = 0; i < N; i++) {
-    const bool full = d.cost_structure[i] == ILQG_COST_SUM || s.te_quad[(size_t)b * N + i] == kk;
-    for (int c = d.cost_begin[i]; c < d.cost_begin[i + 1]; c++) {
-      const DevCost& cd = d.cost[c];
-      const bool is_con = cd.slot >= 0;
-      if (!full && (cd.arg < 0 || is_con)) continue;
-      const float lambda =
-          is_con ? s.lambdas[((size_t)b * d.num_constraints + cd.slot) * d.T + s.lambda_index[kk]] : 0.f;
-      if (cd.arg < 0)
-        quadraticize_record<false>(d, cd, x, n, lambda, mu, nullptr, 0, l + i * n);
-      else
-        quadraticize_record<false>(d, cd, u + d.uoff[cd.arg], d.udim[cd.arg], lambda, mu, nullptr, 0,
-                                   r + d.pair_roff[cd.pair]);
-    }
-  }
-  for (int i = 0; i < N; i++) {
-    const int pii = d.pair_of[i][i], mi = d.udim[i];
-    float sq = 0.f;
-    for (int a = 0; a < mi; a++) sq = fmaf(r[d.pair_roff[pii] + a], r[d.pair_roff[pii] + a], sq);
-    terms[kk * 2 * N + 2 * i] = sq;
-    float sq2 = 0.f;
-    if (kk > 0)
-      for (int a = 0; a < n; a++) sq2 = fmaf(l[i * n + a], l[i * n + a], sq2);
-    terms[kk * 2 * N + 2 * i + 1] = sq2;
-  }
-}
-
-template <int G, int NXMAX, int NPMAX>
-__device__ float merit_function(const TileG<G>& tile, const DevDesc& d, const Slab& s, int b,
-                                const float* xs, const float* us, float* terms) {
-  const int t = tile.thread_rank();
-  for (int kk = t; kk < d.T; kk += G)
-    merit_terms_step<NXMAX, NPMAX>(d, s, b, kk, xs + (size_t)kk * d.n, us + (size_t)kk * d.M, terms);
-  tile.sync();
-  float merit = 0.f;
-  if (t == 0) {
-    // single running fp32 accumulator in (k, i) order, as the reference
-    const int cnt = d.T * 2 * d.N;
-    for (int e = 0; e < cnt; e++) merit += terms[e];
-    merit = 0.5 * merit;
-  }
-  merit = tile.shfl(merit, 0);
-  tile.sync();
-  return merit;
-}
-
-// ILQSolver::TotalCosts, src/ilq_solver.cpp:220-257 (+ PlayerCost::Evaluate player_cost.cpp:128-144):
-// costs only, no constraints; first extreme wins (strict comparisons).
-template <int G>
-__device__ void total_costs(const TileG<G>& tile, const DevDesc& d, const Slab& s, int b,
-                            const float* xs, const float* us, float* vals) {
-  const int t = tile.thread_rank(), n = d.n, M = d.M, N = d.N;
-  for (int kk = t; kk < d.T; kk += G) {
-    const float* x = xs + (size_t)kk * n;
-    const float* u = us + (size_t)kk * M;
-    for (int i = 0; i < N; i++) {
-      float total = 0.f;
-      for (int c = d.cost_begin[i]; c < d.cost_begin[i + 1]; c++) {
-        const DevCost& cd = d.cost[c];
-        if (cd.slot >= 0) continue;
-        total += cd.arg < 0 ? evaluate_record(d, cd, x, n)
-                            : evaluate_record(d, cd, u + d.uoff[cd.arg], d.udim[cd.arg]);
-      }
-      vals[kk * N + i] = total;
-    }
-  }
-  tile.sync();
-  for (int i = t; i < N; i += G) {
-    const int cs = d.cost_structure[i];
-    float total = cs == ILQG_COST_SUM ? 0.f : cs == ILQG_COST_MAX ? -INFINITY : INFINITY;
-    int te = s.te_new[(size_t)b * N + i];
-    for (int kk = 0; kk < d.T; kk++) {
-      const float cur = vals[kk * N + i];
-      if (cs == ILQG_COST_SUM)
-        total += cur;
-      else if (cs == ILQG_COST_MAX && cur > total) {
-        total = cur;
-        te = kk;
-      } else if (cs == ILQG_COST_MIN && cur < total) {
-        total = cur;
-        te = kk;
-      }
-    }
-    s.total_costs[(size_t)b * N + i] = total;
-    s.te_new[(size_t)b * N + i] = te;
-  }
-  tile.sync();
-}
-
-template <int G>
-__device__ __forceinline__ float* tile_smem(float* smem, const DevDesc& d, int tile_in_block) {
-  const int per = round4(2 * d.n + d.M) + round4(d.T * 2 * d.N);
-  return smem + (size_t)tile_in_block * per;
-}
-
-constexpr int KLS_THREADS = 128;
-
-// ILQSolver::Solve prologue, src/ilq_solver.cpp:86-107.
-template <int G, int NXMAX, int NPMAX>
-__global__ void __launch_bounds__(KLS_THREADS)
-k_solve_begin(const __grid_constant__ DevDesc d, const DevParams p, Slab s) {
-  extern __shared__ __align__(16) float smem[];
-  cg::thread_block block = cg::this_thread_block();
-  TileG<G> tile = cg::tiled_partition<G>(block);
-  const int b = blockIdx.x * (KLS_THREADS / G) + tile.meta_group_rank();
-  if (b >= s.B) return;
-  float* sm = tile_smem<G>(smem, d, tile.meta_group_rank());
-  float* scratch = sm + round4(2 * d.n + d.M);
-  const int T = d.T, n = d.n, M = d.M, t = tile.thread_rank();
-  // current strategies <- problem strategies
-  float* P0 = s.st_P[0] + (size_t)b * T * M * n;
-  float* a0 = s.st_a[0] + (size_t)b * T * M;
-  const float* pP = s.prob_P + (size_t)b * T * M * n;
-  const float* pa = s.prob_a + (size_t)b * T * M;
-  for (int e = t; e < T * M * n; e += G) P0[e] = pP[e];
-  for (int e = t; e < T * M; e += G) a0[e] = pa[e];
-  tile.sync();
-  float* oxs = s.op_xs[0] + (size_t)b * T * n;
-  float* ous = s.op_us[0] + (size_t)b * T * M;
-  rollout<G>(tile, d, sm, s.prob_xs + (size_t)b * T * n, s.prob_us + (size_t)b * T * M,
-             s.x0 + (size_t)b * n, pP, pa, false, 1.f, 1.f, 0, oxs, ous);
-  total_costs<G>(tile, d, s, b, oxs, ous, scratch);
-  if (t == 0) {
-    s.op_cur[b] = 0;
-    s.st_cur[b] = 0;
-    s.iters[b] = 0;
-    s.status[b] = p.max_solver_iters > 0 ? ILQG_STATUS_RUNNING : ILQG_STATUS_MAX_ITERS;
-  }
-  for (int i = t; i < d.N; i += G) s.te_quad[(size_t)b * d.N + i] = s.te_new[(size_t)b * d.N + i];
-}
-
-// ILQSolver::ModifyLQStrategies (src/ilq_solver.cpp:289-348) + TotalCosts (:158) + loop exit
-// bookkeeping (:123-124, 168-171).
-template <int G, int NXMAX, int NPMAX>
-__global__ void __launch_bounds__(KLS_THREADS)
-k_linesearch(const __grid_constant__ DevDesc d, const DevParams p, Slab s) {
-  extern __shared__ __align__(16) float smem[];
-  cg::thread_block block = cg::this_thread_block();
-  TileG<G> tile = cg::tiled_partition<G>(block);
-  const int b = blockIdx.x * (KLS_THREADS / G) + tile.meta_group_rank();
-  if (b >= s.B) return;
-  if (s.status[b] != ILQG_STATUS_RUNNING) return;
-  float* sm = tile_smem<G>(smem, d, tile.meta_group_rank());
-  float* scratch = sm + round4(2 * d.n + d.M);
-  const int T = d.T, n = d.n, M = d.M, t = tile.thread_rank();
-  const int cur = s.op_cur[b], scur = s.st_cur[b];
-  const float* last_xs = s.op_xs[cur] + (size_t)b * T * n;
-  const float* last_us = s.op_us[cur] + (size_t)b * T * M;
-  float* cxs = s.op_xs[1 - cur] + (size_t)b * T * n;
-  float* cus = s.op_us[1 - cur] + (size_t)b * T * M;
-  const float* P = s.st_P[1 - scur] + (size_t)b * T * M * n;
-  float* alpha = s.st_a[1 - scur] + (size_t)b * T * M;
-  const float ed = s.expected_decrease[b];
-  const float lm = s.last_merit[b];
-  const float s0 = p.initial_alpha_scaling, rho = p.geometric_alpha_scaling;
-  float step = s0;
-  int nscale = 0, nroll = 1;
-  bool accept = false, converged = false;
-  float new_merit = lm;
-  rollout<G>(tile, d, sm, last_xs, last_us, last_xs, P, alpha, true, s0, rho, 0, cxs, cus);
-  if (!p.linesearch) {
-    accept = true;
-  } else {
-    for (int ii = 0; ii < p.max_backtracking_steps; ii++) {
-      const float merit = merit_function<G, NXMAX, NPMAX>(tile, d, s, b, cxs, cus, scratch);
-      // CheckArmijoCondition :350-362
-      const float scaled_expected_decrease = p.expected_decrease_fraction * step * ed;
-      if (lm - merit >= scaled_expected_decrease) {
-        accept = true;
-        converged = (merit <= lm) && fabsf(lm - merit) < p.convergence_tolerance;  // ilq_solver.h:126-130
-        new_merit = merit;
-        break;
-      }
-      nscale++;
-      step *= rho;
-      rollout<G>(tile, d, sm, last_xs, last_us, last_xs, P, alpha, true, s0, rho, nscale, cxs, cus);
-      nroll++;
-    }
-  }
-  if (accept) {
-    // the scaled LQ strategies become the current strategies
-    for (int e = t; e < T * M; e += G) {
-      float al = alpha[e] * s0;
-      for (int j = 0; j < nscale; j++) al *= rho;
-      alpha[e] = al;
-    }
-    tile.sync();
-    total_costs<G>(tile, d, s, b, cxs, cus, scratch);
-  }
-  if (t == 0) {
-    const int it = s.iters[b] + 1;
-    s.iters[b] = it;
-    s.backtracks[b] += nroll;
-    if (accept) {
-      s.op_cur[b] = 1 - cur;
-      s.st_cur[b] = 1 - scur;
-      s.last_merit[b] = new_merit;
-      s.step[b] = step;
-      if (converged && !p.disable_convergence_exit)
-        s.status[b] = ILQG_STATUS_CONVERGED;
-      else if (it >= p.max_solver_iters)
-        s.status[b] = ILQG_STATUS_MAX_ITERS;
-    } else {
-      s.status[b] = ILQG_STATUS_LINESEARCH_FAILED;  // the log's final iterate stays current
-    }
-  }
 }
 
 // ===========================================================================

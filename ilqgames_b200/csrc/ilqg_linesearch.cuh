@@ -1,0 +1,456 @@
+// ilqg_linesearch.cuh -- K_ls: ILQSolver::ModifyLQStrategies (src/ilq_solver.cpp:289-348) as a
+// speculative, role-specialised pipeline, plus the Solve() prologue built from the same kernel.
+//
+// The reference backtracks sequentially: roll out with alpha * s0 * rho^j, evaluate the merit,
+// test Armijo, repeat.  Candidate j's trajectory and merit depend only on j, never on the
+// outcome of candidates < j, so evaluating several candidates at once and taking the FIRST one
+// that passes Armijo gives exactly the sequential result.  Phases per linesearch:
+//   A  candidates j in [0, JA)       for every running instance        (eval + decide)
+//   B  candidates j in [JA, max_bt)  for instances that rejected all of A (eval + decide)
+//   C  re-roll of the accepted candidate for instances accepted in B   (eval + finalize)
+// Phases B and C launch worst-case grids that exit at once when their device-side work lists
+// are empty, so the host never synchronises.
+//
+// k_ls_eval maps one (instance, candidate) ITEM to one lane, and one ROLE to each warp of the
+// block: warps [0, S) integrate subsystem s (u = u_ref - P dx - alpha, then RK4 x 2 substeps),
+// warps [S, S + N) evaluate player i's cost gradients and values one timestep behind, reading
+// the state/control double buffer in shared memory.  Every warp executes uniform code (same
+// subsystem kind / same player's records), so there is no role divergence inside a warp.
+#pragma once
+#include "ilqg_backward.cuh"
+
+namespace ilqg {
+
+enum { LS_MODE_BEGIN = 0, LS_MODE_A = 1, LS_MODE_B = 2, LS_MODE_C = 3 };
+enum { LS_COUNT_PENDING = 0, LS_COUNT_COMMIT = 1 };
+
+struct LsScratch {
+  float* traj_xs;   // [B * JA][T][n]   phase-A candidate trajectories
+  float* traj_us;   // [B * JA][T][M]
+  float* terms;     // [blocks][T][2N][32]  merit terms, item = lane of its block
+  float* vals;      // [blocks][T][N][32]   per-player cost values
+  float* merit;     // [items]
+  int* pending;     // [B] instances that rejected every phase-A candidate
+  int* commit;      // [B] instances accepted in phase B (need a re-roll)
+  int* accept_j;    // [B]
+  int* counts;      // [2]
+  int JA;
+};
+
+struct LsItem {
+  int b, j;
+  bool valid;
+};
+
+__device__ __forceinline__ LsItem ls_decode(const Slab& s, const LsScratch& ls, int mode, int item,
+                                            int jbase, int jcount) {
+  LsItem it;
+  it.b = 0;
+  it.j = 0;
+  it.valid = false;
+  switch (mode) {
+    case LS_MODE_BEGIN:
+      it.b = item;
+      it.valid = item < s.B;
+      break;
+    case LS_MODE_A:
+      it.b = item / jcount;
+      it.j = jbase + item % jcount;
+      it.valid = it.b < s.B && s.status[it.b] == ILQG_STATUS_RUNNING;
+      break;
+    case LS_MODE_B: {
+      const int p = item / jcount;
+      it.valid = p < ls.counts[LS_COUNT_PENDING];
+      if (it.valid) it.b = ls.pending[p];
+      it.j = jbase + item % jcount;
+      break;
+    }
+    case LS_MODE_C:
+      it.valid = item < ls.counts[LS_COUNT_COMMIT];
+      if (it.valid) {
+        it.b = ls.commit[item];
+        it.j = ls.accept_j[it.b];
+      }
+      break;
+  }
+  return it;
+}
+
+__device__ __forceinline__ void named_barrier_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// Shared memory per block (floats), lane-minor so every access is conflict-free:
+//   xu[2][n + M][32]   state/control double buffer (dynamics -> cost warps)
+//   dx[n][32]          x - x_ref of the current step (between dynamics warps)
+//   acc[N][n + M][32]  per-player gradient accumulators (l_i over the state, r_ij over controls)
+__host__ __device__ inline int ls_smem_floats(int n, int M, int N) {
+  return (2 * (n + M) + n + N * (n + M)) * 32;
+}
+
+__global__ void __launch_bounds__(256)
+k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode,
+          int jbase, int jcount) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = d.n, M = d.M, N = d.N, T = d.T, S = d.num_subsystems;
+  const int item = blockIdx.x * 32 + lane;
+  const LsItem it = ls_decode(s, ls, mode, item, jbase, jcount);
+  if (!__syncthreads_or(it.valid)) return;
+  const bool valid = it.valid;
+  const int b = it.b;
+
+  float* xu = smem;                      // [2][n+M][32]
+  float* dxs = xu + 2 * (n + M) * 32;    // [n][32]
+  float* accs = dxs + n * 32;            // [N][n+M][32]
+
+  // ---- per-item sources / destinations ----
+  const size_t ox = (size_t)b * T * n, ou = (size_t)b * T * M, oP = (size_t)b * T * M * n;
+  const float *last_xs, *last_us, *P, *alpha, *x_start;
+  float *out_xs = nullptr, *out_us = nullptr;
+  bool scaled = true;
+  if (mode == LS_MODE_BEGIN) {
+    last_xs = s.prob_xs + ox;
+    last_us = s.prob_us + ou;
+    P = s.prob_P + oP;
+    alpha = s.prob_a + ou;
+    x_start = s.x0 + (size_t)b * n;
+    scaled = false;
+    out_xs = s.op_xs[0] + ox;
+    out_us = s.op_us[0] + ou;
+  } else {
+    const int cur = valid ? s.op_cur[b] : 0, scur = valid ? s.st_cur[b] : 0;
+    last_xs = s.op_xs[cur] + ox;
+    last_us = s.op_us[cur] + ou;
+    P = s.st_P[1 - scur] + oP;
+    alpha = s.st_a[1 - scur] + ou;
+    x_start = last_xs;
+    if (mode == LS_MODE_A) {
+      out_xs = ls.traj_xs + (size_t)item * T * n;
+      out_us = ls.traj_us + (size_t)item * T * M;
+    } else if (mode == LS_MODE_C) {
+      out_xs = s.op_xs[1 - cur] + ox;
+      out_us = s.op_us[1 - cur] + ou;
+    }
+  }
+  const float s0 = p.initial_alpha_scaling, rho = p.geometric_alpha_scaling;
+  const float dt_half = (float)(d.time_step / 2.0);
+  float* terms = ls.terms + (size_t)blockIdx.x * T * 2 * N * 32;
+  float* vals = ls.vals + (size_t)blockIdx.x * T * N * 32;
+
+  if (warp < S) {
+    // =================== dynamics role: subsystem `warp` ===================
+    const DevSubsystem& sub = d.sub[warp];
+    const int xd = subsystem_xdim(sub.kind);
+    const int nu = sub.kind == ILQG_DYN_AIR3D ? 2 : d.udim[sub.first_player];  // own control rows
+    float x[6];
+#pragma unroll
+    for (int a = 0; a < 6; a++) x[a] = (valid && a < xd) ? x_start[sub.x_offset + a] : 0.f;
+    for (int k = 0; k <= T; k++) {
+      if (k < T) {
+        float* slot = xu + (k & 1) * (n + M) * 32;
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+          if (a < xd) {
+            // last_operating_point.xs[0] is the start state (src/ilq_solver.cpp:88-89)
+            const float ref = (valid && k > 0) ? last_xs[(size_t)k * n + sub.x_offset + a]
+                                               : (valid ? x_start[sub.x_offset + a] : 0.f);
+            dxs[(sub.x_offset + a) * 32 + lane] = x[a] - ref;
+            slot[(sub.x_offset + a) * 32 + lane] = x[a];
+            if (valid && out_xs) out_xs[(size_t)k * n + sub.x_offset + a] = x[a];
+          }
+        named_barrier_sync(1, S * 32);
+        float uu[2] = {0.f, 0.f};
+        for (int q = 0; q < nu; q++) {
+          const int c = q == 0 ? sub.u_offset : sub.u_offset2;
+          float uv = 0.f;
+          if (valid) {
+            const float4* Prow = reinterpret_cast<const float4*>(P + ((size_t)k * M + c) * n);
+            float acc = 0.f;
+            if ((n & 3) == 0) {
+              for (int a4 = 0; a4 < n / 4; a4++) {
+                const float4 pv = __ldg(Prow + a4);
+                acc = fmaf(pv.x, dxs[(4 * a4 + 0) * 32 + lane], acc);
+                acc = fmaf(pv.y, dxs[(4 * a4 + 1) * 32 + lane], acc);
+                acc = fmaf(pv.z, dxs[(4 * a4 + 2) * 32 + lane], acc);
+                acc = fmaf(pv.w, dxs[(4 * a4 + 3) * 32 + lane], acc);
+              }
+            } else {
+              const float* Pr = P + ((size_t)k * M + c) * n;
+              for (int a = 0; a < n; a++) acc = fmaf(__ldg(Pr + a), dxs[a * 32 + lane], acc);
+            }
+            float al = alpha[(size_t)k * M + c];
+            if (scaled) {
+              al *= s0;  // ScaleAlphas(initial_alpha_scaling), then geometric_alpha_scaling^j
+              for (int jj = 0; jj < it.j; jj++) al *= rho;
+            }
+            uv = last_us[(size_t)k * M + c] - acc - al;  // Strategy::operator(), strategy.h:73-76
+            if (out_us) out_us[(size_t)k * M + c] = uv;
+          }
+          slot[(n + c) * 32 + lane] = uv;
+          uu[q] = uv;
+        }
+        if (k < T - 1) subsystem_integrate(sub, dt_half, x, uu[0], uu[1]);
+      }
+      __syncthreads();
+    }
+  } else if (warp < S + N) {
+    // =================== cost role: player `warp - S`, one step behind ===================
+    const int i = warp - S;
+    float* acc = accs + (size_t)i * (n + M) * 32;
+    const float mu = valid ? s.mu[b] : 0.f;
+    const int te = valid ? s.te_quad[(size_t)b * N + i] : 0;
+    const bool additive = d.cost_structure[i] == ILQG_COST_SUM;
+    const int pii = d.pair_of[i][i], mi = d.udim[i];
+    for (int k = 0; k <= T; k++) {
+      if (k >= 1) {
+        const int kk = k - 1;
+        const float* slot = xu + (kk & 1) * (n + M) * 32;
+        for (int a = 0; a < n + M; a++) acc[a * 32 + lane] = 0.f;
+        const bool full = additive || te == kk;
+        float value = 0.f;
+        for (int c = d.cost_begin[i]; c < d.cost_begin[i + 1]; c++) {
+          const DevCost& cd = d.cost[c];
+          const bool is_con = cd.slot >= 0;
+          float v = 0.f;
+          const bool in_quad = full || (cd.arg >= 0 && !is_con);  // QuadraticizeControlCosts
+          if (cd.arg < 0) {
+            if (in_quad) {
+              const float lambda =
+                  (is_con && valid) ? s.lambdas[((size_t)b * d.num_constraints + cd.slot) * T + s.lambda_index[kk]] : 0.f;
+              quadraticize_record<false, 32, 32, true>(d, cd, slot + lane, n, lambda, mu, nullptr, 0,
+                                                        acc + lane, &v);
+            } else if (!is_con) {
+              v = evaluate_record<32>(d, cd, slot + lane, n);
+            }
+          } else {
+            const float* uin = slot + (n + d.uoff[cd.arg]) * 32 + lane;
+            if (in_quad) {
+              const float lambda =
+                  (is_con && valid) ? s.lambdas[((size_t)b * d.num_constraints + cd.slot) * T + s.lambda_index[kk]] : 0.f;
+              quadraticize_record<false, 32, 32, true>(d, cd, uin, d.udim[cd.arg], lambda, mu, nullptr,
+                                                        0, acc + (n + d.uoff[cd.arg]) * 32 + lane, &v);
+            } else if (!is_con) {
+              v = evaluate_record<32>(d, cd, uin, d.udim[cd.arg]);
+            }
+          }
+          if (!is_con) value += v;  // PlayerCost::Evaluate: costs only
+        }
+        // ILQSolver::MeritFunction terms (src/ilq_solver.cpp:416-430)
+        float sq = 0.f;
+        for (int a = 0; a < mi; a++) {
+          const float rv = acc[(n + d.uoff[i] + a) * 32 + lane];
+          sq = fmaf(rv, rv, sq);
+        }
+        float sq2 = 0.f;
+        if (kk > 0)
+          for (int a = 0; a < n; a++) {
+            const float lv = acc[a * 32 + lane];
+            sq2 = fmaf(lv, lv, sq2);
+          }
+        (void)pii;
+        terms[((size_t)kk * 2 * N + 2 * i) * 32 + lane] = sq;
+        terms[((size_t)kk * 2 * N + 2 * i + 1) * 32 + lane] = sq2;
+        vals[((size_t)kk * N + i) * 32 + lane] = value;
+      }
+      __syncthreads();
+    }
+  } else {
+    for (int k = 0; k <= T; k++) __syncthreads();
+  }
+  __syncthreads();
+  // single running fp32 accumulator in (k, i) order, as the reference
+  if (warp == S && valid) {
+    float merit = 0.f;
+    const int cnt = T * 2 * N;
+    for (int e = 0; e < cnt; e++) merit += terms[(size_t)e * 32 + lane];
+    ls.merit[item] = 0.5 * merit;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// accept-side bookkeeping shared by the decide / finalize kernels (one warp per instance)
+// ---------------------------------------------------------------------------
+// ILQSolver::TotalCosts (src/ilq_solver.cpp:220-257) from the per-step values an eval block left
+// behind: ordered over k, first extreme wins.
+__device__ __forceinline__ void ls_total_costs(const DevDesc& d, const Slab& s, int b, const float* vals_block,
+                                               int item_lane, int lane) {
+  const int N = d.N;
+  if (lane < N) {
+    const int i = lane, cs = d.cost_structure[i];
+    float total = cs == ILQG_COST_SUM ? 0.f : cs == ILQG_COST_MAX ? -INFINITY : INFINITY;
+    int te = s.te_new[(size_t)b * N + i];
+    for (int kk = 0; kk < d.T; kk++) {
+      const float cur = vals_block[((size_t)kk * N + i) * 32 + item_lane];
+      if (cs == ILQG_COST_SUM)
+        total += cur;
+      else if (cs == ILQG_COST_MAX && cur > total) {
+        total = cur;
+        te = kk;
+      } else if (cs == ILQG_COST_MIN && cur < total) {
+        total = cur;
+        te = kk;
+      }
+    }
+    s.total_costs[(size_t)b * N + i] = total;
+    s.te_new[(size_t)b * N + i] = te;
+  }
+}
+
+// the scaled LQ strategies become current; counters, merit, status (ilq_solver.cpp:331-336,158-171)
+__device__ __forceinline__ void ls_accept(const DevDesc& d, const DevParams& p, const Slab& s, int b, int j,
+                                          float merit, bool with_merit, int lane) {
+  const int T = d.T, M = d.M;
+  const int cur = s.op_cur[b], scur = s.st_cur[b];
+  float* alpha = s.st_a[1 - scur] + (size_t)b * T * M;
+  const float s0 = p.initial_alpha_scaling, rho = p.geometric_alpha_scaling;
+  for (int e = lane; e < T * M; e += 32) {
+    float al = alpha[e] * s0;
+    for (int jj = 0; jj < j; jj++) al *= rho;
+    alpha[e] = al;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    float step = s0;
+    for (int jj = 0; jj < j; jj++) step *= rho;
+    const float lm = s.last_merit[b];
+    const bool converged = with_merit && (merit <= lm) && fabsf(lm - merit) < p.convergence_tolerance;
+    const int itn = s.iters[b] + 1;
+    s.iters[b] = itn;
+    s.backtracks[b] += j + 1;
+    s.op_cur[b] = 1 - cur;
+    s.st_cur[b] = 1 - scur;
+    if (with_merit) s.last_merit[b] = merit;
+    s.step[b] = step;
+    if (converged && !p.disable_convergence_exit)
+      s.status[b] = ILQG_STATUS_CONVERGED;
+    else if (itn >= p.max_solver_iters)
+      s.status[b] = ILQG_STATUS_MAX_ITERS;
+  }
+}
+
+__device__ __forceinline__ void ls_fail(const DevParams& p, const Slab& s, int b) {
+  s.iters[b] += 1;
+  s.backtracks[b] += p.max_backtracking_steps + 1;  // the reference's last rollout is never evaluated
+  s.status[b] = ILQG_STATUS_LINESEARCH_FAILED;      // the log's final iterate stays current
+}
+
+// CheckArmijoCondition, src/ilq_solver.cpp:350-362
+__device__ __forceinline__ bool ls_armijo(const DevParams& p, float last_merit, float merit, float ed, int j) {
+  float step = p.initial_alpha_scaling;
+  for (int jj = 0; jj < j; jj++) step *= p.geometric_alpha_scaling;
+  const float scaled_expected_decrease = p.expected_decrease_fraction * step * ed;
+  return last_merit - merit >= scaled_expected_decrease;
+}
+
+constexpr int KDEC_WARPS = 4;
+
+// decide after phase A: one warp per instance
+__global__ void __launch_bounds__(KDEC_WARPS * 32)
+k_ls_decide_a(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * KDEC_WARPS + warp;
+  if (b >= s.B || s.status[b] != ILQG_STATUS_RUNNING) return;
+  const int JA = ls.JA, T = d.T, n = d.n, M = d.M;
+  const float lm = s.last_merit[b], ed = s.expected_decrease[b];
+  int acc_j = -1;
+  float acc_merit = 0.f;
+  if (!p.linesearch) {
+    acc_j = 0;
+  } else {
+    for (int j = 0; j < JA; j++) {
+      const float merit = ls.merit[(size_t)b * JA + j];
+      if (ls_armijo(p, lm, merit, ed, j)) {
+        acc_j = j;
+        acc_merit = merit;
+        break;
+      }
+    }
+  }
+  if (acc_j >= 0) {
+    const int item = b * JA + acc_j;
+    const int cur = s.op_cur[b];
+    float4* dxs = reinterpret_cast<float4*>(s.op_xs[1 - cur] + (size_t)b * T * n);
+    const float4* sxs = reinterpret_cast<const float4*>(ls.traj_xs + (size_t)item * T * n);
+    float* dus = s.op_us[1 - cur] + (size_t)b * T * M;
+    const float* sus = ls.traj_us + (size_t)item * T * M;
+    if ((T * n) % 4 == 0) {
+      for (int e = lane; e < T * n / 4; e += 32) dxs[e] = sxs[e];
+    } else {
+      for (int e = lane; e < T * n; e += 32)
+        (s.op_xs[1 - cur] + (size_t)b * T * n)[e] = (ls.traj_xs + (size_t)item * T * n)[e];
+    }
+    for (int e = lane; e < T * M; e += 32) dus[e] = sus[e];
+    ls_total_costs(d, s, b, ls.vals + (size_t)(item / 32) * T * d.N * 32, item % 32, lane);
+    __syncwarp();
+    ls_accept(d, p, s, b, acc_j, acc_merit, p.linesearch != 0, lane);
+  } else if (lane == 0) {
+    if (JA >= p.max_backtracking_steps) {
+      ls_fail(p, s, b);
+    } else {
+      const int slot = atomicAdd(&ls.counts[LS_COUNT_PENDING], 1);
+      ls.pending[slot] = b;
+    }
+  }
+}
+
+// decide after phase B: one thread per pending instance
+__global__ void k_ls_decide_b(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls,
+                              int jbase, int jcount) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= ls.counts[LS_COUNT_PENDING]) return;
+  const int b = ls.pending[q];
+  const float lm = s.last_merit[b], ed = s.expected_decrease[b];
+  for (int jj = 0; jj < jcount; jj++) {
+    const float merit = ls.merit[(size_t)q * jcount + jj];
+    if (ls_armijo(p, lm, merit, ed, jbase + jj)) {
+      ls.accept_j[b] = jbase + jj;
+      const int slot = atomicAdd(&ls.counts[LS_COUNT_COMMIT], 1);
+      ls.commit[slot] = b;
+      return;
+    }
+  }
+  ls_fail(p, s, b);
+}
+
+// finalize after phase C (trajectory already in the operating-point buffer): one warp per commit slot
+__global__ void __launch_bounds__(KDEC_WARPS * 32)
+k_ls_finalize_c(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * KDEC_WARPS + warp;
+  if (q >= ls.counts[LS_COUNT_COMMIT]) return;
+  const int b = ls.commit[q];
+  ls_total_costs(d, s, b, ls.vals + (size_t)(q / 32) * d.T * d.N * 32, q % 32, lane);
+  __syncwarp();
+  ls_accept(d, p, s, b, ls.accept_j[b], ls.merit[q], true, lane);
+}
+
+// Solve() prologue bookkeeping (src/ilq_solver.cpp:86-107) after the LS_MODE_BEGIN rollout
+__global__ void __launch_bounds__(KDEC_WARPS * 32)
+k_begin_finalize(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * KDEC_WARPS + warp;
+  if (b >= s.B) return;
+  const int T = d.T, n = d.n, M = d.M, N = d.N;
+  // current strategies <- problem strategies
+  const float4* pP = reinterpret_cast<const float4*>(s.prob_P + (size_t)b * T * M * n);
+  float4* P0 = reinterpret_cast<float4*>(s.st_P[0] + (size_t)b * T * M * n);
+  if ((T * M * n) % 4 == 0) {
+    for (int e = lane; e < T * M * n / 4; e += 32) P0[e] = pP[e];
+  } else {
+    for (int e = lane; e < T * M * n; e += 32)
+      (s.st_P[0] + (size_t)b * T * M * n)[e] = (s.prob_P + (size_t)b * T * M * n)[e];
+  }
+  for (int e = lane; e < T * M; e += 32) (s.st_a[0] + (size_t)b * T * M)[e] = (s.prob_a + (size_t)b * T * M)[e];
+  ls_total_costs(d, s, b, ls.vals + (size_t)(b / 32) * T * N * 32, b % 32, lane);
+  __syncwarp();
+  if (lane < N) s.te_quad[(size_t)b * N + lane] = s.te_new[(size_t)b * N + lane];
+  if (lane == 0) {
+    s.op_cur[b] = 0;
+    s.st_cur[b] = 0;
+    s.iters[b] = 0;
+    s.status[b] = p.max_solver_iters > 0 ? ILQG_STATUS_RUNNING : ILQG_STATUS_MAX_ITERS;
+  }
+}
+
+}  // namespace ilqg

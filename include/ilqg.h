@@ -307,6 +307,27 @@ int ilqg_al_post_solve(ilqg_handle h);
 int ilqg_download(ilqg_handle h, int what, void* dst, size_t bytes);
 int ilqg_synchronize(ilqg_handle h);
 
+/* Re-initialise per-instance state without reallocating.  `mask` bits:
+ *   ILQG_RESET_SOLVER       last merit / expected decrease = +inf: a freshly constructed
+ *                           ILQSolver (ilq_solver.h:69-74; see SURVEY Q8 for why this matters)
+ *   ILQG_RESET_MULTIPLIERS  lambda = 0, mu = 10 (augmented_lagrangian_solver.cpp:196-207)
+ *   ILQG_RESET_SOLUTION     zero operating point and strategies (Problem::Initialize) */
+enum { ILQG_RESET_SOLVER = 1, ILQG_RESET_MULTIPLIERS = 2, ILQG_RESET_SOLUTION = 4 };
+int ilqg_reset(ilqg_handle h, int mask);
+
+/* Run this handle's kernels and copies on the caller's CUDA stream (a cudaStream_t passed as
+ * a plain pointer; NULL restores the handle's own stream).  Lets a host framework order and
+ * time the work with its own events. */
+int ilqg_set_stream(ilqg_handle h, void* cuda_stream);
+
+/* Per-kernel device timing for the roofline report: when enabled, every hot-path launch is
+ * bracketed by CUDA events on the launch stream.  ilqg_profile_read synchronizes and returns
+ * the accumulated milliseconds and launch count of one kernel kind
+ * (0 = linearize_quadraticize, 1 = lq_backward, 2 = linesearch, 3 = solve_begin) since the
+ * last ilqg_profile(h, 1). */
+int ilqg_profile(ilqg_handle h, int enable);
+int ilqg_profile_read(ilqg_handle h, int kernel, double* total_ms, long long* launches);
+
 /* Launch accounting for bench.py ("gpu_launches"): number of kernels this
  * handle has launched since creation (0 for the oracle). */
 int ilqg_kernel_launches(ilqg_handle h, long long* out);

@@ -1646,6 +1646,35 @@ int ilqg_download(ilqg_handle h, int what, void* dst, size_t bytes) {
 
 int ilqg_synchronize(ilqg_handle h) { return h ? ILQG_OK : ILQG_ERR_BAD_HANDLE; }
 
+int ilqg_reset(ilqg_handle h, int mask) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  for (auto& in : h->inst) {
+    if (mask & ILQG_RESET_SOLVER) {
+      in.last_merit = kInfinity;
+      in.expected_decrease = kInfinity;
+    }
+    if (mask & ILQG_RESET_MULTIPLIERS) {
+      std::fill(in.lambdas.begin(), in.lambdas.end(), (real)0);
+      in.mu = kDefaultMu;
+    }
+    if (mask & ILQG_RESET_SOLUTION) {
+      for (auto* v : {&in.prob_xs, &in.prob_us, &in.prob_Ps, &in.prob_alphas, &in.xs, &in.us, &in.Ps,
+                      &in.alphas})
+        std::fill(v->begin(), v->end(), (real)0);
+    }
+  }
+  return ILQG_OK;
+}
+
+int ilqg_set_stream(ilqg_handle h, void*) { return h ? ILQG_OK : ILQG_ERR_BAD_HANDLE; }
+int ilqg_profile(ilqg_handle h, int) { return h ? ILQG_OK : ILQG_ERR_BAD_HANDLE; }
+int ilqg_profile_read(ilqg_handle h, int, double* total_ms, long long* launches) {
+  if (!h || !total_ms || !launches) return ILQG_ERR_BAD_HANDLE;
+  *total_ms = 0;
+  *launches = 0;
+  return ILQG_OK;
+}
+
 int ilqg_kernel_launches(ilqg_handle h, long long* out) {
   if (!h || !out) return ILQG_ERR_BAD_HANDLE;
   *out = 0;

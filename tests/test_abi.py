@@ -1,0 +1,87 @@
+"""CPU-side checks of the C-ABI boundary: the product library loads, exports every symbol
+include/ilqg.h declares, agrees with the ctypes mirror on struct sizes, validates descriptors,
+and refuses to compute without a CUDA device (no CPU fallback).  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from ilqgames_b200 import _abi as abi
+from ilqgames_b200 import build as b
+from ilqgames_b200 import problems
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def product_lib():
+    b.build()
+    lib = abi.Library(abi.PRODUCT_LIB)
+    return lib
+
+
+def _declared_symbols():
+    text = open(os.path.join(REPO, "include", "ilqg.h")).read()
+    return sorted(set(re.findall(r"\b(ilqg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_match_binding_table():
+    assert _declared_symbols() == sorted(abi.ABI_SYMBOLS)
+
+
+@pytest.mark.parametrize("which", ["product", "oracle"])
+def test_library_exports_every_declared_symbol(which, product_lib, oracle):
+    lib = product_lib if which == "product" else oracle
+    for sym in _declared_symbols():
+        assert hasattr(lib.lib, sym), f"{lib.path} does not export {sym}"
+    lib.verify_struct_sizes()
+
+
+def test_product_has_no_cpu_fallback(product_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    desc, _ = problems.three_player_intersection()
+    h = C.c_void_p()
+    rc = product_lib.lib.ilqg_create(C.byref(desc), C.byref(abi.SolverParams.defaults()), 4, 0, C.byref(h))
+    assert rc == -4  # ILQG_ERR_NO_DEVICE
+    assert b"no CUDA device" in product_lib.lib.ilqg_strerror(rc)
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    with pytest.raises(abi.IlqgError, match="no CPU fallback"):
+        abi.Library(str(tmp_path / "libilqg_b200.so"))
+
+
+@pytest.mark.parametrize("which", ["product", "oracle"])
+def test_invalid_descriptors_are_rejected(which, product_lib, oracle):
+    lib = product_lib if which == "product" else oracle
+    p = abi.SolverParams.defaults()
+    h = C.c_void_p()
+    desc, _ = problems.three_player_intersection()
+    assert lib.lib.ilqg_create(None, C.byref(p), 1, 0, C.byref(h)) == -1
+    assert lib.lib.ilqg_create(C.byref(desc), C.byref(p), 0, 0, C.byref(h)) == -1
+    bad = abi.ProblemDesc.from_buffer_copy(desc)
+    bad.num_time_steps = 1
+    assert lib.lib.ilqg_create(C.byref(bad), C.byref(p), 1, 0, C.byref(h)) == -1
+    bad = abi.ProblemDesc.from_buffer_copy(desc)
+    bad.costs[0].player = 7
+    assert lib.lib.ilqg_create(C.byref(bad), C.byref(p), 1, 0, C.byref(h)) == -1
+    ol = abi.SolverParams.defaults(open_loop=1)  # LQOpenLoopSolver is not on this path
+    assert lib.lib.ilqg_create(C.byref(desc), C.byref(ol), 1, 0, C.byref(h)) == -2
+
+
+def test_descriptor_shapes_of_the_three_configs(oracle):
+    # SURVEY.md section 8 shape table (reference-true shapes)
+    for build, N, n, M, ncon, ncost in ((problems.three_player_intersection, 3, 16, 6, 6, 18),
+                                        (problems.roundabout_merging, 4, 24, 8, 0, 44),
+                                        (problems.air_3d, 2, 3, 2, 4, 8)):
+        desc, x0 = build()
+        h = abi.Handle(oracle, desc, abi.SolverParams.defaults(), 1)
+        assert (h.N, h.n, h.M, h.T) == (N, n, M, 100)
+        assert h.layout.num_constraints == ncon
+        assert desc.num_costs == ncost
+        assert x0.shape == (n,)
+        h.close()

@@ -1,0 +1,298 @@
+"""GPU parity tests proper: the sm_100a library, called through the C ABI, against the CPU oracle
+on identical seeded inputs, against the committed golden fixtures, and -- at BASELINE.json's full
+batch size -- through size-independent properties.
+
+Tolerances (fp32 path; SURVEY.md section 7 "hard parts"):
+  * integer / index outputs (status, iteration and rollout counts, extreme-time indices,
+    lambda index map): bit-exact;
+  * one stage on identical inputs (records, LQ solution, rollout): 1e-4 of the array's max-abs
+    scale.  Measured on B200: <= 2e-6, and the fp64 build of the oracle shows the CUDA path and
+    the fp32 oracle are equally far (same order) from the fp64 answer;
+  * multi-iteration trajectories: instances whose control flow (Armijo decisions) matches are
+    compared at 2e-2 absolute; an Armijo flip on a knife edge is legitimate
+    and is bounded by a minimum matching fraction instead.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from ilqgames_b200 import _abi as abi
+from ilqgames_b200 import problems
+from tests.test_oracle_pins import lq_test_system, lyapunov_iterations
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+STAGE_TOL = 1e-4
+
+CONFIGS = {
+    "three_player_intersection": (problems.three_player_intersection,
+                                  problems.three_player_intersection_params,
+                                  lambda b: problems.three_player_intersection_x0_batch(b, 1024)),
+    "roundabout_merging": (problems.roundabout_merging, problems.roundabout_params,
+                           lambda b: problems.roundabout_x0_batch(b, 4096)),
+    "air_3d": (problems.air_3d, problems.air_3d_params, lambda b: problems.air_3d_x0_grid(4)[:b]),
+}
+
+
+def tame(ref, limit=1e6):
+    """Per-instance mask: the oracle's values are finite and below `limit`.  Some sampled games
+    are numerically unstable in the reference algorithm itself (indefinite proximity Hessians make
+    the Riccati recursion grow to fp32 overflow -- the fp64 oracle reaches 1e72); where the oracle
+    overflows, fp32 rounding decides which entries are inf/nan and there is nothing to compare."""
+    r = np.asarray(ref, np.float64).reshape(len(ref), -1)
+    return np.isfinite(r).all(axis=1) & (np.abs(r).max(axis=1, initial=0.0) < limit)
+
+
+def close(a, b, tol=STAGE_TOL, what="", atol=1e-5, rows=None):
+    """max|a - b| <= tol * max|b| + atol per instance row (norm-wise; atol absorbs cancellation
+    to ~0), over the rows where the oracle is tame."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    assert a.shape == b.shape
+    keep = tame(b) if rows is None else (rows & tame(b))
+    if a.ndim == 1:
+        a, b = a[:, None], b[:, None]
+    a, b = a[keep].reshape(keep.sum(), -1), b[keep].reshape(keep.sum(), -1)
+    if a.size == 0:
+        return
+    scale = np.abs(b).max(axis=1)
+    err = np.abs(a - b).max(axis=1)
+    bad = ~(err <= tol * scale + atol)
+    assert not bad.any(), (f"{what}: worst row max|d| = {np.nanmax(err[bad]) if bad.any() else 0:.3e}, "
+                           f"scale = {scale[bad][0]:.3e}, {bad.sum()} of {len(bad)} rows")
+
+
+def pair(product, oracle, name, batch, **param_overrides):
+    build, params, x0f = CONFIGS[name]
+    desc, _ = build()
+    x0 = x0f(batch)
+    hs = []
+    for lib in (product, oracle):
+        h = abi.Handle(lib, desc, params(**param_overrides), x0.shape[0], 0)
+        h.upload_x0(x0)
+        hs.append(h)
+    return hs
+
+
+# ------------------------------------------------------------------ index logic
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_layout_and_index_maps_bit_exact(product, oracle, name):
+    c, o = pair(product, oracle, name, 2)
+    for field in ("num_time_steps", "num_players", "xdim", "total_udim", "num_pairs", "R_floats",
+                  "r_floats", "num_constraints"):
+        assert getattr(c.layout, field) == getattr(o.layout, field), field
+    for arr in ("udim", "u_offset", "pair_player", "pair_arg", "pair_R_offset", "pair_r_offset",
+                "lambda_index"):
+        assert list(getattr(c.layout, arr)) == list(getattr(o.layout, arr)), arr
+    assert c.layout.record_floats % 4 == 0 and c.layout.record_floats > 0
+
+
+# ------------------------------------------------------------------ LQ solve
+@pytest.mark.parametrize("nominal", [0.0, 0.5])
+def test_lq_backward_reference_test_system(product, oracle, nominal):
+    # LQFeedbackSolverTest.MatchesLyapunovIterations (test/test_lq_solver.cpp:292-317) on the GPU
+    desc = problems.lq_only(100, 2, [1, 1], cross_pairs=[(0, 1), (1, 0)])
+    arrs, (A, B1, B2, Q, R) = lq_test_system(nominal)
+    outs = []
+    for lib in (product, oracle):
+        h = abi.Handle(lib, desc, abi.SolverParams.defaults(), 1)
+        h.upload_lq(**arrs)
+        h.lq_backward()
+        outs.append((h.download(abi.LQ_PS)[0], h.download(abi.LQ_ALPHAS)[0]))
+        h.close()
+    (Pc, ac), (Po, ao) = outs
+    close(Pc, Po, what="P")
+    close(ac, ao, tol=1e-5 if nominal else 1.0, what="alpha")
+    one = lambda v: np.array([[v]])
+    P1, P2 = lyapunov_iterations(A, B1, B2, Q[0], Q[1], one(R[0]), one(R[1]), one(R[2]), one(R[3]))
+    assert np.abs(P1 - Pc[0, 0:1]).max() < 1e-4  # kSmallNumber, the reference's own tolerance
+    assert np.abs(P2 - Pc[0, 1:2]).max() < 1e-4
+    assert np.all(Pc[-1] == 0) and np.all(ac[-1] == 0)
+
+
+def test_lq_backward_gershgorin_and_batch(product, oracle):
+    # random LQ games where the adaptive regularisation fires (indefinite R) -- batch of 5
+    rng = np.random.default_rng(5)
+    B, T, n = 5, 30, 2
+    desc = problems.lq_only(T, n, [1, 1], cross_pairs=[(0, 1), (1, 0)])
+    A = np.tile(np.eye(n) + 0.1 * rng.normal(size=(B, T, n, n)), 1).astype(np.float32)
+    Bs = (0.3 * rng.normal(size=(B, T, n, 2))).astype(np.float32)
+    Qh = rng.normal(size=(B, T, 2, n, n))
+    Q = (Qh @ np.swapaxes(Qh, -1, -2) * 0.2 + 0.1 * np.eye(n)).astype(np.float32)
+    l = rng.normal(size=(B, T, 2, n)).astype(np.float32)
+    R = rng.normal(size=(B, T, 4)).astype(np.float32) * 0.3  # includes negative R_ii
+    r = rng.normal(size=(B, T, 4)).astype(np.float32)
+    res = []
+    for lib in (product, oracle):
+        h = abi.Handle(lib, desc, abi.SolverParams.defaults(), B)
+        h.upload_lq(A, Bs, Q, l, R, r)
+        h.lq_backward()
+        res.append((h.download(abi.LQ_PS), h.download(abi.LQ_ALPHAS), h.download(abi.DELTA_XS)))
+        h.close()
+    for (x, y, nm) in zip(res[0], res[1], ("P", "alpha", "dxs")):
+        close(x, y, tol=2e-3, what=nm)  # looser: random indefinite systems are ill-conditioned
+
+
+# ------------------------------------------------------------------ stage-by-stage parity
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_stage_parity(product, oracle, name):
+    c, o = pair(product, oracle, name, 8)
+    for h in (c, o):
+        h.solve_begin()
+    for what in (abi.XS, abi.US, abi.TOTAL_COSTS):
+        close(c.download(what), o.download(what), what=f"prologue {what}")
+    assert np.array_equal(c.download(abi.TIME_OF_EXTREME), o.download(abi.TIME_OF_EXTREME))
+    for it in range(2):
+        for h in (c, o):
+            h.linearize_quadraticize()
+        for what in (abi.LIN_A, abi.LIN_B, abi.QUAD_Q, abi.QUAD_L, abi.QUAD_R, abi.QUAD_RGRAD):
+            close(c.download(what), o.download(what), what=f"it{it} record field {what}")
+        for h in (c, o):
+            h.lq_backward()
+        for what in (abi.LQ_PS, abi.LQ_ALPHAS, abi.DELTA_XS, abi.EXPECTED_DECREASE):
+            close(c.download(what), o.download(what), rows=tame(o.download(abi.LQ_PS)),
+                  what=f"it{it} LQ {what}")
+        for h in (c, o):
+            h.linesearch()
+        good = tame(o.download(abi.LQ_PS)) & tame(o.download(abi.XS), 1e3)
+        same = c.download(abi.BACKTRACKS)[good] == o.download(abi.BACKTRACKS)[good]
+        assert same.all(), "linesearch depth differs on the stage test inputs"
+        for what in (abi.XS, abi.US, abi.PS, abi.ALPHAS, abi.MERIT, abi.STEP, abi.TOTAL_COSTS):
+            close(c.download(what), o.download(what), rows=good, what=f"it{it} linesearch {what}")
+        for what in (abi.STATUS, abi.ITERS, abi.TIME_OF_EXTREME):
+            assert np.array_equal(c.download(what)[good], o.download(what)[good]), what
+
+
+# ------------------------------------------------------------------ golden fixtures
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_against_golden_fixture(product, name):
+    g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    build, params, _ = CONFIGS[name]
+    desc, _ = build()
+    iters = max(int(k.split("_")[1]) for k in g.files if k.startswith("merit_"))
+    h = abi.Handle(product, desc, params(max_solver_iters=iters), g["x0"].shape[0], 0)
+    h.upload_x0(g["x0"])
+    h.solve_begin()
+    close(h.download(abi.XS), g["xs_0"], what="xs_0")
+    close(h.download(abi.TOTAL_COSTS), g["costs_0"], what="costs_0")
+    alive = np.ones(g["x0"].shape[0], bool)
+    for it in range(1, iters + 1):
+        h.iterate(1)
+        flow = (h.download(abi.BACKTRACKS) == g[f"backtracks_{it}"]) & (
+            h.download(abi.STATUS) == g[f"status_{it}"]) & (h.download(abi.ITERS) == g[f"iters_{it}"])
+        alive &= flow
+        assert alive.mean() >= 0.6, f"iteration {it}: control flow matches only {alive.mean():.0%}"
+        ok = alive & (g[f"status_{it}"] != abi.STATUS_LINESEARCH_FAILED) & tame(g[f"xs_{it}"], 1e3)
+        if ok.any():
+            close(h.download(abi.XS), g[f"xs_{it}"], tol=1e-3, atol=1e-3, rows=ok, what=f"xs_{it}")
+            close(h.download(abi.US), g[f"us_{it}"], tol=1e-3, atol=1e-3, rows=ok, what=f"us_{it}")
+            assert np.array_equal(h.download(abi.TIME_OF_EXTREME)[ok], g[f"t_extreme_{it}"][ok])
+            close(h.download(abi.MERIT), g[f"merit_{it}"], tol=1e-3, rows=ok, what="merit")
+    assert alive[0], "the reference example's own initial state must follow the golden control flow"
+
+
+# ------------------------------------------------------------------ full solves
+@pytest.mark.parametrize("name,batch,iters", [("three_player_intersection", 64, 10),
+                                              ("roundabout_merging", 32, 3), ("air_3d", 36, 10)])
+def test_full_solve_against_oracle(product, oracle, name, batch, iters):
+    c, o = pair(product, oracle, name, batch, max_solver_iters=iters)
+    for h in (c, o):
+        h.solve_begin()
+        h.iterate(iters)
+    flow = (c.download(abi.STATUS) == o.download(abi.STATUS)) & (
+        c.download(abi.ITERS) == o.download(abi.ITERS)) & (
+        c.download(abi.BACKTRACKS) == o.download(abi.BACKTRACKS))
+    assert flow.mean() >= 0.5, f"control flow identical for only {flow.mean():.0%}"
+    ok = flow & (o.download(abi.STATUS) != abi.STATUS_LINESEARCH_FAILED) & tame(o.download(abi.XS), 1e3)
+    assert ok.sum() >= 2
+    xs_c, xs_o = c.download(abi.XS)[ok], o.download(abi.XS)[ok]
+    assert np.isfinite(xs_c).all()
+    rel = np.abs(xs_c - xs_o).max(axis=(1, 2)) / np.maximum(1.0, np.abs(xs_o).max(axis=(1, 2)))
+    assert np.median(rel) < 1e-3
+
+
+# ------------------------------------------------------------------ AL outer update
+def test_augmented_lagrangian_update(product, oracle):
+    c, o = pair(product, oracle, "three_player_intersection", 8, max_solver_iters=3)
+    for h in (c, o):
+        h.solve_begin()
+        h.iterate(3)
+        h.al_update()
+    close(c.download(abi.LAMBDAS), o.download(abi.LAMBDAS), what="lambdas")
+    close(c.download(abi.MU), o.download(abi.MU), what="mu")
+    close(c.download(abi.MAX_CONSTRAINT_ERROR), o.download(abi.MAX_CONSTRAINT_ERROR), what="max err")
+    lam = c.download(abi.LAMBDAS)
+    # lambda slots 43, 81, 86, 91 are never touched by the sweep
+    assert np.all(lam[:, :, [43, 81, 86, 91]] == 0.0)
+    for h in (c, o):
+        h.overwrite_solution(only_successful=True)
+        h.solve_begin()
+        h.iterate(2)
+        h.al_post_solve()
+    assert np.array_equal(c.download(abi.STATUS), o.download(abi.STATUS))
+    close(c.download(abi.XS), o.download(abi.XS), tol=1e-3, what="xs after AL step")
+    close(c.download(abi.MU), o.download(abi.MU), what="mu after post-solve")
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_batch_properties(product):
+    """BASELINE.json's metric size (batch 4096, T = 100): properties that need no oracle run."""
+    B, iters = 4096, 3
+    desc, _ = problems.three_player_intersection()
+    params = problems.three_player_intersection_params(max_solver_iters=iters, disable_convergence_exit=1)
+    x0 = problems.three_player_intersection_x0_batch(B, 4096)
+    h = abi.Handle(product, desc, params, B, 0)
+    h.upload_x0(x0)
+    h.solve_begin()
+    h.iterate(iters)
+    status, its, rolls = h.download(abi.STATUS), h.download(abi.ITERS), h.download(abi.BACKTRACKS)
+    xs, us, Ps, al = (h.download(w) for w in (abi.XS, abi.US, abi.PS, abi.ALPHAS))
+    assert set(np.unique(status)) <= {abi.STATUS_MAX_ITERS, abi.STATUS_LINESEARCH_FAILED}
+    assert np.all(its[status == abi.STATUS_MAX_ITERS] == iters)
+    assert np.all(rolls >= its)
+    np.testing.assert_array_equal(xs[:, 0], x0)           # every trajectory starts at its x0
+    assert np.all(Ps[:, -1] == 0) and np.all(al[:, -1] == 0)
+    ok = status == abi.STATUS_MAX_ITERS
+    assert ok.mean() > 0.8 and np.isfinite(xs[ok]).all() and np.isfinite(us[ok]).all()
+    # batch-position invariance: instances are independent, so a sub-batch solved alone must
+    # reproduce its rows of the big batch bit for bit
+    idx = np.array([0, 1, 777, 2048, 4095])
+    h2 = abi.Handle(product, desc, params, len(idx), 0)
+    h2.upload_x0(x0[idx])
+    h2.solve_begin()
+    h2.iterate(iters)
+    np.testing.assert_array_equal(h2.download(abi.XS), xs[idx])
+    np.testing.assert_array_equal(h2.download(abi.US), us[idx])
+    np.testing.assert_array_equal(h2.download(abi.BACKTRACKS), rolls[idx])
+    # determinism: a second solve from the same warm start and solver state repeats the first
+    h.reset(h.RESET_SOLVER)
+    h.solve_begin()
+    h.iterate(iters)
+    np.testing.assert_array_equal(h.download(abi.XS), xs)
+    # the rollout is consistent with the dynamics: x_{k+1} = RK4(x_k, u_k) re-evaluated in numpy
+    def f(x, u):
+        th1, ph1, v1, a1 = x[:, 2], x[:, 3], x[:, 4], x[:, 5]
+        th2, ph2, v2, a2 = x[:, 8], x[:, 9], x[:, 10], x[:, 11]
+        th3, v3 = x[:, 14], x[:, 15]
+        z = np.zeros_like(x)
+        z[:, 0], z[:, 1], z[:, 2], z[:, 3], z[:, 4], z[:, 5] = (v1 * np.cos(th1), v1 * np.sin(th1),
+                                                              v1 / 4.0 * np.tan(ph1), u[:, 0], a1, u[:, 1])
+        z[:, 6], z[:, 7], z[:, 8], z[:, 9], z[:, 10], z[:, 11] = (v2 * np.cos(th2), v2 * np.sin(th2),
+                                                                 v2 / 4.0 * np.tan(ph2), u[:, 2], a2, u[:, 3])
+        z[:, 12], z[:, 13], z[:, 14], z[:, 15] = v3 * np.cos(th3), v3 * np.sin(th3), u[:, 4], u[:, 5]
+        return z
+    sel = np.nonzero(ok & tame(xs, 100.0))[0][:256]  # wild trajectories amplify fp32 rounding
+    for k in (0, 37, 98):
+        x, u = xs[sel, k].astype(np.float64), us[sel, k].astype(np.float64)
+        for _ in range(2):
+            k1 = 0.05 * f(x, u)
+            k2 = 0.05 * f(x + 0.5 * k1, u)
+            k3 = 0.05 * f(x + 0.5 * k2, u)
+            k4 = 0.05 * f(x + k3, u)
+            x = x + (k1 + 2 * (k2 + k3) + k4) / 6.0
+        ref = xs[sel, k + 1].astype(np.float64)
+        assert (np.abs(x - ref) / np.maximum(1.0, np.abs(ref))).max() < 1e-4
+    h.close()
+    h2.close()
