@@ -4,6 +4,7 @@
 // that would compute returns ILQG_ERR_NO_DEVICE / ILQG_ERR_CUDA.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -322,8 +323,47 @@ int DispatchBackward(ilqg_solver* h, int only_running, bool with_dxs) {
   return rc;
 }
 
+// upper bound on the `+= v` updates one role emits for one record (sizes the K_lq v2 lists)
+int MaxRoleEntries(const DevDesc& d) {
+  int best = 0;
+  for (int i = 0; i < d.N; i++) {
+    int e = 0;
+    for (int c = d.cost_begin[i]; c < d.cost_begin[i + 1]; c++) {
+      const DevCost& cd = d.cost[c];
+      const int dim = cd.arg < 0 ? d.n : d.udim[cd.arg];
+      switch (cd.kind) {
+        case ILQG_COST_QUADRATIC: e += cd.d0 >= 0 ? 2 : 2 * dim; break;
+        case ILQG_COST_PROXIMITY:
+        case ILQG_CONSTRAINT_PROXIMITY: e += 20; break;
+        case ILQG_COST_SEMIQUADRATIC:
+        case ILQG_CONSTRAINT_SINGLE_DIMENSION: e += 2; break;
+        default: e += 6; break;  // polyline kinds
+      }
+    }
+    best = std::max(best, e);
+  }
+  int lin = 0;
+  for (int k = 0; k < d.num_subsystems; k++) lin += 9;
+  return std::max(best, lin);
+}
+
 int LaunchLqRecords(ilqg_solver* h, int only_running) {
   const DevDesc& d = h->d;
+  {
+    // v2: role-per-warp / record-per-lane emission into lists, then per-record assembly
+    const int E = (MaxRoleEntries(d) + 3) & ~3;
+    const size_t smem2 = klq2_smem_bytes(d.n, d.M, d.N, E, d.rec);
+    if (d.N + 1 <= 5 && smem2 <= 110 * 1024 && d.rec < 65536) {
+      int rc2 = SetSmem(k_linearize_quadraticize_v2, smem2);
+      if (rc2 != ILQG_OK) return rc2;
+      const long long recs = (long long)h->B * d.T;
+      ProfScope prof(h, 0);
+      k_linearize_quadraticize_v2<<<(int)((recs + 31) / 32), (d.N + 1) * 32, smem2, h->stream>>>(h->d, h->s, only_running, E);
+      h->launches++;
+      CUDA_TRY(cudaGetLastError());
+      return ILQG_OK;
+    }
+  }
   const size_t smem = sizeof(float) * KLQ_WARPS * (size_t)(d.rec + ((d.n + d.M + 3) & ~3));
   int rc = SetSmem(k_linearize_quadraticize, smem);
   if (rc != ILQG_OK) return rc;
@@ -338,15 +378,23 @@ int LaunchLqRecords(ilqg_solver* h, int only_running) {
 
 int LaunchLsEval(ilqg_solver* h, int mode, int jbase, int jcount, long long items, int prof_kind) {
   const DevDesc& d = h->d;
-  const size_t smem = sizeof(float) * (size_t)ls_smem_floats(d.n, d.M, d.N);
-  int rc = SetSmem(k_ls_eval, smem);
-  if (rc != ILQG_OK) return rc;
+  const size_t smem = sizeof(float) * (size_t)ls_smem_floats(d.n, d.M, d.N, d.num_subsystems);
   const int blocks = (int)((items + 31) / 32);
   if (blocks <= 0) return ILQG_OK;
   if (blocks > h->ls_blocks_max) return ILQG_ERR_INVALID_ARGUMENT;
-  const int threads = (d.num_subsystems + d.N) * 32;
+  const int nw = d.num_subsystems + d.N;
+  int rc = ILQG_ERR_UNSUPPORTED;
   ProfScope prof(h, prof_kind);
-  k_ls_eval<<<blocks, threads, smem, h->stream>>>(h->d, h->p, h->s, h->ls, mode, jbase, jcount);
+#define LS_CASE(NW)                                                                                  \
+  case NW:                                                                                           \
+    if ((rc = SetSmem(k_ls_eval<NW>, smem)) != ILQG_OK) return rc;                                    \
+    k_ls_eval<NW><<<blocks, NW * 32, smem, h->stream>>>(h->d, h->p, h->s, h->ls, mode, jbase, jcount); \
+    break;
+  switch (nw) {
+    LS_CASE(2) LS_CASE(3) LS_CASE(4) LS_CASE(5) LS_CASE(6) LS_CASE(7) LS_CASE(8)
+    default: return ILQG_ERR_UNSUPPORTED;
+  }
+#undef LS_CASE
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   return ILQG_OK;
@@ -630,6 +678,7 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
     std::memset(&ls, 0, sizeof(ls));
     const int max_bt = std::max(1, params->max_backtracking_steps);
     int JA = (int)std::max<size_t>(1, std::min<size_t>(8, 32768 / B));
+    if (const char* e = std::getenv("ILQG_LS_JA")) JA = std::max(1, std::atoi(e));  // tuning knob
     if (!params->linesearch) JA = 1;
     JA = std::min(JA, max_bt);
     ls.JA = JA;

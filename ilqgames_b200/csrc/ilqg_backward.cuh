@@ -16,7 +16,7 @@
 //    so the records are read exactly once.  delta_xs themselves (an optional output of
 //    LQFeedbackSolver::Solve) are produced by k_delta_xs when asked for.
 #pragma once
-#include "ilqg_kernels.cuh"
+#include "ilqg_records.cuh"
 
 namespace ilqg {
 
@@ -115,22 +115,87 @@ struct HwSmem {
   static constexpr int S = pn + r4(NX);            // [MU][MU]
   static constexpr int ya = S + r4(MU * MU);       // [MU] alpha column
   static constexpr int lrr = ya + r4(MU);          // [l | R | r] copied from the record (run-time size)
+  // resident blocks per SM the shared-memory footprint allows (own-control pairs only), used as
+  // the register cap in __launch_bounds__
+  static constexpr int lrr_typ = r4(NP * NX + NP * m * m + NP * m);
+  static constexpr int block_bytes = 4 * 4 * (lrr + lrr_typ) + 1024;
+  static constexpr int min_blocks = (225 * 1024 / block_bytes) < 1 ? 1 : ((225 * 1024 / block_bytes) > 12 ? 12 : (225 * 1024 / block_bytes));
 };
 
 constexpr int KHW_WARPS = 2;  // 4 instances per 64-thread block
 
+// LU solve of S X = [Y | y_alpha] with S held redundantly in registers.  G column groups of
+// right-hand sides per lane plus the alpha column.  PIVOT = false is the fast path used when
+// the Gershgorin step has made S strictly column diagonally dominant (LU without pivoting is
+// then stable, growth factor <= 2); PIVOT = true does partial pivoting with row swaps.
+template <int MU, int G, bool PIVOT>
+__device__ __forceinline__ void lu_solve(float (&Sm)[MU][MU], float (&y)[G][MU], float (&yal)[MU]) {
+#pragma unroll
+  for (int k = 0; k < MU; k++) {
+    if constexpr (PIVOT) {
+      int piv = k;
+      float best = fabsf(Sm[k][k]);
+#pragma unroll
+      for (int r = k + 1; r < MU; r++) {
+        const float v = fabsf(Sm[r][k]);
+        if (v > best) { best = v; piv = r; }
+      }
+#pragma unroll
+      for (int r = k + 1; r < MU; r++) {
+        if (piv == r) {
+#pragma unroll
+          for (int c = 0; c < MU; c++) { const float t = Sm[k][c]; Sm[k][c] = Sm[r][c]; Sm[r][c] = t; }
+#pragma unroll
+          for (int g = 0; g < G; g++) { const float t = y[g][k]; y[g][k] = y[g][r]; y[g][r] = t; }
+          const float t = yal[k]; yal[k] = yal[r]; yal[r] = t;
+        }
+      }
+    }
+    const float inv = 1.0f / Sm[k][k];
+    Sm[k][k] = inv;
+#pragma unroll
+    for (int r = k + 1; r < MU; r++) {
+      const float f = Sm[r][k] * inv;
+#pragma unroll
+      for (int c = k + 1; c < MU; c++) Sm[r][c] = fmaf(-f, Sm[k][c], Sm[r][c]);
+#pragma unroll
+      for (int g = 0; g < G; g++) y[g][r] = fmaf(-f, y[g][k], y[g][r]);
+      yal[r] = fmaf(-f, yal[k], yal[r]);
+    }
+  }
+#pragma unroll
+  for (int r = MU - 1; r >= 0; r--) {
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      float acc = y[g][r];
+#pragma unroll
+      for (int c = r + 1; c < MU; c++) acc = fmaf(-Sm[r][c], y[g][c], acc);
+      y[g][r] = acc * Sm[r][r];
+    }
+    float acc = yal[r];
+#pragma unroll
+    for (int c = r + 1; c < MU; c++) acc = fmaf(-Sm[r][c], yal[c], acc);
+    yal[r] = acc * Sm[r][r];
+  }
+}
+
 template <int NX, int MU, int NP>
-__global__ void __launch_bounds__(KHW_WARPS * 32)
+__global__ void __launch_bounds__(KHW_WARPS * 32, HwSmem<NX, MU, NP>::min_blocks)
 k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, int only_running) {
   using L = HwSmem<NX, MU, NP>;
   constexpr int m = L::m;
   constexpr int TR = NX / 4, TC = NX / 4;   // Z tile per lane (16 lanes cover NX x NX)
-  static_assert(NX % 4 == 0 && MU % NP == 0, "shape not supported by the half-warp kernel");
+  constexpr int G = (NX + 15) / 16;         // right-hand-side columns per lane in the solve
+  constexpr int AB4 = (NX * NX + NX * MU) / 4, A4 = NX * NX / 4;
+  constexpr int AB_PER = (AB4 + 15) / 16;
+  constexpr int LRR4_MAX = (NP * NX + NP * NP * m * m + NP * NP * m + 3) / 4;
+  constexpr int LRR_PER = (LRR4_MAX + 15) / 16;
+  static_assert(NX % 4 == 0 && MU % NP == 0 && (NX * MU) % 4 == 0, "shape not supported by the half-warp kernel");
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int half = lane >> 4, l16 = lane & 15;
   const int T = d.T;
-  const int lrr_floats = d.rec - d.offl;
+  const int lrr_floats = d.rec - d.offl, lrr4 = lrr_floats / 4;
   const int per_inst = L::lrr + lrr_floats;
 
   const int b_own = (blockIdx.x * KHW_WARPS + warp) * 2 + half;
@@ -171,7 +236,25 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
 
   const int a0 = (l16 >> 2) * TR, c0 = (l16 & 3) * TC;
 
+  // register prefetch of the next record's [A|B] and [l|R|r]
+  float4 preAB[AB_PER], preL[LRR_PER];
+  auto prefetch = [&](int k) {
+    const float4* ab = reinterpret_cast<const float4*>(recb + (size_t)k * d.rec + d.offA);
+    const float4* lr = reinterpret_cast<const float4*>(recb + (size_t)k * d.rec + d.offl);
+#pragma unroll
+    for (int t = 0; t < AB_PER; t++) {
+      const int e = l16 + 16 * t;
+      if (e < AB4) preAB[t] = __ldg(ab + e);
+    }
+#pragma unroll
+    for (int t = 0; t < LRR_PER; t++) {
+      const int e = l16 + 16 * t;
+      if (e < lrr4) preL[t] = __ldg(lr + e);
+    }
+  };
+
   // ---- terminal condition (:102-105): Z_i = Q_i[T-1], zeta_i = l_i[T-1]; p_{T-1} = g_{T-1} ----
+  prefetch(T - 2);
   {
     const float* last = recb + (size_t)(T - 1) * d.rec;
     for (int e = l16; e < NP * NX * NX / 4; e += 16)
@@ -199,16 +282,26 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
 
   for (int kk = T - 2; kk >= 0; kk--) {
     const float* rec = recb + (size_t)kk * d.rec;
-    // ---- stage [A|B] and [l|R|r]; keep both B layouts ----
-    for (int e = l16; e < NX * NX / 4; e += 16)
-      reinterpret_cast<float4*>(AW)[e] = __ldg(reinterpret_cast<const float4*>(rec + d.offA) + e);
-    for (int e = l16; e < NX * MU; e += 16) {
-      const float v = __ldg(rec + d.offB + e);
-      Bm[e] = v;
-      Bt[(e % MU) * NX + e / MU] = v;
+    // ---- stage [A|B] and [l|R|r] from the prefetch registers; keep both B layouts ----
+#pragma unroll
+    for (int t = 0; t < AB_PER; t++) {
+      const int e = l16 + 16 * t;
+      if (e < A4) {
+        reinterpret_cast<float4*>(AW)[e] = preAB[t];
+      } else if (e < AB4) {
+        const int f0 = (e - A4) * 4;
+        reinterpret_cast<float4*>(Bm)[e - A4] = preAB[t];
+        const float v[4] = {preAB[t].x, preAB[t].y, preAB[t].z, preAB[t].w};
+#pragma unroll
+        for (int u = 0; u < 4; u++) Bt[((f0 + u) % MU) * NX + (f0 + u) / MU] = v[u];
+      }
     }
-    for (int e = l16; e < lrr_floats / 4; e += 16)
-      reinterpret_cast<float4*>(lrr)[e] = __ldg(reinterpret_cast<const float4*>(rec + d.offl) + e);
+#pragma unroll
+    for (int t = 0; t < LRR_PER; t++) {
+      const int e = l16 + 16 * t;
+      if (e < lrr4) reinterpret_cast<float4*>(lrr)[e] = preL[t];
+    }
+    if (kk > 0) prefetch(kk - 1);
     __syncwarp();
 
     // ---- BZ_i = B_i^T Z_i (:128), stored transposed: BZt[col][c] ----
@@ -257,18 +350,19 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
 
     // ---- Gershgorin (:163-176) + S X = Y (:180): lane col owns P[:, col]; every lane carries alpha ----
     {
-      float Sm[MU][MU], y[(NX + 15) / 16][MU], yal[MU];
+      float Sm[MU][MU], y[G][MU], yal[MU];
 #pragma unroll
       for (int r = 0; r < MU; r++) {
 #pragma unroll
         for (int c = 0; c < MU; c++) Sm[r][c] = S[r * MU + c];
         yal[r] = ya[r];
 #pragma unroll
-        for (int g = 0; g < (NX + 15) / 16; g++) {
+        for (int g = 0; g < G; g++) {
           const int col = l16 + 16 * g;
           y[g][r] = col < NX ? P[r * NX + col] : 0.f;
         }
       }
+      bool dominant = p.adaptive_regularization != 0;
       if (p.adaptive_regularization) {
 #pragma unroll
         for (int c = 0; c < MU; c++) {
@@ -279,58 +373,18 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
           const float eval_lo = Sm[c][c] - radius;
           constexpr float min_eval = 1e-3;
           if (eval_lo < min_eval) Sm[c][c] += radius + min_eval;
+          dominant = dominant && (Sm[c][c] > radius);
         }
       }
-#pragma unroll
-      for (int k = 0; k < MU; k++) {
-        int piv = k;
-        float best = fabsf(Sm[k][k]);
-#pragma unroll
-        for (int r = k + 1; r < MU; r++) {
-          const float v = fabsf(Sm[r][k]);
-          if (v > best) { best = v; piv = r; }
-        }
-#pragma unroll
-        for (int r = k + 1; r < MU; r++) {
-          if (piv == r) {
-#pragma unroll
-            for (int c = 0; c < MU; c++) { const float t = Sm[k][c]; Sm[k][c] = Sm[r][c]; Sm[r][c] = t; }
-#pragma unroll
-            for (int g = 0; g < (NX + 15) / 16; g++) { const float t = y[g][k]; y[g][k] = y[g][r]; y[g][r] = t; }
-            const float t = yal[k]; yal[k] = yal[r]; yal[r] = t;
-          }
-        }
-        const float inv = 1.0f / Sm[k][k];
-        Sm[k][k] = inv;
-#pragma unroll
-        for (int r = k + 1; r < MU; r++) {
-          const float f = Sm[r][k] * inv;
-#pragma unroll
-          for (int c = k + 1; c < MU; c++) Sm[r][c] = fmaf(-f, Sm[k][c], Sm[r][c]);
-#pragma unroll
-          for (int g = 0; g < (NX + 15) / 16; g++) y[g][r] = fmaf(-f, y[g][k], y[g][r]);
-          yal[r] = fmaf(-f, yal[k], yal[r]);
-        }
-      }
-#pragma unroll
-      for (int r = MU - 1; r >= 0; r--) {
-#pragma unroll
-        for (int g = 0; g < (NX + 15) / 16; g++) {
-          float acc = y[g][r];
-#pragma unroll
-          for (int c = r + 1; c < MU; c++) acc = fmaf(-Sm[r][c], y[g][c], acc);
-          y[g][r] = acc * Sm[r][r];
-        }
-        float acc = yal[r];
-#pragma unroll
-        for (int c = r + 1; c < MU; c++) acc = fmaf(-Sm[r][c], yal[c], acc);
-        yal[r] = acc * Sm[r][r];
-      }
+      if (dominant)
+        lu_solve<MU, G, false>(Sm, y, yal);
+      else
+        lu_solve<MU, G, true>(Sm, y, yal);
       __syncwarp();  // every lane has read S, P(=Y) and ya
 #pragma unroll
       for (int r = 0; r < MU; r++) {
 #pragma unroll
-        for (int g = 0; g < (NX + 15) / 16; g++) {
+        for (int g = 0; g < G; g++) {
           const int col = l16 + 16 * g;
           if (col < NX) {
             P[r * NX + col] = y[g][r];
@@ -343,6 +397,7 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
         }
       }
       // own-control part of ExpectedDecrease: (alpha_i^T R_ii) r_ii (src/ilq_solver.cpp:384-386)
+#pragma unroll
       for (int i = 0; i < NP; i++) {
         const int pii = d.pair_of[i][i];
         const float* Rii = Rk + d.pair_Roff[pii];
@@ -399,10 +454,13 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
     }
     // p_k = A_k^T p_{k+1} (+ g_k added per player below); AW still holds A here
     for (int a = l16; a < NX; a += 16) {
-      float acc = 0.f;
-#pragma unroll 4
-      for (int q = 0; q < NX; q++) acc = fmaf(AW[q * NX + a], pv[q], acc);
-      pn[a] = acc;
+      float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+      for (int q = 0; q < NX; q += 2) {
+        acc0 = fmaf(AW[q * NX + a], pv[q], acc0);
+        acc1 = fmaf(AW[(q + 1) * NX + a], pv[q + 1], acc1);
+      }
+      pn[a] = acc0 + acc1;
     }
     __syncwarp();
 
@@ -416,20 +474,33 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
       float q[TR][TC];
 #pragma unroll
       for (int r = 0; r < TR; r++) ldgvec<TC>(rec + d.offQ + (i * NX + a0 + r) * NX + c0, q[r]);
-      // tv = zeta_next + Z_next beta
-      for (int a = l16; a < NX; a += 16) {
-        float acc = 0.f;
-#pragma unroll 4
-        for (int c = 0; c < NX; c++) acc = fmaf(Zi[a * NX + c], beta[c], acc);
-        tv[a] = zi[a] + acc;
+      // tv = zeta_next + Z_next beta: each lane reduces its tile's columns, then the 4 column
+      // groups of a row are combined with two shuffles
+      {
+        float bseg[TC];
+        ldvec<TC>(beta + c0, bseg);
+#pragma unroll
+        for (int r = 0; r < TR; r++) {
+          float zr[TC];
+          ldvec<TC>(Zi + (a0 + r) * NX + c0, zr);
+          float part = 0.f;
+#pragma unroll
+          for (int j = 0; j < TC; j++) part = fmaf(zr[j], bseg[j], part);
+          part += __shfl_xor_sync(0xffffffffu, part, 1);
+          part += __shfl_xor_sync(0xffffffffu, part, 2);
+          if ((l16 & 3) == 0) tv[a0 + r] = zi[a0 + r] + part;
+        }
       }
       __syncwarp();
       // zeta = F^T tv + l (+ P_j^T (R_ij alpha_j - r_ij))
       for (int a = l16; a < NX; a += 16) {
-        float acc = 0.f;
-#pragma unroll 4
-        for (int c = 0; c < NX; c++) acc = fmaf(F[c * NX + a], tv[c], acc);
-        float znew = acc + li[a];
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < NX; c += 2) {
+          acc0 = fmaf(F[c * NX + a], tv[c], acc0);
+          acc1 = fmaf(F[(c + 1) * NX + a], tv[c + 1], acc1);
+        }
+        float znew = (acc0 + acc1) + li[a];
         for (int j = 0; j < NP; j++) {
           const int pr = d.pair_of[i][j];
           if (pr < 0) continue;
@@ -448,17 +519,11 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
         }
         zi[a] = znew;
       }
-      // W = F^T Z_next, stored transposed over the dead A buffer
+      // W^T = Z_next^T F computed directly (tile rows = columns of Z), over the dead A buffer
       float acc[TR][TC];
-      mm_tn<NX, TR, TC>(F + a0, NX, Zi + c0, NX, acc);
-      if (i == 0) __syncwarp();  // last readers of A (p_k) are done before W^T overwrites it
+      mm_tn<NX, TR, TC>(Zi + a0, NX, F + c0, NX, acc);
 #pragma unroll
-      for (int j = 0; j < TC; j++) {
-        float col[TR];
-#pragma unroll
-        for (int r = 0; r < TR; r++) col[r] = acc[r][j];
-        stvec<TR>(AW + (c0 + j) * NX + a0, col);
-      }
+      for (int r = 0; r < TR; r++) stvec<TC>(AW + (a0 + r) * NX + c0, acc[r]);
       __syncwarp();
       // Z = W F + Q (+ P_j^T R_ij P_j)
       mm_tn<NX, TR, TC>(AW + a0, NX, F + c0, NX, acc);

@@ -76,6 +76,16 @@ __device__ __forceinline__ LsItem ls_decode(const Slab& s, const LsScratch& ls, 
   return it;
 }
 
+// gradient accumulator in the lane-minor shared tile; `on` = false keeps only the cost value
+struct GatedSink {
+  float* grad;  // element idx at grad[idx * 32]
+  bool on;
+  __device__ __forceinline__ void H(int, int, float) const {}
+  __device__ __forceinline__ void G(int i, float v) const {
+    if (on) grad[i * 32] += v;
+  }
+};
+
 __device__ __forceinline__ void named_barrier_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -84,11 +94,14 @@ __device__ __forceinline__ void named_barrier_sync(int id, int threads) {
 //   xu[2][n + M][32]   state/control double buffer (dynamics -> cost warps)
 //   dx[n][32]          x - x_ref of the current step (between dynamics warps)
 //   acc[N][n + M][32]  per-player gradient accumulators (l_i over the state, r_ij over controls)
-__host__ __device__ inline int ls_smem_floats(int n, int M, int N) {
-  return (2 * (n + M) + n + N * (n + M)) * 32;
+//   pbuf[S][2][32][2n+4]  prefetched feedback rows (dynamics warps)
+__host__ __device__ inline int ls_smem_floats(int n, int M, int N, int S) {
+  return (2 * (n + M) + n + N * (n + M)) * 32 + S * 2 * 32 * (2 * n + 4);
 }
 
-__global__ void __launch_bounds__(256)
+// NW = S + N warps per block; the register cap targets >= 24 resident warps per SM
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, (16 + NW - 1) / NW)
 k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode,
           int jbase, int jcount) {
   extern __shared__ __align__(16) float smem[];
@@ -103,6 +116,7 @@ k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratc
   float* xu = smem;                      // [2][n+M][32]
   float* dxs = xu + 2 * (n + M) * 32;    // [n][32]
   float* accs = dxs + n * 32;            // [N][n+M][32]
+  float* pbase = accs + N * (n + M) * 32;  // [S][2][32][2n+4]  prefetched feedback rows
 
   // ---- per-item sources / destinations ----
   const size_t ox = (size_t)b * T * n, ou = (size_t)b * T * M, oP = (size_t)b * T * M * n;
@@ -146,16 +160,53 @@ k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratc
     float x[6];
 #pragma unroll
     for (int a = 0; a < 6; a++) x[a] = (valid && a < xd) ? x_start[sub.x_offset + a] : 0.f;
+    // Software pipeline: the feedback rows P[k][own rows][:] of the NEXT step are copied
+    // asynchronously (cp.async, 16 B granules) into a per-lane double buffer while this step
+    // integrates; the small reference values ride in registers.  Lane stride PST = 2n + 4
+    // floats keeps the 128-bit reads of 8 consecutive lanes on distinct banks.
+    const bool vecP = (n & 3) == 0 && nu <= 2;
+    const int PST = 2 * n + 4;
+    float* pbuf = pbase + (size_t)warp * 2 * 32 * PST;
+    float nref[6], nuref[2] = {0.f, 0.f}, nal[2] = {0.f, 0.f};
+    auto prefetch = [&](int k) {
+      if (!valid) return;
+#pragma unroll
+      for (int a = 0; a < 6; a++)
+        if (a < xd)
+          nref[a] = k > 0 ? last_xs[(size_t)k * n + sub.x_offset + a] : x_start[sub.x_offset + a];
+      for (int q = 0; q < nu; q++) {
+        const int c = q == 0 ? sub.u_offset : sub.u_offset2;
+        nuref[q] = last_us[(size_t)k * M + c];
+        nal[q] = alpha[(size_t)k * M + c];
+        if (vecP) {
+          const float* src = P + ((size_t)k * M + c) * n;
+          float* dst = pbuf + ((size_t)(k & 1) * 32 + lane) * PST + q * n;
+          for (int a4 = 0; a4 < n / 4; a4++) {
+            const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst + 4 * a4);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src + 4 * a4) : "memory");
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int a = 0; a < 6; a++) nref[a] = 0.f;
+    prefetch(0);
     for (int k = 0; k <= T; k++) {
       if (k < T) {
         float* slot = xu + (k & 1) * (n + M) * 32;
+        float ref[6], uref[2], al[2];
+#pragma unroll
+        for (int a = 0; a < 6; a++) ref[a] = nref[a];
+        uref[0] = nuref[0]; uref[1] = nuref[1];
+        al[0] = nal[0]; al[1] = nal[1];
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (k + 1 < T) prefetch(k + 1);
 #pragma unroll
         for (int a = 0; a < 6; a++)
           if (a < xd) {
             // last_operating_point.xs[0] is the start state (src/ilq_solver.cpp:88-89)
-            const float ref = (valid && k > 0) ? last_xs[(size_t)k * n + sub.x_offset + a]
-                                               : (valid ? x_start[sub.x_offset + a] : 0.f);
-            dxs[(sub.x_offset + a) * 32 + lane] = x[a] - ref;
+            dxs[(sub.x_offset + a) * 32 + lane] = x[a] - ref[a];
             slot[(sub.x_offset + a) * 32 + lane] = x[a];
             if (valid && out_xs) out_xs[(size_t)k * n + sub.x_offset + a] = x[a];
           }
@@ -165,11 +216,12 @@ k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratc
           const int c = q == 0 ? sub.u_offset : sub.u_offset2;
           float uv = 0.f;
           if (valid) {
-            const float4* Prow = reinterpret_cast<const float4*>(P + ((size_t)k * M + c) * n);
             float acc = 0.f;
-            if ((n & 3) == 0) {
+            if (vecP) {
+              const float4* Prow =
+                  reinterpret_cast<const float4*>(pbuf + ((size_t)(k & 1) * 32 + lane) * PST + q * n);
               for (int a4 = 0; a4 < n / 4; a4++) {
-                const float4 pv = __ldg(Prow + a4);
+                const float4 pv = Prow[a4];
                 acc = fmaf(pv.x, dxs[(4 * a4 + 0) * 32 + lane], acc);
                 acc = fmaf(pv.y, dxs[(4 * a4 + 1) * 32 + lane], acc);
                 acc = fmaf(pv.z, dxs[(4 * a4 + 2) * 32 + lane], acc);
@@ -179,12 +231,12 @@ k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratc
               const float* Pr = P + ((size_t)k * M + c) * n;
               for (int a = 0; a < n; a++) acc = fmaf(__ldg(Pr + a), dxs[a * 32 + lane], acc);
             }
-            float al = alpha[(size_t)k * M + c];
+            float alv = al[q];
             if (scaled) {
-              al *= s0;  // ScaleAlphas(initial_alpha_scaling), then geometric_alpha_scaling^j
-              for (int jj = 0; jj < it.j; jj++) al *= rho;
+              alv *= s0;  // ScaleAlphas(initial_alpha_scaling), then geometric_alpha_scaling^j
+              for (int jj = 0; jj < it.j; jj++) alv *= rho;
             }
-            uv = last_us[(size_t)k * M + c] - acc - al;  // Strategy::operator(), strategy.h:73-76
+            uv = uref[q] - acc - alv;  // Strategy::operator(), strategy.h:73-76
             if (out_us) out_us[(size_t)k * M + c] = uv;
           }
           slot[(n + c) * 32 + lane] = uv;
@@ -212,28 +264,17 @@ k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratc
         for (int c = d.cost_begin[i]; c < d.cost_begin[i + 1]; c++) {
           const DevCost& cd = d.cost[c];
           const bool is_con = cd.slot >= 0;
+          // PlayerCost::Quadraticize vs QuadraticizeControlCosts (src/ilq_solver.cpp:483-487): off the
+          // extreme timestep of a MAX/MIN player only control COSTS enter the gradient; the cost
+          // VALUE (PlayerCost::Evaluate) always counts every state and control cost.
+          const bool in_quad = full || (cd.arg >= 0 && !is_con);
+          if (!in_quad && is_con) continue;
+          const float lambda =
+              (is_con && valid) ? s.lambdas[((size_t)b * d.num_constraints + cd.slot) * T + s.lambda_index[kk]] : 0.f;
+          GatedSink sink{acc + (cd.arg < 0 ? 0 : (n + d.uoff[cd.arg]) * 32) + lane, in_quad};
+          const float* in = cd.arg < 0 ? slot + lane : slot + (n + d.uoff[cd.arg]) * 32 + lane;
           float v = 0.f;
-          const bool in_quad = full || (cd.arg >= 0 && !is_con);  // QuadraticizeControlCosts
-          if (cd.arg < 0) {
-            if (in_quad) {
-              const float lambda =
-                  (is_con && valid) ? s.lambdas[((size_t)b * d.num_constraints + cd.slot) * T + s.lambda_index[kk]] : 0.f;
-              quadraticize_record<false, 32, 32, true>(d, cd, slot + lane, n, lambda, mu, nullptr, 0,
-                                                        acc + lane, &v);
-            } else if (!is_con) {
-              v = evaluate_record<32>(d, cd, slot + lane, n);
-            }
-          } else {
-            const float* uin = slot + (n + d.uoff[cd.arg]) * 32 + lane;
-            if (in_quad) {
-              const float lambda =
-                  (is_con && valid) ? s.lambdas[((size_t)b * d.num_constraints + cd.slot) * T + s.lambda_index[kk]] : 0.f;
-              quadraticize_record<false, 32, 32, true>(d, cd, uin, d.udim[cd.arg], lambda, mu, nullptr,
-                                                        0, acc + (n + d.uoff[cd.arg]) * 32 + lane, &v);
-            } else if (!is_con) {
-              v = evaluate_record<32>(d, cd, uin, d.udim[cd.arg]);
-            }
-          }
+          quadraticize_record_sink<false, 32, true>(d, cd, in, cd.arg < 0 ? n : d.udim[cd.arg], lambda, mu, sink, &v);
           if (!is_con) value += v;  // PlayerCost::Evaluate: costs only
         }
         // ILQSolver::MeritFunction terms (src/ilq_solver.cpp:416-430)

@@ -10,9 +10,9 @@ from tests.golden import make_golden
 
 
 @pytest.mark.parametrize("name", sorted(make_golden.CASES))
-def test_oracle_reproduces_golden(oracle, name):
+def test_oracle_reproduces_golden(oracle, oracle64, name):
     g = np.load(os.path.join(os.path.dirname(make_golden.__file__), f"{name}.npz"))
-    out = make_golden.run_case(oracle, name)
+    out = make_golden.run_case(oracle, name, oracle64)
     assert sorted(out) == sorted(g.files)
     for k in g.files:
         np.testing.assert_array_equal(out[k], g[k], err_msg=k)

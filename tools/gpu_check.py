@@ -15,6 +15,14 @@ oracle = abi.Library(os.path.join(REPO, "oracle", "_build", "libilqg_oracle.so")
 oracle64 = abi.Library(os.path.join(REPO, "oracle", "_build", "libilqg_oracle64.so"))
 
 
+def rowdiff(name, a, b):
+    a = np.asarray(a, np.float64).reshape(len(a), -1)
+    b = np.asarray(b, np.float64).reshape(len(b), -1)
+    err = np.abs(a - b).max(axis=1)
+    print(f"  {name:18s} per-instance max|d| " + " ".join(f"{e:.2e}" for e in err) + "  | scale " +
+          " ".join(f"{v:.1e}" for v in np.abs(b).max(axis=1)))
+
+
 def diff(name, a, b, ref64=None):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
@@ -57,6 +65,10 @@ def stage_compare(title, desc, params, x0, iters=3, fields=None):
         for f, nm in ((abi.XS, "xs"), (abi.US, "us"), (abi.ALPHAS, "alphas"), (abi.MERIT, "merit"),
                       (abi.STEP, "step"), (abi.TOTAL_COSTS, "costs")):
             diff(nm, hs["cuda"].download(f), hs["oracle"].download(f), hs["f64"].download(f))
+        if x0.shape[0] <= 8:
+            for f, nm in ((abi.LQ_PS, "lqP"), (abi.LQ_ALPHAS, "lqAlpha"), (abi.EXPECTED_DECREASE, "ed"),
+                          (abi.XS, "xs"), (abi.MERIT, "merit")):
+                rowdiff(nm, hs["cuda"].download(f), hs["oracle"].download(f))
         for f, nm in ((abi.STATUS, "status"), (abi.ITERS, "iters"), (abi.BACKTRACKS, "backtracks"),
                       (abi.TIME_OF_EXTREME, "t_extreme")):
             a, b = hs["cuda"].download(f), hs["oracle"].download(f)
@@ -129,6 +141,13 @@ if __name__ == "__main__":
     if "c4" in which:
         desc, _ = problems.air_3d()
         stage_compare("Air3D", desc, problems.air_3d_params(), problems.air_3d_x0_grid(4)[:8], iters=2)
+    if "golden" in which:
+        for name, build, params in (("three_player_intersection", problems.three_player_intersection,
+                                     problems.three_player_intersection_params),
+                                    ("roundabout_merging", problems.roundabout_merging, problems.roundabout_params)):
+            g = np.load(os.path.join(REPO, "tests", "golden", name + ".npz"))
+            desc, _ = build()
+            stage_compare("golden " + name, desc, params(), g["x0"], iters=2)
     if "full" in which:
         desc, _ = problems.three_player_intersection()
         full_solve("ThreePlayerIntersection", desc,
