@@ -117,7 +117,7 @@ def _oracle_worker(args):
     t = time.perf_counter()
     h.reset(h.RESET_SOLVER)
     h.solve_begin()
-    h.iterate(iters)
+    h.solve(chunk=iters)
     dt = time.perf_counter() - t
     done = int(h.download(abi.ITERS).sum())
     rolls = int(h.download(abi.BACKTRACKS).sum())
@@ -208,7 +208,12 @@ def run_b200(args):
     def solve():
         h.reset(h.RESET_SOLVER)  # a fresh ILQSolver per solve (last merit = +inf)
         h.solve_begin()
+        # ITERS_PER_SOLVE passes complete ITERS_PER_SOLVE iterations for every instance whose
+        # linesearches resolve within their first window; stragglers (deep backtracking) finish in
+        # extra passes.  count_running() is the only host sync of a solve.
         h.iterate(ITERS_PER_SOLVE)
+        while h.count_running() > 0:
+            h.iterate(2)
 
     # ---- device-resident timing ------------------------------------------------------
     for _ in range(args.warmup):
@@ -250,11 +255,12 @@ def run_b200(args):
     for name, (ms, n) in prof.items():
         if n:
             kern[name] = {"ms_per_launch": ms / n, "launches_per_step": n / prof_steps, "ms_per_step": ms / prof_steps}
-    inst_iters_per_launch = done_per_step / ITERS_PER_SOLVE
+    passes = max(kern.get("lq_backward", {}).get("launches_per_step", ITERS_PER_SOLVE), 1)
+    inst_iters_per_launch = done_per_step / passes
     per_kernel_bytes = {
         "linearize_quadraticize": bytes_model["linearize_quadraticize"] * inst_iters_per_launch,
         "lq_backward": bytes_model["lq_backward"] * inst_iters_per_launch,
-        "linesearch": bytes_model["linesearch_per_rollout"] * roll_per_step / ITERS_PER_SOLVE,
+        "linesearch": bytes_model["linesearch_per_rollout"] * roll_per_step / passes,
     }
     hot = [k for k in ("linearize_quadraticize", "lq_backward", "linesearch") if k in kern]
     dominant = max(hot, key=lambda k: kern[k]["ms_per_step"])

@@ -111,7 +111,7 @@ ABI_SYMBOLS = [
     "ilqg_solve_begin", "ilqg_linearize_quadraticize", "ilqg_lq_backward", "ilqg_linesearch",
     "ilqg_iterate", "ilqg_al_update", "ilqg_overwrite_solution", "ilqg_al_post_solve",
     "ilqg_download", "ilqg_synchronize", "ilqg_kernel_launches", "ilqg_set_stream",
-    "ilqg_profile", "ilqg_profile_read", "ilqg_reset",
+    "ilqg_profile", "ilqg_profile_read", "ilqg_reset", "ilqg_count_running",
 ]
 
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -155,6 +155,7 @@ class Library:
         L.ilqg_kernel_launches.argtypes = [vp, C.POINTER(C.c_longlong)]
         L.ilqg_set_stream.argtypes = [vp, vp]
         L.ilqg_reset.argtypes = [vp, C.c_int]
+        L.ilqg_count_running.argtypes = [vp, ip]
         L.ilqg_profile.argtypes = [vp, C.c_int]
         L.ilqg_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double),
                                         C.POINTER(C.c_longlong)]
@@ -307,6 +308,22 @@ class Handle:
             return done.value
         self.lib.check(self.lib.lib.ilqg_iterate(self._h, max_iters, None), "iterate")
         return None
+
+    def count_running(self) -> int:
+        out = C.c_int(0)
+        self.lib.check(self.lib.lib.ilqg_count_running(self._h, C.byref(out)), "count_running")
+        return out.value
+
+    def solve(self, max_passes: int = 10_000, chunk: int = 4) -> int:
+        """ILQSolver::Solve after solve_begin(): passes until no instance is RUNNING.  Returns the
+        number of passes issued."""
+        done = 0
+        while done < max_passes:
+            self.iterate(chunk)
+            done += chunk
+            if self.count_running() == 0:
+                break
+        return done
 
     def al_update(self):
         self.lib.check(self.lib.lib.ilqg_al_update(self._h), "al_update")

@@ -21,6 +21,7 @@ struct ilqg_solver {
   Slab s;
   LsScratch ls;
   int ls_blocks_max;
+  int ls_cur;  // which open-linesearch queue the next pass consumes
   int device;
   int B;
   cudaStream_t stream;      // the stream work is issued on
@@ -376,19 +377,17 @@ int LaunchLqRecords(ilqg_solver* h, int only_running) {
   return ILQG_OK;
 }
 
-int LaunchLsEval(ilqg_solver* h, int mode, int jbase, int jcount, long long items, int prof_kind) {
+int LaunchLsEval(ilqg_solver* h, int mode, int blocks) {
   const DevDesc& d = h->d;
   const size_t smem = sizeof(float) * (size_t)ls_smem_floats(d.n, d.M, d.N, d.num_subsystems);
-  const int blocks = (int)((items + 31) / 32);
   if (blocks <= 0) return ILQG_OK;
   if (blocks > h->ls_blocks_max) return ILQG_ERR_INVALID_ARGUMENT;
   const int nw = d.num_subsystems + d.N;
   int rc = ILQG_ERR_UNSUPPORTED;
-  ProfScope prof(h, prof_kind);
-#define LS_CASE(NW)                                                                                  \
-  case NW:                                                                                           \
-    if ((rc = SetSmem(k_ls_eval<NW>, smem)) != ILQG_OK) return rc;                                    \
-    k_ls_eval<NW><<<blocks, NW * 32, smem, h->stream>>>(h->d, h->p, h->s, h->ls, mode, jbase, jcount); \
+#define LS_CASE(NW)                                                                              \
+  case NW:                                                                                       \
+    if ((rc = SetSmem(k_ls_eval<NW>, smem)) != ILQG_OK) return rc;                                \
+    k_ls_eval<NW><<<blocks, NW * 32, smem, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur); \
     break;
   switch (nw) {
     LS_CASE(2) LS_CASE(3) LS_CASE(4) LS_CASE(5) LS_CASE(6) LS_CASE(7) LS_CASE(8)
@@ -400,47 +399,39 @@ int LaunchLsEval(ilqg_solver* h, int mode, int jbase, int jcount, long long item
   return ILQG_OK;
 }
 
-// ILQSolver::ModifyLQStrategies as the speculative A/B/C pipeline (ilqg_linesearch.cuh)
-int LaunchLinesearch(ilqg_solver* h) {
-  const int B = h->B, JA = h->ls.JA, max_bt = h->p.max_backtracking_steps;
+// One linesearch pass (ilqg_linesearch.cuh): evaluate this pass's candidate windows, then decide.
+int LaunchLinesearchPass(ilqg_solver* h) {
+  const int B = h->B;
   int rc;
   ProfScope prof(h, 2);
-  const bool was = h->profiling;
-  h->profiling = false;  // one sample for the whole pipeline
-  auto done = [&](int code) {
-    h->profiling = was;
-    return code;
-  };
-  CUDA_TRY(cudaMemsetAsync(h->ls.counts, 0, 2 * sizeof(int), h->stream));
-  if ((rc = LaunchLsEval(h, LS_MODE_A, 0, JA, (long long)B * JA, 2)) != ILQG_OK) return done(rc);
-  const int dec_blocks = (B + KDEC_WARPS - 1) / KDEC_WARPS;
-  k_ls_decide_a<<<dec_blocks, KDEC_WARPS * 32, 0, h->stream>>>(h->d, h->p, h->s, h->ls);
+  CUDA_TRY(cudaMemsetAsync(h->ls.counts + (1 - h->ls_cur), 0, sizeof(int), h->stream));
+  const int nB_blocks = (int)(((long long)B * h->ls.JB + 31) / 32);
+  if ((rc = LaunchLsEval(h, LS_MODE_LS, h->ls.nA_blocks + nB_blocks)) != ILQG_OK) return rc;
+  k_ls_decide<<<(B + KDEC_WARPS - 1) / KDEC_WARPS, KDEC_WARPS * 32, 0, h->stream>>>(h->d, h->p, h->s, h->ls, h->ls_cur);
   h->launches++;
-  if (h->p.linesearch && max_bt > JA) {
-    const int jcount = max_bt - JA;
-    if ((rc = LaunchLsEval(h, LS_MODE_B, JA, jcount, (long long)B * jcount, 2)) != ILQG_OK) return done(rc);
-    k_ls_decide_b<<<(B + 127) / 128, 128, 0, h->stream>>>(h->d, h->p, h->s, h->ls, JA, jcount);
-    h->launches++;
-    if ((rc = LaunchLsEval(h, LS_MODE_C, 0, 1, B, 2)) != ILQG_OK) return done(rc);
-    k_ls_finalize_c<<<dec_blocks, KDEC_WARPS * 32, 0, h->stream>>>(h->d, h->p, h->s, h->ls);
-    h->launches++;
-  }
-  if (cudaGetLastError() != cudaSuccess) return done(ILQG_ERR_CUDA);
-  return done(ILQG_OK);
+  CUDA_TRY(cudaGetLastError());
+  h->ls_cur = 1 - h->ls_cur;
+  return ILQG_OK;
+}
+
+// passes needed to exhaust max_backtracking_steps candidates
+int LinesearchPasses(const ilqg_solver* h) {
+  const int max_bt = std::max(1, h->p.max_backtracking_steps);
+  if (!h->p.linesearch || max_bt <= h->ls.JA) return 1;
+  return 1 + (max_bt - h->ls.JA + h->ls.JB - 1) / h->ls.JB;
 }
 
 int LaunchSolveBegin(ilqg_solver* h) {
   int rc;
   ProfScope prof(h, 3);
-  const bool was = h->profiling;
-  h->profiling = false;
-  rc = LaunchLsEval(h, LS_MODE_BEGIN, 0, 1, h->B, 3);
+  CUDA_TRY(cudaMemsetAsync(h->ls.counts, 0, 2 * sizeof(int), h->stream));
+  h->ls_cur = 0;
+  rc = LaunchLsEval(h, LS_MODE_BEGIN, (h->B + 31) / 32);
   if (rc == ILQG_OK) {
     k_begin_finalize<<<(h->B + KDEC_WARPS - 1) / KDEC_WARPS, KDEC_WARPS * 32, 0, h->stream>>>(h->d, h->p, h->s, h->ls);
     h->launches++;
     if (cudaGetLastError() != cudaSuccess) rc = ILQG_ERR_CUDA;
   }
-  h->profiling = was;
   return rc;
 }
 
@@ -673,30 +664,36 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
   int* lidx_dev = nullptr;
   ALLOC(lidx_dev, T);
   {
-    // linesearch scratch (ilqg_linesearch.cuh): JA speculative candidates per instance in phase A
+    // linesearch scratch (ilqg_linesearch.cuh): a fresh linesearch evaluates JA candidates per
+    // pass, a continued one JB
     LsScratch& ls = h->ls;
     std::memset(&ls, 0, sizeof(ls));
     const int max_bt = std::max(1, params->max_backtracking_steps);
-    int JA = (int)std::max<size_t>(1, std::min<size_t>(8, 32768 / B));
-    if (const char* e = std::getenv("ILQG_LS_JA")) JA = std::max(1, std::atoi(e));  // tuning knob
+    int JA = 4, JB = 16;
+    if (const char* e = std::getenv("ILQG_LS_JA")) JA = std::max(1, std::atoi(e));  // tuning knobs
+    if (const char* e = std::getenv("ILQG_LS_JB")) JB = std::max(1, std::atoi(e));
     if (!params->linesearch) JA = 1;
     JA = std::min(JA, max_bt);
+    JB = std::min(JB, max_bt);
     ls.JA = JA;
-    const size_t per = (size_t)std::max(std::max(JA, max_bt - JA), 1);
-    const size_t blocks_max = (B * per + 31) / 32;
+    ls.JB = JB;
+    ls.nA_blocks = (int)((B * JA + 31) / 32);
+    const size_t blocks_max = (size_t)ls.nA_blocks + (B * JB + 31) / 32;
     h->ls_blocks_max = (int)blocks_max;
+    h->ls_cur = 0;
 #define ALLOCNZ(ptr, count)                                               \
   if ((rc = DevAlloc(h, &(ptr), (count), false)) != ILQG_OK) return fail(rc)
-    ALLOCNZ(ls.traj_xs, B * JA * T * n);
-    ALLOCNZ(ls.traj_us, B * JA * T * M);
+    ALLOCNZ(ls.traj_xs, blocks_max * 32 * T * n);
+    ALLOCNZ(ls.traj_us, blocks_max * 32 * T * M);
     ALLOCNZ(ls.terms, blocks_max * T * 2 * N * 32);
     ALLOCNZ(ls.vals, blocks_max * T * N * 32);
     ALLOCNZ(ls.merit, blocks_max * 32);
 #undef ALLOCNZ
-    ALLOC(ls.pending, B);
-    ALLOC(ls.commit, B);
-    ALLOC(ls.accept_j, B);
+    ALLOC(ls.pend[0], B);
+    ALLOC(ls.pend[1], B);
+    ALLOC(ls.slot, B);
     ALLOC(ls.counts, 2);
+    ALLOC(s.ls_next_j, B);
   }
 #undef ALLOC
   s.lambda_index = lidx_dev;
@@ -825,7 +822,13 @@ int ilqg_lq_backward(ilqg_handle h) {
 
 int ilqg_linesearch(ilqg_handle h) {
   ENTER(h);
-  return LaunchLinesearch(h);
+  // a stand-alone linesearch runs to completion: enough passes to exhaust every candidate
+  const int passes = LinesearchPasses(h);
+  for (int k = 0; k < passes; k++) {
+    const int rc = LaunchLinesearchPass(h);
+    if (rc != ILQG_OK) return rc;
+  }
+  return ILQG_OK;
 }
 
 int ilqg_iterate(ilqg_handle h, int max_iters, int* iters_done) {
@@ -834,7 +837,7 @@ int ilqg_iterate(ilqg_handle h, int max_iters, int* iters_done) {
   for (int it = 0; it < max_iters; it++) {
     if ((rc = LaunchLqRecords(h, 1)) != ILQG_OK) return rc;
     if ((rc = DispatchBackward(h, 1, false)) != ILQG_OK) return rc;
-    if ((rc = LaunchLinesearch(h)) != ILQG_OK) return rc;
+    if ((rc = LaunchLinesearchPass(h)) != ILQG_OK) return rc;
   }
   if (iters_done) {
     std::vector<int> iters(h->B);
@@ -842,6 +845,16 @@ int ilqg_iterate(ilqg_handle h, int max_iters, int* iters_done) {
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     *iters_done = *std::max_element(iters.begin(), iters.end());
   }
+  return ILQG_OK;
+}
+
+int ilqg_count_running(ilqg_handle h, int* running) {
+  ENTER(h);
+  if (!running) return ILQG_ERR_INVALID_ARGUMENT;
+  std::vector<int> st(h->B);
+  CUDA_TRY(cudaMemcpyAsync(st.data(), h->s.status, sizeof(int) * h->B, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  *running = (int)std::count(st.begin(), st.end(), (int)ILQG_STATUS_RUNNING);
   return ILQG_OK;
 }
 

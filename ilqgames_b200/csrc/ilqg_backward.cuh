@@ -200,7 +200,7 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
 
   const int b_own = (blockIdx.x * KHW_WARPS + warp) * 2 + half;
   bool active = b_own < s.B;
-  if (active && only_running) active = s.status[b_own] == ILQG_STATUS_RUNNING;
+  if (active && only_running) active = instance_iterates(s, b_own);
   const unsigned act_mask = __ballot_sync(0xffffffffu, active);
   if (act_mask == 0) return;
   // an inactive half shadows its partner (valid loads, no stores) so the warp stays convergent

@@ -31,10 +31,17 @@ struct Slab {
   float* lambdas;                   // [B][ncon][T]
   float *mu, *last_merit, *expected_decrease, *step, *total_costs, *max_con_err;
   int *status, *iters, *backtracks, *te_quad, *te_new, *op_cur, *st_cur;
+  int* ls_next_j;                   // [B] next linesearch candidate; 0 = no linesearch open
   const int* lambda_index;          // [T]  kk -> Constraint::TimeIndex
 };
 
 __device__ __forceinline__ int round4(int v) { return (v + 3) & ~3; }
+
+// an instance takes part in this pass's linearize / quadraticize / LQ solve if it is running and
+// is not in the middle of a linesearch (ilqg_linesearch.cuh)
+__device__ __forceinline__ bool instance_iterates(const Slab& s, int b) {
+  return s.status[b] == ILQG_STATUS_RUNNING && s.ls_next_j[b] == 0;
+}
 
 // ===========================================================================
 // K_lq: fused ComputeLinearization + ComputeCostQuadraticization
@@ -49,7 +56,7 @@ k_linearize_quadraticize(const __grid_constant__ DevDesc d, Slab s, int only_run
   const long long w = (long long)blockIdx.x * KLQ_WARPS + warp;
   const int b = (int)(w / d.T), k = (int)(w % d.T);
   if (b >= s.B) return;
-  if (only_running && s.status[b] != ILQG_STATUS_RUNNING) return;
+  if (only_running && !instance_iterates(s, b)) return;
   const int n = d.n, M = d.M, N = d.N;
   float* rec = smem + (size_t)warp * (d.rec + round4(n + M));
   float* xu = rec + d.rec;
@@ -176,7 +183,7 @@ k_lq_backward(const __grid_constant__ DevDesc d, const DevParams p, Slab s, int 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * KBWD_WARPS + warp;
   if (b >= s.B) return;
-  if (only_running && s.status[b] != ILQG_STATUS_RUNNING) return;
+  if (only_running && !instance_iterates(s, b)) return;
   const int T = d.T;
   float* sm = smem + (size_t)warp * (L::rec + d.rec);
   float* Z = sm + L::Z;

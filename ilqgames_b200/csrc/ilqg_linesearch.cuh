@@ -1,15 +1,20 @@
 // ilqg_linesearch.cuh -- K_ls: ILQSolver::ModifyLQStrategies (src/ilq_solver.cpp:289-348) as a
-// speculative, role-specialised pipeline, plus the Solve() prologue built from the same kernel.
+// speculative, asynchronous, role-specialised pipeline, plus the Solve() prologue built from the
+// same kernel.
 //
 // The reference backtracks sequentially: roll out with alpha * s0 * rho^j, evaluate the merit,
 // test Armijo, repeat.  Candidate j's trajectory and merit depend only on j, never on the
-// outcome of candidates < j, so evaluating several candidates at once and taking the FIRST one
-// that passes Armijo gives exactly the sequential result.  Phases per linesearch:
-//   A  candidates j in [0, JA)       for every running instance        (eval + decide)
-//   B  candidates j in [JA, max_bt)  for instances that rejected all of A (eval + decide)
-//   C  re-roll of the accepted candidate for instances accepted in B   (eval + finalize)
-// Phases B and C launch worst-case grids that exit at once when their device-side work lists
-// are empty, so the host never synchronises.
+// outcome of candidates < j, so evaluating a WINDOW of candidates at once and taking the FIRST
+// one that passes Armijo gives exactly the sequential result.  Each pass of ilqg_iterate runs
+//   k_ls_eval    candidates [0, JA) for every instance that starts a linesearch in this pass and
+//                candidates [j0, j0 + JB) for every instance whose linesearch is still open
+//   k_ls_decide  first passing candidate -> accept (operating point, strategies, merit, status);
+//                none -> the instance keeps its linesearch open (ls_next_j = j0 + window) and is
+//                queued for the next pass; past max_backtracking_steps -> LINESEARCH_FAILED
+// An instance with an open linesearch is skipped by K_lq / K_bwd until it resolves, so deep
+// backtrackers never stall the batch: every instance performs exactly the reference's sequence of
+// computations, only scheduled in different passes (per-instance
+// Armijo state machine).  The host never synchronises inside a pass.
 //
 // k_ls_eval maps one (instance, candidate) ITEM to one lane, and one ROLE to each warp of the
 // block: warps [0, S) integrate subsystem s (u = u_ref - P dx - alpha, then RK4 x 2 substeps),
@@ -21,20 +26,19 @@
 
 namespace ilqg {
 
-enum { LS_MODE_BEGIN = 0, LS_MODE_A = 1, LS_MODE_B = 2, LS_MODE_C = 3 };
-enum { LS_COUNT_PENDING = 0, LS_COUNT_COMMIT = 1 };
+enum { LS_MODE_BEGIN = 0, LS_MODE_LS = 1 };
 
 struct LsScratch {
-  float* traj_xs;   // [B * JA][T][n]   phase-A candidate trajectories
-  float* traj_us;   // [B * JA][T][M]
+  float* traj_xs;   // [items][T][n]   candidate trajectories (item = global lane index of the launch)
+  float* traj_us;   // [items][T][M]
   float* terms;     // [blocks][T][2N][32]  merit terms, item = lane of its block
   float* vals;      // [blocks][T][N][32]   per-player cost values
   float* merit;     // [items]
-  int* pending;     // [B] instances that rejected every phase-A candidate
-  int* commit;      // [B] instances accepted in phase B (need a re-roll)
-  int* accept_j;    // [B]
-  int* counts;      // [2]
-  int JA;
+  int* pend[2];     // double-buffered queue of instances with an open linesearch
+  int* counts;      // [2] queue lengths
+  int* slot;        // [B] position of an instance in the queue it is in
+  int JA, JB;       // window sizes: fresh linesearch / continued linesearch
+  int nA_blocks;    // blocks of a k_ls_eval launch that serve fresh instances
 };
 
 struct LsItem {
@@ -42,36 +46,30 @@ struct LsItem {
   bool valid;
 };
 
-__device__ __forceinline__ LsItem ls_decode(const Slab& s, const LsScratch& ls, int mode, int item,
-                                            int jbase, int jcount) {
+// cur: which queue this pass consumes
+__device__ __forceinline__ LsItem ls_decode(const DevParams& p, const Slab& s, const LsScratch& ls, int mode,
+                                            int cur, int block, int lane) {
   LsItem it;
   it.b = 0;
   it.j = 0;
   it.valid = false;
-  switch (mode) {
-    case LS_MODE_BEGIN:
-      it.b = item;
-      it.valid = item < s.B;
-      break;
-    case LS_MODE_A:
-      it.b = item / jcount;
-      it.j = jbase + item % jcount;
-      it.valid = it.b < s.B && s.status[it.b] == ILQG_STATUS_RUNNING;
-      break;
-    case LS_MODE_B: {
-      const int p = item / jcount;
-      it.valid = p < ls.counts[LS_COUNT_PENDING];
-      if (it.valid) it.b = ls.pending[p];
-      it.j = jbase + item % jcount;
-      break;
+  if (mode == LS_MODE_BEGIN) {
+    it.b = block * 32 + lane;
+    it.valid = it.b < s.B;
+  } else if (block < ls.nA_blocks) {
+    const int item = block * 32 + lane;
+    it.b = item / ls.JA;
+    it.j = item % ls.JA;
+    it.valid = it.b < s.B && s.status[it.b] == ILQG_STATUS_RUNNING && s.ls_next_j[it.b] == 0 &&
+               it.j < p.max_backtracking_steps;
+  } else {
+    const int item = (block - ls.nA_blocks) * 32 + lane;
+    const int q = item / ls.JB;
+    if (q < ls.counts[cur]) {
+      it.b = ls.pend[cur][q];
+      it.j = s.ls_next_j[it.b] + item % ls.JB;
+      it.valid = it.j < p.max_backtracking_steps;
     }
-    case LS_MODE_C:
-      it.valid = item < ls.counts[LS_COUNT_COMMIT];
-      if (it.valid) {
-        it.b = ls.commit[item];
-        it.j = ls.accept_j[it.b];
-      }
-      break;
   }
   return it;
 }
@@ -102,13 +100,12 @@ __host__ __device__ inline int ls_smem_floats(int n, int M, int N, int S) {
 // NW = S + N warps per block; the register cap targets >= 24 resident warps per SM
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, (16 + NW - 1) / NW)
-k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode,
-          int jbase, int jcount) {
+k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode, int cur_q) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = d.n, M = d.M, N = d.N, T = d.T, S = d.num_subsystems;
   const int item = blockIdx.x * 32 + lane;
-  const LsItem it = ls_decode(s, ls, mode, item, jbase, jcount);
+  const LsItem it = ls_decode(p, s, ls, mode, cur_q, blockIdx.x, lane);
   if (!__syncthreads_or(it.valid)) return;
   const bool valid = it.valid;
   const int b = it.b;
@@ -139,13 +136,8 @@ k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratc
     P = s.st_P[1 - scur] + oP;
     alpha = s.st_a[1 - scur] + ou;
     x_start = last_xs;
-    if (mode == LS_MODE_A) {
-      out_xs = ls.traj_xs + (size_t)item * T * n;
-      out_us = ls.traj_us + (size_t)item * T * M;
-    } else if (mode == LS_MODE_C) {
-      out_xs = s.op_xs[1 - cur] + ox;
-      out_us = s.op_us[1 - cur] + ou;
-    }
+    out_xs = ls.traj_xs + (size_t)item * T * n;
+    out_us = ls.traj_us + (size_t)item * T * M;
   }
   const float s0 = p.initial_alpha_scaling, rho = p.geometric_alpha_scaling;
   const float dt_half = (float)(d.time_step / 2.0);
@@ -310,7 +302,7 @@ k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratc
 }
 
 // ---------------------------------------------------------------------------
-// accept-side bookkeeping shared by the decide / finalize kernels (one warp per instance)
+// decide: one warp per instance
 // ---------------------------------------------------------------------------
 // ILQSolver::TotalCosts (src/ilq_solver.cpp:220-257) from the per-step values an eval block left
 // behind: ordered over k, first extreme wins.
@@ -338,44 +330,6 @@ __device__ __forceinline__ void ls_total_costs(const DevDesc& d, const Slab& s, 
   }
 }
 
-// the scaled LQ strategies become current; counters, merit, status (ilq_solver.cpp:331-336,158-171)
-__device__ __forceinline__ void ls_accept(const DevDesc& d, const DevParams& p, const Slab& s, int b, int j,
-                                          float merit, bool with_merit, int lane) {
-  const int T = d.T, M = d.M;
-  const int cur = s.op_cur[b], scur = s.st_cur[b];
-  float* alpha = s.st_a[1 - scur] + (size_t)b * T * M;
-  const float s0 = p.initial_alpha_scaling, rho = p.geometric_alpha_scaling;
-  for (int e = lane; e < T * M; e += 32) {
-    float al = alpha[e] * s0;
-    for (int jj = 0; jj < j; jj++) al *= rho;
-    alpha[e] = al;
-  }
-  __syncwarp();
-  if (lane == 0) {
-    float step = s0;
-    for (int jj = 0; jj < j; jj++) step *= rho;
-    const float lm = s.last_merit[b];
-    const bool converged = with_merit && (merit <= lm) && fabsf(lm - merit) < p.convergence_tolerance;
-    const int itn = s.iters[b] + 1;
-    s.iters[b] = itn;
-    s.backtracks[b] += j + 1;
-    s.op_cur[b] = 1 - cur;
-    s.st_cur[b] = 1 - scur;
-    if (with_merit) s.last_merit[b] = merit;
-    s.step[b] = step;
-    if (converged && !p.disable_convergence_exit)
-      s.status[b] = ILQG_STATUS_CONVERGED;
-    else if (itn >= p.max_solver_iters)
-      s.status[b] = ILQG_STATUS_MAX_ITERS;
-  }
-}
-
-__device__ __forceinline__ void ls_fail(const DevParams& p, const Slab& s, int b) {
-  s.iters[b] += 1;
-  s.backtracks[b] += p.max_backtracking_steps + 1;  // the reference's last rollout is never evaluated
-  s.status[b] = ILQG_STATUS_LINESEARCH_FAILED;      // the log's final iterate stays current
-}
-
 // CheckArmijoCondition, src/ilq_solver.cpp:350-362
 __device__ __forceinline__ bool ls_armijo(const DevParams& p, float last_merit, float merit, float ed, int j) {
   float step = p.initial_alpha_scaling;
@@ -386,84 +340,91 @@ __device__ __forceinline__ bool ls_armijo(const DevParams& p, float last_merit, 
 
 constexpr int KDEC_WARPS = 4;
 
-// decide after phase A: one warp per instance
 __global__ void __launch_bounds__(KDEC_WARPS * 32)
-k_ls_decide_a(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls) {
+k_ls_decide(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int cur_q) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * KDEC_WARPS + warp;
   if (b >= s.B || s.status[b] != ILQG_STATUS_RUNNING) return;
-  const int JA = ls.JA, T = d.T, n = d.n, M = d.M;
+  const int T = d.T, n = d.n, M = d.M, max_bt = p.max_backtracking_steps;
+  const int j0 = s.ls_next_j[b];
+  const bool fresh = j0 == 0;
+  const int W = fresh ? ls.JA : ls.JB;
+  const size_t base = fresh ? (size_t)b * ls.JA : (size_t)ls.nA_blocks * 32 + (size_t)ls.slot[b] * ls.JB;
   const float lm = s.last_merit[b], ed = s.expected_decrease[b];
-  int acc_j = -1;
+  int acc_jj = -1;
   float acc_merit = 0.f;
   if (!p.linesearch) {
-    acc_j = 0;
+    acc_jj = 0;  // ModifyLQStrategies returns after the first rollout (:322)
   } else {
-    for (int j = 0; j < JA; j++) {
-      const float merit = ls.merit[(size_t)b * JA + j];
-      if (ls_armijo(p, lm, merit, ed, j)) {
-        acc_j = j;
+    for (int jj = 0; jj < W && j0 + jj < max_bt; jj++) {
+      const float merit = ls.merit[base + jj];
+      if (ls_armijo(p, lm, merit, ed, j0 + jj)) {
+        acc_jj = jj;
         acc_merit = merit;
         break;
       }
     }
   }
-  if (acc_j >= 0) {
-    const int item = b * JA + acc_j;
-    const int cur = s.op_cur[b];
-    float4* dxs = reinterpret_cast<float4*>(s.op_xs[1 - cur] + (size_t)b * T * n);
-    const float4* sxs = reinterpret_cast<const float4*>(ls.traj_xs + (size_t)item * T * n);
+  if (acc_jj >= 0) {
+    const int j = j0 + acc_jj;
+    const size_t item = base + acc_jj;
+    const int cur = s.op_cur[b], scur = s.st_cur[b];
+    // accepted candidate -> operating point
+    float* dxs = s.op_xs[1 - cur] + (size_t)b * T * n;
+    const float* sxs = ls.traj_xs + item * T * n;
     float* dus = s.op_us[1 - cur] + (size_t)b * T * M;
-    const float* sus = ls.traj_us + (size_t)item * T * M;
+    const float* sus = ls.traj_us + item * T * M;
     if ((T * n) % 4 == 0) {
-      for (int e = lane; e < T * n / 4; e += 32) dxs[e] = sxs[e];
+      for (int e = lane; e < T * n / 4; e += 32)
+        reinterpret_cast<float4*>(dxs)[e] = reinterpret_cast<const float4*>(sxs)[e];
     } else {
-      for (int e = lane; e < T * n; e += 32)
-        (s.op_xs[1 - cur] + (size_t)b * T * n)[e] = (ls.traj_xs + (size_t)item * T * n)[e];
+      for (int e = lane; e < T * n; e += 32) dxs[e] = sxs[e];
     }
     for (int e = lane; e < T * M; e += 32) dus[e] = sus[e];
-    ls_total_costs(d, s, b, ls.vals + (size_t)(item / 32) * T * d.N * 32, item % 32, lane);
+    ls_total_costs(d, s, b, ls.vals + (item / 32) * T * d.N * 32, (int)(item % 32), lane);
+    // the scaled LQ strategies become current (ScaleAlphas, src/ilq_solver.cpp:66-72,314,339)
+    float* alpha = s.st_a[1 - scur] + (size_t)b * T * M;
+    const float s0 = p.initial_alpha_scaling, rho = p.geometric_alpha_scaling;
+    for (int e = lane; e < T * M; e += 32) {
+      float al = alpha[e] * s0;
+      for (int jj = 0; jj < j; jj++) al *= rho;
+      alpha[e] = al;
+    }
     __syncwarp();
-    ls_accept(d, p, s, b, acc_j, acc_merit, p.linesearch != 0, lane);
+    if (lane == 0) {
+      float step = s0;
+      for (int jj = 0; jj < j; jj++) step *= rho;
+      const bool with_merit = p.linesearch != 0;
+      // HasConverged, ilq_solver.h:126-130
+      const bool converged = with_merit && (acc_merit <= lm) && fabsf(lm - acc_merit) < p.convergence_tolerance;
+      const int itn = s.iters[b] + 1;
+      s.iters[b] = itn;
+      s.backtracks[b] += j + 1;
+      s.op_cur[b] = 1 - cur;
+      s.st_cur[b] = 1 - scur;
+      if (with_merit) s.last_merit[b] = acc_merit;
+      s.step[b] = step;
+      s.ls_next_j[b] = 0;
+      if (converged && !p.disable_convergence_exit)
+        s.status[b] = ILQG_STATUS_CONVERGED;
+      else if (itn >= p.max_solver_iters)
+        s.status[b] = ILQG_STATUS_MAX_ITERS;
+    }
   } else if (lane == 0) {
-    if (JA >= p.max_backtracking_steps) {
-      ls_fail(p, s, b);
+    const int jn = j0 + W;
+    if (jn >= max_bt) {
+      // ModifyLQStrategies returns false (:345-347); the log's final iterate stays current
+      s.iters[b] += 1;
+      s.backtracks[b] += max_bt + 1;  // the reference's last rollout is never evaluated
+      s.status[b] = ILQG_STATUS_LINESEARCH_FAILED;
+      s.ls_next_j[b] = 0;
     } else {
-      const int slot = atomicAdd(&ls.counts[LS_COUNT_PENDING], 1);
-      ls.pending[slot] = b;
+      s.ls_next_j[b] = jn;
+      const int q = atomicAdd(&ls.counts[1 - cur_q], 1);
+      ls.pend[1 - cur_q][q] = b;
+      ls.slot[b] = q;
     }
   }
-}
-
-// decide after phase B: one thread per pending instance
-__global__ void k_ls_decide_b(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls,
-                              int jbase, int jcount) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= ls.counts[LS_COUNT_PENDING]) return;
-  const int b = ls.pending[q];
-  const float lm = s.last_merit[b], ed = s.expected_decrease[b];
-  for (int jj = 0; jj < jcount; jj++) {
-    const float merit = ls.merit[(size_t)q * jcount + jj];
-    if (ls_armijo(p, lm, merit, ed, jbase + jj)) {
-      ls.accept_j[b] = jbase + jj;
-      const int slot = atomicAdd(&ls.counts[LS_COUNT_COMMIT], 1);
-      ls.commit[slot] = b;
-      return;
-    }
-  }
-  ls_fail(p, s, b);
-}
-
-// finalize after phase C (trajectory already in the operating-point buffer): one warp per commit slot
-__global__ void __launch_bounds__(KDEC_WARPS * 32)
-k_ls_finalize_c(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = blockIdx.x * KDEC_WARPS + warp;
-  if (q >= ls.counts[LS_COUNT_COMMIT]) return;
-  const int b = ls.commit[q];
-  ls_total_costs(d, s, b, ls.vals + (size_t)(q / 32) * d.T * d.N * 32, q % 32, lane);
-  __syncwarp();
-  ls_accept(d, p, s, b, ls.accept_j[b], ls.merit[q], true, lane);
 }
 
 // Solve() prologue bookkeeping (src/ilq_solver.cpp:86-107) after the LS_MODE_BEGIN rollout
@@ -490,6 +451,7 @@ k_begin_finalize(const __grid_constant__ DevDesc d, const DevParams p, Slab s, L
     s.op_cur[b] = 0;
     s.st_cur[b] = 0;
     s.iters[b] = 0;
+    s.ls_next_j[b] = 0;
     s.status[b] = p.max_solver_iters > 0 ? ILQG_STATUS_RUNNING : ILQG_STATUS_MAX_ITERS;
   }
 }

@@ -63,7 +63,7 @@ k_linearize_quadraticize_v2(const __grid_constant__ DevDesc d, Slab s, int only_
   const long long w = first + lane;
   const bool in_range = w < total;
   const int b = in_range ? (int)(w / T) : 0, k = in_range ? (int)(w % T) : 0;
-  const bool live = in_range && (!only_running || s.status[b] == ILQG_STATUS_RUNNING);
+  const bool live = in_range && (!only_running || instance_iterates(s, b));
   if (!__syncthreads_or(live)) return;
 
   // ---- stage x, u of the 32 records (each role reads all of it) ----
@@ -122,7 +122,7 @@ k_linearize_quadraticize_v2(const __grid_constant__ DevDesc d, Slab s, int only_
     const long long wr = first + r;
     if (wr >= total) break;
     const int br = (int)(wr / T);
-    if (only_running && s.status[br] != ILQG_STATUS_RUNNING) continue;
+    if (only_running && !instance_iterates(s, br)) continue;
     // template: LinearDynamicsApproximation ctor A = I, B = 0 (linear_dynamics_approximation.h:65-70);
     // QuadraticCostApproximation(xdim, state_reg) / SingleCostApproximation(udim, control_reg)
     for (int e = lane; e < d.rec / 4; e += 32) reinterpret_cast<float4*>(rec)[e] = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -1666,6 +1666,14 @@ int ilqg_reset(ilqg_handle h, int mask) {
   return ILQG_OK;
 }
 
+int ilqg_count_running(ilqg_handle h, int* running) {
+  if (!h || !running) return ILQG_ERR_BAD_HANDLE;
+  int c = 0;
+  for (auto& in : h->inst) c += in.status == ILQG_STATUS_RUNNING;
+  *running = c;
+  return ILQG_OK;
+}
+
 int ilqg_set_stream(ilqg_handle h, void*) { return h ? ILQG_OK : ILQG_ERR_BAD_HANDLE; }
 int ilqg_profile(ilqg_handle h, int) { return h ? ILQG_OK : ILQG_ERR_BAD_HANDLE; }
 int ilqg_profile_read(ilqg_handle h, int, double* total_ms, long long* launches) {

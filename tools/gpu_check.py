@@ -104,7 +104,7 @@ def full_solve(title, desc, params, x0, iters):
         h.upload_x0(x0)
         t = time.time()
         h.solve_begin()
-        h.iterate(iters)
+        h.solve(chunk=iters)
         h.synchronize()
         dt = time.time() - t
         outs[name] = {f: h.download(f) for f in (abi.XS, abi.US, abi.STATUS, abi.ITERS, abi.BACKTRACKS,

@@ -29,4 +29,6 @@ h.upload_x0(x0)
 h.solve_begin()
 h.iterate(iters)
 h.synchronize()
+if len(sys.argv) > 4:
+    h.solve()
 print("done", h.download(abi.ITERS).sum(), h.download(abi.BACKTRACKS).sum())
