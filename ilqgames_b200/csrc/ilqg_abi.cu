@@ -20,6 +20,8 @@ struct ilqg_solver {
   ilqg_layout layout;
   Slab s;
   LsScratch ls;
+  RecordPattern pat;
+  bool pat_ok;
   int ls_blocks_max;
   int ls_cur;  // which open-linesearch queue the next pass consumes
   int device;
@@ -50,6 +52,9 @@ namespace {
       return ILQG_ERR_CUDA;                                                       \
     }                                                                             \
   } while (0)
+
+template <typename T>
+int DevAlloc(ilqg_solver* h, T** out, size_t count, bool zero = true);
 
 inline bool IsConstraintKind(int kind) {
   return kind == ILQG_CONSTRAINT_PROXIMITY || kind == ILQG_CONSTRAINT_SINGLE_DIMENSION;
@@ -324,7 +329,7 @@ int DispatchBackward(ilqg_solver* h, int only_running, bool with_dxs) {
   return rc;
 }
 
-// upper bound on the `+= v` updates one role emits for one record (sizes the K_lq v2 lists)
+// upper bound on the `+= v` updates one role emits for one record (sizes the K_lq value lists)
 int MaxRoleEntries(const DevDesc& d) {
   int best = 0;
   for (int i = 0; i < d.N; i++) {
@@ -348,22 +353,90 @@ int MaxRoleEntries(const DevDesc& d) {
   return std::max(best, lin);
 }
 
+// Discover the static update pattern of the records on the device and build the gather table
+// (ilqg_records.cuh).  Leaves h->pat_ok = false when the shape does not fit (K_lq v1 is used).
+int BuildRecordPattern(ilqg_solver* h) {
+  const DevDesc& d = h->d;
+  h->pat_ok = false;
+  const int NR = d.N + 1;
+  const int E = (MaxRoleEntries(d) + 3) & ~3;
+  if (NR > 5 || d.rec >= 65536 || E <= 0) return ILQG_OK;
+  int *d_off = nullptr, *d_cnt = nullptr;
+  int rc;
+  if ((rc = DevAlloc(h, &d_off, (size_t)NR * E)) != ILQG_OK) return rc;
+  if ((rc = DevAlloc(h, &d_cnt, (size_t)NR)) != ILQG_OK) return rc;
+  k_record_pattern<<<1, 32, 0, h->stream>>>(h->d, d_off, d_cnt, E);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  std::vector<int> off((size_t)NR * E), cnt(NR);
+  CUDA_TRY(cudaMemcpyAsync(off.data(), d_off, off.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(cnt.data(), d_cnt, cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  std::vector<GatherItem> items;
+  std::vector<unsigned short> idx;
+  for (int r = 0; r < NR; r++) {
+    if (cnt[r] > E) return ILQG_OK;  // bound was wrong: fall back
+    // distinct offsets of this role in first-appearance order, entries kept in emission order
+    std::vector<int> seen;
+    for (int e = 0; e < cnt[r]; e++) {
+      const int o = off[(size_t)r * E + e];
+      if (o < 0 || o >= d.rec) return ILQG_ERR_INVALID_ARGUMENT;
+      if (std::find(seen.begin(), seen.end(), o) == seen.end()) seen.push_back(o);
+    }
+    for (int o : seen) {
+      GatherItem it{o, r, (int)idx.size(), 0};
+      for (int e = 0; e < cnt[r]; e++)
+        if (off[(size_t)r * E + e] == o) {
+          idx.push_back((unsigned short)e);
+          it.count++;
+        }
+      items.push_back(it);
+    }
+  }
+  // record template: A = I, Q_i = state_reg I, R_p = control_reg I (owner of the pair)
+  std::vector<float> tmpl(d.rec, 0.f);
+  for (int a = 0; a < d.n; a++) {
+    tmpl[d.offA + a * d.n + a] = 1.f;
+    for (int i = 0; i < d.N; i++) tmpl[d.offQ + (i * d.n + a) * d.n + a] = d.state_reg[i];
+  }
+  for (int p = 0; p < d.num_pairs; p++) {
+    const int mj = d.udim[d.pair_j[p]];
+    for (int a = 0; a < mj; a++) tmpl[d.offR + d.pair_Roff[p] + a * mj + a] = d.control_reg[d.pair_i[p]];
+  }
+  const size_t smem = klq_smem_bytes(d.n, d.M, d.N, E, d.rec, (int)items.size(), (int)idx.size());
+  if (smem > 110 * 1024) return ILQG_OK;
+  GatherItem* d_items = nullptr;
+  unsigned short* d_idx = nullptr;
+  float* d_tmpl = nullptr;
+  if ((rc = DevAlloc(h, &d_items, items.size())) != ILQG_OK) return rc;
+  if ((rc = DevAlloc(h, &d_idx, idx.size())) != ILQG_OK) return rc;
+  if ((rc = DevAlloc(h, &d_tmpl, tmpl.size())) != ILQG_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(GatherItem), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_idx, idx.data(), idx.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_tmpl, tmpl.data(), tmpl.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->pat.items = d_items;
+  h->pat.idx = d_idx;
+  h->pat.tmpl = d_tmpl;
+  h->pat.num_items = (int)items.size();
+  h->pat.num_idx = (int)idx.size();
+  h->pat.E = E;
+  h->pat_ok = true;
+  return ILQG_OK;
+}
+
 int LaunchLqRecords(ilqg_solver* h, int only_running) {
   const DevDesc& d = h->d;
-  {
-    // v2: role-per-warp / record-per-lane emission into lists, then per-record assembly
-    const int E = (MaxRoleEntries(d) + 3) & ~3;
-    const size_t smem2 = klq2_smem_bytes(d.n, d.M, d.N, E, d.rec);
-    if (d.N + 1 <= 5 && smem2 <= 110 * 1024 && d.rec < 65536) {
-      int rc2 = SetSmem(k_linearize_quadraticize_v2, smem2);
-      if (rc2 != ILQG_OK) return rc2;
-      const long long recs = (long long)h->B * d.T;
-      ProfScope prof(h, 0);
-      k_linearize_quadraticize_v2<<<(int)((recs + 31) / 32), (d.N + 1) * 32, smem2, h->stream>>>(h->d, h->s, only_running, E);
-      h->launches++;
-      CUDA_TRY(cudaGetLastError());
-      return ILQG_OK;
-    }
+  if (h->pat_ok) {
+    const size_t smem3 = klq_smem_bytes(d.n, d.M, d.N, h->pat.E, d.rec, h->pat.num_items, h->pat.num_idx);
+    int rc3 = SetSmem(k_linearize_quadraticize_v3, smem3);
+    if (rc3 != ILQG_OK) return rc3;
+    const long long recs = (long long)h->B * d.T;
+    ProfScope prof(h, 0);
+    k_linearize_quadraticize_v3<<<(int)((recs + 31) / 32), (d.N + 1) * 32, smem3, h->stream>>>(h->d, h->s, h->pat, only_running);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ILQG_OK;
   }
   const size_t smem = sizeof(float) * KLQ_WARPS * (size_t)(d.rec + ((d.n + d.M + 3) & ~3));
   int rc = SetSmem(k_linearize_quadraticize, smem);
@@ -377,7 +450,7 @@ int LaunchLqRecords(ilqg_solver* h, int only_running) {
   return ILQG_OK;
 }
 
-int LaunchLsEval(ilqg_solver* h, int mode, int blocks) {
+int LaunchLsEval(ilqg_solver* h, int mode, int blocks, int q_offset) {
   const DevDesc& d = h->d;
   const size_t smem = sizeof(float) * (size_t)ls_smem_floats(d.n, d.M, d.N, d.num_subsystems);
   if (blocks <= 0) return ILQG_OK;
@@ -387,7 +460,7 @@ int LaunchLsEval(ilqg_solver* h, int mode, int blocks) {
 #define LS_CASE(NW)                                                                              \
   case NW:                                                                                       \
     if ((rc = SetSmem(k_ls_eval<NW>, smem)) != ILQG_OK) return rc;                                \
-    k_ls_eval<NW><<<blocks, NW * 32, smem, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur); \
+    k_ls_eval<NW><<<blocks, NW * 32, smem, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset); \
     break;
   switch (nw) {
     LS_CASE(2) LS_CASE(3) LS_CASE(4) LS_CASE(5) LS_CASE(6) LS_CASE(7) LS_CASE(8)
@@ -399,26 +472,31 @@ int LaunchLsEval(ilqg_solver* h, int mode, int blocks) {
   return ILQG_OK;
 }
 
-// One linesearch pass (ilqg_linesearch.cuh): evaluate this pass's candidate windows, then decide.
-int LaunchLinesearchPass(ilqg_solver* h) {
+// ILQSolver::ModifyLQStrategies for the whole batch (ilqg_linesearch.cuh): the first window for
+// everyone, then the remaining candidates for the instances that rejected it, chunk by chunk.
+int LaunchLinesearch(ilqg_solver* h) {
   const int B = h->B;
   int rc;
   ProfScope prof(h, 2);
+  const int dec_blocks = (B + KDEC_WARPS - 1) / KDEC_WARPS;
+  // fresh window: unresolved instances are appended to queue 1 - ls_cur
   CUDA_TRY(cudaMemsetAsync(h->ls.counts + (1 - h->ls_cur), 0, sizeof(int), h->stream));
-  const int nB_blocks = (int)(((long long)B * h->ls.JB + 31) / 32);
-  if ((rc = LaunchLsEval(h, LS_MODE_LS, h->ls.nA_blocks + nB_blocks)) != ILQG_OK) return rc;
-  k_ls_decide<<<(B + KDEC_WARPS - 1) / KDEC_WARPS, KDEC_WARPS * 32, 0, h->stream>>>(h->d, h->p, h->s, h->ls, h->ls_cur);
+  if ((rc = LaunchLsEval(h, LS_MODE_FRESH, h->ls.nA_blocks, 0)) != ILQG_OK) return rc;
+  k_ls_decide<<<dec_blocks, KDEC_WARPS * 32, 0, h->stream>>>(h->d, h->p, h->s, h->ls, LS_MODE_FRESH, h->ls_cur, 0);
   h->launches++;
+  h->ls_cur = 1 - h->ls_cur;  // the queue just filled is now the one to drain
+  if (h->p.linesearch && h->ls.JB > 0) {
+    const int cap = h->ls.cap;
+    const int qblocks = (int)(((long long)cap * h->ls.JB + 31) / 32);
+    for (int q0 = 0; q0 < B; q0 += cap) {
+      if ((rc = LaunchLsEval(h, LS_MODE_QUEUED, qblocks, q0)) != ILQG_OK) return rc;
+      k_ls_decide<<<(cap + KDEC_WARPS - 1) / KDEC_WARPS, KDEC_WARPS * 32, 0, h->stream>>>(
+          h->d, h->p, h->s, h->ls, LS_MODE_QUEUED, h->ls_cur, q0);
+      h->launches++;
+    }
+  }
   CUDA_TRY(cudaGetLastError());
-  h->ls_cur = 1 - h->ls_cur;
   return ILQG_OK;
-}
-
-// passes needed to exhaust max_backtracking_steps candidates
-int LinesearchPasses(const ilqg_solver* h) {
-  const int max_bt = std::max(1, h->p.max_backtracking_steps);
-  if (!h->p.linesearch || max_bt <= h->ls.JA) return 1;
-  return 1 + (max_bt - h->ls.JA + h->ls.JB - 1) / h->ls.JB;
 }
 
 int LaunchSolveBegin(ilqg_solver* h) {
@@ -426,7 +504,7 @@ int LaunchSolveBegin(ilqg_solver* h) {
   ProfScope prof(h, 3);
   CUDA_TRY(cudaMemsetAsync(h->ls.counts, 0, 2 * sizeof(int), h->stream));
   h->ls_cur = 0;
-  rc = LaunchLsEval(h, LS_MODE_BEGIN, (h->B + 31) / 32);
+  rc = LaunchLsEval(h, LS_MODE_BEGIN, (h->B + 31) / 32, 0);
   if (rc == ILQG_OK) {
     k_begin_finalize<<<(h->B + KDEC_WARPS - 1) / KDEC_WARPS, KDEC_WARPS * 32, 0, h->stream>>>(h->d, h->p, h->s, h->ls);
     h->launches++;
@@ -436,7 +514,7 @@ int LaunchSolveBegin(ilqg_solver* h) {
 }
 
 template <typename T>
-int DevAlloc(ilqg_solver* h, T** out, size_t count, bool zero = true) {
+int DevAlloc(ilqg_solver* h, T** out, size_t count, bool zero) {
   void* p = nullptr;
   const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
   cudaError_t e = cudaMalloc(&p, bytes);
@@ -669,16 +747,18 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
     LsScratch& ls = h->ls;
     std::memset(&ls, 0, sizeof(ls));
     const int max_bt = std::max(1, params->max_backtracking_steps);
-    int JA = 4, JB = 16;
+    int JA = 1;
     if (const char* e = std::getenv("ILQG_LS_JA")) JA = std::max(1, std::atoi(e));  // tuning knobs
-    if (const char* e = std::getenv("ILQG_LS_JB")) JB = std::max(1, std::atoi(e));
     if (!params->linesearch) JA = 1;
     JA = std::min(JA, max_bt);
-    JB = std::min(JB, max_bt);
+    const int JB = max_bt - JA;  // the second window covers every remaining candidate
+    int cap = (int)std::max<size_t>(1, (B + 7) / 8);
+    if (const char* e = std::getenv("ILQG_LS_CAP")) cap = std::max(1, std::min<int>((int)B, std::atoi(e)));
     ls.JA = JA;
     ls.JB = JB;
+    ls.cap = cap;
     ls.nA_blocks = (int)((B * JA + 31) / 32);
-    const size_t blocks_max = (size_t)ls.nA_blocks + (B * JB + 31) / 32;
+    const size_t blocks_max = std::max<size_t>(ls.nA_blocks, ((size_t)cap * JB + 31) / 32);
     h->ls_blocks_max = (int)blocks_max;
     h->ls_cur = 0;
 #define ALLOCNZ(ptr, count)                                               \
@@ -706,6 +786,7 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
   if ((rc = Fill(h, s.expected_decrease, INFINITY, B)) != ILQG_OK) return fail(rc);
   if ((rc = Fill(h, s.max_con_err, INFINITY, B)) != ILQG_OK) return fail(rc);
   if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(ILQG_ERR_CUDA);
+  if ((rc = BuildRecordPattern(h)) != ILQG_OK) return fail(rc);
   *out = h;
   return ILQG_OK;
 }
@@ -822,13 +903,7 @@ int ilqg_lq_backward(ilqg_handle h) {
 
 int ilqg_linesearch(ilqg_handle h) {
   ENTER(h);
-  // a stand-alone linesearch runs to completion: enough passes to exhaust every candidate
-  const int passes = LinesearchPasses(h);
-  for (int k = 0; k < passes; k++) {
-    const int rc = LaunchLinesearchPass(h);
-    if (rc != ILQG_OK) return rc;
-  }
-  return ILQG_OK;
+  return LaunchLinesearch(h);
 }
 
 int ilqg_iterate(ilqg_handle h, int max_iters, int* iters_done) {
@@ -837,7 +912,7 @@ int ilqg_iterate(ilqg_handle h, int max_iters, int* iters_done) {
   for (int it = 0; it < max_iters; it++) {
     if ((rc = LaunchLqRecords(h, 1)) != ILQG_OK) return rc;
     if ((rc = DispatchBackward(h, 1, false)) != ILQG_OK) return rc;
-    if ((rc = LaunchLinesearchPass(h)) != ILQG_OK) return rc;
+    if ((rc = LaunchLinesearch(h)) != ILQG_OK) return rc;
   }
   if (iters_done) {
     std::vector<int> iters(h->B);

@@ -301,7 +301,6 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
       const int e = l16 + 16 * t;
       if (e < lrr4) reinterpret_cast<float4*>(lrr)[e] = preL[t];
     }
-    if (kk > 0) prefetch(kk - 1);
     __syncwarp();
 
     // ---- BZ_i = B_i^T Z_i (:128), stored transposed: BZt[col][c] ----
@@ -414,6 +413,9 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
       }
     }
     __syncwarp();
+    // the next record's [A|B], [l|R|r] travel while this step's products run (issued here, after
+    // the solve, so the prefetch registers are not live across it)
+    if (kk > 0) prefetch(kk - 1);
 
     // ---- F = A - sum_i B_i P_i ; beta = - sum_i B_i alpha_i (:189-194) ----
     {
@@ -479,16 +481,19 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
       {
         float bseg[TC];
         ldvec<TC>(beta + c0, bseg);
+        // rows (l16 >> 2) + 4 r: consecutive lanes' rows differ in parity, so the 128-bit row
+        // segments of a quarter-warp fall on distinct banks
 #pragma unroll
         for (int r = 0; r < TR; r++) {
+          const int row = (l16 >> 2) + 4 * r;
           float zr[TC];
-          ldvec<TC>(Zi + (a0 + r) * NX + c0, zr);
+          ldvec<TC>(Zi + row * NX + c0, zr);
           float part = 0.f;
 #pragma unroll
           for (int j = 0; j < TC; j++) part = fmaf(zr[j], bseg[j], part);
           part += __shfl_xor_sync(0xffffffffu, part, 1);
           part += __shfl_xor_sync(0xffffffffu, part, 2);
-          if ((l16 & 3) == 0) tv[a0 + r] = zi[a0 + r] + part;
+          if ((l16 & 3) == 0) tv[row] = zi[row] + part;
         }
       }
       __syncwarp();

@@ -5,16 +5,17 @@
 // The reference backtracks sequentially: roll out with alpha * s0 * rho^j, evaluate the merit,
 // test Armijo, repeat.  Candidate j's trajectory and merit depend only on j, never on the
 // outcome of candidates < j, so evaluating a WINDOW of candidates at once and taking the FIRST
-// one that passes Armijo gives exactly the sequential result.  Each pass of ilqg_iterate runs
-//   k_ls_eval    candidates [0, JA) for every instance that starts a linesearch in this pass and
-//                candidates [j0, j0 + JB) for every instance whose linesearch is still open
-//   k_ls_decide  first passing candidate -> accept (operating point, strategies, merit, status);
-//                none -> the instance keeps its linesearch open (ls_next_j = j0 + window) and is
-//                queued for the next pass; past max_backtracking_steps -> LINESEARCH_FAILED
-// An instance with an open linesearch is skipped by K_lq / K_bwd until it resolves, so deep
-// backtrackers never stall the batch: every instance performs exactly the reference's sequence of
-// computations, only scheduled in different passes (per-instance
-// Armijo state machine).  The host never synchronises inside a pass.
+// one that passes Armijo gives exactly the sequential result.  On the benchmark workload 97.8 %
+// of all linesearches accept j = 0 and most of the rest backtrack >= 8 times (measured with the
+// oracle), hence two windows per linesearch:
+//   k_ls_eval / k_ls_decide   window [0, JA) for every running instance (JA = 1 by default);
+//                             instances that reject it are queued (per-instance Armijo state
+//                             machine: ls_next_j)
+//   k_ls_eval / k_ls_decide   window [JA, max_backtracking_steps) for the queued instances, all
+//                             candidates at once, in chunks of `cap` queue slots so the candidate
+//                             trajectories fit the scratch; first passing candidate is accepted,
+//                             none -> LINESEARCH_FAILED
+// Chunk launches whose queue range is empty exit immediately; the host never synchronises.
 //
 // k_ls_eval maps one (instance, candidate) ITEM to one lane, and one ROLE to each warp of the
 // block: warps [0, S) integrate subsystem s (u = u_ref - P dx - alpha, then RK4 x 2 substeps),
@@ -26,7 +27,7 @@
 
 namespace ilqg {
 
-enum { LS_MODE_BEGIN = 0, LS_MODE_LS = 1 };
+enum { LS_MODE_BEGIN = 0 };
 
 struct LsScratch {
   float* traj_xs;   // [items][T][n]   candidate trajectories (item = global lane index of the launch)
@@ -39,6 +40,7 @@ struct LsScratch {
   int* slot;        // [B] position of an instance in the queue it is in
   int JA, JB;       // window sizes: fresh linesearch / continued linesearch
   int nA_blocks;    // blocks of a k_ls_eval launch that serve fresh instances
+  int cap;          // queue slots one continued-window launch can hold trajectories for
 };
 
 struct LsItem {
@@ -47,8 +49,10 @@ struct LsItem {
 };
 
 // cur: which queue this pass consumes
+enum { LS_MODE_FRESH = 1, LS_MODE_QUEUED = 2 };
+
 __device__ __forceinline__ LsItem ls_decode(const DevParams& p, const Slab& s, const LsScratch& ls, int mode,
-                                            int cur, int block, int lane) {
+                                            int cur, int q_offset, int block, int lane) {
   LsItem it;
   it.b = 0;
   it.j = 0;
@@ -56,16 +60,16 @@ __device__ __forceinline__ LsItem ls_decode(const DevParams& p, const Slab& s, c
   if (mode == LS_MODE_BEGIN) {
     it.b = block * 32 + lane;
     it.valid = it.b < s.B;
-  } else if (block < ls.nA_blocks) {
+  } else if (mode == LS_MODE_FRESH) {
     const int item = block * 32 + lane;
     it.b = item / ls.JA;
     it.j = item % ls.JA;
     it.valid = it.b < s.B && s.status[it.b] == ILQG_STATUS_RUNNING && s.ls_next_j[it.b] == 0 &&
                it.j < p.max_backtracking_steps;
   } else {
-    const int item = (block - ls.nA_blocks) * 32 + lane;
-    const int q = item / ls.JB;
-    if (q < ls.counts[cur]) {
+    const int item = block * 32 + lane;
+    const int q = q_offset + item / ls.JB;
+    if (item / ls.JB < ls.cap && q < ls.counts[cur]) {
       it.b = ls.pend[cur][q];
       it.j = s.ls_next_j[it.b] + item % ls.JB;
       it.valid = it.j < p.max_backtracking_steps;
@@ -100,12 +104,13 @@ __host__ __device__ inline int ls_smem_floats(int n, int M, int N, int S) {
 // NW = S + N warps per block; the register cap targets >= 24 resident warps per SM
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, (16 + NW - 1) / NW)
-k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode, int cur_q) {
+k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode, int cur_q,
+          int q_offset) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = d.n, M = d.M, N = d.N, T = d.T, S = d.num_subsystems;
   const int item = blockIdx.x * 32 + lane;
-  const LsItem it = ls_decode(p, s, ls, mode, cur_q, blockIdx.x, lane);
+  const LsItem it = ls_decode(p, s, ls, mode, cur_q, q_offset, blockIdx.x, lane);
   if (!__syncthreads_or(it.valid)) return;
   const bool valid = it.valid;
   const int b = it.b;
@@ -341,15 +346,23 @@ __device__ __forceinline__ bool ls_armijo(const DevParams& p, float last_merit, 
 constexpr int KDEC_WARPS = 4;
 
 __global__ void __launch_bounds__(KDEC_WARPS * 32)
-k_ls_decide(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int cur_q) {
+k_ls_decide(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode, int cur_q,
+            int q_offset) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * KDEC_WARPS + warp;
-  if (b >= s.B || s.status[b] != ILQG_STATUS_RUNNING) return;
+  const int w = blockIdx.x * KDEC_WARPS + warp;
+  int b;
+  if (mode == LS_MODE_FRESH) {
+    b = w;
+    if (b >= s.B || s.status[b] != ILQG_STATUS_RUNNING || s.ls_next_j[b] != 0) return;
+  } else {
+    if (w >= ls.cap || q_offset + w >= ls.counts[cur_q]) return;
+    b = ls.pend[cur_q][q_offset + w];
+  }
   const int T = d.T, n = d.n, M = d.M, max_bt = p.max_backtracking_steps;
   const int j0 = s.ls_next_j[b];
-  const bool fresh = j0 == 0;
+  const bool fresh = mode == LS_MODE_FRESH;
   const int W = fresh ? ls.JA : ls.JB;
-  const size_t base = fresh ? (size_t)b * ls.JA : (size_t)ls.nA_blocks * 32 + (size_t)ls.slot[b] * ls.JB;
+  const size_t base = fresh ? (size_t)b * ls.JA : (size_t)w * ls.JB;
   const float lm = s.last_merit[b], ed = s.expected_decrease[b];
   int acc_jj = -1;
   float acc_merit = 0.f;

@@ -1,62 +1,154 @@
-// ilqg_records.cuh -- K_lq v2: fused ComputeLinearization + ComputeCostQuadraticization
+// ilqg_records.cuh -- K_lq: fused ComputeLinearization + ComputeCostQuadraticization
 // (src/ilq_solver.cpp:437-455, 471-490) producing the dense LQ records.
 //
-// A block owns 32 consecutive (instance, timestep) records.
-//   phase 1  one ROLE per warp, one record per lane: warps [0, N) run player i's cost /
-//            constraint records, warp N runs every subsystem's Jacobian.  Instead of touching a
-//            dense Hessian each role appends its `+= v` updates (offset in the record, value) to
-//            a lane-minor list in shared memory, in the reference's accumulation order.  All lanes
-//            of a warp execute the same record kinds, so the scalar cost code runs at full SIMT
-//            width (v1 ran it on 3 of 32 lanes).
-//   phase 2  one record at a time per warp: write the record template (zeros, A = I, Q_i =
-//            state_reg * I, R = control_reg * I) into a shared staging buffer, let lane `role`
-//            replay its list in order, then stream the record to HBM with 128-bit stores.
+// Every cost / constraint / subsystem kind emits a FIXED sequence of `+= v` updates for given
+// descriptor indices (ilqg_device.cuh), so WHERE a record is touched is a static property of
+// the problem; only the values depend on (x, u, lambda, mu).  At handle creation
+// k_record_pattern records the offsets once and the host groups them into a gather table:
+//   entry e of role r  ->  record offset;  gather item g = (offset, role, entries to sum in order)
+// A block owns 32 consecutive (instance, timestep) records:
+//   phase 1  one ROLE per warp (player i's costs; the last warp all subsystem Jacobians), one
+//            record per lane -- the scalar cost code runs at full SIMT width -- writing only the
+//            update VALUES into a lane-minor shared array;
+//   phase 2  each warp keeps a staging copy of the record template (A = I, Q_i = state_reg I,
+//            R = control_reg I, zeros elsewhere); per record, lane g adds its gather item's values
+//            (in the reference's accumulation order) onto the template value, the warp streams the
+//            record to HBM with 128-bit stores and restores the touched words.
 #pragma once
 #include "ilqg_kernels.cuh"
 
 namespace ilqg {
 
-struct ListSink {
-  unsigned short* off;  // [E][32] lane-minor
-  float* val;           // [E][32]
+struct GatherItem {
+  int off;    // offset in the record
+  int role;   // which role's value list
+  int start;  // first index into gather_idx
+  int count;  // entries to add, in order
+};
+
+struct RecordPattern {
+  const GatherItem* items;          // [num_items]
+  const unsigned short* idx;        // entry indices
+  const float* tmpl;                // [rec] record template
+  int num_items, num_idx;
+  int E;                            // value-list capacity per role (multiple of 4)
+};
+
+// sink that stores update values (phase 1) ...
+struct ValueSink {
+  float* val;  // [E][32] lane-minor
   int lane, cnt, cap;
-  int base_H, ld, base_G;
-  __device__ __forceinline__ void push(int o, float v) {
-    if (cnt < cap) {
-      off[cnt * 32 + lane] = (unsigned short)o;
-      val[cnt * 32 + lane] = v;
-    }
+  __device__ __forceinline__ void push(float v) {
+    if (cnt < cap) val[cnt * 32 + lane] = v;
     cnt++;
   }
-  __device__ __forceinline__ void H(int r, int c, float v) { push(base_H + r * ld + c, v); }
-  __device__ __forceinline__ void G(int i, float v) { push(base_G + i, v); }
+  __device__ __forceinline__ void H(int, int, float v) { push(v); }
+  __device__ __forceinline__ void G(int, float v) { push(v); }
 };
-
-struct LinListSink {
-  ListSink* ls;
+struct LinValueSink {
+  ValueSink* vs;
+  __device__ __forceinline__ void addA(int, int, float v) { vs->push(v); }
+  __device__ __forceinline__ void addB(int, int, float v) { vs->push(v); }
+};
+// ... and sink that stores update offsets (pattern discovery)
+struct OffsetSink {
+  int* off;
+  int cnt, cap;
+  int base_H, ld, base_G;
+  __device__ __forceinline__ void push(int o) {
+    if (cnt < cap) off[cnt] = o;
+    cnt++;
+  }
+  __device__ __forceinline__ void H(int r, int c, float) { push(base_H + r * ld + c); }
+  __device__ __forceinline__ void G(int i, float) { push(base_G + i); }
+};
+struct LinOffsetSink {
+  OffsetSink* os;
   int offA, offB, n, M;
-  __device__ __forceinline__ void addA(int r, int c, float v) { ls->push(offA + r * n + c, v); }
-  __device__ __forceinline__ void addB(int r, int c, float v) { ls->push(offB + r * M + c, v); }
+  __device__ __forceinline__ void addA(int r, int c, float) { os->push(offA + r * n + c); }
+  __device__ __forceinline__ void addB(int r, int c, float) { os->push(offB + r * M + c); }
 };
 
-// shared memory (bytes): xu[n+M][32] floats | cnt[NR][32] ints | val[NR][E][32] floats |
-//                        off[NR][E][32] u16 | rec[NR][rec] floats      (NR = N + 1 roles = warps)
-__host__ __device__ inline size_t klq2_smem_bytes(int n, int M, int N, int E, int rec) {
+// The walk over one role's records, shared by the value pass and the pattern pass so both see
+// the same sequence.  `full` = PlayerCost::Quadraticize, else QuadraticizeControlCosts
+// (src/ilq_solver.cpp:483-487); in the latter case the skipped records still emit (zeros are
+// pushed by the caller through `skip`).
+template <int XS, class PlayerFn, class LinFn>
+__device__ __forceinline__ void walk_role(const DevDesc& d, int role, PlayerFn&& player, LinFn&& lin) {
+  if (role < d.N) {
+    for (int c = d.cost_begin[role]; c < d.cost_begin[role + 1]; c++) player(d.cost[c]);
+  } else {
+    for (int sidx = 0; sidx < d.num_subsystems; sidx++) lin(d.sub[sidx]);
+  }
+}
+
+// number of updates a record kind emits (HESS = true) -- only used to pad skipped records
+__device__ __forceinline__ int record_updates(const DevCost& cd, int dim) {
+  switch (cd.kind) {
+    case ILQG_COST_QUADRATIC: return cd.d0 >= 0 ? 2 : 2 * dim;
+    case ILQG_COST_PROXIMITY:
+    case ILQG_CONSTRAINT_PROXIMITY: return 20;
+    case ILQG_COST_SEMIQUADRATIC:
+    case ILQG_CONSTRAINT_SINGLE_DIMENSION: return 2;
+    default: return 6;
+  }
+}
+
+// one thread per role: record the offsets of every update at a dummy input
+__global__ void k_record_pattern(const __grid_constant__ DevDesc d, int* offsets /*[NR][E]*/, int* counts, int E) {
+  const int role = threadIdx.x;
+  if (role > d.N) return;
+  float zeros[ILQG_MAX_XDIM + ILQG_MAX_UDIM];
+  for (int a = 0; a < ILQG_MAX_XDIM + ILQG_MAX_UDIM; a++) zeros[a] = 0.5f + 0.37f * a;
+  OffsetSink sink;
+  sink.off = offsets + (size_t)role * E;
+  sink.cnt = 0;
+  sink.cap = E;
+  const float* x = zeros;
+  const float* u = zeros + d.n;
+  walk_role<1>(
+      d, role,
+      [&](const DevCost& cd) {
+        if (cd.arg < 0) {
+          sink.base_H = d.offQ + role * d.n * d.n;
+          sink.ld = d.n;
+          sink.base_G = d.offl + role * d.n;
+          quadraticize_record_sink<true, 1, false>(d, cd, x, d.n, 0.f, 10.f, sink);
+        } else {
+          const int mj = d.udim[cd.arg];
+          sink.base_H = d.offR + d.pair_Roff[cd.pair];
+          sink.ld = mj;
+          sink.base_G = d.offr + d.pair_roff[cd.pair];
+          quadraticize_record_sink<true, 1, false>(d, cd, u + d.uoff[cd.arg], mj, 0.f, 10.f, sink);
+        }
+      },
+      [&](const DevSubsystem& sub) {
+        LinOffsetSink lin{&sink, d.offA, d.offB, d.n, d.M};
+        subsystem_linearize_sink<1>(d, sub, x, u, lin);
+      });
+  counts[role] = sink.cnt;
+}
+
+// shared memory (floats unless noted): xu[n+M][32] | vals[NR][E][32] | rec[NR][rec] |
+//                                      items[num_items] (GatherItem) | idx[num_idx] (u16)
+__host__ __device__ inline size_t klq_smem_bytes(int n, int M, int N, int E, int rec, int num_items, int num_idx) {
   const int NR = N + 1;
-  return sizeof(float) * ((size_t)(n + M) * 32 + (size_t)NR * 32 + (size_t)NR * E * 32 + (size_t)NR * rec) +
-         sizeof(unsigned short) * (size_t)NR * E * 32;
+  size_t b = sizeof(float) * ((size_t)(n + M) * 32 + (size_t)NR * E * 32 + (size_t)NR * rec);
+  b += sizeof(GatherItem) * (size_t)num_items;
+  b += sizeof(unsigned short) * (size_t)((num_idx + 7) & ~7);
+  return b;
 }
 
 __global__ void __launch_bounds__(160)
-k_linearize_quadraticize_v2(const __grid_constant__ DevDesc d, Slab s, int only_running, int E) {
+k_linearize_quadraticize_v3(const __grid_constant__ DevDesc d, Slab s, RecordPattern pat, int only_running) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = d.n, M = d.M, N = d.N, T = d.T, NR = N + 1;
-  float* xu = smem;                                   // [n+M][32]
-  int* cnts = reinterpret_cast<int*>(xu + (n + M) * 32);  // [NR][32]
-  float* vals = reinterpret_cast<float*>(cnts + NR * 32);  // [NR][E][32]
-  float* recs = vals + (size_t)NR * E * 32;           // [NR][rec]
-  unsigned short* offs = reinterpret_cast<unsigned short*>(recs + (size_t)NR * d.rec);  // [NR][E][32]
+  const int n = d.n, M = d.M, N = d.N, T = d.T, NR = N + 1, E = pat.E;
+  float* xu = smem;                                        // [n+M][32]
+  float* vals = xu + (n + M) * 32;                         // [NR][E][32]
+  float* recs = vals + (size_t)NR * E * 32;                // [NR][rec]
+  GatherItem* items = reinterpret_cast<GatherItem*>(recs + (size_t)NR * d.rec);
+  unsigned short* gidx = reinterpret_cast<unsigned short*>(items + pat.num_items);
 
   const long long first = (long long)blockIdx.x * 32;
   const long long total = (long long)s.B * T;
@@ -66,86 +158,74 @@ k_linearize_quadraticize_v2(const __grid_constant__ DevDesc d, Slab s, int only_
   const bool live = in_range && (!only_running || instance_iterates(s, b));
   if (!__syncthreads_or(live)) return;
 
-  // ---- stage x, u of the 32 records (each role reads all of it) ----
+  // ---- block prologue: x, u of the 32 records; gather table; per-warp template copy ----
   {
     const int cur = in_range ? s.op_cur[b] : 0;
     const float* xs = s.op_xs[cur] + ((size_t)b * T + k) * n;
     const float* us = s.op_us[cur] + ((size_t)b * T + k) * M;
     for (int e = warp; e < n + M; e += NR) xu[e * 32 + lane] = in_range ? (e < n ? xs[e] : us[e - n]) : 0.f;
+    for (int e = threadIdx.x; e < pat.num_items; e += blockDim.x) items[e] = pat.items[e];
+    for (int e = threadIdx.x; e < pat.num_idx; e += blockDim.x) gidx[e] = pat.idx[e];
+    float* rec = recs + (size_t)warp * d.rec;
+    for (int e = lane; e < d.rec / 4; e += 32)
+      reinterpret_cast<float4*>(rec)[e] = __ldg(reinterpret_cast<const float4*>(pat.tmpl) + e);
   }
   __syncthreads();
 
-  // ---- phase 1: role = warp, record = lane ----
+  // ---- phase 1: role = warp, record = lane: update values only ----
   {
-    ListSink sink;
-    sink.off = offs + (size_t)warp * E * 32;
+    ValueSink sink;
     sink.val = vals + (size_t)warp * E * 32;
     sink.lane = lane;
     sink.cnt = 0;
     sink.cap = E;
-    const float* x = xu + lane;            // element idx at x[idx * 32]
+    const float* x = xu + lane;  // element idx at x[idx * 32]
     const float* u = xu + n * 32 + lane;
-    if (warp < N) {
-      const int i = warp;
-      const bool full = d.cost_structure[i] == ILQG_COST_SUM || (live && s.te_quad[(size_t)b * N + i] == k);
-      const float mu = live ? s.mu[b] : 0.f;
-      for (int c = d.cost_begin[i]; c < d.cost_begin[i + 1]; c++) {
-        const DevCost& cd = d.cost[c];
-        const bool is_con = cd.slot >= 0;
-        if (!full && (cd.arg < 0 || is_con)) continue;  // QuadraticizeControlCosts
-        const float lambda =
-            (is_con && live) ? s.lambdas[((size_t)b * d.num_constraints + cd.slot) * T + s.lambda_index[k]] : 0.f;
-        if (cd.arg < 0) {
-          sink.base_H = d.offQ + i * n * n;
-          sink.ld = n;
-          sink.base_G = d.offl + i * n;
-          quadraticize_record_sink<true, 32, false>(d, cd, x, n, lambda, mu, sink);
-        } else {
-          const int mj = d.udim[cd.arg];
-          sink.base_H = d.offR + d.pair_Roff[cd.pair];
-          sink.ld = mj;
-          sink.base_G = d.offr + d.pair_roff[cd.pair];
-          quadraticize_record_sink<true, 32, false>(d, cd, u + d.uoff[cd.arg] * 32, mj, lambda, mu, sink);
-        }
-      }
-    } else {
-      LinListSink lin{&sink, d.offA, d.offB, n, M};
-      for (int sidx = 0; sidx < d.num_subsystems; sidx++) subsystem_linearize_sink<32>(d, d.sub[sidx], x, u, lin);
-    }
-    cnts[warp * 32 + lane] = sink.cnt < E ? sink.cnt : E;
+    const float mu = live ? s.mu[b] : 0.f;
+    const bool full = warp < N && (d.cost_structure[warp] == ILQG_COST_SUM ||
+                                   (live && s.te_quad[(size_t)b * N + warp] == k));
+    walk_role<32>(
+        d, warp,
+        [&](const DevCost& cd) {
+          const bool is_con = cd.slot >= 0;
+          const int dim = cd.arg < 0 ? n : d.udim[cd.arg];
+          if (!full && (cd.arg < 0 || is_con)) {  // QuadraticizeControlCosts: record not visited
+            const int cnt = record_updates(cd, dim);
+            for (int e = 0; e < cnt; e++) sink.push(0.f);
+            return;
+          }
+          const float lambda =
+              (is_con && live) ? s.lambdas[((size_t)b * d.num_constraints + cd.slot) * T + s.lambda_index[k]] : 0.f;
+          const float* in = cd.arg < 0 ? x : u + d.uoff[cd.arg] * 32;
+          quadraticize_record_sink<true, 32, false>(d, cd, in, dim, lambda, mu, sink);
+        },
+        [&](const DevSubsystem& sub) {
+          LinValueSink lin{&sink};
+          subsystem_linearize_sink<32>(d, sub, x, u, lin);
+        });
   }
   __syncthreads();
 
-  // ---- phase 2: warp w assembles records w, w + NR, ... ----
+  // ---- phase 2: warp w assembles records w, w + NR, ... on top of its template copy ----
   float* rec = recs + (size_t)warp * d.rec;
   for (int r = warp; r < 32; r += NR) {
     const long long wr = first + r;
     if (wr >= total) break;
     const int br = (int)(wr / T);
     if (only_running && !instance_iterates(s, br)) continue;
-    // template: LinearDynamicsApproximation ctor A = I, B = 0 (linear_dynamics_approximation.h:65-70);
-    // QuadraticCostApproximation(xdim, state_reg) / SingleCostApproximation(udim, control_reg)
-    for (int e = lane; e < d.rec / 4; e += 32) reinterpret_cast<float4*>(rec)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncwarp();
-    for (int a = lane; a < n; a += 32) {
-      rec[d.offA + a * n + a] = 1.f;
-      for (int i = 0; i < N; i++) rec[d.offQ + (i * n + a) * n + a] = d.state_reg[i];
-    }
-    if (lane < d.num_pairs) {
-      const int mj = d.udim[d.pair_j[lane]];
-      for (int a = 0; a < mj; a++) rec[d.offR + d.pair_Roff[lane] + a * mj + a] = d.control_reg[d.pair_i[lane]];
-    }
-    __syncwarp();
-    if (lane < NR) {
-      const int cnt = cnts[lane * 32 + r];
-      const unsigned short* o = offs + (size_t)lane * E * 32 + r;
-      const float* v = vals + (size_t)lane * E * 32 + r;
-      for (int e = 0; e < cnt; e++) rec[o[e * 32]] += v[e * 32];
+    for (int g = lane; g < pat.num_items; g += 32) {
+      const GatherItem it = items[g];
+      const float* v = vals + (size_t)it.role * E * 32 + r;
+      float acc = rec[it.off];
+      for (int t = 0; t < it.count; t++) acc += v[gidx[it.start + t] * 32];
+      rec[it.off] = acc;
     }
     __syncwarp();
     float4* dst = reinterpret_cast<float4*>(s.rec + (size_t)wr * d.rec);
     const float4* src = reinterpret_cast<const float4*>(rec);
     for (int e = lane; e < d.rec / 4; e += 32) dst[e] = src[e];
+    __syncwarp();
+    for (int g = lane; g < pat.num_items; g += 32) rec[items[g].off] = __ldg(pat.tmpl + items[g].off);
     __syncwarp();
   }
 }

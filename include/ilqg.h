@@ -285,15 +285,10 @@ int ilqg_lq_backward(ilqg_handle h);
  * gradients); ilqg_linearize_quadraticize / ilqg_iterate rebuild them. */
 int ilqg_linesearch(ilqg_handle h);
 
-/* max_iters device-side PASSES over the batch, no host synchronisation.  In one pass every
- * RUNNING instance that is not in the middle of a linesearch executes one body of the while
- * loop src/ilq_solver.cpp:123-166 (linearize_quadraticize, lq_backward, then the first
- * candidates of its linesearch); an instance whose Armijo test rejected every candidate
- * evaluated so far continues the SAME linesearch in the next pass instead of stalling the batch
- * (per-instance Armijo state machine).  Per instance the sequence of computations and the result
- * are exactly the reference's; only the schedule differs.  Most instances complete one iLQ
- * iteration per pass; call again (ilqg_count_running tells when) until none is RUNNING.
- * iters_done (nullable; forces a sync) receives the largest per-instance iteration count. */
+/* Up to max_iters passes of the while loop src/ilq_solver.cpp:123-166 for every RUNNING
+ * instance (linearize_quadraticize, lq_backward, linesearch), entirely device-side with no host
+ * synchronisation.  iters_done (nullable; forces a sync) receives the largest per-instance
+ * iteration count. */
 int ilqg_iterate(ilqg_handle h, int max_iters, int* iters_done);
 
 /* Number of instances still ILQG_STATUS_RUNNING (synchronises). */
