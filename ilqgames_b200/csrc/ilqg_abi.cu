@@ -13,7 +13,9 @@
 
 using namespace ilqg;
 
-struct ilqg_solver {
+// One group of instances: its own slab, scratch and stream.  The public handle (ilqg_solver, at the
+// end of this file) owns several groups and runs them on concurrent streams.
+struct SubSolver {
   DevDesc d;
   DevParams p;
   ilqg_problem_desc host_desc;
@@ -54,7 +56,7 @@ namespace {
   } while (0)
 
 template <typename T>
-int DevAlloc(ilqg_solver* h, T** out, size_t count, bool zero = true);
+int DevAlloc(SubSolver* h, T** out, size_t count, bool zero = true);
 
 inline bool IsConstraintKind(int kind) {
   return kind == ILQG_CONSTRAINT_PROXIMITY || kind == ILQG_CONSTRAINT_SINGLE_DIMENSION;
@@ -257,11 +259,11 @@ constexpr int kNumDims = sizeof(kDims) / sizeof(kDims[0]);
 
 
 struct ProfScope {  // brackets one launch with events when profiling is on
-  ilqg_solver* h;
+  SubSolver* h;
   cudaEvent_t a, b;
   int kind;
   bool on;
-  ProfScope(ilqg_solver* hh, int k) : h(hh), a(nullptr), b(nullptr), kind(k), on(hh->profiling) {
+  ProfScope(SubSolver* hh, int k) : h(hh), a(nullptr), b(nullptr), kind(k), on(hh->profiling) {
     if (on) {
       on = cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess;
       if (on) cudaEventRecord(a, h->stream);
@@ -282,7 +284,7 @@ int SetSmem(K kernel, size_t bytes) {
 }
 
 template <int NX, int MU, int NP>
-int LaunchBackward(ilqg_solver* h, int only_running) {
+int LaunchBackward(SubSolver* h, int only_running) {
   const size_t smem = sizeof(float) * KBWD_WARPS * (size_t)(BwdSmem<NX, MU, NP>::rec + h->d.rec);
   int rc = SetSmem(k_lq_backward<NX, MU, NP>, smem);
   if (rc != ILQG_OK) return rc;
@@ -295,7 +297,7 @@ int LaunchBackward(ilqg_solver* h, int only_running) {
 }
 
 template <int NX, int MU, int NP>
-int LaunchBackwardHw(ilqg_solver* h, int only_running) {
+int LaunchBackwardHw(SubSolver* h, int only_running) {
   const size_t per_inst = HwSmem<NX, MU, NP>::lrr + (h->d.rec - h->d.offl);
   const size_t smem = sizeof(float) * KHW_WARPS * 2 * per_inst;
   int rc = SetSmem(k_lq_backward_hw<NX, MU, NP>, smem);
@@ -311,7 +313,7 @@ int LaunchBackwardHw(ilqg_solver* h, int only_running) {
 
 // with_dxs: also produce ILQG_DELTA_XS (an optional output of LQFeedbackSolver::Solve that the
 // iLQ loop itself never reads once ExpectedDecrease is fused into the backward sweep)
-int DispatchBackward(ilqg_solver* h, int only_running, bool with_dxs) {
+int DispatchBackward(SubSolver* h, int only_running, bool with_dxs) {
   int rc = ILQG_ERR_UNSUPPORTED;
   bool hw = true;
   switch (h->dims_key) {
@@ -355,7 +357,7 @@ int MaxRoleEntries(const DevDesc& d) {
 
 // Discover the static update pattern of the records on the device and build the gather table
 // (ilqg_records.cuh).  Leaves h->pat_ok = false when the shape does not fit (K_lq v1 is used).
-int BuildRecordPattern(ilqg_solver* h) {
+int BuildRecordPattern(SubSolver* h) {
   const DevDesc& d = h->d;
   h->pat_ok = false;
   const int NR = d.N + 1;
@@ -384,10 +386,15 @@ int BuildRecordPattern(ilqg_solver* h) {
       if (std::find(seen.begin(), seen.end(), o) == seen.end()) seen.push_back(o);
     }
     for (int o : seen) {
-      GatherItem it{o, r, (int)idx.size(), 0};
+      GatherItem it;
+      std::memset(&it, 0, sizeof(it));
+      it.off = o;
+      it.role = r;
+      it.start = (int)idx.size();
       for (int e = 0; e < cnt[r]; e++)
         if (off[(size_t)r * E + e] == o) {
           idx.push_back((unsigned short)e);
+          if (it.count < 4) it.e[it.count] = (unsigned short)e;
           it.count++;
         }
       items.push_back(it);
@@ -403,6 +410,7 @@ int BuildRecordPattern(ilqg_solver* h) {
     const int mj = d.udim[d.pair_j[p]];
     for (int a = 0; a < mj; a++) tmpl[d.offR + d.pair_Roff[p] + a * mj + a] = d.control_reg[d.pair_i[p]];
   }
+  for (GatherItem& it : items) it.base = tmpl[it.off];
   const size_t smem = klq_smem_bytes(d.n, d.M, d.N, E, d.rec, (int)items.size(), (int)idx.size());
   if (smem > 110 * 1024) return ILQG_OK;
   GatherItem* d_items = nullptr;
@@ -425,7 +433,7 @@ int BuildRecordPattern(ilqg_solver* h) {
   return ILQG_OK;
 }
 
-int LaunchLqRecords(ilqg_solver* h, int only_running) {
+int LaunchLqRecords(SubSolver* h, int only_running) {
   const DevDesc& d = h->d;
   if (h->pat_ok) {
     const size_t smem3 = klq_smem_bytes(d.n, d.M, d.N, h->pat.E, d.rec, h->pat.num_items, h->pat.num_idx);
@@ -450,7 +458,7 @@ int LaunchLqRecords(ilqg_solver* h, int only_running) {
   return ILQG_OK;
 }
 
-int LaunchLsEval(ilqg_solver* h, int mode, int blocks, int q_offset) {
+int LaunchLsEval(SubSolver* h, int mode, int blocks, int q_offset) {
   const DevDesc& d = h->d;
   const size_t smem = sizeof(float) * (size_t)ls_smem_floats(d.n, d.M, d.N, d.num_subsystems);
   if (blocks <= 0) return ILQG_OK;
@@ -474,7 +482,7 @@ int LaunchLsEval(ilqg_solver* h, int mode, int blocks, int q_offset) {
 
 // ILQSolver::ModifyLQStrategies for the whole batch (ilqg_linesearch.cuh): the first window for
 // everyone, then the remaining candidates for the instances that rejected it, chunk by chunk.
-int LaunchLinesearch(ilqg_solver* h) {
+int LaunchLinesearch(SubSolver* h) {
   const int B = h->B;
   int rc;
   ProfScope prof(h, 2);
@@ -499,7 +507,7 @@ int LaunchLinesearch(ilqg_solver* h) {
   return ILQG_OK;
 }
 
-int LaunchSolveBegin(ilqg_solver* h) {
+int LaunchSolveBegin(SubSolver* h) {
   int rc;
   ProfScope prof(h, 3);
   CUDA_TRY(cudaMemsetAsync(h->ls.counts, 0, 2 * sizeof(int), h->stream));
@@ -514,7 +522,7 @@ int LaunchSolveBegin(ilqg_solver* h) {
 }
 
 template <typename T>
-int DevAlloc(ilqg_solver* h, T** out, size_t count, bool zero) {
+int DevAlloc(SubSolver* h, T** out, size_t count, bool zero) {
   void* p = nullptr;
   const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
   cudaError_t e = cudaMalloc(&p, bytes);
@@ -528,7 +536,7 @@ int DevAlloc(ilqg_solver* h, T** out, size_t count, bool zero) {
   return ILQG_OK;
 }
 
-int Fill(ilqg_solver* h, float* p, float v, size_t count) {
+int Fill(SubSolver* h, float* p, float v, size_t count) {
   const int blocks = (int)std::min<size_t>((count + 255) / 256, 1024);
   k_fill<<<blocks, 256, 0, h->stream>>>(p, v, count);
   h->launches++;
@@ -536,7 +544,7 @@ int Fill(ilqg_solver* h, float* p, float v, size_t count) {
   return ILQG_OK;
 }
 
-int EnsureStaging(ilqg_solver* h, size_t floats) {
+int EnsureStaging(SubSolver* h, size_t floats) {
   if (h->staging_floats >= floats) return ILQG_OK;
   if (h->staging) cudaFree(h->staging);
   h->staging = nullptr;
@@ -567,7 +575,7 @@ struct Guard {  // select the handle's device for the duration of a call
   if (!_guard.ok) return ILQG_ERR_CUDA
 
 // download one parity-selected per-instance array through the staging buffer
-int DownloadParity(ilqg_solver* h, float* const src[2], const int* sel, int flip, size_t per, void* dst,
+int DownloadParity(SubSolver* h, float* const src[2], const int* sel, int flip, size_t per, void* dst,
                    size_t bytes) {
   const size_t total = per * (size_t)h->B;
   if (bytes != total * sizeof(float)) return ILQG_ERR_SIZE_MISMATCH;
@@ -582,7 +590,7 @@ int DownloadParity(ilqg_solver* h, float* const src[2], const int* sel, int flip
   return ILQG_OK;
 }
 
-int DownloadFlat(ilqg_solver* h, const void* src, size_t elem_bytes, size_t per, void* dst, size_t bytes) {
+int DownloadFlat(SubSolver* h, const void* src, size_t elem_bytes, size_t per, void* dst, size_t bytes) {
   if (bytes != per * (size_t)h->B * elem_bytes) return ILQG_ERR_SIZE_MISMATCH;
   CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -590,7 +598,7 @@ int DownloadFlat(ilqg_solver* h, const void* src, size_t elem_bytes, size_t per,
 }
 
 // one field of the LQ records, de-interleaved by the copy engine
-int DownloadRecordField(ilqg_solver* h, int off, int floats, void* dst, size_t bytes) {
+int DownloadRecordField(SubSolver* h, int off, int floats, void* dst, size_t bytes) {
   const size_t rows = (size_t)h->B * h->d.T;
   if (bytes != rows * floats * sizeof(float)) return ILQG_ERR_SIZE_MISMATCH;
   if (floats == 0) return ILQG_OK;
@@ -601,7 +609,7 @@ int DownloadRecordField(ilqg_solver* h, int off, int floats, void* dst, size_t b
   return ILQG_OK;
 }
 
-int UploadRecordField(ilqg_solver* h, int off, int floats, const float* src) {
+int UploadRecordField(SubSolver* h, int off, int floats, const float* src) {
   const size_t rows = (size_t)h->B * h->d.T;
   if (floats == 0) return ILQG_OK;
   CUDA_TRY(cudaMemcpy2DAsync(h->s.rec + off, (size_t)h->d.rec * sizeof(float), src,
@@ -612,38 +620,20 @@ int UploadRecordField(ilqg_solver* h, int off, int floats, const float* src) {
 
 }  // namespace
 
-extern "C" {
+typedef SubSolver* SubHandle;
 
-size_t ilqg_abi_struct_size(int which) {
-  switch (which) {
-    case 0: return sizeof(ilqg_problem_desc);
-    case 1: return sizeof(ilqg_solver_params);
-    case 2: return sizeof(ilqg_layout);
-    case 3: return sizeof(ilqg_cost_desc);
-    case 4: return sizeof(ilqg_subsystem_desc);
-  }
-  return 0;
-}
+namespace sub {
 
-const char* ilqg_strerror(int code) {
-  switch (code) {
-    case ILQG_OK: return "ok";
-    case ILQG_ERR_INVALID_ARGUMENT: return "invalid argument";
-    case ILQG_ERR_UNSUPPORTED: return "unsupported descriptor (no kernel compiled for these dimensions/kinds)";
-    case ILQG_ERR_CUDA: return "CUDA error";
-    case ILQG_ERR_NO_DEVICE: return "no CUDA device";
-    case ILQG_ERR_OUT_OF_MEMORY: return "out of memory";
-    case ILQG_ERR_BAD_HANDLE: return "bad handle";
-    case ILQG_ERR_SIZE_MISMATCH: return "host buffer size mismatch";
-  }
-  return "unknown error";
-}
+int ilqg_destroy(SubHandle h);
+
+
+
 
 int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params, int batch, int device,
-                ilqg_handle* out) {
+                SubHandle* out) {
   if (!desc || !params || !out || batch < 1) return ILQG_ERR_INVALID_ARGUMENT;
   if (params->open_loop) return ILQG_ERR_UNSUPPORTED;
-  ilqg_solver* h = new (std::nothrow) ilqg_solver();
+  SubSolver* h = new (std::nothrow) SubSolver();
   if (!h) return ILQG_ERR_OUT_OF_MEMORY;
   std::vector<int> lidx;
   int rc = BuildDeviceDesc(*desc, &h->d, &h->layout, &lidx);  // descriptor errors first
@@ -791,7 +781,7 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
   return ILQG_OK;
 }
 
-int ilqg_destroy(ilqg_handle h) {
+int ilqg_destroy(SubHandle h) {
   if (!h) return ILQG_ERR_BAD_HANDLE;
   Guard guard(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
@@ -806,13 +796,13 @@ int ilqg_destroy(ilqg_handle h) {
   return ILQG_OK;
 }
 
-int ilqg_get_layout(ilqg_handle h, ilqg_layout* out) {
+int ilqg_get_layout(SubHandle h, ilqg_layout* out) {
   if (!h || !out) return ILQG_ERR_BAD_HANDLE;
   *out = h->layout;
   return ILQG_OK;
 }
 
-int ilqg_upload_x0(ilqg_handle h, const float* x0, size_t bytes) {
+int ilqg_upload_x0(SubHandle h, const float* x0, size_t bytes) {
   ENTER(h);
   if (!x0) return ILQG_ERR_INVALID_ARGUMENT;
   if (bytes != sizeof(float) * (size_t)h->B * h->d.n) return ILQG_ERR_SIZE_MISMATCH;
@@ -821,7 +811,7 @@ int ilqg_upload_x0(ilqg_handle h, const float* x0, size_t bytes) {
   return ILQG_OK;
 }
 
-int ilqg_upload_warmstart(ilqg_handle h, const float* xs, const float* us, const float* Ps,
+int ilqg_upload_warmstart(SubHandle h, const float* xs, const float* us, const float* Ps,
                           const float* alphas) {
   ENTER(h);
   const size_t B = h->B, T = h->d.T, n = h->d.n, M = h->d.M;
@@ -844,7 +834,7 @@ int ilqg_upload_warmstart(ilqg_handle h, const float* xs, const float* us, const
   return ILQG_OK;
 }
 
-int ilqg_upload(ilqg_handle h, int what, const void* src, size_t bytes) {
+int ilqg_upload(SubHandle h, int what, const void* src, size_t bytes) {
   ENTER(h);
   if (!src) return ILQG_ERR_INVALID_ARGUMENT;
   const size_t B = h->B, T = h->d.T, N = h->d.N;
@@ -870,7 +860,7 @@ int ilqg_upload(ilqg_handle h, int what, const void* src, size_t bytes) {
   return ILQG_OK;
 }
 
-int ilqg_upload_lq(ilqg_handle h, const float* A, const float* Bs, const float* Q, const float* l,
+int ilqg_upload_lq(SubHandle h, const float* A, const float* Bs, const float* Q, const float* l,
                    const float* R, const float* r) {
   ENTER(h);
   if (!A || !Bs || !Q || !l || !R || !r) return ILQG_ERR_INVALID_ARGUMENT;
@@ -886,27 +876,27 @@ int ilqg_upload_lq(ilqg_handle h, const float* A, const float* Bs, const float* 
   return ILQG_OK;
 }
 
-int ilqg_solve_begin(ilqg_handle h) {
+int ilqg_solve_begin(SubHandle h) {
   ENTER(h);
   return LaunchSolveBegin(h);
 }
 
-int ilqg_linearize_quadraticize(ilqg_handle h) {
+int ilqg_linearize_quadraticize(SubHandle h) {
   ENTER(h);
   return LaunchLqRecords(h, 0);
 }
 
-int ilqg_lq_backward(ilqg_handle h) {
+int ilqg_lq_backward(SubHandle h) {
   ENTER(h);
   return DispatchBackward(h, 0, true);
 }
 
-int ilqg_linesearch(ilqg_handle h) {
+int ilqg_linesearch(SubHandle h) {
   ENTER(h);
   return LaunchLinesearch(h);
 }
 
-int ilqg_iterate(ilqg_handle h, int max_iters, int* iters_done) {
+int ilqg_iterate(SubHandle h, int max_iters, int* iters_done) {
   ENTER(h);
   int rc;
   for (int it = 0; it < max_iters; it++) {
@@ -923,7 +913,7 @@ int ilqg_iterate(ilqg_handle h, int max_iters, int* iters_done) {
   return ILQG_OK;
 }
 
-int ilqg_count_running(ilqg_handle h, int* running) {
+int ilqg_count_running(SubHandle h, int* running) {
   ENTER(h);
   if (!running) return ILQG_ERR_INVALID_ARGUMENT;
   std::vector<int> st(h->B);
@@ -933,7 +923,7 @@ int ilqg_count_running(ilqg_handle h, int* running) {
   return ILQG_OK;
 }
 
-int ilqg_al_update(ilqg_handle h) {
+int ilqg_al_update(SubHandle h) {
   ENTER(h);
   k_al_update<<<h->B, ILQG_MAX_COSTS, 0, h->stream>>>(h->d, h->p, h->s);
   h->launches++;
@@ -941,7 +931,7 @@ int ilqg_al_update(ilqg_handle h) {
   return ILQG_OK;
 }
 
-int ilqg_overwrite_solution(ilqg_handle h, int only_successful) {
+int ilqg_overwrite_solution(SubHandle h, int only_successful) {
   ENTER(h);
   k_overwrite_solution<<<h->B, 256, 0, h->stream>>>(h->d, h->s, only_successful);
   h->launches++;
@@ -949,7 +939,7 @@ int ilqg_overwrite_solution(ilqg_handle h, int only_successful) {
   return ILQG_OK;
 }
 
-int ilqg_al_post_solve(ilqg_handle h) {
+int ilqg_al_post_solve(SubHandle h) {
   ENTER(h);
   k_al_post_solve<<<h->B, 128, 0, h->stream>>>(h->d, h->p, h->s);
   h->launches++;
@@ -957,7 +947,7 @@ int ilqg_al_post_solve(ilqg_handle h) {
   return ILQG_OK;
 }
 
-int ilqg_download(ilqg_handle h, int what, void* dst, size_t bytes) {
+int ilqg_download(SubHandle h, int what, void* dst, size_t bytes) {
   ENTER(h);
   if (!dst) return ILQG_ERR_INVALID_ARGUMENT;
   const DevDesc& d = h->d;
@@ -993,13 +983,13 @@ int ilqg_download(ilqg_handle h, int what, void* dst, size_t bytes) {
   return ILQG_ERR_INVALID_ARGUMENT;
 }
 
-int ilqg_synchronize(ilqg_handle h) {
+int ilqg_synchronize(SubHandle h) {
   ENTER(h);
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return ILQG_OK;
 }
 
-int ilqg_reset(ilqg_handle h, int mask) {
+int ilqg_reset(SubHandle h, int mask) {
   ENTER(h);
   int rc;
   const size_t B = h->B, T = h->d.T, n = h->d.n, M = h->d.M;
@@ -1024,14 +1014,14 @@ int ilqg_reset(ilqg_handle h, int mask) {
   return ILQG_OK;
 }
 
-int ilqg_set_stream(ilqg_handle h, void* cuda_stream) {
+int ilqg_set_stream(SubHandle h, void* cuda_stream) {
   ENTER(h);
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
   return ILQG_OK;
 }
 
-static int DrainSamples(ilqg_solver* h) {
+static int DrainSamples(SubSolver* h) {
   for (auto& sm : h->samples) {
     CUDA_TRY(cudaEventSynchronize(sm.b));
     float ms = 0.f;
@@ -1045,7 +1035,7 @@ static int DrainSamples(ilqg_solver* h) {
   return ILQG_OK;
 }
 
-int ilqg_profile(ilqg_handle h, int enable) {
+int ilqg_profile(SubHandle h, int enable) {
   ENTER(h);
   int rc = DrainSamples(h);
   if (rc != ILQG_OK) return rc;
@@ -1055,7 +1045,7 @@ int ilqg_profile(ilqg_handle h, int enable) {
   return ILQG_OK;
 }
 
-int ilqg_profile_read(ilqg_handle h, int kernel, double* total_ms, long long* launches) {
+int ilqg_profile_read(SubHandle h, int kernel, double* total_ms, long long* launches) {
   ENTER(h);
   if (kernel < 0 || kernel > 3 || !total_ms || !launches) return ILQG_ERR_INVALID_ARGUMENT;
   int rc = DrainSamples(h);
@@ -1065,9 +1055,324 @@ int ilqg_profile_read(ilqg_handle h, int kernel, double* total_ms, long long* la
   return ILQG_OK;
 }
 
-int ilqg_kernel_launches(ilqg_handle h, long long* out) {
+int ilqg_kernel_launches(SubHandle h, long long* out) {
   if (!h || !out) return ILQG_ERR_BAD_HANDLE;
   *out = h->launches;
+  return ILQG_OK;
+}
+
+}  // namespace sub
+
+
+// ===========================================================================
+// Public handle: G groups of instances on concurrent streams.
+//
+// Every kernel of the hot path is latency-bound at the benchmark batch (a sequential sweep over
+// T = 100 timesteps with a few thousand instances leaves most issue slots empty), so the batch is
+// split into groups whose kernel sequences run on separate CUDA streams: while one group's
+// backward sweep waits on shared-memory latency another group's rollout or record assembly
+// issues.  Instances are independent, so the split changes no result.  ILQG_GROUPS overrides the
+// group count (1 = a single stream, used for per-kernel profiling).
+// ===========================================================================
+struct ilqg_solver {
+  std::vector<SubSolver*> subs;
+  std::vector<int> first;  // first instance of each group
+  std::vector<cudaEvent_t> done;
+  cudaEvent_t fork;
+  cudaStream_t stream, own_stream;
+  ilqg_layout layout;
+  int B, device;
+};
+
+namespace {
+
+int Fork(ilqg_solver* h) {
+  if (h->subs.size() == 1 && h->subs[0]->stream == h->stream) return ILQG_OK;
+  CUDA_TRY(cudaEventRecord(h->fork, h->stream));
+  for (SubSolver* g : h->subs) CUDA_TRY(cudaStreamWaitEvent(g->stream, h->fork, 0));
+  return ILQG_OK;
+}
+
+int Join(ilqg_solver* h) {
+  if (h->subs.size() == 1 && h->subs[0]->stream == h->stream) return ILQG_OK;
+  for (size_t k = 0; k < h->subs.size(); k++) {
+    CUDA_TRY(cudaEventRecord(h->done[k], h->subs[k]->stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->done[k], 0));
+  }
+  return ILQG_OK;
+}
+
+template <typename F>
+int ForEach(ilqg_solver* h, F&& f) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  Guard guard(h->device);
+  if (!guard.ok) return ILQG_ERR_CUDA;
+  int rc = Fork(h);
+  if (rc != ILQG_OK) return rc;
+  for (size_t k = 0; k < h->subs.size(); k++)
+    if ((rc = f(h->subs[k], h->first[k])) != ILQG_OK) return rc;
+  return Join(h);
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t ilqg_abi_struct_size(int which) {
+  switch (which) {
+    case 0: return sizeof(ilqg_problem_desc);
+    case 1: return sizeof(ilqg_solver_params);
+    case 2: return sizeof(ilqg_layout);
+    case 3: return sizeof(ilqg_cost_desc);
+    case 4: return sizeof(ilqg_subsystem_desc);
+  }
+  return 0;
+}
+
+const char* ilqg_strerror(int code) {
+  switch (code) {
+    case ILQG_OK: return "ok";
+    case ILQG_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case ILQG_ERR_UNSUPPORTED: return "unsupported descriptor (no kernel compiled for these dimensions/kinds)";
+    case ILQG_ERR_CUDA: return "CUDA error";
+    case ILQG_ERR_NO_DEVICE: return "no CUDA device";
+    case ILQG_ERR_OUT_OF_MEMORY: return "out of memory";
+    case ILQG_ERR_BAD_HANDLE: return "bad handle";
+    case ILQG_ERR_SIZE_MISMATCH: return "host buffer size mismatch";
+  }
+  return "unknown error";
+}
+
+int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params, int batch, int device,
+                ilqg_handle* out) {
+  if (!desc || !params || !out || batch < 1) return ILQG_ERR_INVALID_ARGUMENT;
+  int groups = batch >= 2048 ? 4 : batch >= 512 ? 2 : 1;
+  if (const char* e = std::getenv("ILQG_GROUPS")) groups = std::max(1, std::atoi(e));
+  groups = std::min(groups, batch);
+  ilqg_solver* h = new (std::nothrow) ilqg_solver();
+  if (!h) return ILQG_ERR_OUT_OF_MEMORY;
+  h->B = batch;
+  h->device = device;
+  h->stream = nullptr;
+  h->own_stream = nullptr;
+  h->fork = nullptr;
+  int rc = ILQG_OK;
+  for (int g = 0; g < groups && rc == ILQG_OK; g++) {
+    const int lo = (int)((long long)batch * g / groups), hi = (int)((long long)batch * (g + 1) / groups);
+    SubSolver* sh = nullptr;
+    rc = sub::ilqg_create(desc, params, hi - lo, device, &sh);
+    if (rc == ILQG_OK) {
+      h->subs.push_back(sh);
+      h->first.push_back(lo);
+    }
+  }
+  if (rc == ILQG_OK) {
+    Guard guard(device);
+    if (!guard.ok || cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming) != cudaSuccess)
+      rc = ILQG_ERR_CUDA;
+    h->stream = h->own_stream;
+    for (size_t k = 0; k < h->subs.size() && rc == ILQG_OK; k++) {
+      cudaEvent_t ev;
+      if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) rc = ILQG_ERR_CUDA;
+      else h->done.push_back(ev);
+    }
+  }
+  if (rc != ILQG_OK) {
+    ilqg_destroy(h);
+    return rc;
+  }
+  h->layout = h->subs[0]->layout;
+  h->layout.batch = batch;
+  *out = h;
+  return ILQG_OK;
+}
+
+int ilqg_destroy(ilqg_handle h) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  Guard guard(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (SubSolver* g : h->subs) sub::ilqg_destroy(g);
+  for (cudaEvent_t ev : h->done) cudaEventDestroy(ev);
+  if (h->fork) cudaEventDestroy(h->fork);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return ILQG_OK;
+}
+
+int ilqg_get_layout(ilqg_handle h, ilqg_layout* out) {
+  if (!h || !out) return ILQG_ERR_BAD_HANDLE;
+  *out = h->layout;
+  return ILQG_OK;
+}
+
+// per-instance element counts of every uploadable / downloadable array (floats or ints)
+static size_t PerInstance(const ilqg_solver* h, int what) {
+  const ilqg_layout& lo = h->layout;
+  const size_t T = lo.num_time_steps, n = lo.xdim, M = lo.total_udim, N = lo.num_players;
+  switch (what) {
+    case ILQG_XS: case ILQG_DELTA_XS: return T * n;
+    case ILQG_US: case ILQG_ALPHAS: case ILQG_LQ_ALPHAS: return T * M;
+    case ILQG_PS: case ILQG_LQ_PS: return T * M * n;
+    case ILQG_LIN_A: return T * n * n;
+    case ILQG_LIN_B: return T * n * M;
+    case ILQG_QUAD_Q: return T * N * n * n;
+    case ILQG_QUAD_L: return T * N * n;
+    case ILQG_QUAD_R: return T * (size_t)lo.R_floats;
+    case ILQG_QUAD_RGRAD: return T * (size_t)lo.r_floats;
+    case ILQG_LAMBDAS: return (size_t)lo.num_constraints * T;
+    case ILQG_TOTAL_COSTS: case ILQG_TIME_OF_EXTREME: return N;
+    case ILQG_X0: return n;
+    case ILQG_MU: case ILQG_MERIT: case ILQG_EXPECTED_DECREASE: case ILQG_STEP: case ILQG_MAX_CONSTRAINT_ERROR:
+    case ILQG_STATUS: case ILQG_ITERS: case ILQG_BACKTRACKS: return 1;
+  }
+  return 0;
+}
+
+int ilqg_upload_x0(ilqg_handle h, const float* x0, size_t bytes) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  if (!x0) return ILQG_ERR_INVALID_ARGUMENT;
+  const size_t n = h->layout.xdim;
+  if (bytes != sizeof(float) * (size_t)h->B * n) return ILQG_ERR_SIZE_MISMATCH;
+  return ForEach(h, [&](SubSolver* g, int lo) { return sub::ilqg_upload_x0(g, x0 + (size_t)lo * n, sizeof(float) * (size_t)g->B * n); });
+}
+
+int ilqg_upload_warmstart(ilqg_handle h, const float* xs, const float* us, const float* Ps, const float* alphas) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  const size_t px = PerInstance(h, ILQG_XS), pu = PerInstance(h, ILQG_US), pp = PerInstance(h, ILQG_PS);
+  return ForEach(h, [&](SubSolver* g, int lo) {
+    return sub::ilqg_upload_warmstart(g, xs ? xs + lo * px : nullptr, us ? us + lo * pu : nullptr,
+                                      Ps ? Ps + lo * pp : nullptr, alphas ? alphas + lo * pu : nullptr);
+  });
+}
+
+int ilqg_upload(ilqg_handle h, int what, const void* src, size_t bytes) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  if (!src) return ILQG_ERR_INVALID_ARGUMENT;
+  const size_t per = PerInstance(h, what) * 4;
+  if (per == 0 && what != ILQG_LAMBDAS) return ILQG_ERR_INVALID_ARGUMENT;
+  if (bytes != per * (size_t)h->B) return ILQG_ERR_SIZE_MISMATCH;
+  return ForEach(h, [&](SubSolver* g, int lo) {
+    return sub::ilqg_upload(g, what, (const char*)src + (size_t)lo * per, per * (size_t)g->B);
+  });
+}
+
+int ilqg_upload_lq(ilqg_handle h, const float* A, const float* Bs, const float* Q, const float* l, const float* R,
+                   const float* r) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  if (!A || !Bs || !Q || !l || !R || !r) return ILQG_ERR_INVALID_ARGUMENT;
+  return ForEach(h, [&](SubSolver* g, int lo) {
+    return sub::ilqg_upload_lq(g, A + lo * PerInstance(h, ILQG_LIN_A), Bs + lo * PerInstance(h, ILQG_LIN_B),
+                               Q + lo * PerInstance(h, ILQG_QUAD_Q), l + lo * PerInstance(h, ILQG_QUAD_L),
+                               R + lo * PerInstance(h, ILQG_QUAD_R), r + lo * PerInstance(h, ILQG_QUAD_RGRAD));
+  });
+}
+
+int ilqg_solve_begin(ilqg_handle h) { return ForEach(h, [](SubSolver* g, int) { return sub::ilqg_solve_begin(g); }); }
+int ilqg_linearize_quadraticize(ilqg_handle h) {
+  return ForEach(h, [](SubSolver* g, int) { return sub::ilqg_linearize_quadraticize(g); });
+}
+int ilqg_lq_backward(ilqg_handle h) { return ForEach(h, [](SubSolver* g, int) { return sub::ilqg_lq_backward(g); }); }
+int ilqg_linesearch(ilqg_handle h) { return ForEach(h, [](SubSolver* g, int) { return sub::ilqg_linesearch(g); }); }
+int ilqg_al_update(ilqg_handle h) { return ForEach(h, [](SubSolver* g, int) { return sub::ilqg_al_update(g); }); }
+int ilqg_al_post_solve(ilqg_handle h) { return ForEach(h, [](SubSolver* g, int) { return sub::ilqg_al_post_solve(g); }); }
+int ilqg_overwrite_solution(ilqg_handle h, int only_successful) {
+  return ForEach(h, [&](SubSolver* g, int) { return sub::ilqg_overwrite_solution(g, only_successful); });
+}
+int ilqg_reset(ilqg_handle h, int mask) { return ForEach(h, [&](SubSolver* g, int) { return sub::ilqg_reset(g, mask); }); }
+
+int ilqg_iterate(ilqg_handle h, int max_iters, int* iters_done) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  Guard guard(h->device);
+  if (!guard.ok) return ILQG_ERR_CUDA;
+  int rc = Fork(h);
+  if (rc != ILQG_OK) return rc;
+  // iteration-major, group-minor issue order so the groups' kernels interleave in the hardware queues
+  for (int it = 0; it < max_iters; it++)
+    for (SubSolver* g : h->subs)
+      if ((rc = sub::ilqg_iterate(g, 1, nullptr)) != ILQG_OK) return rc;
+  if ((rc = Join(h)) != ILQG_OK) return rc;
+  if (iters_done) {
+    int most = 0;
+    for (SubSolver* g : h->subs) {
+      int v = 0;
+      if ((rc = sub::ilqg_iterate(g, 0, &v)) != ILQG_OK) return rc;
+      most = std::max(most, v);
+    }
+    *iters_done = most;
+  }
+  return ILQG_OK;
+}
+
+int ilqg_count_running(ilqg_handle h, int* running) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  if (!running) return ILQG_ERR_INVALID_ARGUMENT;
+  int total = 0;
+  for (SubSolver* g : h->subs) {
+    int v = 0;
+    const int rc = sub::ilqg_count_running(g, &v);
+    if (rc != ILQG_OK) return rc;
+    total += v;
+  }
+  *running = total;
+  return ILQG_OK;
+}
+
+int ilqg_download(ilqg_handle h, int what, void* dst, size_t bytes) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  if (!dst) return ILQG_ERR_INVALID_ARGUMENT;
+  const size_t per = PerInstance(h, what) * 4;
+  if (per == 0 && what != ILQG_LAMBDAS && what != ILQG_QUAD_R && what != ILQG_QUAD_RGRAD) return ILQG_ERR_INVALID_ARGUMENT;
+  if (bytes != per * (size_t)h->B) return ILQG_ERR_SIZE_MISMATCH;
+  return ForEach(h, [&](SubSolver* g, int lo) {
+    return sub::ilqg_download(g, what, (char*)dst + (size_t)lo * per, per * (size_t)g->B);
+  });
+}
+
+int ilqg_synchronize(ilqg_handle h) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  Guard guard(h->device);
+  for (SubSolver* g : h->subs) CUDA_TRY(cudaStreamSynchronize(g->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return ILQG_OK;
+}
+
+int ilqg_set_stream(ilqg_handle h, void* cuda_stream) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  Guard guard(h->device);
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return ILQG_OK;
+}
+
+int ilqg_profile(ilqg_handle h, int enable) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  for (SubSolver* g : h->subs) {
+    const int rc = sub::ilqg_profile(g, enable);
+    if (rc != ILQG_OK) return rc;
+  }
+  return ILQG_OK;
+}
+
+int ilqg_profile_read(ilqg_handle h, int kernel, double* total_ms, long long* launches) {
+  if (!h || !total_ms || !launches) return ILQG_ERR_BAD_HANDLE;
+  *total_ms = 0;
+  *launches = 0;
+  for (SubSolver* g : h->subs) {
+    double ms = 0;
+    long long n = 0;
+    const int rc = sub::ilqg_profile_read(g, kernel, &ms, &n);
+    if (rc != ILQG_OK) return rc;
+    *total_ms += ms;
+    *launches += n;
+  }
+  return ILQG_OK;
+}
+
+int ilqg_kernel_launches(ilqg_handle h, long long* out) {
+  if (!h || !out) return ILQG_ERR_BAD_HANDLE;
+  *out = 0;
+  for (SubSolver* g : h->subs) *out += g->launches;
   return ILQG_OK;
 }
 

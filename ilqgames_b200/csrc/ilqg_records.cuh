@@ -20,10 +20,13 @@
 namespace ilqg {
 
 struct GatherItem {
-  int off;    // offset in the record
-  int role;   // which role's value list
-  int start;  // first index into gather_idx
-  int count;  // entries to add, in order
+  int off;     // offset in the record
+  int role;    // which role's value list
+  int start;   // first index into gather_idx (used when count > 4)
+  int count;   // entries to add, in order
+  float base;  // template value at `off` (0, 1 on A's diagonal, the regularisers on Q / R diagonals)
+  unsigned short e[4];  // the first four entry indices inline
+  int pad;
 };
 
 struct RecordPattern {
@@ -205,27 +208,36 @@ k_linearize_quadraticize_v3(const __grid_constant__ DevDesc d, Slab s, RecordPat
         });
   }
   __syncthreads();
+  // xu is dead: reuse its first 32 words as the per-record "assemble me" flags
+  int* flags = reinterpret_cast<int*>(xu);
+  if (warp == 0) flags[lane] = live ? 1 : 0;
+  __syncthreads();
 
   // ---- phase 2: warp w assembles records w, w + NR, ... on top of its template copy ----
   float* rec = recs + (size_t)warp * d.rec;
   for (int r = warp; r < 32; r += NR) {
     const long long wr = first + r;
     if (wr >= total) break;
-    const int br = (int)(wr / T);
-    if (only_running && !instance_iterates(s, br)) continue;
+    if (!flags[r]) continue;
+    // every touched word is rewritten from its template value for each record, so the staging
+    // copy never needs restoring (the touched set is the same for all records)
     for (int g = lane; g < pat.num_items; g += 32) {
       const GatherItem it = items[g];
       const float* v = vals + (size_t)it.role * E * 32 + r;
-      float acc = rec[it.off];
-      for (int t = 0; t < it.count; t++) acc += v[gidx[it.start + t] * 32];
+      float acc = it.base;
+      if (it.count <= 4) {
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+          if (t < it.count) acc += v[it.e[t] * 32];
+      } else {
+        for (int t = 0; t < it.count; t++) acc += v[gidx[it.start + t] * 32];
+      }
       rec[it.off] = acc;
     }
     __syncwarp();
     float4* dst = reinterpret_cast<float4*>(s.rec + (size_t)wr * d.rec);
     const float4* src = reinterpret_cast<const float4*>(rec);
     for (int e = lane; e < d.rec / 4; e += 32) dst[e] = src[e];
-    __syncwarp();
-    for (int g = lane; g < pat.num_items; g += 32) rec[items[g].off] = __ldg(pat.tmpl + items[g].off);
     __syncwarp();
   }
 }
