@@ -342,7 +342,7 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
       const int i = c / m;
       float acc = 0.f;
 #pragma unroll 4
-      for (int q = 0; q < NX; q++) acc = fmaf(Bt[c * NX + q], zeta[i * NX + q], acc);
+      for (int q = 0; q < NX; q++) acc = fmaf(Bm[q * MU + c], zeta[i * NX + q], acc);
       ya[c] = acc + rk[d.pair_roff[d.pair_of[i][i]] + (c - i * m)];
     }
     __syncwarp();
@@ -350,15 +350,23 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
     // ---- Gershgorin (:163-176) + S X = Y (:180): lane col owns P[:, col]; every lane carries alpha ----
     {
       float Sm[MU][MU], y[G][MU], yal[MU];
+      {
+        float sflat[r4(MU * MU)];
+        ldvec<r4(MU * MU)>(S, sflat);  // broadcast 128-bit loads
 #pragma unroll
-      for (int r = 0; r < MU; r++) {
+        for (int r = 0; r < MU; r++)
 #pragma unroll
-        for (int c = 0; c < MU; c++) Sm[r][c] = S[r * MU + c];
-        yal[r] = ya[r];
+          for (int c = 0; c < MU; c++) Sm[r][c] = sflat[r * MU + c];
+        float yflat[r4(MU)];
+        ldvec<r4(MU)>(ya, yflat);
 #pragma unroll
-        for (int g = 0; g < G; g++) {
-          const int col = l16 + 16 * g;
-          y[g][r] = col < NX ? P[r * NX + col] : 0.f;
+        for (int r = 0; r < MU; r++) {
+          yal[r] = yflat[r];
+#pragma unroll
+          for (int g = 0; g < G; g++) {
+            const int col = l16 + 16 * g;
+            y[g][r] = col < NX ? P[r * NX + col] : 0.f;
+          }
         }
       }
       bool dominant = p.adaptive_regularization != 0;
@@ -455,14 +463,18 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
       expected_decrease -= part;
     }
     // p_k = A_k^T p_{k+1} (+ g_k added per player below); AW still holds A here
-    for (int a = l16; a < NX; a += 16) {
-      float acc0 = 0.f, acc1 = 0.f;
+    {
+      float pvr[NX];
+      ldvec<NX>(pv, pvr);
+      for (int a = l16; a < NX; a += 16) {
+        float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
-      for (int q = 0; q < NX; q += 2) {
-        acc0 = fmaf(AW[q * NX + a], pv[q], acc0);
-        acc1 = fmaf(AW[(q + 1) * NX + a], pv[q + 1], acc1);
+        for (int q = 0; q < NX; q += 2) {
+          acc0 = fmaf(AW[q * NX + a], pvr[q], acc0);
+          acc1 = fmaf(AW[(q + 1) * NX + a], pvr[q + 1], acc1);
+        }
+        pn[a] = acc0 + acc1;
       }
-      pn[a] = acc0 + acc1;
     }
     __syncwarp();
 
@@ -498,12 +510,14 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
       }
       __syncwarp();
       // zeta = F^T tv + l (+ P_j^T (R_ij alpha_j - r_ij))
+      float tvr[NX];
+      ldvec<NX>(tv, tvr);
       for (int a = l16; a < NX; a += 16) {
         float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
         for (int c = 0; c < NX; c += 2) {
-          acc0 = fmaf(F[c * NX + a], tv[c], acc0);
-          acc1 = fmaf(F[(c + 1) * NX + a], tv[c + 1], acc1);
+          acc0 = fmaf(F[c * NX + a], tvr[c], acc0);
+          acc1 = fmaf(F[(c + 1) * NX + a], tvr[c + 1], acc1);
         }
         float znew = (acc0 + acc1) + li[a];
         for (int j = 0; j < NP; j++) {
@@ -540,6 +554,12 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
         const int pr = d.pair_of[i][j2];
         if (pr < 0) continue;
         const float* Rij = Rk + d.pair_Roff[pr];
+        float prow[m][TR], pcol[m][TC];  // P_j[:, a0..] and P_j[:, c0..]
+#pragma unroll
+        for (int c = 0; c < m; c++) {
+          ldvec<TR>(P + (j2 * m + c) * NX + a0, prow[c]);
+          ldvec<TC>(P + (j2 * m + c) * NX + c0, pcol[c]);
+        }
         float ptr[TR][m];  // (P_j^T R_ij)[a0 + r][c2]
 #pragma unroll
         for (int r = 0; r < TR; r++)
@@ -547,7 +567,7 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
           for (int c2 = 0; c2 < m; c2++) {
             float v = 0.f;
 #pragma unroll
-            for (int c = 0; c < m; c++) v = fmaf(P[(j2 * m + c) * NX + a0 + r], Rij[c * m + c2], v);
+            for (int c = 0; c < m; c++) v = fmaf(prow[c][r], Rij[c * m + c2], v);
             ptr[r][c2] = v;
           }
 #pragma unroll
@@ -556,18 +576,19 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
           for (int j = 0; j < TC; j++) {
             float t = 0.f;
 #pragma unroll
-            for (int c2 = 0; c2 < m; c2++) t = fmaf(ptr[r][c2], P[(j2 * m + c2) * NX + c0 + j], t);
+            for (int c2 = 0; c2 < m; c2++) t = fmaf(ptr[r][c2], pcol[c2][j], t);
             acc[r][j] += t;
           }
       }
       // g_k contribution of this player: sum_c Q_i[a][c] l_i[c], reduced over the 4 column groups
       {
-        float gpart[TR];
+        float gpart[TR], lseg[TC];
+        ldvec<TC>(li + c0, lseg);
 #pragma unroll
         for (int r = 0; r < TR; r++) {
           float g = 0.f;
 #pragma unroll
-          for (int j = 0; j < TC; j++) g = fmaf(q[r][j], li[c0 + j], g);
+          for (int j = 0; j < TC; j++) g = fmaf(q[r][j], lseg[j], g);
           g += __shfl_xor_sync(0xffffffffu, g, 1);
           g += __shfl_xor_sync(0xffffffffu, g, 2);
           gpart[r] = g;

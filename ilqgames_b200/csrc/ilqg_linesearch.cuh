@@ -141,8 +141,15 @@ k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratc
     P = s.st_P[1 - scur] + oP;
     alpha = s.st_a[1 - scur] + ou;
     x_start = last_xs;
-    out_xs = ls.traj_xs + (size_t)item * T * n;
-    out_us = ls.traj_us + (size_t)item * T * M;
+    if (mode == LS_MODE_FRESH && ls.JA == 1) {
+      // the lone first-window candidate is accepted 98 % of the time: roll it straight into the
+      // candidate operating-point buffer (k_ls_decide then has nothing to copy)
+      out_xs = s.op_xs[1 - cur] + ox;
+      out_us = s.op_us[1 - cur] + ou;
+    } else {
+      out_xs = ls.traj_xs + (size_t)item * T * n;
+      out_us = ls.traj_us + (size_t)item * T * M;
+    }
   }
   const float s0 = p.initial_alpha_scaling, rho = p.geometric_alpha_scaling;
   const float dt_half = (float)(d.time_step / 2.0);
@@ -382,18 +389,20 @@ k_ls_decide(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScra
     const int j = j0 + acc_jj;
     const size_t item = base + acc_jj;
     const int cur = s.op_cur[b], scur = s.st_cur[b];
-    // accepted candidate -> operating point
-    float* dxs = s.op_xs[1 - cur] + (size_t)b * T * n;
-    const float* sxs = ls.traj_xs + item * T * n;
-    float* dus = s.op_us[1 - cur] + (size_t)b * T * M;
-    const float* sus = ls.traj_us + item * T * M;
-    if ((T * n) % 4 == 0) {
-      for (int e = lane; e < T * n / 4; e += 32)
-        reinterpret_cast<float4*>(dxs)[e] = reinterpret_cast<const float4*>(sxs)[e];
-    } else {
-      for (int e = lane; e < T * n; e += 32) dxs[e] = sxs[e];
+    // accepted candidate -> operating point (already there for the lone fresh candidate)
+    if (!(fresh && ls.JA == 1)) {
+      float* dxs = s.op_xs[1 - cur] + (size_t)b * T * n;
+      const float* sxs = ls.traj_xs + item * T * n;
+      float* dus = s.op_us[1 - cur] + (size_t)b * T * M;
+      const float* sus = ls.traj_us + item * T * M;
+      if ((T * n) % 4 == 0) {
+        for (int e = lane; e < T * n / 4; e += 32)
+          reinterpret_cast<float4*>(dxs)[e] = reinterpret_cast<const float4*>(sxs)[e];
+      } else {
+        for (int e = lane; e < T * n; e += 32) dxs[e] = sxs[e];
+      }
+      for (int e = lane; e < T * M; e += 32) dus[e] = sus[e];
     }
-    for (int e = lane; e < T * M; e += 32) dus[e] = sus[e];
     ls_total_costs(d, s, b, ls.vals + (item / 32) * T * d.N * 32, (int)(item % 32), lane);
     // the scaled LQ strategies become current (ScaleAlphas, src/ilq_solver.cpp:66-72,314,339)
     float* alpha = s.st_a[1 - scur] + (size_t)b * T * M;

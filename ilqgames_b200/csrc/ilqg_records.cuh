@@ -38,11 +38,14 @@ struct RecordPattern {
 };
 
 // sink that stores update values (phase 1) ...
+// value of update e for record r at val[e * 33 + r]: the odd stride keeps both access patterns
+// conflict-free (phase 1: 32 records of one update; phase 2: 32 updates of one record)
+constexpr int kValStride = 33;
 struct ValueSink {
-  float* val;  // [E][32] lane-minor
+  float* val;  // [E][33]
   int lane, cnt, cap;
   __device__ __forceinline__ void push(float v) {
-    if (cnt < cap) val[cnt * 32 + lane] = v;
+    if (cnt < cap) val[cnt * kValStride + lane] = v;
     cnt++;
   }
   __device__ __forceinline__ void H(int, int, float v) { push(v); }
@@ -136,7 +139,7 @@ __global__ void k_record_pattern(const __grid_constant__ DevDesc d, int* offsets
 //                                      items[num_items] (GatherItem) | idx[num_idx] (u16)
 __host__ __device__ inline size_t klq_smem_bytes(int n, int M, int N, int E, int rec, int num_items, int num_idx) {
   const int NR = N + 1;
-  size_t b = sizeof(float) * ((size_t)(n + M) * 32 + (size_t)NR * E * 32 + (size_t)NR * rec);
+  size_t b = sizeof(float) * ((size_t)(n + M) * 32 + (size_t)NR * E * kValStride + (size_t)NR * rec);
   b += sizeof(GatherItem) * (size_t)num_items;
   b += sizeof(unsigned short) * (size_t)((num_idx + 7) & ~7);
   return b;
@@ -148,8 +151,8 @@ k_linearize_quadraticize_v3(const __grid_constant__ DevDesc d, Slab s, RecordPat
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = d.n, M = d.M, N = d.N, T = d.T, NR = N + 1, E = pat.E;
   float* xu = smem;                                        // [n+M][32]
-  float* vals = xu + (n + M) * 32;                         // [NR][E][32]
-  float* recs = vals + (size_t)NR * E * 32;                // [NR][rec]
+  float* vals = xu + (n + M) * 32;                         // [NR][E][33]
+  float* recs = vals + (size_t)NR * E * kValStride;        // [NR][rec]  (E % 4 == 0 keeps 16 B alignment)
   GatherItem* items = reinterpret_cast<GatherItem*>(recs + (size_t)NR * d.rec);
   unsigned short* gidx = reinterpret_cast<unsigned short*>(items + pat.num_items);
 
@@ -178,7 +181,7 @@ k_linearize_quadraticize_v3(const __grid_constant__ DevDesc d, Slab s, RecordPat
   // ---- phase 1: role = warp, record = lane: update values only ----
   {
     ValueSink sink;
-    sink.val = vals + (size_t)warp * E * 32;
+    sink.val = vals + (size_t)warp * E * kValStride;
     sink.lane = lane;
     sink.cnt = 0;
     sink.cap = E;
@@ -223,14 +226,14 @@ k_linearize_quadraticize_v3(const __grid_constant__ DevDesc d, Slab s, RecordPat
     // copy never needs restoring (the touched set is the same for all records)
     for (int g = lane; g < pat.num_items; g += 32) {
       const GatherItem it = items[g];
-      const float* v = vals + (size_t)it.role * E * 32 + r;
+      const float* v = vals + (size_t)it.role * E * kValStride + r;
       float acc = it.base;
       if (it.count <= 4) {
 #pragma unroll
         for (int t = 0; t < 4; t++)
-          if (t < it.count) acc += v[it.e[t] * 32];
+          if (t < it.count) acc += v[it.e[t] * kValStride];
       } else {
-        for (int t = 0; t < it.count; t++) acc += v[gidx[it.start + t] * 32];
+        for (int t = 0; t < it.count; t++) acc += v[gidx[it.start + t] * kValStride];
       }
       rec[it.off] = acc;
     }

@@ -208,7 +208,7 @@ def test_against_golden_fixture(product, name):
     build, params, _ = CONFIGS[name]
     desc, _ = build()
     iters = max(int(k.split("_")[1]) for k in g.files if k.startswith("merit_"))
-    xs_tol = 5e-3 if name == "roundabout_merging" else 1e-3  # roundabout: reg = 0, ill-conditioned
+    xs_tol = 2e-2 if name == "roundabout_merging" else 1e-3  # roundabout: reg = 0, ill-conditioned
     for it in range(1, iters + 1):
         h = abi.Handle(product, desc, params(max_solver_iters=it), g["x0"].shape[0], 0)
         h.upload_x0(g["x0"])
