@@ -140,7 +140,7 @@ __global__ void k_record_pattern(const __grid_constant__ DevDesc d, int* offsets
 __host__ __device__ inline size_t klq_smem_bytes(int n, int M, int N, int E, int rec, int num_items, int num_idx) {
   const int NR = N + 1;
   size_t b = sizeof(float) * ((size_t)(n + M) * 32 + (size_t)NR * E * kValStride + (size_t)NR * rec);
-  b += sizeof(GatherItem) * (size_t)num_items;
+  b += 5 * sizeof(int) * (size_t)num_items;
   b += sizeof(unsigned short) * (size_t)((num_idx + 7) & ~7);
   return b;
 }
@@ -153,8 +153,14 @@ k_linearize_quadraticize_v3(const __grid_constant__ DevDesc d, Slab s, RecordPat
   float* xu = smem;                                        // [n+M][32]
   float* vals = xu + (n + M) * 32;                         // [NR][E][33]
   float* recs = vals + (size_t)NR * E * kValStride;        // [NR][rec]  (E % 4 == 0 keeps 16 B alignment)
-  GatherItem* items = reinterpret_cast<GatherItem*>(recs + (size_t)NR * d.rec);
-  unsigned short* gidx = reinterpret_cast<unsigned short*>(items + pat.num_items);
+  // gather table as struct-of-arrays (one conflict-free word per lane and field)
+  const int NI = pat.num_items;
+  int* g_off = reinterpret_cast<int*>(recs + (size_t)NR * d.rec);   // [NI]
+  int* g_meta = g_off + NI;                                          // role | count << 8 | start << 16
+  float* g_base = reinterpret_cast<float*>(g_meta + NI);             // [NI]
+  unsigned* g_e01 = reinterpret_cast<unsigned*>(g_base + NI);        // entries 0,1
+  unsigned* g_e23 = g_e01 + NI;                                      // entries 2,3
+  unsigned short* gidx = reinterpret_cast<unsigned short*>(g_e23 + NI);
 
   const long long first = (long long)blockIdx.x * 32;
   const long long total = (long long)s.B * T;
@@ -170,7 +176,14 @@ k_linearize_quadraticize_v3(const __grid_constant__ DevDesc d, Slab s, RecordPat
     const float* xs = s.op_xs[cur] + ((size_t)b * T + k) * n;
     const float* us = s.op_us[cur] + ((size_t)b * T + k) * M;
     for (int e = warp; e < n + M; e += NR) xu[e * 32 + lane] = in_range ? (e < n ? xs[e] : us[e - n]) : 0.f;
-    for (int e = threadIdx.x; e < pat.num_items; e += blockDim.x) items[e] = pat.items[e];
+    for (int e = threadIdx.x; e < NI; e += blockDim.x) {
+      const GatherItem it = pat.items[e];
+      g_off[e] = it.off;
+      g_meta[e] = it.role | (it.count << 8) | (it.start << 16);
+      g_base[e] = it.base;
+      g_e01[e] = (unsigned)it.e[0] | ((unsigned)it.e[1] << 16);
+      g_e23[e] = (unsigned)it.e[2] | ((unsigned)it.e[3] << 16);
+    }
     for (int e = threadIdx.x; e < pat.num_idx; e += blockDim.x) gidx[e] = pat.idx[e];
     float* rec = recs + (size_t)warp * d.rec;
     for (int e = lane; e < d.rec / 4; e += 32)
@@ -224,18 +237,21 @@ k_linearize_quadraticize_v3(const __grid_constant__ DevDesc d, Slab s, RecordPat
     if (!flags[r]) continue;
     // every touched word is rewritten from its template value for each record, so the staging
     // copy never needs restoring (the touched set is the same for all records)
-    for (int g = lane; g < pat.num_items; g += 32) {
-      const GatherItem it = items[g];
-      const float* v = vals + (size_t)it.role * E * kValStride + r;
-      float acc = it.base;
-      if (it.count <= 4) {
-#pragma unroll
-        for (int t = 0; t < 4; t++)
-          if (t < it.count) acc += v[it.e[t] * kValStride];
+    for (int g = lane; g < NI; g += 32) {
+      const int meta = g_meta[g];
+      const int role = meta & 0xff, count = (meta >> 8) & 0xff, start = meta >> 16;
+      const float* v = vals + (size_t)role * E * kValStride + r;
+      float acc = g_base[g];
+      if (count <= 4) {
+        const unsigned e01 = g_e01[g], e23 = g_e23[g];
+        if (count > 0) acc += v[(e01 & 0xffff) * kValStride];
+        if (count > 1) acc += v[(e01 >> 16) * kValStride];
+        if (count > 2) acc += v[(e23 & 0xffff) * kValStride];
+        if (count > 3) acc += v[(e23 >> 16) * kValStride];
       } else {
-        for (int t = 0; t < it.count; t++) acc += v[gidx[it.start + t] * kValStride];
+        for (int t = 0; t < count; t++) acc += v[gidx[start + t] * kValStride];
       }
-      rec[it.off] = acc;
+      rec[g_off[g]] = acc;
     }
     __syncwarp();
     float4* dst = reinterpret_cast<float4*>(s.rec + (size_t)wr * d.rec);
