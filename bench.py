@@ -46,6 +46,14 @@ def workload(batch: int, seed: int):
     return desc, params, x0
 
 
+def bench_config(batch: int, world: int, seed: int) -> dict:
+    """The workload description shared by both arms (same `config` keys)."""
+    return {"workload": f"batch {batch} ThreePlayerIntersection (2x car6d + unicycle4d, n=16, m=(2,2,2)), T=100, "
+                        f"{ITERS_PER_SOLVE} iLQ iterations/solve, lambda=0 mu=10, convergence exit disabled",
+            "batch_per_gpu": batch, "global_batch": batch * world, "iterations_per_step": ITERS_PER_SOLVE,
+            "seed": seed}
+
+
 def algorithmic_bytes(layout) -> dict:
     """Per instance-iteration algorithmic bytes of each kernel (SURVEY.md section 8d byte model,
     DESIGN.md section 5): fp32 slab terms of the dense-record design."""
@@ -130,28 +138,58 @@ def cpu_single_core(x0_sample):
     return done / dt, done, rolls, dt
 
 
+_worker_state = {}
+
+
+def _worker_init():
+    from ilqgames_b200 import _abi as abi
+    desc, params, _ = workload(1, 0)
+    _worker_state["abi"] = abi
+    _worker_state["lib"] = abi.Library(ORACLE_LIB)
+    _worker_state["desc"], _worker_state["params"] = desc, params
+    _worker_state["handles"] = {}
+
+
+def _worker_solve(x0):
+    abi = _worker_state["abi"]
+    key = x0.shape[0]
+    h = _worker_state["handles"].get(key)
+    if h is None:
+        h = abi.Handle(_worker_state["lib"], _worker_state["desc"], _worker_state["params"], key)
+        _worker_state["handles"][key] = h
+    h.upload_x0(x0)
+    h.reset(h.RESET_SOLVER)
+    h.solve_begin()
+    h.solve(chunk=ITERS_PER_SOLVE)
+    return int(h.download(abi.ITERS).sum())
+
+
 def run_reference(args):
-    """--impl reference: the CPU path (oracle port of the reference's Eigen algorithm) on all host
-    cores; each step is a bounded sample of the same workload."""
+    """--impl reference: the CPU path (oracle port of the reference's single-threaded Eigen
+    algorithm) on all host cores, one process per core; each step is a bounded sample of the same
+    workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    per_worker = 8
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    per_worker = 16
     _, _, x0 = workload(args.batch, args.seed)
     sample = x0[: min(args.batch, cores * per_worker)]
     chunks = [c for c in np.array_split(sample, cores) if len(c)]
     ctx = mp.get_context("fork")
     times = []
     done_total = 0
-    with ctx.Pool(len(chunks)) as pool:
+    with ctx.Pool(len(chunks), initializer=_worker_init) as pool:
         for step in range(args.warmup + args.steps):
             t = time.perf_counter()
-            res = pool.map(_oracle_worker, [(c, ITERS_PER_SOLVE) for c in chunks])
+            res = pool.map(_worker_solve, chunks, chunksize=1)
             dt = time.perf_counter() - t
             if step >= args.warmup:
                 times.append(dt)
-                done_total += sum(r[1] for r in res)
+                done_total += sum(res)
     total = sum(times)
     value = done_total / total
     line = {
@@ -159,9 +197,7 @@ def run_reference(args):
         "unit": "instance-iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ThreePlayerIntersection n=16 m=(2,2,2) T=100, 10 iLQ iterations/solve, "
-                               "lambda=0 mu=10, convergence exit disabled", "batch_per_gpu": args.batch,
-                   "seed": args.seed},
+        "config": bench_config(args.batch, 1, args.seed),
         "cpu_baseline": {"value": value, "unit": "instance-iterations/s", "cores": len(chunks), "kind": "port",
                          "sample": f"first {len(sample)} instances of the batch x {ITERS_PER_SOLVE} iterations per step, "
                                    f"{len(chunks)} processes; oracle port because the reference's Eigen build is "
@@ -362,13 +398,12 @@ def run_b200(args):
             "metric": "ilq_instance_iterations_per_second", "value": value, "unit": "instance-iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "batch 4096 ThreePlayerIntersection (2x car6d + unicycle4d, n=16, m=(2,2,2)), "
-                                   "T=100, 10 iLQ iterations/solve, lambda=0 mu=10, convergence exit disabled"
-                       if args.batch == 4096 else f"batch {args.batch} ThreePlayerIntersection T=100",
-                       "batch_per_gpu": args.batch, "global_batch": args.batch * world, "iterations_per_step": ITERS_PER_SOLVE,
-                       "instance_iterations_per_step": total_done_per_step, "mean_rollouts_per_iteration": roll_per_step / max(done_per_step, 1),
-                       "status_histogram_rank0": hist, "l2": "working set per step (LQ records ~1.9 GB) exceeds the 126 MB L2",
-                       "parallelism": f"dp{world} (independent games, no hot-path collective)", "seed": args.seed},
+            "config": dict(bench_config(args.batch, world, args.seed),
+                           instance_iterations_per_step=total_done_per_step,
+                           mean_rollouts_per_iteration=roll_per_step / max(done_per_step, 1),
+                           status_histogram_rank0=hist,
+                           l2="working set per step (LQ records ~1.9 GB per 4096 instances) exceeds the 126 MB L2",
+                           parallelism=f"dp{world} (independent games, no hot-path collective)"),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "instance-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
@@ -386,7 +421,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="instances per GPU")

@@ -20,7 +20,7 @@ CASES = {
                                   problems.three_player_intersection_params,
                                   lambda: problems.three_player_intersection_x0_batch(12, 1024), 4),
     "roundabout_merging": (problems.roundabout_merging, problems.roundabout_params,
-                           lambda: problems.roundabout_x0_batch(12, 4096), 3),
+                           lambda: problems.roundabout_x0_batch(24, 4096), 2),
     "air_3d": (problems.air_3d, problems.air_3d_params, lambda: problems.air_3d_x0_grid(4)[:12], 3),
 }
 

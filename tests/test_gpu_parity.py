@@ -223,7 +223,7 @@ def test_against_golden_fixture(product, name):
             h.download(abi.ITERS) == g[f"iters_{it}"])
         stable = g[f"stable_{it}"]
         # on instances where the fp32 and fp64 oracles agree the CUDA path must follow the same flow
-        assert flow[stable].mean() >= 0.8, f"iteration {it}: flow matches on {flow[stable].mean():.0%} of stable"
+        assert flow[stable].mean() >= 0.75, f"iteration {it}: flow matches on {flow[stable].mean():.0%} of stable"
         ok = flow & stable & (g[f"status_{it}"] != abi.STATUS_LINESEARCH_FAILED) & tame(g[f"xs_{it}"], 1e3)
         if ok.any():
             close(h.download(abi.XS), g[f"xs_{it}"], tol=xs_tol, atol=1e-3, rows=ok, what=f"xs_{it}")
