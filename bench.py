@@ -66,7 +66,7 @@ def algorithmic_bytes(layout) -> dict:
     dx = T * n
     return {
         "linearize_quadraticize": 4 * (op + AB + QR),
-        "lq_backward": 4 * ((AB + QR + Pa) + (AB + Ql + Pa + dx)),
+        "lq_backward": 4 * (AB + QR + Pa),  # records read once, strategy written once
         "linesearch_per_rollout": 4 * (2 * op + Pa),
     }
 
@@ -312,12 +312,20 @@ def run_b200(args):
             kern[name] = {"ms_per_launch": ms / n, "launches_per_step": n / prof_steps, "ms_per_step": ms / prof_steps}
     passes = max(kern.get("lq_backward", {}).get("launches_per_step", ITERS_PER_SOLVE), 1)
     inst_iters_per_launch = done_per_step / passes
+    # k_ls_eval runs once per linesearch window: the first window for every instance, then the
+    # queued window chunk by chunk (chunks past the end of the queue exit at once) - one entry
+    ev = [kern[k] for k in ("ls_eval_fresh", "ls_eval_queued") if k in kern]
+    if ev:
+        n_l = sum(e["launches_per_step"] for e in ev)
+        ms = sum(e["ms_per_step"] for e in ev)
+        kern["ls_eval"] = {"ms_per_launch": ms / n_l, "launches_per_step": n_l, "ms_per_step": ms}
     per_kernel_bytes = {
         "linearize_quadraticize": bytes_model["linearize_quadraticize"] * inst_iters_per_launch,
         "lq_backward": bytes_model["lq_backward"] * inst_iters_per_launch,
-        "linesearch": bytes_model["linesearch_per_rollout"] * roll_per_step / passes,
     }
-    hot = [k for k in ("linearize_quadraticize", "lq_backward", "linesearch") if k in kern]
+    if "ls_eval" in kern:
+        per_kernel_bytes["ls_eval"] = bytes_model["linesearch_per_rollout"] * roll_per_step / kern["ls_eval"]["launches_per_step"]
+    hot = [k for k in ("linearize_quadraticize", "lq_backward", "ls_eval") if k in kern]
     dominant = max(hot, key=lambda k: kern[k]["ms_per_step"])
     peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):

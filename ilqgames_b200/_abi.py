@@ -350,7 +350,8 @@ class Handle:
     def profile(self, enable: bool):
         self.lib.check(self.lib.lib.ilqg_profile(self._h, int(enable)), "profile")
 
-    KERNEL_NAMES = ("linearize_quadraticize", "lq_backward", "linesearch", "solve_begin")
+    KERNEL_NAMES = ("linearize_quadraticize", "lq_backward", "linesearch", "solve_begin",
+                    "ls_eval_fresh", "ls_eval_queued", "ls_decide", "ls_eval_begin")
 
     def profile_read(self):
         """{kernel name: (total_ms, launches)} since profile(True)."""

@@ -35,8 +35,8 @@ struct SubSolver {
   bool profiling;
   struct Sample { cudaEvent_t a, b; int kind; };
   std::vector<Sample> samples;
-  double prof_ms[4];
-  long long prof_n[4];
+  double prof_ms[8];
+  long long prof_n[8];
   float* staging;
   size_t staging_floats;
   long long launches;
@@ -470,6 +470,7 @@ int LaunchLsEval(SubSolver* h, int mode, int blocks, int q_offset) {
     if ((rc = SetSmem(k_ls_eval<NW>, smem)) != ILQG_OK) return rc;                                \
     k_ls_eval<NW><<<blocks, NW * 32, smem, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset); \
     break;
+  ProfScope prof(h, mode == LS_MODE_FRESH ? 4 : mode == LS_MODE_QUEUED ? 5 : 7);
   switch (nw) {
     LS_CASE(2) LS_CASE(3) LS_CASE(4) LS_CASE(5) LS_CASE(6) LS_CASE(7) LS_CASE(8)
     default: return ILQG_ERR_UNSUPPORTED;
@@ -490,16 +491,22 @@ int LaunchLinesearch(SubSolver* h) {
   // fresh window: unresolved instances are appended to queue 1 - ls_cur
   CUDA_TRY(cudaMemsetAsync(h->ls.counts + (1 - h->ls_cur), 0, sizeof(int), h->stream));
   if ((rc = LaunchLsEval(h, LS_MODE_FRESH, h->ls.nA_blocks, 0)) != ILQG_OK) return rc;
-  k_ls_decide<<<dec_blocks, KDEC_WARPS * 32, 0, h->stream>>>(h->d, h->p, h->s, h->ls, LS_MODE_FRESH, h->ls_cur, 0);
+  {
+    ProfScope pd(h, 6);
+    k_ls_decide<<<dec_blocks, KDEC_WARPS * 32, 0, h->stream>>>(h->d, h->p, h->s, h->ls, LS_MODE_FRESH, h->ls_cur, 0);
+  }
   h->launches++;
   h->ls_cur = 1 - h->ls_cur;  // the queue just filled is now the one to drain
   if (h->p.linesearch && h->ls.JB > 0) {
     const int cap = h->ls.cap;
-    const int qblocks = (int)(((long long)cap * h->ls.JB + 31) / 32);
+    const int qblocks = (int)(((long long)cap * h->ls.JB + h->ls.lpw - 1) / h->ls.lpw);
     for (int q0 = 0; q0 < B; q0 += cap) {
       if ((rc = LaunchLsEval(h, LS_MODE_QUEUED, qblocks, q0)) != ILQG_OK) return rc;
-      k_ls_decide<<<(cap + KDEC_WARPS - 1) / KDEC_WARPS, KDEC_WARPS * 32, 0, h->stream>>>(
-          h->d, h->p, h->s, h->ls, LS_MODE_QUEUED, h->ls_cur, q0);
+      {
+        ProfScope pd(h, 6);
+        k_ls_decide<<<(cap + KDEC_WARPS - 1) / KDEC_WARPS, KDEC_WARPS * 32, 0, h->stream>>>(
+            h->d, h->p, h->s, h->ls, LS_MODE_QUEUED, h->ls_cur, q0);
+      }
       h->launches++;
     }
   }
@@ -512,7 +519,7 @@ int LaunchSolveBegin(SubSolver* h) {
   ProfScope prof(h, 3);
   CUDA_TRY(cudaMemsetAsync(h->ls.counts, 0, 2 * sizeof(int), h->stream));
   h->ls_cur = 0;
-  rc = LaunchLsEval(h, LS_MODE_BEGIN, (h->B + 31) / 32, 0);
+  rc = LaunchLsEval(h, LS_MODE_BEGIN, (h->B + h->ls.lpw - 1) / h->ls.lpw, 0);
   if (rc == ILQG_OK) {
     k_begin_finalize<<<(h->B + KDEC_WARPS - 1) / KDEC_WARPS, KDEC_WARPS * 32, 0, h->stream>>>(h->d, h->p, h->s, h->ls);
     h->launches++;
@@ -667,7 +674,7 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
   h->profiling = false;
   h->stream = nullptr;
   h->own_stream = nullptr;
-  for (int k = 0; k < 4; k++) { h->prof_ms[k] = 0; h->prof_n[k] = 0; }
+  for (int k = 0; k < 8; k++) { h->prof_ms[k] = 0; h->prof_n[k] = 0; }
   DevParams& p = h->p;
   p.convergence_tolerance = params->convergence_tolerance;
   p.max_solver_iters = params->max_solver_iters;
@@ -747,17 +754,22 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
     ls.JA = JA;
     ls.JB = JB;
     ls.cap = cap;
-    ls.nA_blocks = (int)((B * JA + 31) / 32);
-    const size_t blocks_max = std::max<size_t>(ls.nA_blocks, ((size_t)cap * JB + 31) / 32);
+    int lpw = 32;
+    if (const char* e = std::getenv("ILQG_LS_LPW")) lpw = std::atoi(e);
+    if (lpw != 8 && lpw != 16 && lpw != 32 && lpw != 4) lpw = 32;
+    ls.lpw = lpw;
+    ls.nA_blocks = (int)((B * JA + lpw - 1) / lpw);
+    const size_t blocks_max = std::max<size_t>(std::max<size_t>(ls.nA_blocks, (B + lpw - 1) / lpw),
+                                               ((size_t)cap * JB + lpw - 1) / lpw);
     h->ls_blocks_max = (int)blocks_max;
     h->ls_cur = 0;
 #define ALLOCNZ(ptr, count)                                               \
   if ((rc = DevAlloc(h, &(ptr), (count), false)) != ILQG_OK) return fail(rc)
-    ALLOCNZ(ls.traj_xs, blocks_max * 32 * T * n);
-    ALLOCNZ(ls.traj_us, blocks_max * 32 * T * M);
+    ALLOCNZ(ls.traj_xs, blocks_max * lpw * T * n);
+    ALLOCNZ(ls.traj_us, blocks_max * lpw * T * M);
     ALLOCNZ(ls.terms, blocks_max * T * 2 * N * 32);
     ALLOCNZ(ls.vals, blocks_max * T * N * 32);
-    ALLOCNZ(ls.merit, blocks_max * 32);
+    ALLOCNZ(ls.merit, blocks_max * lpw);
 #undef ALLOCNZ
     ALLOC(ls.pend[0], B);
     ALLOC(ls.pend[1], B);
@@ -1040,14 +1052,14 @@ int ilqg_profile(SubHandle h, int enable) {
   int rc = DrainSamples(h);
   if (rc != ILQG_OK) return rc;
   if (enable)
-    for (int k = 0; k < 4; k++) { h->prof_ms[k] = 0; h->prof_n[k] = 0; }
+    for (int k = 0; k < 8; k++) { h->prof_ms[k] = 0; h->prof_n[k] = 0; }
   h->profiling = enable != 0;
   return ILQG_OK;
 }
 
 int ilqg_profile_read(SubHandle h, int kernel, double* total_ms, long long* launches) {
   ENTER(h);
-  if (kernel < 0 || kernel > 3 || !total_ms || !launches) return ILQG_ERR_INVALID_ARGUMENT;
+  if (kernel < 0 || kernel > 7 || !total_ms || !launches) return ILQG_ERR_INVALID_ARGUMENT;
   int rc = DrainSamples(h);
   if (rc != ILQG_OK) return rc;
   *total_ms = h->prof_ms[kernel];

@@ -40,6 +40,8 @@ struct LsScratch {
   int* slot;        // [B] position of an instance in the queue it is in
   int JA, JB;       // window sizes: fresh linesearch / continued linesearch
   int nA_blocks;    // blocks of a k_ls_eval launch that serve fresh instances
+  int lpw;          // items per block (active lanes per warp): 32, 16 or 8.  The rollout is a
+                    // latency chain, so fewer items per warp = more warps per SM to hide it
   int cap;          // queue slots one continued-window launch can hold trajectories for
 };
 
@@ -57,17 +59,18 @@ __device__ __forceinline__ LsItem ls_decode(const DevParams& p, const Slab& s, c
   it.b = 0;
   it.j = 0;
   it.valid = false;
+  if (lane >= ls.lpw) return it;
   if (mode == LS_MODE_BEGIN) {
-    it.b = block * 32 + lane;
+    it.b = block * ls.lpw + lane;
     it.valid = it.b < s.B;
   } else if (mode == LS_MODE_FRESH) {
-    const int item = block * 32 + lane;
+    const int item = block * ls.lpw + lane;
     it.b = item / ls.JA;
     it.j = item % ls.JA;
     it.valid = it.b < s.B && s.status[it.b] == ILQG_STATUS_RUNNING && s.ls_next_j[it.b] == 0 &&
                it.j < p.max_backtracking_steps;
   } else {
-    const int item = block * 32 + lane;
+    const int item = block * ls.lpw + lane;
     const int q = q_offset + item / ls.JB;
     if (item / ls.JB < ls.cap && q < ls.counts[cur]) {
       it.b = ls.pend[cur][q];
@@ -103,13 +106,13 @@ __host__ __device__ inline int ls_smem_floats(int n, int M, int N, int S) {
 
 // NW = S + N warps per block; the register cap targets >= 24 resident warps per SM
 template <int NW>
-__global__ void __launch_bounds__(NW * 32, (16 + NW - 1) / NW)
+__global__ void __launch_bounds__(NW * 32, 2)
 k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode, int cur_q,
           int q_offset) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = d.n, M = d.M, N = d.N, T = d.T, S = d.num_subsystems;
-  const int item = blockIdx.x * 32 + lane;
+  const int item = blockIdx.x * ls.lpw + lane;
   const LsItem it = ls_decode(p, s, ls, mode, cur_q, q_offset, blockIdx.x, lane);
   if (!__syncthreads_or(it.valid)) return;
   const bool valid = it.valid;
@@ -153,6 +156,12 @@ k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratc
   }
   const float s0 = p.initial_alpha_scaling, rho = p.geometric_alpha_scaling;
   const float dt_half = (float)(d.time_step / 2.0);
+  // ScaleAlphas multiplies alpha by rho once per backtrack (src/ilq_solver.cpp:66-72, 331).  When
+  // rho is a power of two every one of those products is exact, so rho^j can be formed once.
+  int rho_e;
+  const bool rho_exact = fabsf(frexpf(rho, &rho_e)) == 0.5f;
+  float rho_j = 1.0f;
+  for (int jj = 0; jj < it.j; jj++) rho_j *= rho;
   float* terms = ls.terms + (size_t)blockIdx.x * T * 2 * N * 32;
   float* vals = ls.vals + (size_t)blockIdx.x * T * N * 32;
 
@@ -178,7 +187,9 @@ k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratc
       for (int a = 0; a < 6; a++)
         if (a < xd)
           nref[a] = k > 0 ? last_xs[(size_t)k * n + sub.x_offset + a] : x_start[sub.x_offset + a];
-      for (int q = 0; q < nu; q++) {
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        if (q >= nu) break;
         const int c = q == 0 ? sub.u_offset : sub.u_offset2;
         nuref[q] = last_us[(size_t)k * M + c];
         nal[q] = alpha[(size_t)k * M + c];
@@ -216,7 +227,9 @@ k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratc
           }
         named_barrier_sync(1, S * 32);
         float uu[2] = {0.f, 0.f};
-        for (int q = 0; q < nu; q++) {
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          if (q >= nu) break;
           const int c = q == 0 ? sub.u_offset : sub.u_offset2;
           float uv = 0.f;
           if (valid) {
@@ -238,7 +251,11 @@ k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratc
             float alv = al[q];
             if (scaled) {
               alv *= s0;  // ScaleAlphas(initial_alpha_scaling), then geometric_alpha_scaling^j
-              for (int jj = 0; jj < it.j; jj++) alv *= rho;
+              if (rho_exact) {
+                alv *= rho_j;
+              } else {
+                for (int jj = 0; jj < it.j; jj++) alv *= rho;
+              }
             }
             uv = uref[q] - acc - alv;  // Strategy::operator(), strategy.h:73-76
             if (out_us) out_us[(size_t)k * M + c] = uv;
@@ -403,7 +420,7 @@ k_ls_decide(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScra
       }
       for (int e = lane; e < T * M; e += 32) dus[e] = sus[e];
     }
-    ls_total_costs(d, s, b, ls.vals + (item / 32) * T * d.N * 32, (int)(item % 32), lane);
+    ls_total_costs(d, s, b, ls.vals + (item / ls.lpw) * T * d.N * 32, (int)(item % ls.lpw), lane);
     // the scaled LQ strategies become current (ScaleAlphas, src/ilq_solver.cpp:66-72,314,339)
     float* alpha = s.st_a[1 - scur] + (size_t)b * T * M;
     const float s0 = p.initial_alpha_scaling, rho = p.geometric_alpha_scaling;
@@ -466,7 +483,7 @@ k_begin_finalize(const __grid_constant__ DevDesc d, const DevParams p, Slab s, L
       (s.st_P[0] + (size_t)b * T * M * n)[e] = (s.prob_P + (size_t)b * T * M * n)[e];
   }
   for (int e = lane; e < T * M; e += 32) (s.st_a[0] + (size_t)b * T * M)[e] = (s.prob_a + (size_t)b * T * M)[e];
-  ls_total_costs(d, s, b, ls.vals + (size_t)(b / 32) * T * N * 32, b % 32, lane);
+  ls_total_costs(d, s, b, ls.vals + (size_t)(b / ls.lpw) * T * N * 32, b % ls.lpw, lane);
   __syncwarp();
   if (lane < N) s.te_quad[(size_t)b * N + lane] = s.te_new[(size_t)b * N + lane];
   if (lane == 0) {

@@ -328,8 +328,10 @@ int ilqg_set_stream(ilqg_handle h, void* cuda_stream);
 /* Per-kernel device timing for the roofline report: when enabled, every hot-path launch is
  * bracketed by CUDA events on the launch stream.  ilqg_profile_read synchronizes and returns
  * the accumulated milliseconds and launch count of one kernel kind
- * (0 = linearize_quadraticize, 1 = lq_backward, 2 = linesearch, 3 = solve_begin) since the
- * last ilqg_profile(h, 1). */
+ * (0 = linearize_quadraticize, 1 = lq_backward, 2 = linesearch [all of its launches],
+ * 3 = solve_begin [all of its launches]; the launches inside 2 and 3 one by one:
+ * 4 = k_ls_eval first window, 5 = k_ls_eval queued window, 6 = k_ls_decide,
+ * 7 = k_ls_eval of solve_begin) since the last ilqg_profile(h, 1). */
 int ilqg_profile(ilqg_handle h, int enable);
 int ilqg_profile_read(ilqg_handle h, int kernel, double* total_ms, long long* launches);
 
