@@ -500,14 +500,21 @@ int LaunchLinesearch(SubSolver* h) {
   if (h->p.linesearch && h->ls.JB > 0) {
     const int cap = h->ls.cap;
     const int qblocks = (int)(((long long)cap * h->ls.JB + h->ls.lpw - 1) / h->ls.lpw);
-    for (int q0 = 0; q0 < B; q0 += cap) {
-      if ((rc = LaunchLsEval(h, LS_MODE_QUEUED, qblocks, q0)) != ILQG_OK) return rc;
-      {
-        ProfScope pd(h, 6);
-        k_ls_decide<<<(cap + KDEC_WARPS - 1) / KDEC_WARPS, KDEC_WARPS * 32, 0, h->stream>>>(
-            h->d, h->p, h->s, h->ls, LS_MODE_QUEUED, h->ls_cur, q0);
+    const int remaining = std::max(1, h->p.max_backtracking_steps) - h->ls.JA;
+    // window after window over the queue; instances whose window ended without an accept AND
+    // whose last rollout was not "absorbed" (ilqg_linesearch.cuh) move on to the other queue
+    for (int done = 0; done < remaining; done += h->ls.JB) {
+      CUDA_TRY(cudaMemsetAsync(h->ls.counts + (1 - h->ls_cur), 0, sizeof(int), h->stream));
+      for (int q0 = 0; q0 < B; q0 += cap) {
+        if ((rc = LaunchLsEval(h, LS_MODE_QUEUED, qblocks, q0)) != ILQG_OK) return rc;
+        {
+          ProfScope pd(h, 6);
+          k_ls_decide<<<(cap + KDEC_WARPS - 1) / KDEC_WARPS, KDEC_WARPS * 32, 0, h->stream>>>(
+              h->d, h->p, h->s, h->ls, LS_MODE_QUEUED, h->ls_cur, q0);
+        }
+        h->launches++;
       }
-      h->launches++;
+      h->ls_cur = 1 - h->ls_cur;
     }
   }
   CUDA_TRY(cudaGetLastError());
@@ -748,8 +755,12 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
     if (const char* e = std::getenv("ILQG_LS_JA")) JA = std::max(1, std::atoi(e));  // tuning knobs
     if (!params->linesearch) JA = 1;
     JA = std::min(JA, max_bt);
-    const int JB = max_bt - JA;  // the second window covers every remaining candidate
-    int cap = (int)std::max<size_t>(1, (B + 7) / 8);
+    // continued linesearches go on in windows of JB candidates; by default one window covers every
+    // remaining candidate (measured best: a second window costs a full rollout latency, and the
+    // "absorbed" shortcut of k_ls_decide rarely triggers before j ~ 40)
+    int JB = max_bt - JA;
+    if (const char* e = std::getenv("ILQG_LS_JB")) JB = std::max(0, std::min(max_bt - JA, std::atoi(e)));
+    int cap = (int)std::max<size_t>(1, (B + 1) / 2);
     if (const char* e = std::getenv("ILQG_LS_CAP")) cap = std::max(1, std::min<int>((int)B, std::atoi(e)));
     ls.JA = JA;
     ls.JB = JB;
@@ -770,6 +781,7 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
     ALLOCNZ(ls.terms, blocks_max * T * 2 * N * 32);
     ALLOCNZ(ls.vals, blocks_max * T * N * 32);
     ALLOCNZ(ls.merit, blocks_max * lpw);
+    ALLOCNZ(ls.absorbed, blocks_max * lpw);
 #undef ALLOCNZ
     ALLOC(ls.pend[0], B);
     ALLOC(ls.pend[1], B);

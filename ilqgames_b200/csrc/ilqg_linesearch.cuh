@@ -35,6 +35,7 @@ struct LsScratch {
   float* terms;     // [blocks][T][2N][32]  merit terms, item = lane of its block
   float* vals;      // [blocks][T][N][32]   per-player cost values
   float* merit;     // [items]
+  int* absorbed;    // [items] 1 = every alpha term of this candidate vanished in rounding (see k_ls_eval)
   int* pend[2];     // double-buffered queue of instances with an open linesearch
   int* counts;      // [2] queue lengths
   int* slot;        // [B] position of an instance in the queue it is in
@@ -181,6 +182,7 @@ k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratc
     const int PST = 2 * n + 4;
     float* pbuf = pbase + (size_t)warp * 2 * 32 * PST;
     float nref[6], nuref[2] = {0.f, 0.f}, nal[2] = {0.f, 0.f};
+    bool absorbed = true;
     auto prefetch = [&](int k) {
       if (!valid) return;
 #pragma unroll
@@ -257,7 +259,9 @@ k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratc
                 for (int jj = 0; jj < it.j; jj++) alv *= rho;
               }
             }
-            uv = uref[q] - acc - alv;  // Strategy::operator(), strategy.h:73-76
+            const float t = uref[q] - acc;
+            uv = t - alv;  // Strategy::operator(), strategy.h:73-76
+            absorbed = absorbed && (uv == t);
             if (out_us) out_us[(size_t)k * M + c] = uv;
           }
           slot[(n + c) * 32 + lane] = uv;
@@ -267,6 +271,7 @@ k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratc
       }
       __syncthreads();
     }
+    dxs[warp * 32 + lane] = absorbed ? 1.f : 0.f;  // dxs is free after the last step (S <= n)
   } else if (warp < S + N) {
     // =================== cost role: player `warp - S`, one step behind ===================
     const int i = warp - S;
@@ -327,6 +332,12 @@ k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratc
     const int cnt = T * 2 * N;
     for (int e = 0; e < cnt; e++) merit += terms[(size_t)e * 32 + lane];
     ls.merit[item] = 0.5 * merit;
+    // If u_k = (u_ref - P dx) - alpha_k s0 rho^j rounded to (u_ref - P dx) at every step, every
+    // deeper candidate (smaller alpha) reproduces this rollout bit for bit: k_ls_decide can run
+    // the rest of the Armijo loop on this merit without another rollout.
+    bool absorbed = true;
+    for (int w2 = 0; w2 < S; w2++) absorbed = absorbed && dxs[w2 * 32 + lane] != 0.f;
+    ls.absorbed[item] = absorbed ? 1 : 0;
   }
 }
 
@@ -388,22 +399,38 @@ k_ls_decide(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScra
   const int W = fresh ? ls.JA : ls.JB;
   const size_t base = fresh ? (size_t)b * ls.JA : (size_t)w * ls.JB;
   const float lm = s.last_merit[b], ed = s.expected_decrease[b];
-  int acc_jj = -1;
+  bool exhausted = false;
+  int acc_jj = -1, acc_j = -1;
   float acc_merit = 0.f;
   if (!p.linesearch) {
     acc_jj = 0;  // ModifyLQStrategies returns after the first rollout (:322)
+    acc_j = j0;
   } else {
-    for (int jj = 0; jj < W && j0 + jj < max_bt; jj++) {
+    int jj = 0;
+    for (; jj < W && j0 + jj < max_bt; jj++) {
       const float merit = ls.merit[base + jj];
       if (ls_armijo(p, lm, merit, ed, j0 + jj)) {
         acc_jj = jj;
+        acc_j = j0 + jj;
         acc_merit = merit;
         break;
       }
     }
+    if (acc_jj < 0 && jj > 0 && j0 + jj < max_bt && ls.absorbed[base + jj - 1]) {
+      // the deeper candidates repeat rollout jj-1 exactly: finish the backtracking loop on its merit
+      const float merit = ls.merit[base + jj - 1];
+      for (int j = j0 + jj; j < max_bt; j++)
+        if (ls_armijo(p, lm, merit, ed, j)) {
+          acc_jj = jj - 1;
+          acc_j = j;
+          acc_merit = merit;
+          break;
+        }
+      if (acc_jj < 0) exhausted = true;
+    }
   }
   if (acc_jj >= 0) {
-    const int j = j0 + acc_jj;
+    const int j = acc_j;
     const size_t item = base + acc_jj;
     const int cur = s.op_cur[b], scur = s.st_cur[b];
     // accepted candidate -> operating point (already there for the lone fresh candidate)
@@ -451,7 +478,7 @@ k_ls_decide(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScra
     }
   } else if (lane == 0) {
     const int jn = j0 + W;
-    if (jn >= max_bt) {
+    if (jn >= max_bt || exhausted) {
       // ModifyLQStrategies returns false (:345-347); the log's final iterate stays current
       s.iters[b] += 1;
       s.backtracks[b] += max_bt + 1;  // the reference's last rollout is never evaluated

@@ -1,6 +1,6 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest13.log 2>&1; tail -3 gpurun_out/pytest13.log
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench13.json 2>gpurun_out/bench13.err; python - <<PY
+for cfg in "99 512" "99 2048" "64 2048" "48 2048" "32 2048"; do set -- $cfg; ILQG_LS_JB=$1 ILQG_LS_CAP=$2 python bench.py --steps 10 --warmup 3 > gpurun_out/bench14.json 2>gpurun_out/bench14.err; python - <<PY
 import json
-d=json.load(open("gpurun_out/bench13.json"))
-print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["clocks"], {k:round(v["ms_per_launch"],3) for k,v in d["roofline"]["kernels"].items()})
+d=json.load(open("gpurun_out/bench14.json"))
+print("$cfg", round(d["value"]), round(d["ms_per_step"],2), {k:round(v["ms_per_launch"],3) for k,v in d["roofline"]["kernels"].items() if k.startswith("ls_") or k=="linesearch"}, d["roofline"]["kernels"]["ls_eval_queued"]["launches_per_step"])
 PY
+done
