@@ -46,6 +46,21 @@ def workload(batch: int, seed: int):
     return desc, params, x0
 
 
+def usable_cores() -> int:
+    """Host cores this process may really use: the affinity mask, capped by a cgroup CPU quota."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            cores = max(1, min(cores, int(float(quota) / float(period))))
+    except (OSError, ValueError):
+        pass
+    return cores
+
+
 def bench_config(batch: int, world: int, seed: int) -> dict:
     """The workload description shared by both arms (same `config` keys)."""
     return {"workload": f"batch {batch} ThreePlayerIntersection (2x car6d + unicycle4d, n=16, m=(2,2,2)), T=100, "
@@ -171,10 +186,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except AttributeError:
-        cores = os.cpu_count() or 1
+    cores = usable_cores()
     per_worker = 16
     _, _, x0 = workload(args.batch, args.seed)
     sample = x0[: min(args.batch, cores * per_worker)]
@@ -222,6 +234,7 @@ def run_b200(args):
                          "for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():

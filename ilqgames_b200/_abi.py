@@ -37,7 +37,8 @@ COST_SUM, COST_MAX, COST_MIN = 0, 1, 2
 
 XS, US, PS, ALPHAS, LIN_A, LIN_B, QUAD_Q, QUAD_L, QUAD_R, QUAD_RGRAD, DELTA_XS = range(1, 12)
 (STATUS, ITERS, MERIT, TOTAL_COSTS, LAMBDAS, MU, EXPECTED_DECREASE, STEP, BACKTRACKS,
- TIME_OF_EXTREME, X0, LQ_PS, LQ_ALPHAS, MAX_CONSTRAINT_ERROR) = range(12, 26)
+ TIME_OF_EXTREME, X0, LQ_PS, LQ_ALPHAS, MAX_CONSTRAINT_ERROR, AL_SUCCESS, AL_ITERATES,
+ AL_STATE) = range(12, 29)
 
 OK = 0
 
@@ -112,6 +113,7 @@ ABI_SYMBOLS = [
     "ilqg_iterate", "ilqg_al_update", "ilqg_overwrite_solution", "ilqg_al_post_solve",
     "ilqg_download", "ilqg_synchronize", "ilqg_kernel_launches", "ilqg_set_stream",
     "ilqg_profile", "ilqg_profile_read", "ilqg_reset", "ilqg_count_running",
+    "ilqg_al_begin", "ilqg_al_advance",
 ]
 
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -156,6 +158,8 @@ class Library:
         L.ilqg_set_stream.argtypes = [vp, vp]
         L.ilqg_reset.argtypes = [vp, C.c_int]
         L.ilqg_count_running.argtypes = [vp, ip]
+        L.ilqg_al_begin.argtypes = [vp, C.c_int, C.c_float]
+        L.ilqg_al_advance.argtypes = [vp, ip]
         L.ilqg_profile.argtypes = [vp, C.c_int]
         L.ilqg_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double),
                                         C.POINTER(C.c_longlong)]
@@ -223,6 +227,7 @@ class Handle:
             EXPECTED_DECREASE: ((), np.float32), STEP: ((), np.float32),
             BACKTRACKS: ((), np.int32), TIME_OF_EXTREME: ((self.N,), np.int32),
             X0: ((self.n,), np.float32), MAX_CONSTRAINT_ERROR: ((), np.float32),
+            AL_SUCCESS: ((), np.int32), AL_ITERATES: ((), np.int32), AL_STATE: ((), np.int32),
         }
 
     # -- lifetime ---------------------------------------------------------------
@@ -324,6 +329,15 @@ class Handle:
             if self.count_running() == 0:
                 break
         return done
+
+    def al_begin(self, max_iterates: int, constraint_error_tolerance: float):
+        self.lib.check(self.lib.lib.ilqg_al_begin(self._h, int(max_iterates),
+                                                  float(constraint_error_tolerance)), "al_begin")
+
+    def al_advance(self) -> int:
+        out = C.c_int(0)
+        self.lib.check(self.lib.lib.ilqg_al_advance(self._h, C.byref(out)), "al_advance")
+        return out.value
 
     def al_update(self):
         self.lib.check(self.lib.lib.ilqg_al_update(self._h), "al_update")

@@ -738,6 +738,10 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
   ALLOC(s.max_con_err, B);
   ALLOC(s.status, B);
   ALLOC(s.iters, B);
+  ALLOC(s.al_state, B);
+  ALLOC(s.al_iterates, B);
+  ALLOC(s.al_success, B);
+  ALLOC(s.al_flags, B);
   ALLOC(s.backtracks, B);
   ALLOC(s.te_quad, B * N);
   ALLOC(s.te_new, B * N);
@@ -949,7 +953,7 @@ int ilqg_count_running(SubHandle h, int* running) {
 
 int ilqg_al_update(SubHandle h) {
   ENTER(h);
-  k_al_update<<<h->B, ILQG_MAX_COSTS, 0, h->stream>>>(h->d, h->p, h->s);
+  k_al_update<<<h->B, ILQG_MAX_COSTS, 0, h->stream>>>(h->d, h->p, h->s, 0);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   return ILQG_OK;
@@ -957,7 +961,7 @@ int ilqg_al_update(SubHandle h) {
 
 int ilqg_overwrite_solution(SubHandle h, int only_successful) {
   ENTER(h);
-  k_overwrite_solution<<<h->B, 256, 0, h->stream>>>(h->d, h->s, only_successful);
+  k_overwrite_solution<<<h->B, 256, 0, h->stream>>>(h->d, h->s, only_successful, 0);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   return ILQG_OK;
@@ -965,8 +969,28 @@ int ilqg_overwrite_solution(SubHandle h, int only_successful) {
 
 int ilqg_al_post_solve(SubHandle h) {
   ENTER(h);
-  k_al_post_solve<<<h->B, 128, 0, h->stream>>>(h->d, h->p, h->s);
+  k_al_post_solve<<<h->B, 128, 0, h->stream>>>(h->d, h->p, h->s, 0);
   h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ILQG_OK;
+}
+
+int ilqg_al_begin(SubHandle h) {
+  ENTER(h);
+  k_al_begin<<<(h->B + 127) / 128, 128, 0, h->stream>>>(h->s);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ILQG_OK;
+}
+
+// one AugmentedLagrangianSolver::Solve round; *active accumulates (device counter, read by the caller)
+int ilqg_al_advance(SubHandle h, int first, int max_iterates, float tolerance, int* d_active) {
+  ENTER(h);
+  k_al_account<<<(h->B + 127) / 128, 128, 0, h->stream>>>(h->d, h->s, first, max_iterates, tolerance, d_active);
+  k_al_post_solve<<<h->B, 128, 0, h->stream>>>(h->d, h->p, h->s, AL_DO_DOWNSCALE);
+  k_al_update<<<h->B, ILQG_MAX_COSTS, 0, h->stream>>>(h->d, h->p, h->s, AL_DO_UPDATE);
+  k_overwrite_solution<<<h->B, 256, 0, h->stream>>>(h->d, h->s, 0, AL_DO_OVERWRITE);
+  h->launches += 4;
   CUDA_TRY(cudaGetLastError());
   return ILQG_OK;
 }
@@ -1002,6 +1026,9 @@ int ilqg_download(SubHandle h, int what, void* dst, size_t bytes) {
     case ILQG_STATUS: return DownloadFlat(h, s.status, 4, 1, dst, bytes);
     case ILQG_ITERS: return DownloadFlat(h, s.iters, 4, 1, dst, bytes);
     case ILQG_BACKTRACKS: return DownloadFlat(h, s.backtracks, 4, 1, dst, bytes);
+    case ILQG_AL_SUCCESS: return DownloadFlat(h, s.al_success, 4, 1, dst, bytes);
+    case ILQG_AL_ITERATES: return DownloadFlat(h, s.al_iterates, 4, 1, dst, bytes);
+    case ILQG_AL_STATE: return DownloadFlat(h, s.al_state, 4, 1, dst, bytes);
     case ILQG_TIME_OF_EXTREME: return DownloadFlat(h, s.te_new, 4, N, dst, bytes);
   }
   return ILQG_ERR_INVALID_ARGUMENT;
@@ -1018,6 +1045,7 @@ int ilqg_reset(SubHandle h, int mask) {
   int rc;
   const size_t B = h->B, T = h->d.T, n = h->d.n, M = h->d.M;
   Slab& s = h->s;
+  CUDA_TRY(cudaMemsetAsync(s.al_state, 0, sizeof(int) * B, h->stream));  // any reset ends an AL solve
   if (mask & ILQG_RESET_SOLVER) {
     if ((rc = Fill(h, s.last_merit, INFINITY, B)) != ILQG_OK) return rc;
     if ((rc = Fill(h, s.expected_decrease, INFINITY, B)) != ILQG_OK) return rc;
@@ -1106,6 +1134,11 @@ struct ilqg_solver {
   cudaStream_t stream, own_stream;
   ilqg_layout layout;
   int B, device;
+  // AugmentedLagrangianSolver::Solve driver state (ilqg_al_begin / ilqg_al_advance)
+  int al_max_iterates = 0;
+  float al_tolerance = 0.f;
+  bool al_first = true;
+  int* al_active_dev = nullptr;
 };
 
 namespace {
@@ -1248,7 +1281,8 @@ static size_t PerInstance(const ilqg_solver* h, int what) {
     case ILQG_TOTAL_COSTS: case ILQG_TIME_OF_EXTREME: return N;
     case ILQG_X0: return n;
     case ILQG_MU: case ILQG_MERIT: case ILQG_EXPECTED_DECREASE: case ILQG_STEP: case ILQG_MAX_CONSTRAINT_ERROR:
-    case ILQG_STATUS: case ILQG_ITERS: case ILQG_BACKTRACKS: return 1;
+    case ILQG_STATUS: case ILQG_ITERS: case ILQG_BACKTRACKS:
+    case ILQG_AL_SUCCESS: case ILQG_AL_ITERATES: case ILQG_AL_STATE: return 1;
   }
   return 0;
 }
@@ -1325,6 +1359,42 @@ int ilqg_iterate(ilqg_handle h, int max_iters, int* iters_done) {
     }
     *iters_done = most;
   }
+  return ILQG_OK;
+}
+
+int ilqg_al_begin(ilqg_handle h, int max_iterates, float constraint_error_tolerance) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  if (max_iterates < 0) return ILQG_ERR_INVALID_ARGUMENT;
+  h->al_max_iterates = max_iterates;
+  h->al_tolerance = constraint_error_tolerance;
+  h->al_first = true;
+  return ForEach(h, [](SubSolver* g, int) { return sub::ilqg_al_begin(g); });
+}
+
+int ilqg_al_advance(ilqg_handle h, int* active) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  int running = 0;
+  int rc = ilqg_count_running(h, &running);
+  if (rc != ILQG_OK) return rc;
+  if (running > 0) return ILQG_ERR_INVALID_ARGUMENT;  // the inner solve has not finished
+  Guard guard(h->device);
+  if (!guard.ok) return ILQG_ERR_CUDA;
+  SubSolver* g0 = h->subs[0];
+  if (!h->al_active_dev) {
+    if ((rc = DevAlloc(g0, &h->al_active_dev, 1)) != ILQG_OK) return rc;
+  }
+  CUDA_TRY(cudaMemsetAsync(h->al_active_dev, 0, sizeof(int), g0->stream));
+  CUDA_TRY(cudaStreamSynchronize(g0->stream));
+  const int first = h->al_first ? 1 : 0;
+  rc = ForEach(h, [&](SubSolver* g, int) {
+    return sub::ilqg_al_advance(g, first, h->al_max_iterates, h->al_tolerance, h->al_active_dev);
+  });
+  if (rc != ILQG_OK) return rc;
+  h->al_first = false;
+  if ((rc = ilqg_synchronize(h)) != ILQG_OK) return rc;
+  int n = 0;
+  CUDA_TRY(cudaMemcpy(&n, h->al_active_dev, sizeof(int), cudaMemcpyDeviceToHost));
+  if (active) *active = n;
   return ILQG_OK;
 }
 

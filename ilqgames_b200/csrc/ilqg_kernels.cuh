@@ -32,6 +32,9 @@ struct Slab {
   float *mu, *last_merit, *expected_decrease, *step, *total_costs, *max_con_err;
   int *status, *iters, *backtracks, *te_quad, *te_new, *op_cur, *st_cur;
   int* ls_next_j;                   // [B] next linesearch candidate; 0 = no linesearch open
+  // AugmentedLagrangianSolver::Solve per game (ilqg_al_begin / ilqg_al_advance):
+  int *al_state, *al_iterates, *al_success;  // state 0 none, 1 active, 2 finished (solve_begin skips it)
+  int* al_flags;                    // [B] scratch of one ilqg_al_advance: AL_DO_* bits
   const int* lambda_index;          // [T]  kk -> Constraint::TimeIndex
 };
 
@@ -574,8 +577,9 @@ __global__ void k_gather_parity(float* dst, const float* src0, const float* src1
 
 // Problem::OverwriteSolution (src/problem.cpp:188-194): prob <- current, optionally only
 // for instances whose last solve did not fail.
-__global__ void k_overwrite_solution(const __grid_constant__ DevDesc d, Slab s, int only_successful) {
+__global__ void k_overwrite_solution(const __grid_constant__ DevDesc d, Slab s, int only_successful, int flag_bit) {
   const int b = blockIdx.x;
+  if (flag_bit && !(s.al_flags[b] & flag_bit)) return;
   if (only_successful && s.status[b] == ILQG_STATUS_LINESEARCH_FAILED) return;
   const int T = d.T, n = d.n, M = d.M, cur = s.op_cur[b], scur = s.st_cur[b];
   const size_t ox = (size_t)b * T * n, ou = (size_t)b * T * M, oP = (size_t)b * T * M * n;
@@ -607,8 +611,9 @@ __global__ void k_prob_to_working(const __grid_constant__ DevDesc d, Slab s) {
 // One augmented-Lagrangian multiplier sweep, src/augmented_lagrangian_solver.cpp:113-143,
 // one thread per (instance, constraint): lambda <- max(0, lambda + mu g) visiting kk in order
 // so the duplicated TimeIndex slots are incremented twice, exactly as the reference.
-__global__ void k_al_update(const __grid_constant__ DevDesc d, const DevParams p, Slab s) {
+__global__ void k_al_update(const __grid_constant__ DevDesc d, const DevParams p, Slab s, int flag_bit) {
   const int b = blockIdx.x;
+  if (flag_bit && !(s.al_flags[b] & flag_bit)) return;
   __shared__ float smax[ILQG_MAX_COSTS];
   const int cidx = threadIdx.x;
   float max_err = -INFINITY;
@@ -639,13 +644,54 @@ __global__ void k_al_update(const __grid_constant__ DevDesc d, const DevParams p
 }
 
 // src/augmented_lagrangian_solver.cpp:165-178
-__global__ void k_al_post_solve(const __grid_constant__ DevDesc d, const DevParams p, Slab s) {
+__global__ void k_al_post_solve(const __grid_constant__ DevDesc d, const DevParams p, Slab s, int flag_bit) {
   const int b = blockIdx.x;
+  if (flag_bit && !(s.al_flags[b] & flag_bit)) return;
   if (s.status[b] != ILQG_STATUS_LINESEARCH_FAILED) return;
   const int cnt = d.num_constraints * d.T;
   for (int e = threadIdx.x; e < cnt; e += blockDim.x)
     s.lambdas[(size_t)b * cnt + e] *= p.geometric_lambda_downscaling;
   if (threadIdx.x == 0) s.mu[b] *= p.geometric_mu_downscaling;
+}
+
+// Bookkeeping of one AugmentedLagrangianSolver::Solve round per game
+// (src/augmented_lagrangian_solver.cpp:94-111, 165-190); the multiplier work it decides on is
+// done by k_al_post_solve / k_al_update / k_overwrite_solution under the AL_DO_* flags.
+enum { AL_DO_DOWNSCALE = 1, AL_DO_UPDATE = 2, AL_DO_OVERWRITE = 4 };
+
+__global__ void k_al_account(const __grid_constant__ DevDesc d, Slab s, int first, int max_iterates, float tolerance,
+                             int* active) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= s.B) return;
+  s.al_flags[b] = 0;
+  if (s.al_state[b] != 1) return;
+  const bool failed = s.status[b] == ILQG_STATUS_LINESEARCH_FAILED;
+  // the inner log holds the initial iterate plus one per completed iteration; the iteration whose
+  // linesearch failed is not logged (src/ilq_solver.cpp:111,146-153,164)
+  const int iterates = s.al_iterates[b] + 1 + s.iters[b] - (failed ? 1 : 0);
+  s.al_iterates[b] = iterates;
+  int flags = (!first && failed) ? AL_DO_DOWNSCALE : 0;
+  if (failed) s.al_success[b] = 0;
+  const bool constrained = d.num_constraints > 0;
+  const float err = s.max_con_err[b];
+  const bool again = constrained && iterates < max_iterates && err > tolerance;
+  if (!again) {
+    if (constrained && err > tolerance) s.al_success[b] = 0;
+    s.al_state[b] = 2;
+  } else {
+    flags |= AL_DO_UPDATE | (failed ? 0 : AL_DO_OVERWRITE);
+    atomicAdd(active, 1);
+  }
+  s.al_flags[b] = flags;
+}
+
+__global__ void k_al_begin(Slab s) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= s.B) return;
+  s.al_state[b] = 1;
+  s.al_iterates[b] = 0;
+  s.al_success[b] = 1;
+  s.max_con_err[b] = INFINITY;
 }
 
 __global__ void k_fill(float* p, float v, size_t count) {

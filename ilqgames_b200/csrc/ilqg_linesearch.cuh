@@ -63,7 +63,7 @@ __device__ __forceinline__ LsItem ls_decode(const DevParams& p, const Slab& s, c
   if (lane >= ls.lpw) return it;
   if (mode == LS_MODE_BEGIN) {
     it.b = block * ls.lpw + lane;
-    it.valid = it.b < s.B;
+    it.valid = it.b < s.B && s.al_state[it.b] != 2;  // a finished AL game is left alone
   } else if (mode == LS_MODE_FRESH) {
     const int item = block * ls.lpw + lane;
     it.b = item / ls.JA;
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(KDEC_WARPS * 32)
 k_begin_finalize(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * KDEC_WARPS + warp;
-  if (b >= s.B) return;
+  if (b >= s.B || s.al_state[b] == 2) return;
   const int T = d.T, n = d.n, M = d.M, N = d.N;
   // current strategies <- problem strategies
   const float4* pP = reinterpret_cast<const float4*>(s.prob_P + (size_t)b * T * M * n);

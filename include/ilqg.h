@@ -218,7 +218,10 @@ enum {
   ILQG_TIME_OF_EXTREME = 21,   /* int32 [B][N]                                */
   ILQG_X0 = 22,
   ILQG_LQ_PS = 23, ILQG_LQ_ALPHAS = 24, /* raw LQ solution (before linesearch scaling) */
-  ILQG_MAX_CONSTRAINT_ERROR = 25 /* float [B], from ilqg_al_update            */
+  ILQG_MAX_CONSTRAINT_ERROR = 25, /* float [B], from ilqg_al_update / ilqg_al_advance */
+  ILQG_AL_SUCCESS = 26,        /* int32 [B] AugmentedLagrangianSolver::Solve's *success */
+  ILQG_AL_ITERATES = 27,       /* int32 [B] log->NumIterates() of the AL solve   */
+  ILQG_AL_STATE = 28           /* int32 [B] 0 = none, 1 = active, 2 = finished   */
 };
 
 typedef struct ilqg_solver* ilqg_handle;
@@ -308,6 +311,25 @@ int ilqg_overwrite_solution(ilqg_handle h, int only_successful);
 /* src/augmented_lagrangian_solver.cpp:165-178: for instances whose inner solve
  * failed, lambda *= geometric_lambda_downscaling, mu *= geometric_mu_downscaling. */
 int ilqg_al_post_solve(ilqg_handle h);
+
+/* AugmentedLagrangianSolver::Solve (src/augmented_lagrangian_solver.cpp:72-210) for a batch:
+ * every game runs ITS OWN outer loop (own multipliers, own mu, own iterate count, own exit),
+ * driven in rounds by the caller:
+ *
+ *     ilqg_al_begin(h, params.max_solver_iters of the AL solver, constraint_error_tolerance);
+ *     do { ilqg_solve_begin(h); ilqg_iterate(h, ...) until ilqg_count_running == 0;
+ *          ilqg_al_advance(h, &active); } while (active > 0);
+ *
+ * ilqg_al_advance does, per game still in its loop: account the inner solve's iterates and
+ * success (:94-100, :179-180), down-scale multipliers after a failed inner solve (:165-178, not
+ * after the first solve), test the loop condition (:109-111; the wall-clock term is the
+ * caller's) and either finish the game (final success flag :187-190; later
+ * ilqg_solve_begin calls skip it) or run the multiplier sweep + ScaleMu (:113-143) and
+ * OverwriteSolution after a successful inner solve (:151-154).  `active` = games that need
+ * another inner solve.  ilqg_solver_params.max_solver_iters is the INNER solver's cap
+ * (params.unconstrained_solver_max_iters, solver_params.h).  ilqg_reset ends an AL solve. */
+int ilqg_al_begin(ilqg_handle h, int max_iterates, float constraint_error_tolerance);
+int ilqg_al_advance(ilqg_handle h, int* active);
 
 int ilqg_download(ilqg_handle h, int what, void* dst, size_t bytes);
 int ilqg_synchronize(ilqg_handle h);

@@ -281,6 +281,9 @@ struct Instance {
   std::vector<int> te_quad, te_new;
   int status, iters, backtracks;
   real max_constraint_error;
+  // AugmentedLagrangianSolver::Solve per instance (ilqg_al_begin / ilqg_al_advance):
+  // 0 = not in an AL solve, 1 = active, 2 = finished (solve_begin leaves it alone)
+  int al_state, al_iterates, al_success;
 };
 
 // ------------------------------- dynamics ----------------------------------
@@ -1229,6 +1232,9 @@ struct ilqg_solver {
   Problem pr;
   int batch;
   std::vector<Instance> inst;
+  int al_max_iterates = 0;
+  float al_tolerance = 0;
+  bool al_first = true;
 };
 
 namespace {
@@ -1265,6 +1271,9 @@ void InitInstance(const Problem& pr, Instance& in) {
   in.iters = 0;
   in.backtracks = 0;
   in.max_constraint_error = kInfinity;
+  in.al_state = 0;
+  in.al_iterates = 0;
+  in.al_success = 1;
 }
 
 template <typename Src>
@@ -1460,6 +1469,7 @@ int ilqg_solve_begin(ilqg_handle h) {
   if (!h) return ILQG_ERR_BAD_HANDLE;
   const Problem& pr = h->pr;
   for (auto& in : h->inst) {
+    if (in.al_state == 2) continue;  // this game's AL loop has ended
     // src/ilq_solver.cpp:86-107
     std::vector<real> last_xs = in.prob_xs, last_us = in.prob_us;
     for (int a = 0; a < pr.n; a++) last_xs[a] = in.x0[a];
@@ -1526,65 +1536,129 @@ int ilqg_iterate(ilqg_handle h, int max_iters, int* iters_done) {
   return ILQG_OK;
 }
 
-// src/augmented_lagrangian_solver.cpp:113-178, per instance.
-int ilqg_al_update(ilqg_handle h) {
-  if (!h) return ILQG_ERR_BAD_HANDLE;
-  const Problem& pr = h->pr;
+}  // extern "C"
+
+namespace {
+
+// src/augmented_lagrangian_solver.cpp:113-143 for one game: multiplier sweep + ScaleMu.
+void AlUpdateOne(const Problem& pr, Instance& in) {
   const ilqg_problem_desc& d = pr.d;
-  for (auto& in : h->inst) {
-    real max_err = -kInfinity;
-    // Outer loop over players then time (:116-139); constraints of one player in
-    // record order, state constraints before control constraints.
-    for (int i = 0; i < pr.N; i++)
-      for (int kk = 0; kk < pr.T; kk++) {
-        // t = op.t0 + kTimeStep * float(kk): same TimeIndex as RelativeTime(kk).
-        const int li = pr.lambda_index[kk];
-        for (int pass = 0; pass < 2; pass++)
-          for (int c = 0; c < d.num_costs; c++) {
-            const ilqg_cost_desc& cd = d.costs[c];
-            const int slot = pr.constraint_slot[c];
-            if (slot < 0 || cd.player != i) continue;
-            if ((pass == 0) != (cd.arg < 0)) continue;
-            const real g = cd.arg < 0
-                               ? EvaluateRecord(pr, cd, &in.xs[(size_t)kk * pr.n], pr.n)
-                               : EvaluateRecord(pr, cd, &in.us[(size_t)kk * pr.M + pr.uoff[cd.arg]],
-                                                d.udim[cd.arg]);
-            max_err = std::max(max_err, g);
-            // Constraint::IncrementLambda, constraint.h:98-102
-            real& lam = in.lambdas[(size_t)slot * pr.T + li];
-            const real new_lambda = lam + in.mu * g;
-            lam = cd.is_equality ? new_lambda : std::max((real)0.0f, new_lambda);
-          }
-      }
-    in.mu *= pr.p.geometric_mu_scaling;  // :143
-    in.max_constraint_error = max_err;
-  }
-  return ILQG_OK;
+  real max_err = -kInfinity;
+  // Outer loop over players then time (:116-139); constraints of one player in
+  // record order, state constraints before control constraints.
+  for (int i = 0; i < pr.N; i++)
+    for (int kk = 0; kk < pr.T; kk++) {
+      // t = op.t0 + kTimeStep * float(kk): same TimeIndex as RelativeTime(kk).
+      const int li = pr.lambda_index[kk];
+      for (int pass = 0; pass < 2; pass++)
+        for (int c = 0; c < d.num_costs; c++) {
+          const ilqg_cost_desc& cd = d.costs[c];
+          const int slot = pr.constraint_slot[c];
+          if (slot < 0 || cd.player != i) continue;
+          if ((pass == 0) != (cd.arg < 0)) continue;
+          const real g = cd.arg < 0
+                             ? EvaluateRecord(pr, cd, &in.xs[(size_t)kk * pr.n], pr.n)
+                             : EvaluateRecord(pr, cd, &in.us[(size_t)kk * pr.M + pr.uoff[cd.arg]],
+                                              d.udim[cd.arg]);
+          max_err = std::max(max_err, g);
+          // Constraint::IncrementLambda, constraint.h:98-102
+          real& lam = in.lambdas[(size_t)slot * pr.T + li];
+          const real new_lambda = lam + in.mu * g;
+          lam = cd.is_equality ? new_lambda : std::max((real)0.0f, new_lambda);
+        }
+    }
+  in.mu *= pr.p.geometric_mu_scaling;  // :143
+  in.max_constraint_error = max_err;
 }
 
 // Problem::OverwriteSolution(log->FinalOperatingPoint(), log->FinalStrategies()),
 // src/problem.cpp:188-194 as called at augmented_lagrangian_solver.cpp:151-154.
+void OverwriteOne(Instance& in) {
+  in.prob_xs = in.xs;
+  in.prob_us = in.us;
+  in.prob_Ps = in.Ps;
+  in.prob_alphas = in.alphas;
+}
+
+// src/augmented_lagrangian_solver.cpp:165-178
+void DownscaleOne(const Problem& pr, Instance& in) {
+  for (auto& lam : in.lambdas) lam *= pr.p.geometric_lambda_downscaling;
+  in.mu *= pr.p.geometric_mu_downscaling;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ilqg_al_update(ilqg_handle h) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  for (auto& in : h->inst) AlUpdateOne(h->pr, in);
+  return ILQG_OK;
+}
+
 int ilqg_overwrite_solution(ilqg_handle h, int only_successful) {
   if (!h) return ILQG_ERR_BAD_HANDLE;
   for (auto& in : h->inst) {
     if (only_successful && in.status == ILQG_STATUS_LINESEARCH_FAILED) continue;
-    in.prob_xs = in.xs;
-    in.prob_us = in.us;
-    in.prob_Ps = in.Ps;
-    in.prob_alphas = in.alphas;
+    OverwriteOne(in);
   }
   return ILQG_OK;
 }
 
-// src/augmented_lagrangian_solver.cpp:165-178: down-scale multipliers of the
-// instances whose inner solve failed.
 int ilqg_al_post_solve(ilqg_handle h) {
   if (!h) return ILQG_ERR_BAD_HANDLE;
   for (auto& in : h->inst) {
     if (in.status != ILQG_STATUS_LINESEARCH_FAILED) continue;
-    for (auto& lam : in.lambdas) lam *= h->pr.p.geometric_lambda_downscaling;
-    in.mu *= h->pr.p.geometric_mu_downscaling;
+    DownscaleOne(h->pr, in);
   }
+  return ILQG_OK;
+}
+
+// AugmentedLagrangianSolver::Solve, src/augmented_lagrangian_solver.cpp:72-210, as a per-game
+// state machine around the inner solves the caller runs:
+//   al_begin; do { solve_begin; iterate until nothing runs; al_advance(&active); } while (active);
+int ilqg_al_begin(ilqg_handle h, int max_iterates, float constraint_error_tolerance) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  if (max_iterates < 0) return ILQG_ERR_INVALID_ARGUMENT;
+  h->al_max_iterates = max_iterates;
+  h->al_tolerance = constraint_error_tolerance;
+  h->al_first = true;
+  for (auto& in : h->inst) {
+    in.al_state = 1;
+    in.al_iterates = 0;
+    in.al_success = 1;                     // :74
+    in.max_constraint_error = kInfinity;   // :108
+  }
+  return ILQG_OK;
+}
+
+int ilqg_al_advance(ilqg_handle h, int* active) {
+  if (!h) return ILQG_ERR_BAD_HANDLE;
+  const Problem& pr = h->pr;
+  int n_active = 0;
+  for (auto& in : h->inst) {
+    if (in.al_state != 1) continue;
+    if (in.status == ILQG_STATUS_RUNNING) return ILQG_ERR_INVALID_ARGUMENT;  // inner solve not finished
+    const bool failed = in.status == ILQG_STATUS_LINESEARCH_FAILED;
+    // the inner log holds the initial iterate plus one per completed iteration; the iteration
+    // whose linesearch failed is not logged (src/ilq_solver.cpp:111,146-153,164); AddLog :94,180
+    in.al_iterates += 1 + in.iters - (failed ? 1 : 0);
+    if (!h->al_first && failed) DownscaleOne(pr, in);  // :165-178
+    in.al_success = in.al_success && !failed;          // :100, :179
+    const bool constrained = pr.num_constraints > 0;   // :103
+    const bool again = constrained && in.al_iterates < h->al_max_iterates &&
+                       in.max_constraint_error > (real)h->al_tolerance;  // :109-111 (time: SURVEY Q2)
+    if (!again) {
+      if (constrained && in.max_constraint_error > (real)h->al_tolerance) in.al_success = 0;  // :187-190
+      in.al_state = 2;
+      continue;
+    }
+    AlUpdateOne(pr, in);             // :113-143
+    if (!failed) OverwriteOne(in);   // :151-154
+    n_active++;
+  }
+  h->al_first = false;
+  if (active) *active = n_active;
   return ILQG_OK;
 }
 
@@ -1635,6 +1709,9 @@ int ilqg_download(ilqg_handle h, int what, void* dst, size_t bytes) {
     case ILQG_STATUS: return iscal(&Instance::status);
     case ILQG_ITERS: return iscal(&Instance::iters);
     case ILQG_BACKTRACKS: return iscal(&Instance::backtracks);
+    case ILQG_AL_SUCCESS: return iscal(&Instance::al_success);
+    case ILQG_AL_ITERATES: return iscal(&Instance::al_iterates);
+    case ILQG_AL_STATE: return iscal(&Instance::al_state);
     case ILQG_TIME_OF_EXTREME:
       if (bytes != sizeof(int32_t) * B * pr.N) return ILQG_ERR_SIZE_MISMATCH;
       for (int b = 0; b < B; b++)
@@ -1649,6 +1726,7 @@ int ilqg_synchronize(ilqg_handle h) { return h ? ILQG_OK : ILQG_ERR_BAD_HANDLE; 
 int ilqg_reset(ilqg_handle h, int mask) {
   if (!h) return ILQG_ERR_BAD_HANDLE;
   for (auto& in : h->inst) {
+    in.al_state = 0;  // any reset ends an augmented-Lagrangian solve
     if (mask & ILQG_RESET_SOLVER) {
       in.last_merit = kInfinity;
       in.expected_decrease = kInfinity;

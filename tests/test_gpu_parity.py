@@ -277,6 +277,43 @@ def test_augmented_lagrangian_update(product, oracle):
     close(c.download(abi.MU), o.download(abi.MU), what="mu after post-solve")
 
 
+def test_augmented_lagrangian_solve(product, oracle, oracle64):
+    """Row f1: the whole AugmentedLagrangianSolver::Solve per game (ilqg_al_begin / ilqg_al_advance).
+    An AL solve chains ~10 inner solves, so only games whose fp32 and fp64 oracle runs agree
+    (same iterate count, same success, close trajectory) are compared by value."""
+    from ilqgames_b200 import al
+    B, cap, tol = 12, 40, 0.1
+    desc, _ = problems.three_player_intersection()
+    x0 = problems.three_player_intersection_x0_batch(B, 2024)
+    res = {}
+    for name, lib in (("cuda", product), ("o32", oracle), ("o64", oracle64)):
+        params = problems.three_player_intersection_params()
+        params.max_solver_iters = params.unconstrained_solver_max_iters
+        h = abi.Handle(lib, desc, params, B, 0)
+        h.upload_x0(x0)
+        res[name] = al.solve_augmented_lagrangian(h, cap, tol, reset_problem=False, reset_lambdas=False,
+                                                  reset_mu=False)
+        assert (h.download(abi.AL_STATE) == 2).all()
+        res[name + "_mu"] = h.download(abi.MU)
+    c, o, o64 = res["cuda"], res["o32"], res["o64"]
+    # invariants of the loop itself, every game
+    assert (c.iterates >= 1).all() and (c.iterates < cap + 11).all()
+    assert not (c.success.astype(bool) & (c.max_constraint_error > tol)).any()
+    assert c.rounds >= 2
+
+    def agree(a, b):
+        same = (a.iterates == b.iterates) & (a.success == b.success)
+        err = np.abs(a.xs.astype(np.float64) - b.xs).reshape(B, -1).max(axis=1)
+        scale = np.abs(b.xs).reshape(B, -1).max(axis=1)
+        return same & (err <= 2e-2 * scale + 1e-3)
+
+    stable = agree(o, o64)
+    assert stable.sum() >= 3, f"only {stable.sum()} of {B} games are well-posed in fp32"
+    match = agree(c, o)
+    assert match[stable].mean() >= 0.75, (match, stable, c.iterates, o.iterates)
+    close(res["cuda_mu"][stable & match], res["o32_mu"][stable & match], tol=1e-4, what="mu after the AL solve")
+
+
 # ------------------------------------------------------------------ full-size properties
 def test_full_batch_properties(product):
     """BASELINE.json's metric size (batch 4096, T = 100): properties that need no oracle run."""
