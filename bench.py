@@ -88,6 +88,9 @@ def algorithmic_bytes(layout) -> dict:
 
 # ------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region (NVML in-process, every
+    20 ms; nvidia-smi as a fallback).  Rows: [sm_mhz, sm_max_mhz, power_w, hw_slowdown,
+    hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap]."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -97,10 +100,41 @@ class ClockSampler:
         self.rows = []
         self._stop = threading.Event()
         self._t = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; map through CUDA_VISIBLE_DEVICES when it is a plain list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = index
+            if vis and all(tok.strip().isdigit() for tok in vis.split(",")):
+                phys = int(vis.split(",")[index])
+            self._dev = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = n.nvmlDeviceGetClockInfo(self._dev, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self._dev, n.NVML_CLOCK_SM)
+        try:
+            pw = n.nvmlDeviceGetPowerUsage(self._dev) / 1000.0
+        except Exception:
+            pw = 0.0
+        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._dev)
+        act = lambda bit: "Active" if (r & bit) else "Not Active"
+        return [str(sm), str(mx), str(pw), act(n.nvmlClocksThrottleReasonHwSlowdown),
+                act(n.nvmlClocksThrottleReasonHwThermalSlowdown), act(n.nvmlClocksThrottleReasonSwThermalSlowdown),
+                act(n.nvmlClocksThrottleReasonSwPowerCap)]
 
     def _run(self):
         while not self._stop.is_set():
             try:
+                if self._nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                    self._stop.wait(0.02)
+                    continue
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], capture_output=True, text=True, timeout=5)
                 if out.returncode == 0 and out.stdout.strip():

@@ -1,0 +1,6 @@
+// Path-compatible entry point: code written against HJReachability/ilqgames includes
+// <ilqgames/utils/quadratic_cost_approximation.h>; the B200 host classes live in <ilqgames/b200/core.h>.
+#ifndef ILQGAMES_B200_FWD_UTILS_QUADRATIC_COST_APPROXIMATION_H
+#define ILQGAMES_B200_FWD_UTILS_QUADRATIC_COST_APPROXIMATION_H
+#include <ilqgames/b200/core.h>
+#endif

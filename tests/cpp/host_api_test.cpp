@@ -1,0 +1,234 @@
+// host_api_test.cpp -- the C++ host classes (include/ilqgames/**) exercised the way the
+// reference's own tests and executables use them; links against any implementation of ilqg.h
+// (the CPU oracle in `-m "not gpu"` runs, libilqg_b200.so on the GPU box).
+//
+//   host_api_test <out.bin>      writes named float arrays that tests/test_host_api.py compares
+//                                with the same computation driven through ctypes
+// Self-checking parts exit non-zero on failure.
+#include <ilqgames/solver/augmented_lagrangian_solver.h>
+#include <ilqgames/solver/ilq_solver.h>
+#include <ilqgames/solver/lq_feedback_solver.h>
+
+#include "../../examples/cpp/intersection_problem.h"
+
+#ifdef DROPIN_REFERENCE_EXAMPLE
+// the reference's own problem definition, compiled unchanged (tests/test_host_api.py builds this
+// variant only where /root/reference exists)
+#include <ilqgames/examples/three_player_intersection_example.h>
+#endif
+
+#include <cstdio>
+#include <cstdlib>
+
+using namespace ilqgames;
+
+namespace {
+
+FILE* g_out = nullptr;
+
+void Dump(const char* name, const float* data, size_t count) {
+  std::fprintf(g_out, "%s %zu\n", name, count);
+  std::fwrite(data, sizeof(float), count, g_out);
+}
+void Dump(const char* name, const std::vector<float>& v) { Dump(name, v.data(), v.size()); }
+
+std::vector<float> Flatten(const OperatingPoint& op) {
+  std::vector<float> out;
+  for (size_t k = 0; k < op.xs.size(); k++) {
+    for (long a = 0; a < op.xs[k].size(); a++) out.push_back(op.xs[k](a));
+    for (const VectorXf& u : op.us[k])
+      for (long a = 0; a < u.size(); a++) out.push_back(u(a));
+  }
+  return out;
+}
+std::vector<float> Flatten(const std::vector<Strategy>& strategies) {
+  std::vector<float> out;
+  for (size_t k = 0; k < strategies[0].Ps.size(); k++)
+    for (const Strategy& s : strategies) {
+      for (long r = 0; r < s.Ps[k].rows(); r++)
+        for (long c = 0; c < s.Ps[k].cols(); c++) out.push_back(s.Ps[k](r, c));
+      for (long r = 0; r < s.alphas[k].size(); r++) out.push_back(s.alphas[k](r));
+    }
+  return out;
+}
+
+#define EXPECT(cond)                                                        \
+  do {                                                                      \
+    if (!(cond)) {                                                          \
+      std::fprintf(stderr, "%s:%d EXPECT failed: %s\n", __FILE__, __LINE__, #cond); \
+      std::exit(1);                                                         \
+    }                                                                       \
+  } while (0)
+
+// ---- the LQ game of the reference's test/test_lq_solver.cpp:143-177, 227-248 ------------------
+class TwoPlayerPointMass1D : public MultiPlayerDynamicalSystem {
+ public:
+  TwoPlayerPointMass1D() : MultiPlayerDynamicalSystem(2) {}
+  Dimension UDim(PlayerIndex) const override { return 1; }
+  PlayerIndex NumPlayers() const override { return 2; }
+  std::vector<Dimension> PositionDimensions() const override { return {0}; }
+  LinearDynamicsApproximation Linearize() const {
+    LinearDynamicsApproximation lin(*this);       // A = I, B = 0
+    lin.A(0, 1) += 1.0f * time::kTimeStep;        // A = I + dt [[0 1] [0 0]]
+    lin.Bs[0](0, 0) = 0.05f * time::kTimeStep;
+    lin.Bs[0](1, 0) = 1.0f * time::kTimeStep;
+    lin.Bs[1](0, 0) = 0.032f * time::kTimeStep;
+    lin.Bs[1](1, 0) = 0.11f * time::kTimeStep;
+    return lin;
+  }
+};
+
+// LQFeedbackSolverTest.MatchesLyapunovIterations (test/test_lq_solver.cpp:292-345): the
+// feedback gains at k = 0 equal the fixed point of the coupled Lyapunov iteration.
+void TestLQMatchesLyapunovIterations() {
+  auto dynamics = std::make_shared<TwoPlayerPointMass1D>();
+  const size_t T = time::kNumTimeSteps;
+  LQFeedbackSolver solver(dynamics, T);
+  const LinearDynamicsApproximation lin = dynamics->Linearize();
+  std::vector<LinearDynamicsApproximation> linearization(T, lin);
+  std::vector<QuadraticCostApproximation> quad_k(2, QuadraticCostApproximation(2));
+  quad_k[0].state.hess = MatrixXf::Identity(2, 2);
+  quad_k[1].state.hess = 0.1f * MatrixXf::Identity(2, 2);
+  const float R11 = 1.0f, R12 = 0.1f, R21 = 0.1f, R22 = 1.0f;
+  auto one = [](float v) { MatrixXf m(1, 1); m(0, 0) = v; return m; };
+  quad_k[0].control.emplace(0, SingleCostApproximation(one(R11), VectorXf::Zero(1)));
+  quad_k[0].control.emplace(1, SingleCostApproximation(one(R12), VectorXf::Zero(1)));
+  quad_k[1].control.emplace(0, SingleCostApproximation(one(R21), VectorXf::Zero(1)));
+  quad_k[1].control.emplace(1, SingleCostApproximation(one(R22), VectorXf::Zero(1)));
+  std::vector<std::vector<QuadraticCostApproximation>> quadraticization(T, quad_k);
+
+  std::vector<VectorXf> delta_xs;
+  const std::vector<Strategy> strategies = solver.Solve(linearization, quadraticization, VectorXf::Zero(2), &delta_xs);
+  EXPECT(strategies.size() == 2 && delta_xs.size() == T);
+
+  // coupled Lyapunov iteration from the test: P <- S^-1 Y, Z_i <- F' Z_i F + Q_i + sum_j P_j' R_ij P_j
+  const MatrixXf &A = lin.A, &B1 = lin.Bs[0], &B2 = lin.Bs[1];
+  MatrixXf Z1 = quad_k[0].state.hess, Z2 = quad_k[1].state.hess, P1(1, 2), P2(1, 2);
+  for (int it = 0; it < 100; it++) {
+    const MatrixXf B1Z = B1.transpose() * Z1, B2Z = B2.transpose() * Z2;
+    const float s11 = R11 + (B1Z * B1)(0, 0), s12 = (B1Z * B2)(0, 0), s21 = (B2Z * B1)(0, 0), s22 = R22 + (B2Z * B2)(0, 0);
+    const MatrixXf y1 = B1Z * A, y2 = B2Z * A;
+    const float det = s11 * s22 - s12 * s21;
+    for (int c = 0; c < 2; c++) {
+      P1(0, c) = (s22 * y1(0, c) - s12 * y2(0, c)) / det;
+      P2(0, c) = (-s21 * y1(0, c) + s11 * y2(0, c)) / det;
+    }
+    const MatrixXf F = A - B1 * P1 - B2 * P2;
+    Z1 = F.transpose() * Z1 * F + quad_k[0].state.hess + R11 * (P1.transpose() * P1) + R12 * (P2.transpose() * P2);
+    Z2 = F.transpose() * Z2 * F + quad_k[1].state.hess + R21 * (P1.transpose() * P1) + R22 * (P2.transpose() * P2);
+  }
+  const float tol = 1e-4f;  // the reference's tolerance (:313-316)
+  EXPECT((strategies[0].Ps[0] - P1).cwiseAbsMax() < tol);
+  EXPECT((strategies[1].Ps[0] - P2).cwiseAbsMax() < tol);
+  // zero nominal and zero gradients: alphas and the delta-x forward pass vanish
+  EXPECT(strategies[0].alphas[0].norm() == 0.0f && delta_xs[T - 1].norm() == 0.0f);
+  Dump("lq_P1_k0", strategies[0].Ps[0].data(), 2);
+  Dump("lq_P2_k0", strategies[1].Ps[0].data(), 2);
+  std::printf("LQFeedbackSolver matches Lyapunov iterations: P1 = [%.6f %.6f], P2 = [%.6f %.6f]\n",
+              strategies[0].Ps[0](0, 0), strategies[0].Ps[0](0, 1), strategies[1].Ps[0](0, 0), strategies[1].Ps[0](0, 1));
+}
+
+template <typename ProblemType>
+std::shared_ptr<Problem> MakeProblem() {
+  auto problem = std::make_shared<ProblemType>();
+  problem->Initialize();
+  return problem;
+}
+
+void TestProblemDescriptor(const std::shared_ptr<Problem>& problem, const char* tag) {
+  ilqg_problem_desc desc;
+  EXPECT(b200::DescribeProblem(*problem, &desc));
+  EXPECT(desc.num_players == 3 && desc.xdim == 16 && desc.num_costs == 18 && desc.num_polylines == 3);
+  std::vector<float> raw(sizeof(desc) / sizeof(float));
+  std::memcpy(raw.data(), &desc, sizeof(desc));
+  Dump((std::string("desc_") + tag).c_str(), raw);
+  Dump((std::string("x0_") + tag).c_str(), problem->InitialState().data(), (size_t)problem->InitialState().size());
+}
+
+// exec/three_player_intersection/main.cpp:109-120
+SolverParams IntersectionParams() {
+  SolverParams params;
+  params.max_backtracking_steps = 100;
+  params.max_solver_iters = 100;
+  params.unconstrained_solver_max_iters = 10;
+  params.linesearch = true;
+  params.expected_decrease_fraction = 0.001;
+  params.initial_alpha_scaling = 0.1;
+  params.convergence_tolerance = 1.0;
+  params.geometric_mu_scaling = 1.1;
+  params.geometric_mu_downscaling = 0.5;
+  params.geometric_lambda_downscaling = 0.5;
+  return params;
+}
+
+void TestILQSolver(const std::shared_ptr<Problem>& problem) {
+  SolverParams params = IntersectionParams();
+  params.max_solver_iters = 4;
+  ILQSolver solver(problem, params);
+  bool success = false;
+  const std::shared_ptr<SolverLog> log = solver.Solve(&success);
+  EXPECT(log->NumIterates() >= 1 && log->NumIterates() <= 5);
+  EXPECT(success == (log->NumIterates() == 5 || log->WasConverged()));
+  EXPECT(log->FinalOperatingPoint().xs.size() == time::kNumTimeSteps);
+  // every iterate starts at the problem's initial state (src/ilq_solver.cpp:88-89)
+  for (size_t it = 0; it < log->NumIterates(); it++)
+    EXPECT((log->State(it, 0) - problem->InitialState()).norm() == 0.0f);
+  const float n_iter = (float)log->NumIterates();
+  Dump("ilq_num_iterates", &n_iter, 1);
+  Dump("ilq_final_op", Flatten(log->FinalOperatingPoint()));
+  Dump("ilq_final_strategies", Flatten(log->FinalStrategies()));
+  Dump("ilq_total_costs", log->TotalCosts());
+  std::printf("ILQSolver::Solve: %zu iterates, success = %d, total costs = [%.4f %.4f %.4f]\n", log->NumIterates(),
+              (int)success, log->TotalCosts()[0], log->TotalCosts()[1], log->TotalCosts()[2]);
+
+  // SolveBatch: game 0 = the problem's own x0 must reproduce Solve(); the problem is untouched
+  std::vector<VectorXf> x0s(3, problem->InitialState());
+  x0s[1](0) += 1.0f;
+  x0s[2](7) -= 2.0f;
+  const std::vector<BatchSolution> batch = solver.SolveBatch(x0s);
+  EXPECT(batch.size() == 3);
+  const std::vector<float> a = Flatten(batch[0].operating_point), b = Flatten(log->FinalOperatingPoint());
+  EXPECT(a == b);
+  EXPECT(batch[1].operating_point.xs[0](0) == x0s[1](0));
+  Dump("batch_op_1", Flatten(batch[1].operating_point));
+  Dump("batch_op_2", Flatten(batch[2].operating_point));
+  std::printf("ILQSolver::SolveBatch: 3 games, iterations = [%d %d %d]\n", batch[0].iterations, batch[1].iterations,
+              batch[2].iterations);
+}
+
+void TestAugmentedLagrangianSolver(const std::shared_ptr<Problem>& problem) {
+  SolverParams params = IntersectionParams();
+  params.max_solver_iters = 30;  // NumIterates cap of the outer loop
+  AugmentedLagrangianSolver solver(problem, params);
+  bool success = false;
+  const std::shared_ptr<SolverLog> log = solver.Solve(&success);
+  EXPECT(log->NumIterates() >= 2);   // the constrained game goes around the outer loop
+  EXPECT(solver.NumIterates() >= (int)log->NumIterates());
+  const float stats[3] = {(float)log->NumIterates(), (float)solver.NumIterates(), success ? 1.0f : 0.0f};
+  Dump("al_stats", stats, 3);
+  Dump("al_final_op", Flatten(log->FinalOperatingPoint()));
+  std::printf("AugmentedLagrangianSolver::Solve: %zu inner solves, %d iterates, success = %d\n", log->NumIterates(),
+              solver.NumIterates(), (int)success);
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  if (argc < 2) {
+    std::fprintf(stderr, "usage: %s <out.bin>\n", argv[0]);
+    return 2;
+  }
+  g_out = std::fopen(argv[1], "wb");
+  if (!g_out) return 2;
+  TestLQMatchesLyapunovIterations();
+  const std::shared_ptr<Problem> problem = MakeProblem<ilqgames_b200_examples::IntersectionProblem>();
+  TestProblemDescriptor(problem, "own");
+#ifdef DROPIN_REFERENCE_EXAMPLE
+  TestProblemDescriptor(MakeProblem<ThreePlayerIntersectionExample>(), "reference");
+#endif
+  TestILQSolver(problem);
+  TestAugmentedLagrangianSolver(problem);
+  std::fclose(g_out);
+  std::printf("host_api_test: all checks passed\n");
+  return 0;
+}

@@ -1,0 +1,134 @@
+"""The C++ host classes (include/ilqgames/**: Problem, ILQSolver, LQFeedbackSolver,
+AugmentedLagrangianSolver, OperatingPoint, Strategy, ...) over the C ABI.
+
+tests/cpp/host_api_test.cpp is written the way the reference's tests and executables use the
+API; here it is compiled with g++, linked against an implementation of ilqg.h (the CPU oracle
+for `-m "not gpu"`, libilqg_b200.so on the GPU box), run, and its dumped results are compared
+with the same computations driven through ctypes.  Where /root/reference exists, the reference's
+own src/three_player_intersection_example.cpp is compiled byte-for-byte unchanged against these
+headers and must describe the same problem."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from ilqgames_b200 import _abi as abi, al, problems
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFERENCE = "/root/reference"
+SRC = os.path.join(REPO, "tests", "cpp", "host_api_test.cpp")
+
+
+def _build(tmp_path, lib_path, dropin=False):
+    exe = str(tmp_path / ("host_api_dropin" if dropin else "host_api_test"))
+    libdir, libfile = os.path.split(lib_path)
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-I" + os.path.join(REPO, "include"), SRC, "-o", exe,
+           "-L" + libdir, "-l" + libfile[3:-3], "-Wl,-rpath," + libdir]
+    if dropin:
+        cmd[5:5] = ["-DDROPIN_REFERENCE_EXAMPLE", "-I" + os.path.join(REFERENCE, "include"),
+                    os.path.join(REFERENCE, "src", "three_player_intersection_example.cpp")]
+    subprocess.run(cmd, check=True)
+    return exe
+
+
+def _run(exe, tmp_path):
+    out = str(tmp_path / "out.bin")
+    res = subprocess.run([exe, out], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "all checks passed" in res.stdout
+    arrays = {}
+    with open(out, "rb") as f:
+        while True:
+            line = f.readline()
+            if not line:
+                break
+            name, n = line.split()
+            arrays[name.decode()] = np.frombuffer(f.read(4 * int(n)), dtype=np.float32)
+    return arrays
+
+
+def _params(**over):
+    p = problems.three_player_intersection_params(**over)
+    return p
+
+
+def _flat_op(xs, us):
+    return np.concatenate([xs, us], axis=-1).reshape(-1)
+
+
+def _check_against_ctypes(lib, got, exact=True):
+    desc, x0 = problems.three_player_intersection()
+    # Problem -> descriptor: byte-identical to the Python builder
+    assert np.array_equal(np.frombuffer(bytes(desc), dtype=np.uint32), got["desc_own"].view(np.uint32))
+    assert np.array_equal(x0, got["x0_own"])
+    same = np.array_equal if exact else (lambda a, b: np.allclose(a, b, rtol=1e-3, atol=1e-3))
+
+    # ILQSolver::Solve, max_solver_iters = 4
+    h = abi.Handle(lib, desc, _params(max_solver_iters=4), 1, 0)
+    h.upload_x0(x0[None])
+    h.solve_begin()
+    h.solve(chunk=1)
+    assert int(got["ilq_num_iterates"][0]) == 1 + int(h.download(abi.ITERS)[0])
+    assert same(_flat_op(h.download(abi.XS)[0], h.download(abi.US)[0]), got["ilq_final_op"])
+    assert same(h.download(abi.TOTAL_COSTS)[0], got["ilq_total_costs"])
+    Ps, alphas = h.download(abi.PS)[0], h.download(abi.ALPHAS)[0]       # [T][M][n], [T][M]
+    T, M, n = Ps.shape
+    strat = []
+    for k in range(T):
+        for i in range(3):
+            strat += [Ps[k, 2 * i:2 * i + 2].reshape(-1), alphas[k, 2 * i:2 * i + 2]]
+    assert same(np.concatenate(strat), got["ilq_final_strategies"])
+
+    # SolveBatch games 1 and 2
+    x0s = np.tile(x0, (3, 1))
+    x0s[1, 0] += 1.0
+    x0s[2, 7] -= 2.0
+    hb = abi.Handle(lib, desc, _params(max_solver_iters=4), 3, 0)
+    hb.upload_x0(x0s)
+    hb.solve_begin()
+    hb.solve()
+    xs, us = hb.download(abi.XS), hb.download(abi.US)
+    assert same(_flat_op(xs[1], us[1]), got["batch_op_1"])
+    assert same(_flat_op(xs[2], us[2]), got["batch_op_2"])
+
+    # AugmentedLagrangianSolver::Solve, NumIterates cap 30
+    p = _params()
+    p.max_solver_iters = p.unconstrained_solver_max_iters
+    ha = abi.Handle(lib, desc, p, 1, 0)
+    ha.upload_x0(x0[None])
+    out = al.solve_augmented_lagrangian(ha, 30, p.constraint_error_tolerance)
+    inner_solves, iterates, success = got["al_stats"]
+    if exact:
+        assert (int(inner_solves), int(iterates), int(success)) == (out.rounds, int(out.iterates[0]), int(out.success[0]))
+    assert same(_flat_op(out.xs[0], out.us[0]), got["al_final_op"])
+    # SURVEY Appendix B known answer of the LQ test system
+    np.testing.assert_allclose(got["lq_P1_k0"], [0.915024, 1.632025], atol=2e-5)
+    np.testing.assert_allclose(got["lq_P2_k0"], [0.0145362, 0.0206234], atol=2e-5)
+
+
+def test_cpp_host_classes_on_the_oracle(oracle, tmp_path):
+    got = _run(_build(tmp_path, oracle.path), tmp_path)
+    _check_against_ctypes(oracle, got)
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference tree is not on this machine")
+def test_reference_example_source_drops_in_unchanged(oracle, tmp_path):
+    """north_star: 'an example like ThreePlayerIntersectionExample drops in unchanged'."""
+    got = _run(_build(tmp_path, oracle.path, dropin=True), tmp_path)
+    assert np.array_equal(got["desc_reference"].view(np.uint32), got["desc_own"].view(np.uint32))
+    assert np.array_equal(got["x0_reference"], got["x0_own"])
+    # and no reference header other than the example's own declaration took part in the build
+    deps = subprocess.run(["g++", "-std=c++17", "-I" + os.path.join(REPO, "include"),
+                           "-I" + os.path.join(REFERENCE, "include"), "-M",
+                           os.path.join(REFERENCE, "src", "three_player_intersection_example.cpp")],
+                          capture_output=True, text=True, check=True).stdout.split()
+    from_ref = sorted(d for d in deps if d.startswith(REFERENCE))
+    assert from_ref == [os.path.join(REFERENCE, "include/ilqgames/examples/three_player_intersection_example.h"),
+                        os.path.join(REFERENCE, "src/three_player_intersection_example.cpp")]
+
+
+@pytest.mark.gpu
+def test_cpp_host_classes_on_the_gpu(product, tmp_path):
+    got = _run(_build(tmp_path, product.path), tmp_path)
+    _check_against_ctypes(product, got, exact=True)
