@@ -18,7 +18,13 @@
 #pragma once
 #include "ilqg_records.cuh"
 
+#ifndef ILQG_MM_UNROLL
+#define ILQG_MM_UNROLL 4
+#endif
+
 namespace ilqg {
+
+constexpr int kMmUnroll = ILQG_MM_UNROLL;
 
 __host__ __device__ constexpr int r4(int v) { return (v + 3) & ~3; }
 
@@ -85,7 +91,10 @@ __device__ __forceinline__ void mm_tn(const float* __restrict__ X, int ldx, cons
   for (int i = 0; i < TR; i++)
 #pragma unroll
     for (int j = 0; j < TC; j++) acc[i][j] = 0.f;
-#pragma unroll
+  // partially unrolled: the kernel is instruction-fetch sensitive (stall_no_instruction in
+  // profiles/r01_lq_backward.md); ILQG_MM_UNROLL q-steps per loop trip keep 2 x ILQG_MM_UNROLL
+  // 128-bit loads in flight
+#pragma unroll kMmUnroll
   for (int q = 0; q < QN; q++) {
     float xr[TR], yr[TC];
     ldvec<TR>(X + q * ldx, xr);

@@ -8,9 +8,15 @@
 #include <ilqgames/b200/eigen_shim.h>
 #include <ilqgames/b200/log_shim.h>
 
+#include <sys/stat.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
+#include <fstream>
+#include <iomanip>
+#include <sstream>
 #include <limits>
 #include <memory>
 #include <string>
@@ -145,7 +151,7 @@ struct QuadraticCostApproximation {
   explicit QuadraticCostApproximation(Dimension xdim, float regularization = 0.0) : state(xdim, regularization) {}
 };
 
-// ---- include/ilqgames/utils/solver_log.h:60-175 (in-memory part; Save() is out of scope) -----
+// ---- include/ilqgames/utils/solver_log.h:60-175, src/solver_log.cpp:113-171 -------------------
 class SolverLog {
  public:
   SolverLog() {}
@@ -187,7 +193,66 @@ class SolverLog {
   }
   Time IndexToTime(size_t idx) const { return InitialTime() + time::kTimeStep * static_cast<Time>(idx); }
 
+  // The reference's on-disk format (src/solver_log.cpp:113-171): one directory per iterate under
+  // <log dir>/<experiment_name>/ holding t0.txt, xs.txt (one state per line), u<player>.txt (one
+  // control per line), costs.txt (one total cost per line) and cumulative_runtimes.txt.  Rows are
+  // written like Eigen prints a transposed vector: default stream precision, single-space
+  // separated, every entry right-aligned to the widest one.  The log directory is the
+  // reference's compile-time ILQGAMES_LOG_DIR; here the environment variable of that name, or
+  // "logs".
+  bool Save(bool only_last_trajectory = false, const std::string& experiment_name = "experiment") const {
+    const char* env = std::getenv("ILQGAMES_LOG_DIR");
+    const std::string root = env ? env : "logs";
+    const std::string dir_name = root + "/" + experiment_name;
+    if (!MakeDirectory(root) || !MakeDirectory(dir_name)) return false;
+    size_t start = 0;
+    if (only_last_trajectory) start = operating_points_.size() - 1;
+    for (size_t ii = start; ii < operating_points_.size(); ii++) {
+      const OperatingPoint& op = operating_points_[ii];
+      const std::string sub = dir_name + "/" + std::to_string(ii);
+      if (!MakeDirectory(sub)) return false;
+      std::ofstream file(sub + "/t0.txt");
+      file << op.t0 << std::endl;
+      file.close();
+      file.open(sub + "/xs.txt");
+      for (const VectorXf& x : op.xs) file << Row(x) << std::endl;
+      file.close();
+      file.open(sub + "/costs.txt");
+      for (float c : total_player_costs_[ii]) file << c << std::endl;
+      file.close();
+      file.open(sub + "/cumulative_runtimes.txt");
+      file << cumulative_runtimes_[ii] << std::endl;
+      file.close();
+      for (PlayerIndex jj = 0; jj < NumPlayers(); jj++) {
+        file.open(sub + "/u" + std::to_string(jj) + ".txt");
+        for (size_t kk = 0; kk < op.us.size(); kk++) file << Row(op.us[kk][jj]) << std::endl;
+        file.close();
+      }
+      if (!file) return false;
+    }
+    return true;
+  }
+
  private:
+  static bool MakeDirectory(const std::string& name) {
+    struct stat st;
+    if (stat(name.c_str(), &st) == 0) return S_ISDIR(st.st_mode);
+    return mkdir(name.c_str(), 0777) == 0;
+  }
+  static std::string Row(const VectorXf& v) {
+    std::vector<std::string> cells;
+    size_t width = 0;
+    for (long a = 0; a < v.size(); a++) {
+      std::ostringstream os;
+      os << v(a);
+      cells.push_back(os.str());
+      width = std::max(width, cells.back().size());
+    }
+    std::ostringstream row;
+    for (size_t a = 0; a < cells.size(); a++) row << (a ? " " : "") << std::setw((int)width) << cells[a];
+    return row.str();
+  }
+
   std::vector<OperatingPoint> operating_points_;
   std::vector<std::vector<Strategy>> strategies_;
   std::vector<std::vector<float>> total_player_costs_;

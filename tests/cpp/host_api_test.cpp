@@ -178,6 +178,9 @@ void TestILQSolver(const std::shared_ptr<Problem>& problem) {
   Dump("ilq_final_op", Flatten(log->FinalOperatingPoint()));
   Dump("ilq_final_strategies", Flatten(log->FinalStrategies()));
   Dump("ilq_total_costs", log->TotalCosts());
+  // SolverLog::Save: the reference's text format (src/solver_log.cpp:113-171) under $ILQGAMES_LOG_DIR
+  EXPECT(log->Save(false, "host_api_test"));
+  EXPECT(log->Save(true, "host_api_test_last"));
   std::printf("ILQSolver::Solve: %zu iterates, success = %d, total costs = [%.4f %.4f %.4f]\n", log->NumIterates(),
               (int)success, log->TotalCosts()[0], log->TotalCosts()[1], log->TotalCosts()[2]);
 

@@ -34,7 +34,8 @@ def _build(tmp_path, lib_path, dropin=False):
 
 def _run(exe, tmp_path):
     out = str(tmp_path / "out.bin")
-    res = subprocess.run([exe, out], capture_output=True, text=True)
+    env = dict(os.environ, ILQGAMES_LOG_DIR=str(tmp_path / "logs"))
+    res = subprocess.run([exe, out], capture_output=True, text=True, env=env)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "all checks passed" in res.stdout
     arrays = {}
@@ -107,9 +108,32 @@ def _check_against_ctypes(lib, got, exact=True):
     np.testing.assert_allclose(got["lq_P2_k0"], [0.0145362, 0.0206234], atol=2e-5)
 
 
+def _check_saved_log(tmp_path, got):
+    """SolverLog::Save, the reference's on-disk format (src/solver_log.cpp:113-171)."""
+    root = tmp_path / "logs" / "host_api_test"
+    n_iter = int(got["ilq_num_iterates"][0])
+    assert sorted(os.listdir(root), key=int) == [str(i) for i in range(n_iter)]
+    last = root / str(n_iter - 1)
+    assert sorted(os.listdir(last)) == ["costs.txt", "cumulative_runtimes.txt", "t0.txt", "u0.txt", "u1.txt",
+                                        "u2.txt", "xs.txt"]
+    op = got["ilq_final_op"].reshape(100, 22)
+    xs = np.loadtxt(last / "xs.txt")
+    us = np.concatenate([np.loadtxt(last / f"u{i}.txt") for i in range(3)], axis=1)
+    np.testing.assert_allclose(xs, op[:, :16], rtol=6e-6, atol=1e-30)   # 6 significant digits
+    np.testing.assert_allclose(us, op[:, 16:], rtol=6e-6, atol=1e-30)
+    np.testing.assert_allclose(np.loadtxt(last / "costs.txt"), got["ilq_total_costs"], rtol=6e-6)
+    assert float(open(last / "t0.txt").read()) == 0.0
+    assert os.listdir(tmp_path / "logs" / "host_api_test_last") == [str(n_iter - 1)]
+    # Eigen-style row: single-space separated, every cell padded to the widest
+    first = open(last / "xs.txt").readline().rstrip("\n")
+    cells = first.split()
+    assert len(first) == len(cells) * max(map(len, cells)) + len(cells) - 1
+
+
 def test_cpp_host_classes_on_the_oracle(oracle, tmp_path):
     got = _run(_build(tmp_path, oracle.path), tmp_path)
     _check_against_ctypes(oracle, got)
+    _check_saved_log(tmp_path, got)
 
 
 @pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference tree is not on this machine")

@@ -1,7 +1,9 @@
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench18.json 2>gpurun_out/bench18.err; python - <<PY
+cp ilqgames_b200/lib/libilqg_b200.so /tmp/orig.so
+for u in 2 4 8 16; do cp ilqgames_b200/lib/variants/libilqg_b200_u$u.so ilqgames_b200/lib/libilqg_b200.so
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench19.json 2>gpurun_out/bench19.err; python - <<PY
 import json
-d=json.load(open("gpurun_out/bench18.json"))
-print(round(d["value"]), round(d["ms_per_step"],2), round(d["e2e"]["value"]), d["clocks"], {k:round(v["ms_per_launch"],3) for k,v in d["roofline"]["kernels"].items()})
+d=json.load(open("gpurun_out/bench19.json"))
+print("u$u", round(d["value"]), round(d["ms_per_step"],2), {k:round(v["ms_per_launch"],3) for k,v in d["roofline"]["kernels"].items() if k in ("lq_backward","linearize_quadraticize","ls_eval_fresh")})
 PY
-export ILQG_GROUPS=1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ls_eval -s 1 -c 1 -f -o gpurun_out/r01c_k_ls_eval_fresh python tools/profile_target.py 4096 3 > gpurun_out/ncu_r01c.log 2>&1
+done
+cp /tmp/orig.so ilqgames_b200/lib/libilqg_b200.so
