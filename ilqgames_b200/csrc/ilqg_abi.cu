@@ -30,6 +30,11 @@ struct SubSolver {
   int B;
   cudaStream_t stream;      // the stream work is issued on
   cudaStream_t own_stream;  // created with the handle
+  // pipelined iteration: the open linesearches of pass i finish on `side` while `stream` already
+  // linearizes / solves pass i + 1 for everyone else (IteratePipelined)
+  cudaStream_t side;
+  cudaEvent_t ev_fresh, ev_side;
+  int pipeline;  // 0 off, 1 = K_lq + K_bwd of the queue on the side stream, 2 = K_lq only
   std::vector<void*> allocs;
   // per-kernel event timing (ilqg_profile)
   bool profiling;
@@ -284,7 +289,7 @@ int SetSmem(K kernel, size_t bytes) {
 }
 
 template <int NX, int MU, int NP>
-int LaunchBackward(SubSolver* h, int only_running) {
+int LaunchBackward(SubSolver* h, int only_running, Sel) {
   const size_t smem = sizeof(float) * KBWD_WARPS * (size_t)(BwdSmem<NX, MU, NP>::rec + h->d.rec);
   int rc = SetSmem(k_lq_backward<NX, MU, NP>, smem);
   if (rc != ILQG_OK) return rc;
@@ -297,7 +302,7 @@ int LaunchBackward(SubSolver* h, int only_running) {
 }
 
 template <int NX, int MU, int NP>
-int LaunchBackwardHw(SubSolver* h, int only_running) {
+int LaunchBackwardHw(SubSolver* h, int only_running, Sel sel) {
   const size_t per_inst = HwSmem<NX, MU, NP>::lrr + (h->d.rec - h->d.offl);
   const size_t smem = sizeof(float) * KHW_WARPS * 2 * per_inst;
   int rc = SetSmem(k_lq_backward_hw<NX, MU, NP>, smem);
@@ -305,7 +310,7 @@ int LaunchBackwardHw(SubSolver* h, int only_running) {
   const int per_block = KHW_WARPS * 2;
   ProfScope prof(h, 1);
   k_lq_backward_hw<NX, MU, NP><<<(h->B + per_block - 1) / per_block, KHW_WARPS * 32, smem, h->stream>>>(
-      h->d, h->p, h->s, only_running);
+      h->d, h->p, h->s, only_running, sel);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   return ILQG_OK;
@@ -313,15 +318,15 @@ int LaunchBackwardHw(SubSolver* h, int only_running) {
 
 // with_dxs: also produce ILQG_DELTA_XS (an optional output of LQFeedbackSolver::Solve that the
 // iLQ loop itself never reads once ExpectedDecrease is fused into the backward sweep)
-int DispatchBackward(SubSolver* h, int only_running, bool with_dxs) {
+int DispatchBackward(SubSolver* h, int only_running, bool with_dxs, Sel sel = Sel{SEL_ALL, nullptr, nullptr}) {
   int rc = ILQG_ERR_UNSUPPORTED;
   bool hw = true;
   switch (h->dims_key) {
-    case 0: rc = LaunchBackwardHw<16, 6, 3>(h, only_running); break;
-    case 1: rc = LaunchBackwardHw<24, 8, 4>(h, only_running); break;
-    case 2: rc = LaunchBackward<3, 2, 2>(h, only_running); hw = false; break;
-    case 3: rc = LaunchBackward<2, 2, 2>(h, only_running); hw = false; break;
-    case 4: rc = LaunchBackwardHw<12, 6, 3>(h, only_running); break;
+    case 0: rc = LaunchBackwardHw<16, 6, 3>(h, only_running, sel); break;
+    case 1: rc = LaunchBackwardHw<24, 8, 4>(h, only_running, sel); break;
+    case 2: rc = LaunchBackward<3, 2, 2>(h, only_running, sel); hw = false; break;
+    case 3: rc = LaunchBackward<2, 2, 2>(h, only_running, sel); hw = false; break;
+    case 4: rc = LaunchBackwardHw<12, 6, 3>(h, only_running, sel); break;
   }
   if (rc == ILQG_OK && hw && with_dxs) {
     k_delta_xs<<<(h->B + 3) / 4, 128, sizeof(float) * 4 * 2 * ILQG_MAX_XDIM, h->stream>>>(h->d, h->s);
@@ -433,7 +438,7 @@ int BuildRecordPattern(SubSolver* h) {
   return ILQG_OK;
 }
 
-int LaunchLqRecords(SubSolver* h, int only_running) {
+int LaunchLqRecords(SubSolver* h, int only_running, Sel sel = Sel{SEL_ALL, nullptr, nullptr}) {
   const DevDesc& d = h->d;
   if (h->pat_ok) {
     const size_t smem3 = klq_smem_bytes(d.n, d.M, d.N, h->pat.E, d.rec, h->pat.num_items, h->pat.num_idx);
@@ -441,7 +446,7 @@ int LaunchLqRecords(SubSolver* h, int only_running) {
     if (rc3 != ILQG_OK) return rc3;
     const long long recs = (long long)h->B * d.T;
     ProfScope prof(h, 0);
-    k_linearize_quadraticize_v3<<<(int)((recs + 31) / 32), (d.N + 1) * 32, smem3, h->stream>>>(h->d, h->s, h->pat, only_running);
+    k_linearize_quadraticize_v3<<<(int)((recs + 31) / 32), (d.N + 1) * 32, smem3, h->stream>>>(h->d, h->s, h->pat, only_running, sel);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return ILQG_OK;
@@ -483,12 +488,11 @@ int LaunchLsEval(SubSolver* h, int mode, int blocks, int q_offset) {
 
 // ILQSolver::ModifyLQStrategies for the whole batch (ilqg_linesearch.cuh): the first window for
 // everyone, then the remaining candidates for the instances that rejected it, chunk by chunk.
-int LaunchLinesearch(SubSolver* h) {
+// first window: candidate j = 0 for every running instance; rejections are appended to a queue
+int LaunchLinesearchFresh(SubSolver* h) {
   const int B = h->B;
   int rc;
-  ProfScope prof(h, 2);
   const int dec_blocks = (B + KDEC_WARPS - 1) / KDEC_WARPS;
-  // fresh window: unresolved instances are appended to queue 1 - ls_cur
   CUDA_TRY(cudaMemsetAsync(h->ls.counts + (1 - h->ls_cur), 0, sizeof(int), h->stream));
   if ((rc = LaunchLsEval(h, LS_MODE_FRESH, h->ls.nA_blocks, 0)) != ILQG_OK) return rc;
   {
@@ -497,12 +501,20 @@ int LaunchLinesearch(SubSolver* h) {
   }
   h->launches++;
   h->ls_cur = 1 - h->ls_cur;  // the queue just filled is now the one to drain
+  CUDA_TRY(cudaGetLastError());
+  return ILQG_OK;
+}
+
+// the remaining candidates of the queued instances, window after window
+int LaunchLinesearchQueued(SubSolver* h) {
+  const int B = h->B;
+  int rc;
   if (h->p.linesearch && h->ls.JB > 0) {
     const int cap = h->ls.cap;
     const int qblocks = (int)(((long long)cap * h->ls.JB + h->ls.lpw - 1) / h->ls.lpw);
     const int remaining = std::max(1, h->p.max_backtracking_steps) - h->ls.JA;
-    // window after window over the queue; instances whose window ended without an accept AND
-    // whose last rollout was not "absorbed" (ilqg_linesearch.cuh) move on to the other queue
+    // instances whose window ended without an accept AND whose last rollout was not "absorbed"
+    // (ilqg_linesearch.cuh) move on to the other queue
     for (int done = 0; done < remaining; done += h->ls.JB) {
       CUDA_TRY(cudaMemsetAsync(h->ls.counts + (1 - h->ls_cur), 0, sizeof(int), h->stream));
       for (int q0 = 0; q0 < B; q0 += cap) {
@@ -518,6 +530,51 @@ int LaunchLinesearch(SubSolver* h) {
     }
   }
   CUDA_TRY(cudaGetLastError());
+  return ILQG_OK;
+}
+
+// ILQSolver::ModifyLQStrategies for the whole batch (ilqg_linesearch.cuh)
+int LaunchLinesearch(SubSolver* h) {
+  int rc;
+  ProfScope prof(h, 2);
+  if ((rc = LaunchLinesearchFresh(h)) != ILQG_OK) return rc;
+  return LaunchLinesearchQueued(h);
+}
+
+// n iterations with the open linesearches of pass i overlapped with K_lq / K_bwd of pass i + 1:
+//   main: K_lq, K_bwd (everyone but the instances queued in pass i-1) | wait side | first window
+//   side:                         wait first window | remaining windows, K_lq + K_bwd over the queue
+// Every instance still completes exactly one iteration per pass; only the order in which the two
+// groups are processed inside a pass changes.
+int IteratePipelined(SubSolver* h, int n) {
+  int rc;
+  cudaStream_t main = h->stream;
+  bool side_busy = false;
+  for (int it = 0; it < n; it++) {
+    const Sel all{SEL_ALL, nullptr, nullptr};
+    const Sel sel = it > 0 ? Sel{SEL_MAIN, nullptr, nullptr} : all;
+    const bool bwd_on_side = h->pipeline == 1;
+    if ((rc = LaunchLqRecords(h, 1, sel)) != ILQG_OK) return rc;
+    if (!bwd_on_side && side_busy) CUDA_TRY(cudaStreamWaitEvent(main, h->ev_side, 0));
+    if ((rc = DispatchBackward(h, 1, false, bwd_on_side ? sel : all)) != ILQG_OK) return rc;
+    if (bwd_on_side && side_busy) CUDA_TRY(cudaStreamWaitEvent(main, h->ev_side, 0));
+    if ((rc = LaunchLinesearchFresh(h)) != ILQG_OK) return rc;
+    const int q_first = h->ls_cur;  // the queue the first window just filled
+    CUDA_TRY(cudaEventRecord(h->ev_fresh, main));
+    CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_fresh, 0));
+    h->stream = h->side;
+    rc = LaunchLinesearchQueued(h);
+    if (rc == ILQG_OK && it + 1 < n) {
+      const Sel list{SEL_LIST, h->ls.pend[q_first], h->ls.counts + q_first};
+      rc = LaunchLqRecords(h, 1, list);
+      if (rc == ILQG_OK && h->pipeline == 1) rc = DispatchBackward(h, 1, false, list);
+    }
+    h->stream = main;
+    if (rc != ILQG_OK) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev_side, h->side));
+    side_busy = true;
+  }
+  if (side_busy) CUDA_TRY(cudaStreamWaitEvent(main, h->ev_side, 0));
   return ILQG_OK;
 }
 
@@ -681,6 +738,9 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
   h->profiling = false;
   h->stream = nullptr;
   h->own_stream = nullptr;
+  h->side = nullptr;
+  h->ev_fresh = h->ev_side = nullptr;
+  h->pipeline = 0;
   for (int k = 0; k < 8; k++) { h->prof_ms[k] = 0; h->prof_n[k] = 0; }
   DevParams& p = h->p;
   p.convergence_tolerance = params->convergence_tolerance;
@@ -714,6 +774,13 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
     ilqg_destroy(h);
     return code;
   };
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  const bool side_high = std::getenv("ILQG_SIDE_PRIORITY") && std::atoi(std::getenv("ILQG_SIDE_PRIORITY")) != 0;
+  if (cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, side_high ? prio_hi : prio_lo) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fresh, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming) != cudaSuccess)
+    return fail(ILQG_ERR_CUDA);
 #define ALLOC(ptr, count)                                          \
   if ((rc = DevAlloc(h, &(ptr), (count))) != ILQG_OK) return fail(rc)
   ALLOC(s.x0, B * n);
@@ -742,6 +809,7 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
   ALLOC(s.al_iterates, B);
   ALLOC(s.al_success, B);
   ALLOC(s.al_flags, B);
+  ALLOC(s.queued_flag, B);
   ALLOC(s.backtracks, B);
   ALLOC(s.te_quad, B * N);
   ALLOC(s.te_new, B * N);
@@ -766,6 +834,8 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
     if (const char* e = std::getenv("ILQG_LS_JB")) JB = std::max(0, std::min(max_bt - JA, std::atoi(e)));
     int cap = (int)std::max<size_t>(1, (B + 1) / 2);
     if (const char* e = std::getenv("ILQG_LS_CAP")) cap = std::max(1, std::min<int>((int)B, std::atoi(e)));
+    h->pipeline = 2;  // measured: 2 > 0 > 1 (profiles/r01_summary.md)
+    if (const char* e = std::getenv("ILQG_PIPELINE")) h->pipeline = std::atoi(e);
     ls.JA = JA;
     ls.JB = JB;
     ls.cap = cap;
@@ -813,6 +883,9 @@ int ilqg_destroy(SubHandle h) {
   if (!h) return ILQG_ERR_BAD_HANDLE;
   Guard guard(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_fresh) cudaEventDestroy(h->ev_fresh);
+  if (h->ev_side) cudaEventDestroy(h->ev_side);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   for (auto& sm : h->samples) {
     cudaEventDestroy(sm.a);
@@ -927,10 +1000,18 @@ int ilqg_linesearch(SubHandle h) {
 int ilqg_iterate(SubHandle h, int max_iters, int* iters_done) {
   ENTER(h);
   int rc;
-  for (int it = 0; it < max_iters; it++) {
-    if ((rc = LaunchLqRecords(h, 1)) != ILQG_OK) return rc;
-    if ((rc = DispatchBackward(h, 1, false)) != ILQG_OK) return rc;
-    if ((rc = LaunchLinesearch(h)) != ILQG_OK) return rc;
+  // the pipelined schedule needs the list-capable kernels (static K_lq, half-warp K_bwd) and a
+  // single queued window; per-kernel profiling wants every kernel alone on the device
+  const bool hw = h->dims_key == 0 || h->dims_key == 1 || h->dims_key == 4;
+  const bool one_window = h->ls.JB >= std::max(1, h->p.max_backtracking_steps) - h->ls.JA;
+  if (h->pipeline && max_iters > 1 && h->pat_ok && hw && one_window && h->p.linesearch && !h->profiling) {
+    if ((rc = IteratePipelined(h, max_iters)) != ILQG_OK) return rc;
+  } else {
+    for (int it = 0; it < max_iters; it++) {
+      if ((rc = LaunchLqRecords(h, 1)) != ILQG_OK) return rc;
+      if ((rc = DispatchBackward(h, 1, false)) != ILQG_OK) return rc;
+      if ((rc = LaunchLinesearch(h)) != ILQG_OK) return rc;
+    }
   }
   if (iters_done) {
     std::vector<int> iters(h->B);
@@ -1345,10 +1426,16 @@ int ilqg_iterate(ilqg_handle h, int max_iters, int* iters_done) {
   if (!guard.ok) return ILQG_ERR_CUDA;
   int rc = Fork(h);
   if (rc != ILQG_OK) return rc;
-  // iteration-major, group-minor issue order so the groups' kernels interleave in the hardware queues
-  for (int it = 0; it < max_iters; it++)
+  if (h->subs[0]->pipeline && max_iters > 1) {
+    // each group runs its own two-stream pipeline (sub::IteratePipelined)
     for (SubSolver* g : h->subs)
-      if ((rc = sub::ilqg_iterate(g, 1, nullptr)) != ILQG_OK) return rc;
+      if ((rc = sub::ilqg_iterate(g, max_iters, nullptr)) != ILQG_OK) return rc;
+  } else {
+    // iteration-major, group-minor issue order so the groups' kernels interleave in the hardware queues
+    for (int it = 0; it < max_iters; it++)
+      for (SubSolver* g : h->subs)
+        if ((rc = sub::ilqg_iterate(g, 1, nullptr)) != ILQG_OK) return rc;
+  }
   if ((rc = Join(h)) != ILQG_OK) return rc;
   if (iters_done) {
     int most = 0;

@@ -190,7 +190,7 @@ __device__ __forceinline__ void lu_solve(float (&Sm)[MU][MU], float (&y)[G][MU],
 
 template <int NX, int MU, int NP>
 __global__ void __launch_bounds__(KHW_WARPS * 32, HwSmem<NX, MU, NP>::min_blocks)
-k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, int only_running) {
+k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, int only_running, Sel sel) {
   using L = HwSmem<NX, MU, NP>;
   constexpr int m = L::m;
   constexpr int TR = NX / 4, TC = NX / 4;   // Z tile per lane (16 lanes cover NX x NX)
@@ -207,9 +207,8 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
   const int lrr_floats = d.rec - d.offl, lrr4 = lrr_floats / 4;
   const int per_inst = L::lrr + lrr_floats;
 
-  const int b_own = (blockIdx.x * KHW_WARPS + warp) * 2 + half;
-  bool active = b_own < s.B;
-  if (active && only_running) active = instance_iterates(s, b_own);
+  bool active = false;
+  const int b_own = sel_instance(s, sel, (blockIdx.x * KHW_WARPS + warp) * 2 + half, only_running, &active);
   const unsigned act_mask = __ballot_sync(0xffffffffu, active);
   if (act_mask == 0) return;
   // an inactive half shadows its partner (valid loads, no stores) so the warp stays convergent

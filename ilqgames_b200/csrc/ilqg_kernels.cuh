@@ -35,6 +35,7 @@ struct Slab {
   // AugmentedLagrangianSolver::Solve per game (ilqg_al_begin / ilqg_al_advance):
   int *al_state, *al_iterates, *al_success;  // state 0 none, 1 active, 2 finished (solve_begin skips it)
   int* al_flags;                    // [B] scratch of one ilqg_al_advance: AL_DO_* bits
+  int* queued_flag;                 // [B] 1 = this pass's first-window candidate was rejected (set by k_ls_decide)
   const int* lambda_index;          // [T]  kk -> Constraint::TimeIndex
 };
 
@@ -44,6 +45,34 @@ __device__ __forceinline__ int round4(int v) { return (v + 3) & ~3; }
 // is not in the middle of a linesearch (ilqg_linesearch.cuh)
 __device__ __forceinline__ bool instance_iterates(const Slab& s, int b) {
   return s.status[b] == ILQG_STATUS_RUNNING && s.ls_next_j[b] == 0;
+}
+
+// Which instances a K_lq / K_bwd launch covers.  The pipelined iteration (ilqg_abi.cu:
+// IteratePipelined) splits a pass in two streams: the instances whose linesearch is still open
+// (the "queued" ones, a few percent) finish it, then get their own K_lq / K_bwd over the queue
+// list, while the rest of the batch is already linearized / solved for the next iteration.
+enum { SEL_ALL = 0, SEL_MAIN = 1, SEL_LIST = 2 };
+struct Sel {
+  int mode;
+  const int* list;   // SEL_LIST: instance ids
+  const int* count;  // SEL_LIST: valid entries
+};
+
+// slot -> instance id (or -1), and whether that instance takes part in this launch
+__device__ __forceinline__ int sel_instance(const Slab& s, const Sel& sel, int slot, int only_running, bool* live) {
+  int b = -1;
+  *live = false;
+  if (sel.mode == SEL_LIST) {
+    if (slot < *sel.count) {
+      b = sel.list[slot];
+      *live = instance_iterates(s, b);
+    }
+  } else if (slot < s.B) {
+    b = slot;
+    *live = !only_running || instance_iterates(s, b);
+    if (sel.mode == SEL_MAIN && s.queued_flag[b]) *live = false;
+  }
+  return b;
 }
 
 // ===========================================================================

@@ -471,6 +471,7 @@ k_ls_decide(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScra
       if (with_merit) s.last_merit[b] = acc_merit;
       s.step[b] = step;
       s.ls_next_j[b] = 0;
+      if (fresh) s.queued_flag[b] = 0;
       if (converged && !p.disable_convergence_exit)
         s.status[b] = ILQG_STATUS_CONVERGED;
       else if (itn >= p.max_solver_iters)
@@ -486,6 +487,7 @@ k_ls_decide(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScra
       s.ls_next_j[b] = 0;
     } else {
       s.ls_next_j[b] = jn;
+      s.queued_flag[b] = 1;
       const int q = atomicAdd(&ls.counts[1 - cur_q], 1);
       ls.pend[1 - cur_q][q] = b;
       ls.slot[b] = q;

@@ -146,7 +146,7 @@ __host__ __device__ inline size_t klq_smem_bytes(int n, int M, int N, int E, int
 }
 
 __global__ void __launch_bounds__(160)
-k_linearize_quadraticize_v3(const __grid_constant__ DevDesc d, Slab s, RecordPattern pat, int only_running) {
+k_linearize_quadraticize_v3(const __grid_constant__ DevDesc d, Slab s, RecordPattern pat, int only_running, Sel sel) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = d.n, M = d.M, N = d.N, T = d.T, NR = N + 1, E = pat.E;
@@ -165,9 +165,10 @@ k_linearize_quadraticize_v3(const __grid_constant__ DevDesc d, Slab s, RecordPat
   const long long first = (long long)blockIdx.x * 32;
   const long long total = (long long)s.B * T;
   const long long w = first + lane;
-  const bool in_range = w < total;
-  const int b = in_range ? (int)(w / T) : 0, k = in_range ? (int)(w % T) : 0;
-  const bool live = in_range && (!only_running || instance_iterates(s, b));
+  bool live = false;
+  const int b_sel = w < total ? sel_instance(s, sel, (int)(w / T), only_running, &live) : -1;
+  const bool in_range = b_sel >= 0;
+  const int b = in_range ? b_sel : 0, k = in_range ? (int)(w % T) : 0;
   if (!__syncthreads_or(live)) return;
 
   // ---- block prologue: x, u of the 32 records; gather table; per-warp template copy ----
@@ -226,7 +227,7 @@ k_linearize_quadraticize_v3(const __grid_constant__ DevDesc d, Slab s, RecordPat
   __syncthreads();
   // xu is dead: reuse its first 32 words as the per-record "assemble me" flags
   int* flags = reinterpret_cast<int*>(xu);
-  if (warp == 0) flags[lane] = live ? 1 : 0;
+  if (warp == 0) flags[lane] = live ? b + 1 : 0;  // 0 = skip, else instance id + 1
   __syncthreads();
 
   // ---- phase 2: warp w assembles records w, w + NR, ... on top of its template copy ----
@@ -254,7 +255,8 @@ k_linearize_quadraticize_v3(const __grid_constant__ DevDesc d, Slab s, RecordPat
       rec[g_off[g]] = acc;
     }
     __syncwarp();
-    float4* dst = reinterpret_cast<float4*>(s.rec + (size_t)wr * d.rec);
+    // (the instance need not be slot wr / T: SEL_LIST maps slots through the queue list)
+    float4* dst = reinterpret_cast<float4*>(s.rec + ((size_t)(flags[r] - 1) * T + (size_t)(wr % T)) * d.rec);
     const float4* src = reinterpret_cast<const float4*>(rec);
     for (int e = lane; e < d.rec / 4; e += 32) dst[e] = src[e];
     __syncwarp();

@@ -1,9 +1,6 @@
-cp ilqgames_b200/lib/libilqg_b200.so /tmp/orig.so
-for u in 2 4 8 16; do cp ilqgames_b200/lib/variants/libilqg_b200_u$u.so ilqgames_b200/lib/libilqg_b200.so
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench19.json 2>gpurun_out/bench19.err; python - <<PY
+for cfg in "0 0 4" "1 1 4" "2 0 4" "2 1 4" "2 1 1" "2 1 2" "1 1 2"; do set -- $cfg; ILQG_PIPELINE=$1 ILQG_SIDE_PRIORITY=$2 ILQG_GROUPS=$3 python bench.py --steps 10 --warmup 3 > gpurun_out/bench22.json 2>gpurun_out/bench22.err; python - <<PY
 import json
-d=json.load(open("gpurun_out/bench19.json"))
-print("u$u", round(d["value"]), round(d["ms_per_step"],2), {k:round(v["ms_per_launch"],3) for k,v in d["roofline"]["kernels"].items() if k in ("lq_backward","linearize_quadraticize","ls_eval_fresh")})
+d=json.load(open("gpurun_out/bench22.json"))
+print("pipeline/prio/groups $cfg", round(d["value"]), round(d["ms_per_step"],2), d["config"]["status_histogram_rank0"])
 PY
 done
-cp /tmp/orig.so ilqgames_b200/lib/libilqg_b200.so
