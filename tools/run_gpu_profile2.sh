@@ -1,6 +1,3 @@
-export ILQG_GROUPS=1
-for k in k_ls_eval:1:fresh k_ls_eval:2:queued; do
-  IFS=: read name skip tag <<< "$k"
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$name -s $skip -c 1 -f -o gpurun_out/r01b_${name}_$tag python tools/profile_target.py 4096 3 > gpurun_out/ncu_r01b_${name}_$tag.log 2>&1
-done
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+export ILQG_GROUPS=1 ILQG_PIPELINE=0
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ls_eval -s 11 -c 1 -f -o gpurun_out/r01d_k_ls_eval_queued python tools/profile_target.py 4096 5 > gpurun_out/ncu_r01d.log 2>&1
+tail -3 gpurun_out/ncu_r01d.log

@@ -1,6 +1,6 @@
-for cfg in "0 0 4" "1 1 4" "2 0 4" "2 1 4" "2 1 1" "2 1 2" "1 1 2"; do set -- $cfg; ILQG_PIPELINE=$1 ILQG_SIDE_PRIORITY=$2 ILQG_GROUPS=$3 python bench.py --steps 10 --warmup 3 > gpurun_out/bench22.json 2>gpurun_out/bench22.err; python - <<PY
+for cfg in "1 4096" "2 4096" "3 4096" "4 4096"; do set -- $cfg; ILQG_LS_JA=$1 python bench.py --steps 10 --warmup 3 > gpurun_out/bench23.json 2>gpurun_out/bench23.err; python - <<PY
 import json
-d=json.load(open("gpurun_out/bench22.json"))
-print("pipeline/prio/groups $cfg", round(d["value"]), round(d["ms_per_step"],2), d["config"]["status_histogram_rank0"])
+d=json.load(open("gpurun_out/bench23.json"))
+print("JA $1", round(d["value"]), round(d["ms_per_step"],2), d["config"]["status_histogram_rank0"], round(d["config"]["mean_rollouts_per_iteration"],2), {k:round(v["ms_per_launch"],3) for k,v in d["roofline"]["kernels"].items() if k.startswith("ls_")})
 PY
 done
