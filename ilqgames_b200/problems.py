@@ -200,11 +200,42 @@ def three_player_intersection_x0_batch(batch: int, seed: int) -> np.ndarray:
 # --------------------------------------------------------------------------
 # RoundaboutMergingExample
 # --------------------------------------------------------------------------
+def _libm():
+    """The C library's float math: std::cos(float) etc. in the reference are cosf/sinf/atan2f, which
+    are not correctly rounded, so rounding a double result to fp32 differs from them in the last
+    bit now and then (caught by tests/golden/make_ref_golden.py:check_polylines)."""
+    import ctypes
+    import ctypes.util
+    global _LIBM
+    if _LIBM is None:
+        _LIBM = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+        for name, nargs in (("cosf", 1), ("sinf", 1), ("atan2f", 2)):
+            fn = getattr(_LIBM, name)
+            fn.restype = ctypes.c_float
+            fn.argtypes = [ctypes.c_float] * nargs
+    return _LIBM
+
+
+_LIBM = None
+
+
+def _cosf(a) -> np.float32:
+    return F(_libm().cosf(float(F(a))))
+
+
+def _sinf(a) -> np.float32:
+    return F(_libm().sinf(float(F(a))))
+
+
+def _atan2f(y, x) -> np.float32:
+    return F(_libm().atan2f(float(F(y)), float(F(x))))
+
+
 def roundabout_lane_center(entrance_angle, exit_angle, distance_from_roundabout):
     """RoundaboutLaneCenter, src/roundabout_lane_center.cpp:50-108 (fp32 arithmetic)."""
     kR, kH = F(12.0), F(2.5)
     ea, xa, dist = F(entrance_angle), F(exit_angle), F(distance_from_roundabout)
-    cos, sin = (lambda a: F(math.cos(float(a)))), (lambda a: F(math.sin(float(a))))
+    cos, sin = _cosf, _sinf
     cx, cy = (kR + kH) * cos(ea), (kR + kH) * sin(ea)
     first_angle = F(float(ea) - math.pi / 2)
     fx, fy = cx + kH * cos(first_angle), cy + kH * sin(first_angle)
@@ -283,7 +314,11 @@ def roundabout_merging(num_time_steps: int = 100, time_step: float = 0.1):
         (ax, ay), (bx, by) = lane_pts[i][0], lane_pts[i][1]
         x0[offs[i] + 0] = ax
         x0[offs[i] + 1] = ay
-        x0[offs[i] + 2] = math.atan2(F(by) - F(ay), F(bx) - F(ax))  # LineSegment2::Heading
+        # LineSegment2::Heading (line_segment2.h:55-70): atan2f of the fp32 unit direction
+        dx, dy = F(F(bx) - F(ax)), F(F(by) - F(ay))
+        ex, ey = F(F(ax) - F(bx)), F(F(ay) - F(by))
+        length = F(np.sqrt(F(F(ex * ex) + F(ey * ey))))
+        x0[offs[i] + 2] = _atan2f(F(dy / length), F(dx / length))
         x0[offs[i] + 4] = speed[i]
     return b.build(), x0
 
@@ -329,8 +364,8 @@ def draw_circle(center, radius, num_segments):
     pts = [(center[0] + radius, center[1] + 0.0)]
     for ii in range(num_segments):
         angle = F(2.0 * math.pi * float(F(ii + 1)) / float(F(num_segments)))
-        pts.append((float(F(center[0]) + F(radius) * F(math.cos(float(angle)))),
-                    float(F(center[1]) + F(radius) * F(math.sin(float(angle))))))
+        pts.append((float(F(center[0]) + F(radius) * _cosf(angle)),
+                    float(F(center[1]) + F(radius) * _sinf(angle))))
     return pts
 
 

@@ -1,0 +1,289 @@
+// oracle/ref_driver.cpp -- TEST INFRASTRUCTURE, not part of the product.
+//
+// A thin extern "C" driver around the UNMODIFIED reference sources (compiled in place from
+// /root/reference/src by oracle/Makefile, target `ref`, against oracle/ref_shim's stand-ins for
+// Eigen3/glog/gflags) so that tests/golden/make_ref_golden.py can run the reference's own
+// ILQSolver::Solve / AugmentedLagrangianSolver::Solve / LQFeedbackSolver::Solve on chosen initial
+// states and commit what they produce as fixtures.  No algorithm lives here: this file only
+// constructs the reference's example Problems, calls the reference's solvers, and copies their
+// logs into flat arrays.
+//
+// Layouts written (all fp32, row-major over the listed indices; matrices row-major [row][col]):
+//   xs     [iterate][T][n]        us     [iterate][T][M]   (players' controls concatenated)
+//   Ps     [T][M][n]              alphas [T][M]            (final strategies)
+//   costs  [N]                                             (final iterate)
+#include <ilqgames/constraint/constraint.h>
+#include <ilqgames/cost/player_cost.h>
+#include <ilqgames/examples/air_3d_example.h>
+#include <ilqgames/examples/roundabout_lane_center.h>
+#include <ilqgames/examples/roundabout_merging_example.h>
+#include <ilqgames/geometry/draw_shapes.h>
+#include <ilqgames/examples/three_player_intersection_example.h>
+#include <ilqgames/solver/augmented_lagrangian_solver.h>
+#include <ilqgames/solver/ilq_solver.h>
+#include <ilqgames/solver/lq_feedback_solver.h>
+#include <ilqgames/solver/lq_open_loop_solver.h>
+#include <ilqgames/solver/problem.h>
+#include <ilqgames/solver/solver_params.h>
+#include <ilqgames/utils/solver_log.h>
+#include <ilqgames/utils/types.h>
+
+#include <cstdint>
+#include <limits>
+#include <memory>
+#include <vector>
+
+using namespace ilqgames;
+
+extern "C" {
+
+// Mirror of include/ilqgames/solver/solver_params.h (the fields the in-scope solvers read).
+struct ilqg_ref_params {
+  float convergence_tolerance;
+  int32_t max_solver_iters;
+  int32_t linesearch;
+  float initial_alpha_scaling;
+  float geometric_alpha_scaling;
+  int32_t max_backtracking_steps;
+  float expected_decrease_fraction;
+  int32_t open_loop;
+  int32_t unconstrained_solver_max_iters;
+  float geometric_mu_scaling;
+  float geometric_mu_downscaling;
+  float geometric_lambda_downscaling;
+  float constraint_error_tolerance;
+};
+
+enum { ILQG_REF_INTERSECTION = 0, ILQG_REF_ROUNDABOUT = 1, ILQG_REF_AIR3D = 2 };
+enum { ILQG_REF_ILQ = 0, ILQG_REF_AL = 1 };
+
+}  // extern "C"
+
+namespace {
+
+std::shared_ptr<Problem> MakeProblem(int which) {
+  std::shared_ptr<Problem> p;
+  if (which == ILQG_REF_INTERSECTION) p = std::make_shared<ThreePlayerIntersectionExample>();
+  else if (which == ILQG_REF_ROUNDABOUT) p = std::make_shared<RoundaboutMergingExample>();
+  else if (which == ILQG_REF_AIR3D) p = std::make_shared<Air3DExample>();
+  else return nullptr;
+  p->Initialize();
+  return p;
+}
+
+SolverParams ToParams(const ilqg_ref_params& q) {
+  SolverParams p;
+  p.convergence_tolerance = q.convergence_tolerance;
+  p.max_solver_iters = (size_t)q.max_solver_iters;
+  p.linesearch = q.linesearch != 0;
+  p.initial_alpha_scaling = q.initial_alpha_scaling;
+  p.geometric_alpha_scaling = q.geometric_alpha_scaling;
+  p.max_backtracking_steps = (size_t)q.max_backtracking_steps;
+  p.expected_decrease_fraction = q.expected_decrease_fraction;
+  p.open_loop = q.open_loop != 0;
+  p.unconstrained_solver_max_iters = (size_t)q.unconstrained_solver_max_iters;
+  p.geometric_mu_scaling = q.geometric_mu_scaling;
+  p.geometric_mu_downscaling = q.geometric_mu_downscaling;
+  p.geometric_lambda_downscaling = q.geometric_lambda_downscaling;
+  p.constraint_error_tolerance = q.constraint_error_tolerance;
+  // Keep multipliers after an AL solve so they can be read back (they are reset by hand below).
+  p.reset_lambdas = false;
+  p.reset_mu = false;
+  return p;
+}
+
+void ResetMultipliers(Problem& problem) {
+  for (auto& pc : problem.PlayerCosts()) {
+    for (const auto& c : pc.StateConstraints()) c->ScaleLambdas(constants::kDefaultLambda);
+    for (const auto& pair : pc.ControlConstraints()) pair.second->ScaleLambdas(constants::kDefaultLambda);
+  }
+  Constraint::GlobalMu() = constants::kDefaultMu;
+}
+
+void CopyIterate(const SolverLog& log, size_t it, const MultiPlayerIntegrableSystem& dyn, float* xs,
+                 float* us) {
+  const size_t T = time::kNumTimeSteps;
+  const int n = dyn.XDim(), M = dyn.TotalUDim(), N = dyn.NumPlayers();
+  for (size_t k = 0; k < T; k++) {
+    if (xs) for (int d = 0; d < n; d++) xs[(it * T + k) * n + d] = log.State(it, k, d);
+    int off = 0;
+    for (int i = 0; i < N; i++) {
+      const int m = dyn.UDim(i);
+      if (us) for (int d = 0; d < m; d++) us[(it * T + k) * M + off + d] = log.Control(it, k, (PlayerIndex)i, d);
+      off += m;
+    }
+  }
+}
+
+// SolverLog's per-iterate strategy accessors are declared but not linkable in the reference
+// (`inline` definitions in src/solver_log.cpp:173-197), so only the final strategies are copied.
+void CopyStrategies(const std::vector<Strategy>& st, const MultiPlayerIntegrableSystem& dyn, float* Ps,
+                    float* alphas) {
+  const size_t T = time::kNumTimeSteps;
+  const int n = dyn.XDim(), M = dyn.TotalUDim(), N = dyn.NumPlayers();
+  for (size_t k = 0; k < T; k++) {
+    int off = 0;
+    for (int i = 0; i < N; i++) {
+      const int m = dyn.UDim(i);
+      for (int d = 0; d < m; d++) {
+        if (alphas) alphas[k * M + off + d] = st[i].alphas[k](d);
+        if (Ps) for (int c = 0; c < n; c++) Ps[(k * M + off + d) * n + c] = st[i].Ps[k](d, c);
+      }
+      off += m;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int ilqg_ref_dims(int which, int* n, int* M, int* N, int* T, int* num_constraints) {
+  auto p = MakeProblem(which);
+  if (!p) return -1;
+  *n = p->Dynamics()->XDim();
+  *M = p->Dynamics()->TotalUDim();
+  *N = p->Dynamics()->NumPlayers();
+  *T = (int)time::kNumTimeSteps;
+  int c = 0;
+  for (auto& pc : p->PlayerCosts()) c += (int)pc.StateConstraints().size() + (int)pc.ControlConstraints().size();
+  *num_constraints = c;
+  return 0;
+}
+
+int ilqg_ref_x0(int which, float* x0) {
+  auto p = MakeProblem(which);
+  if (!p) return -1;
+  for (int d = 0; d < p->Dynamics()->XDim(); d++) x0[d] = p->InitialState()(d);
+  return 0;
+}
+
+// RoundaboutLaneCenter (src/roundabout_lane_center.cpp) / DrawCircle (src/draw_shapes.cpp): the
+// polylines the examples build their lane and target costs on.  Returns the point count.
+int ilqg_ref_roundabout_lane(float entrance_angle, float exit_angle, float distance, float* pts, int max_pts) {
+  const PointList2 p = RoundaboutLaneCenter(entrance_angle, exit_angle, distance);
+  for (size_t i = 0; i < p.size() && (int)i < max_pts; i++) { pts[2 * i] = p[i].x(); pts[2 * i + 1] = p[i].y(); }
+  return (int)p.size();
+}
+
+int ilqg_ref_draw_circle(float cx, float cy, float radius, int num_segments, float* pts, int max_pts) {
+  const Polyline2 c = DrawCircle(Point2(cx, cy), radius, (size_t)num_segments);
+  const auto& segs = c.Segments();
+  int k = 0;
+  for (size_t i = 0; i < segs.size() && k < max_pts; i++, k++) { pts[2 * k] = segs[i].FirstPoint().x(); pts[2 * k + 1] = segs[i].FirstPoint().y(); }
+  if (k < max_pts && !segs.empty()) { pts[2 * k] = segs.back().SecondPoint().x(); pts[2 * k + 1] = segs.back().SecondPoint().y(); k++; }
+  return k;
+}
+
+// One game from x0 (zero initial operating point and strategies, as Problem::Initialize leaves
+// them).  solver = ILQG_REF_ILQ: ILQSolver::Solve(success, inf) with the given multipliers state
+// (lambda = 0, mu as given); ILQG_REF_AL: AugmentedLagrangianSolver::Solve(success, inf).
+// Logs up to max_log iterates (the log's iterate 0 is the initial rollout).  lambdas_out is
+// [constraint][T] in the order players -> state constraints -> control constraints.
+int ilqg_ref_solve(int which, int solver, const float* x0, const ilqg_ref_params* q, float mu0,
+                   int max_log, float* xs, float* us, float* Ps, float* alphas, float* costs,
+                   int* num_iterates, int* success, float* lambdas_out, float* mu_out) {
+  auto problem = MakeProblem(which);
+  if (!problem) return -1;
+  const auto& dyn = *problem->Dynamics();
+  VectorXf x(dyn.XDim());
+  for (int d = 0; d < dyn.XDim(); d++) x(d) = x0[d];
+  problem->ResetInitialState(x);
+  ResetMultipliers(*problem);
+  Constraint::GlobalMu() = mu0;
+
+  const SolverParams params = ToParams(*q);
+  bool ok = false;
+  std::shared_ptr<SolverLog> log;
+  const Time inf = std::numeric_limits<Time>::infinity();
+  if (solver == ILQG_REF_ILQ) {
+    ILQSolver s(problem, params);
+    log = s.Solve(&ok, inf);
+  } else {
+    // Not infinity: the outer loop's guard is `elapsed < max_runtime - bound` with elapsed starting
+    // at max_runtime / max_solver_iters (src/augmented_lagrangian_solver.cpp:83-110), which is
+    // false for inf < inf, so an infinite budget would skip the multiplier loop altogether.
+    AugmentedLagrangianSolver s(problem, params);
+    log = s.Solve(&ok, 1e9);
+  }
+  const int iterates = (int)log->NumIterates();
+  *num_iterates = iterates;
+  *success = ok ? 1 : 0;
+  for (int it = 0; it < iterates && it < max_log; it++)
+    CopyIterate(*log, (size_t)it, dyn, xs, us);
+  CopyStrategies(log->FinalStrategies(), dyn, Ps, alphas);
+  if (costs) {
+    // SolverLog keeps total costs only for the last iterate through its public interface.
+    const auto c = log->TotalCosts();
+    for (size_t i = 0; i < c.size(); i++) costs[i] = c[i];
+  }
+  if (lambdas_out) {
+    size_t c = 0;
+    const size_t T = time::kNumTimeSteps;
+    for (auto& pc : problem->PlayerCosts()) {
+      for (const auto& con : pc.StateConstraints()) {
+        for (size_t k = 0; k < T; k++) lambdas_out[c * T + k] = con->Lambda(time::kTimeStep * (Time)k + 1e-6);
+        c++;
+      }
+      for (const auto& pair : pc.ControlConstraints()) {
+        for (size_t k = 0; k < T; k++) lambdas_out[c * T + k] = pair.second->Lambda(time::kTimeStep * (Time)k + 1e-6);
+        c++;
+      }
+    }
+  }
+  if (mu_out) *mu_out = Constraint::GlobalMu();
+  ResetMultipliers(*problem);
+  return 0;
+}
+
+// ILQSolver with max_solver_iters = 1 from x0: returns the linearization and quadraticization
+// members after the solve -- i.e. A, B of the INITIAL rollout and Q, l, R_ii, r_ii of the
+// accepted operating point (src/ilq_solver.cpp:437-490).  A [T][n][n], B [T][n][M],
+// Q [T][N][n][n], l [T][N][n], R [T][sum m_i^2] (row-major blocks, player order), r [T][M].
+int ilqg_ref_lin_quad(int which, const float* x0, const ilqg_ref_params* q, float mu0, float* A,
+                      float* B, float* Q, float* l, float* R, float* r) {
+  auto problem = MakeProblem(which);
+  if (!problem) return -1;
+  const auto& dyn = *problem->Dynamics();
+  const int n = dyn.XDim(), M = dyn.TotalUDim(), N = dyn.NumPlayers();
+  VectorXf x(n);
+  for (int d = 0; d < n; d++) x(d) = x0[d];
+  problem->ResetInitialState(x);
+  ResetMultipliers(*problem);
+  Constraint::GlobalMu() = mu0;
+  SolverParams params = ToParams(*q);
+  params.max_solver_iters = 1;
+  ILQSolver s(problem, params);
+  bool ok = false;
+  s.Solve(&ok, std::numeric_limits<Time>::infinity());
+  const auto& lin = *s.Linearization();
+  const auto& quad = *s.Quadraticization();
+  const size_t T = time::kNumTimeSteps;
+  int sumsq = 0;
+  for (int i = 0; i < N; i++) sumsq += dyn.UDim(i) * dyn.UDim(i);
+  for (size_t k = 0; k < T; k++) {
+    for (int a = 0; a < n; a++)
+      for (int b = 0; b < n; b++) A[(k * n + a) * n + b] = lin[k].A(a, b);
+    int off = 0, roff = 0;
+    for (int i = 0; i < N; i++) {
+      const int m = dyn.UDim(i);
+      for (int a = 0; a < n; a++)
+        for (int d = 0; d < m; d++) B[(k * n + a) * M + off + d] = lin[k].Bs[i](a, d);
+      for (int a = 0; a < n; a++) {
+        l[(k * N + i) * n + a] = quad[k][i].state.grad(a);
+        for (int b = 0; b < n; b++) Q[((k * N + i) * n + a) * n + b] = quad[k][i].state.hess(a, b);
+      }
+      const auto& cq = quad[k][i].control.at(i);
+      for (int a = 0; a < m; a++) {
+        r[k * M + off + a] = cq.grad(a);
+        for (int b = 0; b < m; b++) R[k * sumsq + roff + a * m + b] = cq.hess(a, b);
+      }
+      off += m;
+      roff += m * m;
+    }
+  }
+  ResetMultipliers(*problem);
+  return ok ? 0 : 1;
+}
+
+}  // extern "C"

@@ -1,0 +1,133 @@
+"""Generate tests/golden/ref_*.npz by RUNNING THE REFERENCE'S OWN SOURCES.
+
+`make -C oracle ref` compiles /root/reference/src/*.cpp (unmodified, in place) against the
+Eigen/glog/gflags stand-ins in oracle/ref_shim into oracle/_ref/libilqg_ref.so; this script calls
+the reference's ILQSolver::Solve / AugmentedLagrangianSolver::Solve on the reference's own example
+Problems through oracle/ref_driver.cpp and stores what they return.  /root/reference only exists
+in the builder container, so the outputs are committed as fixtures; tests/test_ref_pins.py checks
+the CPU oracle against them (bit for bit) and tests/test_gpu_parity.py the CUDA path (tolerance).
+
+What the fixtures pin: control flow, indexing, term order, linesearch, convergence test,
+multiplier updates, every scalar formula of the reference.  What they do not: the rounding of
+Eigen's own kernels (dense products, Householder QR), which the stand-in computes in plain
+dot-product order.
+
+Re-run (builder container only):  python tests/golden/make_ref_golden.py
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+from ilqgames_b200 import problems  # noqa: E402
+from tests.golden import ref_lib as R  # noqa: E402
+
+ILQ_ITERS = 6       # ILQSolver::Solve cap for the per-iterate fixtures
+AL_INNER, AL_OUTER = 10, 40   # unconstrained_solver_max_iters, AL NumIterates cap
+
+CASES = {
+    # name: (reference problem id, descriptor builder, params builder, x0 batch)
+    "three_player_intersection": (R.INTERSECTION, problems.three_player_intersection,
+                                  problems.three_player_intersection_params,
+                                  lambda: problems.three_player_intersection_x0_batch(12, 1024)),
+    "roundabout_merging": (R.ROUNDABOUT, problems.roundabout_merging, problems.roundabout_params,
+                           lambda: problems.roundabout_x0_batch(8, 4096)),
+    "air_3d": (R.AIR3D, problems.air_3d, problems.air_3d_params,
+               lambda: problems.air_3d_x0_grid(4)[:12]),
+}
+
+
+def sorted_rows(a: np.ndarray) -> np.ndarray:
+    """Multipliers as a set of per-constraint rows: the reference keeps control constraints in an
+    unordered_multimap, so their order is an implementation detail."""
+    if a.shape[0] == 0:
+        return a
+    return a[np.lexsort(a.T[::-1])]
+
+
+def run_case(ref: R.RefLibrary, name: str):
+    which, build, params, x0f = CASES[name]
+    _, x0_example = build()
+    x0 = x0f().astype(np.float32)
+    x0[0] = x0_example           # instance 0 = the example's own initial state
+    assert np.array_equal(ref.x0(which), x0[0]), "descriptor x0 differs from the reference example"
+    B = x0.shape[0]
+    n, M, N, T, nc = ref.dims(which)
+    p = params(max_solver_iters=ILQ_ITERS)
+    rp = R.RefParams.from_abi(p)
+    out = {"x0": x0, "ilq_iters": np.int32(ILQ_ITERS)}
+    xs = np.full((B, ILQ_ITERS + 1, T, n), np.nan, np.float32)
+    us = np.full((B, ILQ_ITERS + 1, T, M), np.nan, np.float32)
+    Ps = np.zeros((B, T, M, n), np.float32)
+    alphas = np.zeros((B, T, M), np.float32)
+    costs = np.zeros((B, N), np.float32)
+    iterates = np.zeros(B, np.int32)
+    success = np.zeros(B, np.int32)
+    for b in range(B):
+        r = ref.solve(which, R.ILQ, x0[b], rp, max_log=ILQ_ITERS + 1)
+        k = r["iterates"]
+        xs[b, :k], us[b, :k] = r["xs"], r["us"]
+        Ps[b], alphas[b], costs[b] = r["Ps"], r["alphas"], r["costs"]
+        iterates[b], success[b] = k, r["success"]
+    out.update(ilq_xs=xs, ilq_us=us, ilq_Ps=Ps, ilq_alphas=alphas, ilq_costs=costs,
+               ilq_iterates=iterates, ilq_success=success)
+
+    # linearization at the initial rollout, quadraticization at the first accepted iterate
+    nlq = 2
+    lq = [ref.lin_quad(which, x0[b], rp) for b in range(nlq)]
+    for key in ("A", "B", "Q", "l", "R", "r"):
+        out[f"lq_{key}"] = np.stack([d[key] for d in lq])
+
+    if nc > 0:
+        nal = 6
+        pa = params(max_solver_iters=AL_INNER)
+        rpa = R.RefParams.from_abi(pa)
+        rpa.unconstrained_solver_max_iters = AL_INNER
+        rpa.max_solver_iters = AL_OUTER
+        res = [ref.solve(which, R.AL, x0[b], rpa, max_log=AL_OUTER + AL_INNER + 2) for b in range(nal)]
+        out.update(al_inner=np.int32(AL_INNER), al_outer=np.int32(AL_OUTER),
+                   al_xs=np.stack([r["xs"][-1] for r in res]),
+                   al_us=np.stack([r["us"][-1] for r in res]),
+                   al_Ps=np.stack([r["Ps"] for r in res]),
+                   al_alphas=np.stack([r["alphas"] for r in res]),
+                   al_lambdas_sorted=np.stack([sorted_rows(r["lambdas"]) for r in res]),
+                   al_mu=np.array([r["mu"] for r in res], np.float32),
+                   al_iterates=np.array([r["iterates"] for r in res], np.int32),
+                   al_success=np.array([r["success"] for r in res], np.int32))
+    return out
+
+
+def check_polylines(ref: R.RefLibrary):
+    """The lane / target polylines of problems.py equal the reference's, bit for bit."""
+    import math
+    F = np.float32
+    off, wedge = F(math.pi / 2 * 0.5), F(math.pi)
+    out = {}
+    for i, dist in enumerate((25.0, 10.0, 25.0, 10.0)):
+        ang = F(float(off) + i * 2.0 * math.pi / 4.0)
+        mine = np.asarray(problems.roundabout_lane_center(ang, F(ang + wedge), dist), np.float32)
+        theirs = ref.roundabout_lane(ang, F(ang + wedge), dist)
+        assert np.array_equal(mine, theirs), (i, np.abs(mine - theirs).max())
+        out[f"roundabout_lane_{i}"] = theirs
+    mine = np.asarray(problems.draw_circle((0.0, 0.0), 5.0, 10), np.float32)
+    theirs = ref.draw_circle(0.0, 0.0, 5.0, 10)
+    assert np.array_equal(mine, theirs), np.abs(mine - theirs).max()
+    out["air_3d_circle"] = theirs
+    return out
+
+
+if __name__ == "__main__":
+    subprocess.run(["make", "-C", os.path.join(REPO, "oracle"), "ref"], check=True,
+                   stdout=subprocess.DEVNULL)
+    ref = R.RefLibrary()
+    np.savez_compressed(os.path.join(HERE, "ref_polylines.npz"), **check_polylines(ref))
+    for name in CASES:
+        out = run_case(ref, name)
+        np.savez_compressed(os.path.join(HERE, f"ref_{name}.npz"), **out)
+        print("wrote", name, "iterates", out["ilq_iterates"].tolist(), "success",
+              out["ilq_success"].tolist(),
+              "AL iterates", out.get("al_iterates", np.zeros(0)).tolist())

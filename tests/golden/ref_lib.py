@@ -1,0 +1,102 @@
+"""ctypes wrapper of oracle/_ref/libilqg_ref.so -- the reference's OWN sources (compiled by
+`make -C oracle ref` against the Eigen/glog/gflags stand-ins in oracle/ref_shim) behind the few
+entry points of oracle/ref_driver.cpp.  TEST INFRASTRUCTURE: used by make_ref_golden.py (fixture
+generation, needs /root/reference) and by tests/test_ref_pins.py when the library is present."""
+import ctypes as C
+import os
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REF_LIB = os.path.join(REPO, "oracle", "_ref", "libilqg_ref.so")
+
+INTERSECTION, ROUNDABOUT, AIR3D = 0, 1, 2
+ILQ, AL = 0, 1
+
+
+class RefParams(C.Structure):
+    _fields_ = [("convergence_tolerance", C.c_float), ("max_solver_iters", C.c_int32),
+                ("linesearch", C.c_int32), ("initial_alpha_scaling", C.c_float),
+                ("geometric_alpha_scaling", C.c_float), ("max_backtracking_steps", C.c_int32),
+                ("expected_decrease_fraction", C.c_float), ("open_loop", C.c_int32),
+                ("unconstrained_solver_max_iters", C.c_int32), ("geometric_mu_scaling", C.c_float),
+                ("geometric_mu_downscaling", C.c_float),
+                ("geometric_lambda_downscaling", C.c_float),
+                ("constraint_error_tolerance", C.c_float)]
+
+    @classmethod
+    def from_abi(cls, p) -> "RefParams":
+        """From an ilqgames_b200._abi.SolverParams (same field names)."""
+        return cls(**{name: getattr(p, name) for name, _ in cls._fields_})
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class RefLibrary:
+    def __init__(self, path: str = REF_LIB):
+        self.lib = C.CDLL(path)
+
+    def dims(self, which: int):
+        v = [C.c_int(0) for _ in range(5)]
+        assert self.lib.ilqg_ref_dims(which, *[C.byref(x) for x in v]) == 0
+        return tuple(x.value for x in v)  # n, M, N, T, num_constraints
+
+    def x0(self, which: int) -> np.ndarray:
+        n = self.dims(which)[0]
+        out = np.zeros(n, np.float32)
+        assert self.lib.ilqg_ref_x0(which, _ptr(out)) == 0
+        return out
+
+    def solve(self, which: int, solver: int, x0, params: RefParams, mu0: float = 10.0,
+              max_log: int = 64):
+        n, M, N, T, nc = self.dims(which)
+        x0 = np.ascontiguousarray(x0, np.float32)
+        xs = np.zeros((max_log, T, n), np.float32)
+        us = np.zeros((max_log, T, M), np.float32)
+        Ps = np.zeros((T, M, n), np.float32)
+        alphas = np.zeros((T, M), np.float32)
+        costs = np.zeros(N, np.float32)
+        lambdas = np.zeros((max(nc, 1), T), np.float32)
+        mu = C.c_float(0)
+        iterates, success = C.c_int(0), C.c_int(0)
+        rc = self.lib.ilqg_ref_solve(which, solver, _ptr(x0), C.byref(params), C.c_float(mu0),
+                                     max_log, _ptr(xs), _ptr(us), _ptr(Ps), _ptr(alphas),
+                                     _ptr(costs), C.byref(iterates), C.byref(success),
+                                     _ptr(lambdas), C.byref(mu))
+        assert rc == 0
+        k = min(iterates.value, max_log)
+        return dict(xs=xs[:k], us=us[:k], Ps=Ps, alphas=alphas, costs=costs,
+                    iterates=iterates.value, success=success.value, lambdas=lambdas[:nc],
+                    mu=mu.value)
+
+    def lin_quad(self, which: int, x0, params: RefParams, mu0: float = 10.0):
+        n, M, N, T, _ = self.dims(which)
+        x0 = np.ascontiguousarray(x0, np.float32)
+        A = np.zeros((T, n, n), np.float32)
+        B = np.zeros((T, n, M), np.float32)
+        Q = np.zeros((T, N, n, n), np.float32)
+        l = np.zeros((T, N, n), np.float32)
+        m2 = self._sum_udim_sq(which)
+        R = np.zeros((T, m2), np.float32)
+        r = np.zeros((T, M), np.float32)
+        rc = self.lib.ilqg_ref_lin_quad(which, _ptr(x0), C.byref(params), C.c_float(mu0), _ptr(A),
+                                        _ptr(B), _ptr(Q), _ptr(l), _ptr(R), _ptr(r))
+        assert rc in (0, 1)
+        return dict(A=A, B=B, Q=Q, l=l, R=R, r=r, ok=rc == 0)
+
+    def roundabout_lane(self, entrance_angle, exit_angle, distance) -> np.ndarray:
+        pts = np.zeros((64, 2), np.float32)
+        k = self.lib.ilqg_ref_roundabout_lane(C.c_float(entrance_angle), C.c_float(exit_angle),
+                                              C.c_float(distance), _ptr(pts), 64)
+        return pts[:k]
+
+    def draw_circle(self, cx, cy, radius, num_segments) -> np.ndarray:
+        pts = np.zeros((num_segments + 1, 2), np.float32)
+        k = self.lib.ilqg_ref_draw_circle(C.c_float(cx), C.c_float(cy), C.c_float(radius),
+                                          num_segments, _ptr(pts), num_segments + 1)
+        return pts[:k]
+
+    def _sum_udim_sq(self, which: int) -> int:
+        return {INTERSECTION: 12, ROUNDABOUT: 16, AIR3D: 2}[which]

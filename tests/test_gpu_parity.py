@@ -234,6 +234,55 @@ def test_against_golden_fixture(product, name):
     assert g[f"stable_{iters}"].sum() >= 3, "golden fixture has too few well-posed instances"
 
 
+# ------------------------------------------------------------------ reference fixtures
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_against_reference_fixture(product, oracle64, name):
+    """The CUDA path against outputs of the reference's own sources (tests/golden/ref_*.npz, made
+    by tests/golden/make_ref_golden.py; the CPU oracle reproduces them bit for bit in
+    tests/test_ref_pins.py).  Log iterate `it` of ILQSolver::Solve = the operating point after
+    `it` iterations; instances are compared where the fp64 build of the oracle agrees with the
+    reference's fp32 result to 1e-3 (elsewhere fp32 rounding decides the Armijo branch)."""
+    g = np.load(os.path.join(GOLDEN, f"ref_{name}.npz"))
+    build, params, _ = CONFIGS[name]
+    desc, _ = build()
+    x0 = g["x0"]
+    B = x0.shape[0]
+    iters = int(g["ilq_iters"])
+    xs_tol = 2e-2 if name == "roundabout_merging" else 1e-3
+    compared = 0
+    for it in range(0, iters + 1):
+        hs = []
+        for lib in (product, oracle64):
+            h = abi.Handle(lib, desc, params(max_solver_iters=max(it, 1)), B, 0)
+            h.upload_x0(x0)
+            h.solve_begin()
+            if it > 0:
+                h.solve(chunk=it)
+            hs.append(h)
+        c, o64 = hs
+        logged = g["ilq_iterates"] > it           # the reference logged iterate `it`
+        ref_xs, ref_us = g["ilq_xs"][:, it], g["ilq_us"][:, it]
+        if it == 0:
+            close(c.download(abi.XS), ref_xs, what="initial rollout xs")
+            close(c.download(abi.US), ref_us, what="initial rollout us")
+            continue
+        stable = logged & tame(np.where(np.isfinite(ref_xs), ref_xs, 0.0), 1e3)
+        if stable.any():
+            stable[stable] &= wellposed(ref_xs[stable], o64.download(abi.XS)[stable])
+        stable &= (o64.download(abi.ITERS) == it) & (o64.download(abi.STATUS) != abi.STATUS_LINESEARCH_FAILED)
+        flow = (c.download(abi.ITERS) == it) & (c.download(abi.STATUS) != abi.STATUS_LINESEARCH_FAILED)
+        if stable.any():
+            assert flow[stable].mean() >= 0.75, f"iterate {it}: CUDA path follows the reference on {flow[stable].mean():.0%}"
+        ok = stable & flow
+        if ok.any():
+            close(c.download(abi.XS), ref_xs, tol=xs_tol, atol=1e-3, rows=ok, what=f"ref xs_{it}")
+            close(c.download(abi.US), ref_us, tol=xs_tol, atol=1e-3, rows=ok, what=f"ref us_{it}")
+            compared += int(ok.sum())
+        for h in hs:
+            h.close()
+    assert compared >= 6, f"only {compared} (instance, iterate) pairs were comparable"
+
+
 # ------------------------------------------------------------------ full solves
 @pytest.mark.parametrize("name,batch,iters", [("three_player_intersection", 64, 10),
                                               ("roundabout_merging", 32, 3), ("air_3d", 36, 10)])

@@ -1,0 +1,172 @@
+"""The CPU oracle against outputs of THE REFERENCE ITSELF.
+
+tests/golden/ref_*.npz were produced by tests/golden/make_ref_golden.py from the reference's own
+sources (/root/reference/src/*.cpp compiled unmodified against the Eigen/glog/gflags stand-ins in
+oracle/ref_shim; see oracle/ref_shim/Eigen/Dense for what that pins).  They hold what
+ILQSolver::Solve and AugmentedLagrangianSolver::Solve return on the reference's own example
+Problems: every logged iterate, the final strategies, total costs, success flags, iterate counts,
+multipliers.  The oracle has to reproduce them BIT FOR BIT -- trajectories, feedback gains,
+statuses and counters alike; only the per-player total costs get one ulp of slack (their summation
+order follows an unordered_multimap in the reference).
+
+The GPU parity tests (tests/test_gpu_parity.py::test_against_reference_fixture) hold the CUDA path
+to the same fixtures within the fp32 tolerances stated there."""
+import os
+
+import numpy as np
+import pytest
+
+from ilqgames_b200 import _abi as abi, al, problems
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden")
+
+CASES = {
+    "three_player_intersection": (problems.three_player_intersection,
+                                  problems.three_player_intersection_params),
+    "roundabout_merging": (problems.roundabout_merging, problems.roundabout_params),
+    "air_3d": (problems.air_3d, problems.air_3d_params),
+}
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, f"ref_{name}.npz"))
+
+
+def sorted_rows(a):
+    return a[np.lexsort(a.T[::-1])] if a.shape[0] else a
+
+
+def ulp_close(a, b, ulps):
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    return bool(np.all(np.abs(a - b) <= ulps * np.spacing(np.maximum(np.abs(a), np.abs(b)))))
+
+
+def test_descriptor_polylines_equal_the_references():
+    """RoundaboutLaneCenter / DrawCircle as the reference computes them (cosf/sinf)."""
+    import math
+    g = np.load(os.path.join(GOLDEN, "ref_polylines.npz"))
+    F = np.float32
+    off, wedge = F(math.pi / 2 * 0.5), F(math.pi)
+    for i, dist in enumerate((25.0, 10.0, 25.0, 10.0)):
+        ang = F(float(off) + i * 2.0 * math.pi / 4.0)
+        mine = np.asarray(problems.roundabout_lane_center(ang, F(ang + wedge), dist), np.float32)
+        assert np.array_equal(mine, g[f"roundabout_lane_{i}"])
+    mine = np.asarray(problems.draw_circle((0.0, 0.0), 5.0, 10), np.float32)
+    assert np.array_equal(mine, g["air_3d_circle"])
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_reproduces_reference_ilq_iterates(oracle, name):
+    """ILQSolver::Solve (src/ilq_solver.cpp:76-172): every logged operating point."""
+    g = load(name)
+    build, params = CASES[name]
+    desc, x0_example = build()
+    x0 = g["x0"]
+    assert np.array_equal(np.asarray(x0_example, np.float32), x0[0])
+    iters = int(g["ilq_iters"])
+    B = x0.shape[0]
+    h = abi.Handle(oracle, desc, params(max_solver_iters=iters), B)
+    h.upload_x0(x0)
+    h.solve_begin()
+    # log iterate 0 = the initial rollout (ilq_solver.cpp:104-111)
+    assert np.array_equal(h.download(abi.XS), g["ilq_xs"][:, 0])
+    assert np.array_equal(h.download(abi.US), g["ilq_us"][:, 0])
+    logged = np.ones(B, np.int32)
+    for it in range(1, iters + 1):
+        h.iterate(1)
+        status, done = h.download(abi.STATUS), h.download(abi.ITERS)
+        xs, us = h.download(abi.XS), h.download(abi.US)
+        # an iteration is logged iff its linesearch succeeded (:140-165)
+        newly = (done == it) & (status != abi.STATUS_LINESEARCH_FAILED)
+        logged += newly
+        for b in np.nonzero(newly)[0]:
+            assert np.array_equal(xs[b], g["ilq_xs"][b, it]), (name, b, it)
+            assert np.array_equal(us[b], g["ilq_us"][b, it]), (name, b, it)
+    status = h.download(abi.STATUS)
+    assert np.array_equal(logged, g["ilq_iterates"])
+    assert np.array_equal((status != abi.STATUS_LINESEARCH_FAILED).astype(np.int32), g["ilq_success"])
+    # final strategies: of the last logged iterate
+    ok = g["ilq_success"] == 1
+    assert np.array_equal(h.download(abi.PS)[ok], g["ilq_Ps"][ok])
+    assert np.array_equal(h.download(abi.ALPHAS)[ok], g["ilq_alphas"][ok])
+    assert ulp_close(h.download(abi.TOTAL_COSTS)[ok], g["ilq_costs"][ok], 2)
+    h.close()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_reproduces_reference_lin_quad(oracle, name):
+    """ComputeLinearization at the initial rollout and ComputeCostQuadraticization at the first
+    accepted iterate (src/ilq_solver.cpp:437-490): every A, B, Q, l, R, r entry."""
+    g = load(name)
+    build, params = CASES[name]
+    desc, _ = build()
+    nlq = g["lq_A"].shape[0]
+    h = abi.Handle(oracle, desc, params(max_solver_iters=1), nlq)
+    h.upload_x0(g["x0"][:nlq])
+    h.solve_begin()
+    h.linearize_quadraticize()
+    assert np.array_equal(h.download(abi.LIN_A), g["lq_A"])
+    assert np.array_equal(h.download(abi.LIN_B), g["lq_B"])
+    h.iterate(1)
+    ok = h.download(abi.STATUS) != abi.STATUS_LINESEARCH_FAILED
+    h.linearize_quadraticize()
+    for what, key in ((abi.QUAD_Q, "lq_Q"), (abi.QUAD_L, "lq_l"), (abi.QUAD_R, "lq_R"),
+                      (abi.QUAD_RGRAD, "lq_r")):
+        assert np.array_equal(h.download(what)[ok], g[key][ok]), key
+    assert ok.any()
+    h.close()
+
+
+@pytest.mark.parametrize("name", ["three_player_intersection", "air_3d"])
+def test_oracle_reproduces_reference_augmented_lagrangian(oracle, name):
+    """AugmentedLagrangianSolver::Solve (src/augmented_lagrangian_solver.cpp:72-210): final
+    operating point and strategies, multipliers, mu, NumIterates, success."""
+    g = load(name)
+    build, params = CASES[name]
+    desc, _ = build()
+    nal = g["al_xs"].shape[0]
+    h = abi.Handle(oracle, desc, params(max_solver_iters=int(g["al_inner"])), nal)
+    h.upload_x0(g["x0"][:nal])
+    res = al.solve_augmented_lagrangian(h, max_solver_iters=int(g["al_outer"]),
+                                        reset_lambdas=False, reset_mu=False, reset_problem=False,
+                                        chunk=1)
+    assert np.array_equal(res.iterates, g["al_iterates"])
+    assert np.array_equal(res.success, g["al_success"])
+    assert np.array_equal(res.xs, g["al_xs"])
+    assert np.array_equal(res.us, g["al_us"])
+    assert np.array_equal(res.Ps, g["al_Ps"])
+    assert np.array_equal(res.alphas, g["al_alphas"])
+    assert np.array_equal(h.download(abi.MU), g["al_mu"])
+    lam = h.download(abi.LAMBDAS)
+    for b in range(nal):
+        assert np.array_equal(sorted_rows(lam[b]), g["al_lambdas_sorted"][b]), b
+    h.close()
+
+
+@pytest.mark.skipif(not (os.path.isdir("/root/reference") and
+                         os.path.exists(os.path.join(os.path.dirname(HERE), "oracle", "_ref",
+                                                     "libilqg_ref.so"))),
+                    reason="live reference build only exists in the builder container")
+@pytest.mark.parametrize("name,which,seed", [("three_player_intersection", 0, 7),
+                                              ("roundabout_merging", 1, 11)])
+def test_oracle_against_live_reference_on_fresh_seeds(oracle, name, which, seed):
+    """Same check on initial states that are NOT in the fixtures, calling the compiled reference
+    directly (builder container only)."""
+    from tests.golden import ref_lib as R
+    ref = R.RefLibrary()
+    build, params = CASES[name]
+    desc, _ = build()
+    x0 = (problems.three_player_intersection_x0_batch(4, seed) if which == 0
+          else problems.roundabout_x0_batch(4, seed))
+    p = params(max_solver_iters=5)
+    h = abi.Handle(oracle, desc, p, 4)
+    h.upload_x0(x0)
+    h.solve_begin()
+    h.solve(chunk=1)
+    xs, us, status = h.download(abi.XS), h.download(abi.US), h.download(abi.STATUS)
+    for b in range(4):
+        r = ref.solve(which, R.ILQ, x0[b], R.RefParams.from_abi(p))
+        assert np.array_equal(r["xs"][-1], xs[b]) and np.array_equal(r["us"][-1], us[b])
+        assert r["success"] == int(status[b] != abi.STATUS_LINESEARCH_FAILED)
+    h.close()
