@@ -9,6 +9,7 @@
 
 namespace google {
 inline void InitGoogleLogging(const char*) {}
+inline void SetLogDestination(int, const char*) {}
 struct FatalMessage {
   std::ostringstream os;
   FatalMessage(const char* file, int line, const char* what) { os << file << ":" << line << " Check failed: " << what << " "; }
@@ -37,6 +38,11 @@ constexpr bool fINFO = false, fWARNING = false, fERROR = false, fFATAL = true;
 }  // namespace shim
 }  // namespace google
 
+static bool FLAGS_logtostderr = false;
+static int FLAGS_minloglevel = 0;
+static int FLAGS_v = 0;
+#include <cmath>
+
 #define ILQG_REF_CHECK(cond, text) \
   (cond) ? (void)0 : google::Voidify() & google::FatalMessage(__FILE__, __LINE__, text).stream()
 #define CHECK(c) ILQG_REF_CHECK((c), #c)
@@ -46,6 +52,7 @@ constexpr bool fINFO = false, fWARNING = false, fERROR = false, fFATAL = true;
 #define CHECK_LE(a, b) ILQG_REF_CHECK((a) <= (b), #a " <= " #b)
 #define CHECK_GT(a, b) ILQG_REF_CHECK((a) > (b), #a " > " #b)
 #define CHECK_GE(a, b) ILQG_REF_CHECK((a) >= (b), #a " >= " #b)
+#define CHECK_NEAR(a, b, tol) ILQG_REF_CHECK(std::abs((a) - (b)) <= (tol), #a " near " #b)
 #define CHECK_NOTNULL(p) google::CheckNotNull(__FILE__, __LINE__, #p " != nullptr", (p))
 #define DCHECK(c) CHECK(c)
 #define DCHECK_EQ(a, b) CHECK_EQ(a, b)

@@ -170,3 +170,18 @@ def test_oracle_against_live_reference_on_fresh_seeds(oracle, name, which, seed)
         assert np.array_equal(r["xs"][-1], xs[b]) and np.array_equal(r["us"][-1], us[b])
         assert r["success"] == int(status[b] != abi.STATUS_LINESEARCH_FAILED)
     h.close()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/test"),
+                    reason="the reference tree only exists in the builder container")
+def test_reference_gtest_suite_passes_on_the_shim_build():
+    """`make -C oracle ref-test`: the reference's own test/*.cpp (vendored gtest), unmodified,
+    linked against the reference's own src/*.cpp compiled on oracle/ref_shim.  All of its tests
+    pass, which is what qualifies the stand-ins for Eigen/glog/gflags (and with them the
+    fixtures above) as "the reference run here"."""
+    import subprocess
+    repo = os.path.dirname(HERE)
+    out = subprocess.run(["make", "-C", os.path.join(repo, "oracle"), "ref-test"], check=True,
+                         capture_output=True, text=True).stdout
+    assert "[  PASSED  ] 51 tests." in out, out[-2000:]
+    assert "FAILED" not in out
