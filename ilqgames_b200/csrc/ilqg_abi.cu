@@ -34,6 +34,7 @@ struct SubSolver {
   // linearizes / solves pass i + 1 for everyone else (IteratePipelined)
   cudaStream_t side;
   cudaEvent_t ev_fresh, ev_side;
+  bool side_busy = false;
   int pipeline;  // 0 off, 1 = K_lq + K_bwd of the queue on the side stream, 2 = K_lq only
   std::vector<void*> allocs;
   // per-kernel event timing (ilqg_profile)
@@ -541,6 +542,42 @@ int LaunchLinesearch(SubSolver* h) {
   return LaunchLinesearchQueued(h);
 }
 
+// One pass of the pipelined schedule (pass `it` of `n`).
+int PipelinedStep(SubSolver* h, int it, int n) {
+  int rc;
+  cudaStream_t main = h->stream;
+  if (it == 0) h->side_busy = false;
+  const Sel all{SEL_ALL, nullptr, nullptr};
+  const Sel sel = it > 0 ? Sel{SEL_MAIN, nullptr, nullptr} : all;
+  const bool bwd_on_side = h->pipeline == 1;
+  if ((rc = LaunchLqRecords(h, 1, sel)) != ILQG_OK) return rc;
+  if (!bwd_on_side && h->side_busy) CUDA_TRY(cudaStreamWaitEvent(main, h->ev_side, 0));
+  if ((rc = DispatchBackward(h, 1, false, bwd_on_side ? sel : all)) != ILQG_OK) return rc;
+  if (bwd_on_side && h->side_busy) CUDA_TRY(cudaStreamWaitEvent(main, h->ev_side, 0));
+  if ((rc = LaunchLinesearchFresh(h)) != ILQG_OK) return rc;
+  const int q_first = h->ls_cur;  // the queue the first window just filled
+  CUDA_TRY(cudaEventRecord(h->ev_fresh, main));
+  CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_fresh, 0));
+  h->stream = h->side;
+  rc = LaunchLinesearchQueued(h);
+  if (rc == ILQG_OK && it + 1 < n) {
+    const Sel list{SEL_LIST, h->ls.pend[q_first], h->ls.counts + q_first};
+    rc = LaunchLqRecords(h, 1, list);
+    if (rc == ILQG_OK && h->pipeline == 1) rc = DispatchBackward(h, 1, false, list);
+  }
+  h->stream = main;
+  if (rc != ILQG_OK) return rc;
+  CUDA_TRY(cudaEventRecord(h->ev_side, h->side));
+  h->side_busy = true;
+  return ILQG_OK;
+}
+
+int PipelinedEnd(SubSolver* h) {
+  if (h->side_busy) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_side, 0));
+  h->side_busy = false;
+  return ILQG_OK;
+}
+
 // n iterations with the open linesearches of pass i overlapped with K_lq / K_bwd of pass i + 1:
 //   main: K_lq, K_bwd (everyone but the instances queued in pass i-1) | wait side | first window
 //   side:                         wait first window | remaining windows, K_lq + K_bwd over the queue
@@ -548,34 +585,17 @@ int LaunchLinesearch(SubSolver* h) {
 // groups are processed inside a pass changes.
 int IteratePipelined(SubSolver* h, int n) {
   int rc;
-  cudaStream_t main = h->stream;
-  bool side_busy = false;
-  for (int it = 0; it < n; it++) {
-    const Sel all{SEL_ALL, nullptr, nullptr};
-    const Sel sel = it > 0 ? Sel{SEL_MAIN, nullptr, nullptr} : all;
-    const bool bwd_on_side = h->pipeline == 1;
-    if ((rc = LaunchLqRecords(h, 1, sel)) != ILQG_OK) return rc;
-    if (!bwd_on_side && side_busy) CUDA_TRY(cudaStreamWaitEvent(main, h->ev_side, 0));
-    if ((rc = DispatchBackward(h, 1, false, bwd_on_side ? sel : all)) != ILQG_OK) return rc;
-    if (bwd_on_side && side_busy) CUDA_TRY(cudaStreamWaitEvent(main, h->ev_side, 0));
-    if ((rc = LaunchLinesearchFresh(h)) != ILQG_OK) return rc;
-    const int q_first = h->ls_cur;  // the queue the first window just filled
-    CUDA_TRY(cudaEventRecord(h->ev_fresh, main));
-    CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_fresh, 0));
-    h->stream = h->side;
-    rc = LaunchLinesearchQueued(h);
-    if (rc == ILQG_OK && it + 1 < n) {
-      const Sel list{SEL_LIST, h->ls.pend[q_first], h->ls.counts + q_first};
-      rc = LaunchLqRecords(h, 1, list);
-      if (rc == ILQG_OK && h->pipeline == 1) rc = DispatchBackward(h, 1, false, list);
-    }
-    h->stream = main;
-    if (rc != ILQG_OK) return rc;
-    CUDA_TRY(cudaEventRecord(h->ev_side, h->side));
-    side_busy = true;
-  }
-  if (side_busy) CUDA_TRY(cudaStreamWaitEvent(main, h->ev_side, 0));
-  return ILQG_OK;
+  for (int it = 0; it < n; it++)
+    if ((rc = PipelinedStep(h, it, n)) != ILQG_OK) return rc;
+  return PipelinedEnd(h);
+}
+
+// the pipelined schedule needs the list-capable kernels (static K_lq, half-warp K_bwd) and a
+// single queued window; per-kernel profiling wants every kernel alone on the device
+bool CanPipeline(const SubSolver* h, int max_iters) {
+  const bool hw = h->dims_key == 0 || h->dims_key == 1 || h->dims_key == 4;
+  const bool one_window = h->ls.JB >= std::max(1, h->p.max_backtracking_steps) - h->ls.JA;
+  return h->pipeline && max_iters > 1 && h->pat_ok && hw && one_window && h->p.linesearch && !h->profiling;
 }
 
 int LaunchSolveBegin(SubSolver* h) {
@@ -1000,11 +1020,7 @@ int ilqg_linesearch(SubHandle h) {
 int ilqg_iterate(SubHandle h, int max_iters, int* iters_done) {
   ENTER(h);
   int rc;
-  // the pipelined schedule needs the list-capable kernels (static K_lq, half-warp K_bwd) and a
-  // single queued window; per-kernel profiling wants every kernel alone on the device
-  const bool hw = h->dims_key == 0 || h->dims_key == 1 || h->dims_key == 4;
-  const bool one_window = h->ls.JB >= std::max(1, h->p.max_backtracking_steps) - h->ls.JA;
-  if (h->pipeline && max_iters > 1 && h->pat_ok && hw && one_window && h->p.linesearch && !h->profiling) {
+  if (CanPipeline(h, max_iters)) {
     if ((rc = IteratePipelined(h, max_iters)) != ILQG_OK) return rc;
   } else {
     for (int it = 0; it < max_iters; it++) {
