@@ -38,7 +38,7 @@ COST_SUM, COST_MAX, COST_MIN = 0, 1, 2
 XS, US, PS, ALPHAS, LIN_A, LIN_B, QUAD_Q, QUAD_L, QUAD_R, QUAD_RGRAD, DELTA_XS = range(1, 12)
 (STATUS, ITERS, MERIT, TOTAL_COSTS, LAMBDAS, MU, EXPECTED_DECREASE, STEP, BACKTRACKS,
  TIME_OF_EXTREME, X0, LQ_PS, LQ_ALPHAS, MAX_CONSTRAINT_ERROR, AL_SUCCESS, AL_ITERATES,
- AL_STATE) = range(12, 29)
+ AL_STATE, LQ_X0) = range(12, 30)
 
 OK = 0
 
@@ -228,6 +228,7 @@ class Handle:
             BACKTRACKS: ((), np.int32), TIME_OF_EXTREME: ((self.N,), np.int32),
             X0: ((self.n,), np.float32), MAX_CONSTRAINT_ERROR: ((), np.float32),
             AL_SUCCESS: ((), np.int32), AL_ITERATES: ((), np.int32), AL_STATE: ((), np.int32),
+            LQ_X0: ((self.n,), np.float32),
         }
 
     # -- lifetime ---------------------------------------------------------------

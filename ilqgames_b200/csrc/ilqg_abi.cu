@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "ilqg_linesearch.cuh"
+#include "ilqg_open_loop.cuh"
 
 using namespace ilqg;
 
@@ -35,6 +36,9 @@ struct SubSolver {
   cudaStream_t side;
   cudaEvent_t ev_fresh, ev_side;
   bool side_busy = false;
+  // SolverParams::open_loop: LQOpenLoopSolver instead of LQFeedbackSolver (ilq_solver.h:76-81)
+  bool open_loop = false;
+  float* ol_scratch = nullptr;  // [B][T][OlLayout::srec], ilqg_open_loop.cuh
   int pipeline;  // 0 off, 1 = K_lq + K_bwd of the queue on the side stream, 2 = K_lq only
   std::vector<void*> allocs;
   // per-kernel event timing (ilqg_profile)
@@ -317,9 +321,24 @@ int LaunchBackwardHw(SubSolver* h, int only_running, Sel sel) {
   return ILQG_OK;
 }
 
+int LaunchOpenLoop(SubSolver* h, int only_running, bool use_lq_x0) {
+  const OlLayout L = ol_layout(h->d.n, h->d.M, h->d.N, h->d.rec - h->d.offl);
+  const size_t smem = sizeof(float) * KOL_WARPS * (size_t)L.total;
+  int rc = SetSmem(k_lq_open_loop, smem);
+  if (rc != ILQG_OK) return rc;
+  ProfScope prof(h, 1);
+  k_lq_open_loop<<<(h->B + KOL_WARPS - 1) / KOL_WARPS, KOL_WARPS * 32, smem, h->stream>>>(
+      h->d, h->s, h->ol_scratch, only_running, use_lq_x0 ? h->s.lq_x0 : nullptr);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ILQG_OK;
+}
+
 // with_dxs: also produce ILQG_DELTA_XS (an optional output of LQFeedbackSolver::Solve that the
 // iLQ loop itself never reads once ExpectedDecrease is fused into the backward sweep)
 int DispatchBackward(SubSolver* h, int only_running, bool with_dxs, Sel sel = Sel{SEL_ALL, nullptr, nullptr}) {
+  // with_dxs is the stand-alone ilqg_lq_backward: the only caller with a nonzero x0 argument
+  if (h->open_loop) return LaunchOpenLoop(h, only_running, with_dxs);  // writes delta_xs itself
   int rc = ILQG_ERR_UNSUPPORTED;
   bool hw = true;
   switch (h->dims_key) {
@@ -330,7 +349,7 @@ int DispatchBackward(SubSolver* h, int only_running, bool with_dxs, Sel sel = Se
     case 4: rc = LaunchBackwardHw<12, 6, 3>(h, only_running, sel); break;
   }
   if (rc == ILQG_OK && hw && with_dxs) {
-    k_delta_xs<<<(h->B + 3) / 4, 128, sizeof(float) * 4 * 2 * ILQG_MAX_XDIM, h->stream>>>(h->d, h->s);
+    k_delta_xs<<<(h->B + 3) / 4, 128, sizeof(float) * 4 * 2 * ILQG_MAX_XDIM, h->stream>>>(h->d, h->s, h->s.lq_x0);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
   }
@@ -595,7 +614,7 @@ int IteratePipelined(SubSolver* h, int n) {
 bool CanPipeline(const SubSolver* h, int max_iters) {
   const bool hw = h->dims_key == 0 || h->dims_key == 1 || h->dims_key == 4;
   const bool one_window = h->ls.JB >= std::max(1, h->p.max_backtracking_steps) - h->ls.JA;
-  return h->pipeline && max_iters > 1 && h->pat_ok && hw && one_window && h->p.linesearch && !h->profiling;
+  return h->pipeline && !h->open_loop && max_iters > 1 && h->pat_ok && hw && one_window && h->p.linesearch && !h->profiling;
 }
 
 int LaunchSolveBegin(SubSolver* h) {
@@ -723,7 +742,6 @@ int ilqg_destroy(SubHandle h);
 int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params, int batch, int device,
                 SubHandle* out) {
   if (!desc || !params || !out || batch < 1) return ILQG_ERR_INVALID_ARGUMENT;
-  if (params->open_loop) return ILQG_ERR_UNSUPPORTED;
   SubSolver* h = new (std::nothrow) SubSolver();
   if (!h) return ILQG_ERR_OUT_OF_MEMORY;
   std::vector<int> lidx;
@@ -744,11 +762,13 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
   h->dims_key = -1;
   for (int k = 0; k < kNumDims; k++)
     if (kDims[k].n == h->d.n && kDims[k].M == h->d.M && kDims[k].N == h->d.N) h->dims_key = k;
-  if (h->dims_key < 0) {
+  // the open-loop kernel takes run-time dimensions; the feedback kernels are instantiated per shape
+  if (h->dims_key < 0 && !params->open_loop) {
     delete h;
     return ILQG_ERR_UNSUPPORTED;
   }
   h->host_desc = *desc;
+  h->open_loop = params->open_loop != 0;
   h->B = batch;
   h->device = device;
   h->layout.batch = batch;
@@ -804,6 +824,7 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
 #define ALLOC(ptr, count)                                          \
   if ((rc = DevAlloc(h, &(ptr), (count))) != ILQG_OK) return fail(rc)
   ALLOC(s.x0, B * n);
+  ALLOC(s.lq_x0, B * n);
   for (int k = 0; k < 2; k++) {
     ALLOC(s.op_xs[k], B * T * n);
     ALLOC(s.op_us[k], B * T * M);
@@ -816,6 +837,8 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
   ALLOC(s.prob_a, B * T * M);
   ALLOC(s.rec, B * T * (size_t)h->d.rec);
   ALLOC(s.dxs, B * T * n);
+  if (h->open_loop)
+    ALLOC(h->ol_scratch, B * T * (size_t)ol_layout(h->d.n, h->d.M, h->d.N, h->d.rec - h->d.offl).srec);
   ALLOC(s.lambdas, B * (size_t)h->d.num_constraints * T);
   ALLOC(s.mu, B);
   ALLOC(s.last_merit, B);
@@ -966,6 +989,7 @@ int ilqg_upload(SubHandle h, int what, const void* src, size_t bytes) {
     case ILQG_MU: dst = h->s.mu; want = sizeof(float) * B; break;
     case ILQG_MERIT: dst = h->s.last_merit; want = sizeof(float) * B; break;
     case ILQG_X0: dst = h->s.x0; want = sizeof(float) * B * h->d.n; break;
+    case ILQG_LQ_X0: dst = h->s.lq_x0; want = sizeof(float) * B * h->d.n; break;
     case ILQG_TIME_OF_EXTREME: {
       if (bytes != sizeof(int) * B * N) return ILQG_ERR_SIZE_MISMATCH;
       CUDA_TRY(cudaMemcpyAsync(h->s.te_new, src, bytes, cudaMemcpyHostToDevice, h->stream));
@@ -1115,6 +1139,7 @@ int ilqg_download(SubHandle h, int what, void* dst, size_t bytes) {
     case ILQG_LAMBDAS: return DownloadFlat(h, s.lambdas, 4, (size_t)d.num_constraints * T, dst, bytes);
     case ILQG_TOTAL_COSTS: return DownloadFlat(h, s.total_costs, 4, N, dst, bytes);
     case ILQG_X0: return DownloadFlat(h, s.x0, 4, n, dst, bytes);
+    case ILQG_LQ_X0: return DownloadFlat(h, s.lq_x0, 4, n, dst, bytes);
     case ILQG_MU: return DownloadFlat(h, s.mu, 4, 1, dst, bytes);
     case ILQG_MERIT: return DownloadFlat(h, s.last_merit, 4, 1, dst, bytes);
     case ILQG_EXPECTED_DECREASE: return DownloadFlat(h, s.expected_decrease, 4, 1, dst, bytes);
@@ -1376,7 +1401,7 @@ static size_t PerInstance(const ilqg_solver* h, int what) {
     case ILQG_QUAD_RGRAD: return T * (size_t)lo.r_floats;
     case ILQG_LAMBDAS: return (size_t)lo.num_constraints * T;
     case ILQG_TOTAL_COSTS: case ILQG_TIME_OF_EXTREME: return N;
-    case ILQG_X0: return n;
+    case ILQG_X0: case ILQG_LQ_X0: return n;
     case ILQG_MU: case ILQG_MERIT: case ILQG_EXPECTED_DECREASE: case ILQG_STEP: case ILQG_MAX_CONSTRAINT_ERROR:
     case ILQG_STATUS: case ILQG_ITERS: case ILQG_BACKTRACKS:
     case ILQG_AL_SUCCESS: case ILQG_AL_ITERATES: case ILQG_AL_STATE: return 1;

@@ -617,11 +617,11 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
   if (active && l16 == 0) s.expected_decrease[b] = expected_decrease;
 }
 
-// delta_xs of LQFeedbackSolver::Solve (src/lq_feedback_solver.cpp:217-241) with x0 argument 0:
-// dx_0 = 0, dx_{k+1} = A_k dx_k - sum_i B_i alpha_i[k].  One warp per instance; only
+// delta_xs of LQFeedbackSolver::Solve (src/lq_feedback_solver.cpp:217-241): dx_0 = the x0 argument
+// (ILQG_LQ_X0), dx_{k+1} = A_k dx_k - sum_i B_i alpha_i[k].  One warp per instance; only
 // launched when delta_xs are requested (ilqg_lq_backward / ILQG_DELTA_XS), never by ilqg_iterate.
 __global__ void __launch_bounds__(128)
-k_delta_xs(const __grid_constant__ DevDesc d, Slab s) {
+k_delta_xs(const __grid_constant__ DevDesc d, Slab s, const float* x0arg) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * 4 + warp;
@@ -631,7 +631,7 @@ k_delta_xs(const __grid_constant__ DevDesc d, Slab s) {
   float* dxn = dx + ILQG_MAX_XDIM;
   const float* alpha = s.st_a[1 - s.st_cur[b]] + (size_t)b * T * M;
   float* out = s.dxs + (size_t)b * T * n;
-  for (int a = lane; a < n; a += 32) dx[a] = 0.f;
+  for (int a = lane; a < n; a += 32) dx[a] = x0arg ? x0arg[(size_t)b * n + a] : 0.f;
   __syncwarp();
   for (int kk = 0; kk < T; kk++) {
     const float* rec = s.rec + ((size_t)b * T + kk) * d.rec;

@@ -21,6 +21,7 @@ namespace cg = cooperative_groups;
 struct Slab {
   int B;
   float* x0;                        // [B][n]
+  float* lq_x0;                     // [B][n]  ILQG_LQ_X0: x0 argument of a stand-alone LQ solve
   float* op_xs[2];                  // [B][T][n]   operating point double buffer
   float* op_us[2];                  // [B][T][M]
   float* st_P[2];                   // [B][T][M][n] strategies double buffer

@@ -159,7 +159,8 @@ typedef struct {
   float geometric_alpha_scaling;
   int32_t max_backtracking_steps;
   float expected_decrease_fraction;
-  int32_t open_loop; /* must be 0: LQOpenLoopSolver is not on this path */
+  int32_t open_loop; /* nonzero: LQOpenLoopSolver (src/lq_open_loop_solver.cpp) instead of
+                      * LQFeedbackSolver, as in ILQSolver's constructor (ilq_solver.h:76-81) */
   /* augmented Lagrangian outer loop */
   int32_t unconstrained_solver_max_iters;
   float geometric_mu_scaling;
@@ -221,7 +222,10 @@ enum {
   ILQG_MAX_CONSTRAINT_ERROR = 25, /* float [B], from ilqg_al_update / ilqg_al_advance */
   ILQG_AL_SUCCESS = 26,        /* int32 [B] AugmentedLagrangianSolver::Solve's *success */
   ILQG_AL_ITERATES = 27,       /* int32 [B] log->NumIterates() of the AL solve   */
-  ILQG_AL_STATE = 28           /* int32 [B] 0 = none, 1 = active, 2 = finished   */
+  ILQG_AL_STATE = 28,          /* int32 [B] 0 = none, 1 = active, 2 = finished   */
+  ILQG_LQ_X0 = 29              /* float [B][n] the `x0` argument of LQSolver::Solve used by
+                                * ilqg_lq_backward (upload; zeros until set).  ilqg_iterate
+                                * always solves with x0 - xs[0] = 0 (ilq_solver.cpp:140-143) */
 };
 
 typedef struct ilqg_solver* ilqg_handle;
@@ -275,8 +279,10 @@ int ilqg_solve_begin(ilqg_handle h);
  * (:471-490) at the current operating point, fused; fills the LQ records. */
 int ilqg_linearize_quadraticize(ilqg_handle h);
 
-/* LQFeedbackSolver::Solve (src/lq_feedback_solver.cpp:71-244) on the current
- * LQ records with x0 argument = 0 (x0 - xs[0], ilq_solver.cpp:140-143), plus
+/* LQFeedbackSolver::Solve (src/lq_feedback_solver.cpp:71-244) -- or, with
+ * ilqg_solver_params::open_loop, LQOpenLoopSolver::Solve
+ * (src/lq_open_loop_solver.cpp:73-195) -- on the current LQ records with the
+ * x0 argument ILQG_LQ_X0 (zeros unless uploaded; ILQSolver passes x0 - xs[0] = 0), plus
  * ILQSolver::ExpectedDecrease (:364-398).  Result: ILQG_LQ_PS/ILQG_LQ_ALPHAS,
  * ILQG_DELTA_XS, ILQG_EXPECTED_DECREASE. */
 int ilqg_lq_backward(ilqg_handle h);

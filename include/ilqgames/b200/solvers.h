@@ -278,7 +278,6 @@ class ILQSolver : public GameSolver {
       : GameSolver(problem, params) {
     // the problem is described once, like the reference sizes its scratch here (:76-94)
     CHECK(b200::DescribeProblem(*problem_, &desc_)) << "a cost, constraint or dynamics class has no device record";
-    CHECK(!params_.open_loop) << "LQOpenLoopSolver is not on this path";
     abi_params_ = b200::ToAbi(params_);
     single_.reset(new b200::Handle(desc_, abi_params_, 1));
   }
@@ -365,7 +364,8 @@ class ILQSolver : public GameSolver {
   std::unique_ptr<b200::Handle> single_, batch_;
 };
 
-// ---- include/ilqgames/solver/lq_solver.h:57-81, lq_feedback_solver.h:70-124 --------------------
+// ---- include/ilqgames/solver/lq_solver.h:57-81, lq_feedback_solver.h:70-124,
+// ---- lq_open_loop_solver.h:72-135 --------------------------------------------------------------
 class LQSolver {
  public:
   virtual ~LQSolver() {}
@@ -377,29 +377,21 @@ class LQSolver {
  protected:
   LQSolver(const std::shared_ptr<const MultiPlayerIntegrableSystem>& dynamics, size_t num_time_steps)
       : dynamics_(dynamics), num_time_steps_(num_time_steps) { CHECK_NOTNULL(dynamics.get()); }
-  const std::shared_ptr<const MultiPlayerIntegrableSystem> dynamics_;
-  const size_t num_time_steps_;
-};
 
-class LQFeedbackSolver : public LQSolver {
- public:
-  ~LQFeedbackSolver() {}
-  LQFeedbackSolver(const std::shared_ptr<const MultiPlayerIntegrableSystem>& dynamics, size_t num_time_steps,
-                   bool adaptive_regularization = true)
-      : LQSolver(dynamics, num_time_steps), adaptive_regularization_(adaptive_regularization) {}
-
-  // src/lq_feedback_solver.cpp:71-244.  quadraticization[k][i].control holds R_ij, r_ij for the
-  // players j whose control player i penalises.  costates are not produced (the reference
-  // computes them and never reads them); passing a non-null pointer is an error.
-  std::vector<Strategy> Solve(const std::vector<LinearDynamicsApproximation>& linearization,
-                              const std::vector<std::vector<QuadraticCostApproximation>>& quadraticization,
-                              const VectorXf& x0, std::vector<VectorXf>* delta_xs = nullptr,
-                              std::vector<std::vector<VectorXf>>* costates = nullptr) override {
+  // Both solvers: flatten lin / quad into LQ records, one ilqg_lq_backward on a batch-1 handle.
+  // quadraticization[k][i].control holds R_ij, r_ij for the players j whose control player i
+  // penalises.  costates are not produced (the reference computes them and never reads them,
+  // SURVEY Q4); passing a non-null pointer is an error.
+  std::vector<Strategy> SolveOnDevice(bool open_loop, bool adaptive_regularization,
+                                      const std::vector<LinearDynamicsApproximation>& linearization,
+                                      const std::vector<std::vector<QuadraticCostApproximation>>& quadraticization,
+                                      const VectorXf& x0, std::vector<VectorXf>* delta_xs,
+                                      std::vector<std::vector<VectorXf>>* costates) {
     CHECK(costates == nullptr) << "costates are not produced on this path";
     CHECK_EQ(linearization.size(), num_time_steps_);
     CHECK_EQ(quadraticization.size(), num_time_steps_);
     const int T = (int)num_time_steps_, N = dynamics_->NumPlayers(), n = dynamics_->XDim();
-    if (!handle_) BuildHandle(quadraticization.front());
+    if (!handle_) BuildHandle(quadraticization.front(), open_loop, adaptive_regularization);
     b200::Handle& h = *handle_;
     const ilqg_layout& lo = h.layout();
     const int M = lo.total_udim;
@@ -430,25 +422,28 @@ class LQFeedbackSolver : public LQSolver {
       }
     }
     ILQG_CALL(ilqg_upload_lq(h.get(), A.data(), Bs.data(), Q.data(), l.data(), R.data(), r.data()));
+    std::vector<float> x0f((size_t)n);
+    for (int a = 0; a < n; a++) x0f[(size_t)a] = x0(a);
+    ILQG_CALL(ilqg_upload(h.get(), ILQG_LQ_X0, x0f.data(), sizeof(float) * x0f.size()));
     ILQG_CALL(ilqg_lq_backward(h.get()));
     const auto Ps = h.Download<float>(ILQG_LQ_PS, (size_t)T * M * n), al = h.Download<float>(ILQG_LQ_ALPHAS, (size_t)T * M);
     std::vector<Strategy> strategies = h.StrategiesOf(0, Ps, al);
     if (delta_xs) {
-      // forward pass x* <- A x* - sum_i B_i alpha_i, exactly as written at :237-239
+      // lq_feedback_solver.cpp:217-241 (x* <- A x* - sum_i B_i alpha_i) resp.
+      // lq_open_loop_solver.cpp:158-186 (the optimal state trajectory), computed on the device
+      const auto dx = h.Download<float>(ILQG_DELTA_XS, (size_t)T * n);
       delta_xs->assign(T, VectorXf::Zero(n));
-      VectorXf x_star = x0;
-      for (int k = 0; k < T; k++) {
-        (*delta_xs)[k] = x_star;
-        VectorXf next = linearization[k].A * x_star;
-        for (int i = 0; i < N; i++) next -= linearization[k].Bs[i] * strategies[i].alphas[k];
-        x_star = next;
-      }
+      for (int k = 0; k < T; k++)
+        for (int a = 0; a < n; a++) (*delta_xs)[k](a) = dx[(size_t)k * n + a];
     }
     return strategies;
   }
 
+  const std::shared_ptr<const MultiPlayerIntegrableSystem> dynamics_;
+  const size_t num_time_steps_;
+
  private:
-  void BuildHandle(const std::vector<QuadraticCostApproximation>& quad0) {
+  void BuildHandle(const std::vector<QuadraticCostApproximation>& quad0, bool open_loop, bool adaptive_regularization) {
     ilqg_problem_desc desc;
     std::memset(&desc, 0, sizeof(desc));
     const int N = dynamics_->NumPlayers();
@@ -471,12 +466,46 @@ class LQFeedbackSolver : public LQSolver {
         rec.polyline = -1;
       }
     ilqg_solver_params p = b200::ToAbi(SolverParams());
-    p.adaptive_regularization = adaptive_regularization_;
+    p.adaptive_regularization = adaptive_regularization;
+    p.open_loop = open_loop;
     handle_.reset(new b200::Handle(desc, p, 1));
   }
 
-  const bool adaptive_regularization_;
   std::unique_ptr<b200::Handle> handle_;
+};
+
+class LQFeedbackSolver : public LQSolver {
+ public:
+  ~LQFeedbackSolver() {}
+  LQFeedbackSolver(const std::shared_ptr<const MultiPlayerIntegrableSystem>& dynamics, size_t num_time_steps,
+                   bool adaptive_regularization = true)
+      : LQSolver(dynamics, num_time_steps), adaptive_regularization_(adaptive_regularization) {}
+
+  // src/lq_feedback_solver.cpp:71-244
+  std::vector<Strategy> Solve(const std::vector<LinearDynamicsApproximation>& linearization,
+                              const std::vector<std::vector<QuadraticCostApproximation>>& quadraticization,
+                              const VectorXf& x0, std::vector<VectorXf>* delta_xs = nullptr,
+                              std::vector<std::vector<VectorXf>>* costates = nullptr) override {
+    return SolveOnDevice(false, adaptive_regularization_, linearization, quadraticization, x0, delta_xs, costates);
+  }
+
+ private:
+  const bool adaptive_regularization_;
+};
+
+class LQOpenLoopSolver : public LQSolver {
+ public:
+  ~LQOpenLoopSolver() {}
+  LQOpenLoopSolver(const std::shared_ptr<const MultiPlayerIntegrableSystem>& dynamics, size_t num_time_steps)
+      : LQSolver(dynamics, num_time_steps) {}
+
+  // src/lq_open_loop_solver.cpp:73-195: P stays zero, alphas are the (sign-flipped) open-loop controls
+  std::vector<Strategy> Solve(const std::vector<LinearDynamicsApproximation>& linearization,
+                              const std::vector<std::vector<QuadraticCostApproximation>>& quadraticization,
+                              const VectorXf& x0, std::vector<VectorXf>* delta_xs = nullptr,
+                              std::vector<std::vector<VectorXf>>* costates = nullptr) override {
+    return SolveOnDevice(true, false, linearization, quadraticization, x0, delta_xs, costates);
+  }
 };
 
 // ---- include/ilqgames/solver/augmented_lagrangian_solver.h:60-110 ------------------------------

@@ -190,7 +190,6 @@ int BuildProblem(const ilqg_problem_desc* desc, const ilqg_solver_params* params
   if (d.num_players < 1 || d.num_players > ILQG_MAX_PLAYERS) return ILQG_ERR_INVALID_ARGUMENT;
   if (d.xdim < 1 || d.xdim > ILQG_MAX_XDIM) return ILQG_ERR_INVALID_ARGUMENT;
   if (d.num_costs < 0 || d.num_costs > ILQG_MAX_COSTS) return ILQG_ERR_INVALID_ARGUMENT;
-  if (params->open_loop) return ILQG_ERR_UNSUPPORTED;
   pr->T = d.num_time_steps;
   pr->N = d.num_players;
   pr->n = d.xdim;
@@ -260,6 +259,7 @@ int BuildProblem(const ilqg_problem_desc* desc, const ilqg_solver_params* params
 // ---------------------------- per-instance state ---------------------------
 struct Instance {
   std::vector<real> x0;
+  std::vector<real> lq_x0;  // ILQG_LQ_X0: the x0 argument of a stand-alone LQSolver::Solve
   // Problem::operating_point_ / strategies_ (problem.h:171-172): the warm start
   // every Solve() begins from; only OverwriteSolution changes it.
   std::vector<real> prob_xs, prob_us, prob_Ps, prob_alphas;
@@ -1126,6 +1126,214 @@ void LQFeedbackSolve(const Problem& pr, Instance& in, const real* x0arg) {
   }
 }
 
+// Eigen::LDLT stand-in used for chol_Rs_ (src/lq_open_loop_solver.cpp:124-126): symmetric-pivoted
+// LDL^T of the lower triangle (largest remaining |diagonal| first), then solve for c right-hand
+// sides.  Same arithmetic as oracle/ref_shim/Eigen/Dense (LDLTImpl) so that the oracle and the
+// shim build of the reference agree bit for bit; Eigen's own LDLT is pivoted the same way but
+// blocked differently (rounding-level differences, unpinned like the QR).
+// A is m x m (row-major, destroyed), Bmat is m x c (row-major, becomes the solution).
+void LdltSolve(real* A, int m, real* Bmat, int c) {
+  std::vector<real> w((size_t)m * m), L((size_t)m * m, 0), dvec(m);
+  std::vector<int> perm(m);
+  for (int j = 0; j < m; j++)
+    for (int i = 0; i < m; i++) w[i * m + j] = i >= j ? A[i * m + j] : A[j * m + i];
+  for (int i = 0; i < m; i++) perm[i] = i;
+  for (int k = 0; k < m; k++) {
+    int piv = k;
+    for (int i = k + 1; i < m; i++)
+      if (std::abs(w[i * m + i]) > std::abs(w[piv * m + piv])) piv = i;
+    if (piv != k) {
+      std::swap(perm[k], perm[piv]);
+      for (int j = 0; j < m; j++) std::swap(w[k * m + j], w[piv * m + j]);
+      for (int i = 0; i < m; i++) std::swap(w[i * m + k], w[i * m + piv]);
+    }
+    const real dk = w[k * m + k];
+    dvec[k] = dk;
+    if (dk == 0) {
+      for (int i = k + 1; i < m; i++) w[i * m + k] = 0;
+      continue;
+    }
+    for (int i = k + 1; i < m; i++) w[i * m + k] /= dk;
+    for (int j = k + 1; j < m; j++)
+      for (int i = j; i < m; i++) {
+        w[i * m + j] -= w[i * m + k] * dk * w[j * m + k];
+        w[j * m + i] = w[i * m + j];
+      }
+  }
+  for (int j = 0; j < m; j++) {
+    L[j * m + j] = 1;
+    for (int i = j + 1; i < m; i++) L[i * m + j] = w[i * m + j];
+  }
+  std::vector<real> y(m);
+  for (int j = 0; j < c; j++) {
+    for (int i = 0; i < m; i++) y[i] = Bmat[perm[i] * c + j];
+    for (int i = 0; i < m; i++)
+      for (int k = 0; k < i; k++) y[i] -= L[i * m + k] * y[k];
+    for (int i = 0; i < m; i++) y[i] = dvec[i] != 0 ? y[i] / dvec[i] : (real)0;
+    for (int i = m - 1; i >= 0; i--)
+      for (int k = i + 1; k < m; k++) y[i] -= L[k * m + i] * y[k];
+    for (int i = 0; i < m; i++) Bmat[perm[i] * c + j] = y[i];
+  }
+}
+
+// LQOpenLoopSolver::Solve, src/lq_open_loop_solver.cpp:73-195 (selected by SolverParams::open_loop,
+// include/ilqgames/solver/ilq_solver.h:76-81).  P stays zero; alphas hold the (sign-flipped)
+// open-loop controls; delta_xs is the optimal state trajectory x*.
+void LQOpenLoopSolve(const Problem& pr, Instance& in, const real* x0arg) {
+  const int T = pr.T, n = pr.n, M = pr.M, N = pr.N;
+  const ilqg_problem_desc& d = pr.d;
+  std::vector<real> Ms((size_t)T * N * n * n), ms((size_t)T * N * n);
+  // per step: Lambda (:119-127), the intermediate term (:134-139), warped B_i = R_ii^-1 B_i^T
+  // and warped r_i = R_ii^-1 r_ii (:125-126)
+  std::vector<real> Lam((size_t)T * n * n), inter((size_t)T * n), WB((size_t)T * M * n), Wr((size_t)T * M);
+  std::vector<real> t1(n * n), t2(n * n), X(n * n), tmpv(n), tmpv2(n), Rcopy(ILQG_MAX_UDIM * ILQG_MAX_UDIM),
+      rhs(ILQG_MAX_UDIM * (n + 1)), LamCopy(n * n);
+  std::fill(in.lqPs.begin(), in.lqPs.end(), (real)0);
+  std::fill(in.lqAlphas.begin(), in.lqAlphas.end(), (real)0);
+  auto Mk = [&](int k, int i) { return &Ms[((size_t)k * N + i) * n * n]; };
+  auto mk = [&](int k, int i) { return &ms[((size_t)k * N + i) * n]; };
+  // Lambda^-1 applied to c right-hand sides (qr_capital_lambdas_[kk].solve, :130,143-151,170)
+  auto lam_solve = [&](int kk, real* rhs_nc, int c) {
+    std::memcpy(LamCopy.data(), &Lam[(size_t)kk * n * n], sizeof(real) * n * n);
+    HouseholderQrSolve(LamCopy.data(), n, rhs_nc, c);
+  };
+
+  for (int i = 0; i < N; i++) {  // :112-115
+    std::memcpy(mk(T - 1, i), &in.l[((size_t)(T - 1) * N + i) * n], sizeof(real) * n);
+    std::memcpy(Mk(T - 1, i), &in.Q[((size_t)(T - 1) * N + i) * n * n], sizeof(real) * n * n);
+  }
+  for (int kk = T - 2; kk >= 0; kk--) {
+    const real* A = &in.A[(size_t)kk * n * n];
+    const real* B = &in.B[(size_t)kk * n * M];
+    const real* Rk = &in.R[(size_t)kk * pr.R_floats];
+    const real* rk = &in.r[(size_t)kk * pr.r_floats];
+    real* L = &Lam[(size_t)kk * n * n];
+    for (int a = 0; a < n; a++)
+      for (int c = 0; c < n; c++) L[a * n + c] = a == c ? 1 : 0;
+    for (int i = 0; i < N; i++) {
+      const int mi = d.udim[i], ro = pr.uoff[i], pii = pr.pair_of[i][i];
+      real* Wi = &WB[((size_t)kk * M + ro) * n];   // mi x n
+      real* wri = &Wr[(size_t)kk * M + ro];
+      // warped_Bs = chol(R_ii).solve(B_i^T), warped_rs = chol(R_ii).solve(r_ii)
+      for (int a = 0; a < mi; a++)
+        for (int c = 0; c < n; c++) rhs[a * (n + 1) + c] = B[c * M + ro + a];
+      for (int a = 0; a < mi; a++) rhs[a * (n + 1) + n] = rk[pr.pair_roff[pii] + a];
+      std::memcpy(Rcopy.data(), Rk + pr.pair_Roff[pii], sizeof(real) * mi * mi);
+      LdltSolve(Rcopy.data(), mi, rhs.data(), n + 1);
+      for (int a = 0; a < mi; a++) {
+        for (int c = 0; c < n; c++) Wi[a * n + c] = rhs[a * (n + 1) + c];
+        wri[a] = rhs[a * (n + 1) + n];
+      }
+      // Lambda += (B_i * warped_B_i) * M_{k+1,i}
+      const real* Mn = Mk(kk + 1, i);
+      for (int a = 0; a < n; a++)
+        for (int c = 0; c < n; c++) {
+          real acc = 0;
+          for (int q = 0; q < mi; q++) acc += B[a * M + ro + q] * Wi[q * n + c];
+          t1[a * n + c] = acc;
+        }
+      for (int a = 0; a < n; a++)
+        for (int c = 0; c < n; c++) {
+          real acc = 0;
+          for (int q = 0; q < n; q++) acc += t1[a * n + q] * Mn[q * n + c];
+          L[a * n + c] += acc;
+        }
+    }
+    // intermediate = - sum_i B_i (warped_B_i m_{k+1,i} + warped_r_i)
+    real* it = &inter[(size_t)kk * n];
+    for (int a = 0; a < n; a++) it[a] = 0;
+    for (int i = 0; i < N; i++) {
+      const int mi = d.udim[i], ro = pr.uoff[i];
+      const real* Wi = &WB[((size_t)kk * M + ro) * n];
+      const real* mn = mk(kk + 1, i);
+      real v[ILQG_MAX_UDIM];
+      for (int a = 0; a < mi; a++) {
+        real acc = 0;
+        for (int q = 0; q < n; q++) acc += Wi[a * n + q] * mn[q];
+        v[a] = acc + Wr[(size_t)kk * M + ro + a];
+      }
+      for (int a = 0; a < n; a++) {
+        real acc = 0;
+        for (int q = 0; q < mi; q++) acc += B[a * M + ro + q] * v[q];
+        it[a] -= acc;
+      }
+    }
+    // X = Lambda^-1 A ; s = Lambda^-1 intermediate
+    std::memcpy(X.data(), A, sizeof(real) * n * n);
+    lam_solve(kk, X.data(), n);
+    for (int a = 0; a < n; a++) tmpv[a] = it[a];
+    lam_solve(kk, tmpv.data(), 1);
+    for (int i = 0; i < N; i++) {
+      const real* Mn = Mk(kk + 1, i);
+      const real* mn = mk(kk + 1, i);
+      const real* Qi = &in.Q[((size_t)kk * N + i) * n * n];
+      const real* li = &in.l[((size_t)kk * N + i) * n];
+      // M_k = Q + (A^T M_{k+1}) X
+      for (int a = 0; a < n; a++)
+        for (int c = 0; c < n; c++) {
+          real acc = 0;
+          for (int q = 0; q < n; q++) acc += A[q * n + a] * Mn[q * n + c];
+          t2[a * n + c] = acc;
+        }
+      real* Mc = Mk(kk, i);
+      for (int a = 0; a < n; a++)
+        for (int c = 0; c < n; c++) {
+          real acc = 0;
+          for (int q = 0; q < n; q++) acc += t2[a * n + q] * X[q * n + c];
+          Mc[a * n + c] = Qi[a * n + c] + acc;
+        }
+      // m_k = l + A^T (m_{k+1} + M_{k+1} s)
+      for (int a = 0; a < n; a++) {
+        real acc = 0;
+        for (int q = 0; q < n; q++) acc += Mn[a * n + q] * tmpv[q];
+        tmpv2[a] = mn[a] + acc;
+      }
+      real* mc = mk(kk, i);
+      for (int a = 0; a < n; a++) {
+        real acc = 0;
+        for (int q = 0; q < n; q++) acc += A[q * n + a] * tmpv2[q];
+        mc[a] = li[a] + acc;
+      }
+    }
+  }
+  // :158-192 forward pass
+  std::vector<real> xstar(x0arg, x0arg + n), last(n);
+  for (int kk = 0; kk < T - 1; kk++) {
+    for (int a = 0; a < n; a++) in.dxs[(size_t)kk * n + a] = xstar[a];
+    const real* A = &in.A[(size_t)kk * n * n];
+    last = xstar;
+    for (int a = 0; a < n; a++) {
+      real acc = 0;
+      for (int q = 0; q < n; q++) acc += A[a * n + q] * last[q];
+      xstar[a] = acc + inter[(size_t)kk * n + a];
+    }
+    lam_solve(kk, xstar.data(), 1);
+    for (int i = 0; i < N; i++) {
+      const int mi = d.udim[i], ro = pr.uoff[i];
+      const real* Wi = &WB[((size_t)kk * M + ro) * n];
+      const real* Mn = Mk(kk + 1, i);
+      const real* mn = mk(kk + 1, i);
+      for (int a = 0; a < n; a++) {
+        real acc = 0;
+        for (int q = 0; q < n; q++) acc += Mn[a * n + q] * xstar[q];
+        tmpv[a] = acc + mn[a];
+      }
+      for (int a = 0; a < mi; a++) {
+        real acc = 0;
+        for (int q = 0; q < n; q++) acc += Wi[a * n + q] * tmpv[q];
+        in.lqAlphas[(size_t)kk * M + ro + a] = acc + Wr[(size_t)kk * M + ro + a];
+      }
+    }
+  }
+  for (int a = 0; a < n; a++) in.dxs[(size_t)(T - 1) * n + a] = xstar[a];
+}
+
+// LQSolver::Solve through ILQSolver::lq_solver_ (ilq_solver.h:76-81)
+void LQSolve(const Problem& pr, Instance& in, const real* x0arg) {
+  if (pr.p.open_loop) LQOpenLoopSolve(pr, in, x0arg);
+  else LQFeedbackSolve(pr, in, x0arg);
+}
+
 // ILQSolver::ExpectedDecrease, src/ilq_solver.cpp:364-398 (as written)
 real ExpectedDecrease(const Problem& pr, const Instance& in) {
   const int T = pr.T, n = pr.n, M = pr.M, N = pr.N;
@@ -1242,6 +1450,7 @@ namespace {
 void InitInstance(const Problem& pr, Instance& in) {
   const int T = pr.T, n = pr.n, M = pr.M, N = pr.N;
   in.x0.assign(n, 0);
+  in.lq_x0.assign(n, 0);
   in.prob_xs.assign((size_t)T * n, 0);
   in.prob_us.assign((size_t)T * M, 0);
   in.prob_Ps.assign((size_t)T * M * n, 0);
@@ -1294,7 +1503,7 @@ void IterateOnce(const Problem& pr, Instance& in) {
   LinearizeAll(pr, in);
   in.te_quad = in.te_new;
   std::vector<real> zero(pr.n, 0);
-  LQFeedbackSolve(pr, in, zero.data());
+  LQSolve(pr, in, zero.data());
   bool has_converged = false;
   if (!ModifyLQStrategies(pr, in, &has_converged)) {
     in.status = ILQG_STATUS_LINESEARCH_FAILED;
@@ -1444,6 +1653,10 @@ int ilqg_upload(ilqg_handle h, int what, const void* src, size_t bytes) {
       return ILQG_OK;
     case ILQG_X0:
       return ilqg_upload_x0(h, f, bytes);
+    case ILQG_LQ_X0:
+      if (bytes != sizeof(float) * B * pr.n) return ILQG_ERR_SIZE_MISMATCH;
+      for (int b = 0; b < B; b++) h->inst[b].lq_x0.assign(f + (size_t)b * pr.n, f + (size_t)(b + 1) * pr.n);
+      return ILQG_OK;
   }
   return ILQG_ERR_INVALID_ARGUMENT;
 }
@@ -1497,10 +1710,9 @@ int ilqg_linearize_quadraticize(ilqg_handle h) {
 
 int ilqg_lq_backward(ilqg_handle h) {
   if (!h) return ILQG_ERR_BAD_HANDLE;
-  std::vector<real> zero(h->pr.n, 0);
   for (auto& in : h->inst) {
     in.te_quad = in.te_new;
-    LQFeedbackSolve(h->pr, in, zero.data());
+    LQSolve(h->pr, in, in.lq_x0.data());
     in.expected_decrease = ExpectedDecrease(h->pr, in);
   }
   return ILQG_OK;
@@ -1701,6 +1913,7 @@ int ilqg_download(ilqg_handle h, int what, void* dst, size_t bytes) {
     case ILQG_LAMBDAS: return vec(&Instance::lambdas);
     case ILQG_TOTAL_COSTS: return vec(&Instance::total_costs);
     case ILQG_X0: return vec(&Instance::x0);
+    case ILQG_LQ_X0: return vec(&Instance::lq_x0);
     case ILQG_MU: return scal(&Instance::mu);
     case ILQG_MERIT: return scal(&Instance::last_merit);
     case ILQG_EXPECTED_DECREASE: return scal(&Instance::expected_decrease);

@@ -128,6 +128,62 @@ void TestLQMatchesLyapunovIterations() {
               strategies[0].Ps[0](0, 0), strategies[0].Ps[0](0, 1), strategies[1].Ps[0](0, 0), strategies[1].Ps[0](0, 1));
 }
 
+// LQOpenLoopSolverTest.NashEquilibrium (test/test_lq_solver.cpp:347-379): on the same game with
+// nominal 0.5 and x0 = (1, 1), no player lowers its own open-loop cost by moving one of its
+// alphas by -+0.1 (NumericalCheckLocalNashEquilibrium(..., open_loop = true),
+// src/check_local_nash_equilibrium.cpp:60-135; costs as ComputeStrategyCosts with open_loop:
+// T - 1 steps, state cost at the next state, src/compute_strategy_costs.cpp:61-105).
+void TestLQOpenLoopIsNash() {
+  auto dynamics = std::make_shared<TwoPlayerPointMass1D>();
+  const size_t T = time::kNumTimeSteps;
+  LQOpenLoopSolver solver(dynamics, T);
+  const LinearDynamicsApproximation lin = dynamics->Linearize();
+  std::vector<LinearDynamicsApproximation> linearization(T, lin);
+  const float nominal = 0.5f, rel = 0.1f;
+  const float Qw[2] = {1.0f, rel}, Rw[2][2] = {{1.0f, rel}, {rel, 1.0f}};
+  std::vector<QuadraticCostApproximation> quad_k(2, QuadraticCostApproximation(2));
+  auto one = [](float v) { MatrixXf m(1, 1); m(0, 0) = v; return m; };
+  auto onev = [](float v) { VectorXf m(1); m(0) = v; return m; };
+  for (int i = 0; i < 2; i++) {
+    quad_k[i].state.hess = Qw[i] * MatrixXf::Identity(2, 2);
+    quad_k[i].state.grad = VectorXf::Constant(2, -Qw[i] * nominal);  // weight * (x - nominal) at x = 0
+    for (int j = 0; j < 2; j++)
+      quad_k[i].control.emplace((PlayerIndex)j, SingleCostApproximation(one(Rw[i][j]), onev(-Rw[i][j] * nominal)));
+  }
+  std::vector<std::vector<QuadraticCostApproximation>> quadraticization(T, quad_k);
+  VectorXf x0 = VectorXf::Constant(2, 1.0f);
+  std::vector<VectorXf> delta_xs;
+  const std::vector<Strategy> strategies = solver.Solve(linearization, quadraticization, x0, &delta_xs);
+  EXPECT(strategies.size() == 2 && delta_xs.size() == T);
+  for (size_t k = 0; k < T; k++) EXPECT(strategies[0].Ps[k].cwiseAbsMax() == 0.0f && strategies[1].Ps[k].cwiseAbsMax() == 0.0f);
+
+  auto cost = [&](int player, int pk, int pi, double delta) {
+    double x[2] = {1.0, 1.0}, total = 0.0;
+    for (size_t k = 0; k + 1 < T; k++) {
+      double u[2];
+      for (int i = 0; i < 2; i++) u[i] = -(double)strategies[i].alphas[k](0) - (((int)k == pk && i == pi) ? delta : 0.0);
+      double nx[2];
+      for (int a = 0; a < 2; a++)
+        nx[a] = lin.A(a, 0) * x[0] + lin.A(a, 1) * x[1] + lin.Bs[0](a, 0) * u[0] + lin.Bs[1](a, 0) * u[1];
+      x[0] = nx[0]; x[1] = nx[1];
+      for (int a = 0; a < 2; a++) total += 0.5 * Qw[player] * (x[a] - nominal) * (x[a] - nominal);
+      for (int j = 0; j < 2; j++) total += 0.5 * Rw[player][j] * (u[j] - nominal) * (u[j] - nominal);
+    }
+    return total;
+  };
+  for (int i = 0; i < 2; i++) {
+    const double base = cost(i, -1, -1, 0.0);
+    for (int k = 0; k + 1 < (int)T; k++)
+      for (double delta : {-0.1, 0.1}) EXPECT(cost(i, k, i, delta) >= base - 1e-6);
+  }
+  // delta_xs is the optimal trajectory from x0
+  EXPECT(std::fabs(delta_xs[0](0) - 1.0f) < 1e-6f && std::fabs(delta_xs[0](1) - 1.0f) < 1e-6f);
+  std::vector<float> al;
+  for (size_t k = 0; k < T; k++) { al.push_back(strategies[0].alphas[k](0)); al.push_back(strategies[1].alphas[k](0)); }
+  Dump("lq_open_loop_alphas", al);
+  std::printf("LQOpenLoopSolver is an open-loop Nash equilibrium: alpha[0] = [%.6f %.6f]\n", al[0], al[1]);
+}
+
 template <typename ProblemType>
 std::shared_ptr<Problem> MakeProblem() {
   auto problem = std::make_shared<ProblemType>();
@@ -224,6 +280,7 @@ int main(int argc, char** argv) {
   g_out = std::fopen(argv[1], "wb");
   if (!g_out) return 2;
   TestLQMatchesLyapunovIterations();
+  TestLQOpenLoopIsNash();
   const std::shared_ptr<Problem> problem = MakeProblem<ilqgames_b200_examples::IntersectionProblem>();
   TestProblemDescriptor(problem, "own");
 #ifdef DROPIN_REFERENCE_EXAMPLE

@@ -27,6 +27,7 @@ from ilqgames_b200 import problems  # noqa: E402
 from tests.golden import ref_lib as R  # noqa: E402
 
 ILQ_ITERS = 6       # ILQSolver::Solve cap for the per-iterate fixtures
+OL_ITERS = 4        # same with SolverParams::open_loop
 AL_INNER, AL_OUTER = 10, 40   # unconstrained_solver_max_iters, AL NumIterates cap
 
 CASES = {
@@ -81,6 +82,21 @@ def run_case(ref: R.RefLibrary, name: str):
     lq = [ref.lin_quad(which, x0[b], rp) for b in range(nlq)]
     for key in ("A", "B", "Q", "l", "R", "r"):
         out[f"lq_{key}"] = np.stack([d[key] for d in lq])
+
+    # SolverParams::open_loop: ILQSolver on LQOpenLoopSolver (ilq_solver.h:76-81)
+    nol = min(6, B)
+    pol = params(max_solver_iters=OL_ITERS, open_loop=1)
+    rpol = R.RefParams.from_abi(pol)
+    ol = [ref.solve(which, R.ILQ, x0[b], rpol, max_log=OL_ITERS + 1) for b in range(nol)]
+    ol_xs = np.full((nol, OL_ITERS + 1, T, n), np.nan, np.float32)
+    ol_us = np.full((nol, OL_ITERS + 1, T, M), np.nan, np.float32)
+    for b, r in enumerate(ol):
+        ol_xs[b, :r["iterates"]], ol_us[b, :r["iterates"]] = r["xs"], r["us"]
+    out.update(ol_iters=np.int32(OL_ITERS), ol_xs=ol_xs, ol_us=ol_us,
+               ol_alphas=np.stack([r["alphas"] for r in ol]),
+               ol_Ps_absmax=np.float32(max(np.abs(r["Ps"]).max() for r in ol)),
+               ol_iterates=np.array([r["iterates"] for r in ol], np.int32),
+               ol_success=np.array([r["success"] for r in ol], np.int32))
 
     if nc > 0:
         nal = 6

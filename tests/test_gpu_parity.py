@@ -283,6 +283,73 @@ def test_against_reference_fixture(product, oracle64, name):
     assert compared >= 6, f"only {compared} (instance, iterate) pairs were comparable"
 
 
+# ------------------------------------------------------------------ open-loop LQ solver
+def test_open_loop_lq_reference_test_system(product, oracle):
+    """LQOpenLoopSolver::Solve on the system of LQOpenLoopSolverTest (test/test_lq_solver.cpp:
+    143-177, 347-379; x0 = ones, nominal 0.5): CUDA vs oracle, alphas and delta_xs."""
+    from tests.test_oracle_pins import solve_lq_open_loop
+    x0 = np.ones(2)
+    Pc, ac, dc, _ = solve_lq_open_loop(product, 0.5, x0)
+    Po, ao, do, _ = solve_lq_open_loop(oracle, 0.5, x0)
+    assert np.all(Pc == 0) and np.all(Po == 0)
+    close(ac[None], ao[None], tol=1e-4, what="open-loop alphas")
+    close(dc[None], do[None], tol=1e-4, what="open-loop delta_xs")
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_open_loop_stage_parity(product, oracle, oracle64, name):
+    """One LQOpenLoopSolver::Solve on the LQ records of the initial rollout of each example:
+    alphas, delta_xs, expected decrease against the oracle, on the instances where the fp32 and
+    fp64 oracles agree."""
+    build, params, x0f = CONFIGS[name]
+    desc, _ = build()
+    x0 = x0f(16)
+    hs = []
+    for lib in (product, oracle, oracle64):
+        h = abi.Handle(lib, desc, params(open_loop=1), x0.shape[0], 0)
+        h.upload_x0(x0)
+        h.solve_begin()
+        h.linearize_quadraticize()
+        h.lq_backward()
+        hs.append(h)
+    c, o, o64 = hs
+    good = wellposed(o.download(abi.LQ_ALPHAS), o64.download(abi.LQ_ALPHAS)) & tame(o.download(abi.LQ_ALPHAS))
+    assert good.sum() >= 4, f"only {good.sum()} well-posed instances"
+    assert np.all(c.download(abi.LQ_PS) == 0)
+    close(c.download(abi.LQ_ALPHAS), o.download(abi.LQ_ALPHAS), tol=1e-3, rows=good, what="alphas")
+    close(c.download(abi.DELTA_XS), o.download(abi.DELTA_XS), tol=1e-3, rows=good, what="delta_xs")
+    close(c.download(abi.EXPECTED_DECREASE), o.download(abi.EXPECTED_DECREASE), tol=1e-3, atol=1e-3,
+          rows=good, what="expected decrease")
+    for h in hs:
+        h.close()
+
+
+@pytest.mark.parametrize("name", ["three_player_intersection", "roundabout_merging"])
+def test_open_loop_against_reference_fixture(product, name):
+    """ILQSolver on LQOpenLoopSolver: the CUDA path against the iterates the reference's own sources
+    logged (tests/golden/ref_*.npz, keys ol_*)."""
+    g = np.load(os.path.join(GOLDEN, f"ref_{name}.npz"))
+    build, params, _ = CONFIGS[name]
+    desc, _ = build()
+    nol = g["ol_xs"].shape[0]
+    iters = int(g["ol_iters"])
+    compared = 0
+    for it in range(1, iters + 1):
+        h = abi.Handle(product, desc, params(max_solver_iters=it, open_loop=1), nol, 0)
+        h.upload_x0(g["x0"][:nol])
+        h.solve_begin()
+        h.solve(chunk=it)
+        logged = g["ol_iterates"] > it
+        flow = (h.download(abi.ITERS) == it) & (h.download(abi.STATUS) != abi.STATUS_LINESEARCH_FAILED)
+        assert flow[logged].mean() >= 0.75
+        ok = logged & flow
+        close(h.download(abi.XS), g["ol_xs"][:, it], tol=2e-3, atol=1e-3, rows=ok, what=f"open-loop xs_{it}")
+        close(h.download(abi.US), g["ol_us"][:, it], tol=2e-3, atol=1e-3, rows=ok, what=f"open-loop us_{it}")
+        compared += int(ok.sum())
+        h.close()
+    assert compared >= 6
+
+
 # ------------------------------------------------------------------ full solves
 @pytest.mark.parametrize("name,batch,iters", [("three_player_intersection", 64, 10),
                                               ("roundabout_merging", 32, 3), ("air_3d", 36, 10)])

@@ -179,6 +179,87 @@ def test_lq_feedback_is_local_nash(oracle, nominal):
         assert np.allclose(alphas[0], [-0.383023, -0.499542], atol=2e-4)
 
 
+def solve_lq_open_loop(lib, nominal, x0):
+    desc = problems.lq_only(100, 2, [1, 1], cross_pairs=[(0, 1), (1, 0)])
+    h = abi.Handle(lib, desc, abi.SolverParams.defaults(open_loop=1), 1)
+    arrs, mats = lq_test_system(nominal)
+    h.upload_lq(**arrs)
+    h.upload(abi.LQ_X0, np.asarray(x0, np.float32)[None])
+    h.lq_backward()
+    return h.download(abi.LQ_PS)[0], h.download(abi.LQ_ALPHAS)[0], h.download(abi.DELTA_XS)[0], mats
+
+
+def _open_loop_cost(A, B1, B2, Q, l, R, r, alphas, x0, perturb=None):
+    """ComputeStrategyCosts(..., open_loop = true), src/compute_strategy_costs.cpp:61-105: controls
+    u_i = -alpha_i (zero operating point), T - 1 steps, state costs taken at the NEXT state
+    (PlayerCost::EvaluateOffset, src/player_cost.cpp:175-192)."""
+    T = alphas.shape[0]
+    x = x0.copy()
+    costs = np.zeros(2)
+    for k in range(T - 1):
+        u = -alphas[k]
+        if perturb is not None:
+            u = u - perturb[k]
+        x = A @ x + B1[:, 0] * u[0] + B2[:, 0] * u[1]
+        for i in range(2):
+            costs[i] += 0.5 * x @ Q[i] @ x + l[i] @ x
+            for j in range(2):
+                costs[i] += 0.5 * R[2 * i + j] * u[j] ** 2 + r[2 * i + j] * u[j]
+    return costs
+
+
+def test_lq_open_loop_is_open_loop_nash(oracle):
+    # LQOpenLoopSolverTest.NashEquilibrium, test/test_lq_solver.cpp:347-379 with
+    # NumericalCheckLocalNashEquilibrium(..., open_loop = true)
+    # (src/check_local_nash_equilibrium.cpp:60-135): alpha_i[k] -+ 0.1 for every player and step.
+    nominal = 0.5
+    x0 = np.ones(2)
+    Ps, alphas, dxs, (A, B1, B2, Q, R) = solve_lq_open_loop(oracle, nominal, x0)
+    assert np.all(Ps == 0)                       # :101-107 P is never touched
+    assert np.all(alphas[-1] == 0)
+    alphas = alphas.astype(np.float64)
+    rel = 0.1
+    l = np.stack([-nominal * np.ones(2), -rel * nominal * np.ones(2)])
+    r = np.array([-1.0, -rel, -rel, -1.0]) * nominal
+    base = _open_loop_cost(A, B1, B2, Q, l, R, r, alphas, x0)
+    for i in range(2):
+        for k in range(99):
+            for sign in (-1.0, 1.0):
+                pert = np.zeros((100, 2))
+                pert[k, i] = sign * 0.1
+                c = _open_loop_cost(A, B1, B2, Q, l, R, r, alphas, x0, pert)
+                assert c[i] >= base[i] - 1e-6, (i, k, sign, c[i], base[i])
+    # delta_xs is the optimal state trajectory: x*_0 = x0, x*_{k+1} = A x*_k - sum_i B_i alpha_i[k]
+    x = x0.copy()
+    for k in range(99):
+        assert np.allclose(dxs[k], x, atol=2e-4)
+        x = A @ x - B1[:, 0] * alphas[k, 0] - B2[:, 0] * alphas[k, 1]
+    assert np.allclose(dxs[99], x, atol=2e-4)
+
+
+def test_single_player_open_loop_equals_feedback_at_first_step(oracle):
+    # SinglePlayerOpenLoopFeedback.TestSameSolution, test/test_lq_solver.cpp:381-436
+    T, dt = 100, 0.1
+    A = np.eye(2)
+    A[0, 1] = dt
+    B = dt * 0.41 * np.eye(2)
+    tile = lambda a: np.broadcast_to(a, (1, T) + a.shape).astype(np.float32).copy()
+    arrs = dict(A=tile(A), Bs=tile(B), Q=tile(np.eye(2)[None]), l=tile(np.zeros((1, 2))),
+                R=tile(np.eye(2).reshape(-1)), r=tile(np.zeros(2)))
+    x0 = np.ones(2, np.float32)
+    out = {}
+    for open_loop in (0, 1):
+        h = abi.Handle(oracle, problems.lq_only(T, 2, [2]), abi.SolverParams.defaults(open_loop=open_loop), 1)
+        h.upload_lq(**arrs)
+        h.upload(abi.LQ_X0, x0[None])
+        h.lq_backward()
+        out[open_loop] = (h.download(abi.LQ_PS)[0], h.download(abi.LQ_ALPHAS)[0])
+    # Strategy::operator()(k, dx, u_ref) = u_ref - P dx - alpha (strategy.h:73-76)
+    u_ol = -out[1][1][0]                                  # (0, zero, zero)
+    u_fb = -(out[0][0][0] @ x0) - out[0][1][0]            # (0, x0, zero)
+    assert np.abs(u_ol - u_fb).max() < 0.01 * np.abs(u_fb).max()
+
+
 # --------------------------------------------------------------------------
 # test/test_quadraticization.cpp
 # --------------------------------------------------------------------------

@@ -118,6 +118,37 @@ def test_oracle_reproduces_reference_lin_quad(oracle, name):
     h.close()
 
 
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_reproduces_reference_open_loop_iterates(oracle, name):
+    """ILQSolver::Solve with SolverParams::open_loop, i.e. on LQOpenLoopSolver::Solve
+    (src/lq_open_loop_solver.cpp:73-195): every logged operating point, final alphas, P = 0."""
+    g = load(name)
+    build, params = CASES[name]
+    desc, _ = build()
+    nol = g["ol_xs"].shape[0]
+    iters = int(g["ol_iters"])
+    h = abi.Handle(oracle, desc, params(max_solver_iters=iters, open_loop=1), nol)
+    h.upload_x0(g["x0"][:nol])
+    h.solve_begin()
+    logged = np.ones(nol, np.int32)
+    for it in range(1, iters + 1):
+        h.iterate(1)
+        status, done = h.download(abi.STATUS), h.download(abi.ITERS)
+        xs, us = h.download(abi.XS), h.download(abi.US)
+        newly = (done == it) & (status != abi.STATUS_LINESEARCH_FAILED)
+        logged += newly
+        for b in np.nonzero(newly)[0]:
+            assert np.array_equal(xs[b], g["ol_xs"][b, it]), (name, b, it)
+            assert np.array_equal(us[b], g["ol_us"][b, it]), (name, b, it)
+    assert np.array_equal(logged, g["ol_iterates"])
+    ok = g["ol_success"] == 1
+    assert np.array_equal((h.download(abi.STATUS) != abi.STATUS_LINESEARCH_FAILED).astype(np.int32),
+                          g["ol_success"])
+    assert np.array_equal(h.download(abi.ALPHAS)[ok], g["ol_alphas"][ok])
+    assert float(g["ol_Ps_absmax"]) == 0.0 and np.all(h.download(abi.PS) == 0)
+    h.close()
+
+
 @pytest.mark.parametrize("name", ["three_player_intersection", "air_3d"])
 def test_oracle_reproduces_reference_augmented_lagrangian(oracle, name):
     """AugmentedLagrangianSolver::Solve (src/augmented_lagrangian_solver.cpp:72-210): final
