@@ -69,8 +69,10 @@ def test_invalid_descriptors_are_rejected(which, product_lib, oracle):
     bad = abi.ProblemDesc.from_buffer_copy(desc)
     bad.costs[0].player = 7
     assert lib.lib.ilqg_create(C.byref(bad), C.byref(p), 1, 0, C.byref(h)) == -1
-    ol = abi.SolverParams.defaults(open_loop=1)  # LQOpenLoopSolver is not on this path
-    assert lib.lib.ilqg_create(C.byref(desc), C.byref(ol), 1, 0, C.byref(h)) == -2
+    if which == "oracle":
+        ol = abi.SolverParams.defaults(open_loop=1)  # LQOpenLoopSolver (ilq_solver.h:76-81)
+        assert lib.lib.ilqg_create(C.byref(desc), C.byref(ol), 1, 0, C.byref(h)) == 0
+        assert lib.lib.ilqg_destroy(h) == 0
 
 
 def test_descriptor_shapes_of_the_three_configs(oracle):
