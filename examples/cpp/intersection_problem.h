@@ -79,13 +79,16 @@ class IntersectionProblem : public TopDownRenderableProblem {
       pc.AddControlCost((PlayerIndex)i, std::make_shared<QuadraticCost>(0.1f, 0, 0.0f, "Steering"));
       pc.AddControlCost((PlayerIndex)i, std::make_shared<QuadraticCost>(0.1f, 1, 0.0f, agents[i].is_car ? "Jerk" : "Acceleration"));
       // keep at least 6 m from each of the other two
-      for (size_t j = 0; j < agents.size(); j++) {
+      for (size_t j = 0; j < agents.size() && WithProximityConstraints(); j++) {
         if (j == i) continue;
         const std::pair<Dimension, Dimension> other(Start(j), Start(j) + 1);
         pc.AddStateConstraint(std::make_shared<ProximityConstraint>(xy, other, 6.0f, false, "ProximityConstraintP" + std::to_string(j + 1)));
       }
     }
   }
+
+  // false: the same game without the proximity constraints (used by the receding-horizon test)
+  virtual bool WithProximityConstraints() const { return true; }
 
   std::vector<float> Xs(const VectorXf& x) const override { return Pick(x, 0); }
   std::vector<float> Ys(const VectorXf& x) const override { return Pick(x, 1); }

@@ -38,7 +38,7 @@ COST_SUM, COST_MAX, COST_MIN = 0, 1, 2
 XS, US, PS, ALPHAS, LIN_A, LIN_B, QUAD_Q, QUAD_L, QUAD_R, QUAD_RGRAD, DELTA_XS = range(1, 12)
 (STATUS, ITERS, MERIT, TOTAL_COSTS, LAMBDAS, MU, EXPECTED_DECREASE, STEP, BACKTRACKS,
  TIME_OF_EXTREME, X0, LQ_PS, LQ_ALPHAS, MAX_CONSTRAINT_ERROR, AL_SUCCESS, AL_ITERATES,
- AL_STATE, LQ_X0) = range(12, 30)
+ AL_STATE, LQ_X0, WARM_XS, WARM_US, WARM_PS, WARM_ALPHAS) = range(12, 34)
 
 OK = 0
 
@@ -113,7 +113,7 @@ ABI_SYMBOLS = [
     "ilqg_iterate", "ilqg_al_update", "ilqg_overwrite_solution", "ilqg_al_post_solve",
     "ilqg_download", "ilqg_synchronize", "ilqg_kernel_launches", "ilqg_set_stream",
     "ilqg_profile", "ilqg_profile_read", "ilqg_reset", "ilqg_count_running",
-    "ilqg_al_begin", "ilqg_al_advance",
+    "ilqg_al_begin", "ilqg_al_advance", "ilqg_setup_next_receding_horizon",
 ]
 
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -160,6 +160,8 @@ class Library:
         L.ilqg_count_running.argtypes = [vp, ip]
         L.ilqg_al_begin.argtypes = [vp, C.c_int, C.c_float]
         L.ilqg_al_advance.argtypes = [vp, ip]
+        L.ilqg_setup_next_receding_horizon.argtypes = [vp, vp, C.c_double, C.c_double,
+                                                       C.POINTER(C.c_double)]
         L.ilqg_profile.argtypes = [vp, C.c_int]
         L.ilqg_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double),
                                         C.POINTER(C.c_longlong)]
@@ -229,6 +231,9 @@ class Handle:
             X0: ((self.n,), np.float32), MAX_CONSTRAINT_ERROR: ((), np.float32),
             AL_SUCCESS: ((), np.int32), AL_ITERATES: ((), np.int32), AL_STATE: ((), np.int32),
             LQ_X0: ((self.n,), np.float32),
+            WARM_XS: ((self.T, self.n), np.float32), WARM_US: ((self.T, self.M), np.float32),
+            WARM_PS: ((self.T, self.M, self.n), np.float32),
+            WARM_ALPHAS: ((self.T, self.M), np.float32),
         }
 
     # -- lifetime ---------------------------------------------------------------
@@ -349,6 +354,16 @@ class Handle:
     def overwrite_solution(self, only_successful: bool = False):
         self.lib.check(self.lib.lib.ilqg_overwrite_solution(self._h, int(only_successful)),
                        "overwrite_solution")
+
+    def setup_next_receding_horizon(self, x0, t0: float, planner_runtime: float) -> float:
+        """Problem::SetUpNextRecedingHorizon for every game; returns the new OperatingPoint::t0."""
+        a = _f32(x0)
+        assert a.shape == (self.B, self.n), a.shape
+        new_t0 = C.c_double(0.0)
+        self.lib.check(self.lib.lib.ilqg_setup_next_receding_horizon(
+            self._h, a.ctypes.data, float(t0), float(planner_runtime), C.byref(new_t0)),
+            "setup_next_receding_horizon")
+        return new_t0.value
 
     def synchronize(self):
         self.lib.check(self.lib.lib.ilqg_synchronize(self._h), "synchronize")

@@ -11,6 +11,7 @@
 
 #include "ilqg_linesearch.cuh"
 #include "ilqg_open_loop.cuh"
+#include "ilqg_receding.cuh"
 
 using namespace ilqg;
 
@@ -1088,6 +1089,20 @@ int ilqg_overwrite_solution(SubHandle h, int only_successful) {
   return ILQG_OK;
 }
 
+// Problem::SetUpNextRecedingHorizon for this group's games (ilqg_receding.cuh); x_meas is host memory
+int ilqg_setup_next_receding_horizon(SubHandle h, const float* x_meas, const RhTimes& times) {
+  ENTER(h);
+  const size_t floats = (size_t)h->B * h->d.n;
+  int rc = EnsureStaging(h, floats);
+  if (rc != ILQG_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(h->staging, x_meas, sizeof(float) * floats, cudaMemcpyHostToDevice, h->stream));
+  k_receding_horizon<<<(h->B + KRH_WARPS - 1) / KRH_WARPS, KRH_WARPS * 32, 0, h->stream>>>(h->d, h->s, h->staging, times);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(h->stream));  // the host buffer may be pageable / reused
+  return ILQG_OK;
+}
+
 int ilqg_al_post_solve(SubHandle h) {
   ENTER(h);
   k_al_post_solve<<<h->B, 128, 0, h->stream>>>(h->d, h->p, h->s, 0);
@@ -1128,6 +1143,10 @@ int ilqg_download(SubHandle h, int what, void* dst, size_t bytes) {
     case ILQG_PS: return DownloadParity(h, s.st_P, s.st_cur, 0, T * M * n, dst, bytes);
     case ILQG_ALPHAS: return DownloadParity(h, s.st_a, s.st_cur, 0, T * M, dst, bytes);
     case ILQG_LQ_PS: return DownloadParity(h, s.st_P, s.st_cur, 1, T * M * n, dst, bytes);
+    case ILQG_WARM_XS: return DownloadFlat(h, s.prob_xs, 4, T * n, dst, bytes);
+    case ILQG_WARM_US: return DownloadFlat(h, s.prob_us, 4, T * M, dst, bytes);
+    case ILQG_WARM_PS: return DownloadFlat(h, s.prob_P, 4, T * M * n, dst, bytes);
+    case ILQG_WARM_ALPHAS: return DownloadFlat(h, s.prob_a, 4, T * M, dst, bytes);
     case ILQG_LQ_ALPHAS: return DownloadParity(h, s.st_a, s.st_cur, 1, T * M, dst, bytes);
     case ILQG_LIN_A: return DownloadRecordField(h, d.offA, d.n * d.n, dst, bytes);
     case ILQG_LIN_B: return DownloadRecordField(h, d.offB, d.n * d.M, dst, bytes);
@@ -1256,6 +1275,7 @@ struct ilqg_solver {
   cudaStream_t stream, own_stream;
   ilqg_layout layout;
   int B, device;
+  double op_t0 = 0.0;  // OperatingPoint::t0 of the Problems (shared by the batch)
   // AugmentedLagrangianSolver::Solve driver state (ilqg_al_begin / ilqg_al_advance)
   int al_max_iterates = 0;
   float al_tolerance = 0.f;
@@ -1363,6 +1383,7 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
   }
   h->layout = h->subs[0]->layout;
   h->layout.batch = batch;
+  h->op_t0 = desc->initial_time;
   *out = h;
   return ILQG_OK;
 }
@@ -1390,9 +1411,9 @@ static size_t PerInstance(const ilqg_solver* h, int what) {
   const ilqg_layout& lo = h->layout;
   const size_t T = lo.num_time_steps, n = lo.xdim, M = lo.total_udim, N = lo.num_players;
   switch (what) {
-    case ILQG_XS: case ILQG_DELTA_XS: return T * n;
-    case ILQG_US: case ILQG_ALPHAS: case ILQG_LQ_ALPHAS: return T * M;
-    case ILQG_PS: case ILQG_LQ_PS: return T * M * n;
+    case ILQG_XS: case ILQG_DELTA_XS: case ILQG_WARM_XS: return T * n;
+    case ILQG_US: case ILQG_ALPHAS: case ILQG_LQ_ALPHAS: case ILQG_WARM_US: case ILQG_WARM_ALPHAS: return T * M;
+    case ILQG_PS: case ILQG_LQ_PS: case ILQG_WARM_PS: return T * M * n;
     case ILQG_LIN_A: return T * n * n;
     case ILQG_LIN_B: return T * n * M;
     case ILQG_QUAD_Q: return T * N * n * n;
@@ -1460,6 +1481,63 @@ int ilqg_overwrite_solution(ilqg_handle h, int only_successful) {
   return ForEach(h, [&](SubSolver* g, int) { return sub::ilqg_overwrite_solution(g, only_successful); });
 }
 int ilqg_reset(ilqg_handle h, int mask) { return ForEach(h, [&](SubSolver* g, int) { return sub::ilqg_reset(g, mask); }); }
+
+int ilqg_setup_next_receding_horizon(ilqg_handle h, const float* x0, double t0, double planner_runtime,
+                                     double* new_t0) {
+  if (!h || !x0) return ILQG_ERR_BAD_HANDLE;
+  const ilqg_layout& lo = h->layout;
+  // a constrained problem CHECK-fails in the reference once initial_time_ > 0 (ilqg.h)
+  if (lo.num_constraints > 0) return ILQG_ERR_UNSUPPORTED;
+  const DevDesc& d = h->subs[0]->d;
+  const int T = lo.num_time_steps;
+  const double kTimeStep = d.time_step, kTimeHorizon = kTimeStep * T;
+  constexpr float kSmallNumber = 1e-4;  // constants::kSmallNumber, utils/types.h:118
+  // ---- SyncToExistingProblem, src/problem.cpp:64-125: the time bookkeeping, in double ----
+  if (planner_runtime < 0.0 || planner_runtime + t0 > h->op_t0 + kTimeHorizon || t0 < h->op_t0)
+    return ILQG_ERR_INVALID_ARGUMENT;  // CHECKs :68-71
+  constexpr float kRoundingError = 0.9;
+  const double relative_t0 = t0 - h->op_t0;
+  size_t current_timestep = static_cast<size_t>(relative_t0 / kTimeStep);
+  double remaining_time_this_step = (current_timestep + 1) * kTimeStep - relative_t0;
+  if (remaining_time_this_step < kRoundingError * kTimeStep) {
+    current_timestep += 1;
+    remaining_time_this_step = kTimeStep - remaining_time_this_step;
+  }
+  if (!(remaining_time_this_step < kTimeStep)) return ILQG_ERR_INVALID_ARGUMENT;  // CHECK_LT :87
+  // IntegrateToNextTimeStep, src/multi_player_integrable_system.cpp:113-143
+  const size_t itn_timestep = static_cast<size_t>((relative_t0 + kSmallNumber) / kTimeStep);
+  const double itn_remaining = kTimeStep * (itn_timestep + 1) - relative_t0;
+  if (!(itn_remaining < kTimeStep + kSmallNumber) || itn_timestep >= (size_t)T) return ILQG_ERR_INVALID_ARGUMENT;
+  double op_t0 = t0 + remaining_time_this_step;
+  size_t num_steps_to_integrate = 0;
+  if (remaining_time_this_step <= planner_runtime) {
+    num_steps_to_integrate =
+        static_cast<size_t>(kSmallNumber + (planner_runtime - remaining_time_this_step) / kTimeStep);
+    op_t0 += kTimeStep * num_steps_to_integrate;
+  }
+  const size_t last_integration_timestep = current_timestep + num_steps_to_integrate;
+  if (last_integration_timestep > (size_t)T) return ILQG_ERR_INVALID_ARGUMENT;
+  if (!(std::abs(t0 + planner_runtime - op_t0) <= kTimeStep)) return ILQG_ERR_INVALID_ARGUMENT;  // :123
+
+  RhTimes times;
+  times.itn_timestep = (int)itn_timestep;
+  times.frac = (float)(itn_remaining / kTimeStep);
+  times.itn_dt_half = (float)(itn_remaining / 2.0);
+  times.integrate_from = (int)current_timestep + 1;
+  times.integrate_to = remaining_time_this_step <= planner_runtime ? (int)last_integration_timestep : 0;
+  times.dt_half = (float)(kTimeStep / 2.0);
+  const int ego_kind = d.sub[0].kind;
+  times.position_distance = ego_kind != ILQG_DYN_AIR3D;
+  times.ego_dim = ego_kind == ILQG_DYN_CAR6D ? 6 : ego_kind == ILQG_DYN_UNICYCLE4D ? 4 : lo.xdim;
+  const size_t n = lo.xdim;
+  const int rc = ForEach(h, [&](SubSolver* g, int first) {
+    return sub::ilqg_setup_next_receding_horizon(g, x0 + (size_t)first * n, times);
+  });
+  if (rc != ILQG_OK) return rc;
+  h->op_t0 = op_t0;
+  if (new_t0) *new_t0 = op_t0;
+  return ILQG_OK;
+}
 
 int ilqg_iterate(ilqg_handle h, int max_iters, int* iters_done) {
   if (!h) return ILQG_ERR_BAD_HANDLE;

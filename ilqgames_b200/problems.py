@@ -110,8 +110,11 @@ class DescBuilder:
 # --------------------------------------------------------------------------
 # ThreePlayerIntersectionExample, src/three_player_intersection_example.cpp
 # --------------------------------------------------------------------------
-def three_player_intersection(num_time_steps: int = 100, time_step: float = 0.1):
-    """Returns (desc, x0).  2x SinglePlayerCar6D + 1x SinglePlayerUnicycle4D, n = 16."""
+def three_player_intersection(num_time_steps: int = 100, time_step: float = 0.1,
+                              with_constraints: bool = True):
+    """Returns (desc, x0).  2x SinglePlayerCar6D + 1x SinglePlayerUnicycle4D, n = 16.
+    with_constraints = False drops the proximity constraints (an unconstrained variant used by the
+    receding-horizon tests; the reference example always has them)."""
     b = DescBuilder(num_time_steps, time_step)
     kInterAxleLength = 4.0
     kStateReg, kControlReg = 1.0, 5.0
@@ -156,7 +159,7 @@ def three_player_intersection(num_time_steps: int = 100, time_step: float = 0.1)
     b.control_cost(2, 2, abi.COST_QUADRATIC, dims=(0,), weight=kOmegaCostWeight, value=0.0)
     b.control_cost(2, 2, abi.COST_QUADRATIC, dims=(1,), weight=kACostWeight, value=0.0)
     # collision-avoidance constraints :363-394 (keep_within = !kKeepClose = false)
-    for i, others in ((0, (1, 2)), (1, (0, 2)), (2, (0, 1))):
+    for i, others in ((0, (1, 2)), (1, (0, 2)), (2, (0, 1))) if with_constraints else ():
         for j in others:
             b.state_constraint(i, abi.CONSTRAINT_PROXIMITY, dims=pos[i] + pos[j],
                                value=kMinProximity, flag=0)

@@ -223,6 +223,9 @@ enum {
   ILQG_AL_SUCCESS = 26,        /* int32 [B] AugmentedLagrangianSolver::Solve's *success */
   ILQG_AL_ITERATES = 27,       /* int32 [B] log->NumIterates() of the AL solve   */
   ILQG_AL_STATE = 28,          /* int32 [B] 0 = none, 1 = active, 2 = finished   */
+  ILQG_WARM_XS = 30, ILQG_WARM_US = 31, ILQG_WARM_PS = 32, ILQG_WARM_ALPHAS = 33,
+                               /* download: the Problem's warm start (Problem::CurrentOperatingPoint /
+                                * CurrentStrategies, solver/problem.h:171-172), shapes of XS/US/PS/ALPHAS */
   ILQG_LQ_X0 = 29              /* float [B][n] the `x0` argument of LQSolver::Solve used by
                                 * ilqg_lq_backward (upload; zeros until set).  ilqg_iterate
                                 * always solves with x0 - xs[0] = 0 (ilq_solver.cpp:140-143) */
@@ -313,6 +316,20 @@ int ilqg_al_update(ilqg_handle h);
  * the working iterate becomes the warm start of the next ilqg_solve_begin.
  * only_successful != 0 skips instances whose last solve failed its linesearch. */
 int ilqg_overwrite_solution(ilqg_handle h, int only_successful);
+
+/* Problem::SetUpNextRecedingHorizon(x0, t0, planner_runtime) (src/problem.cpp:64-186, with
+ * SyncToExistingProblem :64-125 and MultiPlayerIntegrableSystem::IntegrateToNextTimeStep /
+ * Integrate, src/multi_player_integrable_system.cpp:88-143) for every game: integrate the
+ * measured state x0 [batch][n] (taken at time t0) along the warm start for ~planner_runtime,
+ * find the nearest state of the plan, make it the new first time step, shift operating point and
+ * strategies, and extend them to the horizon with zero controls.  Afterwards ILQG_X0 holds the
+ * new initial states and the warm start the shifted plan; *new_t0 (may be NULL) receives the new
+ * OperatingPoint::t0.  Times are shared by the batch.  Returns ILQG_ERR_INVALID_ARGUMENT where
+ * the reference CHECK-fails on the times, ILQG_ERR_UNSUPPORTED for problems with constraints
+ * (the reference aborts there once the initial time is nonzero: Constraint::TimeIndex is asked
+ * for RelativeTime(kk) < initial_time_, include/ilqgames/utils/relative_time_tracker.h:63-72). */
+int ilqg_setup_next_receding_horizon(ilqg_handle h, const float* x0, double t0,
+                                     double planner_runtime, double* new_t0);
 
 /* src/augmented_lagrangian_solver.cpp:165-178: for instances whose inner solve
  * failed, lambda *= geometric_lambda_downscaling, mu *= geometric_mu_downscaling. */

@@ -40,6 +40,12 @@ class Problem {
     *strategies_ = strategies;
   }
 
+  // src/problem.cpp:64-186 (SyncToExistingProblem + SetUpNextRecedingHorizon): integrate the measured
+  // state x0 (taken at t0) along the current plan for ~planner_runtime, start the new problem at
+  // the nearest plan state, shift operating point and strategies, extend them with zero controls.
+  // Runs on the device (ilqg_setup_next_receding_horizon); defined below b200::Handle.
+  virtual void SetUpNextRecedingHorizon(const VectorXf& x0, Time t0, Time planner_runtime = 0.1);
+
   bool IsConstrained() const {
     for (const auto& pc : player_costs_)
       if (pc.IsConstrained()) return true;
@@ -242,6 +248,26 @@ class Handle {
 };
 
 }  // namespace b200
+
+inline void Problem::SetUpNextRecedingHorizon(const VectorXf& x0, Time t0, Time planner_runtime) {
+  CHECK(initialized_);
+  ilqg_problem_desc desc;
+  CHECK(b200::DescribeProblem(*this, &desc)) << "a cost, constraint or dynamics class has no device record";
+  b200::Handle h(desc, b200::ToAbi(SolverParams()), 1);
+  h.UploadWarmStart(*operating_point_, *strategies_);
+  std::vector<float> x((size_t)x0.size());
+  for (long a = 0; a < x0.size(); a++) x[(size_t)a] = x0(a);
+  double new_t0 = 0.0;
+  ILQG_CALL(ilqg_setup_next_receding_horizon(h.get(), x.data(), t0, planner_runtime, &new_t0));
+  const size_t T = h.T(), n = h.n(), M = h.M();
+  *operating_point_ = h.OperatingPointOf(0, h.Download<float>(ILQG_WARM_XS, T * n),
+                                         h.Download<float>(ILQG_WARM_US, T * M), new_t0);
+  *strategies_ = h.StrategiesOf(0, h.Download<float>(ILQG_WARM_PS, T * M * n),
+                                h.Download<float>(ILQG_WARM_ALPHAS, T * M));
+  const std::vector<float> nx = h.Download<float>(ILQG_X0, n);
+  for (size_t a = 0; a < n; a++) x0_((long)a) = nx[a];
+}
+
 
 // ---- include/ilqgames/solver/game_solver.h:58-95 -----------------------------------------------
 class GameSolver {

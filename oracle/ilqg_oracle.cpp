@@ -332,9 +332,9 @@ void EvaluateDynamics(const Problem& pr, const real* x, const real* u, real* xdo
 // MultiPlayerDynamicalSystem::Integrate, src/multi_player_dynamical_system.cpp:52-77.
 // RK4 with 2 substeps; the double `dt` narrows to the vector scalar type when it
 // multiplies a VectorXf (Eigen scalar promotion), as do the 0.5/2.0/6.0 literals.
-void Integrate(const Problem& pr, const real* x0, const real* u, real* xout) {
+void Integrate(const Problem& pr, const real* x0, const real* u, real* xout, double time_interval) {
   const int n = pr.n;
-  const double dt_d = pr.d.time_step / static_cast<double>(2);
+  const double dt_d = time_interval / static_cast<double>(2);
   const real dt = (real)dt_d;
   real x[ILQG_MAX_XDIM], k1[ILQG_MAX_XDIM], k2[ILQG_MAX_XDIM], k3[ILQG_MAX_XDIM],
       k4[ILQG_MAX_XDIM], tmp[ILQG_MAX_XDIM];
@@ -353,6 +353,10 @@ void Integrate(const Problem& pr, const real* x0, const real* u, real* xout) {
     }
   }
   for (int a = 0; a < n; a++) xout[a] = x[a];
+}
+
+void Integrate(const Problem& pr, const real* x0, const real* u, real* xout) {
+  Integrate(pr, x0, u, xout, pr.d.time_step);
 }
 
 // ConcatenatedDynamicalSystem::Linearize, src/concatenated_dynamical_system.cpp:86-107
@@ -1439,6 +1443,7 @@ bool ModifyLQStrategies(const Problem& pr, Instance& in, bool* has_converged) {
 struct ilqg_solver {
   Problem pr;
   int batch;
+  double op_t0 = 0;  // OperatingPoint::t0 of the Problems (uniform over the batch)
   std::vector<Instance> inst;
   int al_max_iterates = 0;
   float al_tolerance = 0;
@@ -1531,6 +1536,7 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
     return rc;
   }
   s->batch = batch;
+  s->op_t0 = desc->initial_time;
   s->inst.resize(batch);
   for (auto& in : s->inst) InitInstance(s->pr, in);
   *out = s;
@@ -1817,6 +1823,117 @@ int ilqg_overwrite_solution(ilqg_handle h, int only_successful) {
   return ILQG_OK;
 }
 
+// Problem::SetUpNextRecedingHorizon (src/problem.cpp:64-186) for every game of the batch: the
+// warm start (Problem::operating_point_ / strategies_) is re-based to start planner_runtime after
+// t0 from the measured state x0.  Times are shared by the batch, states are per game.
+int ilqg_setup_next_receding_horizon(ilqg_handle h, const float* x0_in, double t0, double planner_runtime,
+                                     double* new_t0) {
+  if (!h || !x0_in) return ILQG_ERR_BAD_HANDLE;
+  const Problem& pr = h->pr;
+  // a constrained problem CHECK-fails in the reference once initial_time_ > 0: quadraticization
+  // asks Constraint::TimeIndex(RelativeTime(kk)) (relative_time_tracker.h:63-72, ilq_solver.cpp:475)
+  if (pr.num_constraints > 0) return ILQG_ERR_UNSUPPORTED;
+  const int T = pr.T, n = pr.n, M = pr.M, N = pr.N;
+  const double kTimeStep = pr.d.time_step, kTimeHorizon = kTimeStep * T;
+  // ---- SyncToExistingProblem :64-125, the scalar part (CHECKs become argument errors) ----
+  if (planner_runtime < 0.0 || planner_runtime + t0 > h->op_t0 + kTimeHorizon || t0 < h->op_t0)
+    return ILQG_ERR_INVALID_ARGUMENT;
+  constexpr float kRoundingError = 0.9;
+  const double relative_t0 = t0 - h->op_t0;
+  size_t current_timestep = static_cast<size_t>(relative_t0 / kTimeStep);
+  double remaining_time_this_step = (current_timestep + 1) * kTimeStep - relative_t0;
+  if (remaining_time_this_step < kRoundingError * kTimeStep) {
+    current_timestep += 1;
+    remaining_time_this_step = kTimeStep - remaining_time_this_step;
+  }
+  if (!(remaining_time_this_step < kTimeStep)) return ILQG_ERR_INVALID_ARGUMENT;  // CHECK_LT :87
+  // IntegrateToNextTimeStep's own bookkeeping (src/multi_player_integrable_system.cpp:113-143)
+  const size_t itn_timestep = static_cast<size_t>((relative_t0 + kSmallNumber) / kTimeStep);
+  const double itn_remaining = kTimeStep * (itn_timestep + 1) - relative_t0;
+  if (!(itn_remaining < kTimeStep + kSmallNumber) || itn_timestep >= (size_t)T)
+    return ILQG_ERR_INVALID_ARGUMENT;
+  const float frac = itn_remaining / kTimeStep;
+  double op_t0 = t0 + remaining_time_this_step;
+  size_t num_steps_to_integrate = 0;
+  const bool integrate_more = remaining_time_this_step <= planner_runtime;
+  if (integrate_more) {
+    num_steps_to_integrate =
+        static_cast<size_t>(kSmallNumber + (planner_runtime - remaining_time_this_step) / kTimeStep);
+    op_t0 += kTimeStep * num_steps_to_integrate;
+  }
+  const size_t last_integration_timestep = current_timestep + num_steps_to_integrate;
+  if (last_integration_timestep > (size_t)T) return ILQG_ERR_INVALID_ARGUMENT;
+  if (!(std::abs(t0 + planner_runtime - op_t0) <= kTimeStep)) return ILQG_ERR_INVALID_ARGUMENT;  // :123
+
+  const ilqg_subsystem_desc& ego = pr.d.subsystems[0];
+  const bool concatenated = ego.kind != ILQG_DYN_AIR3D;
+  for (int b = 0; b < h->batch; b++) {
+    Instance& in = h->inst[b];
+    real x[ILQG_MAX_XDIM], u[ILQG_MAX_UDIM], ref[ILQG_MAX_XDIM], nx[ILQG_MAX_XDIM];
+    // Strategy::operator() (strategy.h:73-76): u = u_ref - P dx - alpha
+    auto controls = [&](size_t kk, const real* state, const real* state_ref) {
+      for (int c = 0; c < M; c++) {
+        real acc = 0;
+        for (int a = 0; a < n; a++) acc += in.prob_Ps[(kk * M + c) * n + a] * (state[a] - state_ref[a]);
+        u[c] = (in.prob_us[kk * M + c] - acc) - in.prob_alphas[kk * M + c];
+      }
+    };
+    for (int a = 0; a < n; a++) x[a] = x0_in[(size_t)b * n + a];
+    // x0_ref: interpolated reference state (:130-135)
+    for (int a = 0; a < n; a++)
+      ref[a] = itn_timestep + 1 < (size_t)T
+                   ? frac * in.prob_xs[itn_timestep * n + a] + (real)(1.0 - frac) * in.prob_xs[(itn_timestep + 1) * n + a]
+                   : in.prob_xs[(size_t)(T - 1) * n + a];
+    controls(itn_timestep, x, ref);
+    Integrate(pr, x, u, nx, itn_remaining);
+    std::memcpy(x, nx, sizeof(real) * n);
+    if (integrate_more) {
+      for (size_t kk = current_timestep + 1; kk < last_integration_timestep; kk++) {  // :96-111
+        controls(kk, x, &in.prob_xs[kk * n]);
+        Integrate(pr, x, u, nx);
+        std::memcpy(x, nx, sizeof(real) * n);
+      }
+    }
+    // nearest state of the existing plan (:101-110); ConcatenatedDynamicalSystem::DistanceBetween
+    // only looks at the first subsystem's position (src/concatenated_dynamical_system.cpp:109-113)
+    auto distance = [&](const real* a) {
+      if (concatenated) {
+        const real dx = x[ego.x_offset] - a[ego.x_offset], dy = x[ego.x_offset + 1] - a[ego.x_offset + 1];
+        return dx * dx + dy * dy;
+      }
+      real acc = 0;
+      for (int q = 0; q < n; q++) acc += (x[q] - a[q]) * (x[q] - a[q]);
+      return acc;
+    };
+    size_t first = 0;
+    for (size_t kk = 1; kk < (size_t)T; kk++)
+      if (distance(&in.prob_xs[kk * n]) < distance(&in.prob_xs[first * n])) first = kk;
+    // x0_ = Stitch(nearest, x) (:117; concatenated_dynamical_system.h:75-85)
+    const int ego_dim = ego.kind == ILQG_DYN_CAR6D ? 6 : ego.kind == ILQG_DYN_UNICYCLE4D ? 4 : n;
+    for (int a = 0; a < n; a++) in.x0[a] = a < ego_dim ? in.prob_xs[first * n + a] : x[a];
+    // ---- SetUpNextRecedingHorizon :127-186: shift the plan, extend it with zero controls ----
+    const size_t kept = (size_t)T - first;
+    for (size_t kk = 0; kk < kept; kk++) {
+      const size_t src = kk + first;
+      if (src == kk) continue;
+      std::memcpy(&in.prob_xs[kk * n], &in.prob_xs[src * n], sizeof(real) * n);
+      std::memcpy(&in.prob_us[kk * M], &in.prob_us[src * M], sizeof(real) * M);
+      std::memcpy(&in.prob_Ps[kk * M * n], &in.prob_Ps[src * M * n], sizeof(real) * M * n);
+      std::memcpy(&in.prob_alphas[kk * M], &in.prob_alphas[src * M], sizeof(real) * M);
+    }
+    for (size_t kk = kept; kk < (size_t)T; kk++) {
+      std::fill(&in.prob_Ps[kk * M * n], &in.prob_Ps[(kk + 1) * M * n], (real)0);
+      std::fill(&in.prob_alphas[kk * M], &in.prob_alphas[(kk + 1) * M], (real)0);
+      std::fill(&in.prob_us[kk * M], &in.prob_us[(kk + 1) * M], (real)0);
+      Integrate(pr, &in.prob_xs[(kk - 1) * n], &in.prob_us[(kk - 1) * M], &in.prob_xs[kk * n]);
+    }
+    (void)N;
+  }
+  h->op_t0 = op_t0;
+  if (new_t0) *new_t0 = op_t0;
+  return ILQG_OK;
+}
+
 int ilqg_al_post_solve(ilqg_handle h) {
   if (!h) return ILQG_ERR_BAD_HANDLE;
   for (auto& in : h->inst) {
@@ -1898,6 +2015,10 @@ int ilqg_download(ilqg_handle h, int what, void* dst, size_t bytes) {
   };
   switch (what) {
     case ILQG_XS: return vec(&Instance::xs);
+    case ILQG_WARM_XS: return vec(&Instance::prob_xs);
+    case ILQG_WARM_US: return vec(&Instance::prob_us);
+    case ILQG_WARM_PS: return vec(&Instance::prob_Ps);
+    case ILQG_WARM_ALPHAS: return vec(&Instance::prob_alphas);
     case ILQG_US: return vec(&Instance::us);
     case ILQG_PS: return vec(&Instance::Ps);
     case ILQG_ALPHAS: return vec(&Instance::alphas);

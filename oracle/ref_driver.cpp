@@ -26,6 +26,7 @@
 #include <ilqgames/solver/problem.h>
 #include <ilqgames/solver/solver_params.h>
 #include <ilqgames/utils/solver_log.h>
+#include <ilqgames/utils/relative_time_tracker.h>
 #include <ilqgames/utils/types.h>
 
 #include <cstdint>
@@ -234,6 +235,44 @@ int ilqg_ref_solve(int which, int solver, const float* x0, const ilqg_ref_params
   if (mu_out) *mu_out = Constraint::GlobalMu();
   ResetMultipliers(*problem);
   return 0;
+}
+
+// ILQSolver::Solve from x0, Problem::OverwriteSolution with the final iterate, then
+// Problem::SetUpNextRecedingHorizon(x_meas, t, planner_runtime) (src/problem.cpp:127-186).
+// Returns what the Problem holds afterwards: InitialState (x0_out [n]), CurrentOperatingPoint
+// (xs [T][n], us [T][M], t0), CurrentStrategies (Ps [T][M][n], alphas [T][M]).
+int ilqg_ref_receding_horizon(int which, const float* x0, const ilqg_ref_params* q, const float* x_meas,
+                              double t, double planner_runtime, float* x0_out, float* xs, float* us,
+                              float* Ps, float* alphas, double* t0_out) {
+  auto problem = MakeProblem(which);
+  if (!problem) return -1;
+  const auto& dyn = *problem->Dynamics();
+  const int n = dyn.XDim(), M = dyn.TotalUDim(), N = dyn.NumPlayers();
+  VectorXf x(n), xm(n);
+  for (int d = 0; d < n; d++) { x(d) = x0[d]; xm(d) = x_meas[d]; }
+  problem->ResetInitialState(x);
+  ResetMultipliers(*problem);
+  const SolverParams params = ToParams(*q);
+  ILQSolver s(problem, params);
+  bool ok = false;
+  auto log = s.Solve(&ok, std::numeric_limits<Time>::infinity());
+  problem->OverwriteSolution(log->FinalOperatingPoint(), log->FinalStrategies());
+  problem->SetUpNextRecedingHorizon(xm, t, planner_runtime);
+  const OperatingPoint& op = problem->CurrentOperatingPoint();
+  const size_t T = time::kNumTimeSteps;
+  for (int d = 0; d < n; d++) x0_out[d] = problem->InitialState()(d);
+  for (size_t k = 0; k < T; k++) {
+    for (int d = 0; d < n; d++) xs[k * n + d] = op.xs[k](d);
+    int off = 0;
+    for (int i = 0; i < N; i++) {
+      for (int d = 0; d < dyn.UDim(i); d++) us[k * M + off + d] = op.us[k][i](d);
+      off += dyn.UDim(i);
+    }
+  }
+  CopyStrategies(problem->CurrentStrategies(), dyn, Ps, alphas);
+  *t0_out = op.t0;
+  RelativeTimeTracker::ResetInitialTime(0.0);
+  return ok ? 0 : 1;
 }
 
 // ILQSolver with max_solver_iters = 1 from x0: returns the linearization and quadraticization

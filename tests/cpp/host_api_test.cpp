@@ -255,6 +255,57 @@ void TestILQSolver(const std::shared_ptr<Problem>& problem) {
               batch[2].iterations);
 }
 
+// Problem::SetUpNextRecedingHorizon (src/problem.cpp:127-186) as a receding-horizon caller uses it
+// (src/receding_horizon_simulator.cpp:100-107): solve, write the solution back, re-base the plan
+// on a measured state, solve again from the shifted warm start.
+class IntersectionWithoutConstraints : public ilqgames_b200_examples::IntersectionProblem {
+  bool WithProximityConstraints() const override { return false; }
+};
+
+void TestRecedingHorizon() {
+  const std::shared_ptr<Problem> problem = MakeProblem<IntersectionWithoutConstraints>();
+  EXPECT(!problem->IsConstrained());
+  SolverParams params = IntersectionParams();
+  params.max_solver_iters = 3;
+  ILQSolver solver(problem, params);
+  bool success = false;
+  std::shared_ptr<SolverLog> log = solver.Solve(&success);
+  EXPECT(success);
+  problem->OverwriteSolution(log->FinalOperatingPoint(), log->FinalStrategies());
+  const OperatingPoint plan = log->FinalOperatingPoint();
+  const Time t = 0.33, planner_runtime = 0.25;
+  VectorXf x = plan.xs[3];
+  x(0) += 0.05f;  // the measured state is a little off the plan
+  x(7) -= 0.03f;
+  problem->SetUpNextRecedingHorizon(x, t, planner_runtime);
+  const OperatingPoint& op = problem->CurrentOperatingPoint();
+  // :95 / :107 -- the new problem starts within one time step of t + planner_runtime
+  EXPECT(std::fabs(t + planner_runtime - op.t0) <= time::kTimeStep);
+  EXPECT(op.xs.size() == time::kNumTimeSteps && problem->CurrentStrategies()[0].Ps.size() == time::kNumTimeSteps);
+  // the first plan state is one of the old plan's states (the nearest one), the ego part of the new
+  // initial state is taken from it (ConcatenatedDynamicalSystem::Stitch)
+  size_t first = 0;
+  for (size_t k = 0; k < plan.xs.size(); k++)
+    if ((plan.xs[k] - op.xs[0]).norm() == 0.0f) first = k;
+  EXPECT(first >= 4 && first <= 8);
+  for (int a = 0; a < 6; a++) EXPECT(problem->InitialState()(a) == op.xs[0](a));
+  // shifted rows are copies; the tail is the zero-control extension
+  EXPECT((plan.xs[first + 10] - op.xs[10]).norm() == 0.0f);
+  const size_t T = time::kNumTimeSteps;
+  for (size_t k = T - first; k < T; k++)
+    for (const Strategy& st : problem->CurrentStrategies()) EXPECT(st.Ps[k].cwiseAbsMax() == 0.0f && st.alphas[k].norm() == 0.0f);
+  const float t0f = (float)op.t0;
+  Dump("rh_t0", &t0f, 1);
+  Dump("rh_x0", problem->InitialState().data(), (size_t)problem->InitialState().size());
+  Dump("rh_op", Flatten(op));
+  Dump("rh_strategies", Flatten(problem->CurrentStrategies()));
+  // the next solve starts from the shifted warm start at the new initial state
+  log = solver.Solve(&success);
+  EXPECT((log->State(0, 0) - problem->InitialState()).norm() == 0.0f);
+  Dump("rh_next_op", Flatten(log->FinalOperatingPoint()));
+  std::printf("Problem::SetUpNextRecedingHorizon: first time step of the new problem = %zu, t0 = %.4f\n", first, op.t0);
+}
+
 void TestAugmentedLagrangianSolver(const std::shared_ptr<Problem>& problem) {
   SolverParams params = IntersectionParams();
   params.max_solver_iters = 30;  // NumIterates cap of the outer loop
@@ -288,6 +339,7 @@ int main(int argc, char** argv) {
 #endif
   TestILQSolver(problem);
   TestAugmentedLagrangianSolver(problem);
+  TestRecedingHorizon();
   std::fclose(g_out);
   std::printf("host_api_test: all checks passed\n");
   return 0;

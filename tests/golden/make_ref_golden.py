@@ -28,6 +28,9 @@ from tests.golden import ref_lib as R  # noqa: E402
 
 ILQ_ITERS = 6       # ILQSolver::Solve cap for the per-iterate fixtures
 OL_ITERS = 4        # same with SolverParams::open_loop
+RH_ITERS = 2        # ILQ iterations before SetUpNextRecedingHorizon
+# (t0, planner_runtime) pairs; times on the 0.1 s grid CHECK-fail in the reference (problem.cpp:87)
+RH_CASES = [(0.25, 0.1), (0.33, 0.25), (1.02, 0.1), (0.55, 0.0), (2.07, 0.5)]
 AL_INNER, AL_OUTER = 10, 40   # unconstrained_solver_max_iters, AL NumIterates cap
 
 CASES = {
@@ -97,6 +100,27 @@ def run_case(ref: R.RefLibrary, name: str):
                ol_Ps_absmax=np.float32(max(np.abs(r["Ps"]).max() for r in ol)),
                ol_iterates=np.array([r["iterates"] for r in ol], np.int32),
                ol_success=np.array([r["success"] for r in ol], np.int32))
+
+    if nc == 0:
+        # Problem::SetUpNextRecedingHorizon (src/problem.cpp:127-186) after an ILQSolver::Solve whose
+        # final iterate was written back with OverwriteSolution; measured states = plan + noise
+        nrh = 3
+        prh = params(max_solver_iters=RH_ITERS)
+        rprh = R.RefParams.from_abi(prh)
+        rng = np.random.default_rng(3)
+        plans = [ref.solve(which, R.ILQ, x0[b], rprh, max_log=RH_ITERS + 1)["xs"][-1] for b in range(nrh)]
+        rh = {k: [] for k in ("x_meas", "x0", "xs", "us", "Ps", "alphas", "t0")}
+        for (t, runtime) in RH_CASES:
+            k = int(t / 0.1)
+            xm = np.stack([plans[b][k] for b in range(nrh)]) + rng.normal(0, 0.05, size=(nrh, n)).astype(np.float32)
+            res = [ref.receding_horizon(which, x0[b], rprh, xm[b], t, runtime) for b in range(nrh)]
+            rh["x_meas"].append(xm)
+            for key in ("x0", "xs", "us", "Ps", "alphas"):
+                rh[key].append(np.stack([r[key] for r in res]))
+            assert len({r["t0"] for r in res}) == 1
+            rh["t0"].append(res[0]["t0"])
+        out.update(rh_iters=np.int32(RH_ITERS), rh_cases=np.array(RH_CASES, np.float64),
+                   **{f"rh_{k}": np.array(v) for k, v in rh.items()})
 
     if nc > 0:
         nal = 6

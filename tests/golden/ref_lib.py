@@ -86,6 +86,22 @@ class RefLibrary:
         assert rc in (0, 1)
         return dict(A=A, B=B, Q=Q, l=l, R=R, r=r, ok=rc == 0)
 
+    def receding_horizon(self, which: int, x0, params: RefParams, x_meas, t: float,
+                         planner_runtime: float):
+        n, M, N, T, _ = self.dims(which)
+        x0 = np.ascontiguousarray(x0, np.float32)
+        x_meas = np.ascontiguousarray(x_meas, np.float32)
+        x0_out = np.zeros(n, np.float32)
+        xs, us = np.zeros((T, n), np.float32), np.zeros((T, M), np.float32)
+        Ps, alphas = np.zeros((T, M, n), np.float32), np.zeros((T, M), np.float32)
+        t0 = C.c_double(0)
+        rc = self.lib.ilqg_ref_receding_horizon(which, _ptr(x0), C.byref(params), _ptr(x_meas),
+                                                C.c_double(t), C.c_double(planner_runtime),
+                                                _ptr(x0_out), _ptr(xs), _ptr(us), _ptr(Ps),
+                                                _ptr(alphas), C.byref(t0))
+        assert rc in (0, 1)
+        return dict(x0=x0_out, xs=xs, us=us, Ps=Ps, alphas=alphas, t0=t0.value, ok=rc == 0)
+
     def roundabout_lane(self, entrance_angle, exit_angle, distance) -> np.ndarray:
         pts = np.zeros((64, 2), np.float32)
         k = self.lib.ilqg_ref_roundabout_lane(C.c_float(entrance_angle), C.c_float(exit_angle),

@@ -103,6 +103,23 @@ def _check_against_ctypes(lib, got, exact=True):
     if exact:
         assert (int(inner_solves), int(iterates), int(success)) == (out.rounds, int(out.iterates[0]), int(out.success[0]))
     assert same(_flat_op(out.xs[0], out.us[0]), got["al_final_op"])
+    # Problem::SetUpNextRecedingHorizon on the unconstrained variant, then the next solve
+    desc_u, _ = problems.three_player_intersection(with_constraints=False)
+    hr = abi.Handle(lib, desc_u, _params(max_solver_iters=3), 1, 0)
+    hr.upload_x0(x0[None])
+    hr.solve_begin()
+    hr.solve(chunk=1)
+    hr.overwrite_solution()
+    xm = hr.download(abi.XS)[0, 3].copy()
+    xm[0] += np.float32(0.05)
+    xm[7] -= np.float32(0.03)
+    new_t0 = hr.setup_next_receding_horizon(xm[None], 0.33, 0.25)
+    assert np.float32(new_t0) == got["rh_t0"][0]
+    assert same(hr.download(abi.X0)[0], got["rh_x0"])
+    assert same(_flat_op(hr.download(abi.WARM_XS)[0], hr.download(abi.WARM_US)[0]), got["rh_op"])
+    hr.solve_begin()
+    hr.solve(chunk=1)
+    assert same(_flat_op(hr.download(abi.XS)[0], hr.download(abi.US)[0]), got["rh_next_op"])
     # SURVEY Appendix B known answer of the LQ test system
     np.testing.assert_allclose(got["lq_P1_k0"], [0.915024, 1.632025], atol=2e-5)
     np.testing.assert_allclose(got["lq_P2_k0"], [0.0145362, 0.0206234], atol=2e-5)

@@ -149,6 +149,52 @@ def test_oracle_reproduces_reference_open_loop_iterates(oracle, name):
     h.close()
 
 
+def receding_horizon_cases(lib, g, desc, params):
+    """For every fixture case: solve, write the solution back, SetUpNextRecedingHorizon; yields
+    (case index, handle, new t0)."""
+    nrh = g["rh_x0"].shape[1]
+    for c, (t, runtime) in enumerate(g["rh_cases"]):
+        h = abi.Handle(lib, desc, params(max_solver_iters=int(g["rh_iters"])), nrh, 0)
+        h.upload_x0(g["x0"][:nrh])
+        h.solve_begin()
+        h.solve(chunk=1)
+        h.overwrite_solution()
+        new_t0 = h.setup_next_receding_horizon(g["rh_x_meas"][c], float(t), float(runtime))
+        yield c, h, new_t0
+        h.close()
+
+
+def test_oracle_reproduces_reference_receding_horizon(oracle):
+    """Problem::SetUpNextRecedingHorizon (src/problem.cpp:64-186): new initial state, shifted and
+    extended operating point and strategies, new t0 -- bit for bit."""
+    g = load("roundabout_merging")
+    build, params = CASES["roundabout_merging"]
+    desc, _ = build()
+    shifted = 0
+    for c, h, new_t0 in receding_horizon_cases(oracle, g, desc, params):
+        assert new_t0 == g["rh_t0"][c]
+        assert np.array_equal(h.download(abi.X0), g["rh_x0"][c])
+        for what, key in ((abi.WARM_XS, "rh_xs"), (abi.WARM_US, "rh_us"), (abi.WARM_PS, "rh_Ps"),
+                          (abi.WARM_ALPHAS, "rh_alphas")):
+            assert np.array_equal(h.download(what), g[key][c]), (c, key)
+        shifted += int(np.any(g["rh_Ps"][c][:, -5:] == 0))
+    assert shifted >= 3   # the plan really moved: trailing strategies are the zero extension
+
+
+def test_receding_horizon_argument_errors(oracle):
+    """Where the reference CHECK-fails (src/problem.cpp:68-71, :87) the ABI returns an error."""
+    desc, _ = problems.roundabout_merging()
+    h = abi.Handle(oracle, desc, problems.roundabout_params(), 2)
+    x = problems.roundabout_x0_batch(2, 1)
+    for t, runtime in ((-0.5, 0.1), (0.25, -0.1), (9.95, 0.2), (1.0, 0.1)):
+        with pytest.raises(abi.IlqgError):
+            h.setup_next_receding_horizon(x, t, runtime)
+    desc_c, _ = problems.three_player_intersection()   # constrained: the reference aborts later
+    hc = abi.Handle(oracle, desc_c, problems.three_player_intersection_params(), 1)
+    with pytest.raises(abi.IlqgError):
+        hc.setup_next_receding_horizon(problems.three_player_intersection_x0_batch(1, 1), 0.25, 0.1)
+
+
 @pytest.mark.parametrize("name", ["three_player_intersection", "air_3d"])
 def test_oracle_reproduces_reference_augmented_lagrangian(oracle, name):
     """AugmentedLagrangianSolver::Solve (src/augmented_lagrangian_solver.cpp:72-210): final
