@@ -108,7 +108,12 @@ def run_case(ref: R.RefLibrary, name: str):
         prh = params(max_solver_iters=RH_ITERS)
         rprh = R.RefParams.from_abi(prh)
         rng = np.random.default_rng(3)
-        plans = [ref.solve(which, R.ILQ, x0[b], rprh, max_log=RH_ITERS + 1)["xs"][-1] for b in range(nrh)]
+        sol = [ref.solve(which, R.ILQ, x0[b], rprh, max_log=RH_ITERS + 1) for b in range(nrh)]
+        plans = [r["xs"][-1] for r in sol]
+        # the plan SetUpNextRecedingHorizon starts from (lets a test skip the solve)
+        out.update(rh_plan_xs=np.stack(plans), rh_plan_us=np.stack([r["us"][-1] for r in sol]),
+                   rh_plan_Ps=np.stack([r["Ps"] for r in sol]),
+                   rh_plan_alphas=np.stack([r["alphas"] for r in sol]))
         rh = {k: [] for k in ("x_meas", "x0", "xs", "us", "Ps", "alphas", "t0")}
         for (t, runtime) in RH_CASES:
             k = int(t / 0.1)

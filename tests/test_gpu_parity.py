@@ -371,7 +371,9 @@ def test_receding_horizon_against_reference_fixture(product):
     g = np.load(os.path.join(GOLDEN, "ref_roundabout_merging.npz"))
     build, params, _ = CONFIGS["roundabout_merging"]
     desc, _ = build()
-    for c, h, new_t0 in receding_horizon_cases(product, g, desc, params):
+    # from the reference's plan, so that the comparison is about this step and not about the
+    # (ill-conditioned, reg = 0) RoundaboutMerging solve before it
+    for c, h, new_t0 in receding_horizon_cases(product, g, desc, params, from_plan=True):
         assert new_t0 == g["rh_t0"][c]
         close(h.download(abi.X0), g["rh_x0"][c], tol=1e-4, what=f"case {c} x0")
         close(h.download(abi.WARM_XS), g["rh_xs"][c], tol=1e-3, atol=1e-3, what=f"case {c} xs")
