@@ -35,6 +35,7 @@ sys.path.insert(0, REPO)
 
 ITERS_PER_SOLVE = 10
 ORACLE_LIB = os.path.join(REPO, "oracle", "_build", "libilqg_oracle.so")
+REF_BUILD_LIB = os.path.join(REPO, "oracle", "_ref", "libilqg_ref.so")
 
 
 def workload(batch: int, seed: int):
@@ -187,6 +188,28 @@ def cpu_single_core(x0_sample):
     return done / dt, done, rolls, dt
 
 
+def cpu_reference_build(x0_sample):
+    """The reference's OWN sources (oracle/_ref/libilqg_ref.so: /root/reference/src compiled against
+    the Eigen/glog/gflags stand-ins of oracle/ref_shim) on the same games, one host core.  Reported
+    next to the port, not instead of it: the stand-in's dense kernels are plain loops, so this is a
+    lower bound on what the reference built on real Eigen would do.  None when the library was not
+    built (it needs /root/reference at build time)."""
+    if not os.path.exists(REF_BUILD_LIB):
+        return None
+    from tests.golden import ref_lib
+    ref = ref_lib.RefLibrary(REF_BUILD_LIB)
+    _, params, _ = workload(1, 0)
+    rp = ref_lib.RefParams.from_abi(params)
+    rp.convergence_tolerance = 0.0   # HasConverged needs |delta| < tolerance: never, like the GPU arm
+    t = time.perf_counter()
+    done = 0
+    for x in x0_sample:
+        done += ref.solve(ref_lib.INTERSECTION, ref_lib.ILQ, x, rp, mu0=10.0, max_log=1)["iterates"] - 1
+    dt = time.perf_counter() - t
+    return {"value": done / dt, "unit": "instance-iterations/s", "cores": 1,
+            "sample": f"{len(x0_sample)} instances, {dt:.1f} s; reference sources on oracle/ref_shim (no Eigen3 in the image)"}
+
+
 _worker_state = {}
 
 
@@ -246,8 +269,10 @@ def run_reference(args):
         "config": bench_config(args.batch, 1, args.seed),
         "cpu_baseline": {"value": value, "unit": "instance-iterations/s", "cores": len(chunks), "kind": "port",
                          "sample": f"first {len(sample)} instances of the batch x {ITERS_PER_SOLVE} iterations per step, "
-                                   f"{len(chunks)} processes; oracle port because the reference's Eigen build is "
-                                   "impossible here (no Eigen3/glog/gflags)"},
+                                   f"{len(chunks)} processes; oracle port of the reference's Eigen path: faster than "
+                                   "the reference's own sources built on the Eigen stand-ins of oracle/ref_shim "
+                                   "(reference_build), to which it is bit-identical (tests/test_ref_pins.py)",
+                         "reference_build": cpu_reference_build(sample[:16])},
         "e2e": {"value": value, "unit": "instance-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -445,7 +470,11 @@ def run_b200(args):
         cpu = {"value": v, "unit": "instance-iterations/s", "cores": 1, "kind": "port",
                "sample": f"first {len(sample)} instances of the same batch, {ITERS_PER_SOLVE} iterations each, "
                          f"{dt:.1f} s on one host core (of {os.cpu_count()}); oracle port of the reference's "
-                         "Eigen path (reference itself not buildable: no Eigen3/glog/gflags)"}
+                         "Eigen path (bit-identical to the reference's own sources built on Eigen stand-ins, "
+                         "tests/test_ref_pins.py; the image has no Eigen3/glog/gflags)"}
+        ref_build = cpu_reference_build(sample[:16])
+        if ref_build:
+            cpu["reference_build"] = ref_build
 
     if rank == 0:
         hist = np.bincount(status, minlength=6).tolist()
