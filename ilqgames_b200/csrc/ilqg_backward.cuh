@@ -84,25 +84,58 @@ __device__ __forceinline__ void stvec(float* p, const float (&in)[K]) {
 }
 
 // acc[TR][TC] = sum_q X[q][a0 + .] * Y[q][c0 + .]   (X: ldx floats per row, Y: ldy)
+//
+// Even TC: the inner products run on FFMA2 (`fma.rn.f32x2`, new on sm_100): one instruction does
+// acc[i][j], acc[i][j+1] += x[i] * (y[j], y[j+1]) -- the SASS form takes the scalar x[i] as a
+// broadcast operand, so no packing moves are needed and each half is an IEEE fma (results are bit
+// for bit those of two FFMAs).  K_bwd is bound by instruction issue / per-warp latency, not by
+// the FMA pipe (profiles/r01_schedule_experiments.md), and these loops were 38 % of its
+// instructions.
 template <int QN, int TR, int TC>
 __device__ __forceinline__ void mm_tn(const float* __restrict__ X, int ldx, const float* __restrict__ Y,
                                       int ldy, float (&acc)[TR][TC]) {
-#pragma unroll
-  for (int i = 0; i < TR; i++)
-#pragma unroll
-    for (int j = 0; j < TC; j++) acc[i][j] = 0.f;
-  // partially unrolled: the kernel is instruction-fetch sensitive (stall_no_instruction in
-  // profiles/r01_lq_backward.md); ILQG_MM_UNROLL q-steps per loop trip keep 2 x ILQG_MM_UNROLL
-  // 128-bit loads in flight
-#pragma unroll kMmUnroll
-  for (int q = 0; q < QN; q++) {
-    float xr[TR], yr[TC];
-    ldvec<TR>(X + q * ldx, xr);
-    ldvec<TC>(Y + q * ldy, yr);
+  if constexpr (TC % 2 == 0) {
+    float2 acc2[TR][TC / 2];
 #pragma unroll
     for (int i = 0; i < TR; i++)
 #pragma unroll
-      for (int j = 0; j < TC; j++) acc[i][j] = fmaf(xr[i], yr[j], acc[i][j]);
+      for (int j = 0; j < TC / 2; j++) acc2[i][j] = make_float2(0.f, 0.f);
+#pragma unroll kMmUnroll
+    for (int q = 0; q < QN; q++) {
+      float xr[TR], yr[TC];
+      ldvec<TR>(X + q * ldx, xr);
+      ldvec<TC>(Y + q * ldy, yr);
+#pragma unroll
+      for (int i = 0; i < TR; i++)
+#pragma unroll
+        for (int j = 0; j < TC / 2; j++)
+          acc2[i][j] = __ffma2_rn(make_float2(xr[i], xr[i]), make_float2(yr[2 * j], yr[2 * j + 1]), acc2[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < TR; i++)
+#pragma unroll
+      for (int j = 0; j < TC / 2; j++) {
+        acc[i][2 * j] = acc2[i][j].x;
+        acc[i][2 * j + 1] = acc2[i][j].y;
+      }
+  } else {
+#pragma unroll
+    for (int i = 0; i < TR; i++)
+#pragma unroll
+      for (int j = 0; j < TC; j++) acc[i][j] = 0.f;
+    // partially unrolled: the kernel is instruction-fetch sensitive (stall_no_instruction in
+    // profiles/r01_lq_backward.md); ILQG_MM_UNROLL q-steps per loop trip keep 2 x ILQG_MM_UNROLL
+    // 128-bit loads in flight
+#pragma unroll kMmUnroll
+    for (int q = 0; q < QN; q++) {
+      float xr[TR], yr[TC];
+      ldvec<TR>(X + q * ldx, xr);
+      ldvec<TC>(Y + q * ldy, yr);
+#pragma unroll
+      for (int i = 0; i < TR; i++)
+#pragma unroll
+        for (int j = 0; j < TC; j++) acc[i][j] = fmaf(xr[i], yr[j], acc[i][j]);
+    }
   }
 }
 
