@@ -12,21 +12,73 @@
 
 namespace ilqgames {
 
-// ---- include/ilqgames/geometry/polyline2.h:55-105 (the point list; queries run on the device)
+// ---- include/ilqgames/geometry/line_segment2.h:52-96: the accessors host code uses to place
+// agents on a lane (src/roundabout_merging_example.cpp:195-212); closest-point queries run on the
+// device (csrc/ilqg_device.cuh: segment_closest)
+class LineSegment2 {
+ public:
+  LineSegment2(const Point2& point1, const Point2& point2) : p1_(point1), p2_(point2) {
+    length_ = (point1 - point2).norm();
+    CHECK_GT(length_, constants::kSmallNumber);
+    unit_direction_ = (point2 - point1) / length_;
+  }
+  float Length() const { return length_; }
+  const Point2& FirstPoint() const { return p1_; }
+  const Point2& SecondPoint() const { return p2_; }
+  const Point2& UnitDirection() const { return unit_direction_; }
+  float Heading() const { return std::atan2(unit_direction_.y(), unit_direction_.x()); }
+
+ private:
+  Point2 p1_, p2_, unit_direction_;
+  float length_;
+};
+
+// ---- include/ilqgames/geometry/polyline2.h:55-105 (point list + the route-walking accessors;
+// closest-point queries run on the device)
 class Polyline2 {
  public:
-  Polyline2(const PointList2& points) : points_(points) { CHECK_GT(points.size(), 1u); }
-  void AddPoint(const Point2& point) { points_.push_back(point); }
+  Polyline2(const PointList2& points) : points_(points) {
+    CHECK_GT(points.size(), 1u);
+    for (size_t k = 1; k < points.size(); k++) segments_.emplace_back(points[k - 1], points[k]);
+  }
+  void AddPoint(const Point2& point) {
+    segments_.emplace_back(points_.back(), point);
+    points_.push_back(point);
+  }
   const PointList2& Points() const { return points_; }
-  size_t NumSegments() const { return points_.size() - 1; }
+  const std::vector<LineSegment2>& Segments() const { return segments_; }
+  size_t NumSegments() const { return segments_.size(); }
   float Length() const {
     float len = 0;
-    for (size_t k = 0; k + 1 < points_.size(); k++) len += (points_[k + 1] - points_[k]).norm();
+    for (const LineSegment2& seg : segments_) len += seg.Length();
     return len;
+  }
+
+  // The point `route_pos` metres along the polyline (src/polyline2.cpp:68-107): the segment that
+  // contains that arclength (the last one when it lies beyond the end), walked from its first point.
+  Point2 PointAt(float route_pos, bool* is_vertex = nullptr, LineSegment2* segment = nullptr,
+                 bool* is_endpoint = nullptr) const {
+    size_t idx = 0;
+    float start = 0.0f;  // arclength at which segment idx begins
+    while (idx + 1 < segments_.size() && start + segments_[idx].Length() <= route_pos) {
+      start += segments_[idx].Length();
+      idx++;
+    }
+    const LineSegment2& seg = segments_[idx];
+    if (segment) *segment = seg;
+    const float remaining = route_pos - start;
+    CHECK_GE(remaining, 0.0f);
+    if (is_vertex) *is_vertex = remaining < constants::kSmallNumber || remaining > seg.Length();
+    const Point2 point = seg.FirstPoint() + remaining * seg.UnitDirection();
+    if (is_endpoint)
+      *is_endpoint = (idx == 0 || idx + 1 == segments_.size()) &&
+                     (point == segments_.front().FirstPoint() || point == segments_.back().SecondPoint());
+    return point;
   }
 
  private:
   PointList2 points_;
+  std::vector<LineSegment2> segments_;
 };
 
 // Collects records and polylines while a Problem describes itself.

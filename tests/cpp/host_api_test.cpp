@@ -14,6 +14,8 @@
 #ifdef DROPIN_REFERENCE_EXAMPLE
 // the reference's own problem definition, compiled unchanged (tests/test_host_api.py builds this
 // variant only where /root/reference exists)
+#include <ilqgames/examples/air_3d_example.h>
+#include <ilqgames/examples/roundabout_merging_example.h>
 #include <ilqgames/examples/three_player_intersection_example.h>
 #endif
 
@@ -191,10 +193,11 @@ std::shared_ptr<Problem> MakeProblem() {
   return problem;
 }
 
-void TestProblemDescriptor(const std::shared_ptr<Problem>& problem, const char* tag) {
+void TestProblemDescriptor(const std::shared_ptr<Problem>& problem, const char* tag, int players = 3, int xdim = 16,
+                           int costs = 18, int polylines = 3) {
   ilqg_problem_desc desc;
   EXPECT(b200::DescribeProblem(*problem, &desc));
-  EXPECT(desc.num_players == 3 && desc.xdim == 16 && desc.num_costs == 18 && desc.num_polylines == 3);
+  EXPECT(desc.num_players == players && desc.xdim == xdim && desc.num_costs == costs && desc.num_polylines == polylines);
   std::vector<float> raw(sizeof(desc) / sizeof(float));
   std::memcpy(raw.data(), &desc, sizeof(desc));
   Dump((std::string("desc_") + tag).c_str(), raw);
@@ -336,6 +339,10 @@ int main(int argc, char** argv) {
   TestProblemDescriptor(problem, "own");
 #ifdef DROPIN_REFERENCE_EXAMPLE
   TestProblemDescriptor(MakeProblem<ThreePlayerIntersectionExample>(), "reference");
+  // src/roundabout_merging_example.cpp (+ roundabout_lane_center.cpp, initialize_along_route.cpp) and
+  // src/air_3d_example.cpp (+ draw_shapes.cpp), all compiled unchanged
+  TestProblemDescriptor(MakeProblem<RoundaboutMergingExample>(), "roundabout", 4, 24, 44, 4);
+  TestProblemDescriptor(MakeProblem<Air3DExample>(), "air3d", 2, 3, 8, 1);
 #endif
   TestILQSolver(problem);
   TestAugmentedLagrangianSolver(problem);

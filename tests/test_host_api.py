@@ -26,8 +26,13 @@ def _build(tmp_path, lib_path, dropin=False):
     cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-I" + os.path.join(REPO, "include"), SRC, "-o", exe,
            "-L" + libdir, "-l" + libfile[3:-3], "-Wl,-rpath," + libdir]
     if dropin:
-        cmd[5:5] = ["-DDROPIN_REFERENCE_EXAMPLE", "-I" + os.path.join(REFERENCE, "include"),
-                    os.path.join(REFERENCE, "src", "three_player_intersection_example.cpp")]
+        # the reference's example sources and the three free functions they call, byte for byte;
+        # compat/ supplies <glog/logging.h> and <gflags/gflags.h>, which the image does not have
+        cmd[5:5] = ["-DDROPIN_REFERENCE_EXAMPLE", "-I" + os.path.join(REPO, "include", "ilqgames", "b200", "compat"),
+                    "-I" + os.path.join(REFERENCE, "include")] + [
+            os.path.join(REFERENCE, "src", f + ".cpp") for f in (
+                "three_player_intersection_example", "roundabout_merging_example", "roundabout_lane_center",
+                "initialize_along_route", "air_3d_example", "draw_shapes")]
     subprocess.run(cmd, check=True)
     return exe
 
@@ -158,6 +163,14 @@ def test_reference_example_source_drops_in_unchanged(oracle, tmp_path):
     """north_star: 'an example like ThreePlayerIntersectionExample drops in unchanged'."""
     got = _run(_build(tmp_path, oracle.path, dropin=True), tmp_path)
     assert np.array_equal(got["desc_reference"].view(np.uint32), got["desc_own"].view(np.uint32))
+    # RoundaboutMergingExample and Air3DExample: the descriptors DescribeProblem builds from the
+    # reference's own example code equal the ones problems.py writes out by hand, bit for bit
+    for tag, build in (("roundabout", problems.roundabout_merging), ("air3d", problems.air_3d)):
+        desc, x0 = build()
+        mine = np.frombuffer(bytes(desc), dtype=np.uint32)
+        theirs = got["desc_" + tag].view(np.uint32)
+        assert np.array_equal(mine, theirs), (tag, np.nonzero(mine != theirs)[0][:8])
+        assert np.array_equal(np.asarray(x0, np.float32), got["x0_" + tag]), tag
     assert np.array_equal(got["x0_reference"], got["x0_own"])
     # and no reference header other than the example's own declaration took part in the build
     deps = subprocess.run(["g++", "-std=c++17", "-I" + os.path.join(REPO, "include"),
