@@ -37,6 +37,8 @@ struct SubSolver {
   cudaStream_t side;
   cudaEvent_t ev_fresh, ev_side;
   bool side_busy = false;
+  int sm_count = 148;
+  int ls_split = 1;  // linesearch windows as rollout + merit kernels (ILQG_LS_SPLIT=0: the fused k_ls_eval)
   // SolverParams::open_loop: LQOpenLoopSolver instead of LQFeedbackSolver (ilq_solver.h:76-81)
   bool open_loop = false;
   float* ol_scratch = nullptr;  // [B][T][OlLayout::srec], ilqg_open_loop.cuh
@@ -484,11 +486,43 @@ int LaunchLqRecords(SubSolver* h, int only_running, Sel sel = Sel{SEL_ALL, nullp
   return ILQG_OK;
 }
 
+// rollout + merit of one linesearch window as three kernels (ilqg_linesearch.cuh, "Split evaluation")
+int LaunchLsSplit(SubSolver* h, int mode, int blocks, int q_offset) {
+  const DevDesc& d = h->d;
+  const int S = d.num_subsystems;
+  const size_t smem_r = sizeof(float) * (size_t)ls_rollout_smem_floats(d.n, S);
+  const size_t smem_m = sizeof(float) * (size_t)ls_merit_smem_floats(d.n, d.M, d.N);
+  int rc = ILQG_ERR_UNSUPPORTED;
+#define LS_ROLL(SS)                                                                               \
+  case SS:                                                                                        \
+    if ((rc = SetSmem(k_ls_rollout<SS>, smem_r)) != ILQG_OK) return rc;                            \
+    k_ls_rollout<SS><<<blocks, SS * 32, smem_r, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset); \
+    break;
+  switch (S) {
+    LS_ROLL(1) LS_ROLL(2) LS_ROLL(3) LS_ROLL(4)
+    default: return ILQG_ERR_UNSUPPORTED;
+  }
+#undef LS_ROLL
+  if ((rc = SetSmem(k_ls_merit, smem_m)) != ILQG_OK) return rc;
+  // the merit kernels stride over the item blocks that hold work (known on the device only):
+  // grids sized for the machine, a few resident blocks per SM
+  const int chunks = (d.T + KLS_MERIT_CHUNK - 1) / KLS_MERIT_CHUNK;
+  const dim3 grid_m(std::min(blocks, std::max(1, h->sm_count * 8 / chunks)), chunks);
+  k_ls_merit<<<grid_m, d.N * 32, smem_m, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset, blocks);
+  k_ls_merit_sum<<<std::min((blocks + 3) / 4, h->sm_count * 4), 128, 0, h->stream>>>(h->d, h->p, h->s, h->ls, mode,
+                                                                                   h->ls_cur, q_offset, blocks);
+  h->launches += 3;
+  CUDA_TRY(cudaGetLastError());
+  return ILQG_OK;
+}
+
 int LaunchLsEval(SubSolver* h, int mode, int blocks, int q_offset) {
   const DevDesc& d = h->d;
   const size_t smem = sizeof(float) * (size_t)ls_smem_floats(d.n, d.M, d.N, d.num_subsystems);
   if (blocks <= 0) return ILQG_OK;
   if (blocks > h->ls_blocks_max) return ILQG_ERR_INVALID_ARGUMENT;
+  ProfScope prof(h, mode == LS_MODE_FRESH ? 4 : mode == LS_MODE_QUEUED ? 5 : 7);
+  if (h->ls_split && d.num_subsystems <= 4) return LaunchLsSplit(h, mode, blocks, q_offset);
   const int nw = d.num_subsystems + d.N;
   int rc = ILQG_ERR_UNSUPPORTED;
 #define LS_CASE(NW)                                                                              \
@@ -496,7 +530,6 @@ int LaunchLsEval(SubSolver* h, int mode, int blocks, int q_offset) {
     if ((rc = SetSmem(k_ls_eval<NW>, smem)) != ILQG_OK) return rc;                                \
     k_ls_eval<NW><<<blocks, NW * 32, smem, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset); \
     break;
-  ProfScope prof(h, mode == LS_MODE_FRESH ? 4 : mode == LS_MODE_QUEUED ? 5 : 7);
   switch (nw) {
     LS_CASE(2) LS_CASE(3) LS_CASE(4) LS_CASE(5) LS_CASE(6) LS_CASE(7) LS_CASE(8)
     default: return ILQG_ERR_UNSUPPORTED;
@@ -760,6 +793,8 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
     delete h;
     return ILQG_ERR_INVALID_ARGUMENT;
   }
+  if (cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || h->sm_count < 1)
+    h->sm_count = 148;
   h->dims_key = -1;
   for (int k = 0; k < kNumDims; k++)
     if (kDims[k].n == h->d.n && kDims[k].M == h->d.M && kDims[k].N == h->d.N) h->dims_key = k;
@@ -876,15 +911,19 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
     // "absorbed" shortcut of k_ls_decide rarely triggers before j ~ 40)
     int JB = max_bt - JA;
     if (const char* e = std::getenv("ILQG_LS_JB")) JB = std::max(0, std::min(max_bt - JA, std::atoi(e)));
-    int cap = (int)std::max<size_t>(1, (B + 1) / 2);
+    // queue slots one continued-window launch holds candidate trajectories for: the whole batch
+    // (one launch, no empty second chunk) while that scratch stays under 8 GiB, else chunks
+    const size_t per_slot = (size_t)std::max(1, JB) * T * (n + M) * sizeof(float);
+    int cap = (int)std::max<size_t>(1, std::min<size_t>(B, std::max<size_t>((B + 1) / 2, ((size_t)8 << 30) / per_slot)));
     if (const char* e = std::getenv("ILQG_LS_CAP")) cap = std::max(1, std::min<int>((int)B, std::atoi(e)));
-    h->pipeline = 2;  // measured: 2 > 0 > 1 (profiles/r01_summary.md)
+    h->pipeline = 0;  // measured with the split linesearch: 0 > 2 > 1 (profiles/r01_schedule_experiments.md)
     if (const char* e = std::getenv("ILQG_PIPELINE")) h->pipeline = std::atoi(e);
     ls.JA = JA;
     ls.JB = JB;
     ls.cap = cap;
     int lpw = 32;
     if (const char* e = std::getenv("ILQG_LS_LPW")) lpw = std::atoi(e);
+    if (const char* e = std::getenv("ILQG_LS_SPLIT")) h->ls_split = std::atoi(e);
     if (lpw != 8 && lpw != 16 && lpw != 32 && lpw != 4) lpw = 32;
     ls.lpw = lpw;
     ls.nA_blocks = (int)((B * JA + lpw - 1) / lpw);
@@ -1345,7 +1384,9 @@ const char* ilqg_strerror(int code) {
 int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params, int batch, int device,
                 ilqg_handle* out) {
   if (!desc || !params || !out || batch < 1) return ILQG_ERR_INVALID_ARGUMENT;
-  int groups = batch >= 2048 ? 4 : batch >= 512 ? 2 : 1;
+  // one group: with the linesearch split into rollout and merit kernels the plain sequence on one
+  // stream is the fastest schedule measured (profiles/r01_schedule_experiments.md)
+  int groups = 1;
   if (const char* e = std::getenv("ILQG_GROUPS")) groups = std::max(1, std::atoi(e));
   groups = std::min(groups, batch);
   ilqg_solver* h = new (std::nothrow) ilqg_solver();

@@ -146,22 +146,27 @@ struct HwSmem {
   static constexpr int F = Z + NP * NX * NX;       // [NX][NX]
   static constexpr int AW = F + NX * NX;           // A, later W^T
   static constexpr int Bm = AW + NX * NX;          // [NX][MU]
-  static constexpr int Bt = Bm + r4(NX * MU);      // [MU][NX]
-  static constexpr int BZt = Bt + r4(MU * NX);     // [NX][MU]   (B_i^T Z_i)^T
-  static constexpr int P = BZt + r4(NX * MU);      // [MU][NX]   Y, then the solution P
+  // (B_i^T Z_i)^T [NX][MU] lives in the head of the F buffer: it is dead once S X = Y is
+  // solved, F is only formed after that.  Together with reading B in its stored layout when F is
+  // formed (no transposed copy) this keeps an instance under 7 KB, i.e. 8 blocks per SM -- the
+  // occupancy the 128-register budget allows; K_bwd's time follows its resident warps.
+  static constexpr int BZt = F;
+  static constexpr int P = Bm + r4(NX * MU);       // [MU][NX]   Y, then the solution P
   static constexpr int zeta = P + r4(MU * NX);     // [NP][NX]
-  static constexpr int tv = zeta + r4(NP * NX);    // [NX]
-  static constexpr int beta = tv + r4(NX);         // [NX]
+  static constexpr int beta = zeta + r4(NP * NX);  // [NX]
   static constexpr int pv = beta + r4(NX);         // [NX] adjoint p_{k+1}
   static constexpr int pn = pv + r4(NX);           // [NX] scratch for p_k
   static constexpr int S = pn + r4(NX);            // [MU][MU]
+  static constexpr int tv = S;                     // [NX] shares S (dead once the solve has loaded it)
+  static_assert(r4(MU * MU) >= NX, "tv is overlaid on S");
   static constexpr int ya = S + r4(MU * MU);       // [MU] alpha column
   static constexpr int lrr = ya + r4(MU);          // [l | R | r] copied from the record (run-time size)
   // resident blocks per SM the shared-memory footprint allows (own-control pairs only), used as
   // the register cap in __launch_bounds__
   static constexpr int lrr_typ = r4(NP * NX + NP * m * m + NP * m);
-  static constexpr int block_bytes = 4 * 4 * (lrr + lrr_typ) + 1024;
-  static constexpr int min_blocks = (225 * 1024 / block_bytes) < 1 ? 1 : ((225 * 1024 / block_bytes) > 12 ? 12 : (225 * 1024 / block_bytes));
+  static constexpr int block_bytes = 4 * 4 * (lrr + lrr_typ) + 1024;  // + the per-block reservation
+  static constexpr int fit = 228 * 1024 / block_bytes;               // 228 KB of shared memory per SM
+  static constexpr int min_blocks = fit < 1 ? 1 : (fit > 12 ? 12 : fit);
 };
 
 constexpr int KHW_WARPS = 2;  // 4 instances per 64-thread block
@@ -253,7 +258,6 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
   float* F = sm + L::F;
   float* AW = sm + L::AW;
   float* Bm = sm + L::Bm;
-  float* Bt = sm + L::Bt;
   float* BZt = sm + L::BZt;
   float* P = sm + L::P;
   float* zeta = sm + L::zeta;
@@ -323,18 +327,14 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
 
   for (int kk = T - 2; kk >= 0; kk--) {
     const float* rec = recb + (size_t)kk * d.rec;
-    // ---- stage [A|B] and [l|R|r] from the prefetch registers; keep both B layouts ----
+    // ---- stage [A|B] and [l|R|r] from the prefetch registers ----
 #pragma unroll
     for (int t = 0; t < AB_PER; t++) {
       const int e = l16 + 16 * t;
       if (e < A4) {
         reinterpret_cast<float4*>(AW)[e] = preAB[t];
       } else if (e < AB4) {
-        const int f0 = (e - A4) * 4;
         reinterpret_cast<float4*>(Bm)[e - A4] = preAB[t];
-        const float v[4] = {preAB[t].x, preAB[t].y, preAB[t].z, preAB[t].w};
-#pragma unroll
-        for (int u = 0; u < 4; u++) Bt[((f0 + u) % MU) * NX + (f0 + u) / MU] = v[u];
       }
     }
 #pragma unroll
@@ -473,8 +473,23 @@ k_lq_backward_hw(const __grid_constant__ DevDesc d, const DevParams p, Slab s, i
       for (int r = 0; r < TR; r++) ldvec<TC>(AW + (a0 + r) * NX + c0, f[r]);
 #pragma unroll
       for (int i = 0; i < NP; i++) {
+        // F[a][c] -= sum_q B_i[a][q] P_i[q][c], B read in its stored [NX][MU] layout
         float acc[TR][TC];
-        mm_tn<m, TR, TC>(Bt + (i * m) * NX + a0, NX, P + (i * m) * NX + c0, NX, acc);
+#pragma unroll
+        for (int r = 0; r < TR; r++)
+#pragma unroll
+          for (int j = 0; j < TC; j++) acc[r][j] = 0.f;
+#pragma unroll
+        for (int q = 0; q < m; q++) {
+          float pr[TC];
+          ldvec<TC>(P + (i * m + q) * NX + c0, pr);
+#pragma unroll
+          for (int r = 0; r < TR; r++) {
+            const float bv = Bm[(a0 + r) * MU + i * m + q];
+#pragma unroll
+            for (int j = 0; j < TC; j++) acc[r][j] = fmaf(bv, pr[j], acc[r][j]);
+          }
+        }
 #pragma unroll
         for (int r = 0; r < TR; r++)
 #pragma unroll

@@ -341,6 +341,323 @@ k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratc
   }
 }
 
+// ===========================================================================
+// Split evaluation: rollout and merit as two kernels.
+//
+// Only the rollout is inherently sequential in k.  The merit terms (per-step gradients of the
+// players' costs) depend on (x_k, u_k) alone, so once a candidate trajectory is in global memory
+// -- where it has to go anyway to be promoted -- they can be evaluated for all time steps at
+// once.  In the fused k_ls_eval above the cost warps sit on the rollout's latency chain and pace
+// it (ncu source view: both roles wait for each other at the per-step barrier, and removing a
+// quarter of the dynamics warps' instructions did not move the kernel,
+// profiles/r01_schedule_experiments.md).  Split:
+//   k_ls_rollout    S warps per block (one per subsystem), 32 items per block: the dynamics role
+//                   alone, one named barrier per step, ~30 KB shared memory and ~100 threads per
+//                   block, so a whole queued window is resident at once;
+//   k_ls_merit      N warps per block (one per player), grid (item block, chunk of time steps):
+//                   the cost role over a chunk of the stored trajectory, all chunks in parallel;
+//   k_ls_merit_sum  one thread per item: the ordered (k, i) sum of the merit terms.
+// Same arithmetic on the same fp32 values in the same order as the fused kernel: merits, cost
+// values and therefore every Armijo decision are bit-identical to it.
+// ===========================================================================
+struct LsIo {
+  const float *last_xs, *last_us, *P, *alpha, *x_start;
+  float *out_xs, *out_us;
+  bool scaled;
+};
+
+// where an item reads its strategy / reference from and rolls its trajectory to
+__device__ __forceinline__ LsIo ls_io(const Slab& s, const LsScratch& ls, int mode, const LsItem& it, int item,
+                                      int T, int n, int M) {
+  LsIo io;
+  const int b = it.b;
+  const size_t ox = (size_t)b * T * n, ou = (size_t)b * T * M, oP = (size_t)b * T * M * n;
+  io.scaled = true;
+  if (mode == LS_MODE_BEGIN) {
+    io.last_xs = s.prob_xs + ox;
+    io.last_us = s.prob_us + ou;
+    io.P = s.prob_P + oP;
+    io.alpha = s.prob_a + ou;
+    io.x_start = s.x0 + (size_t)b * n;
+    io.scaled = false;
+    io.out_xs = s.op_xs[0] + ox;
+    io.out_us = s.op_us[0] + ou;
+  } else {
+    const int cur = it.valid ? s.op_cur[b] : 0, scur = it.valid ? s.st_cur[b] : 0;
+    io.last_xs = s.op_xs[cur] + ox;
+    io.last_us = s.op_us[cur] + ou;
+    io.P = s.st_P[1 - scur] + oP;
+    io.alpha = s.st_a[1 - scur] + ou;
+    io.x_start = io.last_xs;
+    if (mode == LS_MODE_FRESH && ls.JA == 1) {
+      // the lone first-window candidate is accepted 98 % of the time: roll it straight into the
+      // candidate operating-point buffer (k_ls_decide then has nothing to copy)
+      io.out_xs = s.op_xs[1 - cur] + ox;
+      io.out_us = s.op_us[1 - cur] + ou;
+    } else {
+      io.out_xs = ls.traj_xs + (size_t)item * T * n;
+      io.out_us = ls.traj_us + (size_t)item * T * M;
+    }
+  }
+  return io;
+}
+
+// shared memory of k_ls_rollout (floats): dx[2][n][32] + abs[S][32] + pbuf[S][2][32][2n+4]
+__host__ __device__ inline int ls_rollout_smem_floats(int n, int S) {
+  return 2 * n * 32 + S * 32 + S * 2 * 32 * (2 * n + 4);
+}
+
+template <int S>
+__global__ void __launch_bounds__(S * 32)
+k_ls_rollout(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode, int cur_q,
+             int q_offset) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = d.n, M = d.M, T = d.T;
+  const int item = blockIdx.x * ls.lpw + lane;
+  const LsItem it = ls_decode(p, s, ls, mode, cur_q, q_offset, blockIdx.x, lane);
+  if (!__syncthreads_or(it.valid)) return;
+  const bool valid = it.valid;
+  const LsIo io = ls_io(s, ls, mode, it, item, T, n, M);
+  float* dxs2 = smem;                          // [2][n][32]
+  float* absf = dxs2 + 2 * n * 32;             // [S][32]
+  float* pbase = absf + S * 32;                // [S][2][32][2n+4]  prefetched feedback rows
+  const float s0 = p.initial_alpha_scaling, rho = p.geometric_alpha_scaling;
+  const float dt_half = (float)(d.time_step / 2.0);
+  // ScaleAlphas multiplies alpha by rho once per backtrack (src/ilq_solver.cpp:66-72, 331).  When
+  // rho is a power of two every one of those products is exact, so rho^j can be formed once.
+  int rho_e;
+  const bool rho_exact = fabsf(frexpf(rho, &rho_e)) == 0.5f;
+  float rho_j = 1.0f;
+  for (int jj = 0; jj < it.j; jj++) rho_j *= rho;
+
+  const DevSubsystem& sub = d.sub[warp];
+  const int xd = subsystem_xdim(sub.kind);
+  const int nu = sub.kind == ILQG_DYN_AIR3D ? 2 : d.udim[sub.first_player];  // own control rows
+  float x[6];
+#pragma unroll
+  for (int a = 0; a < 6; a++) x[a] = (valid && a < xd) ? io.x_start[sub.x_offset + a] : 0.f;
+  // Software pipeline: the feedback rows P[k][own rows][:] of the NEXT step are copied
+  // asynchronously (cp.async, 16 B granules) into a per-lane double buffer while this step
+  // integrates; the small reference values ride in registers.  Lane stride PST = 2n + 4
+  // floats keeps the 128-bit reads of 8 consecutive lanes on distinct banks.
+  const bool vecP = (n & 3) == 0 && nu <= 2;
+  const int PST = 2 * n + 4;
+  float* pbuf = pbase + (size_t)warp * 2 * 32 * PST;
+  float nref[6], nuref[2] = {0.f, 0.f}, nal[2] = {0.f, 0.f};
+  bool absorbed = true;
+  auto prefetch = [&](int k) {
+    if (!valid) return;
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+      if (a < xd)
+        nref[a] = k > 0 ? io.last_xs[(size_t)k * n + sub.x_offset + a] : io.x_start[sub.x_offset + a];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      if (q >= nu) break;
+      const int c = q == 0 ? sub.u_offset : sub.u_offset2;
+      nuref[q] = io.last_us[(size_t)k * M + c];
+      nal[q] = io.alpha[(size_t)k * M + c];
+      if (vecP) {
+        const float* src = io.P + ((size_t)k * M + c) * n;
+        float* dst = pbuf + ((size_t)(k & 1) * 32 + lane) * PST + q * n;
+        for (int a4 = 0; a4 < n / 4; a4++) {
+          const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst + 4 * a4);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src + 4 * a4) : "memory");
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int a = 0; a < 6; a++) nref[a] = 0.f;
+  prefetch(0);
+  for (int k = 0; k < T; k++) {
+    float* dxs = dxs2 + (k & 1) * n * 32;
+    float ref[6], uref[2], al[2];
+#pragma unroll
+    for (int a = 0; a < 6; a++) ref[a] = nref[a];
+    uref[0] = nuref[0]; uref[1] = nuref[1];
+    al[0] = nal[0]; al[1] = nal[1];
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (k + 1 < T) prefetch(k + 1);
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+      if (a < xd) {
+        // last_operating_point.xs[0] is the start state (src/ilq_solver.cpp:88-89)
+        dxs[(sub.x_offset + a) * 32 + lane] = x[a] - ref[a];
+        if (valid) io.out_xs[(size_t)k * n + sub.x_offset + a] = x[a];
+      }
+    // the one barrier of a step: dx is double-buffered, so the warp that races ahead writes the
+    // other half while the others may still be reading this one
+    if (S > 1) __syncthreads();
+    else __syncwarp();
+    float uu[2] = {0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      if (q >= nu) break;
+      const int c = q == 0 ? sub.u_offset : sub.u_offset2;
+      float uv = 0.f;
+      if (valid) {
+        float acc = 0.f;
+        if (vecP) {
+          const float4* Prow = reinterpret_cast<const float4*>(pbuf + ((size_t)(k & 1) * 32 + lane) * PST + q * n);
+          for (int a4 = 0; a4 < n / 4; a4++) {
+            const float4 pv = Prow[a4];
+            acc = fmaf(pv.x, dxs[(4 * a4 + 0) * 32 + lane], acc);
+            acc = fmaf(pv.y, dxs[(4 * a4 + 1) * 32 + lane], acc);
+            acc = fmaf(pv.z, dxs[(4 * a4 + 2) * 32 + lane], acc);
+            acc = fmaf(pv.w, dxs[(4 * a4 + 3) * 32 + lane], acc);
+          }
+        } else {
+          const float* Pr = io.P + ((size_t)k * M + c) * n;
+          for (int a = 0; a < n; a++) acc = fmaf(__ldg(Pr + a), dxs[a * 32 + lane], acc);
+        }
+        float alv = al[q];
+        if (io.scaled) {
+          alv *= s0;  // ScaleAlphas(initial_alpha_scaling), then geometric_alpha_scaling^j
+          if (rho_exact) {
+            alv *= rho_j;
+          } else {
+            for (int jj = 0; jj < it.j; jj++) alv *= rho;
+          }
+        }
+        const float t = uref[q] - acc;
+        uv = t - alv;  // Strategy::operator(), strategy.h:73-76
+        absorbed = absorbed && (uv == t);
+        io.out_us[(size_t)k * M + c] = uv;
+      }
+      uu[q] = uv;
+    }
+    if (k < T - 1) subsystem_integrate(sub, dt_half, x, uu[0], uu[1]);
+  }
+  // If u_k = (u_ref - P dx) - alpha_k s0 rho^j rounded to (u_ref - P dx) at every step, every
+  // deeper candidate (smaller alpha) reproduces this rollout bit for bit: k_ls_decide can run
+  // the rest of the Armijo loop on this merit without another rollout.
+  absf[warp * 32 + lane] = absorbed ? 1.f : 0.f;
+  __syncthreads();
+  if (warp == 0 && valid) {
+    bool all_absorbed = true;
+    for (int w2 = 0; w2 < S; w2++) all_absorbed = all_absorbed && absf[w2 * 32 + lane] != 0.f;
+    ls.absorbed[item] = all_absorbed ? 1 : 0;
+  }
+}
+
+// Item blocks of a window launch that can hold valid items.  A queued window is launched for `cap`
+// queue slots without the host knowing how many are filled; the filled ones are a prefix.
+__device__ __forceinline__ int ls_live_blocks(const LsScratch& ls, int mode, int cur_q, int q_offset, int blocks) {
+  if (mode != LS_MODE_QUEUED) return blocks;
+  const int live = min(max(ls.counts[cur_q] - q_offset, 0), ls.cap);
+  return min(blocks, (int)(((long long)live * ls.JB + ls.lpw - 1) / ls.lpw));
+}
+
+// time steps one k_ls_merit block covers
+constexpr int KLS_MERIT_CHUNK = 5;
+
+// shared memory of k_ls_merit (floats): per player warp xu[n + M][32] + acc[n + M][32]
+__host__ __device__ inline int ls_merit_smem_floats(int n, int M, int N) { return N * 2 * (n + M) * 32; }
+
+__global__ void __launch_bounds__(ILQG_MAX_PLAYERS * 32)
+k_ls_merit(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode, int cur_q,
+           int q_offset, int blocks) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = d.n, M = d.M, N = d.N, T = d.T;
+  const int live_blocks = ls_live_blocks(ls, mode, cur_q, q_offset, blocks);
+  // grid-stride over the item blocks (the grid is sized for the machine, not for `blocks`)
+  for (int ib = blockIdx.x; ib < live_blocks; ib += gridDim.x) {
+  const int item = ib * ls.lpw + lane;
+  const LsItem it = ls_decode(p, s, ls, mode, cur_q, q_offset, ib, lane);
+  if (!__syncthreads_or(it.valid)) continue;
+  const bool valid = it.valid;
+  const int b = it.b;
+  const LsIo io = ls_io(s, ls, mode, it, item, T, n, M);
+  const int i = warp;  // player
+  float* slot = smem + (size_t)i * 2 * (n + M) * 32;   // [n + M][32]  this step's state and controls
+  float* acc = slot + (n + M) * 32;                     // [n + M][32]  gradient accumulators
+  float* terms = ls.terms + (size_t)ib * T * 2 * N * 32;
+  float* vals = ls.vals + (size_t)ib * T * N * 32;
+  const float mu = valid ? s.mu[b] : 0.f;
+  const int te = valid ? s.te_quad[(size_t)b * N + i] : 0;
+  const bool additive = d.cost_structure[i] == ILQG_COST_SUM;
+  const int mi = d.udim[i];
+  const int k0 = blockIdx.y * KLS_MERIT_CHUNK, k1 = min(T, k0 + KLS_MERIT_CHUNK);
+  for (int kk = k0; kk < k1; kk++) {
+    // the stored candidate trajectory (item-major in global memory) -> lane-minor tile
+    if (valid) {
+      const float* xs = io.out_xs + (size_t)kk * n;
+      const float* us = io.out_us + (size_t)kk * M;
+      if ((n & 3) == 0 && (((size_t)T * n) & 3) == 0) {
+        for (int a4 = 0; a4 < n / 4; a4++) {
+          const float4 v = *reinterpret_cast<const float4*>(xs + 4 * a4);
+          slot[(4 * a4 + 0) * 32 + lane] = v.x;
+          slot[(4 * a4 + 1) * 32 + lane] = v.y;
+          slot[(4 * a4 + 2) * 32 + lane] = v.z;
+          slot[(4 * a4 + 3) * 32 + lane] = v.w;
+        }
+      } else {
+        for (int a = 0; a < n; a++) slot[a * 32 + lane] = xs[a];
+      }
+      for (int c = 0; c < M; c++) slot[(n + c) * 32 + lane] = us[c];
+    } else {
+      for (int a = 0; a < n + M; a++) slot[a * 32 + lane] = 0.f;
+    }
+    for (int a = 0; a < n + M; a++) acc[a * 32 + lane] = 0.f;
+    const bool full = additive || te == kk;
+    float value = 0.f;
+    for (int c = d.cost_begin[i]; c < d.cost_begin[i + 1]; c++) {
+      const DevCost& cd = d.cost[c];
+      const bool is_con = cd.slot >= 0;
+      // PlayerCost::Quadraticize vs QuadraticizeControlCosts (src/ilq_solver.cpp:483-487): off the
+      // extreme timestep of a MAX/MIN player only control COSTS enter the gradient; the cost
+      // VALUE (PlayerCost::Evaluate) always counts every state and control cost.
+      const bool in_quad = full || (cd.arg >= 0 && !is_con);
+      if (!in_quad && is_con) continue;
+      const float lambda =
+          (is_con && valid) ? s.lambdas[((size_t)b * d.num_constraints + cd.slot) * T + s.lambda_index[kk]] : 0.f;
+      GatedSink sink{acc + (cd.arg < 0 ? 0 : (n + d.uoff[cd.arg]) * 32) + lane, in_quad};
+      const float* in = cd.arg < 0 ? slot + lane : slot + (n + d.uoff[cd.arg]) * 32 + lane;
+      float v = 0.f;
+      quadraticize_record_sink<false, 32, true>(d, cd, in, cd.arg < 0 ? n : d.udim[cd.arg], lambda, mu, sink, &v);
+      if (!is_con) value += v;  // PlayerCost::Evaluate: costs only
+    }
+    // ILQSolver::MeritFunction terms (src/ilq_solver.cpp:416-430)
+    float sq = 0.f;
+    for (int a = 0; a < mi; a++) {
+      const float rv = acc[(n + d.uoff[i] + a) * 32 + lane];
+      sq = fmaf(rv, rv, sq);
+    }
+    float sq2 = 0.f;
+    if (kk > 0)
+      for (int a = 0; a < n; a++) {
+        const float lv = acc[a * 32 + lane];
+        sq2 = fmaf(lv, lv, sq2);
+      }
+    terms[((size_t)kk * 2 * N + 2 * i) * 32 + lane] = sq;
+    terms[((size_t)kk * 2 * N + 2 * i + 1) * 32 + lane] = sq2;
+    vals[((size_t)kk * N + i) * 32 + lane] = value;
+  }
+  __syncthreads();  // the tiles are reused by the next item block
+  }
+}
+
+// single running fp32 accumulator in (k, i) order, as the reference (src/ilq_solver.cpp:416-430)
+__global__ void __launch_bounds__(128)
+k_ls_merit_sum(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode, int cur_q,
+               int q_offset, int blocks) {
+  const int lane = threadIdx.x & 31;
+  const int live_blocks = ls_live_blocks(ls, mode, cur_q, q_offset, blocks);
+  for (int w = blockIdx.x * 4 + (threadIdx.x >> 5); w < live_blocks; w += gridDim.x * 4) {
+    const LsItem it = ls_decode(p, s, ls, mode, cur_q, q_offset, w, lane);
+    if (!it.valid) continue;
+    const float* terms = ls.terms + (size_t)w * d.T * 2 * d.N * 32;
+    float merit = 0.f;
+    const int cnt = d.T * 2 * d.N;
+    for (int e = 0; e < cnt; e++) merit += terms[(size_t)e * 32 + lane];
+    ls.merit[w * ls.lpw + lane] = 0.5 * merit;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // decide: one warp per instance
 // ---------------------------------------------------------------------------
