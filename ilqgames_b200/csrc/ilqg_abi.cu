@@ -852,7 +852,9 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
   };
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-  const bool side_high = std::getenv("ILQG_SIDE_PRIORITY") && std::atoi(std::getenv("ILQG_SIDE_PRIORITY")) != 0;
+  // the side stream carries the few open linesearches, which are latency chains: its blocks must
+  // not queue behind the thousands of K_lq blocks of the main stream
+  const bool side_high = !std::getenv("ILQG_SIDE_PRIORITY") || std::atoi(std::getenv("ILQG_SIDE_PRIORITY")) != 0;
   if (cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, side_high ? prio_hi : prio_lo) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fresh, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming) != cudaSuccess)
@@ -916,7 +918,9 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
     const size_t per_slot = (size_t)std::max(1, JB) * T * (n + M) * sizeof(float);
     int cap = (int)std::max<size_t>(1, std::min<size_t>(B, std::max<size_t>((B + 1) / 2, ((size_t)8 << 30) / per_slot)));
     if (const char* e = std::getenv("ILQG_LS_CAP")) cap = std::max(1, std::min<int>((int)B, std::atoi(e)));
-    h->pipeline = 0;  // measured with the split linesearch: 0 > 2 > 1 (profiles/r01_schedule_experiments.md)
+    // measured with the split linesearch: 2 with a high-priority side stream > 0 > 2 > 1
+    // (profiles/r01_schedule_experiments.md)
+    h->pipeline = 2;
     if (const char* e = std::getenv("ILQG_PIPELINE")) h->pipeline = std::atoi(e);
     ls.JA = JA;
     ls.JB = JB;
