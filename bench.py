@@ -293,7 +293,9 @@ def run_b200(args):
                          "for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: one JSON line only
+        # one JSON line only on stdout: whatever NCCL logs (its version banner at NCCL_DEBUG >= VERSION)
+        # goes to a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/ilqg_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
