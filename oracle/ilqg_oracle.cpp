@@ -6,20 +6,26 @@
 // cpu_baseline / --impl reference legs and __graft_entry__.smoke() may load the
 // library built from this file; the product (ilqgames_b200/) never does.
 //
-// Parity pinning: the reference C++ cannot be built in this environment (no
-// Eigen3 / glog / gflags), so this restatement is pinned
-// against the reference's own tests instead, transcribed with file:line
-// citations in tests/test_oracle_pins.py:
+// Parity pinning (details in DESIGN.md section 6):
+//  1. against outputs of the reference itself.  The reference's build system cannot run here
+//     (cmake + Eigen3 + glog + gflags are absent), but `make -C oracle ref` compiles the
+//     reference's OWN src/*.cpp, unmodified, against the stand-in headers under oracle/ref_shim
+//     (the reference's own 51-test gtest suite passes on that build: `make ref-test`).
+//     tests/golden/make_ref_golden.py runs it and commits tests/golden/ref_*.npz; this
+//     restatement reproduces those fixtures BIT FOR BIT (tests/test_ref_pins.py): ILQSolver
+//     iterates, final strategies, AugmentedLagrangianSolver results with multipliers, the open-loop
+//     solver, Problem::SetUpNextRecedingHorizon, on all three example problems.  What that does
+//     not pin is the rounding of Eigen's own dense kernels (stand-in: plain loops).
+//  2. against the reference's own tests, transcribed with file:line citations in
+//     tests/test_oracle_pins.py:
 //   * geometry golden values     test/test_polyline2.cpp:52-125,
 //                                test/test_line_segment2.cpp:57-102
-//   * LQ solve known answer      test/test_lq_solver.cpp:292-317 (Lyapunov, 1e-4)
+//   * LQ solve known answer      test/test_lq_solver.cpp:292-317 (Lyapunov, 1e-4), Nash checks
+//                                :319-379, open loop vs feedback :381-436
 //   * analytic derivatives vs finite differences
 //                                test/test_quadraticization.cpp:138-201,
 //                                test/test_linearization.cpp:142-196
 //   * player cost known answers  test/test_player_cost.cpp:84-122
-// The reference holds NO test of ILQSolver iterates / linesearch / AL loop, so
-// for those rows parity is pinned only by this restatement ("parity unpinned by
-// reference tests" -- see DESIGN.md).
 //
 // Every function cites the reference file:line it follows.  Scalars are `real`
 // (float by default = the reference's MatrixXf/VectorXf; build with
