@@ -552,7 +552,10 @@ __device__ __forceinline__ int ls_live_blocks(const LsScratch& ls, int mode, int
 }
 
 // time steps one k_ls_merit block covers
-constexpr int KLS_MERIT_CHUNK = 5;
+#ifndef ILQG_MERIT_CHUNK
+#define ILQG_MERIT_CHUNK 5
+#endif
+constexpr int KLS_MERIT_CHUNK = ILQG_MERIT_CHUNK;
 
 // shared memory of k_ls_merit (floats): per player warp xu[n + M][32] + acc[n + M][32]
 __host__ __device__ inline int ls_merit_smem_floats(int n, int M, int N) { return N * 2 * (n + M) * 32; }
