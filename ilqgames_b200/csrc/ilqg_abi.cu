@@ -486,7 +486,10 @@ int LaunchLqRecords(SubSolver* h, int only_running, Sel sel = Sel{SEL_ALL, nullp
   return ILQG_OK;
 }
 
-// rollout + merit of one linesearch window as three kernels (ilqg_linesearch.cuh, "Split evaluation")
+// linesearch windows as rollout + merit kernels (k_ls_decide then sums the merit terms itself)?
+int LsSplit(const SubSolver* h) { return h->ls_split && h->d.num_subsystems <= 4 ? 1 : 0; }
+
+// rollout + merit of one linesearch window as two kernels (ilqg_linesearch.cuh, "Split evaluation")
 int LaunchLsSplit(SubSolver* h, int mode, int blocks, int q_offset) {
   const DevDesc& d = h->d;
   const int S = d.num_subsystems;
@@ -509,9 +512,7 @@ int LaunchLsSplit(SubSolver* h, int mode, int blocks, int q_offset) {
   const int chunks = (d.T + KLS_MERIT_CHUNK - 1) / KLS_MERIT_CHUNK;
   const dim3 grid_m(std::min(blocks, std::max(1, h->sm_count * 8 / chunks)), chunks);
   k_ls_merit<<<grid_m, d.N * 32, smem_m, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset, blocks);
-  k_ls_merit_sum<<<std::min((blocks + 3) / 4, h->sm_count * 4), 128, 0, h->stream>>>(h->d, h->p, h->s, h->ls, mode,
-                                                                                   h->ls_cur, q_offset, blocks);
-  h->launches += 3;
+  h->launches += 2;
   CUDA_TRY(cudaGetLastError());
   return ILQG_OK;
 }
@@ -522,7 +523,7 @@ int LaunchLsEval(SubSolver* h, int mode, int blocks, int q_offset) {
   if (blocks <= 0) return ILQG_OK;
   if (blocks > h->ls_blocks_max) return ILQG_ERR_INVALID_ARGUMENT;
   ProfScope prof(h, mode == LS_MODE_FRESH ? 4 : mode == LS_MODE_QUEUED ? 5 : 7);
-  if (h->ls_split && d.num_subsystems <= 4) return LaunchLsSplit(h, mode, blocks, q_offset);
+  if (LsSplit(h)) return LaunchLsSplit(h, mode, blocks, q_offset);
   const int nw = d.num_subsystems + d.N;
   int rc = ILQG_ERR_UNSUPPORTED;
 #define LS_CASE(NW)                                                                              \
@@ -551,7 +552,8 @@ int LaunchLinesearchFresh(SubSolver* h) {
   if ((rc = LaunchLsEval(h, LS_MODE_FRESH, h->ls.nA_blocks, 0)) != ILQG_OK) return rc;
   {
     ProfScope pd(h, 6);
-    k_ls_decide<<<dec_blocks, KDEC_WARPS * 32, 0, h->stream>>>(h->d, h->p, h->s, h->ls, LS_MODE_FRESH, h->ls_cur, 0);
+    k_ls_decide<<<dec_blocks, KDEC_WARPS * 32, 0, h->stream>>>(h->d, h->p, h->s, h->ls, LS_MODE_FRESH, h->ls_cur, 0,
+                                                               LsSplit(h));
   }
   h->launches++;
   h->ls_cur = 1 - h->ls_cur;  // the queue just filled is now the one to drain
@@ -576,7 +578,7 @@ int LaunchLinesearchQueued(SubSolver* h) {
         {
           ProfScope pd(h, 6);
           k_ls_decide<<<(cap + KDEC_WARPS - 1) / KDEC_WARPS, KDEC_WARPS * 32, 0, h->stream>>>(
-              h->d, h->p, h->s, h->ls, LS_MODE_QUEUED, h->ls_cur, q0);
+              h->d, h->p, h->s, h->ls, LS_MODE_QUEUED, h->ls_cur, q0, LsSplit(h));
         }
         h->launches++;
       }

@@ -356,7 +356,8 @@ k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratc
 //                   block, so a whole queued window is resident at once;
 //   k_ls_merit      N warps per block (one per player), grid (item block, chunk of time steps):
 //                   the cost role over a chunk of the stored trajectory, all chunks in parallel;
-//   k_ls_merit_sum  one thread per item: the ordered (k, i) sum of the merit terms.
+//   (k_ls_decide then adds up each candidate's terms in the reference's (k, i) order, one lane
+//   per candidate.)
 // Same arithmetic on the same fp32 values in the same order as the fused kernel: merits, cost
 // values and therefore every Armijo decision are bit-identical to it.
 // ===========================================================================
@@ -644,23 +645,6 @@ k_ls_merit(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScrat
   }
 }
 
-// single running fp32 accumulator in (k, i) order, as the reference (src/ilq_solver.cpp:416-430)
-__global__ void __launch_bounds__(128)
-k_ls_merit_sum(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode, int cur_q,
-               int q_offset, int blocks) {
-  const int lane = threadIdx.x & 31;
-  const int live_blocks = ls_live_blocks(ls, mode, cur_q, q_offset, blocks);
-  for (int w = blockIdx.x * 4 + (threadIdx.x >> 5); w < live_blocks; w += gridDim.x * 4) {
-    const LsItem it = ls_decode(p, s, ls, mode, cur_q, q_offset, w, lane);
-    if (!it.valid) continue;
-    const float* terms = ls.terms + (size_t)w * d.T * 2 * d.N * 32;
-    float merit = 0.f;
-    const int cnt = d.T * 2 * d.N;
-    for (int e = 0; e < cnt; e++) merit += terms[(size_t)e * 32 + lane];
-    ls.merit[w * ls.lpw + lane] = 0.5 * merit;
-  }
-}
-
 // ---------------------------------------------------------------------------
 // decide: one warp per instance
 // ---------------------------------------------------------------------------
@@ -702,7 +686,7 @@ constexpr int KDEC_WARPS = 4;
 
 __global__ void __launch_bounds__(KDEC_WARPS * 32)
 k_ls_decide(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode, int cur_q,
-            int q_offset) {
+            int q_offset, int sum_terms) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w = blockIdx.x * KDEC_WARPS + warp;
   int b;
@@ -726,19 +710,55 @@ k_ls_decide(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScra
     acc_jj = 0;  // ModifyLQStrategies returns after the first rollout (:322)
     acc_j = j0;
   } else {
-    int jj = 0;
-    for (; jj < W && j0 + jj < max_bt; jj++) {
-      const float merit = ls.merit[base + jj];
-      if (ls_armijo(p, lm, merit, ed, j0 + jj)) {
-        acc_jj = jj;
-        acc_j = j0 + jj;
-        acc_merit = merit;
-        break;
+    // The reference's loop looks at the candidates one after the other; here each lane takes one:
+    // its merit (with sum_terms, the ordered (k, i) sum of the terms k_ls_merit left -- a single
+    // running fp32 accumulator as in src/ilq_solver.cpp:416-430; consecutive candidates sit in
+    // consecutive lanes of the term tiles, so the loads of a round coalesce), its Armijo test, and
+    // a ballot finds the first candidate that passes.
+    const int ncand = max(0, min(W, max_bt - j0));
+    const int cnt = T * 2 * d.N;
+    float last_merit = 0.f;  // merit of candidate ncand - 1 (for the absorbed shortcut)
+    for (int r0 = 0; r0 < ncand && acc_jj < 0; r0 += 32) {
+      const int c = r0 + lane;
+      float merit = 0.f;
+      if (sum_terms && ncand == 1) {
+        // a lone candidate (the first window): the lanes fetch its terms together, 32 per round,
+        // and the ordered sum runs over shuffled values instead of dependent loads
+        const size_t item = base;
+        const float* terms = ls.terms + (item / ls.lpw) * (size_t)cnt * 32 + item % ls.lpw;
+        float acc = 0.f;
+        for (int e0 = 0; e0 < cnt; e0 += 32) {
+          const float v = e0 + lane < cnt ? terms[(size_t)(e0 + lane) * 32] : 0.f;
+          const int m = min(32, cnt - e0);
+          for (int l = 0; l < m; l++) acc += __shfl_sync(0xffffffffu, v, l);
+        }
+        merit = 0.5 * acc;
+      } else if (c < ncand) {
+        const size_t item = base + c;
+        if (sum_terms) {
+          const float* terms = ls.terms + (item / ls.lpw) * (size_t)cnt * 32 + item % ls.lpw;
+          float acc = 0.f;
+#pragma unroll 8
+          for (int e = 0; e < cnt; e++) acc += terms[(size_t)e * 32];
+          merit = 0.5 * acc;
+        } else {
+          merit = ls.merit[item];
+        }
       }
+      const bool pass = c < ncand && ls_armijo(p, lm, merit, ed, j0 + c);
+      const unsigned hits = __ballot_sync(0xffffffffu, pass);
+      if (hits) {
+        const int first = __ffs(hits) - 1;
+        acc_jj = r0 + first;
+        acc_j = j0 + acc_jj;
+        acc_merit = __shfl_sync(0xffffffffu, merit, first);
+      }
+      if (ncand - 1 >= r0 && ncand - 1 < r0 + 32) last_merit = __shfl_sync(0xffffffffu, merit, ncand - 1 - r0);
     }
+    const int jj = ncand;  // candidates examined when none passed
     if (acc_jj < 0 && jj > 0 && j0 + jj < max_bt && ls.absorbed[base + jj - 1]) {
       // the deeper candidates repeat rollout jj-1 exactly: finish the backtracking loop on its merit
-      const float merit = ls.merit[base + jj - 1];
+      const float merit = last_merit;
       for (int j = j0 + jj; j < max_bt; j++)
         if (ls_armijo(p, lm, merit, ed, j)) {
           acc_jj = jj - 1;
