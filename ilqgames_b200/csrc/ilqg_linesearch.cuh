@@ -652,25 +652,34 @@ k_ls_merit(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScrat
 // behind: ordered over k, first extreme wins.
 __device__ __forceinline__ void ls_total_costs(const DevDesc& d, const Slab& s, int b, const float* vals_block,
                                                int item_lane, int lane) {
+  // All lanes of the (converged) warp fetch 32 time steps of a player's values at once; the ordered
+  // scan (single fp32 accumulator / strict first-extreme compare, as the reference) then runs over
+  // shuffled registers instead of a chain of dependent global loads.
   const int N = d.N;
-  if (lane < N) {
-    const int i = lane, cs = d.cost_structure[i];
+  for (int i = 0; i < N; i++) {
+    const int cs = d.cost_structure[i];
     float total = cs == ILQG_COST_SUM ? 0.f : cs == ILQG_COST_MAX ? -INFINITY : INFINITY;
     int te = s.te_new[(size_t)b * N + i];
-    for (int kk = 0; kk < d.T; kk++) {
-      const float cur = vals_block[((size_t)kk * N + i) * 32 + item_lane];
-      if (cs == ILQG_COST_SUM)
-        total += cur;
-      else if (cs == ILQG_COST_MAX && cur > total) {
-        total = cur;
-        te = kk;
-      } else if (cs == ILQG_COST_MIN && cur < total) {
-        total = cur;
-        te = kk;
+    for (int k0 = 0; k0 < d.T; k0 += 32) {
+      const float v = k0 + lane < d.T ? vals_block[((size_t)(k0 + lane) * N + i) * 32 + item_lane] : 0.f;
+      const int m = min(32, d.T - k0);
+      for (int l = 0; l < m; l++) {
+        const float cur = __shfl_sync(0xffffffffu, v, l);
+        if (cs == ILQG_COST_SUM)
+          total += cur;
+        else if (cs == ILQG_COST_MAX && cur > total) {
+          total = cur;
+          te = k0 + l;
+        } else if (cs == ILQG_COST_MIN && cur < total) {
+          total = cur;
+          te = k0 + l;
+        }
       }
     }
-    s.total_costs[(size_t)b * N + i] = total;
-    s.te_new[(size_t)b * N + i] = te;
+    if (lane == 0) {
+      s.total_costs[(size_t)b * N + i] = total;
+      s.te_new[(size_t)b * N + i] = te;
+    }
   }
 }
 
@@ -737,9 +746,17 @@ k_ls_decide(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScra
         const size_t item = base + c;
         if (sum_terms) {
           const float* terms = ls.terms + (item / ls.lpw) * (size_t)cnt * 32 + item % ls.lpw;
+          // 24 loads in flight per trip: the adds are a dependent chain, the loads are not
           float acc = 0.f;
-#pragma unroll 8
-          for (int e = 0; e < cnt; e++) acc += terms[(size_t)e * 32];
+          int e = 0;
+          for (; e + 24 <= cnt; e += 24) {
+            float v[24];
+#pragma unroll
+            for (int u = 0; u < 24; u++) v[u] = terms[(size_t)(e + u) * 32];
+#pragma unroll
+            for (int u = 0; u < 24; u++) acc += v[u];
+          }
+          for (; e < cnt; e++) acc += terms[(size_t)e * 32];
           merit = 0.5 * acc;
         } else {
           merit = ls.merit[item];
