@@ -38,7 +38,6 @@ struct SubSolver {
   cudaEvent_t ev_fresh, ev_side;
   bool side_busy = false;
   int sm_count = 148;
-  int ls_split = 1;  // linesearch windows as rollout + merit kernels (ILQG_LS_SPLIT=0: the fused k_ls_eval)
   // SolverParams::open_loop: LQOpenLoopSolver instead of LQFeedbackSolver (ilq_solver.h:76-81)
   bool open_loop = false;
   float* ol_scratch = nullptr;  // [B][T][OlLayout::srec], ilqg_open_loop.cuh
@@ -486,9 +485,6 @@ int LaunchLqRecords(SubSolver* h, int only_running, Sel sel = Sel{SEL_ALL, nullp
   return ILQG_OK;
 }
 
-// linesearch windows as rollout + merit kernels (k_ls_decide then sums the merit terms itself)?
-int LsSplit(const SubSolver* h) { return h->ls_split && h->d.num_subsystems <= 4 ? 1 : 0; }
-
 // rollout + merit of one linesearch window as two kernels (ilqg_linesearch.cuh, "Split evaluation")
 int LaunchLsSplit(SubSolver* h, int mode, int blocks, int q_offset) {
   const DevDesc& d = h->d;
@@ -518,27 +514,10 @@ int LaunchLsSplit(SubSolver* h, int mode, int blocks, int q_offset) {
 }
 
 int LaunchLsEval(SubSolver* h, int mode, int blocks, int q_offset) {
-  const DevDesc& d = h->d;
-  const size_t smem = sizeof(float) * (size_t)ls_smem_floats(d.n, d.M, d.N, d.num_subsystems);
   if (blocks <= 0) return ILQG_OK;
   if (blocks > h->ls_blocks_max) return ILQG_ERR_INVALID_ARGUMENT;
   ProfScope prof(h, mode == LS_MODE_FRESH ? 4 : mode == LS_MODE_QUEUED ? 5 : 7);
-  if (LsSplit(h)) return LaunchLsSplit(h, mode, blocks, q_offset);
-  const int nw = d.num_subsystems + d.N;
-  int rc = ILQG_ERR_UNSUPPORTED;
-#define LS_CASE(NW)                                                                              \
-  case NW:                                                                                       \
-    if ((rc = SetSmem(k_ls_eval<NW>, smem)) != ILQG_OK) return rc;                                \
-    k_ls_eval<NW><<<blocks, NW * 32, smem, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset); \
-    break;
-  switch (nw) {
-    LS_CASE(2) LS_CASE(3) LS_CASE(4) LS_CASE(5) LS_CASE(6) LS_CASE(7) LS_CASE(8)
-    default: return ILQG_ERR_UNSUPPORTED;
-  }
-#undef LS_CASE
-  h->launches++;
-  CUDA_TRY(cudaGetLastError());
-  return ILQG_OK;
+  return LaunchLsSplit(h, mode, blocks, q_offset);
 }
 
 // ILQSolver::ModifyLQStrategies for the whole batch (ilqg_linesearch.cuh): the first window for
@@ -552,8 +531,7 @@ int LaunchLinesearchFresh(SubSolver* h) {
   if ((rc = LaunchLsEval(h, LS_MODE_FRESH, h->ls.nA_blocks, 0)) != ILQG_OK) return rc;
   {
     ProfScope pd(h, 6);
-    k_ls_decide<<<dec_blocks, KDEC_WARPS * 32, 0, h->stream>>>(h->d, h->p, h->s, h->ls, LS_MODE_FRESH, h->ls_cur, 0,
-                                                               LsSplit(h));
+    k_ls_decide<<<dec_blocks, KDEC_WARPS * 32, 0, h->stream>>>(h->d, h->p, h->s, h->ls, LS_MODE_FRESH, h->ls_cur, 0);
   }
   h->launches++;
   h->ls_cur = 1 - h->ls_cur;  // the queue just filled is now the one to drain
@@ -578,7 +556,7 @@ int LaunchLinesearchQueued(SubSolver* h) {
         {
           ProfScope pd(h, 6);
           k_ls_decide<<<(cap + KDEC_WARPS - 1) / KDEC_WARPS, KDEC_WARPS * 32, 0, h->stream>>>(
-              h->d, h->p, h->s, h->ls, LS_MODE_QUEUED, h->ls_cur, q0, LsSplit(h));
+              h->d, h->p, h->s, h->ls, LS_MODE_QUEUED, h->ls_cur, q0);
         }
         h->launches++;
       }
@@ -929,7 +907,6 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
     ls.cap = cap;
     int lpw = 32;
     if (const char* e = std::getenv("ILQG_LS_LPW")) lpw = std::atoi(e);
-    if (const char* e = std::getenv("ILQG_LS_SPLIT")) h->ls_split = std::atoi(e);
     if (lpw != 8 && lpw != 16 && lpw != 32 && lpw != 4) lpw = 32;
     ls.lpw = lpw;
     ls.nA_blocks = (int)((B * JA + lpw - 1) / lpw);
@@ -943,7 +920,6 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
     ALLOCNZ(ls.traj_us, blocks_max * lpw * T * M);
     ALLOCNZ(ls.terms, blocks_max * T * 2 * N * 32);
     ALLOCNZ(ls.vals, blocks_max * T * N * 32);
-    ALLOCNZ(ls.merit, blocks_max * lpw);
     ALLOCNZ(ls.absorbed, blocks_max * lpw);
 #undef ALLOCNZ
     ALLOC(ls.pend[0], B);

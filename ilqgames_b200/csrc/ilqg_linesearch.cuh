@@ -1,6 +1,6 @@
 // ilqg_linesearch.cuh -- K_ls: ILQSolver::ModifyLQStrategies (src/ilq_solver.cpp:289-348) as a
-// speculative, asynchronous, role-specialised pipeline, plus the Solve() prologue built from the
-// same kernel.
+// speculative, asynchronous pipeline of small kernels, plus the Solve() prologue built from the
+// same kernels.
 //
 // The reference backtracks sequentially: roll out with alpha * s0 * rho^j, evaluate the merit,
 // test Armijo, repeat.  Candidate j's trajectory and merit depend only on j, never on the
@@ -8,20 +8,16 @@
 // one that passes Armijo gives exactly the sequential result.  On the benchmark workload 97.8 %
 // of all linesearches accept j = 0 and most of the rest backtrack >= 8 times (measured with the
 // oracle), hence two windows per linesearch:
-//   k_ls_eval / k_ls_decide   window [0, JA) for every running instance (JA = 1 by default);
-//                             instances that reject it are queued (per-instance Armijo state
-//                             machine: ls_next_j)
-//   k_ls_eval / k_ls_decide   window [JA, max_backtracking_steps) for the queued instances, all
-//                             candidates at once, in chunks of `cap` queue slots so the candidate
-//                             trajectories fit the scratch; first passing candidate is accepted,
-//                             none -> LINESEARCH_FAILED
-// Chunk launches whose queue range is empty exit immediately; the host never synchronises.
+//   window [0, JA) for every running instance (JA = 1 by default); instances that reject it are
+//                  queued (per-instance Armijo state machine: ls_next_j)
+//   window [JA, max_backtracking_steps) for the queued instances, all candidates at once, in chunks
+//                  of `cap` queue slots so the candidate trajectories fit the scratch; first passing
+//                  candidate is accepted, none -> LINESEARCH_FAILED
+// Launches whose queue range is empty exit immediately; the host never synchronises.
 //
-// k_ls_eval maps one (instance, candidate) ITEM to one lane, and one ROLE to each warp of the
-// block: warps [0, S) integrate subsystem s (u = u_ref - P dx - alpha, then RK4 x 2 substeps),
-// warps [S, S + N) evaluate player i's cost gradients and values one timestep behind, reading
-// the state/control double buffer in shared memory.  Every warp executes uniform code (same
-// subsystem kind / same player's records), so there is no role divergence inside a warp.
+// A window is k_ls_rollout (one (instance, candidate) ITEM per lane, one subsystem per warp:
+// u = u_ref - P dx - alpha, then RK4 x 2 substeps), k_ls_merit (one player per warp: the cost
+// gradients and values of the stored trajectory, all time steps in parallel) and k_ls_decide.
 #pragma once
 #include "ilqg_backward.cuh"
 
@@ -34,13 +30,12 @@ struct LsScratch {
   float* traj_us;   // [items][T][M]
   float* terms;     // [blocks][T][2N][32]  merit terms, item = lane of its block
   float* vals;      // [blocks][T][N][32]   per-player cost values
-  float* merit;     // [items]
-  int* absorbed;    // [items] 1 = every alpha term of this candidate vanished in rounding (see k_ls_eval)
+  int* absorbed;    // [items] 1 = every alpha term of this candidate vanished in rounding (see k_ls_rollout)
   int* pend[2];     // double-buffered queue of instances with an open linesearch
   int* counts;      // [2] queue lengths
   int* slot;        // [B] position of an instance in the queue it is in
   int JA, JB;       // window sizes: fresh linesearch / continued linesearch
-  int nA_blocks;    // blocks of a k_ls_eval launch that serve fresh instances
+  int nA_blocks;    // item blocks of a first-window launch
   int lpw;          // items per block (active lanes per warp): 32, 16 or 8.  The rollout is a
                     // latency chain, so fewer items per warp = more warps per SM to hide it
   int cap;          // queue slots one continued-window launch can hold trajectories for
@@ -92,254 +87,6 @@ struct GatedSink {
   }
 };
 
-__device__ __forceinline__ void named_barrier_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-
-// Shared memory per block (floats), lane-minor so every access is conflict-free:
-//   xu[2][n + M][32]   state/control double buffer (dynamics -> cost warps)
-//   dx[n][32]          x - x_ref of the current step (between dynamics warps)
-//   acc[N][n + M][32]  per-player gradient accumulators (l_i over the state, r_ij over controls)
-//   pbuf[S][2][32][2n+4]  prefetched feedback rows (dynamics warps)
-__host__ __device__ inline int ls_smem_floats(int n, int M, int N, int S) {
-  return (2 * (n + M) + n + N * (n + M)) * 32 + S * 2 * 32 * (2 * n + 4);
-}
-
-// NW = S + N warps per block; the register cap targets >= 24 resident warps per SM
-template <int NW>
-__global__ void __launch_bounds__(NW * 32, 2)
-k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode, int cur_q,
-          int q_offset) {
-  extern __shared__ __align__(16) float smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = d.n, M = d.M, N = d.N, T = d.T, S = d.num_subsystems;
-  const int item = blockIdx.x * ls.lpw + lane;
-  const LsItem it = ls_decode(p, s, ls, mode, cur_q, q_offset, blockIdx.x, lane);
-  if (!__syncthreads_or(it.valid)) return;
-  const bool valid = it.valid;
-  const int b = it.b;
-
-  float* xu = smem;                      // [2][n+M][32]
-  float* dxs = xu + 2 * (n + M) * 32;    // [n][32]
-  float* accs = dxs + n * 32;            // [N][n+M][32]
-  float* pbase = accs + N * (n + M) * 32;  // [S][2][32][2n+4]  prefetched feedback rows
-
-  // ---- per-item sources / destinations ----
-  const size_t ox = (size_t)b * T * n, ou = (size_t)b * T * M, oP = (size_t)b * T * M * n;
-  const float *last_xs, *last_us, *P, *alpha, *x_start;
-  float *out_xs = nullptr, *out_us = nullptr;
-  bool scaled = true;
-  if (mode == LS_MODE_BEGIN) {
-    last_xs = s.prob_xs + ox;
-    last_us = s.prob_us + ou;
-    P = s.prob_P + oP;
-    alpha = s.prob_a + ou;
-    x_start = s.x0 + (size_t)b * n;
-    scaled = false;
-    out_xs = s.op_xs[0] + ox;
-    out_us = s.op_us[0] + ou;
-  } else {
-    const int cur = valid ? s.op_cur[b] : 0, scur = valid ? s.st_cur[b] : 0;
-    last_xs = s.op_xs[cur] + ox;
-    last_us = s.op_us[cur] + ou;
-    P = s.st_P[1 - scur] + oP;
-    alpha = s.st_a[1 - scur] + ou;
-    x_start = last_xs;
-    if (mode == LS_MODE_FRESH && ls.JA == 1) {
-      // the lone first-window candidate is accepted 98 % of the time: roll it straight into the
-      // candidate operating-point buffer (k_ls_decide then has nothing to copy)
-      out_xs = s.op_xs[1 - cur] + ox;
-      out_us = s.op_us[1 - cur] + ou;
-    } else {
-      out_xs = ls.traj_xs + (size_t)item * T * n;
-      out_us = ls.traj_us + (size_t)item * T * M;
-    }
-  }
-  const float s0 = p.initial_alpha_scaling, rho = p.geometric_alpha_scaling;
-  const float dt_half = (float)(d.time_step / 2.0);
-  // ScaleAlphas multiplies alpha by rho once per backtrack (src/ilq_solver.cpp:66-72, 331).  When
-  // rho is a power of two every one of those products is exact, so rho^j can be formed once.
-  int rho_e;
-  const bool rho_exact = fabsf(frexpf(rho, &rho_e)) == 0.5f;
-  float rho_j = 1.0f;
-  for (int jj = 0; jj < it.j; jj++) rho_j *= rho;
-  float* terms = ls.terms + (size_t)blockIdx.x * T * 2 * N * 32;
-  float* vals = ls.vals + (size_t)blockIdx.x * T * N * 32;
-
-  if (warp < S) {
-    // =================== dynamics role: subsystem `warp` ===================
-    const DevSubsystem& sub = d.sub[warp];
-    const int xd = subsystem_xdim(sub.kind);
-    const int nu = sub.kind == ILQG_DYN_AIR3D ? 2 : d.udim[sub.first_player];  // own control rows
-    float x[6];
-#pragma unroll
-    for (int a = 0; a < 6; a++) x[a] = (valid && a < xd) ? x_start[sub.x_offset + a] : 0.f;
-    // Software pipeline: the feedback rows P[k][own rows][:] of the NEXT step are copied
-    // asynchronously (cp.async, 16 B granules) into a per-lane double buffer while this step
-    // integrates; the small reference values ride in registers.  Lane stride PST = 2n + 4
-    // floats keeps the 128-bit reads of 8 consecutive lanes on distinct banks.
-    const bool vecP = (n & 3) == 0 && nu <= 2;
-    const int PST = 2 * n + 4;
-    float* pbuf = pbase + (size_t)warp * 2 * 32 * PST;
-    float nref[6], nuref[2] = {0.f, 0.f}, nal[2] = {0.f, 0.f};
-    bool absorbed = true;
-    auto prefetch = [&](int k) {
-      if (!valid) return;
-#pragma unroll
-      for (int a = 0; a < 6; a++)
-        if (a < xd)
-          nref[a] = k > 0 ? last_xs[(size_t)k * n + sub.x_offset + a] : x_start[sub.x_offset + a];
-#pragma unroll
-      for (int q = 0; q < 2; q++) {
-        if (q >= nu) break;
-        const int c = q == 0 ? sub.u_offset : sub.u_offset2;
-        nuref[q] = last_us[(size_t)k * M + c];
-        nal[q] = alpha[(size_t)k * M + c];
-        if (vecP) {
-          const float* src = P + ((size_t)k * M + c) * n;
-          float* dst = pbuf + ((size_t)(k & 1) * 32 + lane) * PST + q * n;
-          for (int a4 = 0; a4 < n / 4; a4++) {
-            const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst + 4 * a4);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src + 4 * a4) : "memory");
-          }
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-#pragma unroll
-    for (int a = 0; a < 6; a++) nref[a] = 0.f;
-    prefetch(0);
-    for (int k = 0; k <= T; k++) {
-      if (k < T) {
-        float* slot = xu + (k & 1) * (n + M) * 32;
-        float ref[6], uref[2], al[2];
-#pragma unroll
-        for (int a = 0; a < 6; a++) ref[a] = nref[a];
-        uref[0] = nuref[0]; uref[1] = nuref[1];
-        al[0] = nal[0]; al[1] = nal[1];
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (k + 1 < T) prefetch(k + 1);
-#pragma unroll
-        for (int a = 0; a < 6; a++)
-          if (a < xd) {
-            // last_operating_point.xs[0] is the start state (src/ilq_solver.cpp:88-89)
-            dxs[(sub.x_offset + a) * 32 + lane] = x[a] - ref[a];
-            slot[(sub.x_offset + a) * 32 + lane] = x[a];
-            if (valid && out_xs) out_xs[(size_t)k * n + sub.x_offset + a] = x[a];
-          }
-        named_barrier_sync(1, S * 32);
-        float uu[2] = {0.f, 0.f};
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-          if (q >= nu) break;
-          const int c = q == 0 ? sub.u_offset : sub.u_offset2;
-          float uv = 0.f;
-          if (valid) {
-            float acc = 0.f;
-            if (vecP) {
-              const float4* Prow =
-                  reinterpret_cast<const float4*>(pbuf + ((size_t)(k & 1) * 32 + lane) * PST + q * n);
-              for (int a4 = 0; a4 < n / 4; a4++) {
-                const float4 pv = Prow[a4];
-                acc = fmaf(pv.x, dxs[(4 * a4 + 0) * 32 + lane], acc);
-                acc = fmaf(pv.y, dxs[(4 * a4 + 1) * 32 + lane], acc);
-                acc = fmaf(pv.z, dxs[(4 * a4 + 2) * 32 + lane], acc);
-                acc = fmaf(pv.w, dxs[(4 * a4 + 3) * 32 + lane], acc);
-              }
-            } else {
-              const float* Pr = P + ((size_t)k * M + c) * n;
-              for (int a = 0; a < n; a++) acc = fmaf(__ldg(Pr + a), dxs[a * 32 + lane], acc);
-            }
-            float alv = al[q];
-            if (scaled) {
-              alv *= s0;  // ScaleAlphas(initial_alpha_scaling), then geometric_alpha_scaling^j
-              if (rho_exact) {
-                alv *= rho_j;
-              } else {
-                for (int jj = 0; jj < it.j; jj++) alv *= rho;
-              }
-            }
-            const float t = uref[q] - acc;
-            uv = t - alv;  // Strategy::operator(), strategy.h:73-76
-            absorbed = absorbed && (uv == t);
-            if (out_us) out_us[(size_t)k * M + c] = uv;
-          }
-          slot[(n + c) * 32 + lane] = uv;
-          uu[q] = uv;
-        }
-        if (k < T - 1) subsystem_integrate(sub, dt_half, x, uu[0], uu[1]);
-      }
-      __syncthreads();
-    }
-    dxs[warp * 32 + lane] = absorbed ? 1.f : 0.f;  // dxs is free after the last step (S <= n)
-  } else if (warp < S + N) {
-    // =================== cost role: player `warp - S`, one step behind ===================
-    const int i = warp - S;
-    float* acc = accs + (size_t)i * (n + M) * 32;
-    const float mu = valid ? s.mu[b] : 0.f;
-    const int te = valid ? s.te_quad[(size_t)b * N + i] : 0;
-    const bool additive = d.cost_structure[i] == ILQG_COST_SUM;
-    const int pii = d.pair_of[i][i], mi = d.udim[i];
-    for (int k = 0; k <= T; k++) {
-      if (k >= 1) {
-        const int kk = k - 1;
-        const float* slot = xu + (kk & 1) * (n + M) * 32;
-        for (int a = 0; a < n + M; a++) acc[a * 32 + lane] = 0.f;
-        const bool full = additive || te == kk;
-        float value = 0.f;
-        for (int c = d.cost_begin[i]; c < d.cost_begin[i + 1]; c++) {
-          const DevCost& cd = d.cost[c];
-          const bool is_con = cd.slot >= 0;
-          // PlayerCost::Quadraticize vs QuadraticizeControlCosts (src/ilq_solver.cpp:483-487): off the
-          // extreme timestep of a MAX/MIN player only control COSTS enter the gradient; the cost
-          // VALUE (PlayerCost::Evaluate) always counts every state and control cost.
-          const bool in_quad = full || (cd.arg >= 0 && !is_con);
-          if (!in_quad && is_con) continue;
-          const float lambda =
-              (is_con && valid) ? s.lambdas[((size_t)b * d.num_constraints + cd.slot) * T + s.lambda_index[kk]] : 0.f;
-          GatedSink sink{acc + (cd.arg < 0 ? 0 : (n + d.uoff[cd.arg]) * 32) + lane, in_quad};
-          const float* in = cd.arg < 0 ? slot + lane : slot + (n + d.uoff[cd.arg]) * 32 + lane;
-          float v = 0.f;
-          quadraticize_record_sink<false, 32, true>(d, cd, in, cd.arg < 0 ? n : d.udim[cd.arg], lambda, mu, sink, &v);
-          if (!is_con) value += v;  // PlayerCost::Evaluate: costs only
-        }
-        // ILQSolver::MeritFunction terms (src/ilq_solver.cpp:416-430)
-        float sq = 0.f;
-        for (int a = 0; a < mi; a++) {
-          const float rv = acc[(n + d.uoff[i] + a) * 32 + lane];
-          sq = fmaf(rv, rv, sq);
-        }
-        float sq2 = 0.f;
-        if (kk > 0)
-          for (int a = 0; a < n; a++) {
-            const float lv = acc[a * 32 + lane];
-            sq2 = fmaf(lv, lv, sq2);
-          }
-        (void)pii;
-        terms[((size_t)kk * 2 * N + 2 * i) * 32 + lane] = sq;
-        terms[((size_t)kk * 2 * N + 2 * i + 1) * 32 + lane] = sq2;
-        vals[((size_t)kk * N + i) * 32 + lane] = value;
-      }
-      __syncthreads();
-    }
-  } else {
-    for (int k = 0; k <= T; k++) __syncthreads();
-  }
-  __syncthreads();
-  // single running fp32 accumulator in (k, i) order, as the reference
-  if (warp == S && valid) {
-    float merit = 0.f;
-    const int cnt = T * 2 * N;
-    for (int e = 0; e < cnt; e++) merit += terms[(size_t)e * 32 + lane];
-    ls.merit[item] = 0.5 * merit;
-    // If u_k = (u_ref - P dx) - alpha_k s0 rho^j rounded to (u_ref - P dx) at every step, every
-    // deeper candidate (smaller alpha) reproduces this rollout bit for bit: k_ls_decide can run
-    // the rest of the Armijo loop on this merit without another rollout.
-    bool absorbed = true;
-    for (int w2 = 0; w2 < S; w2++) absorbed = absorbed && dxs[w2 * 32 + lane] != 0.f;
-    ls.absorbed[item] = absorbed ? 1 : 0;
-  }
-}
 
 // ===========================================================================
 // Split evaluation: rollout and merit as two kernels.
@@ -347,10 +94,9 @@ k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratc
 // Only the rollout is inherently sequential in k.  The merit terms (per-step gradients of the
 // players' costs) depend on (x_k, u_k) alone, so once a candidate trajectory is in global memory
 // -- where it has to go anyway to be promoted -- they can be evaluated for all time steps at
-// once.  In the fused k_ls_eval above the cost warps sit on the rollout's latency chain and pace
-// it (ncu source view: both roles wait for each other at the per-step barrier, and removing a
-// quarter of the dynamics warps' instructions did not move the kernel,
-// profiles/r01_schedule_experiments.md).  Split:
+// once.  (Until session 2 of round 1 one fused kernel did both, with cost warps one step behind
+// the dynamics warps; the cost warps sat on the rollout's latency chain and paced it: ncu source
+// view, profiles/r01_schedule_experiments.md.)  Split:
 //   k_ls_rollout    S warps per block (one per subsystem), 32 items per block: the dynamics role
 //                   alone, one named barrier per step, ~30 KB shared memory and ~100 threads per
 //                   block, so a whole queued window is resident at once;
@@ -358,7 +104,7 @@ k_ls_eval(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratc
 //                   the cost role over a chunk of the stored trajectory, all chunks in parallel;
 //   (k_ls_decide then adds up each candidate's terms in the reference's (k, i) order, one lane
 //   per candidate.)
-// Same arithmetic on the same fp32 values in the same order as the fused kernel: merits, cost
+// Same arithmetic on the same fp32 values in the same order as the fused kernel had: merits, cost
 // values and therefore every Armijo decision are bit-identical to it.
 // ===========================================================================
 struct LsIo {
@@ -695,7 +441,7 @@ constexpr int KDEC_WARPS = 4;
 
 __global__ void __launch_bounds__(KDEC_WARPS * 32)
 k_ls_decide(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode, int cur_q,
-            int q_offset, int sum_terms) {
+            int q_offset) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w = blockIdx.x * KDEC_WARPS + warp;
   int b;
@@ -720,7 +466,7 @@ k_ls_decide(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScra
     acc_j = j0;
   } else {
     // The reference's loop looks at the candidates one after the other; here each lane takes one:
-    // its merit (with sum_terms, the ordered (k, i) sum of the terms k_ls_merit left -- a single
+    // its merit (the ordered (k, i) sum of the terms k_ls_merit left -- a single
     // running fp32 accumulator as in src/ilq_solver.cpp:416-430; consecutive candidates sit in
     // consecutive lanes of the term tiles, so the loads of a round coalesce), its Armijo test, and
     // a ballot finds the first candidate that passes.
@@ -730,7 +476,7 @@ k_ls_decide(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScra
     for (int r0 = 0; r0 < ncand && acc_jj < 0; r0 += 32) {
       const int c = r0 + lane;
       float merit = 0.f;
-      if (sum_terms && ncand == 1) {
+      if (ncand == 1) {
         // a lone candidate (the first window): the lanes fetch its terms together, 32 per round,
         // and the ordered sum runs over shuffled values instead of dependent loads
         const size_t item = base;
@@ -744,23 +490,19 @@ k_ls_decide(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScra
         merit = 0.5 * acc;
       } else if (c < ncand) {
         const size_t item = base + c;
-        if (sum_terms) {
-          const float* terms = ls.terms + (item / ls.lpw) * (size_t)cnt * 32 + item % ls.lpw;
-          // 24 loads in flight per trip: the adds are a dependent chain, the loads are not
-          float acc = 0.f;
-          int e = 0;
-          for (; e + 24 <= cnt; e += 24) {
-            float v[24];
+        const float* terms = ls.terms + (item / ls.lpw) * (size_t)cnt * 32 + item % ls.lpw;
+        // 24 loads in flight per trip: the adds are a dependent chain, the loads are not
+        float acc = 0.f;
+        int e = 0;
+        for (; e + 24 <= cnt; e += 24) {
+          float v[24];
 #pragma unroll
-            for (int u = 0; u < 24; u++) v[u] = terms[(size_t)(e + u) * 32];
+          for (int u = 0; u < 24; u++) v[u] = terms[(size_t)(e + u) * 32];
 #pragma unroll
-            for (int u = 0; u < 24; u++) acc += v[u];
-          }
-          for (; e < cnt; e++) acc += terms[(size_t)e * 32];
-          merit = 0.5 * acc;
-        } else {
-          merit = ls.merit[item];
+          for (int u = 0; u < 24; u++) acc += v[u];
         }
+        for (; e < cnt; e++) acc += terms[(size_t)e * 32];
+        merit = 0.5 * acc;
       }
       const bool pass = c < ncand && ls_armijo(p, lm, merit, ed, j0 + c);
       const unsigned hits = __ballot_sync(0xffffffffu, pass);
