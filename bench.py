@@ -386,7 +386,7 @@ def run_b200(args):
             kern[name] = {"ms_per_launch": ms / n, "launches_per_step": n / prof_steps, "ms_per_step": ms / prof_steps}
     passes = max(kern.get("lq_backward", {}).get("launches_per_step", ITERS_PER_SOLVE), 1)
     inst_iters_per_launch = done_per_step / passes
-    # k_ls_eval runs once per linesearch window: the first window for every instance, then the
+    # a linesearch window (k_ls_rollout + k_ls_merit) runs once per window: the first window for every instance, then the
     # queued window chunk by chunk (chunks past the end of the queue exit at once) - one entry
     ev = [kern[k] for k in ("ls_eval_fresh", "ls_eval_queued") if k in kern]
     if ev:

@@ -375,8 +375,8 @@ int ilqg_set_stream(ilqg_handle h, void* cuda_stream);
  * the accumulated milliseconds and launch count of one kernel kind
  * (0 = linearize_quadraticize, 1 = lq_backward, 2 = linesearch [all of its launches],
  * 3 = solve_begin [all of its launches]; the launches inside 2 and 3 one by one:
- * 4 = k_ls_eval first window, 5 = k_ls_eval queued window, 6 = k_ls_decide,
- * 7 = k_ls_eval of solve_begin) since the last ilqg_profile(h, 1). */
+ * 4 = rollout + merit kernels of the first linesearch window, 5 = of the queued window,
+ * 6 = k_ls_decide, 7 = rollout + merit of solve_begin) since the last ilqg_profile(h, 1). */
 int ilqg_profile(ilqg_handle h, int enable);
 int ilqg_profile_read(ilqg_handle h, int kernel, double* total_ms, long long* launches);
 
