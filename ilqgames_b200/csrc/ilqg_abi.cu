@@ -1503,7 +1503,11 @@ int ilqg_al_post_solve(ilqg_handle h) { return ForEach(h, [](SubSolver* g, int) 
 int ilqg_overwrite_solution(ilqg_handle h, int only_successful) {
   return ForEach(h, [&](SubSolver* g, int) { return sub::ilqg_overwrite_solution(g, only_successful); });
 }
-int ilqg_reset(ilqg_handle h, int mask) { return ForEach(h, [&](SubSolver* g, int) { return sub::ilqg_reset(g, mask); }); }
+int ilqg_reset(ilqg_handle h, int mask) {
+  const int rc = ForEach(h, [&](SubSolver* g, int) { return sub::ilqg_reset(g, mask); });
+  if (rc == ILQG_OK && (mask & ILQG_RESET_SOLUTION)) h->op_t0 = h->subs[0]->host_desc.initial_time;  // a fresh OperatingPoint's t0
+  return rc;
+}
 
 int ilqg_setup_next_receding_horizon(ilqg_handle h, const float* x0, double t0, double planner_runtime,
                                      double* new_t0) {

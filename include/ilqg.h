@@ -361,7 +361,8 @@ int ilqg_synchronize(ilqg_handle h);
  *   ILQG_RESET_SOLVER       last merit / expected decrease = +inf: a freshly constructed
  *                           ILQSolver (ilq_solver.h:69-74; see SURVEY Q8 for why this matters)
  *   ILQG_RESET_MULTIPLIERS  lambda = 0, mu = 10 (augmented_lagrangian_solver.cpp:196-207)
- *   ILQG_RESET_SOLUTION     zero operating point and strategies (Problem::Initialize) */
+ *   ILQG_RESET_SOLUTION     zero operating point and strategies, t0 back to the descriptor's
+ *                           initial time (Problem::Initialize) */
 enum { ILQG_RESET_SOLVER = 1, ILQG_RESET_MULTIPLIERS = 2, ILQG_RESET_SOLUTION = 4 };
 int ilqg_reset(ilqg_handle h, int mask);
 

@@ -2081,6 +2081,7 @@ int ilqg_reset(ilqg_handle h, int mask) {
         std::fill(v->begin(), v->end(), (real)0);
     }
   }
+  if (mask & ILQG_RESET_SOLUTION) h->op_t0 = h->pr.d.initial_time;  // a fresh OperatingPoint's t0
   return ILQG_OK;
 }
 

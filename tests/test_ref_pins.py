@@ -267,3 +267,18 @@ def test_reference_gtest_suite_passes_on_the_shim_build():
                          capture_output=True, text=True).stdout
     assert "[  PASSED  ] 51 tests." in out, out[-2000:]
     assert "FAILED" not in out
+
+
+def test_reset_solution_rewinds_the_receding_horizon_clock(oracle):
+    """ILQG_RESET_SOLUTION = Problem::Initialize: zero plan and t0 back at the initial time, so the
+    same receding-horizon call is accepted again (t0 must not precede the plan's t0)."""
+    desc, _ = problems.roundabout_merging()
+    h = abi.Handle(oracle, desc, problems.roundabout_params(max_solver_iters=1), 2)
+    x = problems.roundabout_x0_batch(2, 1)
+    h.upload_x0(x)
+    assert h.setup_next_receding_horizon(x, 0.25, 0.1) > 0.25
+    with pytest.raises(abi.IlqgError):          # the plan now starts after t = 0.25
+        h.setup_next_receding_horizon(x, 0.05, 0.0)
+    h.reset(h.RESET_SOLUTION)
+    assert np.all(h.download(abi.WARM_XS) == 0)
+    assert h.setup_next_receding_horizon(x, 0.05, 0.0) > 0.05
