@@ -1,0 +1,37 @@
+"""bench.py's output contract on the CPU arm (`--impl reference`): exactly one JSON line on stdout
+with the keys the driver reads.  The GPU arm prints the same line plus `roofline` (checked on the
+GPU box by the driver's own run)."""
+import json
+import os
+import subprocess
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line():
+    res = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--batch", "32"], capture_output=True, text=True, cwd=REPO, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, res.stdout
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "ilq_instance_iterations_per_second"
+    assert line["unit"] == "instance-iterations/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["steps"] == 1 and line["warmup"] == 0
+    cpu = line["cpu_baseline"]
+    assert cpu["kind"] == "port" and cpu["cores"] >= 1 and cpu["value"] == line["value"] and cpu["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_gpu_arm_refuses_to_run_without_a_device():
+    """No CPU fallback: without CUDA the default arm exits with an error instead of timing the oracle."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    res = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, cwd=REPO, timeout=600)
+    assert res.returncode != 0 and "CUDA" in (res.stderr + res.stdout)
+    assert not [l for l in res.stdout.splitlines() if l.strip().startswith("{")]
