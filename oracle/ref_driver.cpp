@@ -24,6 +24,7 @@
 #include <ilqgames/solver/lq_feedback_solver.h>
 #include <ilqgames/solver/lq_open_loop_solver.h>
 #include <ilqgames/solver/problem.h>
+#include <ilqgames/solver/solution_splicer.h>
 #include <ilqgames/solver/solver_params.h>
 #include <ilqgames/utils/solver_log.h>
 #include <ilqgames/utils/relative_time_tracker.h>
@@ -273,6 +274,66 @@ int ilqg_ref_receding_horizon(int which, const float* x0, const ilqg_ref_params*
   *t0_out = op.t0;
   RelativeTimeTracker::ResetInitialTime(0.0);
   return ok ? 0 : 1;
+}
+
+// SolutionSplicer (src/solution_splicer.cpp:57-131) on synthetic logs: a stored plan of T steps
+// starting at t0 = 0 whose entries encode (tag 1, time step, dimension), spliced with a new
+// horizon starting at new_t0 (tag 2).  Two-player system, n = 3, m = (1, 2).  Outputs the spliced
+// plan: xs [steps][3], us [steps][3], alphas [steps][3], P(0, 0) per player [steps][2], t0.
+namespace {
+struct SpliceDynamics : public MultiPlayerDynamicalSystem {
+  SpliceDynamics() : MultiPlayerDynamicalSystem(3) {}
+  Dimension UDim(PlayerIndex i) const { return i == 0 ? 1 : 2; }
+  PlayerIndex NumPlayers() const { return 2; }
+  VectorXf Evaluate(Time, const VectorXf& x, const std::vector<VectorXf>&) const { return x; }
+  LinearDynamicsApproximation Linearize(Time, const VectorXf&, const std::vector<VectorXf>&) const {
+    return LinearDynamicsApproximation(*this);
+  }
+  float DistanceBetween(const VectorXf& a, const VectorXf& b) const { return (a - b).squaredNorm(); }
+  std::vector<Dimension> PositionDimensions() const { return {0, 1}; }
+};
+
+void FillLog(SolverLog* log, const std::shared_ptr<const MultiPlayerIntegrableSystem>& dyn, Time t0, float tag) {
+  const size_t T = time::kNumTimeSteps;
+  OperatingPoint op(T, t0, dyn);
+  std::vector<Strategy> st;
+  for (PlayerIndex i = 0; i < 2; i++) st.emplace_back(T, dyn->XDim(), dyn->UDim(i));
+  for (size_t k = 0; k < T; k++) {
+    for (int d = 0; d < 3; d++) op.xs[k](d) = tag * 1000.f + (float)k + 0.01f * d;
+    int c = 0;
+    for (PlayerIndex i = 0; i < 2; i++)
+      for (int d = 0; d < dyn->UDim(i); d++, c++) {
+        op.us[k][i](d) = -(tag * 1000.f + (float)k + 0.01f * c);
+        st[i].alphas[k](d) = tag * 100.f + 0.5f * (float)k + 0.01f * c;
+        st[i].Ps[k](d, 0) = tag * 10.f + 0.25f * (float)k + (float)i;
+      }
+  }
+  log->AddSolverIterate(op, st, std::vector<float>(2, 0.f), 0.0, true);
+}
+}  // namespace
+
+int ilqg_ref_splice(double new_t0, int max_steps, float* xs, float* us, float* alphas, float* P00, double* t0_out) {
+  const std::shared_ptr<const MultiPlayerIntegrableSystem> dyn(new SpliceDynamics);
+  SolverLog stored, fresh;
+  FillLog(&stored, dyn, 0.0, 1.f);
+  FillLog(&fresh, dyn, new_t0, 2.f);
+  SolutionSplicer splicer(stored);
+  splicer.Splice(fresh);
+  const OperatingPoint& op = splicer.CurrentOperatingPoint();
+  const int steps = (int)op.xs.size();
+  for (int k = 0; k < steps && k < max_steps; k++) {
+    for (int d = 0; d < 3; d++) xs[k * 3 + d] = op.xs[k](d);
+    int c = 0;
+    for (PlayerIndex i = 0; i < 2; i++) {
+      for (int d = 0; d < dyn->UDim(i); d++, c++) {
+        us[k * 3 + c] = op.us[k][i](d);
+        alphas[k * 3 + c] = splicer.CurrentStrategies()[i].alphas[k](d);
+      }
+      P00[k * 2 + i] = splicer.CurrentStrategies()[i].Ps[k](0, 0);
+    }
+  }
+  *t0_out = op.t0;
+  return steps;
 }
 
 // ILQSolver with max_solver_iters = 1 from x0: returns the linearization and quadraticization

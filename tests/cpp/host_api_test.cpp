@@ -8,6 +8,7 @@
 #include <ilqgames/solver/augmented_lagrangian_solver.h>
 #include <ilqgames/solver/ilq_solver.h>
 #include <ilqgames/solver/lq_feedback_solver.h>
+#include <ilqgames/solver/solution_splicer.h>
 
 #include "../../examples/cpp/intersection_problem.h"
 
@@ -309,6 +310,69 @@ void TestRecedingHorizon() {
   std::printf("Problem::SetUpNextRecedingHorizon: first time step of the new problem = %zu, t0 = %.4f\n", first, op.t0);
 }
 
+// SolutionSplicer (src/solution_splicer.cpp:57-131) on the synthetic logs of
+// oracle/ref_driver.cpp:ilqg_ref_splice (same fill formula), for a new horizon that starts before
+// and after the five-step keep window; tests/test_host_api.py compares the dumps with what the
+// reference's own SolutionSplicer produced (tests/golden/ref_splice.npz).
+class SpliceDynamics : public MultiPlayerDynamicalSystem {
+ public:
+  SpliceDynamics() : MultiPlayerDynamicalSystem(3) {}
+  Dimension UDim(PlayerIndex i) const override { return i == 0 ? 1 : 2; }
+  PlayerIndex NumPlayers() const override { return 2; }
+  std::vector<Dimension> PositionDimensions() const override { return {0, 1}; }
+};
+
+void FillLog(SolverLog* log, const std::shared_ptr<const MultiPlayerIntegrableSystem>& dyn, Time t0, float tag) {
+  const size_t T = time::kNumTimeSteps;
+  OperatingPoint op(T, t0, dyn);
+  std::vector<Strategy> st;
+  for (PlayerIndex i = 0; i < 2; i++) st.emplace_back(T, dyn->XDim(), dyn->UDim(i));
+  for (size_t k = 0; k < T; k++) {
+    for (int d = 0; d < 3; d++) op.xs[k](d) = tag * 1000.f + (float)k + 0.01f * d;
+    int c = 0;
+    for (PlayerIndex i = 0; i < 2; i++)
+      for (int d = 0; d < dyn->UDim(i); d++, c++) {
+        op.us[k][i](d) = -(tag * 1000.f + (float)k + 0.01f * c);
+        st[i].alphas[k](d) = tag * 100.f + 0.5f * (float)k + 0.01f * c;
+        st[i].Ps[k](d, 0) = tag * 10.f + 0.25f * (float)k + (float)i;
+      }
+  }
+  log->AddSolverIterate(op, st, std::vector<float>(2, 0.f), 0.0, true);
+}
+
+void TestSolutionSplicer() {
+  const std::shared_ptr<const MultiPlayerIntegrableSystem> dyn(new SpliceDynamics);
+  int which = 0;
+  for (const Time new_t0 : {0.3, 1.2, 0.0}) {
+    SolverLog stored, fresh;
+    FillLog(&stored, dyn, 0.0, 1.f);
+    FillLog(&fresh, dyn, new_t0, 2.f);
+    SolutionSplicer splicer(stored);
+    EXPECT(splicer.ContainsTime(5.0) && !splicer.ContainsTime(10.5));
+    splicer.Splice(fresh);
+    const OperatingPoint& op = splicer.CurrentOperatingPoint();
+    std::vector<float> xs, us, al, p00;
+    for (size_t k = 0; k < op.xs.size(); k++) {
+      for (int d = 0; d < 3; d++) xs.push_back(op.xs[k](d));
+      for (PlayerIndex i = 0; i < 2; i++) {
+        for (int d = 0; d < dyn->UDim(i); d++) {
+          us.push_back(op.us[k][i](d));
+          al.push_back(splicer.CurrentStrategies()[i].alphas[k](d));
+        }
+        p00.push_back(splicer.CurrentStrategies()[i].Ps[k](0, 0));
+      }
+    }
+    const std::string tag = "splice" + std::to_string(which++) + "_";
+    const float t0f = (float)op.t0;
+    Dump((tag + "t0").c_str(), &t0f, 1);
+    Dump((tag + "xs").c_str(), xs);
+    Dump((tag + "us").c_str(), us);
+    Dump((tag + "alphas").c_str(), al);
+    Dump((tag + "P00").c_str(), p00);
+  }
+  std::printf("SolutionSplicer: spliced 3 synthetic horizons\n");
+}
+
 void TestAugmentedLagrangianSolver(const std::shared_ptr<Problem>& problem) {
   SolverParams params = IntersectionParams();
   params.max_solver_iters = 30;  // NumIterates cap of the outer loop
@@ -347,6 +411,7 @@ int main(int argc, char** argv) {
   TestILQSolver(problem);
   TestAugmentedLagrangianSolver(problem);
   TestRecedingHorizon();
+  TestSolutionSplicer();
   std::fclose(g_out);
   std::printf("host_api_test: all checks passed\n");
   return 0;

@@ -30,6 +30,7 @@ ILQ_ITERS = 6       # ILQSolver::Solve cap for the per-iterate fixtures
 OL_ITERS = 4        # same with SolverParams::open_loop
 RH_ITERS = 2        # ILQ iterations before SetUpNextRecedingHorizon
 # (t0, planner_runtime) pairs; times on the 0.1 s grid CHECK-fail in the reference (problem.cpp:87)
+SPLICE_T0S = [0.3, 1.2, 0.0]   # start times of the spliced-in horizon (tests/cpp/host_api_test.cpp uses the same)
 RH_CASES = [(0.25, 0.1), (0.33, 0.25), (1.02, 0.1), (0.55, 0.0), (2.07, 0.5)]
 AL_INNER, AL_OUTER = 10, 40   # unconstrained_solver_max_iters, AL NumIterates cap
 
@@ -170,6 +171,12 @@ if __name__ == "__main__":
                    stdout=subprocess.DEVNULL)
     ref = R.RefLibrary()
     np.savez_compressed(os.path.join(HERE, "ref_polylines.npz"), **check_polylines(ref))
+    # SolutionSplicer::Splice on synthetic logs (new horizon inside / beyond the keep window / at t0)
+    splice = {}
+    for c, new_t0 in enumerate(SPLICE_T0S):
+        for k, v in ref.splice(new_t0).items():
+            splice[f"splice{c}_{k}"] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, "ref_splice.npz"), **splice)
     for name in CASES:
         out = run_case(ref, name)
         np.savez_compressed(os.path.join(HERE, f"ref_{name}.npz"), **out)

@@ -102,6 +102,15 @@ class RefLibrary:
         assert rc in (0, 1)
         return dict(x0=x0_out, xs=xs, us=us, Ps=Ps, alphas=alphas, t0=t0.value, ok=rc == 0)
 
+    def splice(self, new_t0: float, max_steps: int = 128):
+        """SolutionSplicer::Splice on the synthetic logs of oracle/ref_driver.cpp."""
+        xs, us, al = (np.zeros((max_steps, 3), np.float32) for _ in range(3))
+        p00 = np.zeros((max_steps, 2), np.float32)
+        t0 = C.c_double(0)
+        k = self.lib.ilqg_ref_splice(C.c_double(new_t0), max_steps, _ptr(xs), _ptr(us), _ptr(al), _ptr(p00),
+                                     C.byref(t0))
+        return dict(xs=xs[:k], us=us[:k], alphas=al[:k], P00=p00[:k], t0=t0.value)
+
     def roundabout_lane(self, entrance_angle, exit_angle, distance) -> np.ndarray:
         pts = np.zeros((64, 2), np.float32)
         k = self.lib.ilqg_ref_roundabout_lane(C.c_float(entrance_angle), C.c_float(exit_angle),

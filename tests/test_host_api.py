@@ -125,6 +125,12 @@ def _check_against_ctypes(lib, got, exact=True):
     hr.solve_begin()
     hr.solve(chunk=1)
     assert same(_flat_op(hr.download(abi.XS)[0], hr.download(abi.US)[0]), got["rh_next_op"])
+    # SolutionSplicer::Splice: the host class against the reference's own (tests/golden/ref_splice.npz)
+    g = np.load(os.path.join(REPO, "tests", "golden", "ref_splice.npz"))
+    for c in range(3):
+        assert np.float32(g[f"splice{c}_t0"]) == got[f"splice{c}_t0"][0]
+        for key in ("xs", "us", "alphas", "P00"):
+            assert np.array_equal(g[f"splice{c}_{key}"].reshape(-1), got[f"splice{c}_{key}"]), (c, key)
     # SURVEY Appendix B known answer of the LQ test system
     np.testing.assert_allclose(got["lq_P1_k0"], [0.915024, 1.632025], atol=2e-5)
     np.testing.assert_allclose(got["lq_P2_k0"], [0.0145362, 0.0206234], atol=2e-5)
