@@ -2,7 +2,7 @@
 """Summarise `ncu --set full` reports (gpurun_out/*.ncu-rep) into profiles/<round>_<name>.md and
 profiles/traffic.json (DRAM bytes per launch, keyed by the bench's kernel names).
 
-usage: tools/ncu_summary.py r01 k_lq=gpurun_out/x.ncu-rep k_bwd=... k_ls_eval=...
+usage: tools/ncu_summary.py r01 k_lq=gpurun_out/x.ncu-rep k_bwd=... ls_rollout=... ls_merit=...
 """
 import csv
 import json
