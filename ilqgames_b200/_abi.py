@@ -113,7 +113,7 @@ ABI_SYMBOLS = [
     "ilqg_iterate", "ilqg_al_update", "ilqg_overwrite_solution", "ilqg_al_post_solve",
     "ilqg_download", "ilqg_synchronize", "ilqg_kernel_launches", "ilqg_set_stream",
     "ilqg_profile", "ilqg_profile_read", "ilqg_reset", "ilqg_count_running",
-    "ilqg_al_begin", "ilqg_al_advance", "ilqg_setup_next_receding_horizon",
+    "ilqg_al_begin", "ilqg_al_advance", "ilqg_setup_next_receding_horizon", "ilqg_integrate_plan",
 ]
 
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -162,6 +162,7 @@ class Library:
         L.ilqg_al_advance.argtypes = [vp, ip]
         L.ilqg_setup_next_receding_horizon.argtypes = [vp, vp, C.c_double, C.c_double,
                                                        C.POINTER(C.c_double)]
+        L.ilqg_integrate_plan.argtypes = [vp, vp, C.c_double, C.c_double, vp]
         L.ilqg_profile.argtypes = [vp, C.c_int]
         L.ilqg_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double),
                                         C.POINTER(C.c_longlong)]
@@ -364,6 +365,15 @@ class Handle:
             self._h, a.ctypes.data, float(t0), float(planner_runtime), C.byref(new_t0)),
             "setup_next_receding_horizon")
         return new_t0.value
+
+    def integrate_plan(self, x0, t0: float, t: float) -> np.ndarray:
+        """MultiPlayerIntegrableSystem::Integrate(t0, t, x0, plan) for every game: [B][n] -> [B][n]."""
+        a = _f32(x0)
+        assert a.shape == (self.B, self.n), a.shape
+        out = np.zeros_like(a)
+        self.lib.check(self.lib.lib.ilqg_integrate_plan(self._h, a.ctypes.data, float(t0), float(t),
+                                                        out.ctypes.data), "integrate_plan")
+        return out
 
     def synchronize(self):
         self.lib.check(self.lib.lib.ilqg_synchronize(self._h), "synchronize")

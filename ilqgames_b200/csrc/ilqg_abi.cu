@@ -1124,6 +1124,20 @@ int ilqg_setup_next_receding_horizon(SubHandle h, const float* x_meas, const RhT
   return ILQG_OK;
 }
 
+int ilqg_integrate_plan(SubHandle h, const float* x_in, const IpTimes& times, float* x_out) {
+  ENTER(h);
+  const size_t floats = (size_t)h->B * h->d.n;
+  int rc = EnsureStaging(h, floats);
+  if (rc != ILQG_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(h->staging, x_in, sizeof(float) * floats, cudaMemcpyHostToDevice, h->stream));
+  k_integrate_plan<<<(h->B + KRH_WARPS - 1) / KRH_WARPS, KRH_WARPS * 32, 0, h->stream>>>(h->d, h->s, h->staging, times);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(x_out, h->staging, sizeof(float) * floats, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));  // the host buffers may be pageable / reused
+  return ILQG_OK;
+}
+
 int ilqg_al_post_solve(SubHandle h) {
   ENTER(h);
   k_al_post_solve<<<h->B, 128, 0, h->stream>>>(h->d, h->p, h->s, 0);
@@ -1564,6 +1578,58 @@ int ilqg_setup_next_receding_horizon(ilqg_handle h, const float* x0, double t0, 
   h->op_t0 = op_t0;
   if (new_t0) *new_t0 = op_t0;
   return ILQG_OK;
+}
+
+// The trip count of the RK4 loop of MultiPlayerDynamicalSystem::Integrate
+// (src/multi_player_dynamical_system.cpp:61-65) for one (t0, interval), in double as there.
+static int Rk4Substeps(double t0, double time_interval) {
+  const double dt = time_interval / static_cast<double>(2);
+  int count = 0;
+  for (double t = t0; t < t0 + time_interval - 0.5 * dt && count < 4; t += dt) count++;
+  return count;
+}
+
+int ilqg_integrate_plan(ilqg_handle h, const float* x0, double t0, double t, float* x_out) {
+  if (!h || !x0 || !x_out) return ILQG_ERR_BAD_HANDLE;
+  const ilqg_layout& lo = h->layout;
+  const DevDesc& d = h->subs[0]->d;
+  if (d.num_subsystems <= 0 || d.sub[0].kind == ILQG_DYN_NONE) return ILQG_ERR_UNSUPPORTED;
+  const int T = lo.num_time_steps;
+  const double kTimeStep = d.time_step, plan_t0 = h->op_t0;
+  constexpr float kSmallNumber = 1e-4;  // constants::kSmallNumber, utils/types.h:118
+  // ---- src/multi_player_integrable_system.cpp:54-83: the time bookkeeping, in double ----
+  if (!(t >= t0) || !(t0 >= plan_t0)) return ILQG_ERR_INVALID_ARGUMENT;  // CHECK_GE :57-58
+  const double relative_t0 = t0 - plan_t0;
+  const size_t current_timestep = static_cast<size_t>(relative_t0 / kTimeStep);
+  const double relative_t = t - plan_t0;
+  const size_t final_timestep = static_cast<size_t>(relative_t / kTimeStep);
+  // IntegrateToNextTimeStep :113-143
+  const bool to_next = t0 > plan_t0;
+  const size_t itn_timestep = static_cast<size_t>((relative_t0 + kSmallNumber) / kTimeStep);
+  const double itn_remaining = kTimeStep * (itn_timestep + 1) - relative_t0;
+  if (to_next && (!(itn_remaining < kTimeStep + kSmallNumber) || itn_timestep >= (size_t)T))
+    return ILQG_ERR_INVALID_ARGUMENT;  // CHECK_LT :126-127
+  // IntegrateFromPriorTimeStep :145-171
+  const double remaining_until_t = relative_t - kTimeStep * final_timestep;
+  if (final_timestep >= (size_t)T || !(remaining_until_t < kTimeStep)) return ILQG_ERR_INVALID_ARGUMENT;  // :154-155
+
+  IpTimes times;
+  times.to_next = to_next ? 1 : 0;
+  times.itn_timestep = (int)itn_timestep;
+  times.frac = (float)(itn_remaining / kTimeStep);
+  times.itn_dt_half = (float)(itn_remaining / 2.0);
+  times.itn_substeps = Rk4Substeps(t0, itn_remaining);
+  times.integrate_from = (int)current_timestep + 1;
+  times.integrate_to = (int)final_timestep;
+  times.dt_half = (float)(kTimeStep / 2.0);
+  times.step_substeps = Rk4Substeps(0.0, kTimeStep);
+  times.prior_timestep = (int)final_timestep;
+  times.prior_dt_half = (float)(remaining_until_t / 2.0);
+  times.prior_substeps = Rk4Substeps(plan_t0 + kTimeStep * final_timestep, remaining_until_t);
+  const size_t n = lo.xdim;
+  return ForEach(h, [&](SubSolver* g, int first) {
+    return sub::ilqg_integrate_plan(g, x0 + (size_t)first * n, times, x_out + (size_t)first * n);
+  });
 }
 
 int ilqg_iterate(ilqg_handle h, int max_iters, int* iters_done) {

@@ -133,4 +133,82 @@ k_receding_horizon(const __grid_constant__ DevDesc d, Slab s, const float* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// MultiPlayerIntegrableSystem::Integrate(Time t0, Time t, x0, operating_point, strategies)
+// (src/multi_player_integrable_system.cpp:54-83): carry a measured state along the stored plan --
+// what src/receding_horizon_simulator.cpp:100-102,126-128 runs between solves.  The plan is read
+// only.  As above, the double time arithmetic is done once on the host (IpTimes); one warp per game.
+struct IpTimes {
+  int to_next;                       // t0 is past the plan's start: IntegrateToNextTimeStep first (:75-76)
+  int itn_timestep;                  // its time step, interpolation weight, RK4 substep and trip count
+  float frac, itn_dt_half;
+  int itn_substeps;
+  int integrate_from, integrate_to;  // whole time steps (:79-80)
+  float dt_half;
+  int step_substeps;
+  int prior_timestep;                // IntegrateFromPriorTimeStep (:145-171)
+  float prior_dt_half;
+  int prior_substeps;
+};
+
+__global__ void __launch_bounds__(KRH_WARPS * 32)
+k_integrate_plan(const __grid_constant__ DevDesc d, Slab s, float* __restrict__ x_io, IpTimes r) {
+  __shared__ float sx[KRH_WARPS][ILQG_MAX_XDIM], sref[KRH_WARPS][ILQG_MAX_XDIM], su[KRH_WARPS][ILQG_MAX_UDIM];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * KRH_WARPS + warp;
+  if (b >= s.B) return;
+  const int T = d.T, n = d.n, M = d.M;
+  float* x = sx[warp];
+  float* ref = sref[warp];
+  float* u = su[warp];
+  const float* pxs = s.prob_xs + (size_t)b * T * n;
+  const float* pus = s.prob_us + (size_t)b * T * M;
+  const float* pP = s.prob_P + (size_t)b * T * M * n;
+  const float* pa = s.prob_a + (size_t)b * T * M;
+
+  // Strategy::operator() (strategy.h:73-76) at time step kk, then one Integrate over 2 * dt_half
+  auto advance = [&](int kk, float dt_half, int substeps) {
+    for (int c = lane; c < M; c += 32) {
+      float acc = 0.f;
+      for (int a = 0; a < n; a++) acc += pP[((size_t)kk * M + c) * n + a] * (x[a] - ref[a]);
+      u[c] = (pus[(size_t)kk * M + c] - acc) - pa[(size_t)kk * M + c];
+    }
+    __syncwarp();
+    if (lane < d.num_subsystems) {
+      const DevSubsystem& sub = d.sub[lane];
+      const int xd = subsystem_xdim(sub.kind);
+      float xl[6];
+#pragma unroll
+      for (int a = 0; a < 6; a++) xl[a] = a < xd ? x[sub.x_offset + a] : 0.f;
+      subsystem_integrate(sub, dt_half, xl, u[sub.u_offset], u[sub.u_offset2], substeps);
+#pragma unroll
+      for (int a = 0; a < 6; a++)
+        if (a < xd) x[sub.x_offset + a] = xl[a];
+    }
+    __syncwarp();
+  };
+  auto reference_row = [&](int kk) {
+    for (int a = lane; a < n; a += 32) ref[a] = pxs[(size_t)kk * n + a];
+    __syncwarp();
+  };
+
+  for (int a = lane; a < n; a += 32) x[a] = x_io[(size_t)b * n + a];
+  __syncwarp();
+  if (r.to_next) {  // :113-143, against the interpolated reference state
+    for (int a = lane; a < n; a += 32)
+      ref[a] = r.itn_timestep + 1 < T
+                   ? r.frac * pxs[(size_t)r.itn_timestep * n + a] + (float)(1.0 - r.frac) * pxs[(size_t)(r.itn_timestep + 1) * n + a]
+                   : pxs[(size_t)(T - 1) * n + a];
+    __syncwarp();
+    advance(r.itn_timestep, r.itn_dt_half, r.itn_substeps);
+  }
+  for (int kk = r.integrate_from; kk < r.integrate_to; kk++) {  // :85-111
+    reference_row(kk);
+    advance(kk, r.dt_half, r.step_substeps);
+  }
+  reference_row(r.prior_timestep);
+  advance(r.prior_timestep, r.prior_dt_half, r.prior_substeps);
+  for (int a = lane; a < n; a += 32) x_io[(size_t)b * n + a] = x[a];
+}
+
 }  // namespace ilqg

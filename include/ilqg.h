@@ -331,6 +331,17 @@ int ilqg_overwrite_solution(ilqg_handle h, int only_successful);
 int ilqg_setup_next_receding_horizon(ilqg_handle h, const float* x0, double t0,
                                      double planner_runtime, double* new_t0);
 
+/* MultiPlayerIntegrableSystem::Integrate(Time t0, Time t, x0, operating_point, strategies)
+ * (src/multi_player_integrable_system.cpp:54-83, with IntegrateToNextTimeStep :113-143, the time
+ * step loop :85-111 and IntegrateFromPriorTimeStep :145-171) for every game: the state x0
+ * [batch][n], taken at time t0, is carried to time t under the game's warm start (operating point
+ * and strategies, u_i = u_ref - P_i (x - x_ref) - alpha_i), which is not modified.  x_out
+ * [batch][n] receives the states; it may alias x0.  This is what a receding-horizon caller runs
+ * between solves (src/receding_horizon_simulator.cpp:100-102,126-128).  Times are shared by the
+ * batch.  ILQG_ERR_INVALID_ARGUMENT where the reference CHECK-fails: t < t0, t0 before the plan's
+ * t0, or t at/after the plan's last time step. */
+int ilqg_integrate_plan(ilqg_handle h, const float* x0, double t0, double t, float* x_out);
+
 /* src/augmented_lagrangian_solver.cpp:165-178: for instances whose inner solve
  * failed, lambda *= geometric_lambda_downscaling, mu *= geometric_mu_downscaling. */
 int ilqg_al_post_solve(ilqg_handle h);

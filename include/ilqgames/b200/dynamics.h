@@ -84,6 +84,12 @@ class MultiPlayerIntegrableSystem {
   // subsystem table of ilqg_problem_desc; false = not describable
   virtual bool Describe(ilqg_problem_desc* /*desc*/) const { return false; }
 
+  // src/multi_player_integrable_system.cpp:54-83: the state x0, taken at time t0, carried to time t
+  // under the given plan (u_i = u_ref - P_i (x - x_ref) - alpha_i).  Runs on the device
+  // (ilqg_integrate_plan); defined in solvers.h below b200::Handle.
+  VectorXf Integrate(Time t0, Time t, const VectorXf& x0, const OperatingPoint& operating_point,
+                     const std::vector<Strategy>& strategies) const;
+
  protected:
   MultiPlayerIntegrableSystem(Dimension xdim) : xdim_(xdim) {}
   const Dimension xdim_;

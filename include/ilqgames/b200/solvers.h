@@ -251,8 +251,14 @@ class Handle {
 
 inline void Problem::SetUpNextRecedingHorizon(const VectorXf& x0, Time t0, Time planner_runtime) {
   CHECK(initialized_);
+  // the stored plan may be longer than the horizon: a receding-horizon caller overwrites it with a
+  // SolutionSplicer's plan first (src/receding_horizon_simulator.cpp:105-109, src/problem.cpp:160-169)
+  const size_t horizon = time::kNumTimeSteps, stored = operating_point_->xs.size();
+  CHECK_GE(stored, horizon);
+  CHECK_LE(planner_runtime + t0, operating_point_->t0 + time::kTimeHorizon);  // :70
   ilqg_problem_desc desc;
   CHECK(b200::DescribeProblem(*this, &desc)) << "a cost, constraint or dynamics class has no device record";
+  desc.num_time_steps = (int32_t)stored;
   b200::Handle h(desc, b200::ToAbi(SolverParams()), 1);
   h.UploadWarmStart(*operating_point_, *strategies_);
   std::vector<float> x((size_t)x0.size());
@@ -264,8 +270,42 @@ inline void Problem::SetUpNextRecedingHorizon(const VectorXf& x0, Time t0, Time 
                                          h.Download<float>(ILQG_WARM_US, T * M), new_t0);
   *strategies_ = h.StrategiesOf(0, h.Download<float>(ILQG_WARM_PS, T * M * n),
                                 h.Download<float>(ILQG_WARM_ALPHAS, T * M));
+  // the new problem is the first `horizon` steps of the re-based plan (:160-169)
+  operating_point_->xs.resize(horizon);
+  operating_point_->us.resize(horizon);
+  for (Strategy& strategy : *strategies_) {
+    strategy.Ps.resize(horizon);
+    strategy.alphas.resize(horizon);
+  }
   const std::vector<float> nx = h.Download<float>(ILQG_X0, n);
   for (size_t a = 0; a < n; a++) x0_((long)a) = nx[a];
+}
+
+inline VectorXf MultiPlayerIntegrableSystem::Integrate(Time t0, Time t, const VectorXf& x0,
+                                                       const OperatingPoint& operating_point,
+                                                       const std::vector<Strategy>& strategies) const {
+  CHECK_GE(t, t0);
+  CHECK_GE(t0, operating_point.t0);
+  CHECK_EQ(strategies.size(), NumPlayers());
+  CHECK_EQ((long)x0.size(), (long)XDim());
+  // a dynamics-only descriptor: the plan's own length and start time, no cost records
+  ilqg_problem_desc desc;
+  std::memset(&desc, 0, sizeof(desc));
+  desc.num_time_steps = (int32_t)operating_point.xs.size();
+  desc.time_step = time::kTimeStep;
+  desc.initial_time = operating_point.t0;
+  desc.num_players = NumPlayers();
+  desc.xdim = XDim();
+  for (PlayerIndex ii = 0; ii < NumPlayers(); ii++) desc.udim[ii] = UDim(ii);
+  CHECK(Describe(&desc)) << "this dynamics class has no device record";
+  b200::Handle h(desc, b200::ToAbi(SolverParams()), 1);
+  h.UploadWarmStart(operating_point, strategies);
+  std::vector<float> x((size_t)x0.size()), out((size_t)x0.size());
+  for (long a = 0; a < x0.size(); a++) x[(size_t)a] = x0(a);
+  ILQG_CALL(ilqg_integrate_plan(h.get(), x.data(), t0, t, out.data()));
+  VectorXf result(x0.size());
+  for (long a = 0; a < x0.size(); a++) result(a) = out[(size_t)a];
+  return result;
 }
 
 

@@ -338,14 +338,17 @@ void EvaluateDynamics(const Problem& pr, const real* x, const real* u, real* xdo
 // MultiPlayerDynamicalSystem::Integrate, src/multi_player_dynamical_system.cpp:52-77.
 // RK4 with 2 substeps; the double `dt` narrows to the vector scalar type when it
 // multiplies a VectorXf (Eigen scalar promotion), as do the 0.5/2.0/6.0 literals.
-void Integrate(const Problem& pr, const real* x0, const real* u, real* xout, double time_interval) {
+// `substeps` is how often the reference's loop `for (t = t0; t < t0 + interval - 0.5 * dt; t += dt)`
+// runs: 2 for any interval that is not vanishingly small next to t0 (Rk4Substeps below).
+void Integrate(const Problem& pr, const real* x0, const real* u, real* xout, double time_interval,
+               int substeps = 2) {
   const int n = pr.n;
   const double dt_d = time_interval / static_cast<double>(2);
   const real dt = (real)dt_d;
   real x[ILQG_MAX_XDIM], k1[ILQG_MAX_XDIM], k2[ILQG_MAX_XDIM], k3[ILQG_MAX_XDIM],
       k4[ILQG_MAX_XDIM], tmp[ILQG_MAX_XDIM];
   for (int a = 0; a < n; a++) x[a] = x0[a];
-  for (int sub = 0; sub < 2; sub++) {
+  for (int sub = 0; sub < substeps; sub++) {
     EvaluateDynamics(pr, x, u, k1);
     for (int a = 0; a < n; a++) { k1[a] = dt * k1[a]; tmp[a] = x[a] + (real)0.5 * k1[a]; }
     EvaluateDynamics(pr, tmp, u, k2);
@@ -363,6 +366,15 @@ void Integrate(const Problem& pr, const real* x0, const real* u, real* xout, dou
 
 void Integrate(const Problem& pr, const real* x0, const real* u, real* xout) {
   Integrate(pr, x0, u, xout, pr.d.time_step);
+}
+
+// The trip count of the RK4 loop of MultiPlayerDynamicalSystem::Integrate
+// (src/multi_player_dynamical_system.cpp:61-65), evaluated in double like the reference does.
+int Rk4Substeps(double t0, double time_interval) {
+  const double dt = time_interval / static_cast<double>(2);
+  int count = 0;
+  for (double t = t0; t < t0 + time_interval - 0.5 * dt && count < 4; t += dt) count++;
+  return count;
 }
 
 // ConcatenatedDynamicalSystem::Linearize, src/concatenated_dynamical_system.cpp:86-107
@@ -1937,6 +1949,65 @@ int ilqg_setup_next_receding_horizon(ilqg_handle h, const float* x0_in, double t
   }
   h->op_t0 = op_t0;
   if (new_t0) *new_t0 = op_t0;
+  return ILQG_OK;
+}
+
+// MultiPlayerIntegrableSystem::Integrate(t0, t, x0, operating_point, strategies),
+// src/multi_player_integrable_system.cpp:54-83, for every game under its warm start.
+int ilqg_integrate_plan(ilqg_handle h, const float* x0_in, double t0, double t, float* x_out) {
+  if (!h || !x0_in || !x_out) return ILQG_ERR_BAD_HANDLE;
+  const Problem& pr = h->pr;
+  if (pr.d.num_subsystems <= 0 || pr.d.subsystems[0].kind == ILQG_DYN_NONE) return ILQG_ERR_UNSUPPORTED;
+  const int T = pr.T, n = pr.n, M = pr.M;
+  const double kTimeStep = pr.d.time_step, plan_t0 = h->op_t0;
+  if (!(t >= t0) || !(t0 >= plan_t0)) return ILQG_ERR_INVALID_ARGUMENT;  // CHECK_GE :57-58
+  const double relative_t0 = t0 - plan_t0;                               // :64-70
+  const size_t current_timestep = static_cast<size_t>(relative_t0 / kTimeStep);
+  const double relative_t = t - plan_t0;
+  const size_t final_timestep = static_cast<size_t>(relative_t / kTimeStep);
+  // IntegrateToNextTimeStep :113-143, taken only when t0 is past the plan's start (:75)
+  const bool to_next = t0 > plan_t0;
+  const size_t itn_timestep = static_cast<size_t>((relative_t0 + kSmallNumber) / kTimeStep);
+  const double itn_remaining = kTimeStep * (itn_timestep + 1) - relative_t0;
+  if (to_next && (!(itn_remaining < kTimeStep + kSmallNumber) || itn_timestep >= (size_t)T))
+    return ILQG_ERR_INVALID_ARGUMENT;  // CHECK_LT :126-127
+  const float frac = itn_remaining / kTimeStep;
+  // IntegrateFromPriorTimeStep :145-171 (its time step is final_timestep again)
+  const double remaining_until_t = relative_t - kTimeStep * final_timestep;
+  if (final_timestep >= (size_t)T || !(remaining_until_t < kTimeStep)) return ILQG_ERR_INVALID_ARGUMENT;  // :154-155
+  const int itn_substeps = Rk4Substeps(t0, itn_remaining);
+  const int step_substeps = Rk4Substeps(0.0, kTimeStep);
+  const int prior_substeps = Rk4Substeps(plan_t0 + kTimeStep * final_timestep, remaining_until_t);
+
+  for (int b = 0; b < h->batch; b++) {
+    const Instance& in = h->inst[b];
+    real x[ILQG_MAX_XDIM], u[ILQG_MAX_UDIM], ref[ILQG_MAX_XDIM], nx[ILQG_MAX_XDIM];
+    auto controls = [&](size_t kk, const real* state_ref) {  // Strategy::operator(), strategy.h:73-76
+      for (int c = 0; c < M; c++) {
+        real acc = 0;
+        for (int a = 0; a < n; a++) acc += in.prob_Ps[(kk * M + c) * n + a] * (x[a] - state_ref[a]);
+        u[c] = (in.prob_us[kk * M + c] - acc) - in.prob_alphas[kk * M + c];
+      }
+    };
+    for (int a = 0; a < n; a++) x[a] = x0_in[(size_t)b * n + a];
+    if (to_next) {
+      for (int a = 0; a < n; a++)
+        ref[a] = itn_timestep + 1 < (size_t)T
+                     ? frac * in.prob_xs[itn_timestep * n + a] + (real)(1.0 - frac) * in.prob_xs[(itn_timestep + 1) * n + a]
+                     : in.prob_xs[(size_t)(T - 1) * n + a];
+      controls(itn_timestep, ref);
+      Integrate(pr, x, u, nx, itn_remaining, itn_substeps);
+      std::memcpy(x, nx, sizeof(real) * n);
+    }
+    for (size_t kk = current_timestep + 1; kk < final_timestep; kk++) {  // :85-111
+      controls(kk, &in.prob_xs[kk * n]);
+      Integrate(pr, x, u, nx, kTimeStep, step_substeps);
+      std::memcpy(x, nx, sizeof(real) * n);
+    }
+    controls(final_timestep, &in.prob_xs[final_timestep * n]);
+    Integrate(pr, x, u, nx, remaining_until_t, prior_substeps);
+    for (int a = 0; a < n; a++) x_out[(size_t)b * n + a] = (float)nx[a];
+  }
   return ILQG_OK;
 }
 

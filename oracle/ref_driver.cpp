@@ -276,6 +276,86 @@ int ilqg_ref_receding_horizon(int which, const float* x0, const ilqg_ref_params*
   return ok ? 0 : 1;
 }
 
+namespace {
+// A plan of `steps` time steps (possibly longer than the horizon, as a SolutionSplicer holds) from
+// flat arrays: xs [steps][n], us [steps][M], Ps [steps][M][n], alphas [steps][M].
+void LoadPlan(const MultiPlayerIntegrableSystem& dyn, int steps, const float* xs, const float* us, const float* Ps,
+              const float* alphas, double plan_t0, OperatingPoint* op, std::vector<Strategy>* strategies) {
+  const int n = dyn.XDim(), M = dyn.TotalUDim(), N = dyn.NumPlayers();
+  *op = OperatingPoint((size_t)steps, (PlayerIndex)N, plan_t0);
+  strategies->clear();
+  for (int i = 0; i < N; i++) strategies->emplace_back((size_t)steps, dyn.XDim(), dyn.UDim(i));
+  for (int k = 0; k < steps; k++) {
+    op->xs[k] = VectorXf(n);
+    for (int d = 0; d < n; d++) op->xs[k](d) = xs[(size_t)k * n + d];
+    int off = 0;
+    for (int i = 0; i < N; i++) {
+      const int m = dyn.UDim(i);
+      op->us[k][i] = VectorXf(m);
+      for (int r = 0; r < m; r++) {
+        op->us[k][i](r) = us[(size_t)k * M + off + r];
+        (*strategies)[i].alphas[k](r) = alphas[(size_t)k * M + off + r];
+        for (int d = 0; d < n; d++) (*strategies)[i].Ps[k](r, d) = Ps[((size_t)k * M + off + r) * n + d];
+      }
+      off += m;
+    }
+  }
+}
+}  // namespace
+
+// MultiPlayerIntegrableSystem::Integrate(t0, t, x0, operating_point, strategies)
+// (src/multi_player_integrable_system.cpp:54-83) of problem `which`'s dynamics under the given plan.
+int ilqg_ref_integrate(int which, int steps, const float* xs, const float* us, const float* Ps,
+                       const float* alphas, double plan_t0, const float* x0, double t0, double t, float* x_out) {
+  auto problem = MakeProblem(which);
+  if (!problem) return -1;
+  const auto& dyn = *problem->Dynamics();
+  OperatingPoint op(1, 1, 0.0);
+  std::vector<Strategy> strategies;
+  LoadPlan(dyn, steps, xs, us, Ps, alphas, plan_t0, &op, &strategies);
+  VectorXf x(dyn.XDim());
+  for (int d = 0; d < dyn.XDim(); d++) x(d) = x0[d];
+  const VectorXf out = dyn.Integrate(t0, t, x, op, strategies);
+  for (int d = 0; d < dyn.XDim(); d++) x_out[d] = out(d);
+  return 0;
+}
+
+// Problem::OverwriteSolution with a plan of `steps` >= kNumTimeSteps time steps (a spliced plan),
+// then Problem::SetUpNextRecedingHorizon(x_meas, t, planner_runtime): the sequence of
+// src/receding_horizon_simulator.cpp:105-109.  Outputs as ilqg_ref_receding_horizon.
+int ilqg_ref_receding_from_plan(int which, int steps, const float* plan_xs, const float* plan_us,
+                                const float* plan_Ps, const float* plan_alphas, double plan_t0,
+                                const float* x_meas, double t, double planner_runtime, float* x0_out,
+                                float* xs, float* us, float* Ps, float* alphas, double* t0_out) {
+  auto problem = MakeProblem(which);
+  if (!problem) return -1;
+  const auto& dyn = *problem->Dynamics();
+  const int n = dyn.XDim(), M = dyn.TotalUDim(), N = dyn.NumPlayers();
+  OperatingPoint plan(1, 1, 0.0);
+  std::vector<Strategy> strategies;
+  LoadPlan(dyn, steps, plan_xs, plan_us, plan_Ps, plan_alphas, plan_t0, &plan, &strategies);
+  problem->OverwriteSolution(plan, strategies);
+  VectorXf xm(n);
+  for (int d = 0; d < n; d++) xm(d) = x_meas[d];
+  problem->SetUpNextRecedingHorizon(xm, t, planner_runtime);
+  const OperatingPoint& op = problem->CurrentOperatingPoint();
+  const size_t T = time::kNumTimeSteps;
+  if (op.xs.size() != T) return 2;
+  for (int d = 0; d < n; d++) x0_out[d] = problem->InitialState()(d);
+  for (size_t k = 0; k < T; k++) {
+    for (int d = 0; d < n; d++) xs[k * n + d] = op.xs[k](d);
+    int off = 0;
+    for (int i = 0; i < N; i++) {
+      for (int d = 0; d < dyn.UDim(i); d++) us[k * M + off + d] = op.us[k][i](d);
+      off += dyn.UDim(i);
+    }
+  }
+  CopyStrategies(problem->CurrentStrategies(), dyn, Ps, alphas);
+  *t0_out = op.t0;
+  RelativeTimeTracker::ResetInitialTime(0.0);
+  return 0;
+}
+
 // SolutionSplicer (src/solution_splicer.cpp:57-131) on synthetic logs: a stored plan of T steps
 // starting at t0 = 0 whose entries encode (tag 1, time step, dimension), spliced with a new
 // horizon starting at new_t0 (tag 2).  Two-player system, n = 3, m = (1, 2).  Outputs the spliced

@@ -8,6 +8,7 @@
 #include <ilqgames/solver/augmented_lagrangian_solver.h>
 #include <ilqgames/solver/ilq_solver.h>
 #include <ilqgames/solver/lq_feedback_solver.h>
+#include <ilqgames/examples/receding_horizon_simulator.h>
 #include <ilqgames/solver/solution_splicer.h>
 
 #include "../../examples/cpp/intersection_problem.h"
@@ -281,6 +282,12 @@ void TestRecedingHorizon() {
   VectorXf x = plan.xs[3];
   x(0) += 0.05f;  // the measured state is a little off the plan
   x(7) -= 0.03f;
+  // MultiPlayerIntegrableSystem::Integrate(t0, t, ...) along the plan
+  // (src/multi_player_integrable_system.cpp:54-83): the measured state a little later
+  const VectorXf x_later = problem->Dynamics()->Integrate(t, 0.81, x, plan, log->FinalStrategies());
+  EXPECT(x_later.size() == x.size());
+  EXPECT((x_later - plan.xs[8]).norm() < 0.5f && (x_later - x).norm() > 0.1f);  // it moved, and stayed near the plan
+  Dump("ip_out", x_later.data(), (size_t)x_later.size());
   problem->SetUpNextRecedingHorizon(x, t, planner_runtime);
   const OperatingPoint& op = problem->CurrentOperatingPoint();
   // :95 / :107 -- the new problem starts within one time step of t + planner_runtime
@@ -308,6 +315,52 @@ void TestRecedingHorizon() {
   EXPECT((log->State(0, 0) - problem->InitialState()).norm() == 0.0f);
   Dump("rh_next_op", Flatten(log->FinalOperatingPoint()));
   std::printf("Problem::SetUpNextRecedingHorizon: first time step of the new problem = %zu, t0 = %.4f\n", first, op.t0);
+}
+
+// RecedingHorizonSimulator (src/receding_horizon_simulator.cpp:65-137) with a scripted clock (every
+// reading is 20 ms after the last, so each solve "takes" 20 ms): one log per solver call, each new
+// problem starts about planner_runtime after the time it was set up at, from where the state
+// really is; the same script gives the same run.
+void TestRecedingHorizonSimulator() {
+  const Time final_time = 1.5, planner_runtime = 0.5, tick = 0.02;
+  std::vector<std::vector<float>> runs;
+  for (int run = 0; run < 2; run++) {
+    const std::shared_ptr<Problem> problem = MakeProblem<IntersectionWithoutConstraints>();
+    SolverParams params = IntersectionParams();
+    params.max_solver_iters = 30;
+    ILQSolver solver(problem, params);
+    Time fake_now = 0.0;
+    const std::vector<std::shared_ptr<const SolverLog>> logs =
+        RecedingHorizonSimulator(final_time, planner_runtime, &solver, [&] { return fake_now += tick; });
+    // t advances by 0.25 s of driving + 20 ms of solving per round: rounds at t = 0.25, 0.52, ..., 1.33
+    EXPECT(logs.size() == 6);
+    std::vector<float> summary;
+    for (size_t k = 0; k < logs.size(); k++) {
+      const OperatingPoint& op = logs[k]->FinalOperatingPoint();
+      EXPECT(op.xs.size() == time::kNumTimeSteps);
+      if (k > 0) {
+        const Time set_up_at = 0.25 * k + tick * (k - 1);
+        EXPECT(std::fabs(set_up_at + planner_runtime - op.t0) <= time::kTimeStep);  // src/problem.cpp:123
+        EXPECT(op.t0 > logs[k - 1]->FinalOperatingPoint().t0);
+      }
+      summary.push_back((float)op.t0);
+      summary.push_back((float)logs[k]->NumIterates());
+      summary.push_back(logs[k]->WasConverged() ? 1.0f : 0.0f);
+      for (long a = 0; a < op.xs[0].size(); a++) summary.push_back(op.xs[0](a));
+      for (long a = 0; a < op.xs[50].size(); a++) summary.push_back(op.xs[50](a));
+    }
+    // the cars drive on: player 1's position at the start of each new problem keeps moving
+    const OperatingPoint& first = logs.front()->FinalOperatingPoint();
+    const OperatingPoint& last = logs.back()->FinalOperatingPoint();
+    EXPECT((last.xs[0].head(2) - first.xs[0].head(2)).norm() > 1.0f);
+    runs.push_back(summary);
+    if (run == 0) {
+      Dump("sim_summary", summary);
+      std::printf("RecedingHorizonSimulator: %zu solver calls, last problem starts at t0 = %.3f\n", logs.size(),
+                  last.t0);
+    }
+  }
+  EXPECT(runs[0] == runs[1]);
 }
 
 // SolutionSplicer (src/solution_splicer.cpp:57-131) on the synthetic logs of
@@ -411,6 +464,7 @@ int main(int argc, char** argv) {
   TestILQSolver(problem);
   TestAugmentedLagrangianSolver(problem);
   TestRecedingHorizon();
+  TestRecedingHorizonSimulator();
   TestSolutionSplicer();
   std::fclose(g_out);
   std::printf("host_api_test: all checks passed\n");

@@ -33,6 +33,18 @@ RH_ITERS = 2        # ILQ iterations before SetUpNextRecedingHorizon
 SPLICE_T0S = [0.3, 1.2, 0.0]   # start times of the spliced-in horizon (tests/cpp/host_api_test.cpp uses the same)
 RH_CASES = [(0.25, 0.1), (0.33, 0.25), (1.02, 0.1), (0.55, 0.0), (2.07, 0.5)]
 AL_INNER, AL_OUTER = 10, 40   # unconstrained_solver_max_iters, AL NumIterates cap
+# MultiPlayerIntegrableSystem::Integrate(t0, t, ...): (plan t0, t0, t).  t0 at the plan's start (no
+# IntegrateToNextTimeStep), both times inside one step, t == t0, times on the 0.1 s grid (where
+# relative_t / kTimeStep truncates one step low), a plan that does not start at zero.
+IP_CASES = [(0.0, 0.0, 0.25), (0.0, 0.13, 0.52), (0.0, 0.30, 0.34), (0.0, 0.4, 0.4), (0.0, 1.07, 2.5),
+            (0.0, 0.2, 0.7), (1.3, 1.51, 2.25)]
+# the same on a plan five steps longer than the horizon, as SolutionSplicer hands over
+IP_LONG_CASES = [(0.5, 0.77, 1.9), (0.5, 10.2, 10.93)]
+# SetUpNextRecedingHorizon from the long plan (plan t0 = 0.5): (t, planner_runtime); the first fits in
+# the stored plan, the second runs past its end and is extended with zero controls
+RHL_T0 = 0.5
+RHL_CASES = [(0.62, 0.1), (0.97, 0.45), (1.33, 0.2)]
+IP_GAMES = 3
 
 CASES = {
     # name: (reference problem id, descriptor builder, params builder, x0 batch)
@@ -147,6 +159,59 @@ def run_case(ref: R.RefLibrary, name: str):
     return out
 
 
+def long_plan(plan: dict, t0: float) -> dict:
+    """A plan five time steps longer than the horizon: five made-up executed steps (the plan's
+    first five, displaced so that no nearest-state search lands on them) in front of `plan`."""
+    out = {k: np.concatenate([plan[k][:5] - np.float32(1.0), plan[k]]) for k in ("xs", "us", "Ps", "alphas")}
+    out["t0"] = t0
+    return out
+
+
+def final_plan(g, b: int) -> dict:
+    last = int(g["ilq_iterates"][b]) - 1
+    return dict(xs=g["ilq_xs"][b, last], us=g["ilq_us"][b, last], Ps=g["ilq_Ps"][b], alphas=g["ilq_alphas"][b])
+
+
+def run_integrate(ref: R.RefLibrary, name: str, g) -> dict:
+    """Dynamics()->Integrate(t0, t, x0, plan) under the final ILQ iterate of ref_<name>.npz, from
+    measured states = plan state at t0 + noise; and, for the unconstrained problem,
+    OverwriteSolution(long plan) + SetUpNextRecedingHorizon."""
+    which = CASES[name][0]
+    n = ref.dims(which)[0]
+    rng = np.random.default_rng(11)
+    out = {"ip_cases": np.array(IP_CASES, np.float64), "ip_long_cases": np.array(IP_LONG_CASES, np.float64)}
+    for tag, cases, make in (("ip", IP_CASES, lambda p, t0: dict(p, t0=t0)), ("ip_long", IP_LONG_CASES, long_plan)):
+        xin, xout = [], []
+        for (plan_t0, t0, t) in cases:
+            rows_in, rows_out = [], []
+            for b in range(IP_GAMES):
+                plan = make(final_plan(g, b), plan_t0)
+                k = int((t0 - plan_t0) / 0.1)
+                x = (plan["xs"][k] + rng.normal(0, 0.05, size=n)).astype(np.float32)
+                rows_in.append(x)
+                rows_out.append(ref.integrate(which, plan, x, t0, t))
+            xin.append(np.stack(rows_in))
+            xout.append(np.stack(rows_out))
+        out[f"{tag}_x_in"], out[f"{tag}_x_out"] = np.stack(xin), np.stack(xout)
+    if ref.dims(which)[4] == 0:
+        rh = {k: [] for k in ("x_meas", "x0", "xs", "us", "Ps", "alphas", "t0")}
+        for (t, runtime) in RHL_CASES:
+            res, xm = [], []
+            for b in range(IP_GAMES):
+                plan = long_plan(final_plan(g, b), RHL_T0)
+                k = int((t - RHL_T0) / 0.1)
+                xm.append((plan["xs"][k] + rng.normal(0, 0.05, size=n)).astype(np.float32))
+                res.append(ref.receding_from_plan(which, plan, xm[-1], t, runtime))
+            rh["x_meas"].append(np.stack(xm))
+            for key in ("x0", "xs", "us", "Ps", "alphas"):
+                rh[key].append(np.stack([r[key] for r in res]))
+            assert len({r["t0"] for r in res}) == 1
+            rh["t0"].append(res[0]["t0"])
+        out.update(rhl_cases=np.array(RHL_CASES, np.float64), rhl_plan_t0=np.float64(RHL_T0),
+                   **{f"rhl_{k}": np.array(v) for k, v in rh.items()})
+    return out
+
+
 def check_polylines(ref: R.RefLibrary):
     """The lane / target polylines of problems.py equal the reference's, bit for bit."""
     import math
@@ -177,9 +242,14 @@ if __name__ == "__main__":
         for k, v in ref.splice(new_t0).items():
             splice[f"splice{c}_{k}"] = np.asarray(v)
     np.savez_compressed(os.path.join(HERE, "ref_splice.npz"), **splice)
+    only_integrate = "--integrate-only" in sys.argv   # keep the committed solver fixtures, add ref_integrate_*
     for name in CASES:
-        out = run_case(ref, name)
-        np.savez_compressed(os.path.join(HERE, f"ref_{name}.npz"), **out)
+        if only_integrate:
+            out = dict(np.load(os.path.join(HERE, f"ref_{name}.npz")))
+        else:
+            out = run_case(ref, name)
+            np.savez_compressed(os.path.join(HERE, f"ref_{name}.npz"), **out)
+        np.savez_compressed(os.path.join(HERE, f"ref_integrate_{name}.npz"), **run_integrate(ref, name, out))
         print("wrote", name, "iterates", out["ilq_iterates"].tolist(), "success",
               out["ilq_success"].tolist(),
               "AL iterates", out.get("al_iterates", np.zeros(0)).tolist())

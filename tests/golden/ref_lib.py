@@ -102,6 +102,36 @@ class RefLibrary:
         assert rc in (0, 1)
         return dict(x0=x0_out, xs=xs, us=us, Ps=Ps, alphas=alphas, t0=t0.value, ok=rc == 0)
 
+    def integrate(self, which: int, plan: dict, x0, t0: float, t: float) -> np.ndarray:
+        """MultiPlayerIntegrableSystem::Integrate(t0, t, x0, plan) of problem `which`'s dynamics;
+        plan = dict(xs [S][n], us [S][M], Ps [S][M][n], alphas [S][M], t0)."""
+        n = self.dims(which)[0]
+        arrs = [np.ascontiguousarray(plan[k], np.float32) for k in ("xs", "us", "Ps", "alphas")]
+        x0 = np.ascontiguousarray(x0, np.float32)
+        out = np.zeros(n, np.float32)
+        rc = self.lib.ilqg_ref_integrate(which, int(arrs[0].shape[0]), *[_ptr(a) for a in arrs],
+                                         C.c_double(plan["t0"]), _ptr(x0), C.c_double(t0), C.c_double(t),
+                                         _ptr(out))
+        assert rc == 0
+        return out
+
+    def receding_from_plan(self, which: int, plan: dict, x_meas, t: float, planner_runtime: float):
+        """Problem::OverwriteSolution(plan) + SetUpNextRecedingHorizon; the plan may be longer than
+        the horizon (a spliced plan)."""
+        n, M, N, T, _ = self.dims(which)
+        arrs = [np.ascontiguousarray(plan[k], np.float32) for k in ("xs", "us", "Ps", "alphas")]
+        x_meas = np.ascontiguousarray(x_meas, np.float32)
+        x0_out = np.zeros(n, np.float32)
+        xs, us = np.zeros((T, n), np.float32), np.zeros((T, M), np.float32)
+        Ps, alphas = np.zeros((T, M, n), np.float32), np.zeros((T, M), np.float32)
+        t0 = C.c_double(0)
+        rc = self.lib.ilqg_ref_receding_from_plan(
+            which, int(arrs[0].shape[0]), *[_ptr(a) for a in arrs], C.c_double(plan["t0"]), _ptr(x_meas),
+            C.c_double(t), C.c_double(planner_runtime), _ptr(x0_out), _ptr(xs), _ptr(us), _ptr(Ps),
+            _ptr(alphas), C.byref(t0))
+        assert rc == 0, rc
+        return dict(x0=x0_out, xs=xs, us=us, Ps=Ps, alphas=alphas, t0=t0.value)
+
     def splice(self, new_t0: float, max_steps: int = 128):
         """SolutionSplicer::Splice on the synthetic logs of oracle/ref_driver.cpp."""
         xs, us, al = (np.zeros((max_steps, 3), np.float32) for _ in range(3))

@@ -385,6 +385,52 @@ def test_receding_horizon_against_reference_fixture(product):
         assert np.all(h.download(abi.WARM_PS)[ref_zero.all(axis=(2, 3))] == 0)
 
 
+def wellposed_rows(in_double, want, tol=1e-5):
+    """Games where the oracle's fp64 build agrees with the reference's fp32 result: elsewhere (the
+    reg = 0 RoundaboutMerging plans carry gains ~5e3) fp32 rounding alone moves the answer."""
+    a, b = np.asarray(in_double, np.float64), np.asarray(want, np.float64)
+    a, b = a.reshape(len(a), -1), b.reshape(len(b), -1)
+    return np.abs(a - b).max(axis=1) <= tol * np.maximum(1.0, np.abs(b).max(axis=1))
+
+
+@pytest.mark.parametrize("name", ["three_player_intersection", "roundabout_merging", "air_3d"])
+def test_integrate_plan_against_reference_fixture(product, oracle64, name):
+    """MultiPlayerIntegrableSystem::Integrate(t0, t, x0, plan) on the device (k_integrate_plan)
+    against what the reference's own sources return (tests/golden/ref_integrate_<name>.npz): plans
+    of the horizon's length and five steps longer, t0 at / past the plan's start, both times inside
+    one step, t == t0, grid times.  fp32 tolerance (the device contracts a*b+c into fma), on the
+    games where the computation is well posed."""
+    from tests.test_ref_pins import integrate_plan_cases
+    n_cases = n_rows = 0
+    for (tag, c, got, want), (_, _, in_double, _) in zip(integrate_plan_cases(product, name),
+                                                        integrate_plan_cases(oracle64, name)):
+        assert np.isfinite(got).all()
+        rows = wellposed_rows(in_double, want)
+        close(got, want, tol=1e-4, atol=1e-4, what=f"{tag} case {c}", rows=rows)
+        n_cases += 1
+        n_rows += int(rows.sum())
+    assert n_cases == 9 and n_rows >= 18
+
+
+def test_receding_horizon_from_spliced_plan_against_reference_fixture(product, oracle64):
+    """OverwriteSolution(spliced plan, 105 steps) + SetUpNextRecedingHorizon as the receding-horizon
+    simulator runs them (src/receding_horizon_simulator.cpp:105-109), keys rhl_* of
+    tests/golden/ref_integrate_roundabout_merging.npz."""
+    from tests.test_ref_pins import long_plan_receding_cases
+    T = 100
+    compared = 0
+    for (c, h, new_t0, gi), (_, h64, _, _) in zip(long_plan_receding_cases(product), long_plan_receding_cases(oracle64)):
+        assert new_t0 == gi["rhl_t0"][c]
+        rows = wellposed_rows(h64.download(abi.WARM_XS)[:, :T], gi["rhl_xs"][c]) & wellposed_rows(
+            h64.download(abi.X0), gi["rhl_x0"][c])
+        close(h.download(abi.X0), gi["rhl_x0"][c], tol=1e-3, what=f"case {c} x0", rows=rows)
+        for what, key in ((abi.WARM_XS, "rhl_xs"), (abi.WARM_US, "rhl_us"), (abi.WARM_PS, "rhl_Ps"),
+                          (abi.WARM_ALPHAS, "rhl_alphas")):
+            close(h.download(what)[:, :T], gi[key][c], tol=1e-3, atol=1e-3, what=f"case {c} {key}", rows=rows)
+        compared += int(rows.sum())
+    assert compared >= 4
+
+
 # ------------------------------------------------------------------ full solves
 @pytest.mark.parametrize("name,batch,iters", [("three_player_intersection", 64, 10),
                                               ("roundabout_merging", 32, 3), ("air_3d", 36, 10)])

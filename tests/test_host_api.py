@@ -118,6 +118,8 @@ def _check_against_ctypes(lib, got, exact=True):
     xm = hr.download(abi.XS)[0, 3].copy()
     xm[0] += np.float32(0.05)
     xm[7] -= np.float32(0.03)
+    # Dynamics()->Integrate(0.33, 0.81, x, plan, strategies) -> ilqg_integrate_plan
+    assert same(hr.integrate_plan(xm[None], 0.33, 0.81)[0], got["ip_out"])
     new_t0 = hr.setup_next_receding_horizon(xm[None], 0.33, 0.25)
     assert np.float32(new_t0) == got["rh_t0"][0]
     assert same(hr.download(abi.X0)[0], got["rh_x0"])
@@ -125,6 +127,9 @@ def _check_against_ctypes(lib, got, exact=True):
     hr.solve_begin()
     hr.solve(chunk=1)
     assert same(_flat_op(hr.download(abi.XS)[0], hr.download(abi.US)[0]), got["rh_next_op"])
+    # RecedingHorizonSimulator with a scripted clock: six solver calls, start times increasing
+    sim = got["sim_summary"].reshape(6, 3 + 2 * 16)
+    assert np.all(np.diff(sim[:, 0]) > 0) and sim[0, 0] == 0 and np.all(sim[:, 1] >= 1)
     # SolutionSplicer::Splice: the host class against the reference's own (tests/golden/ref_splice.npz)
     g = np.load(os.path.join(REPO, "tests", "golden", "ref_splice.npz"))
     for c in range(3):

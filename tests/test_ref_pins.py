@@ -186,6 +186,95 @@ def test_oracle_reproduces_reference_receding_horizon(oracle):
     assert shifted >= 6   # the plan really moved: trailing strategies are the zero extension
 
 
+def final_plan(g, b):
+    last = int(g["ilq_iterates"][b]) - 1
+    return dict(xs=g["ilq_xs"][b, last], us=g["ilq_us"][b, last], Ps=g["ilq_Ps"][b], alphas=g["ilq_alphas"][b])
+
+
+def long_plan(plan):
+    """tests/golden/make_ref_golden.py:long_plan -- five made-up executed steps in front of `plan`."""
+    return {k: np.concatenate([plan[k][:5] - np.float32(1.0), plan[k]]) for k in ("xs", "us", "Ps", "alphas")}
+
+
+def plan_handle(lib, name, games, plan_t0, long):
+    """A handle whose warm start is the final ILQ iterate of ref_<name>.npz for `games` games
+    (five steps longer than the horizon if `long`), its OperatingPoint::t0 = plan_t0."""
+    g = load(name)
+    build, params = CASES[name]
+    desc, _ = build()
+    plans = [final_plan(g, b) for b in range(games)]
+    if long:
+        plans = [long_plan(p) for p in plans]
+    desc.num_time_steps = plans[0]["xs"].shape[0]
+    desc.initial_time = plan_t0
+    h = abi.Handle(lib, desc, params(), games)
+    h.upload_warmstart(*[np.stack([p[k] for p in plans]) for k in ("xs", "us", "Ps", "alphas")])
+    return h
+
+
+def integrate_plan_cases(lib, name):
+    """Every MultiPlayerIntegrableSystem::Integrate(t0, t, ...) case of ref_integrate_<name>.npz:
+    yields (tag, case, what the library returns, what the reference returned)."""
+    gi = np.load(os.path.join(GOLDEN, f"ref_integrate_{name}.npz"))
+    for tag, long in (("ip", False), ("ip_long", True)):
+        for c, (plan_t0, t0, t) in enumerate(gi[f"{tag}_cases"]):
+            h = plan_handle(lib, name, gi[f"{tag}_x_in"].shape[1], float(plan_t0), long)
+            before = h.download(abi.WARM_XS)
+            got = h.integrate_plan(gi[f"{tag}_x_in"][c], float(t0), float(t))
+            assert np.array_equal(h.download(abi.WARM_XS), before)   # the plan is read only
+            h.close()
+            yield tag, c, got, gi[f"{tag}_x_out"][c]
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_reproduces_reference_integrate(oracle, name):
+    """MultiPlayerIntegrableSystem::Integrate(Time t0, Time t, x0, operating_point, strategies)
+    (src/multi_player_integrable_system.cpp:54-83) -- what the receding-horizon simulator runs
+    between solves -- bit for bit, including its time-index truncation on grid times."""
+    n_cases = 0
+    for tag, c, got, want in integrate_plan_cases(oracle, name):
+        assert np.array_equal(got, want), (tag, c, np.abs(got - want).max())
+        n_cases += 1
+    assert n_cases == 9
+
+
+def long_plan_receding_cases(lib):
+    """Problem::OverwriteSolution(spliced plan) + SetUpNextRecedingHorizon as
+    src/receding_horizon_simulator.cpp:105-109 runs them: the stored plan is five steps longer than
+    the horizon; the first kNumTimeSteps steps of what the library leaves are the new problem."""
+    gi = np.load(os.path.join(GOLDEN, "ref_integrate_roundabout_merging.npz"))
+    for c, (t, runtime) in enumerate(gi["rhl_cases"]):
+        h = plan_handle(lib, "roundabout_merging", gi["rhl_x_meas"].shape[1], float(gi["rhl_plan_t0"]), True)
+        new_t0 = h.setup_next_receding_horizon(gi["rhl_x_meas"][c], float(t), float(runtime))
+        yield c, h, new_t0, gi
+        h.close()
+
+
+def test_oracle_reproduces_reference_receding_horizon_from_spliced_plan(oracle):
+    T = 100
+    extended = 0
+    for c, h, new_t0, gi in long_plan_receding_cases(oracle):
+        assert new_t0 == gi["rhl_t0"][c]
+        assert np.array_equal(h.download(abi.X0), gi["rhl_x0"][c])
+        for what, key in ((abi.WARM_XS, "rhl_xs"), (abi.WARM_US, "rhl_us"), (abi.WARM_PS, "rhl_Ps"),
+                          (abi.WARM_ALPHAS, "rhl_alphas")):
+            assert np.array_equal(h.download(what)[:, :T], gi[key][c]), (c, key)
+        extended += int(np.all(gi["rhl_Ps"][c][:, T - 1] == 0))
+    assert 1 <= extended < 3   # one case fits in the stored plan, one runs past its end
+
+
+def test_integrate_plan_argument_errors(oracle):
+    """CHECK_GE(t, t0), CHECK_GE(t0, operating_point.t0) (:57-58), CHECK_LT(current_timestep,
+    xs.size()) (:154) become error codes."""
+    h = plan_handle(oracle, "air_3d", 2, 1.0, False)
+    x = np.zeros((2, 3), np.float32)
+    for t0, t in ((1.5, 1.4), (0.9, 1.2), (1.2, 11.0), (1.2, 11.5)):
+        with pytest.raises(abi.IlqgError):
+            h.integrate_plan(x, t0, t)
+    assert h.integrate_plan(x, 1.2, 10.95).shape == (2, 3)
+    h.close()
+
+
 def test_receding_horizon_argument_errors(oracle):
     """Where the reference CHECK-fails (src/problem.cpp:68-71, :87) the ABI returns an error."""
     desc, _ = problems.roundabout_merging()
