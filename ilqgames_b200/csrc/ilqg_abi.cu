@@ -266,6 +266,7 @@ constexpr DimsEntry kDims[] = {
     {3, 2, 2},   // Air3D
     {2, 2, 2},   // test/test_lq_solver.cpp point-mass LQ game
     {12, 6, 3},  // BASELINE.json's "3x unicycle4d" variant
+    {18, 6, 3},  // ThreePlayerOvertaking: 3x Car6D (warp-per-game kernel: 18 is not a multiple of 4)
 };
 constexpr int kNumDims = sizeof(kDims) / sizeof(kDims[0]);
 
@@ -349,6 +350,7 @@ int DispatchBackward(SubSolver* h, int only_running, bool with_dxs, Sel sel = Se
     case 2: rc = LaunchBackward<3, 2, 2>(h, only_running, sel); hw = false; break;
     case 3: rc = LaunchBackward<2, 2, 2>(h, only_running, sel); hw = false; break;
     case 4: rc = LaunchBackwardHw<12, 6, 3>(h, only_running, sel); break;
+    case 5: rc = LaunchBackward<18, 6, 3>(h, only_running, sel); hw = false; break;
   }
   if (rc == ILQG_OK && hw && with_dxs) {
     k_delta_xs<<<(h->B + 3) / 4, 128, sizeof(float) * 4 * 2 * ILQG_MAX_XDIM, h->stream>>>(h->d, h->s, h->s.lq_x0);

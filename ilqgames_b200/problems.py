@@ -360,6 +360,66 @@ def roundabout_params(**overrides) -> abi.SolverParams:
 
 
 # --------------------------------------------------------------------------
+# ThreePlayerOvertakingExample (src/three_player_overtaking_example.cpp)
+# --------------------------------------------------------------------------
+def three_player_overtaking(num_time_steps: int = 100, time_step: float = 0.1):
+    """Returns (desc, x0).  3x SinglePlayerCar6D on a two-lane straight road, n = 18,
+    unconstrained; only record kinds the three headline examples already use."""
+    b = DescBuilder(num_time_steps, time_step)
+    kOmegaCostWeight, kJerkCostWeight = 500000.0, 500.0
+    nominal_v_weight, nominal_v = [10.0, 1.0, 1.0], [15.0, 10.0, 10.0]
+    kLaneCostWeight, kLaneBoundaryCostWeight, kLaneHalfWidth = 25.0, 100.0, 2.5
+    kMinProximity, kProximityCostWeight = 5.0, 100.0
+    start = [(2.5, -10.0, 10.0), (-1.0, -10.0, 2.0), (2.5, 10.0, 2.0)]   # x, y, speed (:113-130)
+    for _ in range(3):
+        b.add_player(2, 0.0, 0.0)                                          # PlayerCost("P1") ... (:198-200)
+    offs = [b.add_subsystem(abi.DYN_CAR6D, 6, i, [4.0]) for i in range(3)]
+    lane1 = b.add_polyline([(start[1][0], -1000.0), (start[1][0], 1000.0)])  # :206-209
+    lane2 = b.add_polyline([(start[2][0], -1000.0), (start[2][0], 1000.0)])
+    pos = [(o + 0, o + 1) for o in offs]
+    for i, lane in enumerate((lane1, lane1, lane2)):                       # :211-254
+        b.state_cost(i, abi.COST_QUADRATIC_POLYLINE2, dims=pos[i], weight=kLaneCostWeight, polyline=lane)
+        b.state_cost(i, abi.COST_SEMIQUADRATIC_POLYLINE2, dims=pos[i], weight=kLaneBoundaryCostWeight,
+                     polyline=lane, value=kLaneHalfWidth, flag=1)
+        b.state_cost(i, abi.COST_SEMIQUADRATIC_POLYLINE2, dims=pos[i], weight=kLaneBoundaryCostWeight,
+                     polyline=lane, value=-kLaneHalfWidth, flag=0)
+    for i in range(3):                                                     # :262-286
+        b.state_cost(i, abi.COST_QUADRATIC, dims=(offs[i] + 4,), weight=nominal_v_weight[i], value=nominal_v[i])
+    for i in range(3):                                                     # :289-308
+        b.control_cost(i, i, abi.COST_QUADRATIC, dims=(0,), weight=kOmegaCostWeight, value=0.0)
+        b.control_cost(i, i, abi.COST_QUADRATIC, dims=(1,), weight=kJerkCostWeight, value=0.0)
+    for i, others in ((0, (1, 2)), (1, (0, 2))):                           # :311-327; P3's are commented out
+        for j in others:
+            b.state_cost(i, abi.COST_PROXIMITY, dims=pos[i] + pos[j], weight=kProximityCostWeight,
+                         value=kMinProximity)
+    x0 = np.zeros(b.d.xdim, dtype=F)                                       # :181-195
+    for i, (x, y, v) in enumerate(start):
+        x0[offs[i] + 0], x0[offs[i] + 1], x0[offs[i] + 2], x0[offs[i] + 4] = x, y, F(math.pi / 2), v
+    return b.build(), x0
+
+
+def three_player_overtaking_params(**overrides) -> abi.SolverParams:
+    """SolverParams of exec/three_player_overtaking/main.cpp:71-74,108-112."""
+    base = dict(max_backtracking_steps=100, linesearch=1, expected_decrease_fraction=0.1,
+                initial_alpha_scaling=0.75, convergence_tolerance=0.01)
+    base.update(overrides)
+    return abi.SolverParams.defaults(**base)
+
+
+def three_player_overtaking_x0_batch(batch: int, seed: int) -> np.ndarray:
+    """Synthetic initial states: the example's, with positions moved U(-1, 1) m, headings
+    U(-0.05, 0.05) rad and speeds scaled U(0.8, 1.2)."""
+    _, x0 = three_player_overtaking()
+    rng = np.random.default_rng(seed)
+    out = np.tile(x0, (batch, 1))
+    for o in (0, 6, 12):
+        out[:, o:o + 2] += rng.uniform(-1.0, 1.0, size=(batch, 2)).astype(F)
+        out[:, o + 2] += rng.uniform(-0.05, 0.05, size=batch).astype(F)
+        out[:, o + 4] *= rng.uniform(0.8, 1.2, size=batch).astype(F)
+    return out.astype(F)
+
+
+# --------------------------------------------------------------------------
 # Air3DExample
 # --------------------------------------------------------------------------
 def draw_circle(center, radius, num_segments):

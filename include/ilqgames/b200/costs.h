@@ -273,6 +273,7 @@ ILQGAMES_B200_UNSUPPORTED_COST(CurvatureCost);
 ILQGAMES_B200_UNSUPPORTED_COST(FinalTimeCost);
 ILQGAMES_B200_UNSUPPORTED_COST(LocallyConvexProximityCost);
 ILQGAMES_B200_UNSUPPORTED_COST(NominalPathLengthCost);
+ILQGAMES_B200_UNSUPPORTED_COST(OrientationCost);
 ILQGAMES_B200_UNSUPPORTED_COST(WeightedConvexProximityCost);
 #undef ILQGAMES_B200_UNSUPPORTED_COST
 

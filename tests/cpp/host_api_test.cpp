@@ -19,6 +19,7 @@
 #include <ilqgames/examples/air_3d_example.h>
 #include <ilqgames/examples/roundabout_merging_example.h>
 #include <ilqgames/examples/three_player_intersection_example.h>
+#include <ilqgames/examples/three_player_overtaking_example.h>
 #endif
 
 #include <cstdio>
@@ -460,6 +461,8 @@ int main(int argc, char** argv) {
   // src/air_3d_example.cpp (+ draw_shapes.cpp), all compiled unchanged
   TestProblemDescriptor(MakeProblem<RoundaboutMergingExample>(), "roundabout", 4, 24, 44, 4);
   TestProblemDescriptor(MakeProblem<Air3DExample>(), "air3d", 2, 3, 8, 1);
+  // src/three_player_overtaking_example.cpp: a fourth example, made of the same record kinds (n = 18)
+  TestProblemDescriptor(MakeProblem<ThreePlayerOvertakingExample>(), "overtaking", 3, 18, 22, 2);
 #endif
   TestILQSolver(problem);
   TestAugmentedLagrangianSolver(problem);

@@ -55,6 +55,10 @@ CASES = {
                            lambda: problems.roundabout_x0_batch(8, 4096)),
     "air_3d": (R.AIR3D, problems.air_3d, problems.air_3d_params,
                lambda: problems.air_3d_x0_grid(4)[:12]),
+    # a fourth example of the reference that needs no record kind beyond the three above (n = 18)
+    "three_player_overtaking": (R.OVERTAKING, problems.three_player_overtaking,
+                                problems.three_player_overtaking_params,
+                                lambda: problems.three_player_overtaking_x0_batch(8, 18)),
 }
 
 
@@ -244,6 +248,8 @@ if __name__ == "__main__":
     np.savez_compressed(os.path.join(HERE, "ref_splice.npz"), **splice)
     only_integrate = "--integrate-only" in sys.argv   # keep the committed solver fixtures, add ref_integrate_*
     for name in CASES:
+        if "--only" in sys.argv and name != sys.argv[sys.argv.index("--only") + 1]:
+            continue
         if only_integrate:
             out = dict(np.load(os.path.join(HERE, f"ref_{name}.npz")))
         else:

@@ -26,6 +26,7 @@ CASES = {
                                   problems.three_player_intersection_params),
     "roundabout_merging": (problems.roundabout_merging, problems.roundabout_params),
     "air_3d": (problems.air_3d, problems.air_3d_params),
+    "three_player_overtaking": (problems.three_player_overtaking, problems.three_player_overtaking_params),
 }
 
 
