@@ -75,8 +75,9 @@ class DescBuilder:
 
     # costs ------------------------------------------------------------------
     def _rec(self, player, category, kind, arg=-1, dims=(0,), weight=1.0, value=0.0, flag=0,
-             polyline=-1, is_equality=0):
+             polyline=-1, is_equality=0, active_from=0.0):
         r = abi.CostDesc()
+        r.active_from = active_from   # FinalTimeCost threshold (0 = always)
         r.kind, r.player, r.arg, r.is_equality = kind, player, arg, is_equality
         for k in range(4):
             r.dim[k] = dims[k] if k < len(dims) else 0
@@ -413,6 +414,77 @@ def three_player_overtaking_x0_batch(batch: int, seed: int) -> np.ndarray:
     rng = np.random.default_rng(seed)
     out = np.tile(x0, (batch, 1))
     for o in (0, 6, 12):
+        out[:, o:o + 2] += rng.uniform(-1.0, 1.0, size=(batch, 2)).astype(F)
+        out[:, o + 2] += rng.uniform(-0.05, 0.05, size=batch).astype(F)
+        out[:, o + 4] *= rng.uniform(0.8, 1.2, size=batch).astype(F)
+    return out.astype(F)
+
+
+# --------------------------------------------------------------------------
+# TwoPlayerCollisionExample (src/two_player_collision_example.cpp)
+# --------------------------------------------------------------------------
+def two_player_collision(num_time_steps: int = 100, time_step: float = 0.1):
+    """Returns (desc, x0).  2x SinglePlayerCar6D driving at each other, n = 12, unconstrained; goal
+    costs are FinalTimeCost-wrapped QuadraticCosts (records with active_from = 9.5 s).  CPU oracle
+    only for now: the CUDA library has no time gate yet and answers ILQG_ERR_UNSUPPORTED."""
+    b = DescBuilder(num_time_steps, time_step)
+    kOmegaCostWeight, kJerkCostWeight = 5000.0, 3250.0
+    kLaneCostWeight, kLaneBoundaryCostWeight, kLaneHalfWidth = F(250.0), F(50000.0), F(2.5)
+    kMinProximity, kProximityCostWeight, kGoalCostWeight = 7.5, 5000.0, 1000.0
+    for _ in range(2):
+        b.add_player(2, 1.0, 0.0)                                         # PlayerCost("P1", 1.0, 0.0) (:175-176)
+    offs = [b.add_subsystem(abi.DYN_CAR6D, 6, i, [4.0]) for i in range(2)]
+    pos = [(o + 0, o + 1) for o in offs]
+    edge = float(F(2.5 + float(kLaneHalfWidth)))
+    lane1_p1p2 = b.add_polyline([(2.5, -50.0), (2.5, 50.0)])               # :182
+    # player 1 (:183-245): lane centre, left boundary, five boundary pieces around the crossing
+    b.state_cost(0, abi.COST_QUADRATIC_POLYLINE2, dims=pos[0], weight=kLaneCostWeight, polyline=lane1_p1p2)
+    b.state_cost(0, abi.COST_SEMIQUADRATIC_POLYLINE2, dims=pos[0], weight=F(kLaneBoundaryCostWeight * F(1000)),
+                 polyline=lane1_p1p2, value=-kLaneHalfWidth, flag=0)
+    pieces = [([(edge, -50.0), (edge, -5.0)], 1), ([(edge, 5.0), (edge, 50.0)], 1), ([(10.0, -5.0), (10.0, 5.0)], 1),
+              ([(edge, 5.0), (25.0, 5.0)], 0), ([(edge, -5.0), (25.0, -5.0)], 1)]
+    # player 2 (:186-209): lane centre, left and right boundary -- declared between player 1's
+    # costs in the source, but each PlayerCost keeps its own order
+    b.state_cost(1, abi.COST_QUADRATIC_POLYLINE2, dims=pos[1], weight=F(kLaneCostWeight * F(10)), polyline=lane1_p1p2)
+    b.state_cost(1, abi.COST_SEMIQUADRATIC_POLYLINE2, dims=pos[1], weight=F(kLaneBoundaryCostWeight * F(10)),
+                 polyline=lane1_p1p2, value=-kLaneHalfWidth, flag=0)
+    b.state_cost(1, abi.COST_SEMIQUADRATIC_POLYLINE2, dims=pos[1], weight=kLaneBoundaryCostWeight,
+                 polyline=lane1_p1p2, value=kLaneHalfWidth, flag=1)
+    for pts, oriented_right in pieces:
+        b.state_cost(0, abi.COST_SEMIQUADRATIC_POLYLINE2, dims=pos[0], weight=kLaneBoundaryCostWeight,
+                     polyline=b.add_polyline(pts), value=0.0, flag=oriented_right)
+    for i, w in enumerate((10.0, 1.0)):                                    # :252-266
+        b.state_cost(i, abi.COST_QUADRATIC, dims=(offs[i] + 4,), weight=w, value=5.0)
+    for i in range(2):                                                     # :269-281
+        b.control_cost(i, i, abi.COST_QUADRATIC, dims=(0,), weight=kOmegaCostWeight, value=0.0)
+        b.control_cost(i, i, abi.COST_QUADRATIC, dims=(1,), weight=kJerkCostWeight, value=0.0)
+    active_from = 10.0 - float(F(0.5))                                     # kTimeHorizon - kFinalTimeWindow (:284-299)
+    for i, (gx, gy) in enumerate(((2.5, 50.0), (2.5, -50.0))):
+        b.state_cost(i, abi.COST_QUADRATIC, dims=(pos[i][0],), weight=kGoalCostWeight, value=gx, active_from=active_from)
+        b.state_cost(i, abi.COST_QUADRATIC, dims=(pos[i][1],), weight=kGoalCostWeight, value=gy, active_from=active_from)
+    b.state_cost(0, abi.COST_PROXIMITY, dims=pos[0] + pos[1], weight=kProximityCostWeight, value=kMinProximity)
+    b.state_cost(1, abi.COST_PROXIMITY, dims=pos[1] + pos[0], weight=kProximityCostWeight, value=kMinProximity)
+    x0 = np.zeros(b.d.xdim, dtype=F)                                       # :164-172
+    for i, (x, y, th, v) in enumerate(((2.5, -50.0, math.pi / 2, 10.0), (2.5, 50.0, -math.pi / 2, 2.0))):
+        x0[offs[i] + 0], x0[offs[i] + 1], x0[offs[i] + 2], x0[offs[i] + 4] = x, y, F(th), v
+    return b.build(), x0
+
+
+def two_player_collision_params(**overrides) -> abi.SolverParams:
+    """SolverParams of exec/two_player_collision/main.cpp:71-74,108-112."""
+    base = dict(max_backtracking_steps=100, linesearch=1, expected_decrease_fraction=0.1,
+                initial_alpha_scaling=0.75, convergence_tolerance=0.01)
+    base.update(overrides)
+    return abi.SolverParams.defaults(**base)
+
+
+def two_player_collision_x0_batch(batch: int, seed: int) -> np.ndarray:
+    """Synthetic initial states: the example's, positions moved U(-1, 1) m, headings U(-0.05, 0.05)
+    rad, speeds scaled U(0.8, 1.2)."""
+    _, x0 = two_player_collision()
+    rng = np.random.default_rng(seed)
+    out = np.tile(x0, (batch, 1))
+    for o in (0, 6):
         out[:, o:o + 2] += rng.uniform(-1.0, 1.0, size=(batch, 2)).astype(F)
         out[:, o + 2] += rng.uniform(-0.05, 0.05, size=batch).astype(F)
         out[:, o + 4] *= rng.uniform(0.8, 1.2, size=batch).astype(F)

@@ -113,6 +113,12 @@ typedef struct {
   int32_t polyline;    /* index into the polyline table, or -1                  */
   float weight;
   float value;
+  /* FinalTimeCost(cost, threshold_time) (include/ilqgames/cost/final_time_cost.h:55-88): the
+   * record counts only at time steps whose RelativeTime(kk) = kk * time_step is
+   * >= RelativeTimeTracker::initial_time_ + active_from; 0 = always.  Costs only (not
+   * constraints).  ilqg_create of the CUDA library answers ILQG_ERR_UNSUPPORTED for a nonzero
+   * value (no device implementation yet); the CPU oracle implements it. */
+  double active_from;
 } ilqg_cost_desc;
 
 /* PlayerCost::CostStructure, include/ilqgames/cost/player_cost.h:105-111 */

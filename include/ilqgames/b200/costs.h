@@ -261,6 +261,26 @@ class Polyline2SignedDistanceCost : public TimeInvariantCost {
   const bool oriented_same_as_polyline_;
 };
 
+// include/ilqgames/cost/final_time_cost.h:55-88: the wrapped cost counts only from threshold_time
+// (relative to the initial time) on -- the wrapped cost's record with a time gate.
+class FinalTimeCost : public Cost {
+ public:
+  ~FinalTimeCost() {}
+  FinalTimeCost(const std::shared_ptr<const Cost>& cost, Time threshold_time, const std::string& name = "")
+      : Cost(0.0, name), cost_(cost), threshold_time_(threshold_time) {
+    CHECK_NOTNULL(cost.get());
+  }
+  bool Describe(ilqg_cost_desc* out, DescribeContext* ctx) const override {
+    if (!cost_->Describe(out, ctx)) return false;
+    out->active_from = threshold_time_;
+    return true;
+  }
+
+ private:
+  const std::shared_ptr<const Cost> cost_;
+  const Time threshold_time_;
+};
+
 // Costs the in-scope example sources include but never add to a player: constructible, not
 // describable (ilqg_create would be refused).
 #define ILQGAMES_B200_UNSUPPORTED_COST(Name)                                              \
@@ -270,7 +290,6 @@ class Polyline2SignedDistanceCost : public TimeInvariantCost {
     explicit Name(float weight, Args&&...) : TimeInvariantCost(weight, #Name) {}           \
   }
 ILQGAMES_B200_UNSUPPORTED_COST(CurvatureCost);
-ILQGAMES_B200_UNSUPPORTED_COST(FinalTimeCost);
 ILQGAMES_B200_UNSUPPORTED_COST(LocallyConvexProximityCost);
 ILQGAMES_B200_UNSUPPORTED_COST(NominalPathLengthCost);
 ILQGAMES_B200_UNSUPPORTED_COST(OrientationCost);

@@ -180,7 +180,25 @@ struct Problem {
   int num_constraints;
   int constraint_slot[ILQG_MAX_COSTS];  // cost record -> lambda slot or -1
   std::vector<int> lambda_index;         // kk -> TimeIndex
+  int first_step[ILQG_MAX_COSTS];        // FinalTimeCost gate: record c counts at kk >= first_step[c]
 };
+
+// FinalTimeCost::Evaluate / Quadraticize (include/ilqgames/cost/final_time_cost.h:64-77): active
+// iff t >= initial_time_ + threshold_time_, with t = RelativeTime(kk) = kk * kTimeStep
+// (relative_time_tracker.h:63-65; src/ilq_solver.cpp:236,475) and initial_time_ the tracker's
+// static, which Problem::SyncToExistingProblem moves (src/problem.cpp:120).
+void UpdateCostGates(Problem* pr, double tracker_initial_time) {
+  for (int c = 0; c < pr->d.num_costs; c++) {
+    const double threshold = pr->d.costs[c].active_from;
+    int first = 0;
+    if (threshold != 0.0) {
+      first = pr->T;
+      for (int kk = 0; kk < pr->T; kk++)
+        if (static_cast<double>(kk) * pr->d.time_step >= tracker_initial_time + threshold) { first = kk; break; }
+    }
+    pr->first_step[c] = first;
+  }
+}
 
 inline bool IsConstraintKind(int kind) {
   return kind == ILQG_CONSTRAINT_PROXIMITY || kind == ILQG_CONSTRAINT_SINGLE_DIMENSION;
@@ -247,8 +265,11 @@ int BuildProblem(const ilqg_problem_desc* desc, const ilqg_solver_params* params
     }
 
   pr->num_constraints = 0;
-  for (int c = 0; c < d.num_costs; c++)
+  for (int c = 0; c < d.num_costs; c++) {
     pr->constraint_slot[c] = IsConstraintKind(d.costs[c].kind) ? pr->num_constraints++ : -1;
+    if (pr->constraint_slot[c] >= 0 && d.costs[c].active_from != 0.0) return ILQG_ERR_INVALID_ARGUMENT;
+  }
+  UpdateCostGates(pr, d.initial_time);
 
   // RelativeTimeTracker::RelativeTime / TimeIndex in double,
   // include/ilqgames/utils/relative_time_tracker.h:63-72.
@@ -813,6 +834,7 @@ void QuadraticizeStep(const Problem& pr, const Instance& in, int kk, const real*
   }
   for (int c = 0; c < d.num_costs; c++) {
     const ilqg_cost_desc& cd = d.costs[c];
+    if (kk < pr.first_step[c]) continue;  // FinalTimeCost::Quadraticize returns before its cost's
     const int i = cd.player;
     const bool full = d.cost_structure[i] == ILQG_COST_SUM || in.te_quad[i] == kk;
     const int slot = pr.constraint_slot[c];
@@ -832,12 +854,13 @@ void QuadraticizeStep(const Problem& pr, const Instance& in, int kk, const real*
 
 // PlayerCost::Evaluate(t, x, us), src/player_cost.cpp:128-144: state + control
 // COSTS only (no constraints).
-real EvaluatePlayerCost(const Problem& pr, int i, const real* x, const real* u) {
+real EvaluatePlayerCost(const Problem& pr, int i, int kk, const real* x, const real* u) {
   real total = 0.0;
   const ilqg_problem_desc& d = pr.d;
   for (int c = 0; c < d.num_costs; c++) {
     const ilqg_cost_desc& cd = d.costs[c];
     if (cd.player != i || pr.constraint_slot[c] >= 0) continue;
+    if (kk < pr.first_step[c]) continue;  // FinalTimeCost::Evaluate is 0 before its threshold
     if (cd.arg < 0)
       total += EvaluateRecord(pr, cd, x, pr.n);
     else
@@ -855,7 +878,7 @@ void TotalCosts(const Problem& pr, Instance& in) {
   }
   for (int kk = 0; kk < T; kk++)
     for (int i = 0; i < N; i++) {
-      const real cur = EvaluatePlayerCost(pr, i, &in.xs[(size_t)kk * n], &in.us[(size_t)kk * M]);
+      const real cur = EvaluatePlayerCost(pr, i, kk, &in.xs[(size_t)kk * n], &in.us[(size_t)kk * M]);
       const int cs = pr.d.cost_structure[i];
       if (cs == ILQG_COST_SUM)
         in.total_costs[i] += cur;
@@ -1948,6 +1971,7 @@ int ilqg_setup_next_receding_horizon(ilqg_handle h, const float* x0_in, double t
     (void)N;
   }
   h->op_t0 = op_t0;
+  UpdateCostGates(&h->pr, op_t0);  // RelativeTimeTracker::ResetInitialTime(op.t0), src/problem.cpp:120
   if (new_t0) *new_t0 = op_t0;
   return ILQG_OK;
 }
@@ -2152,7 +2176,10 @@ int ilqg_reset(ilqg_handle h, int mask) {
         std::fill(v->begin(), v->end(), (real)0);
     }
   }
-  if (mask & ILQG_RESET_SOLUTION) h->op_t0 = h->pr.d.initial_time;  // a fresh OperatingPoint's t0
+  if (mask & ILQG_RESET_SOLUTION) {
+    h->op_t0 = h->pr.d.initial_time;  // a fresh OperatingPoint's t0
+    UpdateCostGates(&h->pr, h->op_t0);
+  }
   return ILQG_OK;
 }
 

@@ -20,6 +20,7 @@
 #include <ilqgames/examples/roundabout_merging_example.h>
 #include <ilqgames/examples/three_player_intersection_example.h>
 #include <ilqgames/examples/three_player_overtaking_example.h>
+#include <ilqgames/examples/two_player_collision_example.h>
 #endif
 
 #include <cstdio>
@@ -463,6 +464,8 @@ int main(int argc, char** argv) {
   TestProblemDescriptor(MakeProblem<Air3DExample>(), "air3d", 2, 3, 8, 1);
   // src/three_player_overtaking_example.cpp: a fourth example, made of the same record kinds (n = 18)
   TestProblemDescriptor(MakeProblem<ThreePlayerOvertakingExample>(), "overtaking", 3, 18, 22, 2);
+  // src/two_player_collision_example.cpp: FinalTimeCost-wrapped goal costs -> records with a time gate
+  TestProblemDescriptor(MakeProblem<TwoPlayerCollisionExample>(), "collision", 2, 12, 22, 6);
 #endif
   TestILQSolver(problem);
   TestAugmentedLagrangianSolver(problem);

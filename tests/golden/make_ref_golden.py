@@ -59,6 +59,9 @@ CASES = {
     "three_player_overtaking": (R.OVERTAKING, problems.three_player_overtaking,
                                 problems.three_player_overtaking_params,
                                 lambda: problems.three_player_overtaking_x0_batch(8, 18)),
+    # FinalTimeCost-wrapped goal costs (records with a time gate), n = 12, two players
+    "two_player_collision": (R.COLLISION, problems.two_player_collision, problems.two_player_collision_params,
+                             lambda: problems.two_player_collision_x0_batch(8, 12)),
 }
 
 

@@ -75,6 +75,24 @@ def test_invalid_descriptors_are_rejected(which, product_lib, oracle):
         assert lib.lib.ilqg_destroy(h) == 0
 
 
+def test_time_gated_records_fail_loudly_on_the_cuda_library(product_lib, oracle):
+    """FinalTimeCost records (ilqg_cost_desc::active_from != 0) exist in the oracle only so far: the
+    CUDA library must refuse them rather than ignore the gate."""
+    desc, _ = problems.two_player_collision()
+    assert sum(1 for c in range(desc.num_costs) if desc.costs[c].active_from != 0.0) == 4
+    p = problems.two_player_collision_params()
+    h = C.c_void_p()
+    assert product_lib.lib.ilqg_create(C.byref(desc), C.byref(p), 1, 0, C.byref(h)) == -2  # ILQG_ERR_UNSUPPORTED
+    assert oracle.lib.ilqg_create(C.byref(desc), C.byref(p), 1, 0, C.byref(h)) == 0
+    assert oracle.lib.ilqg_destroy(h) == 0
+    # a gate on a constraint record is not a thing in the reference (FinalTimeCost wraps Costs)
+    bad, _ = problems.three_player_intersection()
+    for c in range(bad.num_costs):
+        if bad.costs[c].kind == abi.CONSTRAINT_PROXIMITY:
+            bad.costs[c].active_from = 1.0
+    assert oracle.lib.ilqg_create(C.byref(bad), C.byref(p), 1, 0, C.byref(h)) == -1
+
+
 def test_descriptor_shapes_of_the_three_configs(oracle):
     # SURVEY.md section 8 shape table (reference-true shapes)
     for build, N, n, M, ncon, ncost in ((problems.three_player_intersection, 3, 16, 6, 6, 18),

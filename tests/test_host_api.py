@@ -32,7 +32,8 @@ def _build(tmp_path, lib_path, dropin=False):
                     "-I" + os.path.join(REFERENCE, "include")] + [
             os.path.join(REFERENCE, "src", f + ".cpp") for f in (
                 "three_player_intersection_example", "roundabout_merging_example", "roundabout_lane_center",
-                "initialize_along_route", "air_3d_example", "draw_shapes", "three_player_overtaking_example")]
+                "initialize_along_route", "air_3d_example", "draw_shapes", "three_player_overtaking_example",
+                "two_player_collision_example")]
     subprocess.run(cmd, check=True)
     return exe
 
@@ -174,10 +175,12 @@ def test_reference_example_source_drops_in_unchanged(oracle, tmp_path):
     """north_star: 'an example like ThreePlayerIntersectionExample drops in unchanged'."""
     got = _run(_build(tmp_path, oracle.path, dropin=True), tmp_path)
     assert np.array_equal(got["desc_reference"].view(np.uint32), got["desc_own"].view(np.uint32))
-    # RoundaboutMergingExample, Air3DExample, ThreePlayerOvertakingExample: the descriptors DescribeProblem builds from the
+    # RoundaboutMergingExample, Air3DExample, ThreePlayerOvertakingExample,
+    # TwoPlayerCollisionExample: the descriptors DescribeProblem builds from the
     # reference's own example code equal the ones problems.py writes out by hand, bit for bit
     for tag, build in (("roundabout", problems.roundabout_merging), ("air3d", problems.air_3d),
-                       ("overtaking", problems.three_player_overtaking)):
+                       ("overtaking", problems.three_player_overtaking),
+                       ("collision", problems.two_player_collision)):
         desc, x0 = build()
         mine = np.frombuffer(bytes(desc), dtype=np.uint32)
         theirs = got["desc_" + tag].view(np.uint32)

@@ -27,6 +27,7 @@ CASES = {
     "roundabout_merging": (problems.roundabout_merging, problems.roundabout_params),
     "air_3d": (problems.air_3d, problems.air_3d_params),
     "three_player_overtaking": (problems.three_player_overtaking, problems.three_player_overtaking_params),
+    "two_player_collision": (problems.two_player_collision, problems.two_player_collision_params),
 }
 
 
