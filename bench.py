@@ -498,10 +498,42 @@ def run_b200(args):
             "cpu_baseline": cpu,
             "gather_ms": gather_ms,
         }
+        if args.with_al and world == 1:
+            line["al_solve"] = al_solve_table(lib, args.batch, args.seed, local)
         emit(line)
     h.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def al_solve_table(lib, batch: int, seed: int, device: int = 0, al_iterates_cap: int = 100, repeats: int = 2):
+    """SURVEY 8(d)'s second table: the FULL AugmentedLagrangianSolver::Solve of the batch (every
+    game runs its own outer loop: inner ILQSolver solves capped at unconstrained_solver_max_iters,
+    multiplier sweeps, exit on constraint error or the NumIterates cap), timed on the host clock
+    around a synchronised solve.  Works on any library implementing include/ilqg.h."""
+    from ilqgames_b200 import _abi as abi, al, problems
+    desc, _ = problems.three_player_intersection()
+    p = problems.three_player_intersection_params()
+    p.max_solver_iters = p.unconstrained_solver_max_iters   # the handle's cap is the inner solver's
+    x0 = problems.three_player_intersection_x0_batch(batch, seed)
+    h = abi.Handle(lib, desc, p, batch, device)
+    h.upload_x0(x0)
+    best = None
+    for _ in range(repeats + 1):          # first pass = warm-up
+        h.reset(h.RESET_SOLVER | h.RESET_MULTIPLIERS | h.RESET_SOLUTION)
+        h.synchronize()
+        t0 = time.perf_counter()
+        out = al.solve_augmented_lagrangian(h, al_iterates_cap, p.constraint_error_tolerance)
+        h.synchronize()
+        dt = time.perf_counter() - t0
+        row = {"seconds": dt, "inner_solves": out.rounds, "logged_iterates": int(out.iterates.sum()),
+               "logged_iterates_per_s": int(out.iterates.sum()) / dt, "games": batch,
+               "games_per_s": batch / dt, "success_fraction": float(out.success.mean()),
+               "al_iterates_cap": al_iterates_cap}
+        if best is None or row["seconds"] < best["seconds"]:
+            best = row
+    h.close()
+    return best
 
 
 _RESULT_FD = None
@@ -533,6 +565,8 @@ def main():
     ap.add_argument("--seed", type=int, default=4096)
     ap.add_argument("--cpu-sample", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--with-al", action="store_true",
+                    help="also time the full augmented-Lagrangian solve of the batch (adds `al_solve`; N = 1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -35,3 +35,13 @@ def test_gpu_arm_refuses_to_run_without_a_device():
                          capture_output=True, text=True, cwd=REPO, timeout=600)
     assert res.returncode != 0 and "CUDA" in (res.stderr + res.stdout)
     assert not [l for l in res.stdout.splitlines() if l.strip().startswith("{")]
+
+
+def test_al_solve_table_runs_through_the_abi(oracle):
+    """bench.py --with-al (SURVEY 8d's second table, the full AugmentedLagrangianSolver::Solve of
+    the batch): the helper is library-agnostic, so the oracle can stand in here."""
+    import bench
+    row = bench.al_solve_table(oracle, 3, 1024, 0, al_iterates_cap=25, repeats=0)
+    assert row["games"] == 3 and row["inner_solves"] >= 2
+    assert row["logged_iterates"] >= 3 * 2 and row["seconds"] > 0
+    assert 0.0 <= row["success_fraction"] <= 1.0
