@@ -1,5 +1,7 @@
 """Short, torch-free target for ncu: one Solve() prologue + a few iLQ iterations at the bench
-batch size.  usage: python tools/profile_target.py [batch] [iters] [config]"""
+batch size.  usage: python tools/profile_target.py [batch] [iters] [c1|c3|overtaking|c4] [finish]
+With a fifth argument the solve also runs to the end and a state is carried along the plan
+(ilqg_integrate_plan), so compute-sanitizer sees those kernels too."""
 import os
 import sys
 
@@ -18,6 +20,10 @@ elif config == "c3":
     desc, _ = problems.roundabout_merging()
     params = problems.roundabout_params(max_solver_iters=iters, disable_convergence_exit=1)
     x0 = problems.roundabout_x0_batch(batch, 4096)
+elif config == "overtaking":   # n = 18: the warp-per-game K_bwd instance
+    desc, _ = problems.three_player_overtaking()
+    params = problems.three_player_overtaking_params(max_solver_iters=iters, disable_convergence_exit=1)
+    x0 = problems.three_player_overtaking_x0_batch(batch, 18)
 else:
     desc, _ = problems.air_3d()
     params = problems.air_3d_params(max_solver_iters=iters, disable_convergence_exit=1)
@@ -31,4 +37,6 @@ h.iterate(iters)
 h.synchronize()
 if len(sys.argv) > 4:
     h.solve()
+    h.overwrite_solution()
+    h.integrate_plan(x0, 0.13, 0.52)
 print("done", h.download(abi.ITERS).sum(), h.download(abi.BACKTRACKS).sum())
