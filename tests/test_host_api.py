@@ -201,3 +201,22 @@ def test_reference_example_source_drops_in_unchanged(oracle, tmp_path):
 def test_cpp_host_classes_on_the_gpu(product, tmp_path):
     got = _run(_build(tmp_path, product.path), tmp_path)
     _check_against_ctypes(product, got, exact=True)
+
+
+def test_example_programs_build_and_run_on_the_oracle(oracle, tmp_path):
+    """examples/cpp: the GUI-less counterparts of exec/three_player_intersection and
+    exec/receding_horizon_example, linked against the CPU oracle here."""
+    subprocess.run(["make", "-C", os.path.join(REPO, "examples", "cpp"), "ILQG_LIB=" + oracle.path,
+                    "OUT=" + str(tmp_path)], check=True, capture_output=True)
+    env = dict(os.environ, ILQGAMES_LOG_DIR=str(tmp_path / "logs"))
+    res = subprocess.run([str(tmp_path / "three_player_intersection"), "4", "example_run"], capture_output=True,
+                         text=True, env=env, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "AugmentedLagrangianSolver:" in res.stdout and "ILQSolver::SolveBatch: 4 games" in res.stdout
+    assert os.path.isdir(tmp_path / "logs" / "example_run")
+    res = subprocess.run([str(tmp_path / "receding_horizon"), "1.0", "2.0"], capture_output=True, text=True,
+                         env=env, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    calls = [ln for ln in res.stdout.splitlines() if ln.strip().startswith("call ")]
+    # a generous planner_runtime: the simulator CHECKs that no solve outlasts it, on a loaded host too
+    assert len(calls) >= 2 and "horizon starts at t0 = 0.00 s" in calls[0]
