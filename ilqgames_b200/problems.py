@@ -492,6 +492,62 @@ def two_player_collision_x0_batch(batch: int, seed: int) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------
+# TwoPlayerCollisionAvoidanceReachabilityExample
+# (src/two_player_collision_avoidance_reachability_example.cpp)
+# --------------------------------------------------------------------------
+def two_player_collision_avoidance_reachability(num_time_steps: int = 100, time_step: float = 0.1,
+                                                px0: float = 0.0, py0: float = -5.0):
+    """Returns (desc, x0).  2x SinglePlayerCar5D, n = 10, both players max-over-time of a
+    SignedDistanceCost between the cars.  CPU oracle only for now (ILQG_DYN_CAR5D and
+    ILQG_COST_SIGNED_DISTANCE have no device implementation yet)."""
+    b = DescBuilder(num_time_steps, time_step)
+    kOmegaCostWeight = 0.1
+    heading1, speed = F(0.1), F(5.0)
+    for _ in range(2):
+        b.add_player(2, 0.0, 0.0, abi.COST_MAX)                            # SetMaxOverTime (:160-161)
+    offs = [b.add_subsystem(abi.DYN_CAR5D, 5, i, [4.0]) for i in range(2)]
+    # nominal distance (:140-151): where the two cars are at half the horizon if they hold their
+    # initial headings and speeds; the double time * float speed narrows to float on the Point2
+    half = F(0.5 * (time_step * num_time_steps) * float(speed))
+    p1 = (F(F(px0) + F(half * _cosf(heading1))), F(F(py0) + F(half * _sinf(heading1))))
+    p2 = (F(F(0.0) + F(half * _cosf(F(0.0)))), F(F(0.0) + F(half * _sinf(F(0.0)))))
+    dx, dy = F(p1[0] - p2[0]), F(p1[1] - p2[1])
+    nominal = F(np.sqrt(F(F(dx * dx) + F(dy * dy))))
+    pos = [(o + 0, o + 1) for o in offs]
+    # SignedDistanceCost(dims1, dims2, nominal, "CollisionAvoidance"): the string literal binds to
+    # `bool less_is_positive` (a pointer converts to bool before it converts to std::string)
+    for i in range(2):
+        b.state_cost(i, abi.COST_SIGNED_DISTANCE, dims=pos[0] + pos[1], weight=1.0, value=float(nominal), flag=1)
+        b.control_cost(i, i, abi.COST_QUADRATIC, dims=(-1,), weight=kOmegaCostWeight, value=0.0)
+    x0 = np.zeros(b.d.xdim, dtype=F)                                       # :106-117
+    x0[offs[0] + 0], x0[offs[0] + 1], x0[offs[0] + 2], x0[offs[0] + 4] = px0, py0, heading1, speed
+    x0[offs[1] + 4] = speed
+    return b.build(), x0
+
+
+def two_player_collision_avoidance_reachability_params(**overrides) -> abi.SolverParams:
+    """SolverParams of exec/two_player_collision_avoidance_reachability_example/main.cpp:76-79,
+    114-121 (its two regularization fields are dead)."""
+    base = dict(max_backtracking_steps=100, linesearch=1, expected_decrease_fraction=0.1,
+                initial_alpha_scaling=0.1, convergence_tolerance=0.01)
+    base.update(overrides)
+    return abi.SolverParams.defaults(**base)
+
+
+def two_player_collision_avoidance_reachability_x0_batch(batch: int, seed: int) -> np.ndarray:
+    """Synthetic initial states: the example's, positions moved U(-1, 1) m, headings U(-0.1, 0.1)
+    rad, speeds scaled U(0.8, 1.2)."""
+    _, x0 = two_player_collision_avoidance_reachability()
+    rng = np.random.default_rng(seed)
+    out = np.tile(x0, (batch, 1))
+    for o in (0, 5):
+        out[:, o:o + 2] += rng.uniform(-1.0, 1.0, size=(batch, 2)).astype(F)
+        out[:, o + 2] += rng.uniform(-0.1, 0.1, size=batch).astype(F)
+        out[:, o + 4] *= rng.uniform(0.8, 1.2, size=batch).astype(F)
+    return out.astype(F)
+
+
+# --------------------------------------------------------------------------
 # Air3DExample
 # --------------------------------------------------------------------------
 def draw_circle(center, radius, num_segments):

@@ -75,7 +75,9 @@ enum {
   ILQG_DYN_NONE = 0,       /* LQ-only handle: lin/quad come from ilqg_upload_lq */
   ILQG_DYN_CAR6D = 1,      /* params[0] = inter-axle distance                  */
   ILQG_DYN_UNICYCLE4D = 2,
-  ILQG_DYN_AIR3D = 3       /* params[0] = evader speed, params[1] = pursuer    */
+  ILQG_DYN_AIR3D = 3,      /* params[0] = evader speed, params[1] = pursuer    */
+  ILQG_DYN_CAR5D = 4       /* single_player_car_5d.h:102-147; params[0] = inter-axle distance.
+                            * CPU oracle only so far: the CUDA library answers ILQG_ERR_UNSUPPORTED */
 };
 
 typedef struct {
@@ -100,7 +102,10 @@ enum {
   ILQG_COST_SEMIQUADRATIC_POLYLINE2 = 5,  /* dim[0..1], polyline, weight, value=threshold, flag=oriented_right */
   ILQG_COST_POLYLINE2_SIGNED_DISTANCE = 6,/* dim[0..1], polyline, value=nominal, flag=oriented_same_as_polyline */
   ILQG_CONSTRAINT_PROXIMITY = 7,          /* dim[0..3], value=threshold, flag=keep_within      */
-  ILQG_CONSTRAINT_SINGLE_DIMENSION = 8    /* dim[0], value=threshold, flag=keep_below          */
+  ILQG_CONSTRAINT_SINGLE_DIMENSION = 8,   /* dim[0], value=threshold, flag=keep_below          */
+  ILQG_COST_SIGNED_DISTANCE = 9           /* src/signed_distance_cost.cpp:50-112: dim[0..3]=x1,y1,x2,y2,
+                                           * value=nominal, flag=less_is_positive (weight unused).
+                                           * CPU oracle only so far (CUDA: ILQG_ERR_UNSUPPORTED) */
 };
 
 typedef struct {

@@ -4,4 +4,5 @@
 #ifndef ILQGAMES_B200_COMPAT_GLOG_LOGGING_H
 #define ILQGAMES_B200_COMPAT_GLOG_LOGGING_H
 #include <ilqgames/b200/log_shim.h>
+#include <gflags/gflags.h>  // glog built with gflags support pulls it in; some example sources rely on that
 #endif

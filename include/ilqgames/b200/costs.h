@@ -187,6 +187,36 @@ class ProximityCost : public TimeInvariantCost {
   const Dimension xidx1_, yidx1_, xidx2_, yidx2_;
 };
 
+// src/signed_distance_cost.cpp:50-112 (include/ilqgames/cost/signed_distance_cost.h:52-88):
+// nominal minus the distance between two positions, unweighted.  ILQG_COST_SIGNED_DISTANCE, which
+// only the CPU oracle implements so far.  The defaulted bool sits before the name as in the
+// reference, so a call that passes a string literal fourth binds it to less_is_positive there too.
+class SignedDistanceCost : public TimeInvariantCost {
+ public:
+  SignedDistanceCost(const std::pair<Dimension, Dimension>& dims1, const std::pair<Dimension, Dimension>& dims2,
+                     float nominal = 0.0, bool less_is_positive = true, const std::string& name = "")
+      : TimeInvariantCost(1.0, name), xdim1_(dims1.first), ydim1_(dims1.second), xdim2_(dims2.first),
+        ydim2_(dims2.second), nominal_(nominal), less_is_positive_(less_is_positive) {
+    CHECK_GE(xdim1_, 0);
+    CHECK_GE(ydim1_, 0);
+    CHECK_GE(xdim2_, 0);
+    CHECK_GE(ydim2_, 0);
+  }
+  bool Describe(ilqg_cost_desc* out, DescribeContext*) const override {
+    out->kind = ILQG_COST_SIGNED_DISTANCE;
+    out->dim[0] = xdim1_; out->dim[1] = ydim1_; out->dim[2] = xdim2_; out->dim[3] = ydim2_;
+    out->weight = weight_;
+    out->value = nominal_;
+    out->flag = less_is_positive_;
+    return true;
+  }
+
+ private:
+  const Dimension xdim1_, ydim1_, xdim2_, ydim2_;
+  const float nominal_;
+  const bool less_is_positive_;
+};
+
 // src/semiquadratic_cost.cpp:51-85
 class SemiquadraticCost : public TimeInvariantCost {
  public:

@@ -58,13 +58,24 @@ class SinglePlayerUnicycle4D : public SinglePlayerDynamicalSystem {
   static constexpr Dimension kNumUDims = 2, kOmegaIdx = 0, kAIdx = 1;
 };
 
-// included by the intersection example, used by none of the in-scope problems
+// include/ilqgames/dynamics/single_player_car_5d.h:60-147; state (x, y, theta, phi, v), controls
+// (steering rate, acceleration).  Described as ILQG_DYN_CAR5D, which only the CPU oracle
+// implements so far (the CUDA library refuses it).
 class SinglePlayerCar5D : public SinglePlayerDynamicalSystem {
  public:
-  SinglePlayerCar5D(float inter_axle_distance) : SinglePlayerDynamicalSystem(kNumXDims, kNumUDims) { (void)inter_axle_distance; }
+  SinglePlayerCar5D(float inter_axle_distance)
+      : SinglePlayerDynamicalSystem(kNumXDims, kNumUDims), inter_axle_distance_(inter_axle_distance) {}
   std::vector<Dimension> PositionDimensions() const override { return {kPxIdx, kPyIdx}; }
+  bool Describe(ilqg_subsystem_desc* out) const override {
+    out->kind = ILQG_DYN_CAR5D;
+    out->params[0] = inter_axle_distance_;
+    return true;
+  }
   static constexpr Dimension kNumXDims = 5, kPxIdx = 0, kPyIdx = 1, kThetaIdx = 2, kPhiIdx = 3, kVIdx = 4;
   static constexpr Dimension kNumUDims = 2, kOmegaIdx = 0, kAIdx = 1;
+
+ private:
+  const float inter_axle_distance_;
 };
 
 // include/ilqgames/dynamics/multi_player_integrable_system.h:58-140

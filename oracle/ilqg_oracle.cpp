@@ -334,6 +334,15 @@ void EvaluateDynamics(const Problem& pr, const real* x, const real* u, real* xdo
         xd[5] = us[1];
         break;
       }
+      case ILQG_DYN_CAR5D: {  // single_player_car_5d.h:102-113
+        const real L = sd.params[0];
+        xd[0] = xs[4] * std::cos(xs[2]);
+        xd[1] = xs[4] * std::sin(xs[2]);
+        xd[2] = (xs[4] / L) * std::tan(xs[3]);
+        xd[3] = us[0];
+        xd[4] = us[1];
+        break;
+      }
       case ILQG_DYN_UNICYCLE4D: {  // single_player_unicycle_4d.h:90-99
         xd[0] = xs[3] * std::cos(xs[2]);
         xd[1] = xs[3] * std::sin(xs[2]);
@@ -435,6 +444,22 @@ void Linearize(const Problem& pr, const real* x, const real* u, real* A, real* B
         BB(5, 1) = kTimeStep;
         break;
       }
+      case ILQG_DYN_CAR5D: {  // single_player_car_5d.h:115-138
+        const real L = sd.params[0];
+        const real ctheta = std::cos(xs[2]) * kTimeStep;
+        const real stheta = std::sin(xs[2]) * kTimeStep;
+        const real cphi = std::cos(xs[3]);
+        const real tphi = std::tan(xs[3]);
+        AA(0, 2) += -xs[4] * stheta;
+        AA(0, 4) += ctheta;
+        AA(1, 2) += xs[4] * ctheta;
+        AA(1, 4) += stheta;
+        AA(2, 3) += xs[4] * kTimeStep / (L * cphi * cphi);
+        AA(2, 4) += tphi * kTimeStep / L;
+        BB(3, 0) = kTimeStep;
+        BB(4, 1) = kTimeStep;
+        break;
+      }
       case ILQG_DYN_UNICYCLE4D: {
         const real ctheta = std::cos(xs[2]) * kTimeStep;
         const real stheta = std::sin(xs[2]) * kTimeStep;
@@ -526,6 +551,12 @@ real EvaluateRecord(const Problem& pr, const ilqg_cost_desc& cd, const real* in,
       if (delta_sq >= threshold_sq_) return 0.0;
       const real gap = threshold_ - std::sqrt(delta_sq);
       return 0.5 * weight_ * gap * gap;
+    }
+    case ILQG_COST_SIGNED_DISTANCE: {  // src/signed_distance_cost.cpp:50-62
+      const real dx = in[cd.dim[0]] - in[cd.dim[2]];
+      const real dy = in[cd.dim[1]] - in[cd.dim[3]];
+      const real cost = (real)cd.value - std::hypot(dx, dy);
+      return cd.flag ? cost : -cost;
     }
     case ILQG_COST_SEMIQUADRATIC: {  // src/semiquadratic_cost.cpp:51-59
       const real diff = in[cd.dim[0]] - cd.value;
@@ -663,6 +694,40 @@ void QuadraticizeRecord(const Problem& pr, const ilqg_cost_desc& cd, const real*
       H(yidx1_, xidx2_) -= hess_x1y1;
       H(xidx2_, yidx2_) += hess_x1y1;
       H(yidx2_, xidx2_) += hess_x1y1;
+      break;
+    }
+    case ILQG_COST_SIGNED_DISTANCE: {  // src/signed_distance_cost.cpp:64-112
+      const int xdim1_ = cd.dim[0], ydim1_ = cd.dim[1], xdim2_ = cd.dim[2], ydim2_ = cd.dim[3];
+      const real s = cd.flag ? 1.0 : -1.0;
+      const real delta_x = in[xdim1_] - in[xdim2_];
+      const real delta_y = in[ydim1_] - in[ydim2_];
+      const real norm = std::hypot(delta_x, delta_y);
+      const real norm_3 = norm * norm * norm;
+      const real dx1 = -s * delta_x / norm;
+      const real dy1 = -s * delta_y / norm;
+      const real ddx1 = -s * delta_y * delta_y / norm_3;
+      const real ddy1 = -s * delta_x * delta_x / norm_3;
+      const real dx1dy1 = s * delta_x * delta_y / norm_3;
+      grad[xdim1_] += dx1;
+      grad[ydim1_] += dy1;
+      grad[xdim2_] -= dx1;
+      grad[ydim2_] -= dy1;
+      H(xdim1_, xdim1_) += ddx1;
+      H(ydim1_, ydim1_) += ddy1;
+      H(xdim1_, ydim1_) += dx1dy1;
+      H(ydim1_, xdim1_) += dx1dy1;
+      H(xdim2_, xdim2_) += ddx1;
+      H(ydim2_, ydim2_) += ddy1;
+      H(xdim2_, ydim2_) += dx1dy1;
+      H(ydim2_, xdim2_) += dx1dy1;
+      H(xdim1_, xdim2_) -= ddx1;
+      H(xdim1_, ydim2_) -= dx1dy1;
+      H(ydim1_, xdim2_) -= dx1dy1;
+      H(ydim1_, ydim2_) -= ddy1;
+      H(xdim2_, xdim1_) -= ddx1;
+      H(xdim2_, ydim1_) -= dx1dy1;
+      H(ydim2_, xdim1_) -= dx1dy1;
+      H(ydim2_, ydim1_) -= ddy1;
       break;
     }
     case ILQG_COST_SEMIQUADRATIC: {  // src/semiquadratic_cost.cpp:63-85
@@ -1950,7 +2015,7 @@ int ilqg_setup_next_receding_horizon(ilqg_handle h, const float* x0_in, double t
     for (size_t kk = 1; kk < (size_t)T; kk++)
       if (distance(&in.prob_xs[kk * n]) < distance(&in.prob_xs[first * n])) first = kk;
     // x0_ = Stitch(nearest, x) (:117; concatenated_dynamical_system.h:75-85)
-    const int ego_dim = ego.kind == ILQG_DYN_CAR6D ? 6 : ego.kind == ILQG_DYN_UNICYCLE4D ? 4 : n;
+    const int ego_dim = ego.kind == ILQG_DYN_CAR6D ? 6 : ego.kind == ILQG_DYN_CAR5D ? 5 : ego.kind == ILQG_DYN_UNICYCLE4D ? 4 : n;
     for (int a = 0; a < n; a++) in.x0[a] = a < ego_dim ? in.prob_xs[first * n + a] : x[a];
     // ---- SetUpNextRecedingHorizon :127-186: shift the plan, extend it with zero controls ----
     const size_t kept = (size_t)T - first;

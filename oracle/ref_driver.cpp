@@ -20,6 +20,7 @@
 #include <ilqgames/geometry/draw_shapes.h>
 #include <ilqgames/examples/three_player_intersection_example.h>
 #include <ilqgames/examples/three_player_overtaking_example.h>
+#include <ilqgames/examples/two_player_collision_avoidance_reachability_example.h>
 #include <ilqgames/examples/two_player_collision_example.h>
 #include <ilqgames/solver/augmented_lagrangian_solver.h>
 #include <ilqgames/solver/ilq_solver.h>
@@ -58,7 +59,7 @@ struct ilqg_ref_params {
   float constraint_error_tolerance;
 };
 
-enum { ILQG_REF_INTERSECTION = 0, ILQG_REF_ROUNDABOUT = 1, ILQG_REF_AIR3D = 2, ILQG_REF_OVERTAKING = 3, ILQG_REF_COLLISION = 4 };
+enum { ILQG_REF_INTERSECTION = 0, ILQG_REF_ROUNDABOUT = 1, ILQG_REF_AIR3D = 2, ILQG_REF_OVERTAKING = 3, ILQG_REF_COLLISION = 4, ILQG_REF_REACHABILITY2 = 5 };
 enum { ILQG_REF_ILQ = 0, ILQG_REF_AL = 1 };
 
 }  // extern "C"
@@ -72,6 +73,7 @@ std::shared_ptr<Problem> MakeProblem(int which) {
   else if (which == ILQG_REF_AIR3D) p = std::make_shared<Air3DExample>();
   else if (which == ILQG_REF_OVERTAKING) p = std::make_shared<ThreePlayerOvertakingExample>();
   else if (which == ILQG_REF_COLLISION) p = std::make_shared<TwoPlayerCollisionExample>();
+  else if (which == ILQG_REF_REACHABILITY2) p = std::make_shared<TwoPlayerCollisionAvoidanceReachabilityExample>();
   else return nullptr;
   p->Initialize();
   return p;

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <iostream>
 #include <sstream>
+#include <gflags/gflags.h>  // glog built with gflags support pulls it in; some example sources rely on that
 
 namespace google {
 inline void InitGoogleLogging(const char*) {}

@@ -20,6 +20,7 @@
 #include <ilqgames/examples/roundabout_merging_example.h>
 #include <ilqgames/examples/three_player_intersection_example.h>
 #include <ilqgames/examples/three_player_overtaking_example.h>
+#include <ilqgames/examples/two_player_collision_avoidance_reachability_example.h>
 #include <ilqgames/examples/two_player_collision_example.h>
 #endif
 
@@ -466,6 +467,8 @@ int main(int argc, char** argv) {
   TestProblemDescriptor(MakeProblem<ThreePlayerOvertakingExample>(), "overtaking", 3, 18, 22, 2);
   // src/two_player_collision_example.cpp: FinalTimeCost-wrapped goal costs -> records with a time gate
   TestProblemDescriptor(MakeProblem<TwoPlayerCollisionExample>(), "collision", 2, 12, 22, 6);
+  // src/two_player_collision_avoidance_reachability_example.cpp: SinglePlayerCar5D + SignedDistanceCost
+  TestProblemDescriptor(MakeProblem<TwoPlayerCollisionAvoidanceReachabilityExample>(), "reachability2", 2, 10, 4, 0);
 #endif
   TestILQSolver(problem);
   TestAugmentedLagrangianSolver(problem);

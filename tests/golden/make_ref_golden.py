@@ -62,6 +62,11 @@ CASES = {
     # FinalTimeCost-wrapped goal costs (records with a time gate), n = 12, two players
     "two_player_collision": (R.COLLISION, problems.two_player_collision, problems.two_player_collision_params,
                              lambda: problems.two_player_collision_x0_batch(8, 12)),
+    # SinglePlayerCar5D dynamics and SignedDistanceCost, both players max-over-time, n = 10
+    "two_player_collision_avoidance_reachability": (
+        R.REACHABILITY2, problems.two_player_collision_avoidance_reachability,
+        problems.two_player_collision_avoidance_reachability_params,
+        lambda: problems.two_player_collision_avoidance_reachability_x0_batch(8, 10)),
 }
 
 

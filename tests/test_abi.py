@@ -85,6 +85,12 @@ def test_time_gated_records_fail_loudly_on_the_cuda_library(product_lib, oracle)
     assert product_lib.lib.ilqg_create(C.byref(desc), C.byref(p), 1, 0, C.byref(h)) == -2  # ILQG_ERR_UNSUPPORTED
     assert oracle.lib.ilqg_create(C.byref(desc), C.byref(p), 1, 0, C.byref(h)) == 0
     assert oracle.lib.ilqg_destroy(h) == 0
+    # likewise SinglePlayerCar5D / SignedDistanceCost (oracle-only kinds so far)
+    desc5, _ = problems.two_player_collision_avoidance_reachability()
+    p5 = problems.two_player_collision_avoidance_reachability_params()
+    assert product_lib.lib.ilqg_create(C.byref(desc5), C.byref(p5), 1, 0, C.byref(h)) == -2
+    assert oracle.lib.ilqg_create(C.byref(desc5), C.byref(p5), 1, 0, C.byref(h)) == 0
+    assert oracle.lib.ilqg_destroy(h) == 0
     # a gate on a constraint record is not a thing in the reference (FinalTimeCost wraps Costs)
     bad, _ = problems.three_player_intersection()
     for c in range(bad.num_costs):

@@ -28,6 +28,8 @@ CASES = {
     "air_3d": (problems.air_3d, problems.air_3d_params),
     "three_player_overtaking": (problems.three_player_overtaking, problems.three_player_overtaking_params),
     "two_player_collision": (problems.two_player_collision, problems.two_player_collision_params),
+    "two_player_collision_avoidance_reachability": (problems.two_player_collision_avoidance_reachability,
+                                                    problems.two_player_collision_avoidance_reachability_params),
 }
 
 
