@@ -52,7 +52,7 @@ class CostDesc(C.Structure):
     _fields_ = [("kind", C.c_int32), ("player", C.c_int32), ("arg", C.c_int32),
                 ("is_equality", C.c_int32), ("dim", C.c_int32 * 4), ("flag", C.c_int32),
                 ("polyline", C.c_int32), ("weight", C.c_float), ("value", C.c_float),
-                ("active_from", C.c_double)]
+                ("active_from", C.c_double), ("group", C.c_int32), ("group_is_min", C.c_int32)]
 
 
 class ProblemDesc(C.Structure):

@@ -154,6 +154,7 @@ int BuildDeviceDesc(const ilqg_problem_desc& h, DevDesc* d, ilqg_layout* lo, std
     if (cd.player < 0 || cd.player >= d->N || cd.arg >= d->N) return ILQG_ERR_INVALID_ARGUMENT;
     // FinalTimeCost's time gate has no device implementation yet (include/ilqg.h: active_from)
     if (cd.active_from != 0.0) return ILQG_ERR_UNSUPPORTED;
+    if (cd.group != 0) return ILQG_ERR_UNSUPPORTED;  // ExtremeValueCost: oracle only so far
     if (cd.arg >= 0) has[cd.player][cd.arg] = true;
   }
   d->num_pairs = 0;

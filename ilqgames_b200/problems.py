@@ -75,9 +75,10 @@ class DescBuilder:
 
     # costs ------------------------------------------------------------------
     def _rec(self, player, category, kind, arg=-1, dims=(0,), weight=1.0, value=0.0, flag=0,
-             polyline=-1, is_equality=0, active_from=0.0):
+             polyline=-1, is_equality=0, active_from=0.0, group=0, group_is_min=0):
         r = abi.CostDesc()
         r.active_from = active_from   # FinalTimeCost threshold (0 = always)
+        r.group, r.group_is_min = group, int(group_is_min)   # ExtremeValueCost membership (0 = none)
         r.kind, r.player, r.arg, r.is_equality = kind, player, arg, is_equality
         for k in range(4):
             r.dim[k] = dims[k] if k < len(dims) else 0
@@ -542,6 +543,63 @@ def two_player_collision_avoidance_reachability_x0_batch(batch: int, seed: int) 
     out = np.tile(x0, (batch, 1))
     for o in (0, 5):
         out[:, o:o + 2] += rng.uniform(-1.0, 1.0, size=(batch, 2)).astype(F)
+        out[:, o + 2] += rng.uniform(-0.1, 0.1, size=batch).astype(F)
+        out[:, o + 4] *= rng.uniform(0.8, 1.2, size=batch).astype(F)
+    return out.astype(F)
+
+
+# --------------------------------------------------------------------------
+# ThreePlayerCollisionAvoidanceReachabilityExample
+# (src/three_player_collision_avoidance_reachability_example.cpp)
+# --------------------------------------------------------------------------
+def three_player_collision_avoidance_reachability(num_time_steps: int = 100, time_step: float = 0.1,
+                                                  d0: float = 5.0, v0: float = 5.0, buffer: float = 3.0):
+    """Returns (desc, x0).  3x SinglePlayerCar5D heading for the origin, n = 15; each player's cost
+    is the max over time of an ExtremeValueCost (max of two SignedDistanceCosts to the other cars)
+    plus a control cost, with box constraints on both controls.  CPU oracle only for now."""
+    b = DescBuilder(num_time_steps, time_step)
+    kOmegaMax, kAMax, kControlCostWeight = 1.0, 0.1, 0.1
+    for _ in range(3):
+        b.add_player(2, 0.0, 0.0, abi.COST_MAX)                            # SetMaxOverTime (:216-218)
+    offs = [b.add_subsystem(abi.DYN_CAR5D, 5, i, [4.0]) for i in range(3)]
+    pos = [(o + 0, o + 1) for o in offs]
+    # ExtremeValueCost({a, b}, kTakeMin = false) per player (:187-213): one group per player
+    members = {0: ((0, 1), (0, 2)), 1: ((0, 1), (1, 2)), 2: ((1, 2), (0, 2))}
+    for i in range(3):
+        for (a, c) in members[i]:
+            b.state_cost(i, abi.COST_SIGNED_DISTANCE, dims=pos[a] + pos[c], weight=1.0, value=buffer, flag=1,
+                         group=i + 1, group_is_min=0)
+        b.control_cost(i, i, abi.COST_QUADRATIC, dims=(-1,), weight=kControlCostWeight, value=0.0)   # :135-139
+        for dim, bound in ((0, kOmegaMax), (1, kAMax)):                                              # :141-185
+            b.control_constraint(i, i, abi.CONSTRAINT_SINGLE_DIMENSION, dims=(dim,), value=bound, flag=1)
+            b.control_constraint(i, i, abi.CONSTRAINT_SINGLE_DIMENSION, dims=(dim,), value=-bound, flag=0)
+    x0 = np.zeros(b.d.xdim, dtype=F)                                       # :106-124, double arithmetic narrowed on store
+    kAnglePerturbation = float(F(0.1))
+    starts = [(d0, 0.0, -math.pi + kAnglePerturbation),
+              (-0.5 * d0, 0.5 * math.sqrt(3.0) * d0, -math.pi / 3.0 + kAnglePerturbation),
+              (-0.5 * d0, -0.5 * math.sqrt(3.0) * d0, math.pi / 3.0 + kAnglePerturbation)]
+    for i, (x, y, th) in enumerate(starts):
+        x0[offs[i] + 0], x0[offs[i] + 1], x0[offs[i] + 2], x0[offs[i] + 4] = x, y, th, v0
+    return b.build(), x0
+
+
+def three_player_collision_avoidance_reachability_params(**overrides) -> abi.SolverParams:
+    """SolverParams of exec/three_player_collision_avoidance_reachability_example/main.cpp:76-79,
+    114-121 (its two regularization fields are dead)."""
+    base = dict(max_backtracking_steps=100, linesearch=1, expected_decrease_fraction=0.1,
+                initial_alpha_scaling=0.1, convergence_tolerance=0.01)
+    base.update(overrides)
+    return abi.SolverParams.defaults(**base)
+
+
+def three_player_collision_avoidance_reachability_x0_batch(batch: int, seed: int) -> np.ndarray:
+    """Synthetic initial states: the example's, positions moved U(-0.5, 0.5) m, headings
+    U(-0.1, 0.1) rad, speeds scaled U(0.8, 1.2)."""
+    _, x0 = three_player_collision_avoidance_reachability()
+    rng = np.random.default_rng(seed)
+    out = np.tile(x0, (batch, 1))
+    for o in (0, 5, 10):
+        out[:, o:o + 2] += rng.uniform(-0.5, 0.5, size=(batch, 2)).astype(F)
         out[:, o + 2] += rng.uniform(-0.1, 0.1, size=batch).astype(F)
         out[:, o + 4] *= rng.uniform(0.8, 1.2, size=batch).astype(F)
     return out.astype(F)

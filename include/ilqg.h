@@ -124,6 +124,13 @@ typedef struct {
    * constraints).  ilqg_create of the CUDA library answers ILQG_ERR_UNSUPPORTED for a nonzero
    * value (no device implementation yet); the CPU oracle implements it. */
   double active_from;
+  /* ExtremeValueCost(costs, is_min) (include/ilqgames/cost/extreme_value_cost.h:54-80,
+   * src/extreme_value_cost.cpp:50-84): consecutive records of one player with the same group > 0
+   * are its sub-costs, in order; whenever the cost is evaluated or quadraticized only the member
+   * with the largest (group_is_min: smallest) value counts, the first one on ties.  0 = a plain
+   * record.  CPU oracle only so far (CUDA: ILQG_ERR_UNSUPPORTED). */
+  int32_t group;
+  int32_t group_is_min;
 } ilqg_cost_desc;
 
 /* PlayerCost::CostStructure, include/ilqgames/cost/player_cost.h:105-111 */

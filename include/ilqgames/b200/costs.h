@@ -10,6 +10,8 @@
 #include <ilqg.h>
 #include <ilqgames/b200/core.h>
 
+#include <cstring>
+
 namespace ilqgames {
 
 // ---- include/ilqgames/geometry/line_segment2.h:52-96: the accessors host code uses to place
@@ -84,6 +86,7 @@ class Polyline2 {
 // Collects records and polylines while a Problem describes itself.
 struct DescribeContext {
   ilqg_problem_desc* desc;
+  int num_groups = 0;  // ExtremeValueCost objects described so far (their members share a group id)
   // identical point lists share one table entry (the four roundabout players reuse lanes)
   int AddPolyline(const Polyline2& polyline) {
     const PointList2& pts = polyline.Points();
@@ -117,6 +120,15 @@ class Cost {
   float Weight() const { return weight_; }
   // fills kind / dim / flag / polyline / weight / value; the caller sets player, arg
   virtual bool Describe(ilqg_cost_desc* /*out*/, DescribeContext* /*ctx*/) const { return false; }
+  // every record this cost contributes, in order: one for a plain cost, its members for a composite
+  virtual bool DescribeAll(std::vector<ilqg_cost_desc>* out, DescribeContext* ctx) const {
+    ilqg_cost_desc rec;
+    std::memset(&rec, 0, sizeof(rec));
+    rec.polyline = -1;
+    if (!Describe(&rec, ctx)) return false;
+    out->push_back(rec);
+    return true;
+  }
 
  protected:
   explicit Cost(float weight, const std::string& name = "") : name_(name), weight_(weight) {}
@@ -309,6 +321,31 @@ class FinalTimeCost : public Cost {
  private:
   const std::shared_ptr<const Cost> cost_;
   const Time threshold_time_;
+};
+
+// include/ilqgames/cost/extreme_value_cost.h:54-80, src/extreme_value_cost.cpp:50-84: the largest
+// (is_min: smallest) of several costs -- its members' records, tied together by a group id.  Only
+// the CPU oracle implements groups so far.
+class ExtremeValueCost : public Cost {
+ public:
+  ExtremeValueCost(const std::vector<std::shared_ptr<const Cost>>& costs, bool is_min, const std::string& name = "")
+      : Cost(1.0, name), is_min_(is_min), costs_(costs) {}
+  bool DescribeAll(std::vector<ilqg_cost_desc>* out, DescribeContext* ctx) const override {
+    if (costs_.empty()) return false;
+    const int group = ++ctx->num_groups;
+    for (const auto& cost : costs_) {
+      std::vector<ilqg_cost_desc> member;
+      if (!cost->DescribeAll(&member, ctx) || member.size() != 1 || member[0].group != 0) return false;  // no nesting
+      member[0].group = group;
+      member[0].group_is_min = is_min_;
+      out->push_back(member[0]);
+    }
+    return true;
+  }
+
+ private:
+  const bool is_min_;
+  const std::vector<std::shared_ptr<const Cost>> costs_;
 };
 
 // Costs the in-scope example sources include but never add to a player: constructible, not

@@ -128,15 +128,23 @@ inline bool DescribeProblem(const Problem& problem, ilqg_problem_desc* desc) {
     desc->num_costs++;
     return true;
   };
+  // a Cost may contribute several records (ExtremeValueCost: one per member)
+  auto push_cost = [&](int player, int arg, const Cost& cost) {
+    std::vector<ilqg_cost_desc> records;
+    if (!cost.DescribeAll(&records, &ctx)) return false;
+    for (const ilqg_cost_desc& described : records)
+      if (!push(player, arg, false, [&](ilqg_cost_desc* r) { *r = described; return true; })) return false;
+    return true;
+  };
   for (size_t ii = 0; ii < pcs.size(); ii++) {
     const PlayerCost& pc = pcs[ii];
     desc->state_regularization[ii] = pc.StateRegularization();
     desc->control_regularization[ii] = pc.ControlRegularization();
     desc->cost_structure[ii] = pc.CostStructure();
     for (const auto& c : pc.StateCosts())
-      if (!push((int)ii, -1, false, [&](ilqg_cost_desc* r) { return c->Describe(r, &ctx); })) return false;
+      if (!push_cost((int)ii, -1, *c)) return false;
     for (const auto& pr : pc.ControlCosts())
-      if (!push((int)ii, pr.first, false, [&](ilqg_cost_desc* r) { return pr.second->Describe(r, &ctx); })) return false;
+      if (!push_cost((int)ii, pr.first, *pr.second)) return false;
     for (const auto& c : pc.StateConstraints())
       if (!push((int)ii, -1, c->IsEquality(), [&](ilqg_cost_desc* r) { return c->Describe(r, &ctx); })) return false;
     for (const auto& pr : pc.ControlConstraints())

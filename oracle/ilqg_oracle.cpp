@@ -268,6 +268,10 @@ int BuildProblem(const ilqg_problem_desc* desc, const ilqg_solver_params* params
   for (int c = 0; c < d.num_costs; c++) {
     pr->constraint_slot[c] = IsConstraintKind(d.costs[c].kind) ? pr->num_constraints++ : -1;
     if (pr->constraint_slot[c] >= 0 && d.costs[c].active_from != 0.0) return ILQG_ERR_INVALID_ARGUMENT;
+    // ExtremeValueCost members: plain, ungated costs
+    if (d.costs[c].group < 0) return ILQG_ERR_INVALID_ARGUMENT;
+    if (d.costs[c].group > 0 && (pr->constraint_slot[c] >= 0 || d.costs[c].active_from != 0.0))
+      return ILQG_ERR_INVALID_ARGUMENT;
   }
   UpdateCostGates(pr, d.initial_time);
 
@@ -871,6 +875,32 @@ void QuadraticizeRecord(const Problem& pr, const ilqg_cost_desc& cd, const real*
 #undef H
 }
 
+// ExtremeValueCost::ExtremeCost, src/extreme_value_cost.cpp:64-84: of the group of records that
+// starts at `first` (consecutive records of one player and argument with the same group id) the
+// member with the largest (group_is_min: smallest) value, the first one on ties.  *next = one past
+// the group.  A NaN member never wins; if all are NaN the reference dereferences an unset pointer
+// -- the first member stands in here.
+int ExtremeMember(const Problem& pr, int first, const real* x, const real* u, int* next, real* value_out) {
+  const ilqg_problem_desc& d = pr.d;
+  const ilqg_cost_desc& head = d.costs[first];
+  const bool is_min = head.group_is_min != 0;
+  real extreme = is_min ? kInfinity : -kInfinity;
+  int chosen = first, c = first;
+  for (; c < d.num_costs; c++) {
+    const ilqg_cost_desc& cd = d.costs[c];
+    if (cd.group != head.group || cd.player != head.player || cd.arg != head.arg) break;
+    const real value = cd.arg < 0 ? EvaluateRecord(pr, cd, x, pr.n)
+                                  : EvaluateRecord(pr, cd, u + pr.uoff[cd.arg], d.udim[cd.arg]);
+    if ((is_min && value < extreme) || (!is_min && value > extreme)) {
+      extreme = value;
+      chosen = c;
+    }
+  }
+  *next = c;
+  if (value_out) *value_out = extreme;
+  return chosen;
+}
+
 // PlayerCost::Quadraticize / QuadraticizeControlCosts, src/player_cost.cpp:194-225,
 // as dispatched by ILQSolver::ComputeCostQuadraticization (src/ilq_solver.cpp:471-490).
 // Writes Q_i, l_i (all players) and R_p, r_p (all pairs) for time step kk.
@@ -897,7 +927,10 @@ void QuadraticizeStep(const Problem& pr, const Instance& in, int kk, const real*
     // The (i,i) block always exists in every in-scope example.
     for (int a = 0; a < mj; a++) Rp[a * mj + a] = d.control_regularization[i];
   }
-  for (int c = 0; c < d.num_costs; c++) {
+  for (int c0 = 0, next = 0; c0 < d.num_costs; c0 = next) {
+    next = c0 + 1;
+    // an ExtremeValueCost quadraticizes its extreme member only (src/extreme_value_cost.cpp:56-62)
+    const int c = d.costs[c0].group > 0 ? ExtremeMember(pr, c0, x, u, &next, nullptr) : c0;
     const ilqg_cost_desc& cd = d.costs[c];
     if (kk < pr.first_step[c]) continue;  // FinalTimeCost::Quadraticize returns before its cost's
     const int i = cd.player;
@@ -922,7 +955,11 @@ void QuadraticizeStep(const Problem& pr, const Instance& in, int kk, const real*
 real EvaluatePlayerCost(const Problem& pr, int i, int kk, const real* x, const real* u) {
   real total = 0.0;
   const ilqg_problem_desc& d = pr.d;
-  for (int c = 0; c < d.num_costs; c++) {
+  for (int c0 = 0, next = 0; c0 < d.num_costs; c0 = next) {
+    next = c0 + 1;
+    if (d.costs[c0].player != i) continue;
+    // ExtremeValueCost::Evaluate: the extreme member's value (src/extreme_value_cost.cpp:50-54)
+    const int c = d.costs[c0].group > 0 ? ExtremeMember(pr, c0, x, u, &next, nullptr) : c0;
     const ilqg_cost_desc& cd = d.costs[c];
     if (cd.player != i || pr.constraint_slot[c] >= 0) continue;
     if (kk < pr.first_step[c]) continue;  // FinalTimeCost::Evaluate is 0 before its threshold

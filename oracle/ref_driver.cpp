@@ -18,6 +18,7 @@
 #include <ilqgames/examples/roundabout_lane_center.h>
 #include <ilqgames/examples/roundabout_merging_example.h>
 #include <ilqgames/geometry/draw_shapes.h>
+#include <ilqgames/examples/three_player_collision_avoidance_reachability_example.h>
 #include <ilqgames/examples/three_player_intersection_example.h>
 #include <ilqgames/examples/three_player_overtaking_example.h>
 #include <ilqgames/examples/two_player_collision_avoidance_reachability_example.h>
@@ -59,7 +60,7 @@ struct ilqg_ref_params {
   float constraint_error_tolerance;
 };
 
-enum { ILQG_REF_INTERSECTION = 0, ILQG_REF_ROUNDABOUT = 1, ILQG_REF_AIR3D = 2, ILQG_REF_OVERTAKING = 3, ILQG_REF_COLLISION = 4, ILQG_REF_REACHABILITY2 = 5 };
+enum { ILQG_REF_INTERSECTION = 0, ILQG_REF_ROUNDABOUT = 1, ILQG_REF_AIR3D = 2, ILQG_REF_OVERTAKING = 3, ILQG_REF_COLLISION = 4, ILQG_REF_REACHABILITY2 = 5, ILQG_REF_REACHABILITY3 = 6 };
 enum { ILQG_REF_ILQ = 0, ILQG_REF_AL = 1 };
 
 }  // extern "C"
@@ -74,6 +75,7 @@ std::shared_ptr<Problem> MakeProblem(int which) {
   else if (which == ILQG_REF_OVERTAKING) p = std::make_shared<ThreePlayerOvertakingExample>();
   else if (which == ILQG_REF_COLLISION) p = std::make_shared<TwoPlayerCollisionExample>();
   else if (which == ILQG_REF_REACHABILITY2) p = std::make_shared<TwoPlayerCollisionAvoidanceReachabilityExample>();
+  else if (which == ILQG_REF_REACHABILITY3) p = std::make_shared<ThreePlayerCollisionAvoidanceReachabilityExample>();
   else return nullptr;
   p->Initialize();
   return p;

@@ -18,6 +18,7 @@
 // variant only where /root/reference exists)
 #include <ilqgames/examples/air_3d_example.h>
 #include <ilqgames/examples/roundabout_merging_example.h>
+#include <ilqgames/examples/three_player_collision_avoidance_reachability_example.h>
 #include <ilqgames/examples/three_player_intersection_example.h>
 #include <ilqgames/examples/three_player_overtaking_example.h>
 #include <ilqgames/examples/two_player_collision_avoidance_reachability_example.h>
@@ -469,6 +470,8 @@ int main(int argc, char** argv) {
   TestProblemDescriptor(MakeProblem<TwoPlayerCollisionExample>(), "collision", 2, 12, 22, 6);
   // src/two_player_collision_avoidance_reachability_example.cpp: SinglePlayerCar5D + SignedDistanceCost
   TestProblemDescriptor(MakeProblem<TwoPlayerCollisionAvoidanceReachabilityExample>(), "reachability2", 2, 10, 4, 0);
+  // src/three_player_collision_avoidance_reachability_example.cpp: ExtremeValueCost -> grouped records
+  TestProblemDescriptor(MakeProblem<ThreePlayerCollisionAvoidanceReachabilityExample>(), "reachability3", 3, 15, 21, 0);
 #endif
   TestILQSolver(problem);
   TestAugmentedLagrangianSolver(problem);

@@ -67,6 +67,11 @@ CASES = {
         R.REACHABILITY2, problems.two_player_collision_avoidance_reachability,
         problems.two_player_collision_avoidance_reachability_params,
         lambda: problems.two_player_collision_avoidance_reachability_x0_batch(8, 10)),
+    # ExtremeValueCost (a group of records), box constraints on the controls, n = 15
+    "three_player_collision_avoidance_reachability": (
+        R.REACHABILITY3, problems.three_player_collision_avoidance_reachability,
+        problems.three_player_collision_avoidance_reachability_params,
+        lambda: problems.three_player_collision_avoidance_reachability_x0_batch(8, 15)),
 }
 
 

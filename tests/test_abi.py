@@ -91,6 +91,28 @@ def test_time_gated_records_fail_loudly_on_the_cuda_library(product_lib, oracle)
     assert product_lib.lib.ilqg_create(C.byref(desc5), C.byref(p5), 1, 0, C.byref(h)) == -2
     assert oracle.lib.ilqg_create(C.byref(desc5), C.byref(p5), 1, 0, C.byref(h)) == 0
     assert oracle.lib.ilqg_destroy(h) == 0
+    # ... and ExtremeValueCost groups; a group member that is a constraint or gated is invalid
+    desc3, _ = problems.three_player_collision_avoidance_reachability()
+    assert sorted({desc3.costs[c].group for c in range(desc3.num_costs)}) == [0, 1, 2, 3]
+    assert oracle.lib.ilqg_create(C.byref(desc3), C.byref(p5), 1, 0, C.byref(h)) == 0
+    assert oracle.lib.ilqg_destroy(h) == 0
+    for c in range(desc3.num_subsystems):
+        desc3.subsystems[c].kind = abi.DYN_UNICYCLE4D      # leave only the groups for the CUDA parser to object to
+    desc3.xdim = 12
+    for c in range(desc3.num_subsystems):
+        desc3.subsystems[c].x_offset = 4 * c
+    for c in range(desc3.num_costs):
+        if desc3.costs[c].kind == abi.COST_SIGNED_DISTANCE:
+            desc3.costs[c].kind = abi.COST_PROXIMITY
+            for q in range(4):
+                desc3.costs[c].dim[q] = desc3.costs[c].dim[q] // 5 * 4 + desc3.costs[c].dim[q] % 5
+    assert product_lib.lib.ilqg_create(C.byref(desc3), C.byref(p5), 1, 0, C.byref(h)) == -2
+    for c in range(desc3.num_costs):
+        desc3.costs[c].group = 0
+    rc = product_lib.lib.ilqg_create(C.byref(desc3), C.byref(p5), 1, 0, C.byref(h))
+    assert rc in (-4, 0)   # parses: "no device" on the CPU-only builder, a handle on a GPU box
+    if rc == 0:
+        assert product_lib.lib.ilqg_destroy(h) == 0
     # a gate on a constraint record is not a thing in the reference (FinalTimeCost wraps Costs)
     bad, _ = problems.three_player_intersection()
     for c in range(bad.num_costs):

@@ -33,7 +33,8 @@ def _build(tmp_path, lib_path, dropin=False):
             os.path.join(REFERENCE, "src", f + ".cpp") for f in (
                 "three_player_intersection_example", "roundabout_merging_example", "roundabout_lane_center",
                 "initialize_along_route", "air_3d_example", "draw_shapes", "three_player_overtaking_example",
-                "two_player_collision_example", "two_player_collision_avoidance_reachability_example")]
+                "two_player_collision_example", "two_player_collision_avoidance_reachability_example",
+                "three_player_collision_avoidance_reachability_example")]
     subprocess.run(cmd, check=True)
     return exe
 
@@ -181,7 +182,8 @@ def test_reference_example_source_drops_in_unchanged(oracle, tmp_path):
     for tag, build in (("roundabout", problems.roundabout_merging), ("air3d", problems.air_3d),
                        ("overtaking", problems.three_player_overtaking),
                        ("collision", problems.two_player_collision),
-                       ("reachability2", problems.two_player_collision_avoidance_reachability)):
+                       ("reachability2", problems.two_player_collision_avoidance_reachability),
+                       ("reachability3", problems.three_player_collision_avoidance_reachability)):
         desc, x0 = build()
         mine = np.frombuffer(bytes(desc), dtype=np.uint32)
         theirs = got["desc_" + tag].view(np.uint32)

@@ -30,6 +30,8 @@ CASES = {
     "two_player_collision": (problems.two_player_collision, problems.two_player_collision_params),
     "two_player_collision_avoidance_reachability": (problems.two_player_collision_avoidance_reachability,
                                                     problems.two_player_collision_avoidance_reachability_params),
+    "three_player_collision_avoidance_reachability": (problems.three_player_collision_avoidance_reachability,
+                                                      problems.three_player_collision_avoidance_reachability_params),
 }
 
 
@@ -293,7 +295,8 @@ def test_receding_horizon_argument_errors(oracle):
         hc.setup_next_receding_horizon(problems.three_player_intersection_x0_batch(1, 1), 0.25, 0.1)
 
 
-@pytest.mark.parametrize("name", ["three_player_intersection", "air_3d"])
+@pytest.mark.parametrize("name", ["three_player_intersection", "air_3d",
+                                  "three_player_collision_avoidance_reachability"])
 def test_oracle_reproduces_reference_augmented_lagrangian(oracle, name):
     """AugmentedLagrangianSolver::Solve (src/augmented_lagrangian_solver.cpp:72-210): final
     operating point and strategies, multipliers, mu, NumIterates, success."""
