@@ -606,6 +606,92 @@ def three_player_collision_avoidance_reachability_x0_batch(batch: int, seed: int
 
 
 # --------------------------------------------------------------------------
+# OnePlayerReachabilityExample (src/one_player_reachability_example.cpp)
+# --------------------------------------------------------------------------
+def one_player_reachability(num_time_steps: int = 100, time_step: float = 0.1, px0: float = 1.75,
+                            py0: float = 1.75, theta0: float = 0.0):
+    """Returns (desc, x0).  ONE player: a SinglePlayerDubinsCar (n = 3, m = 1) avoiding a disc,
+    max-over-time signed distance to its 10-gon boundary, turn rate boxed by two constraints.
+    CPU oracle only for now (ILQG_DYN_DUBINS has no device implementation yet)."""
+    b = DescBuilder(num_time_steps, time_step)
+    kTargetRadius, kOmegaMax, kOmegaCostWeight, kSpeed = 2.0, 1.0, 0.1, 1.0
+    b.add_player(1, 0.0, 0.0, abi.COST_MAX)                                # SetMaxOverTime
+    b.add_subsystem(abi.DYN_DUBINS, 3, 0, [kSpeed])
+    circle = b.add_polyline(draw_circle((0.0, 0.0), kTargetRadius, 10))
+    # Polyline2SignedDistanceCost(circle, dims, kAvoid, "Target"): as in Air3DExample the bool lands
+    # in `float nominal` (1.0) and the string literal in `bool oriented_same_as_polyline` (true)
+    b.state_cost(0, abi.COST_POLYLINE2_SIGNED_DISTANCE, dims=(0, 1), polyline=circle, value=1.0, flag=1)
+    b.control_cost(0, 0, abi.COST_QUADRATIC, dims=(-1,), weight=kOmegaCostWeight, value=0.0)
+    b.control_constraint(0, 0, abi.CONSTRAINT_SINGLE_DIMENSION, dims=(0,), value=kOmegaMax, flag=1)
+    b.control_constraint(0, 0, abi.CONSTRAINT_SINGLE_DIMENSION, dims=(0,), value=-kOmegaMax, flag=0)
+    x0 = np.array([px0, py0, theta0], dtype=F)
+    return b.build(), x0
+
+
+def one_player_reachability_params(**overrides) -> abi.SolverParams:
+    """SolverParams of exec/one_player_reachability_example/main.cpp (same flags as the other
+    reachability executables)."""
+    base = dict(max_backtracking_steps=100, linesearch=1, expected_decrease_fraction=0.1,
+                initial_alpha_scaling=0.1, convergence_tolerance=0.01)
+    base.update(overrides)
+    return abi.SolverParams.defaults(**base)
+
+
+def one_player_reachability_x0_batch(batch: int, seed: int) -> np.ndarray:
+    """Synthetic initial states: positions U(-4, 4)^2 outside the disc's radius + 0.5, headings U(-pi, pi)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < batch:
+        x, y = rng.uniform(-4.0, 4.0, size=2)
+        if math.hypot(x, y) > 2.5:
+            out.append((x, y, rng.uniform(-math.pi, math.pi)))
+    return np.array(out, dtype=F)
+
+
+# --------------------------------------------------------------------------
+# DubinsOriginExample (src/dubins_origin_example.cpp)
+# --------------------------------------------------------------------------
+def dubins_origin(num_time_steps: int = 100, time_step: float = 0.1):
+    """Returns (desc, x0).  2x SinglePlayerDubinsCar, n = 6, m = (1, 1): P1 wants P2 at the origin,
+    P2 wants to be where P1 is (QuadraticDifferenceCost).  Its executable runs WITHOUT the
+    linesearch (SolverParams::linesearch = false, SURVEY Q9).  CPU oracle only for now."""
+    b = DescBuilder(num_time_steps, time_step)
+    kOmegaCostWeight, kAttractionCostWeight, kGoalCostWeight, kSpeed = 100.0, 10.0, 10.0, 1.0
+    for _ in range(2):
+        b.add_player(1, 0.0, 0.0)
+    offs = [b.add_subsystem(abi.DYN_DUBINS, 3, i, [kSpeed]) for i in range(2)]
+    p1, p2 = (offs[0] + 0, offs[0] + 1), (offs[1] + 0, offs[1] + 1)
+    b.state_cost(1, abi.COST_QUADRATIC_DIFFERENCE, dims=p1 + p2, weight=kAttractionCostWeight, flag=2)   # :124-129
+    b.control_cost(0, 0, abi.COST_QUADRATIC, dims=(0,), weight=kOmegaCostWeight, value=0.0)               # :132-138
+    b.control_cost(1, 1, abi.COST_QUADRATIC, dims=(0,), weight=kOmegaCostWeight, value=0.0)
+    b.state_cost(0, abi.COST_QUADRATIC, dims=(p2[0],), weight=kGoalCostWeight, value=0.0)                 # :141-146
+    b.state_cost(0, abi.COST_QUADRATIC, dims=(p2[1],), weight=kGoalCostWeight, value=0.0)
+    x0 = np.zeros(b.d.xdim, dtype=F)                                       # :70-75, :107-114
+    x0[offs[0] + 1], x0[offs[0] + 2] = -10.0, F(math.pi - 0.01)
+    x0[offs[1] + 1], x0[offs[1] + 2] = 10.0, F(1.5 * math.pi)
+    return b.build(), x0
+
+
+def dubins_origin_params(**overrides) -> abi.SolverParams:
+    """SolverParams of exec/dubins_origin_example/main.cpp:72-75,110-114: no linesearch."""
+    base = dict(max_backtracking_steps=100, linesearch=0, expected_decrease_fraction=0.1,
+                initial_alpha_scaling=0.1, convergence_tolerance=0.1)
+    base.update(overrides)
+    return abi.SolverParams.defaults(**base)
+
+
+def dubins_origin_x0_batch(batch: int, seed: int) -> np.ndarray:
+    """Synthetic initial states: the example's, positions moved U(-2, 2) m, headings U(-0.3, 0.3) rad."""
+    _, x0 = dubins_origin()
+    rng = np.random.default_rng(seed)
+    out = np.tile(x0, (batch, 1))
+    for o in (0, 3):
+        out[:, o:o + 2] += rng.uniform(-2.0, 2.0, size=(batch, 2)).astype(F)
+        out[:, o + 2] += rng.uniform(-0.3, 0.3, size=batch).astype(F)
+    return out.astype(F)
+
+
+# --------------------------------------------------------------------------
 # Air3DExample
 # --------------------------------------------------------------------------
 def draw_circle(center, radius, num_segments):

@@ -76,8 +76,10 @@ enum {
   ILQG_DYN_CAR6D = 1,      /* params[0] = inter-axle distance                  */
   ILQG_DYN_UNICYCLE4D = 2,
   ILQG_DYN_AIR3D = 3,      /* params[0] = evader speed, params[1] = pursuer    */
-  ILQG_DYN_CAR5D = 4       /* single_player_car_5d.h:102-147; params[0] = inter-axle distance.
+  ILQG_DYN_CAR5D = 4,      /* single_player_car_5d.h:102-147; params[0] = inter-axle distance.
                             * CPU oracle only so far: the CUDA library answers ILQG_ERR_UNSUPPORTED */
+  ILQG_DYN_DUBINS = 5      /* single_player_dubins_car.h:56-118: (x, y, theta), control = turn rate,
+                            * params[0] = constant speed.  CPU oracle only so far as well */
 };
 
 typedef struct {
@@ -103,8 +105,11 @@ enum {
   ILQG_COST_POLYLINE2_SIGNED_DISTANCE = 6,/* dim[0..1], polyline, value=nominal, flag=oriented_same_as_polyline */
   ILQG_CONSTRAINT_PROXIMITY = 7,          /* dim[0..3], value=threshold, flag=keep_within      */
   ILQG_CONSTRAINT_SINGLE_DIMENSION = 8,   /* dim[0], value=threshold, flag=keep_below          */
-  ILQG_COST_SIGNED_DISTANCE = 9           /* src/signed_distance_cost.cpp:50-112: dim[0..3]=x1,y1,x2,y2,
+  ILQG_COST_SIGNED_DISTANCE = 9,          /* src/signed_distance_cost.cpp:50-112: dim[0..3]=x1,y1,x2,y2,
                                            * value=nominal, flag=less_is_positive (weight unused).
+                                           * CPU oracle only so far (CUDA: ILQG_ERR_UNSUPPORTED) */
+  ILQG_COST_QUADRATIC_DIFFERENCE = 10     /* src/quadratic_difference_cost.cpp:50-91: 0.5 w sum (in[a_k] - in[b_k])^2
+                                           * over flag = 1 or 2 pairs, dim[0..1] = a, dim[2..3] = b.
                                            * CPU oracle only so far (CUDA: ILQG_ERR_UNSUPPORTED) */
 };
 

@@ -199,6 +199,31 @@ class ProximityCost : public TimeInvariantCost {
   const Dimension xidx1_, yidx1_, xidx2_, yidx2_;
 };
 
+// src/quadratic_difference_cost.cpp:50-91: half the weighted squared difference of two sets of
+// dimensions (one or two pairs fit a record).  ILQG_COST_QUADRATIC_DIFFERENCE: CPU oracle only so far.
+class QuadraticDifferenceCost : public TimeInvariantCost {
+ public:
+  QuadraticDifferenceCost(float weight, const std::vector<Dimension>& dims1, const std::vector<Dimension>& dims2,
+                          const std::string& name = "")
+      : TimeInvariantCost(weight, name), dims1_(dims1), dims2_(dims2) {
+    CHECK_EQ(dims1_.size(), dims2_.size());
+  }
+  bool Describe(ilqg_cost_desc* out, DescribeContext*) const override {
+    if (dims1_.empty() || dims1_.size() > 2) return false;
+    out->kind = ILQG_COST_QUADRATIC_DIFFERENCE;
+    for (size_t k = 0; k < dims1_.size(); k++) {
+      out->dim[k] = dims1_[k];
+      out->dim[2 + k] = dims2_[k];
+    }
+    out->flag = (int32_t)dims1_.size();
+    out->weight = weight_;
+    return true;
+  }
+
+ private:
+  const std::vector<Dimension> dims1_, dims2_;
+};
+
 // src/signed_distance_cost.cpp:50-112 (include/ilqgames/cost/signed_distance_cost.h:52-88):
 // nominal minus the distance between two positions, unweighted.  ILQG_COST_SIGNED_DISTANCE, which
 // only the CPU oracle implements so far.  The defaulted bool sits before the name as in the

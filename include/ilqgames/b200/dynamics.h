@@ -78,6 +78,24 @@ class SinglePlayerCar5D : public SinglePlayerDynamicalSystem {
   const float inter_axle_distance_;
 };
 
+// include/ilqgames/dynamics/single_player_dubins_car.h:56-118; state (x, y, theta) at constant
+// speed, control = turn rate.  ILQG_DYN_DUBINS: CPU oracle only so far.
+class SinglePlayerDubinsCar : public SinglePlayerDynamicalSystem {
+ public:
+  SinglePlayerDubinsCar(float v) : SinglePlayerDynamicalSystem(kNumXDims, kNumUDims), v_(v) { CHECK_GT(v_, 0.0); }
+  std::vector<Dimension> PositionDimensions() const override { return {kPxIdx, kPyIdx}; }
+  bool Describe(ilqg_subsystem_desc* out) const override {
+    out->kind = ILQG_DYN_DUBINS;
+    out->params[0] = v_;
+    return true;
+  }
+  static constexpr Dimension kNumXDims = 3, kPxIdx = 0, kPyIdx = 1, kThetaIdx = 2;
+  static constexpr Dimension kNumUDims = 1, kOmegaIdx = 0;
+
+ private:
+  const float v_;
+};
+
 // include/ilqgames/dynamics/multi_player_integrable_system.h:58-140
 class MultiPlayerIntegrableSystem {
  public:

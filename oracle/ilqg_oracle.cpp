@@ -347,6 +347,13 @@ void EvaluateDynamics(const Problem& pr, const real* x, const real* u, real* xdo
         xd[4] = us[1];
         break;
       }
+      case ILQG_DYN_DUBINS: {  // single_player_dubins_car.h:93-101
+        const real v = sd.params[0];
+        xd[0] = v * std::cos(xs[2]);
+        xd[1] = v * std::sin(xs[2]);
+        xd[2] = us[0];
+        break;
+      }
       case ILQG_DYN_UNICYCLE4D: {  // single_player_unicycle_4d.h:90-99
         xd[0] = xs[3] * std::cos(xs[2]);
         xd[1] = xs[3] * std::sin(xs[2]);
@@ -464,6 +471,15 @@ void Linearize(const Problem& pr, const real* x, const real* u, real* A, real* B
         BB(4, 1) = kTimeStep;
         break;
       }
+      case ILQG_DYN_DUBINS: {  // single_player_dubins_car.h:103-116
+        const real v = sd.params[0];
+        const real ctheta = std::cos(xs[2]) * kTimeStep;
+        const real stheta = std::sin(xs[2]) * kTimeStep;
+        AA(0, 2) += -v * stheta;
+        AA(1, 2) += v * ctheta;
+        BB(2, 0) = kTimeStep;
+        break;
+      }
       case ILQG_DYN_UNICYCLE4D: {
         const real ctheta = std::cos(xs[2]) * kTimeStep;
         const real stheta = std::sin(xs[2]) * kTimeStep;
@@ -561,6 +577,14 @@ real EvaluateRecord(const Problem& pr, const ilqg_cost_desc& cd, const real* in,
       const real dy = in[cd.dim[1]] - in[cd.dim[3]];
       const real cost = (real)cd.value - std::hypot(dx, dy);
       return cd.flag ? cost : -cost;
+    }
+    case ILQG_COST_QUADRATIC_DIFFERENCE: {  // src/quadratic_difference_cost.cpp:50-60
+      real total = 0.0;
+      for (int ii = 0; ii < cd.flag; ii++) {
+        const real diff = in[cd.dim[ii]] - in[cd.dim[2 + ii]];
+        total += diff * diff;
+      }
+      return 0.5 * weight_ * total;
     }
     case ILQG_COST_SEMIQUADRATIC: {  // src/semiquadratic_cost.cpp:51-59
       const real diff = in[cd.dim[0]] - cd.value;
@@ -732,6 +756,20 @@ void QuadraticizeRecord(const Problem& pr, const ilqg_cost_desc& cd, const real*
       H(xdim2_, ydim1_) -= dx1dy1;
       H(ydim2_, xdim1_) -= dx1dy1;
       H(ydim2_, ydim1_) -= ddy1;
+      break;
+    }
+    case ILQG_COST_QUADRATIC_DIFFERENCE: {  // src/quadratic_difference_cost.cpp:62-91
+      for (int ii = 0; ii < cd.flag; ii++) {
+        const int a = cd.dim[ii], b = cd.dim[2 + ii];
+        const real dx = weight_ * (in[a] - in[b]);
+        const real dy = -dx;
+        H(a, a) += weight_;
+        H(b, b) += weight_;
+        H(a, b) += -weight_;
+        H(b, a) += -weight_;
+        grad[a] += dx;
+        grad[b] += dy;
+      }
       break;
     }
     case ILQG_COST_SEMIQUADRATIC: {  // src/semiquadratic_cost.cpp:63-85
@@ -2052,7 +2090,7 @@ int ilqg_setup_next_receding_horizon(ilqg_handle h, const float* x0_in, double t
     for (size_t kk = 1; kk < (size_t)T; kk++)
       if (distance(&in.prob_xs[kk * n]) < distance(&in.prob_xs[first * n])) first = kk;
     // x0_ = Stitch(nearest, x) (:117; concatenated_dynamical_system.h:75-85)
-    const int ego_dim = ego.kind == ILQG_DYN_CAR6D ? 6 : ego.kind == ILQG_DYN_CAR5D ? 5 : ego.kind == ILQG_DYN_UNICYCLE4D ? 4 : n;
+    const int ego_dim = ego.kind == ILQG_DYN_CAR6D ? 6 : ego.kind == ILQG_DYN_CAR5D ? 5 : ego.kind == ILQG_DYN_UNICYCLE4D ? 4 : ego.kind == ILQG_DYN_DUBINS ? 3 : n;
     for (int a = 0; a < n; a++) in.x0[a] = a < ego_dim ? in.prob_xs[first * n + a] : x[a];
     // ---- SetUpNextRecedingHorizon :127-186: shift the plan, extend it with zero controls ----
     const size_t kept = (size_t)T - first;

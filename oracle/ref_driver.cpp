@@ -15,6 +15,8 @@
 #include <ilqgames/constraint/constraint.h>
 #include <ilqgames/cost/player_cost.h>
 #include <ilqgames/examples/air_3d_example.h>
+#include <ilqgames/examples/dubins_origin_example.h>
+#include <ilqgames/examples/one_player_reachability_example.h>
 #include <ilqgames/examples/roundabout_lane_center.h>
 #include <ilqgames/examples/roundabout_merging_example.h>
 #include <ilqgames/geometry/draw_shapes.h>
@@ -60,7 +62,7 @@ struct ilqg_ref_params {
   float constraint_error_tolerance;
 };
 
-enum { ILQG_REF_INTERSECTION = 0, ILQG_REF_ROUNDABOUT = 1, ILQG_REF_AIR3D = 2, ILQG_REF_OVERTAKING = 3, ILQG_REF_COLLISION = 4, ILQG_REF_REACHABILITY2 = 5, ILQG_REF_REACHABILITY3 = 6 };
+enum { ILQG_REF_INTERSECTION = 0, ILQG_REF_ROUNDABOUT = 1, ILQG_REF_AIR3D = 2, ILQG_REF_OVERTAKING = 3, ILQG_REF_COLLISION = 4, ILQG_REF_REACHABILITY2 = 5, ILQG_REF_REACHABILITY3 = 6, ILQG_REF_REACHABILITY1 = 7, ILQG_REF_DUBINS_ORIGIN = 8 };
 enum { ILQG_REF_ILQ = 0, ILQG_REF_AL = 1 };
 
 }  // extern "C"
@@ -76,6 +78,8 @@ std::shared_ptr<Problem> MakeProblem(int which) {
   else if (which == ILQG_REF_COLLISION) p = std::make_shared<TwoPlayerCollisionExample>();
   else if (which == ILQG_REF_REACHABILITY2) p = std::make_shared<TwoPlayerCollisionAvoidanceReachabilityExample>();
   else if (which == ILQG_REF_REACHABILITY3) p = std::make_shared<ThreePlayerCollisionAvoidanceReachabilityExample>();
+  else if (which == ILQG_REF_REACHABILITY1) p = std::make_shared<OnePlayerReachabilityExample>();
+  else if (which == ILQG_REF_DUBINS_ORIGIN) p = std::make_shared<DubinsOriginExample>();
   else return nullptr;
   p->Initialize();
   return p;

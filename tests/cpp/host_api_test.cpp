@@ -17,6 +17,8 @@
 // the reference's own problem definition, compiled unchanged (tests/test_host_api.py builds this
 // variant only where /root/reference exists)
 #include <ilqgames/examples/air_3d_example.h>
+#include <ilqgames/examples/dubins_origin_example.h>
+#include <ilqgames/examples/one_player_reachability_example.h>
 #include <ilqgames/examples/roundabout_merging_example.h>
 #include <ilqgames/examples/three_player_collision_avoidance_reachability_example.h>
 #include <ilqgames/examples/three_player_intersection_example.h>
@@ -472,6 +474,10 @@ int main(int argc, char** argv) {
   TestProblemDescriptor(MakeProblem<TwoPlayerCollisionAvoidanceReachabilityExample>(), "reachability2", 2, 10, 4, 0);
   // src/three_player_collision_avoidance_reachability_example.cpp: ExtremeValueCost -> grouped records
   TestProblemDescriptor(MakeProblem<ThreePlayerCollisionAvoidanceReachabilityExample>(), "reachability3", 3, 15, 21, 0);
+  // src/one_player_reachability_example.cpp: a single player on a SinglePlayerDubinsCar
+  TestProblemDescriptor(MakeProblem<OnePlayerReachabilityExample>(), "reachability1", 1, 3, 4, 1);
+  // src/dubins_origin_example.cpp: two Dubins cars, QuadraticDifferenceCost
+  TestProblemDescriptor(MakeProblem<DubinsOriginExample>(), "dubins_origin", 2, 6, 5, 0);
 #endif
   TestILQSolver(problem);
   TestAugmentedLagrangianSolver(problem);

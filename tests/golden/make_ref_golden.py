@@ -72,6 +72,13 @@ CASES = {
         R.REACHABILITY3, problems.three_player_collision_avoidance_reachability,
         problems.three_player_collision_avoidance_reachability_params,
         lambda: problems.three_player_collision_avoidance_reachability_x0_batch(8, 15)),
+    # a single player: SinglePlayerDubinsCar, n = 3, m = 1
+    "one_player_reachability": (R.REACHABILITY1, problems.one_player_reachability,
+                                problems.one_player_reachability_params,
+                                lambda: problems.one_player_reachability_x0_batch(8, 3)),
+    # QuadraticDifferenceCost; the executable's parameters switch the linesearch off
+    "dubins_origin": (R.DUBINS_ORIGIN, problems.dubins_origin, problems.dubins_origin_params,
+                      lambda: problems.dubins_origin_x0_batch(8, 6)),
 }
 
 

@@ -34,7 +34,8 @@ def _build(tmp_path, lib_path, dropin=False):
                 "three_player_intersection_example", "roundabout_merging_example", "roundabout_lane_center",
                 "initialize_along_route", "air_3d_example", "draw_shapes", "three_player_overtaking_example",
                 "two_player_collision_example", "two_player_collision_avoidance_reachability_example",
-                "three_player_collision_avoidance_reachability_example")]
+                "three_player_collision_avoidance_reachability_example", "one_player_reachability_example",
+                "dubins_origin_example")]
     subprocess.run(cmd, check=True)
     return exe
 
@@ -183,7 +184,9 @@ def test_reference_example_source_drops_in_unchanged(oracle, tmp_path):
                        ("overtaking", problems.three_player_overtaking),
                        ("collision", problems.two_player_collision),
                        ("reachability2", problems.two_player_collision_avoidance_reachability),
-                       ("reachability3", problems.three_player_collision_avoidance_reachability)):
+                       ("reachability3", problems.three_player_collision_avoidance_reachability),
+                       ("reachability1", problems.one_player_reachability),
+                       ("dubins_origin", problems.dubins_origin)):
         desc, x0 = build()
         mine = np.frombuffer(bytes(desc), dtype=np.uint32)
         theirs = got["desc_" + tag].view(np.uint32)

@@ -32,6 +32,8 @@ CASES = {
                                                     problems.two_player_collision_avoidance_reachability_params),
     "three_player_collision_avoidance_reachability": (problems.three_player_collision_avoidance_reachability,
                                                       problems.three_player_collision_avoidance_reachability_params),
+    "one_player_reachability": (problems.one_player_reachability, problems.one_player_reachability_params),
+    "dubins_origin": (problems.dubins_origin, problems.dubins_origin_params),
 }
 
 
@@ -114,9 +116,14 @@ def test_oracle_reproduces_reference_lin_quad(oracle, name):
     h.linearize_quadraticize()
     assert np.array_equal(h.download(abi.LIN_A), g["lq_A"])
     assert np.array_equal(h.download(abi.LIN_B), g["lq_B"])
-    h.iterate(1)
-    ok = h.download(abi.STATUS) != abi.STATUS_LINESEARCH_FAILED
-    h.linearize_quadraticize()
+    if params().linesearch:
+        h.iterate(1)
+        ok = h.download(abi.STATUS) != abi.STATUS_LINESEARCH_FAILED
+        h.linearize_quadraticize()
+    else:
+        # without the linesearch nothing re-quadraticizes after the step: what
+        # ILQSolver::Quadraticization() holds after one iteration is still the initial rollout's
+        ok = np.ones(nlq, bool)
     for what, key in ((abi.QUAD_Q, "lq_Q"), (abi.QUAD_L, "lq_l"), (abi.QUAD_R, "lq_R"),
                       (abi.QUAD_RGRAD, "lq_r")):
         assert np.array_equal(h.download(what)[ok], g[key][ok]), key
@@ -296,7 +303,7 @@ def test_receding_horizon_argument_errors(oracle):
 
 
 @pytest.mark.parametrize("name", ["three_player_intersection", "air_3d",
-                                  "three_player_collision_avoidance_reachability"])
+                                  "three_player_collision_avoidance_reachability", "one_player_reachability"])
 def test_oracle_reproduces_reference_augmented_lagrangian(oracle, name):
     """AugmentedLagrangianSolver::Solve (src/augmented_lagrangian_solver.cpp:72-210): final
     operating point and strategies, multipliers, mu, NumIterates, success."""
