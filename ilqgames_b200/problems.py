@@ -692,6 +692,49 @@ def dubins_origin_x0_batch(batch: int, seed: int) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------
+# TwoPlayerReachabilityExample (src/two_player_reachability_example.cpp)
+# --------------------------------------------------------------------------
+def two_player_reachability(num_time_steps: int = 100, time_step: float = 0.1, px0: float = 0.0,
+                            py0: float = -10.0, theta0: float = math.pi / 4.0, v0: float = 5.0):
+    """Returns (desc, x0).  TwoPlayerUnicycle4D (one coupled subsystem, n = 4, m = (2, 2)): P1
+    maximises over time, P2 minimises over time the signed distance to a disc.  Unconstrained.
+    CPU oracle only for now."""
+    b = DescBuilder(num_time_steps, time_step)
+    kControlCostWeight, kTargetRadius = 0.1, 1.0
+    b.add_player(2, 0.0, 0.0, abi.COST_MAX)                                # p1_cost.SetMaxOverTime()
+    b.add_player(2, 0.0, 0.0, abi.COST_MIN)                                # p2_cost.SetMinOverTime()
+    b.add_subsystem(abi.DYN_TWO_PLAYER_UNICYCLE4D, 4, 0, [])
+    circle = b.add_polyline(draw_circle((0.0, 0.0), kTargetRadius, 10))
+    # Polyline2SignedDistanceCost(circle, dims, !kReach / kReach, "Target"): bool -> float nominal,
+    # string literal -> bool oriented_same_as_polyline, as in Air3DExample
+    b.state_cost(0, abi.COST_POLYLINE2_SIGNED_DISTANCE, dims=(0, 1), polyline=circle, value=0.0, flag=1)
+    b.state_cost(1, abi.COST_POLYLINE2_SIGNED_DISTANCE, dims=(0, 1), polyline=circle, value=1.0, flag=1)
+    b.control_cost(0, 0, abi.COST_QUADRATIC, dims=(-1,), weight=kControlCostWeight, value=0.0)
+    b.control_cost(1, 1, abi.COST_QUADRATIC, dims=(-1,), weight=kControlCostWeight, value=0.0)
+    x0 = np.array([px0, py0, theta0, v0], dtype=F)
+    return b.build(), x0
+
+
+def two_player_reachability_params(**overrides) -> abi.SolverParams:
+    """SolverParams of exec/two_player_reachability_example/main.cpp:75-78."""
+    base = dict(max_backtracking_steps=100, linesearch=1, expected_decrease_fraction=0.1,
+                initial_alpha_scaling=0.1, convergence_tolerance=0.01)
+    base.update(overrides)
+    return abi.SolverParams.defaults(**base)
+
+
+def two_player_reachability_x0_batch(batch: int, seed: int) -> np.ndarray:
+    """Synthetic initial states: positions U(-10, 10)^2 outside radius 2, headings U(-pi, pi), speeds U(3, 6)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < batch:
+        x, y = rng.uniform(-10.0, 10.0, size=2)
+        if math.hypot(x, y) > 2.0:
+            out.append((x, y, rng.uniform(-math.pi, math.pi), rng.uniform(3.0, 6.0)))
+    return np.array(out, dtype=F)
+
+
+# --------------------------------------------------------------------------
 # Air3DExample
 # --------------------------------------------------------------------------
 def draw_circle(center, radius, num_segments):

@@ -78,8 +78,11 @@ enum {
   ILQG_DYN_AIR3D = 3,      /* params[0] = evader speed, params[1] = pursuer    */
   ILQG_DYN_CAR5D = 4,      /* single_player_car_5d.h:102-147; params[0] = inter-axle distance.
                             * CPU oracle only so far: the CUDA library answers ILQG_ERR_UNSUPPORTED */
-  ILQG_DYN_DUBINS = 5      /* single_player_dubins_car.h:56-118: (x, y, theta), control = turn rate,
+  ILQG_DYN_DUBINS = 5,     /* single_player_dubins_car.h:56-118: (x, y, theta), control = turn rate,
                             * params[0] = constant speed.  CPU oracle only so far as well */
+  ILQG_DYN_TWO_PLAYER_UNICYCLE4D = 6 /* two_player_unicycle_4d.h:60-137: one coupled subsystem
+                            * (x, y, theta, v); player first_player steers (omega, a), the next
+                            * one pushes the position (dx, dy).  CPU oracle only so far */
 };
 
 typedef struct {

@@ -205,6 +205,27 @@ class Air3D : public MultiPlayerDynamicalSystem {
   const float evader_speed_, pursuer_speed_;
 };
 
+// include/ilqgames/dynamics/two_player_unicycle_4d.h:60-137: one unicycle (x, y, theta, v); player 1
+// steers it (omega, a), player 2 pushes its position (dx, dy).  ILQG_DYN_TWO_PLAYER_UNICYCLE4D: CPU
+// oracle only so far.
+class TwoPlayerUnicycle4D : public MultiPlayerDynamicalSystem {
+ public:
+  TwoPlayerUnicycle4D() : MultiPlayerDynamicalSystem(kNumXDims) {}
+  Dimension UDim(PlayerIndex player_idx) const override { return player_idx == 0 ? kNumU1Dims : kNumU2Dims; }
+  PlayerIndex NumPlayers() const override { return kNumPlayers; }
+  std::vector<Dimension> PositionDimensions() const override { return {kPxIdx, kPyIdx}; }
+  bool Describe(ilqg_problem_desc* desc) const override {
+    desc->num_subsystems = 1;
+    ilqg_subsystem_desc& s = desc->subsystems[0];
+    s = ilqg_subsystem_desc();
+    s.kind = ILQG_DYN_TWO_PLAYER_UNICYCLE4D;
+    return true;
+  }
+  static constexpr Dimension kNumXDims = 4, kPxIdx = 0, kPyIdx = 1, kThetaIdx = 2, kVIdx = 3;
+  static constexpr PlayerIndex kNumPlayers = 2;
+  static constexpr Dimension kNumU1Dims = 2, kOmegaIdx = 0, kAIdx = 1, kNumU2Dims = 2, kDxIdx = 0, kDyIdx = 1;
+};
+
 }  // namespace ilqgames
 
 #endif

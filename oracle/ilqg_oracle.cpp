@@ -361,6 +361,14 @@ void EvaluateDynamics(const Problem& pr, const real* x, const real* u, real* xdo
         xd[3] = us[1];
         break;
       }
+      case ILQG_DYN_TWO_PLAYER_UNICYCLE4D: {  // two_player_unicycle_4d.h:104-117
+        const real* u2 = u + pr.uoff[sd.first_player + 1];
+        xd[0] = xs[3] * std::cos(xs[2]) + u2[0];
+        xd[1] = xs[3] * std::sin(xs[2]) + u2[1];
+        xd[2] = us[0];
+        xd[3] = us[1];
+        break;
+      }
       case ILQG_DYN_AIR3D: {  // air_3d.h:114-127
         const real ve = sd.params[0], vp = sd.params[1];
         const real u1 = us[0];
@@ -489,6 +497,20 @@ void Linearize(const Problem& pr, const real* x, const real* u, real* A, real* B
         AA(1, 3) += stheta;
         BB(2, 0) = kTimeStep;
         BB(3, 1) = kTimeStep;
+        break;
+      }
+      case ILQG_DYN_TWO_PLAYER_UNICYCLE4D: {  // two_player_unicycle_4d.h:119-137
+        const int uo2 = pr.uoff[sd.first_player + 1];
+        const real ctheta = std::cos(xs[2]) * kTimeStep;
+        const real stheta = std::sin(xs[2]) * kTimeStep;
+        AA(0, 2) += -xs[3] * stheta;
+        AA(0, 3) += ctheta;
+        AA(1, 2) += xs[3] * ctheta;
+        AA(1, 3) += stheta;
+        BB(2, 0) = kTimeStep;
+        BB(3, 1) = kTimeStep;
+        B[(o + 0) * M + (uo2 + 0)] = kTimeStep;
+        B[(o + 1) * M + (uo2 + 1)] = kTimeStep;
         break;
       }
       case ILQG_DYN_AIR3D: {
@@ -2047,7 +2069,7 @@ int ilqg_setup_next_receding_horizon(ilqg_handle h, const float* x0_in, double t
   if (!(std::abs(t0 + planner_runtime - op_t0) <= kTimeStep)) return ILQG_ERR_INVALID_ARGUMENT;  // :123
 
   const ilqg_subsystem_desc& ego = pr.d.subsystems[0];
-  const bool concatenated = ego.kind != ILQG_DYN_AIR3D;
+  const bool concatenated = ego.kind != ILQG_DYN_AIR3D;  // TwoPlayerUnicycle4D::DistanceBetween is positional too
   for (int b = 0; b < h->batch; b++) {
     Instance& in = h->inst[b];
     real x[ILQG_MAX_XDIM], u[ILQG_MAX_UDIM], ref[ILQG_MAX_XDIM], nx[ILQG_MAX_XDIM];
@@ -2078,6 +2100,13 @@ int ilqg_setup_next_receding_horizon(ilqg_handle h, const float* x0_in, double t
     // nearest state of the existing plan (:101-110); ConcatenatedDynamicalSystem::DistanceBetween
     // only looks at the first subsystem's position (src/concatenated_dynamical_system.cpp:109-113)
     auto distance = [&](const real* a) {
+      if (ego.kind == ILQG_DYN_DUBINS) {
+        // SinglePlayerDubinsCar has no DistanceBetween of its own: the base class's squared 2-norm
+        // of the whole subsystem state, heading included (single_player_dynamical_system.h:68-71)
+        real acc = 0;
+        for (int q = 0; q < 3; q++) acc += (x[ego.x_offset + q] - a[ego.x_offset + q]) * (x[ego.x_offset + q] - a[ego.x_offset + q]);
+        return acc;
+      }
       if (concatenated) {
         const real dx = x[ego.x_offset] - a[ego.x_offset], dy = x[ego.x_offset + 1] - a[ego.x_offset + 1];
         return dx * dx + dy * dy;

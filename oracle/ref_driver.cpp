@@ -25,6 +25,7 @@
 #include <ilqgames/examples/three_player_overtaking_example.h>
 #include <ilqgames/examples/two_player_collision_avoidance_reachability_example.h>
 #include <ilqgames/examples/two_player_collision_example.h>
+#include <ilqgames/examples/two_player_reachability_example.h>
 #include <ilqgames/solver/augmented_lagrangian_solver.h>
 #include <ilqgames/solver/ilq_solver.h>
 #include <ilqgames/solver/lq_feedback_solver.h>
@@ -62,7 +63,7 @@ struct ilqg_ref_params {
   float constraint_error_tolerance;
 };
 
-enum { ILQG_REF_INTERSECTION = 0, ILQG_REF_ROUNDABOUT = 1, ILQG_REF_AIR3D = 2, ILQG_REF_OVERTAKING = 3, ILQG_REF_COLLISION = 4, ILQG_REF_REACHABILITY2 = 5, ILQG_REF_REACHABILITY3 = 6, ILQG_REF_REACHABILITY1 = 7, ILQG_REF_DUBINS_ORIGIN = 8 };
+enum { ILQG_REF_INTERSECTION = 0, ILQG_REF_ROUNDABOUT = 1, ILQG_REF_AIR3D = 2, ILQG_REF_OVERTAKING = 3, ILQG_REF_COLLISION = 4, ILQG_REF_REACHABILITY2 = 5, ILQG_REF_REACHABILITY3 = 6, ILQG_REF_REACHABILITY1 = 7, ILQG_REF_DUBINS_ORIGIN = 8, ILQG_REF_REACHABILITY_2P = 9 };
 enum { ILQG_REF_ILQ = 0, ILQG_REF_AL = 1 };
 
 }  // extern "C"
@@ -80,6 +81,7 @@ std::shared_ptr<Problem> MakeProblem(int which) {
   else if (which == ILQG_REF_REACHABILITY3) p = std::make_shared<ThreePlayerCollisionAvoidanceReachabilityExample>();
   else if (which == ILQG_REF_REACHABILITY1) p = std::make_shared<OnePlayerReachabilityExample>();
   else if (which == ILQG_REF_DUBINS_ORIGIN) p = std::make_shared<DubinsOriginExample>();
+  else if (which == ILQG_REF_REACHABILITY_2P) p = std::make_shared<TwoPlayerReachabilityExample>();
   else return nullptr;
   p->Initialize();
   return p;

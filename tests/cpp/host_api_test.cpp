@@ -25,6 +25,7 @@
 #include <ilqgames/examples/three_player_overtaking_example.h>
 #include <ilqgames/examples/two_player_collision_avoidance_reachability_example.h>
 #include <ilqgames/examples/two_player_collision_example.h>
+#include <ilqgames/examples/two_player_reachability_example.h>
 #endif
 
 #include <cstdio>
@@ -478,6 +479,8 @@ int main(int argc, char** argv) {
   TestProblemDescriptor(MakeProblem<OnePlayerReachabilityExample>(), "reachability1", 1, 3, 4, 1);
   // src/dubins_origin_example.cpp: two Dubins cars, QuadraticDifferenceCost
   TestProblemDescriptor(MakeProblem<DubinsOriginExample>(), "dubins_origin", 2, 6, 5, 0);
+  // src/two_player_reachability_example.cpp: TwoPlayerUnicycle4D, a coupled system like Air3D
+  TestProblemDescriptor(MakeProblem<TwoPlayerReachabilityExample>(), "reachability_2p", 2, 4, 4, 1);
 #endif
   TestILQSolver(problem);
   TestAugmentedLagrangianSolver(problem);

@@ -79,6 +79,10 @@ CASES = {
     # QuadraticDifferenceCost; the executable's parameters switch the linesearch off
     "dubins_origin": (R.DUBINS_ORIGIN, problems.dubins_origin, problems.dubins_origin_params,
                       lambda: problems.dubins_origin_x0_batch(8, 6)),
+    # TwoPlayerUnicycle4D: a coupled (non-concatenated) system besides Air3D, max / min over time
+    "two_player_reachability": (R.REACHABILITY_2P, problems.two_player_reachability,
+                                problems.two_player_reachability_params,
+                                lambda: problems.two_player_reachability_x0_batch(8, 4)),
 }
 
 

@@ -34,6 +34,7 @@ CASES = {
                                                       problems.three_player_collision_avoidance_reachability_params),
     "one_player_reachability": (problems.one_player_reachability, problems.one_player_reachability_params),
     "dubins_origin": (problems.dubins_origin, problems.dubins_origin_params),
+    "two_player_reachability": (problems.two_player_reachability, problems.two_player_reachability_params),
 }
 
 
@@ -181,11 +182,18 @@ def receding_horizon_cases(lib, g, desc, params, from_plan=False):
         h.close()
 
 
-def test_oracle_reproduces_reference_receding_horizon(oracle):
+UNCONSTRAINED = ["roundabout_merging", "three_player_overtaking", "two_player_collision",
+                 "two_player_collision_avoidance_reachability", "dubins_origin", "two_player_reachability"]
+
+
+@pytest.mark.parametrize("name", UNCONSTRAINED)
+def test_oracle_reproduces_reference_receding_horizon(oracle, name):
     """Problem::SetUpNextRecedingHorizon (src/problem.cpp:64-186): new initial state, shifted and
-    extended operating point and strategies, new t0 -- bit for bit."""
-    g = load("roundabout_merging")
-    build, params = CASES["roundabout_merging"]
+    extended operating point and strategies, new t0 -- bit for bit, for every unconstrained example
+    (concatenated systems stitch the ego part of the nearest plan state in, TwoPlayerUnicycle4D
+    takes that state whole; each subsystem kind integrates the zero-control extension)."""
+    g = load(name)
+    build, params = CASES[name]
     desc, _ = build()
     shifted = 0
     for from_plan in (False, True):
