@@ -108,7 +108,8 @@ int BuildDeviceDesc(const ilqg_problem_desc& h, DevDesc* d, ilqg_layout* lo, std
   for (int k = 0; k < h.num_subsystems; k++) {
     const ilqg_subsystem_desc& hs = h.subsystems[k];
     DevSubsystem& ds = d->sub[k];
-    if (hs.kind == ILQG_DYN_CAR5D || hs.kind == ILQG_DYN_DUBINS || hs.kind == ILQG_DYN_TWO_PLAYER_UNICYCLE4D)
+    if (hs.kind == ILQG_DYN_CAR5D || hs.kind == ILQG_DYN_DUBINS || hs.kind == ILQG_DYN_TWO_PLAYER_UNICYCLE4D ||
+        hs.kind == ILQG_DYN_POINT_MASS_2D)
       return ILQG_ERR_UNSUPPORTED;  // oracle only so far (include/ilqg.h)
     const int xd = SubsystemXdim(hs.kind);
     if (xd == 0 || hs.x_offset < 0 || hs.x_offset + xd > d->n) return ILQG_ERR_INVALID_ARGUMENT;

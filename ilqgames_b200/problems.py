@@ -735,6 +735,49 @@ def two_player_reachability_x0_batch(batch: int, seed: int) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------
+# ModifiedAir3DExample (src/modified_air_3d_example.cpp)
+# --------------------------------------------------------------------------
+def modified_air_3d(num_time_steps: int = 100, time_step: float = 0.1, rx0: float = 4.0, ry0: float = 3.0,
+                    rtheta0: float = math.pi / 4.0, ve: float = 1.0, vp: float = 1.0):
+    """Returns (desc, x0).  2x SinglePlayerPointMass2D (n = 8, m = (2, 2)), pursuit-evasion written
+    with QuadraticDifferenceCosts of weight -1e6 / +1e6; state regularization 1.  CPU oracle only
+    for now."""
+    b = DescBuilder(num_time_steps, time_step)
+    kOmegaCostWeight = 0.1
+    for _ in range(2):
+        b.add_player(2, 1.0, 0.0)                                          # PlayerCost("P1", 1.0, 0.0)
+    offs = [b.add_subsystem(abi.DYN_POINT_MASS_2D, 4, i, []) for i in range(2)]
+    p1, p2 = (offs[0] + 0, offs[0] + 1), (offs[1] + 0, offs[1] + 1)
+    for i, w in enumerate((-1e6, 1e6)):                                    # kEvaderWeight, kPursuerWeight
+        b.state_cost(i, abi.COST_QUADRATIC_DIFFERENCE, dims=p1 + p2, weight=w, flag=2)
+        b.control_cost(i, i, abi.COST_QUADRATIC, dims=(-1,), weight=kOmegaCostWeight, value=0.0)
+    x0 = np.zeros(b.d.xdim, dtype=F)                                       # double arithmetic, narrowed on store
+    x0[offs[0] + 2] = ve
+    x0[offs[1] + 0], x0[offs[1] + 1] = rx0, ry0
+    x0[offs[1] + 2], x0[offs[1] + 3] = vp * math.cos(rtheta0), vp * math.sin(rtheta0)
+    return b.build(), x0
+
+
+def modified_air_3d_params(**overrides) -> abi.SolverParams:
+    """SolverParams of exec/modified_air_3d_example/main.cpp:75-78."""
+    base = dict(max_backtracking_steps=100, linesearch=1, expected_decrease_fraction=0.1,
+                initial_alpha_scaling=0.1, convergence_tolerance=0.01)
+    base.update(overrides)
+    return abi.SolverParams.defaults(**base)
+
+
+def modified_air_3d_x0_batch(batch: int, seed: int) -> np.ndarray:
+    """Synthetic initial states: pursuer position U(-6, 6)^2, heading U(-pi, pi), both speeds 1."""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((batch, 8), dtype=F)
+    out[:, 2] = 1.0
+    out[:, 4:6] = rng.uniform(-6.0, 6.0, size=(batch, 2))
+    th = rng.uniform(-math.pi, math.pi, size=batch)
+    out[:, 6], out[:, 7] = np.cos(th), np.sin(th)
+    return out
+
+
+# --------------------------------------------------------------------------
 # Air3DExample
 # --------------------------------------------------------------------------
 def draw_circle(center, radius, num_segments):

@@ -80,9 +80,11 @@ enum {
                             * CPU oracle only so far: the CUDA library answers ILQG_ERR_UNSUPPORTED */
   ILQG_DYN_DUBINS = 5,     /* single_player_dubins_car.h:56-118: (x, y, theta), control = turn rate,
                             * params[0] = constant speed.  CPU oracle only so far as well */
-  ILQG_DYN_TWO_PLAYER_UNICYCLE4D = 6 /* two_player_unicycle_4d.h:60-137: one coupled subsystem
+  ILQG_DYN_TWO_PLAYER_UNICYCLE4D = 6, /* two_player_unicycle_4d.h:60-137: one coupled subsystem
                             * (x, y, theta, v); player first_player steers (omega, a), the next
                             * one pushes the position (dx, dy).  CPU oracle only so far */
+  ILQG_DYN_POINT_MASS_2D = 7 /* single_player_point_mass_2d.h:56-118: (x, y, vx, vy), controls
+                            * (ax, ay).  CPU oracle only so far */
 };
 
 typedef struct {

@@ -96,6 +96,20 @@ class SinglePlayerDubinsCar : public SinglePlayerDynamicalSystem {
   const float v_;
 };
 
+// include/ilqgames/dynamics/single_player_point_mass_2d.h:56-118; state (x, y, vx, vy), controls
+// (ax, ay).  ILQG_DYN_POINT_MASS_2D: CPU oracle only so far.
+class SinglePlayerPointMass2D : public SinglePlayerDynamicalSystem {
+ public:
+  SinglePlayerPointMass2D() : SinglePlayerDynamicalSystem(kNumXDims, kNumUDims) {}
+  std::vector<Dimension> PositionDimensions() const override { return {kPxIdx, kPyIdx}; }
+  bool Describe(ilqg_subsystem_desc* out) const override {
+    out->kind = ILQG_DYN_POINT_MASS_2D;
+    return true;
+  }
+  static constexpr Dimension kNumXDims = 4, kPxIdx = 0, kPyIdx = 1, kVxIdx = 2, kVyIdx = 3;
+  static constexpr Dimension kNumUDims = 2, kAxIdx = 0, kAyIdx = 1;
+};
+
 // include/ilqgames/dynamics/multi_player_integrable_system.h:58-140
 class MultiPlayerIntegrableSystem {
  public:

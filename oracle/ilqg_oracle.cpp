@@ -361,6 +361,13 @@ void EvaluateDynamics(const Problem& pr, const real* x, const real* u, real* xdo
         xd[3] = us[1];
         break;
       }
+      case ILQG_DYN_POINT_MASS_2D: {  // single_player_point_mass_2d.h:91-101
+        xd[0] = xs[2];
+        xd[1] = xs[3];
+        xd[2] = us[0];
+        xd[3] = us[1];
+        break;
+      }
       case ILQG_DYN_TWO_PLAYER_UNICYCLE4D: {  // two_player_unicycle_4d.h:104-117
         const real* u2 = u + pr.uoff[sd.first_player + 1];
         xd[0] = xs[3] * std::cos(xs[2]) + u2[0];
@@ -495,6 +502,13 @@ void Linearize(const Problem& pr, const real* x, const real* u, real* A, real* B
         AA(0, 3) += ctheta;
         AA(1, 2) += xs[3] * ctheta;
         AA(1, 3) += stheta;
+        BB(2, 0) = kTimeStep;
+        BB(3, 1) = kTimeStep;
+        break;
+      }
+      case ILQG_DYN_POINT_MASS_2D: {  // single_player_point_mass_2d.h:103-111
+        AA(0, 2) += kTimeStep;
+        AA(1, 3) += kTimeStep;
         BB(2, 0) = kTimeStep;
         BB(3, 1) = kTimeStep;
         break;
@@ -2119,7 +2133,7 @@ int ilqg_setup_next_receding_horizon(ilqg_handle h, const float* x0_in, double t
     for (size_t kk = 1; kk < (size_t)T; kk++)
       if (distance(&in.prob_xs[kk * n]) < distance(&in.prob_xs[first * n])) first = kk;
     // x0_ = Stitch(nearest, x) (:117; concatenated_dynamical_system.h:75-85)
-    const int ego_dim = ego.kind == ILQG_DYN_CAR6D ? 6 : ego.kind == ILQG_DYN_CAR5D ? 5 : ego.kind == ILQG_DYN_UNICYCLE4D ? 4 : ego.kind == ILQG_DYN_DUBINS ? 3 : n;
+    const int ego_dim = ego.kind == ILQG_DYN_CAR6D ? 6 : ego.kind == ILQG_DYN_CAR5D ? 5 : (ego.kind == ILQG_DYN_UNICYCLE4D || ego.kind == ILQG_DYN_POINT_MASS_2D) ? 4 : ego.kind == ILQG_DYN_DUBINS ? 3 : n;
     for (int a = 0; a < n; a++) in.x0[a] = a < ego_dim ? in.prob_xs[first * n + a] : x[a];
     // ---- SetUpNextRecedingHorizon :127-186: shift the plan, extend it with zero controls ----
     const size_t kept = (size_t)T - first;

@@ -18,6 +18,7 @@
 // variant only where /root/reference exists)
 #include <ilqgames/examples/air_3d_example.h>
 #include <ilqgames/examples/dubins_origin_example.h>
+#include <ilqgames/examples/modified_air_3d_example.h>
 #include <ilqgames/examples/one_player_reachability_example.h>
 #include <ilqgames/examples/roundabout_merging_example.h>
 #include <ilqgames/examples/three_player_collision_avoidance_reachability_example.h>
@@ -481,6 +482,8 @@ int main(int argc, char** argv) {
   TestProblemDescriptor(MakeProblem<DubinsOriginExample>(), "dubins_origin", 2, 6, 5, 0);
   // src/two_player_reachability_example.cpp: TwoPlayerUnicycle4D, a coupled system like Air3D
   TestProblemDescriptor(MakeProblem<TwoPlayerReachabilityExample>(), "reachability_2p", 2, 4, 4, 1);
+  // src/modified_air_3d_example.cpp: two SinglePlayerPointMass2D
+  TestProblemDescriptor(MakeProblem<ModifiedAir3DExample>(), "modified_air3d", 2, 8, 4, 0);
 #endif
   TestILQSolver(problem);
   TestAugmentedLagrangianSolver(problem);

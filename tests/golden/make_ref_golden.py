@@ -83,6 +83,9 @@ CASES = {
     "two_player_reachability": (R.REACHABILITY_2P, problems.two_player_reachability,
                                 problems.two_player_reachability_params,
                                 lambda: problems.two_player_reachability_x0_batch(8, 4)),
+    # SinglePlayerPointMass2D (linear dynamics), cost weights of -1e6 / +1e6
+    "modified_air_3d": (R.MODIFIED_AIR3D, problems.modified_air_3d, problems.modified_air_3d_params,
+                        lambda: problems.modified_air_3d_x0_batch(8, 8)),
 }
 
 

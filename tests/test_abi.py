@@ -91,6 +91,8 @@ def test_time_gated_records_fail_loudly_on_the_cuda_library(product_lib, oracle)
     assert product_lib.lib.ilqg_create(C.byref(desc5), C.byref(p5), 1, 0, C.byref(h)) == -2
     assert oracle.lib.ilqg_create(C.byref(desc5), C.byref(p5), 1, 0, C.byref(h)) == 0
     assert oracle.lib.ilqg_destroy(h) == 0
+    descpm, _ = problems.modified_air_3d()                       # SinglePlayerPointMass2D
+    assert product_lib.lib.ilqg_create(C.byref(descpm), C.byref(p5), 1, 0, C.byref(h)) == -2
     desc2p, _ = problems.two_player_reachability()               # TwoPlayerUnicycle4D
     assert product_lib.lib.ilqg_create(C.byref(desc2p), C.byref(p5), 1, 0, C.byref(h)) == -2
     desc1, _ = problems.one_player_reachability()                # SinglePlayerDubinsCar

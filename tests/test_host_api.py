@@ -35,7 +35,8 @@ def _build(tmp_path, lib_path, dropin=False):
                 "initialize_along_route", "air_3d_example", "draw_shapes", "three_player_overtaking_example",
                 "two_player_collision_example", "two_player_collision_avoidance_reachability_example",
                 "three_player_collision_avoidance_reachability_example", "one_player_reachability_example",
-                "dubins_origin_example", "two_player_reachability_example")]
+                "dubins_origin_example", "two_player_reachability_example",
+                "modified_air_3d_example")]
     subprocess.run(cmd, check=True)
     return exe
 
@@ -187,7 +188,8 @@ def test_reference_example_source_drops_in_unchanged(oracle, tmp_path):
                        ("reachability3", problems.three_player_collision_avoidance_reachability),
                        ("reachability1", problems.one_player_reachability),
                        ("dubins_origin", problems.dubins_origin),
-                       ("reachability_2p", problems.two_player_reachability)):
+                       ("reachability_2p", problems.two_player_reachability),
+                       ("modified_air3d", problems.modified_air_3d)):
         desc, x0 = build()
         mine = np.frombuffer(bytes(desc), dtype=np.uint32)
         theirs = got["desc_" + tag].view(np.uint32)

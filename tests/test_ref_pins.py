@@ -35,6 +35,7 @@ CASES = {
     "one_player_reachability": (problems.one_player_reachability, problems.one_player_reachability_params),
     "dubins_origin": (problems.dubins_origin, problems.dubins_origin_params),
     "two_player_reachability": (problems.two_player_reachability, problems.two_player_reachability_params),
+    "modified_air_3d": (problems.modified_air_3d, problems.modified_air_3d_params),
 }
 
 
@@ -183,7 +184,8 @@ def receding_horizon_cases(lib, g, desc, params, from_plan=False):
 
 
 UNCONSTRAINED = ["roundabout_merging", "three_player_overtaking", "two_player_collision",
-                 "two_player_collision_avoidance_reachability", "dubins_origin", "two_player_reachability"]
+                 "two_player_collision_avoidance_reachability", "dubins_origin", "two_player_reachability",
+                 "modified_air_3d"]
 
 
 @pytest.mark.parametrize("name", UNCONSTRAINED)
