@@ -17,7 +17,10 @@
 #include <ilqgames/examples/air_3d_example.h>
 #include <ilqgames/examples/dubins_origin_example.h>
 #include <ilqgames/examples/modified_air_3d_example.h>
+#include <ilqgames/examples/modified_three_player_intersection_example.h>
 #include <ilqgames/examples/one_player_reachability_example.h>
+#include <ilqgames/examples/skeleton_example.h>
+#include <ilqgames/examples/three_player_intersection_reachability_example.h>
 #include <ilqgames/examples/roundabout_lane_center.h>
 #include <ilqgames/examples/roundabout_merging_example.h>
 #include <ilqgames/geometry/draw_shapes.h>
@@ -64,7 +67,8 @@ struct ilqg_ref_params {
   float constraint_error_tolerance;
 };
 
-enum { ILQG_REF_INTERSECTION = 0, ILQG_REF_ROUNDABOUT = 1, ILQG_REF_AIR3D = 2, ILQG_REF_OVERTAKING = 3, ILQG_REF_COLLISION = 4, ILQG_REF_REACHABILITY2 = 5, ILQG_REF_REACHABILITY3 = 6, ILQG_REF_REACHABILITY1 = 7, ILQG_REF_DUBINS_ORIGIN = 8, ILQG_REF_REACHABILITY_2P = 9, ILQG_REF_MODIFIED_AIR3D = 10 };
+enum { ILQG_REF_INTERSECTION = 0, ILQG_REF_ROUNDABOUT = 1, ILQG_REF_AIR3D = 2, ILQG_REF_OVERTAKING = 3, ILQG_REF_COLLISION = 4, ILQG_REF_REACHABILITY2 = 5, ILQG_REF_REACHABILITY3 = 6, ILQG_REF_REACHABILITY1 = 7, ILQG_REF_DUBINS_ORIGIN = 8, ILQG_REF_REACHABILITY_2P = 9, ILQG_REF_MODIFIED_AIR3D = 10,
+       ILQG_REF_MODIFIED_INTERSECTION = 11, ILQG_REF_SKELETON = 12, ILQG_REF_INTERSECTION_REACHABILITY = 13 };
 enum { ILQG_REF_ILQ = 0, ILQG_REF_AL = 1 };
 
 }  // extern "C"
@@ -84,6 +88,9 @@ std::shared_ptr<Problem> MakeProblem(int which) {
   else if (which == ILQG_REF_DUBINS_ORIGIN) p = std::make_shared<DubinsOriginExample>();
   else if (which == ILQG_REF_REACHABILITY_2P) p = std::make_shared<TwoPlayerReachabilityExample>();
   else if (which == ILQG_REF_MODIFIED_AIR3D) p = std::make_shared<ModifiedAir3DExample>();
+  else if (which == ILQG_REF_MODIFIED_INTERSECTION) p = std::make_shared<ModifiedThreePlayerIntersectionExample>();
+  else if (which == ILQG_REF_SKELETON) p = std::make_shared<SkeletonExample>();
+  else if (which == ILQG_REF_INTERSECTION_REACHABILITY) p = std::make_shared<ThreePlayerIntersectionReachabilityExample>();
   else return nullptr;
   p->Initialize();
   return p;

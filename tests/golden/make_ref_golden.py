@@ -89,12 +89,64 @@ CASES = {
 }
 
 
+_SOURCE_DUMP = {}
+
+
+def source_descriptor(tag: str):
+    """(desc, x0) of a reference example as include/ilqgames/**'s DescribeProblem emits it from the
+    example's OWN source, compiled unchanged (tests/cpp/host_api_test.cpp, drop-in build): for
+    examples made of record kinds that already exist nobody has to transcribe constants by hand."""
+    if not _SOURCE_DUMP:
+        import pathlib
+        import tempfile
+        from ilqgames_b200 import _abi as abi
+        from tests import test_host_api as T
+        tmp = pathlib.Path(tempfile.mkdtemp())
+        exe = T._build(tmp, os.path.join(REPO, "oracle", "_build", "libilqg_oracle.so"), dropin=True)
+        _SOURCE_DUMP.update(T._run(exe, tmp))
+        _SOURCE_DUMP["__abi"] = abi
+    abi = _SOURCE_DUMP["__abi"]
+    desc = abi.ProblemDesc.from_buffer_copy(_SOURCE_DUMP["desc_" + tag].tobytes())
+    return desc, _SOURCE_DUMP["x0_" + tag].copy()
+
+
+def generic_params(initial_alpha_scaling, convergence_tolerance, expected_decrease_fraction):
+    def make(**overrides):
+        from ilqgames_b200 import _abi as abi
+        base = dict(max_backtracking_steps=100, linesearch=1, expected_decrease_fraction=expected_decrease_fraction,
+                    initial_alpha_scaling=initial_alpha_scaling, convergence_tolerance=convergence_tolerance)
+        base.update(overrides)
+        return abi.SolverParams.defaults(**base)
+    return make
+
+
+def generic_x0_batch(tag: str, batch: int, seed: int):
+    """The example's own initial state plus N(0, 0.05) on every state dimension."""
+    _, x0 = source_descriptor(tag)
+    rng = np.random.default_rng(seed)
+    return (np.tile(x0, (batch, 1)) + rng.normal(0, 0.05, size=(batch, len(x0)))).astype(np.float32)
+
+
+# examples whose descriptor comes from their own source: name -> (reference id, dump tag, SolverParams of
+# the example's executable: initial_alpha_scaling, convergence_tolerance, expected_decrease)
+FROM_SOURCE = {
+    "modified_three_player_intersection": (R.MODIFIED_INTERSECTION, "modified_intersection", (1.0, 1.0, 0.9)),
+    "skeleton": (R.SKELETON, "skeleton", (0.25, 0.01, 0.1)),
+    "three_player_intersection_reachability": (R.INTERSECTION_REACHABILITY, "intersection_reachability", (0.1, 0.01, 0.1)),
+}
+
+
 def sorted_rows(a: np.ndarray) -> np.ndarray:
     """Multipliers as a set of per-constraint rows: the reference keeps control constraints in an
     unordered_multimap, so their order is an implementation detail."""
     if a.shape[0] == 0:
         return a
     return a[np.lexsort(a.T[::-1])]
+
+
+for _name, (_which, _tag, _p) in FROM_SOURCE.items():
+    CASES[_name] = (_which, (lambda t=_tag: source_descriptor(t)), generic_params(*_p),
+                    (lambda t=_tag: generic_x0_batch(t, 8, 7)))
 
 
 def run_case(ref: R.RefLibrary, name: str):
@@ -108,6 +160,11 @@ def run_case(ref: R.RefLibrary, name: str):
     p = params(max_solver_iters=ILQ_ITERS)
     rp = R.RefParams.from_abi(p)
     out = {"x0": x0, "ilq_iters": np.int32(ILQ_ITERS)}
+    if name in FROM_SOURCE:
+        # the test side has no hand-written builder for these: it reads the descriptor from here
+        desc, _ = build()
+        out["desc_bytes"] = np.frombuffer(bytes(desc), np.uint8).copy()
+        out["solver_params"] = np.array(FROM_SOURCE[name][2], np.float64)
     xs = np.full((B, ILQ_ITERS + 1, T, n), np.nan, np.float32)
     us = np.full((B, ILQ_ITERS + 1, T, M), np.nan, np.float32)
     Ps = np.zeros((B, T, M, n), np.float32)

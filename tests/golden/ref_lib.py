@@ -11,6 +11,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 REF_LIB = os.path.join(REPO, "oracle", "_ref", "libilqg_ref.so")
 
 INTERSECTION, ROUNDABOUT, AIR3D, OVERTAKING, COLLISION, REACHABILITY2, REACHABILITY3, REACHABILITY1, DUBINS_ORIGIN, REACHABILITY_2P, MODIFIED_AIR3D = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
+MODIFIED_INTERSECTION, SKELETON, INTERSECTION_REACHABILITY = 11, 12, 13
 ILQ, AL = 0, 1
 
 
@@ -154,4 +155,5 @@ class RefLibrary:
         return pts[:k]
 
     def _sum_udim_sq(self, which: int) -> int:
-        return {INTERSECTION: 12, ROUNDABOUT: 16, AIR3D: 2, OVERTAKING: 12, COLLISION: 8, REACHABILITY2: 8, REACHABILITY3: 12, REACHABILITY1: 1, DUBINS_ORIGIN: 2, REACHABILITY_2P: 8, MODIFIED_AIR3D: 8}[which]
+        return {INTERSECTION: 12, ROUNDABOUT: 16, AIR3D: 2, OVERTAKING: 12, COLLISION: 8, REACHABILITY2: 8, REACHABILITY3: 12, REACHABILITY1: 1, DUBINS_ORIGIN: 2, REACHABILITY_2P: 8, MODIFIED_AIR3D: 8, MODIFIED_INTERSECTION: 12, SKELETON: 8,
+                INTERSECTION_REACHABILITY: 12}[which]

@@ -36,7 +36,8 @@ def _build(tmp_path, lib_path, dropin=False):
                 "two_player_collision_example", "two_player_collision_avoidance_reachability_example",
                 "three_player_collision_avoidance_reachability_example", "one_player_reachability_example",
                 "dubins_origin_example", "two_player_reachability_example",
-                "modified_air_3d_example")]
+                "modified_air_3d_example", "modified_three_player_intersection_example", "skeleton_example",
+                "three_player_intersection_reachability_example")]
     subprocess.run(cmd, check=True)
     return exe
 

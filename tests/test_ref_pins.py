@@ -43,6 +43,27 @@ def load(name):
     return np.load(os.path.join(GOLDEN, f"ref_{name}.npz"))
 
 
+def _from_fixture(name):
+    """Examples without a hand-written builder in problems.py: the fixture carries the descriptor
+    that include/ilqgames/**'s DescribeProblem emitted from the example's own source
+    (tests/golden/make_ref_golden.py:source_descriptor) and the executable's solver parameters."""
+    def build():
+        g = load(name)
+        return abi.ProblemDesc.from_buffer_copy(g["desc_bytes"].tobytes()), g["x0"][0].copy()
+
+    def params(**overrides):
+        alpha, tol, decrease = (float(v) for v in load(name)["solver_params"])
+        base = dict(max_backtracking_steps=100, linesearch=1, expected_decrease_fraction=decrease,
+                    initial_alpha_scaling=alpha, convergence_tolerance=tol)
+        base.update(overrides)
+        return abi.SolverParams.defaults(**base)
+    return build, params
+
+
+for _name in ("modified_three_player_intersection", "skeleton", "three_player_intersection_reachability"):
+    CASES[_name] = _from_fixture(_name)
+
+
 def sorted_rows(a):
     return a[np.lexsort(a.T[::-1])] if a.shape[0] else a
 
@@ -185,7 +206,8 @@ def receding_horizon_cases(lib, g, desc, params, from_plan=False):
 
 UNCONSTRAINED = ["roundabout_merging", "three_player_overtaking", "two_player_collision",
                  "two_player_collision_avoidance_reachability", "dubins_origin", "two_player_reachability",
-                 "modified_air_3d"]
+                 "modified_air_3d", "modified_three_player_intersection", "skeleton",
+                 "three_player_intersection_reachability"]
 
 
 @pytest.mark.parametrize("name", UNCONSTRAINED)
