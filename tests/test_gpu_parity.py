@@ -287,27 +287,6 @@ def test_against_reference_fixture(product, oracle64, name):
     assert compared >= 6, f"only {compared} (instance, iterate) pairs were comparable"
 
 
-# ------------------------------------------------------------------ widening: a fourth example
-# The K_bwd instance for n = 18 (the warp-per-game kernel; 18 is not a multiple of 4, which the
-# half-warp kernel needs) was added after this round's GPU minutes were spent: the CPU side (oracle
-# bit for bit against the reference, tests/test_ref_pins.py; the example source compiling unchanged,
-# tests/test_host_api.py) is verified, the device side runs for the first time in the driver's own
-# GPU pass.  Not strict: a pass is reported as XPASS.
-FIRST_DEVICE_RUN = pytest.mark.xfail(strict=False, reason="n = 18 K_bwd instance not yet run on a device")
-
-
-@FIRST_DEVICE_RUN
-def test_overtaking_stage_parity(product, oracle, oracle64):
-    # one iteration: after it these games sit at the merit floor, where the number of backtracking
-    # steps is decided by rounding (the oracle's own fp32 and fp64 builds take 18 and 48)
-    test_stage_parity(product, oracle, oracle64, "three_player_overtaking", iterations=1)
-
-
-@FIRST_DEVICE_RUN
-def test_overtaking_against_reference_fixture(product, oracle64):
-    test_against_reference_fixture(product, oracle64, "three_player_overtaking")
-
-
 # ------------------------------------------------------------------ open-loop LQ solver
 def test_open_loop_lq_reference_test_system(product, oracle):
     """LQOpenLoopSolver::Solve on the system of LQOpenLoopSolverTest (test/test_lq_solver.cpp:
