@@ -14,8 +14,11 @@
 //     tests/golden/make_ref_golden.py runs it and commits tests/golden/ref_*.npz; this
 //     restatement reproduces those fixtures BIT FOR BIT (tests/test_ref_pins.py): ILQSolver
 //     iterates, final strategies, AugmentedLagrangianSolver results with multipliers, the open-loop
-//     solver, Problem::SetUpNextRecedingHorizon, on all three example problems.  What that does
-//     not pin is the rounding of Eigen's own dense kernels (stand-in: plain loops).
+//     solver, Problem::SetUpNextRecedingHorizon, MultiPlayerIntegrableSystem::Integrate(t0, t, ..),
+//     on the three headline example problems and on the eleven other examples of the reference
+//     that are not built on the flat systems (every dynamics and cost class those use is restated
+//     here, also the ones the CUDA library does not implement yet).  What that does not pin is the
+//     rounding of Eigen's own dense kernels (stand-in: plain loops).
 //  2. against the reference's own tests, transcribed with file:line citations in
 //     tests/test_oracle_pins.py:
 //   * geometry golden values     test/test_polyline2.cpp:52-125,
