@@ -365,17 +365,22 @@ def test_oracle_reproduces_reference_augmented_lagrangian(oracle, name):
                          os.path.exists(os.path.join(os.path.dirname(HERE), "oracle", "_ref",
                                                      "libilqg_ref.so"))),
                     reason="live reference build only exists in the builder container")
-@pytest.mark.parametrize("name,which,seed", [("three_player_intersection", 0, 7),
-                                              ("roundabout_merging", 1, 11)])
-def test_oracle_against_live_reference_on_fresh_seeds(oracle, name, which, seed):
+@pytest.mark.parametrize("which,name", list(enumerate([
+    "three_player_intersection", "roundabout_merging", "air_3d", "three_player_overtaking", "two_player_collision",
+    "two_player_collision_avoidance_reachability", "three_player_collision_avoidance_reachability",
+    "one_player_reachability", "dubins_origin", "two_player_reachability", "modified_air_3d",
+    "modified_three_player_intersection", "skeleton", "three_player_intersection_reachability"])))
+def test_oracle_against_live_reference_on_fresh_seeds(oracle, which, name):
     """Same check on initial states that are NOT in the fixtures, calling the compiled reference
-    directly (builder container only)."""
+    directly (builder container only): the example's own initial state plus N(0, 0.1) on every
+    state dimension, five ILQSolver iterations, final iterate and success flag bit for bit.
+    `which` is the example's id in oracle/ref_driver.cpp."""
     from tests.golden import ref_lib as R
     ref = R.RefLibrary()
     build, params = CASES[name]
-    desc, _ = build()
-    x0 = (problems.three_player_intersection_x0_batch(4, seed) if which == 0
-          else problems.roundabout_x0_batch(4, seed))
+    desc, x0_example = build()
+    rng = np.random.default_rng(1000 + which)
+    x0 = (np.tile(x0_example, (4, 1)) + rng.normal(0, 0.1, size=(4, len(x0_example)))).astype(np.float32)
     p = params(max_solver_iters=5)
     h = abi.Handle(oracle, desc, p, 4)
     h.upload_x0(x0)
