@@ -5,6 +5,7 @@
 //   ffma     each lane owns a 2 x 4 tile of the result (what the CUDA-core kernels do)
 //   mma3     mma.sync.m16n8k8 TF32 with the three-product split (hi.hi + hi.lo + lo.hi), which
 //            profiles/r01_tf32_study.md shows is the cheapest variant inside the parity tolerance
+//   mma3i    mma3 with one accumulator per split product (dependent chain of 2 instead of 6 MMAs)
 //   mma1     the same with plain TF32 (one product; an upper bound on what the split costs)
 // at several warps per SM, and checks warp 0's result against a double-precision chain on the host.
 //
@@ -43,10 +44,13 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], 
 }
 
 // C (16 x 16, row-major, ld LD) = op(A) * B with A, B row-major in shared memory; TA: use A'.
-template <bool TA, int SPLIT>
+// INDEP: the three split products go to three accumulators that are added at the end, which cuts the
+// dependent MMA chain per output tile from 6 to 2 instructions.
+template <bool TA, int SPLIT, bool INDEP = false>
 __device__ __forceinline__ void mm_mma(const float* A, const float* B, float* C, int lane) {
   const int g = lane >> 2, t = lane & 3;
   float acc[2][4] = {};
+  float acc_a[2][4] = {}, acc_b[2][4] = {};
 #pragma unroll
   for (int ks = 0; ks < 2; ks++) {
     float af[4];
@@ -67,11 +71,17 @@ __device__ __forceinline__ void mm_mma(const float* A, const float* B, float* C,
       unsigned bh[2] = {tf32(bf[0]), tf32(bf[1])};
       if (SPLIT == 3) {
         unsigned bl[2] = {tf32(bf[0] - __uint_as_float(bh[0])), tf32(bf[1] - __uint_as_float(bh[1]))};
-        mma_tf32(acc[nt], al, bh);  // small terms first
-        mma_tf32(acc[nt], ah, bl);
+        mma_tf32(INDEP ? acc_a[nt] : acc[nt], al, bh);  // small terms first
+        mma_tf32(INDEP ? acc_b[nt] : acc[nt], ah, bl);
       }
       mma_tf32(acc[nt], ah, bh);
     }
+  }
+  if (INDEP) {
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+      for (int q = 0; q < 4; q++) acc[nt][q] += acc_a[nt][q] + acc_b[nt][q];
   }
 #pragma unroll
   for (int nt = 0; nt < 2; nt++) {
@@ -98,7 +108,7 @@ __device__ __forceinline__ void mm_ffma(const float* A, const float* B, float* C
   *reinterpret_cast<float4*>(&C[(r0 + 1) * LD + c0]) = make_float4(acc[1][0], acc[1][1], acc[1][2], acc[1][3]);
 }
 
-// MODE 0: ffma, 1: mma TF32 x 1, 3: mma TF32 x 3
+// MODE 0: ffma, 1: mma TF32 x 1, 3: mma TF32 x 3, 4: mma TF32 x 3 with independent accumulators
 template <int MODE>
 __global__ void __launch_bounds__(WARPS * 32) k_chain(const float* __restrict__ F0, const float* __restrict__ Z0,
                                                      float* __restrict__ out, int games, int steps) {
@@ -113,9 +123,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_chain(const float* __restrict__ 
   }
   __syncwarp();
   for (int s = 0; s < steps; s++) {
-    if (MODE == 0) mm_ffma<false>(Z, F, W, lane); else mm_mma<false, MODE>(Z, F, W, lane);
+    constexpr int SPLIT = MODE == 1 ? 1 : 3;
+    if (MODE == 0) mm_ffma<false>(Z, F, W, lane); else mm_mma<false, SPLIT, MODE == 4>(Z, F, W, lane);
     __syncwarp();
-    if (MODE == 0) mm_ffma<true>(F, W, Z, lane); else mm_mma<true, MODE>(F, W, Z, lane);
+    if (MODE == 0) mm_ffma<true>(F, W, Z, lane); else mm_mma<true, SPLIT, MODE == 4>(F, W, Z, lane);
     __syncwarp();
   }
   for (int e = lane; e < N * N; e += 32) out[(size_t)game * N * N + e] = Z[(e / N) * LD + e % N];
@@ -181,14 +192,15 @@ int main(int argc, char** argv) {
   std::vector<float> got(N * N);
   for (int wps : {4, 8, 16, 32, 64}) {
     const int games = sms * wps;
-    for (int mode : {0, 3, 1}) {
+    for (int mode : {0, 3, 4, 1}) {
       const float ms = mode == 0 ? run<0>(dF, dZ, dout, games, steps, repeats)
                        : mode == 3 ? run<3>(dF, dZ, dout, games, steps, repeats)
+                       : mode == 4 ? run<4>(dF, dZ, dout, games, steps, repeats)
                                    : run<1>(dF, dZ, dout, games, steps, repeats);
       CK(cudaMemcpy(got.data(), dout, sizeof(float) * N * N, cudaMemcpyDeviceToHost));
       double err = 0;
       for (int e = 0; e < N * N; e++) err = std::fmax(err, std::fabs(got[e] - Zd[e]));
-      std::printf("%-6s %10d %12.4f %16.1f %14.2f %12.2e\n", mode == 0 ? "ffma" : mode == 3 ? "mma3" : "mma1", wps, ms,
+      std::printf("%-6s %10d %12.4f %16.1f %14.2f %12.2e\n", mode == 0 ? "ffma" : mode == 3 ? "mma3" : mode == 4 ? "mma3i" : "mma1", wps, ms,
                   1e6 * ms / steps, 2.0 * steps * games / (ms * 1e6), err / scale);
     }
   }
