@@ -289,6 +289,13 @@ COST_CASES = {
                             None, True),
     "SingleDimensionConstraint": (abi.CONSTRAINT_SINGLE_DIMENSION, dict(dims=(0,), value=1.0, flag=1),
                                   None, True),
+    # kinds added with the widening of SURVEY 8 f4 (test/test_quadraticization.cpp has the same checks:
+    # QuadraticDifferenceCostTest :210-214 with dims {0, 1} / {1, 2}, SignedDistanceCostTest :291-295)
+    "SignedDistanceCost": (abi.COST_SIGNED_DISTANCE, dict(dims=(0, 1, 2, 3), value=5.0, flag=1), None, False),
+    "SignedDistanceCostFlipped": (abi.COST_SIGNED_DISTANCE, dict(dims=(0, 1, 2, 3), value=5.0, flag=0), None,
+                                  False),
+    "QuadraticDifferenceCost": (abi.COST_QUADRATIC_DIFFERENCE, dict(dims=(0, 1, 1, 2), weight=1.0, flag=2), None,
+                                False),
 }
 
 
@@ -345,12 +352,16 @@ def _dyn_handle(lib, which):
         desc, _ = problems.three_player_intersection()
     elif which == "roundabout":
         desc, _ = problems.roundabout_merging()
-    else:
+    elif which == "air3d":
         desc, _ = problems.air_3d()
+    else:   # the dynamics added with the widening: Car5D, Dubins car, point mass, two-player unicycle
+        desc, _ = {"car5d": problems.two_player_collision_avoidance_reachability, "dubins": problems.dubins_origin,
+                   "point_mass": problems.modified_air_3d, "two_player_unicycle": problems.two_player_reachability}[which]()
     return abi.Handle(lib, desc, abi.SolverParams.defaults(), 1)
 
 
-@pytest.mark.parametrize("which", ["three_player", "roundabout", "air3d"])
+@pytest.mark.parametrize("which", ["three_player", "roundabout", "air3d", "car5d", "dubins", "point_mass",
+                                   "two_player_unicycle"])
 def test_linearization_matches_forward_differences(oracle, which):
     # CheckLinearization, test/test_linearization.cpp:142-196: A, B_i against forward
     # differences of Evaluate with h = 1e-3 (continuous-time Jacobian * dt + I), tol 1e-2,
