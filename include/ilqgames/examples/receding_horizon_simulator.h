@@ -7,8 +7,9 @@
 //
 // Host-side sequencing only: the solves (ILQSolver / AugmentedLagrangianSolver), the re-basing
 // (ilqg_setup_next_receding_horizon) and the integration along the plan (ilqg_integrate_plan) all
-// run on the device.  The optional `now` argument (seconds, monotonic) replaces the wall clock,
-// which makes a run reproducible; the default is std::chrono::system_clock like the reference.
+// run on the device.  The optional `now` argument (seconds, monotonic) replaces the wall clock
+// (and lifts the solver's own wall-clock budget), which makes a run reproducible; the default is
+// std::chrono::system_clock and a budget of planner_runtime per solve, like the reference.
 #ifndef ILQGAMES_B200_EXAMPLES_RECEDING_HORIZON_SIMULATOR_H
 #define ILQGAMES_B200_EXAMPLES_RECEDING_HORIZON_SIMULATOR_H
 
@@ -63,7 +64,9 @@ inline std::vector<std::shared_ptr<const SolverLog>> RecedingHorizonSimulator(
     // the running plan becomes the problem's warm start, re-based to where the solve will end
     problem.OverwriteSolution(splicer.CurrentOperatingPoint(), splicer.CurrentStrategies());
     problem.SetUpNextRecedingHorizon(x, t, planner_runtime);
-    const Time elapsed = timed_solve(planner_runtime).first;
+    // with a scripted clock the solver's own wall-clock cut-off is lifted as well: the run is meant
+    // to be reproducible, and a loaded host must not decide how many iterations a solve gets
+    const Time elapsed = timed_solve(now ? constants::kInfinity : planner_runtime).first;
     CHECK_LE(elapsed, planner_runtime);  // :118
     VLOG(1) << "t = " << t << ": Solved warm-started problem in " << elapsed << " seconds.";
 
