@@ -9,6 +9,7 @@
 #include <new>
 #include <vector>
 
+#include "ilqg_backward_tc.cuh"
 #include "ilqg_linesearch.cuh"
 #include "ilqg_open_loop.cuh"
 #include "ilqg_receding.cuh"
@@ -26,6 +27,15 @@ struct SubSolver {
   LsScratch ls;
   RecordPattern pat;
   bool pat_ok;
+  // compact records (ilqg_records.cuh) and the tensor-core backward sweep's tables (ilqg_backward_tc.cuh)
+  CompactPattern cp;
+  TcTables tc;
+  bool cp_ok = false;       // K_lq v4 + k_lq_backward_tc usable for this descriptor
+  int tc_nxp = 0, tc_mup = 0;
+  bool use_compact = true;  // ILQG_RECORDS=dense forces the round-1 dense-record kernels (A/B runs)
+  // which representation of the LQ records is current: K_lq v4 writes the compact one,
+  // ilqg_upload_lq / K_lq v3 the dense one; EnsureDense expands compact -> dense on demand
+  bool compact_valid = false, dense_valid = false;
   int ls_blocks_max;
   int ls_cur;  // which open-linesearch queue the next pass consumes
   int device;
@@ -302,6 +312,41 @@ int SetSmem(K kernel, size_t bytes) {
   return ILQG_OK;
 }
 
+// ---- compact records + tensor-core backward sweep (ilqg_records.cuh, ilqg_backward_tc.cuh) ----
+// instantiations of k_lq_backward_tc: padded state dimension, padded stacked control dimension,
+// scatter / Q-add table entries per lane, minimum resident blocks per SM
+#define ILQG_TC_INSTANCES(X)                                                                        \
+  X(8, 2, 2, 4, 8) X(8, 4, 2, 4, 8) X(16, 2, 3, 6, 6) X(16, 4, 3, 6, 6) X(16, 6, 3, 6, 6) X(16, 8, 3, 6, 4) \
+  X(24, 4, 4, 10, 3) X(24, 6, 4, 10, 3) X(24, 8, 4, 10, 3)
+
+// the per-lane table budgets of the instance for (nxp, mup), or false when there is none
+bool TcBudget(int nxp, int mup, int* sc, int* qa) {
+#define X(NXP, MUP, SC, QA, MINB) \
+  if (nxp == NXP && mup == MUP) { *sc = SC; *qa = QA; return true; }
+  ILQG_TC_INSTANCES(X)
+#undef X
+  return false;
+}
+
+int EnsureDenseAlloc(SubSolver* h) {
+  if (h->s.rec) return ILQG_OK;
+  return DevAlloc(h, &h->s.rec, (size_t)h->B * h->d.T * (size_t)h->d.rec);
+}
+
+// dense LQ records for the consumers that want them (downloads, the open-loop solver, the
+// dense-record backward kernels): expanded from the compact ones when those are newer
+int EnsureDense(SubSolver* h) {
+  int rc = EnsureDenseAlloc(h);
+  if (rc != ILQG_OK) return rc;
+  if (h->dense_valid || !h->compact_valid) return ILQG_OK;
+  const long long recs = (long long)h->B * h->d.T;
+  k_expand_records<<<(int)((recs + 3) / 4), 128, 0, h->stream>>>(h->d, h->s, h->pat, h->cp);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  h->dense_valid = true;
+  return ILQG_OK;
+}
+
 template <int NX, int MU, int NP>
 int LaunchBackward(SubSolver* h, int only_running, Sel) {
   const size_t smem = sizeof(float) * KBWD_WARPS * (size_t)(BwdSmem<NX, MU, NP>::rec + h->d.rec);
@@ -345,12 +390,52 @@ int LaunchOpenLoop(SubSolver* h, int only_running, bool use_lq_x0) {
 
 // with_dxs: also produce ILQG_DELTA_XS (an optional output of LQFeedbackSolver::Solve that the
 // iLQ loop itself never reads once ExpectedDecrease is fused into the backward sweep)
+template <int NXP, int MUP, int SC, int QA, int MINB>
+int LaunchBackwardTc(SubSolver* h, int only_running, Sel sel) {
+  const size_t smem = sizeof(float) * (((size_t)h->tc.total_words + 3) / 4 * 4 + 2 * KTC_WARPS + (size_t)KTC_WARPS * h->tc.per_game);
+  int rc = SetSmem(k_lq_backward_tc<NXP, MUP, SC, QA, MINB>, smem);
+  if (rc != ILQG_OK) return rc;
+  ProfScope prof(h, 1);
+  k_lq_backward_tc<NXP, MUP, SC, QA, MINB><<<(h->B + KTC_WARPS - 1) / KTC_WARPS, KTC_WARPS * 32, smem, h->stream>>>(
+      h->d, h->p, h->s, h->tc, only_running, sel);
+  h->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return ILQG_OK;
+}
+
+int DispatchBackwardTc(SubSolver* h, int only_running, Sel sel) {
+#define X(NXP, MUP, SC, QA, MINB) \
+  if (h->tc_nxp == NXP && h->tc_mup == MUP) return LaunchBackwardTc<NXP, MUP, SC, QA, MINB>(h, only_running, sel);
+  ILQG_TC_INSTANCES(X)
+#undef X
+  return ILQG_ERR_UNSUPPORTED;
+}
+
 int DispatchBackward(SubSolver* h, int only_running, bool with_dxs, Sel sel = Sel{SEL_ALL, nullptr, nullptr}) {
+  int rc = ILQG_ERR_UNSUPPORTED;
+  if (!h->open_loop && h->cp_ok && h->use_compact && h->compact_valid) {
+    // the hot path: tensor-core sweep over the compact records
+    if ((rc = DispatchBackwardTc(h, only_running, sel)) != ILQG_OK) return rc;
+    if (with_dxs) {
+      if ((rc = EnsureDense(h)) != ILQG_OK) return rc;
+      k_delta_xs<<<(h->B + 3) / 4, 128, sizeof(float) * 4 * 2 * ILQG_MAX_XDIM, h->stream>>>(h->d, h->s, h->s.lq_x0);
+      h->launches++;
+      CUDA_TRY(cudaGetLastError());
+    }
+    return ILQG_OK;
+  }
+  if ((rc = EnsureDense(h)) != ILQG_OK) return rc;
   // with_dxs is the stand-alone ilqg_lq_backward: the only caller with a nonzero x0 argument
   if (h->open_loop) return LaunchOpenLoop(h, only_running, with_dxs);  // writes delta_xs itself
-  int rc = ILQG_ERR_UNSUPPORTED;
+  rc = ILQG_ERR_UNSUPPORTED;
   bool hw = true;
-  switch (h->dims_key) {
+  int key = h->dims_key;
+  // the half-warp kernel hard-codes a uniform control dimension m = M / N: anything
+  // else must not reach it
+  if (key == 0 || key == 1 || key == 4)
+    for (int i = 0; i < h->d.N; i++)
+      if (h->d.udim[i] * h->d.N != h->d.M) key = -1;
+  switch (key) {
     case 0: rc = LaunchBackwardHw<16, 6, 3>(h, only_running, sel); break;
     case 1: rc = LaunchBackwardHw<24, 8, 4>(h, only_running, sel); break;
     case 2: rc = LaunchBackward<3, 2, 2>(h, only_running, sel); hw = false; break;
@@ -388,6 +473,164 @@ int MaxRoleEntries(const DevDesc& d) {
   int lin = 0;
   for (int k = 0; k < d.num_subsystems; k++) lin += 9;
   return std::max(best, lin);
+}
+
+template <typename T>
+int UploadVector(SubSolver* h, const std::vector<T>& v, const T** out) {
+  T* dptr = nullptr;
+  int rc = DevAlloc(h, &dptr, v.size());
+  if (rc != ILQG_OK) return rc;
+  if (!v.empty())
+    CUDA_TRY(cudaMemcpyAsync(dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  *out = dptr;
+  return ILQG_OK;
+}
+
+// From the gather items (one per touched record offset): the compact record layout, the g_k table of
+// K_lq v4 and the index tables of the tensor-core sweep.  Leaves h->cp_ok = false (dense-record
+// kernels are used) when the descriptor does not fit the compact kernels' envelope.
+int BuildCompactTables(SubSolver* h, const std::vector<GatherItem>& items) {
+  const DevDesc& d = h->d;
+  h->cp_ok = false;
+  const int n = d.n, M = d.M, N = d.N;
+  const int NI = (int)items.size();
+  if (NI == 0 || NI >= (int)kItemReg || d.num_subsystems == 0) return ILQG_OK;
+  const int NIp = (NI + n + N + 31) & ~31;  // items | g_k | the N state regularisers | pad
+  const int NXP = (n + 7) & ~7, MUP = (M + 1) & ~1;
+  int sc_budget = 0, qa_budget = 0;
+  if (!TcBudget(NXP, MUP, &sc_budget, &qa_budget)) return ILQG_OK;
+  std::vector<int> item_at(d.rec, -1);
+  for (int g = 0; g < NI; g++) {
+    if (item_at[items[g].off] >= 0) return ILQG_OK;  // two roles on one offset: not a compact pattern
+    item_at[items[g].off] = g;
+  }
+  // g_k[a] = sum_i sum_c Q_i[a][c] l_i[c] over the terms that can be non-zero
+  std::vector<uint2> gk;
+  std::vector<int> gk_start(n + 1, 0);
+  for (int a = 0; a < n; a++) {
+    gk_start[a] = (int)gk.size();
+    for (int i = 0; i < N; i++)
+      for (int c = 0; c < n; c++) {
+        const int li = item_at[d.offl + i * n + c];
+        if (li < 0) continue;  // l_i[c] is the template's zero
+        const int qi = item_at[d.offQ + (i * n + a) * n + c];
+        unsigned qcode;
+        if (qi >= 0) qcode = (unsigned)qi;
+        else if (a == c && d.state_reg[i] != 0.f) qcode = kItemReg + i;
+        else continue;
+        gk.push_back(make_uint2(qcode | ((unsigned)li << 16), (unsigned)i));
+      }
+  }
+  gk_start[n] = (int)gk.size();
+
+  const TcFixed L = tc_fixed(NXP, MUP);
+  TcTables& tc = h->tc;
+  std::memset(&tc, 0, sizeof(tc));
+  tc.NI = NI;
+  tc.NIp = NIp;
+  tc.off_vals = L.fixed;
+  tc.off_Z = tc.off_vals + 2 * NIp;  // two record buffers: the next record lands while this one is in use
+  const int MM = (MUP * MUP + 3) & ~3;
+  // control-cost pair that owns offset `rel` of the R (mode 0) / r (mode 1) block
+  auto pair_at = [&](int rel, int mode) {
+    for (int pp = 0; pp < d.num_pairs; pp++) {
+      const int mj = d.udim[d.pair_j[pp]];
+      const int lo = mode == 0 ? d.pair_Roff[pp] : d.pair_roff[pp], len = mode == 0 ? mj * mj : mj;
+      if (rel >= lo && rel < lo + len) return pp;
+    }
+    return -1;
+  };
+  tc.per_game = tc.off_Z + N * NXP * L.LD + 4;  // + a scratch word the padding entries of the tables hit
+  if (tc.per_game >= 65536) return ILQG_OK;
+  std::vector<unsigned> scat, bnz, brow_rows, brow, qadd;
+  struct BEntry { int q, c, item, player; };
+  std::vector<BEntry> bs;
+  auto owner_of = [&](int c) {
+    int o = 0;
+    for (int i = 1; i < N; i++)
+      if (c >= d.uoff[i]) o = i;
+    return o;
+  };
+  for (int g = 0; g < NI; g++) {
+    const int off = items[g].off;
+    if (off < d.offB) {  // A
+      const int idx = off - d.offA, q = idx / n, c = idx % n;
+      scat.push_back((unsigned)g | ((unsigned)(L.F + q * L.LD + c) << 16));
+    } else if (off < d.offQ) {  // B
+      const int idx = off - d.offB, q = idx / M, c = idx % M;
+      bs.push_back({q, c, g, owner_of(c)});
+    } else if (off < d.offl) {  // Q_i
+      const int idx = off - d.offQ, i = idx / (n * n), r = (idx / n) % n, c = idx % n;
+      qadd.push_back((unsigned)g | ((unsigned)(i * NXP * L.LD + r * L.LD + c) << 16));
+    } else if (off < d.offR) {  // l_i
+      const int idx = off - d.offl, i = idx / n, a = idx % n;
+      scat.push_back((unsigned)g | ((unsigned)(L.l + i * NXP + a) << 16));
+    } else if (off < d.offr) {  // R_ij -> Omega_i[co_j + a][co_j + c]
+      const int pp = pair_at(off - d.offR, 0);
+      if (pp < 0) return ILQG_OK;
+      const int i = d.pair_i[pp], j = d.pair_j[pp], mj = d.udim[j], co = d.uoff[j];
+      const int idx = off - d.offR - d.pair_Roff[pp], a = idx / mj, c = idx % mj;
+      scat.push_back((unsigned)g | ((unsigned)(L.Om + i * MM + (co + a) * MUP + co + c) << 16));
+    } else {  // r_ij -> rho_i[co_j + c]
+      const int pp = pair_at(off - d.offr, 1);
+      if (pp < 0) return ILQG_OK;
+      const int i = d.pair_i[pp], j = d.pair_j[pp], co = d.uoff[j];
+      scat.push_back((unsigned)g | ((unsigned)(L.rho + i * 8 + co + off - d.offr - d.pair_roff[pp]) << 16));
+    }
+  }
+  for (int i = 0; i < N; i++)  // the template's state regulariser on the diagonal of Q_i
+    for (int a = 0; a < n; a++)
+      if (d.state_reg[i] != 0.f && item_at[d.offQ + (i * n + a) * n + a] < 0)
+        qadd.push_back((unsigned)(NI + n + i) | ((unsigned)(i * NXP * L.LD + a * L.LD + a) << 16));
+  std::sort(bs.begin(), bs.end(), [](const BEntry& x, const BEntry& y) { return x.c != y.c ? x.c < y.c : x.q < y.q; });
+  for (int c = 0, e = 0; c <= M; c++) {
+    while (e < (int)bs.size() && bs[e].c < c) e++;
+    tc.bnz_start[c] = e;
+  }
+  tc.bnz_start[M] = (int)bs.size();
+  for (const BEntry& b : bs) bnz.push_back((unsigned)b.q | ((unsigned)b.c << 8) | ((unsigned)b.item << 16));
+  std::sort(bs.begin(), bs.end(), [](const BEntry& x, const BEntry& y) {
+    return x.q != y.q ? x.q < y.q : (x.player != y.player ? x.player < y.player : x.c < y.c);
+  });
+  for (size_t e = 0; e < bs.size();) {
+    size_t e1 = e;
+    while (e1 < bs.size() && bs[e1].q == bs[e].q) e1++;
+    brow_rows.push_back((unsigned)bs[e].q | ((unsigned)e << 8) | ((unsigned)(e1 - e) << 20));
+    e = e1;
+  }
+  for (const BEntry& b : bs) brow.push_back((unsigned)b.c | ((unsigned)b.player << 8) | ((unsigned)b.item << 16));
+  if (bs.size() >= 4096 || (int)scat.size() > 32 * sc_budget || (int)qadd.size() > 32 * qa_budget) return ILQG_OK;
+  tc.nscat = (int)scat.size();
+  tc.nqadd = (int)qadd.size();
+  // the kernel walks exactly 32 x budget entries: pad with item 0 -> the scratch word after Z
+  scat.resize((size_t)32 * sc_budget, (unsigned)(tc.off_Z + N * NXP * L.LD) << 16);
+  qadd.resize((size_t)32 * qa_budget, (unsigned)(N * NXP * L.LD) << 16);
+  std::vector<unsigned> words;
+  auto append = [&](const std::vector<unsigned>& v) {
+    const int at = (int)words.size();
+    words.insert(words.end(), v.begin(), v.end());
+    return at;
+  };
+  tc.scat = append(scat);
+  tc.bnz = append(bnz); tc.nbnz = (int)bnz.size();
+  tc.brow_rows = append(brow_rows); tc.nbrow_rows = (int)brow_rows.size();
+  tc.brow = append(brow);
+  tc.qadd = append(qadd);
+  tc.total_words = (int)words.size();
+  const size_t smem = sizeof(float) * (((size_t)tc.total_words + 3) / 4 * 4 + 2 * KTC_WARPS + (size_t)KTC_WARPS * tc.per_game);
+  if (smem > 200 * 1024) return ILQG_OK;
+  int rc;
+  if ((rc = UploadVector(h, words, &tc.words)) != ILQG_OK) return rc;
+  if ((rc = UploadVector(h, gk, &h->cp.gk)) != ILQG_OK) return rc;
+  if ((rc = UploadVector(h, gk_start, &h->cp.gk_start)) != ILQG_OK) return rc;
+  h->cp.NI = NI;
+  h->cp.NIp = NIp;
+  if ((rc = DevAlloc(h, &h->s.crec, (size_t)h->B * d.T * NIp)) != ILQG_OK) return rc;
+  h->tc_nxp = NXP;
+  h->tc_mup = MUP;
+  h->cp_ok = true;
+  return ILQG_OK;
 }
 
 // Discover the static update pattern of the records on the device and build the gather table
@@ -465,11 +708,31 @@ int BuildRecordPattern(SubSolver* h) {
   h->pat.num_idx = (int)idx.size();
   h->pat.E = E;
   h->pat_ok = true;
-  return ILQG_OK;
+  return BuildCompactTables(h, items);
 }
 
 int LaunchLqRecords(SubSolver* h, int only_running, Sel sel = Sel{SEL_ALL, nullptr, nullptr}) {
   const DevDesc& d = h->d;
+  if (h->pat_ok && h->cp_ok && h->use_compact && !h->open_loop) {
+    const size_t smem4 = klq4_smem_bytes(d.n, d.M, d.N, h->pat.E, h->cp.NIp, h->pat.num_items, h->pat.num_idx);
+    int rc4 = SetSmem(k_linearize_quadraticize_v4, smem4);
+    if (rc4 != ILQG_OK) return rc4;
+    const long long recs = (long long)h->B * d.T;
+    ProfScope prof(h, 0);
+    k_linearize_quadraticize_v4<<<(int)((recs + 31) / 32), (d.N + 1) * 32, smem4, h->stream>>>(h->d, h->s, h->pat, h->cp,
+                                                                                             only_running, sel);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    h->compact_valid = true;
+    h->dense_valid = false;
+    return ILQG_OK;
+  }
+  {
+    int rca = EnsureDense(h);  // partial launches (only_running / lists) keep the other games' records
+    if (rca != ILQG_OK) return rca;
+    h->dense_valid = true;
+    h->compact_valid = false;
+  }
   if (h->pat_ok) {
     const size_t smem3 = klq_smem_bytes(d.n, d.M, d.N, h->pat.E, d.rec, h->pat.num_items, h->pat.num_idx);
     int rc3 = SetSmem(k_linearize_quadraticize_v3, smem3);
@@ -634,7 +897,7 @@ int IteratePipelined(SubSolver* h, int n) {
 // the pipelined schedule needs the list-capable kernels (static K_lq, half-warp K_bwd) and a
 // single queued window; per-kernel profiling wants every kernel alone on the device
 bool CanPipeline(const SubSolver* h, int max_iters) {
-  const bool hw = h->dims_key == 0 || h->dims_key == 1 || h->dims_key == 4;
+  const bool hw = h->dims_key == 0 || h->dims_key == 1 || h->dims_key == 4 || (h->cp_ok && h->use_compact);
   const bool one_window = h->ls.JB >= std::max(1, h->p.max_backtracking_steps) - h->ls.JA;
   return h->pipeline && !h->open_loop && max_iters > 1 && h->pat_ok && hw && one_window && h->p.linesearch && !h->profiling;
 }
@@ -734,6 +997,8 @@ int DownloadRecordField(SubSolver* h, int off, int floats, void* dst, size_t byt
   const size_t rows = (size_t)h->B * h->d.T;
   if (bytes != rows * floats * sizeof(float)) return ILQG_ERR_SIZE_MISMATCH;
   if (floats == 0) return ILQG_OK;
+  int rcd = EnsureDense(h);
+  if (rcd != ILQG_OK) return rcd;
   CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)floats * sizeof(float), h->s.rec + off,
                              (size_t)h->d.rec * sizeof(float), (size_t)floats * sizeof(float), rows,
                              cudaMemcpyDeviceToHost, h->stream));
@@ -744,6 +1009,10 @@ int DownloadRecordField(SubSolver* h, int off, int floats, void* dst, size_t byt
 int UploadRecordField(SubSolver* h, int off, int floats, const float* src) {
   const size_t rows = (size_t)h->B * h->d.T;
   if (floats == 0) return ILQG_OK;
+  int rcd = EnsureDense(h);  // fields not uploaded keep what the records held
+  if (rcd != ILQG_OK) return rcd;
+  h->dense_valid = true;
+  h->compact_valid = false;
   CUDA_TRY(cudaMemcpy2DAsync(h->s.rec + off, (size_t)h->d.rec * sizeof(float), src,
                              (size_t)floats * sizeof(float), (size_t)floats * sizeof(float), rows,
                              cudaMemcpyHostToDevice, h->stream));
@@ -786,11 +1055,9 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
   h->dims_key = -1;
   for (int k = 0; k < kNumDims; k++)
     if (kDims[k].n == h->d.n && kDims[k].M == h->d.M && kDims[k].N == h->d.N) h->dims_key = k;
-  // the open-loop kernel takes run-time dimensions; the feedback kernels are instantiated per shape
-  if (h->dims_key < 0 && !params->open_loop) {
-    delete h;
-    return ILQG_ERR_UNSUPPORTED;
-  }
+  // the open-loop kernel and the tensor-core sweep over compact records take run-time dimensions;
+  // the dense-record feedback kernels are instantiated per shape (checked after the pattern is built)
+  if (const char* e = std::getenv("ILQG_RECORDS")) h->use_compact = std::strcmp(e, "dense") != 0;
   h->host_desc = *desc;
   h->open_loop = params->open_loop != 0;
   h->B = batch;
@@ -861,7 +1128,6 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
   ALLOC(s.prob_us, B * T * M);
   ALLOC(s.prob_P, B * T * M * n);
   ALLOC(s.prob_a, B * T * M);
-  ALLOC(s.rec, B * T * (size_t)h->d.rec);
   ALLOC(s.dxs, B * T * n);
   if (h->open_loop)
     ALLOC(h->ol_scratch, B * T * (size_t)ol_layout(h->d.n, h->d.M, h->d.N, h->d.rec - h->d.offl).srec);
@@ -948,6 +1214,7 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
   if ((rc = Fill(h, s.max_con_err, INFINITY, B)) != ILQG_OK) return fail(rc);
   if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(ILQG_ERR_CUDA);
   if ((rc = BuildRecordPattern(h)) != ILQG_OK) return fail(rc);
+  if (h->dims_key < 0 && !h->open_loop && !(h->cp_ok && h->use_compact)) return fail(ILQG_ERR_UNSUPPORTED);
   *out = h;
   return ILQG_OK;
 }

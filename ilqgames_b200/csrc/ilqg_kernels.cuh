@@ -27,7 +27,8 @@ struct Slab {
   float* st_P[2];                   // [B][T][M][n] strategies double buffer
   float* st_a[2];                   // [B][T][M]
   float *prob_xs, *prob_us, *prob_P, *prob_a;  // Problem's warm start
-  float* rec;                       // [B][T][rec]  LQ records
+  float* rec;                       // [B][T][rec]  dense LQ records (allocated on first use, ilqg_abi.cu:EnsureDense)
+  float* crec;                      // [B][T][NIp]  compact LQ records (ilqg_records.cuh)
   float* dxs;                       // [B][T][n]
   float* lambdas;                   // [B][ncon][T]
   float *mu, *last_merit, *expected_decrease, *step, *total_costs, *max_con_err;

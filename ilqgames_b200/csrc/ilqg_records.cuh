@@ -263,4 +263,177 @@ k_linearize_quadraticize_v3(const __grid_constant__ DevDesc d, Slab s, RecordPat
   }
 }
 
+
+// ===========================================================================
+// Compact LQ records (round 2).
+//
+// A dense record is 1188 floats for ThreePlayerIntersection, but only the ~150 words the gather
+// table touches ever differ from the static template: writing the dense record and reading it
+// back was 10 x the information content.  K_lq v4 therefore stores, per
+// (instance, timestep), only
+//     [ item values (NI, in gather-table order) | g_k = sum_i Q_i l_i (n) | state_reg (N) | pad -> multiple of 32 ]
+// and the backward sweep (ilqg_backward_tc.cuh) rebuilds what it needs in shared memory from the
+// template plus static index tables derived from the same pattern at ilqg_create.  g_k is the
+// per-timestep vector ExpectedDecrease's adjoint recursion needs (src/ilq_solver.cpp:387-392);
+// computing it here keeps Q out of the sweep's shared memory altogether.
+// Dense records (downloads of ILQG_LIN_* / ILQG_QUAD_*, the open-loop solver, stand-alone LQ
+// solves on uploaded matrices) are expanded on demand by k_expand_records.
+// ===========================================================================
+struct CompactPattern {
+  int NI;                      // items per record
+  int NIp;                     // floats per compact record
+  const uint2* gk;             // g_k CSR entries: x = q item | l item << 16, y = player
+  const int* gk_start;         // [n + 1]
+};
+
+constexpr unsigned kItemReg = 0xFFF0u;  // item code 0xFFF0 + i: the constant state_reg[i] (template diagonal of Q_i)
+
+// shared memory: xu[n+M][32] | vals[NR][E][33] | itemv[NR][NIp] | gather table SoA | idx (u16)
+__host__ __device__ inline size_t klq4_smem_bytes(int n, int M, int N, int E, int NIp, int num_items, int num_idx) {
+  const int NR = N + 1;
+  size_t b = sizeof(float) * ((size_t)(n + M) * 32 + (size_t)NR * E * kValStride + (size_t)NR * NIp);
+  b += 4 * sizeof(int) * (size_t)num_items;
+  b += sizeof(unsigned short) * (size_t)((num_idx + 7) & ~7);
+  return b;
+}
+
+__global__ void __launch_bounds__(160)
+k_linearize_quadraticize_v4(const __grid_constant__ DevDesc d, Slab s, RecordPattern pat, CompactPattern cp,
+                            int only_running, Sel sel) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = d.n, M = d.M, N = d.N, T = d.T, NR = N + 1, E = pat.E;
+  float* xu = smem;                                        // [n+M][32]
+  float* vals = xu + (n + M) * 32;                         // [NR][E][33]
+  float* itembuf = vals + (size_t)NR * E * kValStride;     // [NR][NIp]
+  const int NI = pat.num_items;
+  int* g_meta = reinterpret_cast<int*>(itembuf + (size_t)NR * cp.NIp);  // role | count << 8 | start << 16
+  float* g_base = reinterpret_cast<float*>(g_meta + NI);             // [NI]
+  unsigned* g_e01 = reinterpret_cast<unsigned*>(g_base + NI);        // entries 0,1
+  unsigned* g_e23 = g_e01 + NI;                                      // entries 2,3
+  unsigned short* gidx = reinterpret_cast<unsigned short*>(g_e23 + NI);
+
+  const long long first = (long long)blockIdx.x * 32;
+  const long long total = (long long)s.B * T;
+  const long long w = first + lane;
+  bool live = false;
+  const int b_sel = w < total ? sel_instance(s, sel, (int)(w / T), only_running, &live) : -1;
+  const bool in_range = b_sel >= 0;
+  const int b = in_range ? b_sel : 0, k = in_range ? (int)(w % T) : 0;
+  if (!__syncthreads_or(live)) return;
+
+  {
+    const int cur = in_range ? s.op_cur[b] : 0;
+    const float* xs = s.op_xs[cur] + ((size_t)b * T + k) * n;
+    const float* us = s.op_us[cur] + ((size_t)b * T + k) * M;
+    for (int e = warp; e < n + M; e += NR) xu[e * 32 + lane] = in_range ? (e < n ? xs[e] : us[e - n]) : 0.f;
+    for (int e = threadIdx.x; e < NI; e += blockDim.x) {
+      const GatherItem it = pat.items[e];
+      g_meta[e] = it.role | (it.count << 8) | (it.start << 16);
+      g_base[e] = it.base;
+      g_e01[e] = (unsigned)it.e[0] | ((unsigned)it.e[1] << 16);
+      g_e23[e] = (unsigned)it.e[2] | ((unsigned)it.e[3] << 16);
+    }
+    for (int e = threadIdx.x; e < pat.num_idx; e += blockDim.x) gidx[e] = pat.idx[e];
+  }
+  __syncthreads();
+
+  // ---- phase 1: role = warp, record = lane: update values only (as v3) ----
+  {
+    ValueSink sink;
+    sink.val = vals + (size_t)warp * E * kValStride;
+    sink.lane = lane;
+    sink.cnt = 0;
+    sink.cap = E;
+    const float* x = xu + lane;
+    const float* u = xu + n * 32 + lane;
+    const float mu = live ? s.mu[b] : 0.f;
+    const bool full = warp < N && (d.cost_structure[warp] == ILQG_COST_SUM ||
+                                   (live && s.te_quad[(size_t)b * N + warp] == k));
+    walk_role<32>(
+        d, warp,
+        [&](const DevCost& cd) {
+          const bool is_con = cd.slot >= 0;
+          const int dim = cd.arg < 0 ? n : d.udim[cd.arg];
+          if (!full && (cd.arg < 0 || is_con)) {
+            const int cnt = record_updates(cd, dim);
+            for (int e = 0; e < cnt; e++) sink.push(0.f);
+            return;
+          }
+          const float lambda =
+              (is_con && live) ? s.lambdas[((size_t)b * d.num_constraints + cd.slot) * T + s.lambda_index[k]] : 0.f;
+          const float* in = cd.arg < 0 ? x : u + d.uoff[cd.arg] * 32;
+          quadraticize_record_sink<true, 32, false>(d, cd, in, dim, lambda, mu, sink);
+        },
+        [&](const DevSubsystem& sub) {
+          LinValueSink lin{&sink};
+          subsystem_linearize_sink<32>(d, sub, x, u, lin);
+        });
+  }
+  __syncthreads();
+  int* flags = reinterpret_cast<int*>(xu);
+  if (warp == 0) flags[lane] = live ? b + 1 : 0;
+  __syncthreads();
+
+  // ---- phase 2: warp w turns records w, w + NR, ... into item values + g_k ----
+  float* itv = itembuf + (size_t)warp * cp.NIp;
+  for (int r = warp; r < 32; r += NR) {
+    const long long wr = first + r;
+    if (wr >= total) break;
+    if (!flags[r]) continue;
+    for (int g = lane; g < NI; g += 32) {
+      const int meta = g_meta[g];
+      const int role = meta & 0xff, count = (meta >> 8) & 0xff, start = meta >> 16;
+      const float* v = vals + (size_t)role * E * kValStride + r;
+      float acc = g_base[g];
+      if (count <= 4) {
+        const unsigned e01 = g_e01[g], e23 = g_e23[g];
+        if (count > 0) acc += v[(e01 & 0xffff) * kValStride];
+        if (count > 1) acc += v[(e01 >> 16) * kValStride];
+        if (count > 2) acc += v[(e23 & 0xffff) * kValStride];
+        if (count > 3) acc += v[(e23 >> 16) * kValStride];
+      } else {
+        for (int t = 0; t < count; t++) acc += v[gidx[start + t] * kValStride];
+      }
+      itv[g] = acc;
+    }
+    __syncwarp();
+    // g_k[a] = sum_i (sum_c Q_i[a][c] l_i[c]): per-player fma chains over the non-zero terms, in
+    // ascending c (what the dense sweep computed, zeros skipped)
+    float gk = 0.f;
+    if (lane < n) {
+      int cur = -1;
+      float gi = 0.f;
+      const int e1 = __ldg(cp.gk_start + lane + 1);
+      for (int e = __ldg(cp.gk_start + lane); e < e1; e++) {
+        const uint2 u = __ldg(cp.gk + e);
+        if ((int)u.y != cur) { gk += gi; gi = 0.f; cur = (int)u.y; }
+        const unsigned qi = u.x & 0xffffu;
+        const float qv = qi >= kItemReg ? d.state_reg[qi - kItemReg] : itv[qi];
+        gi = fmaf(qv, itv[u.x >> 16], gi);
+      }
+      gk += gi;
+    }
+    float* dst = s.crec + ((size_t)(flags[r] - 1) * T + (size_t)(wr % T)) * cp.NIp;
+    for (int g = lane; g < NI; g += 32) dst[g] = itv[g];
+    if (lane < n) dst[NI + lane] = gk;
+    if (lane < N) dst[NI + n + lane] = d.state_reg[lane];  // constants the sweep adds to the diagonal of Q_i
+    __syncwarp();
+  }
+}
+
+// dense records from compact ones: template + items (one warp per record)
+__global__ void __launch_bounds__(128)
+k_expand_records(const __grid_constant__ DevDesc d, Slab s, RecordPattern pat, CompactPattern cp) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * 4 + warp;
+  if (w >= (long long)s.B * d.T) return;
+  float* dst = s.rec + (size_t)w * d.rec;
+  const float* src = s.crec + (size_t)w * cp.NIp;
+  for (int e = lane; e < d.rec / 4; e += 32)
+    reinterpret_cast<float4*>(dst)[e] = __ldg(reinterpret_cast<const float4*>(pat.tmpl) + e);
+  __syncwarp();
+  for (int g = lane; g < cp.NI; g += 32) dst[pat.items[g].off] = src[g];
+}
+
 }  // namespace ilqg
