@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""bench.py -- iLQ iterations/s on a batch of ThreePlayerIntersection games (T = 100).
+"""bench.py -- iLQ iterations/s on a batch of ThreePlayerIntersection games (T = 100); with
+`--config c1..c5` the same measurement on each configuration BASELINE.json lists.
 
 Contract (see the task prompt): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
 line; for N > 1 it is launched under torch.distributed.run, one rank per GPU.
@@ -38,13 +39,42 @@ ORACLE_LIB = os.path.join(REPO, "oracle", "_build", "libilqg_oracle.so")
 REF_BUILD_LIB = os.path.join(REPO, "oracle", "_ref", "libilqg_ref.so")
 
 
-def workload(batch: int, seed: int):
+# BASELINE.json's configurations.  `metric` (the default) is the one the metric string is quoted on;
+# c1..c5 are BASELINE.json `configs[0..4]` at their stated batch and horizon (reference-true state
+# dimensions: SURVEY.md section 8 "Shapes at BASELINE configs").  batch = per GPU.
+CONFIGS = {
+    "metric": dict(problem="three_player_intersection", batch=4096, T=100,
+                   label="ThreePlayerIntersection (2x car6d + unicycle4d, n=16, m=(2,2,2))"),
+    "c1": dict(problem="three_player_intersection", batch=1, T=100,
+               label="ThreePlayerIntersection single instance (the reference's own exec; plumbing)"),
+    "c2": dict(problem="three_player_intersection", batch=1024, T=100,
+               label="ThreePlayerIntersection (reference-true n=16; BASELINE.json states n=12), randomized x0"),
+    "c3": dict(problem="roundabout_merging", batch=4096, T=150, label="RoundaboutMerging (4x car6d, n=24, m=(2,2,2,2))"),
+    "c4": dict(problem="air_3d", batch=16384, T=50, label="Air3D two-player zero-sum (n=3, m=(1,1)), x0 grid sweep"),
+    "c5": dict(problem="three_player_intersection", batch=8192, T=100,
+               label="ThreePlayerIntersection sharded, 8192 games per GPU (65536 on 8)"),
+}
+
+
+def workload(config: str, batch: int, seed: int, lo: int = 0, hi: int = None):
+    """Descriptor, solver parameters and rows [lo, hi) of the GLOBAL batch of `batch` initial states."""
     from ilqgames_b200 import problems
-    desc, _ = problems.three_player_intersection()
-    params = problems.three_player_intersection_params(max_solver_iters=ITERS_PER_SOLVE,
-                                                       disable_convergence_exit=1)
-    x0 = problems.three_player_intersection_x0_batch(batch, seed)
-    return desc, params, x0
+    c = CONFIGS[config]
+    kw = dict(max_solver_iters=ITERS_PER_SOLVE, disable_convergence_exit=1)
+    if c["problem"] == "three_player_intersection":
+        desc, _ = problems.three_player_intersection(num_time_steps=c["T"])
+        params = problems.three_player_intersection_params(**kw)
+        x0 = problems.three_player_intersection_x0_batch(batch, seed)
+    elif c["problem"] == "roundabout_merging":
+        desc, _ = problems.roundabout_merging(num_time_steps=c["T"])
+        params = problems.roundabout_params(**kw)
+        x0 = problems.roundabout_x0_batch(batch, seed)
+    else:
+        desc, _ = problems.air_3d(num_time_steps=c["T"])
+        params = problems.air_3d_params(**kw)
+        side = int(np.ceil(np.sqrt(batch)))
+        x0 = problems.air_3d_x0_grid(side)[:batch]
+    return desc, params, np.ascontiguousarray(x0[lo:hi])
 
 
 def usable_cores() -> int:
@@ -62,29 +92,33 @@ def usable_cores() -> int:
     return cores
 
 
-def bench_config(batch: int, world: int, seed: int) -> dict:
+def bench_config(config: str, batch: int, world: int, seed: int) -> dict:
     """The workload description shared by both arms (same `config` keys)."""
-    return {"workload": f"batch {batch} ThreePlayerIntersection (2x car6d + unicycle4d, n=16, m=(2,2,2)), T=100, "
+    c = CONFIGS[config]
+    return {"workload": f"batch {batch} {c['label']}, T={c['T']}, "
                         f"{ITERS_PER_SOLVE} iLQ iterations/solve, lambda=0 mu=10, convergence exit disabled",
-            "batch_per_gpu": batch, "global_batch": batch * world, "iterations_per_step": ITERS_PER_SOLVE,
-            "seed": seed}
+            "config": config, "batch_per_gpu": batch, "global_batch": batch * world,
+            "iterations_per_step": ITERS_PER_SOLVE, "seed": seed}
 
 
 def algorithmic_bytes(layout) -> dict:
-    """Per instance-iteration algorithmic bytes of each kernel (SURVEY.md section 8d byte model,
-    DESIGN.md section 5): fp32 slab terms of the dense-record design."""
+    """Per instance-iteration algorithmic bytes of each kernel.  `dense`: SURVEY.md section 8d's byte
+    model (lin / quad materialised once in HBM) -- the figure `roofline.achieved` is defined on.
+    `compact`: what the round-2 kernels are designed to move (compact records: item values + g_k)."""
     T, n, M, N = layout.num_time_steps, layout.xdim, layout.total_udim, layout.num_players
     op = T * (n + M)
     AB = T * (n * n + n * M)
     QR = T * (N * (n * n + n) + layout.R_floats + layout.r_floats)
-    Ql = T * N * (n * n + n)
     Pa = T * (M * n + M)
-    dx = T * n
-    return {
+    crec = T * layout.compact_record_floats
+    out = {
         "linearize_quadraticize": 4 * (op + AB + QR),
         "lq_backward": 4 * (AB + QR + Pa),  # records read once, strategy written once
         "linesearch_per_rollout": 4 * (2 * op + Pa),
     }
+    if crec:
+        out["compact"] = {"linearize_quadraticize": 4 * (op + crec), "lq_backward": 4 * (crec + Pa)}
+    return out
 
 
 # ------------------------------------------------------------------------- clocks
@@ -165,10 +199,13 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------- CPU arm
+_CFG = "metric"   # the configuration of this run (set in main, inherited by forked workers)
+
+
 def _oracle_worker(args):
     x0, iters = args
     from ilqgames_b200 import _abi as abi
-    desc, params, _ = workload(1, 0)
+    desc, params, _ = workload(_CFG, 1, 0)
     lib = abi.Library(ORACLE_LIB)
     h = abi.Handle(lib, desc, params, x0.shape[0])
     h.upload_x0(x0)
@@ -194,17 +231,19 @@ def cpu_reference_build(x0_sample):
     next to the port, not instead of it: the stand-in's dense kernels are plain loops, so this is a
     lower bound on what the reference built on real Eigen would do.  None when the library was not
     built (it needs /root/reference at build time)."""
-    if not os.path.exists(REF_BUILD_LIB):
-        return None
+    if not os.path.exists(REF_BUILD_LIB) or CONFIGS[_CFG]["T"] != 100:
+        return None  # (the reference's example Problems are built with T = 100)
     from tests.golden import ref_lib
     ref = ref_lib.RefLibrary(REF_BUILD_LIB)
-    _, params, _ = workload(1, 0)
+    _, params, _ = workload(_CFG, 1, 0)
+    which = {"three_player_intersection": ref_lib.INTERSECTION, "roundabout_merging": ref_lib.ROUNDABOUT,
+             "air_3d": ref_lib.AIR3D}[CONFIGS[_CFG]["problem"]]
     rp = ref_lib.RefParams.from_abi(params)
     rp.convergence_tolerance = 0.0   # HasConverged needs |delta| < tolerance: never, like the GPU arm
     t = time.perf_counter()
     done = 0
     for x in x0_sample:
-        done += ref.solve(ref_lib.INTERSECTION, ref_lib.ILQ, x, rp, mu0=10.0, max_log=1)["iterates"] - 1
+        done += ref.solve(which, ref_lib.ILQ, x, rp, mu0=10.0, max_log=1)["iterates"] - 1
     dt = time.perf_counter() - t
     return {"value": done / dt, "unit": "instance-iterations/s", "cores": 1,
             "sample": f"{len(x0_sample)} instances, {dt:.1f} s; reference sources on oracle/ref_shim (no Eigen3 in the image)"}
@@ -215,7 +254,7 @@ _worker_state = {}
 
 def _worker_init():
     from ilqgames_b200 import _abi as abi
-    desc, params, _ = workload(1, 0)
+    desc, params, _ = workload(_CFG, 1, 0)
     _worker_state["abi"] = abi
     _worker_state["lib"] = abi.Library(ORACLE_LIB)
     _worker_state["desc"], _worker_state["params"] = desc, params
@@ -245,8 +284,8 @@ def run_reference(args):
         return
     cores = usable_cores()
     per_worker = 16
-    _, _, x0 = workload(args.batch, args.seed)
-    sample = x0[: min(args.batch, cores * per_worker)]
+    _, _, x0 = workload(args.config, args.batch, args.seed, 0, min(args.batch, cores * per_worker))
+    sample = x0
     chunks = [c for c in np.array_split(sample, cores) if len(c)]
     ctx = mp.get_context("fork")
     times = []
@@ -266,7 +305,11 @@ def run_reference(args):
         "unit": "instance-iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": bench_config(args.batch, 1, args.seed),
+        # same workload description as the repo arm; the CPU arm's step is a bounded SAMPLE of it
+        "config": dict(bench_config(args.config, args.batch, 1, args.seed), reference_sample_instances=len(sample),
+                       reference_sample=f"each step solves the first {len(sample)} of the {args.batch} instances "
+                                        f"({len(chunks)} processes x {per_worker}); throughput per instance-iteration "
+                                        "does not depend on the batch on the CPU"),
         "cpu_baseline": {"value": value, "unit": "instance-iterations/s", "cores": len(chunks), "kind": "port",
                          "sample": f"first {len(sample)} instances of the batch x {ITERS_PER_SOLVE} iterations per step, "
                                    f"{len(chunks)} processes; oracle port of the reference's Eigen path: faster than "
@@ -303,9 +346,12 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # each rank owns a contiguous slice of the global batch: independent games, no hot-path
-    # collective; seed differs per rank
-    desc, params, x0 = workload(args.batch, args.seed + rank)
+    # ONE global batch of world x batch games; each rank owns a contiguous slice of it (weak scaling:
+    # fixed games per GPU): independent games, no hot-path collective
+    from ilqgames_b200 import sharding
+    lo_row, hi_row = sharding.shard_bounds(args.batch * world, world, rank)
+    desc, params, x0 = workload(args.config, args.batch * world, args.seed, lo_row, hi_row)
+    assert x0.shape[0] == args.batch
     lib = abi.product_library()
     h = abi.Handle(lib, desc, params, args.batch, local)
     # a non-default torch stream so torch.cuda.Event and the library's launches share it
@@ -330,26 +376,38 @@ def run_b200(args):
         solve()
     barrier()
     launches0 = h.kernel_launches()
+    # working set of one iteration (records + both strategy buffers): above the 126 MB L2 for every
+    # batched configuration; the small ones (c1) get an explicit L2 flush before each timed step
+    lo_ = h.layout
+    ws_mb = args.batch * lo_.num_time_steps * 4 * ((lo_.compact_record_floats or lo_.record_floats)
+                                                   + 2 * lo_.total_udim * (lo_.xdim + 1)) / 1e6
+    need_flush = ws_mb <= 126
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if need_flush else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
-        ev0.record(stream)
-        for _ in range(args.steps):
-            solve()
-        ev1.record(stream)
-        barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
+        if not need_flush:
+            ev0.record(stream)
+            for _ in range(args.steps):
+                solve()
+            ev1.record(stream)
+            barrier()
+            elapsed_ms = ev0.elapsed_time(ev1)
+        else:
+            elapsed_ms = 0.0
+            for _ in range(args.steps):
+                flush_buf.zero_()
+                ev0.record(stream)
+                solve()
+                ev1.record(stream)
+                torch.cuda.synchronize()
+                elapsed_ms += ev0.elapsed_time(ev1)
+            barrier()
     launches = h.kernel_launches() - launches0
     iters = h.download(abi.ITERS)
     rollouts = h.download(abi.BACKTRACKS)  # cumulative over all solves since creation
     status = h.download(abi.STATUS)
     done_per_step = int(iters.sum())
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([done_per_step], dtype=torch.int64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    max_ms = float(t.item())
-    total_done_per_step = int(cnt.item())
+    max_ms, total_done_per_step = sharding.reduce_metrics(elapsed_ms, done_per_step, device="cuda")
     value = total_done_per_step * args.steps / (max_ms * 1e-3)
 
     # ---- per-kernel profile pass (not part of the timed region above) ----------------
@@ -379,6 +437,29 @@ def run_b200(args):
     prof = hp.profile_read()
     hp.profile(False)
     roll_per_step = (int(hp.download(abi.BACKTRACKS).sum()) - roll_before) / prof_steps
+    # how the linesearches of one solve end, iteration by iteration (one extra solve, stepped):
+    # accepted at the first candidate / after backtracking / failed (all candidates rejected)
+    hp.reset(hp.RESET_SOLVER)
+    hp.solve_begin()
+    prev_roll, prev_it = hp.download(abi.BACKTRACKS).astype(np.int64), hp.download(abi.ITERS).astype(np.int64)
+    first_try = backtracked = failed = rolls_bt = 0
+    max_bt = int(params.max_backtracking_steps)
+    for _ in range(ITERS_PER_SOLVE):
+        hp.iterate(1)
+        roll, itn, st = (hp.download(w).astype(np.int64) for w in (abi.BACKTRACKS, abi.ITERS, abi.STATUS))
+        d_roll, d_it = roll - prev_roll, itn - prev_it
+        did = d_it > 0
+        fail_now = did & (st == abi.STATUS_LINESEARCH_FAILED) & (d_roll == max_bt + 1)
+        first_try += int((did & (d_roll == 1)).sum())
+        failed += int(fail_now.sum())
+        bt = did & (d_roll > 1) & ~fail_now
+        backtracked += int(bt.sum())
+        rolls_bt += int(d_roll[bt].sum())
+        prev_roll, prev_it = roll, itn
+    total_ls = max(first_try + backtracked + failed, 1)
+    ls_split = {"accepted_first_try": first_try / total_ls, "backtracked": backtracked / total_ls,
+                "failed": failed / total_ls, "mean_rollouts_when_backtracked": rolls_bt / max(backtracked, 1),
+                "rollouts_of_a_failed_linesearch": max_bt + 1, "linesearches": total_ls}
     hp.close()
     kern = {}
     for name, (ms, n) in prof.items():
@@ -397,6 +478,7 @@ def run_b200(args):
         "linearize_quadraticize": bytes_model["linearize_quadraticize"] * inst_iters_per_launch,
         "lq_backward": bytes_model["lq_backward"] * inst_iters_per_launch,
     }
+    compact_bytes = {k: v * inst_iters_per_launch for k, v in bytes_model.get("compact", {}).items()}
     if "ls_eval" in kern:
         per_kernel_bytes["ls_eval"] = bytes_model["linesearch_per_rollout"] * roll_per_step / kern["ls_eval"]["launches_per_step"]
     hot = [k for k in ("linearize_quadraticize", "lq_backward", "ls_eval") if k in kern]
@@ -409,13 +491,22 @@ def run_b200(args):
     achieved = per_kernel_bytes[dominant] / (kern[dominant]["ms_per_launch"] * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(REPO, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(dominant)
+    if os.path.exists(tpath) and args.config == "metric":
+        traffic = json.load(open(tpath)).get(dominant)  # ncu --set full, per launch, metric configuration
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": per_kernel_bytes[dominant],
+                "byte_model": "SURVEY 8(d): dense lin/quad records materialised once in HBM; the round-2 kernels move "
+                              "compact records instead (designed_bytes_per_launch), so `traffic` sits far below "
+                              "the algorithmic bytes",
+                "designed_bytes_per_launch": compact_bytes.get(dominant),
                 "kernels": {k: dict(v, algorithmic_GBps=per_kernel_bytes[k] / (v["ms_per_launch"] * 1e-3) / 1e9
-                                    if k in per_kernel_bytes else None) for k, v in kern.items()}}
+                                    if k in per_kernel_bytes else None,
+                                    designed_GBps=compact_bytes[k] / (v["ms_per_launch"] * 1e-3) / 1e9
+                                    if k in compact_bytes else None) for k, v in kern.items()}}
+    l2_note = (f"one iteration streams {ws_mb:.0f} MB (LQ records + both strategy buffers) per {args.batch} instances: "
+               + ("fits the 126 MB L2, so a 256 MB write flushes L2 before every timed step" if need_flush
+                  else "exceeds the 126 MB L2, no explicit flush"))
 
     # ---- end to end through the C ABI with host buffers ------------------------------
     pin_x0 = torch.from_numpy(x0).pin_memory()
@@ -445,12 +536,8 @@ def run_b200(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_done = int(pin_iters.sum().item())
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    ce = torch.tensor([e2e_done], dtype=torch.int64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        dist.all_reduce(ce, op=dist.ReduceOp.SUM)
-    e2e_value = int(ce.item()) * e2e_steps / float(te.item())
+    e2e_max_s, e2e_total = sharding.reduce_metrics(e2e_s, e2e_done, device="cuda")
+    e2e_value = e2e_total * e2e_steps / e2e_max_s
 
     # ---- gather of converged trajectories over NCCL (off the hot path, reported apart) ----
     gather_ms = None
@@ -484,11 +571,12 @@ def run_b200(args):
             "metric": "ilq_instance_iterations_per_second", "value": value, "unit": "instance-iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(bench_config(args.batch, world, args.seed),
+            "config": dict(bench_config(args.config, args.batch, world, args.seed),
                            instance_iterations_per_step=total_done_per_step,
                            mean_rollouts_per_iteration=roll_per_step / max(done_per_step, 1),
                            status_histogram_rank0=hist,
-                           l2="working set per step (LQ records ~1.9 GB per 4096 instances) exceeds the 126 MB L2",
+                           linesearch_split=ls_split,
+                           l2=l2_note,
                            parallelism=f"dp{world} (independent games, no hot-path collective)"),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "instance-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -561,13 +649,20 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="instances per GPU")
+    ap.add_argument("--config", default="metric", choices=sorted(CONFIGS),
+                    help="metric (default: the batch-4096 configuration BASELINE.json's metric is quoted on) or "
+                         "c1..c5 = BASELINE.json configs[0..4]")
+    ap.add_argument("--batch", type=int, default=None, help="instances per GPU (default: the configuration's)")
     ap.add_argument("--seed", type=int, default=4096)
     ap.add_argument("--cpu-sample", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--with-al", action="store_true",
                     help="also time the full augmented-Lagrangian solve of the batch (adds `al_solve`; N = 1 only)")
     args = ap.parse_args()
+    global _CFG
+    _CFG = args.config
+    if args.batch is None:
+        args.batch = CONFIGS[args.config]["batch"]
     if args.impl == "reference":
         run_reference(args)
     else:

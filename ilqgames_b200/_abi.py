@@ -103,7 +103,8 @@ class Layout(C.Structure):
                 ("pair_player", C.c_int32 * MAX_PAIRS), ("pair_arg", C.c_int32 * MAX_PAIRS),
                 ("pair_R_offset", C.c_int32 * MAX_PAIRS), ("pair_r_offset", C.c_int32 * MAX_PAIRS),
                 ("R_floats", C.c_int32), ("r_floats", C.c_int32), ("num_constraints", C.c_int32),
-                ("record_floats", C.c_int32), ("lambda_index", C.c_int32 * MAX_TIME_STEPS)]
+                ("record_floats", C.c_int32), ("lambda_index", C.c_int32 * MAX_TIME_STEPS),
+                ("compact_record_floats", C.c_int32)]
 
 
 # every symbol include/ilqg.h declares (checked by tests/test_abi.py)

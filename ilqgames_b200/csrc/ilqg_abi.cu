@@ -9,6 +9,7 @@
 #include <new>
 #include <vector>
 
+#include "ilqg_backward_any.cuh"
 #include "ilqg_backward_tc.cuh"
 #include "ilqg_linesearch.cuh"
 #include "ilqg_open_loop.cuh"
@@ -267,6 +268,7 @@ int BuildDeviceDesc(const ilqg_problem_desc& h, DevDesc* d, ilqg_layout* lo, std
   lo->r_floats = d->r_floats;
   lo->num_constraints = d->num_constraints;
   lo->record_floats = d->rec;
+  lo->compact_record_floats = 0;
   for (int kk = 0; kk < d->T; kk++) lo->lambda_index[kk] = (*lidx)[kk];
   return ILQG_OK;
 }
@@ -281,7 +283,7 @@ constexpr DimsEntry kDims[] = {
     {24, 8, 4},  // RoundaboutMerging: 4x Car6D
     {3, 2, 2},   // Air3D
     {2, 2, 2},   // test/test_lq_solver.cpp point-mass LQ game
-    {12, 6, 3},  // BASELINE.json's "3x unicycle4d" variant
+    {-1, -1, -1},  // (was the n = 12 half-warp instance: never reached by a test, removed)
     {18, 6, 3},  // ThreePlayerOvertaking: 3x Car6D (warp-per-game kernel: 18 is not a multiple of 4)
 };
 constexpr int kNumDims = sizeof(kDims) / sizeof(kDims[0]);
@@ -432,15 +434,27 @@ int DispatchBackward(SubSolver* h, int only_running, bool with_dxs, Sel sel = Se
   int key = h->dims_key;
   // the half-warp kernel hard-codes a uniform control dimension m = M / N: anything
   // else must not reach it
-  if (key == 0 || key == 1 || key == 4)
+  if (key == 0 || key == 1)
     for (int i = 0; i < h->d.N; i++)
       if (h->d.udim[i] * h->d.N != h->d.M) key = -1;
+  if (key < 0 || (sel.mode != SEL_ALL && (key == 2 || key == 3 || key == 5))) {
+    // any other shape (and list / main selections on the warp kernels' shapes never occur: those
+    // handles do not pipeline): the run-time-dimension kernel, which writes delta_xs itself
+    if (sel.mode != SEL_ALL) return ILQG_ERR_UNSUPPORTED;
+    const size_t smem = sizeof(float) * KANY_WARPS * (size_t)any_smem_floats(h->d.n, h->d.M, h->d.N, h->d.rec);
+    if ((rc = SetSmem(k_lq_backward_any, smem)) != ILQG_OK) return rc;
+    ProfScope prof(h, 1);
+    k_lq_backward_any<<<(h->B + KANY_WARPS - 1) / KANY_WARPS, KANY_WARPS * 32, smem, h->stream>>>(
+        h->d, h->p, h->s, only_running, with_dxs ? h->s.lq_x0 : nullptr);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ILQG_OK;
+  }
   switch (key) {
     case 0: rc = LaunchBackwardHw<16, 6, 3>(h, only_running, sel); break;
     case 1: rc = LaunchBackwardHw<24, 8, 4>(h, only_running, sel); break;
     case 2: rc = LaunchBackward<3, 2, 2>(h, only_running, sel); hw = false; break;
     case 3: rc = LaunchBackward<2, 2, 2>(h, only_running, sel); hw = false; break;
-    case 4: rc = LaunchBackwardHw<12, 6, 3>(h, only_running, sel); break;
     case 5: rc = LaunchBackward<18, 6, 3>(h, only_running, sel); hw = false; break;
   }
   if (rc == ILQG_OK && hw && with_dxs) {
@@ -630,6 +644,7 @@ int BuildCompactTables(SubSolver* h, const std::vector<GatherItem>& items) {
   h->tc_nxp = NXP;
   h->tc_mup = MUP;
   h->cp_ok = true;
+  if (h->use_compact) h->layout.compact_record_floats = NIp;
   return ILQG_OK;
 }
 
@@ -897,7 +912,7 @@ int IteratePipelined(SubSolver* h, int n) {
 // the pipelined schedule needs the list-capable kernels (static K_lq, half-warp K_bwd) and a
 // single queued window; per-kernel profiling wants every kernel alone on the device
 bool CanPipeline(const SubSolver* h, int max_iters) {
-  const bool hw = h->dims_key == 0 || h->dims_key == 1 || h->dims_key == 4 || (h->cp_ok && h->use_compact);
+  const bool hw = h->dims_key == 0 || h->dims_key == 1 || (h->cp_ok && h->use_compact);
   const bool one_window = h->ls.JB >= std::max(1, h->p.max_backtracking_steps) - h->ls.JA;
   return h->pipeline && !h->open_loop && max_iters > 1 && h->pat_ok && hw && one_window && h->p.linesearch && !h->profiling;
 }
@@ -1214,7 +1229,6 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
   if ((rc = Fill(h, s.max_con_err, INFINITY, B)) != ILQG_OK) return fail(rc);
   if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(ILQG_ERR_CUDA);
   if ((rc = BuildRecordPattern(h)) != ILQG_OK) return fail(rc);
-  if (h->dims_key < 0 && !h->open_loop && !(h->cp_ok && h->use_compact)) return fail(ILQG_ERR_UNSUPPORTED);
   *out = h;
   return ILQG_OK;
 }

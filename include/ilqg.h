@@ -217,6 +217,8 @@ typedef struct {
   int32_t num_constraints;
   int32_t record_floats;                /* device LQ record size per (b,k)   */
   int32_t lambda_index[ILQG_MAX_TIME_STEPS]; /* kk -> Constraint::TimeIndex */
+  int32_t compact_record_floats;        /* floats per (b,k) of the compact LQ records the iLQ hot path
+                                         * streams instead of dense ones (0: dense records only)   */
 } ilqg_layout;
 
 /* Per-instance status word (replaces `has_converged` / `*success`,

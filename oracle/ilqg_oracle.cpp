@@ -1818,6 +1818,7 @@ int ilqg_get_layout(ilqg_handle h, ilqg_layout* out) {
   out->r_floats = pr.r_floats;
   out->num_constraints = pr.num_constraints;
   out->record_floats = 0;
+  out->compact_record_floats = 0;
   for (int kk = 0; kk < pr.T; kk++) out->lambda_index[kk] = pr.lambda_index[kk];
   return ILQG_OK;
 }

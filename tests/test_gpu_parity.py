@@ -25,6 +25,19 @@ pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 STAGE_TOL = 1e-4
+# Fraction of the well-posed games on which the CUDA path must take exactly the oracle's Armijo
+# decisions (status, iteration count, backtrack count).  Measured on B200 in round 2 with the counts
+# every test now reports (gpurun_out/parity_counts.jsonl -> profiles/r02_parity_counts.md): the
+# thresholds sit a margin below the measured fractions.
+FLOW_MIN = 0.85
+
+
+def flow_ok(flow, stable):
+    """At least FLOW_MIN of the stable games follow the oracle's control flow; with a handful of
+    stable games one stray knife-edge decision is allowed (1 of 6 is already below 85 %)."""
+    n = int(stable.sum())
+    misses = int((stable & ~flow).sum())
+    return misses <= max(1, int((1.0 - FLOW_MIN) * n))
 
 CONFIGS = {
     "three_player_intersection": (problems.three_player_intersection,
@@ -32,12 +45,28 @@ CONFIGS = {
                                   lambda b: problems.three_player_intersection_x0_batch(b, 1024)),
     "roundabout_merging": (problems.roundabout_merging, problems.roundabout_params,
                            lambda b: problems.roundabout_x0_batch(b, 4096)),
-    "air_3d": (problems.air_3d, problems.air_3d_params, lambda b: problems.air_3d_x0_grid(4)[:b]),
+    # 8 x 8 grid of relative positions (round 1 used a 4 x 4 grid: "batch 36" was really 16 games)
+    "air_3d": (problems.air_3d, problems.air_3d_params, lambda b: problems.air_3d_x0_grid(8)[:b]),
     # widening: a fourth example of the reference, same record kinds, n = 18
     "three_player_overtaking": (problems.three_player_overtaking, problems.three_player_overtaking_params,
                                 lambda b: problems.three_player_overtaking_x0_batch(b, 18)),
 }
 HEADLINE = ["air_3d", "roundabout_merging", "three_player_intersection"]
+
+
+COUNTS = os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out", "parity_counts.jsonl")
+
+
+def report(test, **numbers):
+    """Every masked comparison says how much it compared: printed (pytest -s / -rP) and appended to
+    gpurun_out/parity_counts.jsonl when that directory exists (the GPU box's scratch)."""
+    import json
+    line = json.dumps({"test": test, **{k: (float(v) if isinstance(v, (float, np.floating)) else int(v))
+                                        for k, v in numbers.items()}})
+    print("[parity]", line)
+    if os.path.isdir(os.path.dirname(COUNTS)):
+        with open(COUNTS, "a") as f:
+            f.write(line + "\n")
 
 
 def tame(ref, limit=1e6):
@@ -49,26 +78,45 @@ def tame(ref, limit=1e6):
     return np.isfinite(r).all(axis=1) & (np.abs(r).max(axis=1, initial=0.0) < limit)
 
 
-def close(a, b, tol=STAGE_TOL, what="", atol=1e-5, rows=None):
+def close(a, b, tol=STAGE_TOL, what="", atol=1e-5, rows=None, cond=None):
     """max|a - b| <= tol * max|b| + atol per instance row (norm-wise; atol absorbs cancellation
-    to ~0), over the rows where the oracle is tame."""
+    to ~0), over the rows where the oracle is tame.
+
+    cond (optional): per-row max|o32 - o64| of the same quantity, the fp32 oracle's OWN distance to
+    the fp64 answer.  A row is held to `tol` plus 4 x that distance: the tensor-core sweep does not
+    share the oracle's rounding (3xTF32 products, different summation order), so on an
+    ill-conditioned game -- one the oracle itself only resolves to 4e-4 -- it cannot sit within 1e-4
+    of the fp32 oracle, only within a small multiple of the oracle's own error (measured:
+    median 2.2 x for P, 1.0 x for alpha, tools/stage_errors.py).  Well-conditioned rows
+    (cond ~ 1e-6 of scale) keep the plain tolerance.  Returns the number of rows compared."""
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     assert a.shape == b.shape
     finite = np.isfinite(b.reshape(len(b), -1)).all(axis=1)
     keep = finite if rows is None else (rows & finite)
     if not keep.any():
-        return
+        return 0
     if a.ndim == 1:
         a, b = a[:, None], b[:, None]
     a, b = a[keep].reshape(keep.sum(), -1), b[keep].reshape(keep.sum(), -1)
     if a.size == 0:
-        return
+        return 0
     scale = np.abs(b).max(axis=1)
     err = np.abs(a - b).max(axis=1)
-    bad = ~(err <= tol * scale + atol)
+    slack = 0.0 if cond is None else 4.0 * np.asarray(cond, np.float64)[keep]
+    bad = ~(err <= tol * scale + atol + slack)
     assert not bad.any(), (f"{what}: worst row max|d| = {np.nanmax(err[bad]) if bad.any() else 0:.3e}, "
                            f"scale = {scale[bad][0]:.3e}, {bad.sum()} of {len(bad)} rows")
+    return int(keep.sum())
+
+
+def row_distance(o32, o64):
+    """Per-row max|o32 - o64| (nan / inf -> inf): the `cond` argument of close()."""
+    a = np.asarray(o32, np.float64).reshape(len(o32), -1)
+    b = np.asarray(o64, np.float64).reshape(len(o64), -1)
+    with np.errstate(invalid="ignore"):
+        e = np.abs(a - b).max(axis=1)
+    return np.where(np.isfinite(e), e, np.inf)
 
 
 def wellposed(o32, o64, tol=1e-3):
@@ -155,19 +203,26 @@ def test_lq_backward_gershgorin_and_batch(product, oracle):
 
 
 # ------------------------------------------------------------------ stage-by-stage parity
-@pytest.mark.parametrize("name", HEADLINE)
-def test_stage_parity(product, oracle, oracle64, name, iterations=2):
+# BASELINE.json's configs name T = 150 for RoundaboutMerging and T = 50 for Air3D (the reference's
+# own examples use 100): both horizons are run
+STAGE_CASES = [(n, 100) for n in HEADLINE] + [("roundabout_merging", 150), ("air_3d", 50)]
+
+
+@pytest.mark.parametrize("name,T", STAGE_CASES)
+def test_stage_parity(product, oracle, oracle64, name, T, iterations=2):
     build, params, x0f = CONFIGS[name]
-    desc, _ = build()
+    desc, _ = build(num_time_steps=T)
     x0 = x0f(16)
+    B = x0.shape[0]
     hs = []
     for lib in (product, oracle, oracle64):
-        h = abi.Handle(lib, desc, params(), x0.shape[0], 0)
+        h = abi.Handle(lib, desc, params(), B, 0)
         h.upload_x0(x0)
         h.solve_begin()
         hs.append(h)
     c, o, o64 = hs
-    good = np.ones(x0.shape[0], bool)  # instances still well posed (fp32 and fp64 oracles agree)
+    good = np.ones(B, bool)  # instances still well posed (fp32 and fp64 oracles agree)
+    compared = []
 
     def check(what, tol=None, label=""):
         # the first iteration sees identical inputs; later ones inherit ~1e-6 input differences
@@ -178,7 +233,9 @@ def test_stage_parity(product, oracle, oracle64, name, iterations=2):
         nonlocal good
         a, b, b64 = c.download(what), o.download(what), o64.download(what)
         good = good & wellposed(b, b64)
-        close(a, b, tol=tol, rows=good, what=f"{label} field {what}")
+        # the LQ solution is the one stage whose rounding the CUDA path does not share with the oracle
+        cond = row_distance(b, b64) if "LQ" in label else None
+        compared.append(close(a, b, tol=tol, rows=good, what=f"{label} field {what}", cond=cond))
 
     for what in (abi.XS, abi.US, abi.TOTAL_COSTS):
         check(what, label="prologue")
@@ -199,7 +256,16 @@ def test_stage_parity(product, oracle, oracle64, name, iterations=2):
             check(what, label=f"it{it} linesearch")
         for what in (abi.STATUS, abi.ITERS, abi.BACKTRACKS, abi.TIME_OF_EXTREME):
             assert np.array_equal(c.download(what)[good], o.download(what)[good]), what
-    assert good.sum() >= 4, f"only {good.sum()} well-posed instances left"
+    report(f"stage_parity[{name},T={T}]", batch=B, wellposed_at_end=good.sum(), min_rows_compared=min(compared),
+           max_rows_compared=max(compared))
+    # measured on B200 (round 2): 13 (intersection) / 11 (roundabout) / 16 (air3d) of 16 games stay
+    # well posed through two iterations at T = 100; RoundaboutMerging at T = 150 (regularisation 0,
+    # a 50 % longer Riccati sweep) keeps 7 -- the fp32 and fp64 ORACLES part on the other nine
+    floor = 5 if (name, T) == ("roundabout_merging", 150) else B // 2
+    assert good.sum() >= floor, f"only {good.sum()} of {B} well-posed instances left"
+    assert min(compared) >= floor
+    for h in hs:
+        h.close()
 
 
 # ------------------------------------------------------------------ golden fixtures
@@ -213,6 +279,7 @@ def test_against_golden_fixture(product, name):
     desc, _ = build()
     iters = max(int(k.split("_")[1]) for k in g.files if k.startswith("merit_"))
     xs_tol = 2e-2 if name == "roundabout_merging" else 1e-3  # roundabout: reg = 0, ill-conditioned
+    total_compared = 0
     for it in range(1, iters + 1):
         h = abi.Handle(product, desc, params(max_solver_iters=it), g["x0"].shape[0], 0)
         h.upload_x0(g["x0"])
@@ -227,15 +294,19 @@ def test_against_golden_fixture(product, name):
             h.download(abi.ITERS) == g[f"iters_{it}"])
         stable = g[f"stable_{it}"]
         # on instances where the fp32 and fp64 oracles agree the CUDA path must follow the same flow
-        assert flow[stable].mean() >= 0.75, f"iteration {it}: flow matches on {flow[stable].mean():.0%} of stable"
         ok = flow & stable & (g[f"status_{it}"] != abi.STATUS_LINESEARCH_FAILED) & tame(g[f"xs_{it}"], 1e3)
-        if ok.any():
-            close(h.download(abi.XS), g[f"xs_{it}"], tol=xs_tol, atol=1e-3, rows=ok, what=f"xs_{it}")
-            close(h.download(abi.US), g[f"us_{it}"], tol=xs_tol, atol=1e-3, rows=ok, what=f"us_{it}")
-            assert np.array_equal(h.download(abi.TIME_OF_EXTREME)[ok], g[f"t_extreme_{it}"][ok])
-            close(h.download(abi.MERIT), g[f"merit_{it}"], tol=max(1e-3, xs_tol), rows=ok, what="merit")
+        report(f"golden_fixture[{name}] it{it}", batch=len(flow), stable=stable.sum(), flow_on_stable=flow[stable].mean(),
+               rows_compared=ok.sum())
+        assert flow_ok(flow, stable), f"iteration {it}: flow matches on {flow[stable].mean():.0%} of stable"
+        assert ok.sum() >= max(2, int(0.5 * stable.sum())), f"iteration {it}: only {ok.sum()} rows comparable"
+        n_cmp = close(h.download(abi.XS), g[f"xs_{it}"], tol=xs_tol, atol=1e-3, rows=ok, what=f"xs_{it}")
+        close(h.download(abi.US), g[f"us_{it}"], tol=xs_tol, atol=1e-3, rows=ok, what=f"us_{it}")
+        assert np.array_equal(h.download(abi.TIME_OF_EXTREME)[ok], g[f"t_extreme_{it}"][ok])
+        close(h.download(abi.MERIT), g[f"merit_{it}"], tol=max(1e-3, xs_tol), rows=ok, what="merit")
+        total_compared += n_cmp
         h.close()
     assert g[f"stable_{iters}"].sum() >= 3, "golden fixture has too few well-posed instances"
+    assert total_compared >= 2 * iters
 
 
 # ------------------------------------------------------------------ reference fixtures
@@ -253,7 +324,7 @@ def test_against_reference_fixture(product, oracle64, name):
     B = x0.shape[0]
     iters = int(g["ilq_iters"])
     xs_tol = 2e-2 if name == "roundabout_merging" else 1e-3
-    compared = 0
+    compared = stable_total = 0
     for it in range(0, iters + 1):
         hs = []
         for lib in (product, oracle64):
@@ -275,16 +346,18 @@ def test_against_reference_fixture(product, oracle64, name):
             stable[stable] &= wellposed(ref_xs[stable], o64.download(abi.XS)[stable])
         stable &= (o64.download(abi.ITERS) == it) & (o64.download(abi.STATUS) != abi.STATUS_LINESEARCH_FAILED)
         flow = (c.download(abi.ITERS) == it) & (c.download(abi.STATUS) != abi.STATUS_LINESEARCH_FAILED)
-        if stable.any():
-            assert flow[stable].mean() >= 0.75, f"iterate {it}: CUDA path follows the reference on {flow[stable].mean():.0%}"
         ok = stable & flow
-        if ok.any():
-            close(c.download(abi.XS), ref_xs, tol=xs_tol, atol=1e-3, rows=ok, what=f"ref xs_{it}")
-            close(c.download(abi.US), ref_us, tol=xs_tol, atol=1e-3, rows=ok, what=f"ref us_{it}")
-            compared += int(ok.sum())
+        report(f"reference_fixture[{name}] it{it}", batch=B, stable=stable.sum(),
+               flow_on_stable=flow[stable].mean() if stable.any() else -1.0, rows_compared=ok.sum())
+        if stable.any():
+            assert flow_ok(flow, stable), f"iterate {it}: CUDA path follows the reference on {flow[stable].mean():.0%}"
+        close(c.download(abi.XS), ref_xs, tol=xs_tol, atol=1e-3, rows=ok, what=f"ref xs_{it}")
+        close(c.download(abi.US), ref_us, tol=xs_tol, atol=1e-3, rows=ok, what=f"ref us_{it}")
+        compared += int(ok.sum())
+        stable_total += int(stable.sum())
         for h in hs:
             h.close()
-    assert compared >= 6, f"only {compared} (instance, iterate) pairs were comparable"
+    assert compared >= max(6, int(0.8 * stable_total)), f"only {compared} of {stable_total} stable (instance, iterate) pairs compared"
 
 
 # ------------------------------------------------------------------ open-loop LQ solver
@@ -354,13 +427,13 @@ def test_open_loop_against_reference_fixture(product, oracle64, name):
             stable[stable] &= wellposed(ref_xs[stable], o64.download(abi.XS)[stable])
         stable &= (o64.download(abi.ITERS) == it) & (o64.download(abi.STATUS) != abi.STATUS_LINESEARCH_FAILED)
         flow = (c.download(abi.ITERS) == it) & (c.download(abi.STATUS) != abi.STATUS_LINESEARCH_FAILED)
-        if stable.any():
-            assert flow[stable].mean() >= 0.75
         ok = stable & flow
-        if ok.any():
-            close(c.download(abi.XS), ref_xs, tol=2e-3, atol=1e-3, rows=ok, what=f"open-loop xs_{it}")
-            close(c.download(abi.US), ref_us, tol=2e-3, atol=1e-3, rows=ok, what=f"open-loop us_{it}")
-            compared += int(ok.sum())
+        report(f"open_loop_fixture[{name}] it{it}", batch=nol, stable=stable.sum(),
+               flow_on_stable=flow[stable].mean() if stable.any() else -1.0, rows_compared=ok.sum())
+        assert flow_ok(flow, stable)
+        close(c.download(abi.XS), ref_xs, tol=2e-3, atol=1e-3, rows=ok, what=f"open-loop xs_{it}")
+        close(c.download(abi.US), ref_us, tol=2e-3, atol=1e-3, rows=ok, what=f"open-loop us_{it}")
+        compared += int(ok.sum())
         for h in hs:
             h.close()
     assert compared >= 6, f"only {compared} (instance, iterate) pairs were comparable"
@@ -436,6 +509,11 @@ def test_receding_horizon_from_spliced_plan_against_reference_fixture(product, o
 
 
 # ------------------------------------------------------------------ full solves
+# measured round 2 (B200): see profiles/r02_parity_counts.md; thresholds = measured minus a margin
+# (intersection 0.92, roundabout 0.75, air3d 0.97 of the whole batch, ill-posed games included)
+FULL_SOLVE_FLOW_MIN = {"three_player_intersection": 0.85, "roundabout_merging": 0.65, "air_3d": 0.9}
+
+
 @pytest.mark.parametrize("name,batch,iters", [("three_player_intersection", 64, 10),
                                               ("roundabout_merging", 32, 3), ("air_3d", 36, 10)])
 def test_full_solve_against_oracle(product, oracle, name, batch, iters):
@@ -446,9 +524,13 @@ def test_full_solve_against_oracle(product, oracle, name, batch, iters):
     flow = (c.download(abi.STATUS) == o.download(abi.STATUS)) & (
         c.download(abi.ITERS) == o.download(abi.ITERS)) & (
         c.download(abi.BACKTRACKS) == o.download(abi.BACKTRACKS))
-    assert flow.mean() >= 0.5, f"control flow identical for only {flow.mean():.0%}"
     ok = flow & (o.download(abi.STATUS) != abi.STATUS_LINESEARCH_FAILED) & tame(o.download(abi.XS), 1e3)
-    assert ok.sum() >= 2
+    solvable = (o.download(abi.STATUS) != abi.STATUS_LINESEARCH_FAILED) & tame(o.download(abi.XS), 1e3)
+    report(f"full_solve[{name}]", batch=len(flow), flow=flow.mean(), oracle_solvable=solvable.sum(), rows_compared=ok.sum())
+    # control flow over `iters` chained linesearches: every fp32 implementation parts from another on
+    # the knife-edge games (the oracle's own fp32 and fp64 builds do), hence a fraction, not equality
+    assert flow.mean() >= FULL_SOLVE_FLOW_MIN[name], f"control flow identical for only {flow.mean():.0%}"
+    assert ok.sum() >= max(2, int(0.5 * solvable.sum())), f"only {ok.sum()} of {solvable.sum()} solvable games compared"
     xs_c, xs_o = c.download(abi.XS)[ok], o.download(abi.XS)[ok]
     assert np.isfinite(xs_c).all()
     rel = np.abs(xs_c - xs_o).max(axis=(1, 2)) / np.maximum(1.0, np.abs(xs_o).max(axis=(1, 2)))
@@ -577,6 +659,41 @@ def test_full_batch_properties(product):
     h2.close()
 
 
+def test_full_batch_sampled_rows_against_oracle(product, oracle, oracle64):
+    """BASELINE.json's metric size against the oracle itself: the batch-4096 solve of the bench
+    workload (seed 4096), 256 rows sampled across the batch re-solved by the fp32 and fp64 oracles.
+    First iteration by value on every well-posed row; after three iterations control flow and
+    trajectories on the rows where the two oracles agree."""
+    B, iters = 4096, 3
+    desc, _ = problems.three_player_intersection()
+    x0 = problems.three_player_intersection_x0_batch(B, 4096)
+    idx = np.sort(np.random.default_rng(7).choice(B, 256, replace=False))
+    for it, tol in ((1, 1e-3), (iters, 2e-3)):
+        params = problems.three_player_intersection_params(max_solver_iters=it, disable_convergence_exit=1)
+        res = []
+        for lib, x in ((product, x0), (oracle, x0[idx]), (oracle64, x0[idx])):
+            h = abi.Handle(lib, desc, params, len(x), 0)
+            h.upload_x0(x)
+            h.solve_begin()
+            h.solve(chunk=it)
+            sel = idx if len(x) == B else slice(None)
+            res.append({w: h.download(w)[sel] for w in (abi.XS, abi.US, abi.STATUS, abi.ITERS, abi.BACKTRACKS)})
+            h.close()
+        c, o, o64 = res
+        same = lambda a, b: (a[abi.STATUS] == b[abi.STATUS]) & (a[abi.ITERS] == b[abi.ITERS]) & (
+            a[abi.BACKTRACKS] == b[abi.BACKTRACKS])
+        stable = same(o, o64) & wellposed(o[abi.XS], o64[abi.XS]) & tame(o[abi.XS], 1e3) & (
+            o[abi.STATUS] != abi.STATUS_LINESEARCH_FAILED)
+        flow = same(c, o)
+        ok = stable & flow
+        report(f"full_batch_sampled it{it}", sampled=len(idx), stable=stable.sum(), flow_on_stable=flow[stable].mean(),
+               rows_compared=ok.sum())
+        assert stable.sum() >= 192   # measured: 236 / 226 of 256
+        assert flow_ok(flow, stable)
+        close(c[abi.XS], o[abi.XS], tol=tol, atol=1e-3, rows=ok, what=f"xs after {it} iterations")
+        close(c[abi.US], o[abi.US], tol=tol, atol=1e-3, rows=ok, what=f"us after {it} iterations")
+
+
 # ------------------------------------------------------------------ ragged sizes
 @pytest.mark.parametrize("batch,T", [(1, 100), (33, 100), (100, 23), (7, 2), (65, 57)])
 def test_ragged_batch_and_horizon(product, oracle, oracle64, batch, T):
@@ -600,12 +717,13 @@ def test_ragged_batch_and_horizon(product, oracle, oracle64, batch, T):
         h.solve(chunk=2)
     flow = (c.download(abi.STATUS) == o.download(abi.STATUS)) & (c.download(abi.ITERS) == o.download(abi.ITERS)) & (
         c.download(abi.BACKTRACKS) == o.download(abi.BACKTRACKS))
-    assert flow.mean() >= 0.7, f"control flow identical for only {flow.mean():.0%}"
     ok = flow & (o.download(abi.STATUS) != abi.STATUS_LINESEARCH_FAILED) & tame(o.download(abi.XS), 1e3)
     ok &= wellposed(o.download(abi.XS), o64.download(abi.XS))
-    if ok.any():
-        close(c.download(abi.XS), o.download(abi.XS), tol=2e-3, atol=1e-3, rows=ok, what="xs after 2 iterations")
-        close(c.download(abi.US), o.download(abi.US), tol=2e-3, atol=1e-3, rows=ok, what="us after 2 iterations")
+    report(f"ragged[{batch},{T}]", batch=batch, flow=flow.mean(), rows_compared=ok.sum())
+    assert flow.mean() >= 0.7, f"control flow identical for only {flow.mean():.0%}"
+    assert ok.sum() >= max(1, batch // 2), f"only {ok.sum()} of {batch} rows comparable"
+    close(c.download(abi.XS), o.download(abi.XS), tol=2e-3, atol=1e-3, rows=ok, what="xs after 2 iterations")
+    close(c.download(abi.US), o.download(abi.US), tol=2e-3, atol=1e-3, rows=ok, what="us after 2 iterations")
     np.testing.assert_array_equal(c.download(abi.XS)[:, 0], x0)
     for h in hs:
         h.close()
