@@ -48,6 +48,10 @@ struct SubSolver {
   cudaStream_t side;
   cudaEvent_t ev_fresh, ev_side;
   bool side_busy = false;
+  // staggered groups (ILQG_STAGGER): group g starts its first pass when group g - 1 has finished its first
+  // backward sweep, so that one group's latency-bound linesearch runs under the other's K_lq / K_bwd
+  cudaEvent_t stagger_signal = nullptr;   // recorded after this group's first K_bwd of an iterate call
+  cudaEvent_t stagger_wait = nullptr;     // armed per iterate call: the previous group's signal
   int sm_count = 148;
   // SolverParams::open_loop: LQOpenLoopSolver instead of LQFeedbackSolver (ilq_solver.h:76-81)
   bool open_loop = false;
@@ -869,9 +873,11 @@ int PipelinedStep(SubSolver* h, int it, int n) {
   const Sel all{SEL_ALL, nullptr, nullptr};
   const Sel sel = it > 0 ? Sel{SEL_MAIN, nullptr, nullptr} : all;
   const bool bwd_on_side = h->pipeline == 1;
+  if (it == 0 && h->stagger_wait) CUDA_TRY(cudaStreamWaitEvent(main, h->stagger_wait, 0));
   if ((rc = LaunchLqRecords(h, 1, sel)) != ILQG_OK) return rc;
   if (!bwd_on_side && h->side_busy) CUDA_TRY(cudaStreamWaitEvent(main, h->ev_side, 0));
   if ((rc = DispatchBackward(h, 1, false, bwd_on_side ? sel : all)) != ILQG_OK) return rc;
+  if (it == 0 && h->stagger_signal) CUDA_TRY(cudaEventRecord(h->stagger_signal, main));
   if (bwd_on_side && h->side_busy) CUDA_TRY(cudaStreamWaitEvent(main, h->ev_side, 0));
   if ((rc = LaunchLinesearchFresh(h)) != ILQG_OK) return rc;
   const int q_first = h->ls_cur;  // the queue the first window just filled
@@ -1127,7 +1133,8 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
   const bool side_high = !std::getenv("ILQG_SIDE_PRIORITY") || std::atoi(std::getenv("ILQG_SIDE_PRIORITY")) != 0;
   if (cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, side_high ? prio_hi : prio_lo) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fresh, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming) != cudaSuccess)
+      cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->stagger_signal, cudaEventDisableTiming) != cudaSuccess)
     return fail(ILQG_ERR_CUDA);
 #define ALLOC(ptr, count)                                          \
   if ((rc = DevAlloc(h, &(ptr), (count))) != ILQG_OK) return fail(rc)
@@ -1240,6 +1247,7 @@ int ilqg_destroy(SubHandle h) {
   if (h->side) cudaStreamDestroy(h->side);
   if (h->ev_fresh) cudaEventDestroy(h->ev_fresh);
   if (h->ev_side) cudaEventDestroy(h->ev_side);
+  if (h->stagger_signal) cudaEventDestroy(h->stagger_signal);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   for (auto& sm : h->samples) {
     cudaEventDestroy(sm.a);
@@ -1928,9 +1936,13 @@ int ilqg_iterate(ilqg_handle h, int max_iters, int* iters_done) {
   int rc = Fork(h);
   if (rc != ILQG_OK) return rc;
   if (h->subs[0]->pipeline && max_iters > 1) {
-    // each group runs its own two-stream pipeline (sub::IteratePipelined)
-    for (SubSolver* g : h->subs)
-      if ((rc = sub::ilqg_iterate(g, max_iters, nullptr)) != ILQG_OK) return rc;
+    // each group runs its own two-stream pipeline (sub::IteratePipelined); with ILQG_STAGGER the groups
+    // start half a pass apart
+    static const bool stagger = std::getenv("ILQG_STAGGER") && std::atoi(std::getenv("ILQG_STAGGER")) != 0;
+    for (size_t k = 0; k < h->subs.size(); k++) {
+      h->subs[k]->stagger_wait = (stagger && k > 0) ? h->subs[k - 1]->stagger_signal : nullptr;
+      if ((rc = sub::ilqg_iterate(h->subs[k], max_iters, nullptr)) != ILQG_OK) return rc;
+    }
   } else {
     // iteration-major, group-minor issue order so the groups' kernels interleave in the hardware queues
     for (int it = 0; it < max_iters; it++)

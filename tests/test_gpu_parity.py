@@ -223,6 +223,7 @@ def test_stage_parity(product, oracle, oracle64, name, T, iterations=2):
     c, o, o64 = hs
     good = np.ones(B, bool)  # instances still well posed (fp32 and fp64 oracles agree)
     compared = []
+    flips = 0
 
     def check(what, tol=None, label=""):
         # the first iteration sees identical inputs; later ones inherit ~1e-6 input differences
@@ -252,12 +253,20 @@ def test_stage_parity(product, oracle, oracle64, name, T, iterations=2):
         for h in hs:
             h.linesearch()
         good = good & (o.download(abi.BACKTRACKS) == o64.download(abi.BACKTRACKS))
+        # control flow first: where the fp32 and fp64 oracles agree the CUDA path takes the same Armijo
+        # decisions, up to the odd knife-edge game (its merit differs from the oracle's by rounding);
+        # such a game is counted, bounded, and leaves the value comparisons that follow
+        same = np.ones(B, bool)
+        for what in (abi.STATUS, abi.ITERS, abi.BACKTRACKS):
+            same &= c.download(what) == o.download(what)
+        flips += int((good & ~same).sum())
+        assert flow_ok(same, good), f"it{it}: control flow differs on {(good & ~same).sum()} of {good.sum()} well-posed games"
+        good = good & same
         for what in (abi.XS, abi.US, abi.PS, abi.ALPHAS, abi.MERIT, abi.STEP, abi.TOTAL_COSTS):
             check(what, label=f"it{it} linesearch")
-        for what in (abi.STATUS, abi.ITERS, abi.BACKTRACKS, abi.TIME_OF_EXTREME):
-            assert np.array_equal(c.download(what)[good], o.download(what)[good]), what
+        assert np.array_equal(c.download(abi.TIME_OF_EXTREME)[good], o.download(abi.TIME_OF_EXTREME)[good])
     report(f"stage_parity[{name},T={T}]", batch=B, wellposed_at_end=good.sum(), min_rows_compared=min(compared),
-           max_rows_compared=max(compared))
+           max_rows_compared=max(compared), armijo_flips=flips)
     # measured on B200 (round 2): 13 (intersection) / 11 (roundabout) / 16 (air3d) of 16 games stay
     # well posed through two iterations at T = 100; RoundaboutMerging at T = 150 (regularisation 0,
     # a 50 % longer Riccati sweep) keeps 7 -- the fp32 and fp64 ORACLES part on the other nine
