@@ -33,6 +33,7 @@ struct SubSolver {
   TcTables tc;
   bool cp_ok = false;       // K_lq v4 + k_lq_backward_tc usable for this descriptor
   int tc_nxp = 0, tc_mup = 0;
+  int tc_blocks_cap = 0;    // ILQG_TC_BLOCKS
   bool use_compact = true;  // ILQG_RECORDS=dense forces the round-1 dense-record kernels (A/B runs)
   // which representation of the LQ records is current: K_lq v4 writes the compact one,
   // ilqg_upload_lq / K_lq v3 the dense one; EnsureDense expands compact -> dense on demand
@@ -322,7 +323,7 @@ int SetSmem(K kernel, size_t bytes) {
 // instantiations of k_lq_backward_tc: padded state dimension, padded stacked control dimension,
 // scatter / Q-add table entries per lane, minimum resident blocks per SM
 #define ILQG_TC_INSTANCES(X)                                                                        \
-  X(8, 2, 2, 4, 8) X(8, 4, 2, 4, 8) X(16, 2, 3, 6, 6) X(16, 4, 3, 6, 6) X(16, 6, 3, 6, 6) X(16, 8, 3, 6, 4) \
+  X(8, 2, 2, 4, 8) X(8, 4, 2, 4, 8) X(16, 2, 3, 6, 4) X(16, 4, 3, 6, 4) X(16, 6, 3, 6, 4) X(16, 8, 3, 6, 4) \
   X(24, 4, 4, 10, 3) X(24, 6, 4, 10, 3) X(24, 8, 4, 10, 3)
 
 // the per-lane table budgets of the instance for (nxp, mup), or false when there is none
@@ -398,7 +399,11 @@ int LaunchOpenLoop(SubSolver* h, int only_running, bool use_lq_x0) {
 // iLQ loop itself never reads once ExpectedDecrease is fused into the backward sweep)
 template <int NXP, int MUP, int SC, int QA, int MINB>
 int LaunchBackwardTc(SubSolver* h, int only_running, Sel sel) {
-  const size_t smem = sizeof(float) * (((size_t)h->tc.total_words + 3) / 4 * 4 + 2 * KTC_WARPS + (size_t)KTC_WARPS * h->tc.per_game);
+  size_t smem = sizeof(float) * (((size_t)h->tc.total_words + 3) / 4 * 4 + 2 * KTC_WARPS + (size_t)KTC_WARPS * h->tc.per_game);
+  // ILQG_TC_BLOCKS = k caps the sweep at k resident blocks per SM (by asking for more shared memory than it
+  // needs), which leaves registers and shared memory for the side stream's linesearch blocks to run under it
+  if (h->tc_blocks_cap > 0)  // the least request with which cap + 1 blocks no longer fit (1 KB per block is reserved)
+    smem = std::max(smem, ((size_t)(228 * 1024 / (h->tc_blocks_cap + 1) - 1024 + 16) + 15) & ~(size_t)15);
   int rc = SetSmem(k_lq_backward_tc<NXP, MUP, SC, QA, MINB>, smem);
   if (rc != ILQG_OK) return rc;
   ProfScope prof(h, 1);
@@ -514,7 +519,7 @@ int BuildCompactTables(SubSolver* h, const std::vector<GatherItem>& items) {
   const int n = d.n, M = d.M, N = d.N;
   const int NI = (int)items.size();
   if (NI == 0 || NI >= (int)kItemReg || d.num_subsystems == 0) return ILQG_OK;
-  const int NIp = (NI + n + N + 31) & ~31;  // items | g_k | the N state regularisers | pad
+  const int NIp = (NI + n + N + 3) & ~3;  // items | g_k | the N state regularisers | pad (16-byte multiple: bulk copies)
   const int NXP = (n + 7) & ~7, MUP = (M + 1) & ~1;
   int sc_budget = 0, qa_budget = 0;
   if (!TcBudget(NXP, MUP, &sc_budget, &qa_budget)) return ILQG_OK;
@@ -547,9 +552,15 @@ int BuildCompactTables(SubSolver* h, const std::vector<GatherItem>& items) {
   std::memset(&tc, 0, sizeof(tc));
   tc.NI = NI;
   tc.NIp = NIp;
-  tc.off_vals = L.fixed;
-  tc.off_Z = tc.off_vals + 2 * NIp;  // two record buffers: the next record lands while this one is in use
   const int MM = (MUP * MUP + 3) & ~3;
+  tc.off_zeta = L.fixed;
+  tc.off_l = tc.off_zeta + N * NXP;
+  tc.off_Om = tc.off_l + N * NXP;
+  tc.off_rho = tc.off_Om + N * MM;
+  tc.off_om = tc.off_rho + N * 8;
+  tc.off_edr = tc.off_om + N * 8;
+  tc.off_vals = tc.off_edr + N * 8;
+  tc.off_Z = tc.off_vals + 2 * NIp;  // two record buffers: the next record lands while this one is in use
   // control-cost pair that owns offset `rel` of the R (mode 0) / r (mode 1) block
   auto pair_at = [&](int rel, int mode) {
     for (int pp = 0; pp < d.num_pairs; pp++) {
@@ -583,18 +594,18 @@ int BuildCompactTables(SubSolver* h, const std::vector<GatherItem>& items) {
       qadd.push_back((unsigned)g | ((unsigned)(i * NXP * L.LD + r * L.LD + c) << 16));
     } else if (off < d.offR) {  // l_i
       const int idx = off - d.offl, i = idx / n, a = idx % n;
-      scat.push_back((unsigned)g | ((unsigned)(L.l + i * NXP + a) << 16));
+      scat.push_back((unsigned)g | ((unsigned)(tc.off_l + i * NXP + a) << 16));
     } else if (off < d.offr) {  // R_ij -> Omega_i[co_j + a][co_j + c]
       const int pp = pair_at(off - d.offR, 0);
       if (pp < 0) return ILQG_OK;
       const int i = d.pair_i[pp], j = d.pair_j[pp], mj = d.udim[j], co = d.uoff[j];
       const int idx = off - d.offR - d.pair_Roff[pp], a = idx / mj, c = idx % mj;
-      scat.push_back((unsigned)g | ((unsigned)(L.Om + i * MM + (co + a) * MUP + co + c) << 16));
+      scat.push_back((unsigned)g | ((unsigned)(tc.off_Om + i * MM + (co + a) * MUP + co + c) << 16));
     } else {  // r_ij -> rho_i[co_j + c]
       const int pp = pair_at(off - d.offr, 1);
       if (pp < 0) return ILQG_OK;
       const int i = d.pair_i[pp], j = d.pair_j[pp], co = d.uoff[j];
-      scat.push_back((unsigned)g | ((unsigned)(L.rho + i * 8 + co + off - d.offr - d.pair_roff[pp]) << 16));
+      scat.push_back((unsigned)g | ((unsigned)(tc.off_rho + i * 8 + co + off - d.offr - d.pair_roff[pp]) << 16));
     }
   }
   for (int i = 0; i < N; i++)  // the template's state regulariser on the diagonal of Q_i
@@ -1079,6 +1090,7 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
   // the open-loop kernel and the tensor-core sweep over compact records take run-time dimensions;
   // the dense-record feedback kernels are instantiated per shape (checked after the pattern is built)
   if (const char* e = std::getenv("ILQG_RECORDS")) h->use_compact = std::strcmp(e, "dense") != 0;
+  if (const char* e = std::getenv("ILQG_TC_BLOCKS")) h->tc_blocks_cap = std::max(0, std::atoi(e));
   h->host_desc = *desc;
   h->open_loop = params->open_loop != 0;
   h->B = batch;

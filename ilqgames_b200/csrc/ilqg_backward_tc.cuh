@@ -46,15 +46,19 @@ struct TcTables {
   int qadd, nqadd;         // item (or kItemReg + i) | offset into Z << 16
   int bnz_start[ILQG_MAX_UDIM + 1];
   int NI, NIp;
-  int off_vals, off_Z, per_game;  // run-time part of the per-game layout (floats)
+  // run-time part of the per-game layout (floats): the arrays sized by the number of players
+  int off_zeta, off_l, off_Om, off_rho, off_om, off_edr, off_vals, off_Z, per_game;
 };
 
-// fixed part of the per-game shared-memory layout (floats); vals [NIp] and Z [N][NXP][LD] follow at
-// TcTables::off_vals / off_Z.  Shared by the kernel and by the host code that builds the tables.
-//   Om  [4][MUP][MUP]  Omega_i: player i's control Hessians R_ij as blocks of one stacked M x M matrix
-//   rho [4][8]         the matching stacked gradients r_ij
+// fixed part of the per-game shared-memory layout (floats); the arrays sized by the number of players
+// follow at TcTables::off_*:
+//   zeta [N][NXP], l [N][NXP]
+//   Om   [N][MUP][MUP]  Omega_i: player i's control Hessians R_ij as blocks of one stacked M x M matrix
+//   rho  [N][8]         the matching stacked gradients r_ij;  om, edr [N][8]: per-step control-cost vectors
+//   vals [2][NIp]       this step's compact record and the next one in flight;  Z [N][NXP][LD]
+// Shared by the kernel and by the host code that builds the tables.
 struct TcFixed {
-  int LD, F, P, BZt, tv, ya, zeta, beta, pv, pn, l, Om, rho, om, edr, fixed;
+  int LD, F, P, BZt, tv, ya, beta, pv, pn, fixed;
 };
 __host__ __device__ constexpr TcFixed tc_fixed(int NXP, int MUP) {
   TcFixed L{};
@@ -63,17 +67,11 @@ __host__ __device__ constexpr TcFixed tc_fixed(int NXP, int MUP) {
   L.P = L.F + NXP * L.LD;           // [MUP][LD]  Y, then the solution P
   L.BZt = L.P + MUP * L.LD;         // [NXP][8]   (B_i' Z_i)' ...
   L.tv = L.BZt;                     // [4][NXP]   ... later zeta_i + Z_i beta (B'Z is dead by then)
-  L.ya = L.BZt + NXP * 8;           // [8] y_alpha, then alpha
-  L.zeta = L.ya + 8;                // [4][NXP]
-  L.beta = L.zeta + 4 * NXP;        // [NXP]
+  L.ya = L.BZt + (NXP * 8 > 4 * NXP ? NXP * 8 : 4 * NXP);  // [8] y_alpha, then alpha
+  L.beta = L.ya + 8;                // [NXP]
   L.pv = L.beta + NXP;              // [NXP]
   L.pn = L.pv + NXP;                // [NXP]
-  L.l = L.pn + NXP;                 // [4][NXP]
-  L.Om = L.l + 4 * NXP;             // [4][MUP][MUP]
-  L.rho = L.Om + 4 * r4(MUP * MUP); // [4][8]
-  L.om = L.rho + 32;                // [4][8]  omega_i = Omega_i alpha - rho_i
-  L.edr = L.om + 32;                // [4][8]  (alpha_i' R_ii) for ExpectedDecrease
-  L.fixed = L.edr + 32;
+  L.fixed = L.pn + NXP;
   return L;
 }
 
@@ -202,15 +200,15 @@ k_lq_backward_tc(const __grid_constant__ DevDesc d, const DevParams p, Slab s, c
   float* BZt = sm + L.BZt;
   float* tv = sm + L.tv;
   float* ya = sm + L.ya;
-  float* zeta = sm + L.zeta;
+  float* zeta = sm + tb.off_zeta;
   float* beta = sm + L.beta;
   float* pv = sm + L.pv;
   float* pn = sm + L.pn;
-  float* lst = sm + L.l;
-  float* Om = sm + L.Om;
-  float* rho = sm + L.rho;
-  float* om = sm + L.om;
-  float* edr = sm + L.edr;
+  float* lst = sm + tb.off_l;
+  float* Om = sm + tb.off_Om;
+  float* rho = sm + tb.off_rho;
+  float* om = sm + tb.off_om;
+  float* edr = sm + tb.off_edr;
   float* vals = sm + tb.off_vals;          // the record of this step; the next one lands NIp floats further
   float* vals_next = vals + tb.NIp;
   float* Zs = sm + tb.off_Z;     // [NP][NXP][LD]
@@ -487,9 +485,15 @@ k_lq_backward_tc(const __grid_constant__ DevDesc d, const DevParams p, Slab s, c
     {
       // (alpha_i' R_ii) r_ii: one lane per player runs the reference's chain over its own controls
       float t1 = 0.f;
-      if (lane < NP) {
-        const int uo = d.uoff[lane], mi = d.udim[lane];
-        for (int c = uo; c < uo + mi; c++) t1 = fmaf(edr[lane * 8 + c], rho[lane * 8 + c], t1);
+      {
+        const int pl = lane & 3;  // (every lane computes some player's sum; lanes 0 .. NP - 1 are read below)
+        const int uo = pl < NP ? d.uoff[pl] : 0, mi = pl < NP ? d.udim[pl] : 0;
+        float er[8], rr[8];
+        ldvec<8>(edr + (pl < NP ? pl : 0) * 8, er);
+        ldvec<8>(rho + (pl < NP ? pl : 0) * 8, rr);
+#pragma unroll
+        for (int c = 0; c < MUP; c++)
+          if (c >= uo && c < uo + mi) t1 = fmaf(er[c], rr[c], t1);
       }
 #pragma unroll
       for (int i = 0; i < ILQG_MAX_PLAYERS; i++) {
