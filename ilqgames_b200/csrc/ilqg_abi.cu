@@ -28,6 +28,7 @@ struct SubSolver {
   LsScratch ls;
   RecordPattern pat;
   bool pat_ok;
+  bool v3_ok = false;       // the dense-record K_lq v3 fits its shared-memory budget for this pattern
   // compact records (ilqg_records.cuh) and the tensor-core backward sweep's tables (ilqg_backward_tc.cuh)
   CompactPattern cp;
   TcTables tc;
@@ -91,7 +92,33 @@ inline bool IsConstraintKind(int kind) {
 }
 
 int SubsystemXdim(int kind) {
-  return kind == ILQG_DYN_CAR6D ? 6 : kind == ILQG_DYN_UNICYCLE4D ? 4 : kind == ILQG_DYN_AIR3D ? 3 : 0;
+  switch (kind) {
+    case ILQG_DYN_CAR6D: return 6;
+    case ILQG_DYN_CAR5D: return 5;
+    case ILQG_DYN_UNICYCLE4D:
+    case ILQG_DYN_POINT_MASS_2D:
+    case ILQG_DYN_TWO_PLAYER_UNICYCLE4D: return 4;
+    case ILQG_DYN_DUBINS:
+    case ILQG_DYN_AIR3D: return 3;
+    default: return 0;
+  }
+}
+
+// FinalTimeCost::Evaluate / Quadraticize (include/ilqgames/cost/final_time_cost.h:64-77): active iff
+// t >= initial_time_ + threshold_time_ with t = RelativeTime(kk) = kk * kTimeStep in double
+// (relative_time_tracker.h:63-65) and initial_time_ the tracker's static, which
+// Problem::SyncToExistingProblem moves (src/problem.cpp:120).  -> first time step of every record.
+void UpdateCostGates(DevDesc* d, double tracker_initial_time) {
+  for (int c = 0; c < d->num_costs; c++) {
+    const double threshold = d->cost[c].active_from;
+    int first = 0;
+    if (threshold != 0.0) {
+      first = d->T;
+      for (int kk = 0; kk < d->T; kk++)
+        if (static_cast<double>(kk) * d->time_step >= tracker_initial_time + threshold) { first = kk; break; }
+    }
+    d->cost[c].first_step = first;
+  }
 }
 
 // Host "problem compiler": ilqg_problem_desc -> DevDesc + ilqg_layout.
@@ -124,19 +151,24 @@ int BuildDeviceDesc(const ilqg_problem_desc& h, DevDesc* d, ilqg_layout* lo, std
   for (int k = 0; k < h.num_subsystems; k++) {
     const ilqg_subsystem_desc& hs = h.subsystems[k];
     DevSubsystem& ds = d->sub[k];
-    if (hs.kind == ILQG_DYN_CAR5D || hs.kind == ILQG_DYN_DUBINS || hs.kind == ILQG_DYN_TWO_PLAYER_UNICYCLE4D ||
-        hs.kind == ILQG_DYN_POINT_MASS_2D)
-      return ILQG_ERR_UNSUPPORTED;  // oracle only so far (include/ilqg.h)
     const int xd = SubsystemXdim(hs.kind);
     if (xd == 0 || hs.x_offset < 0 || hs.x_offset + xd > d->n) return ILQG_ERR_INVALID_ARGUMENT;
-    const int np = hs.kind == ILQG_DYN_AIR3D ? 2 : 1;
+    const bool two = hs.kind == ILQG_DYN_AIR3D || hs.kind == ILQG_DYN_TWO_PLAYER_UNICYCLE4D;
+    const int np = two ? 2 : 1;
     if (hs.first_player < 0 || hs.first_player + np > d->N) return ILQG_ERR_INVALID_ARGUMENT;
-    if (hs.kind != ILQG_DYN_AIR3D && d->udim[hs.first_player] != 2) return ILQG_ERR_INVALID_ARGUMENT;
+    // control dimension of each of its players: 1 for Air3D's turn rates and the Dubins car, else 2
+    const int m_each = (hs.kind == ILQG_DYN_AIR3D || hs.kind == ILQG_DYN_DUBINS) ? 1 : 2;
+    for (int q = 0; q < np; q++)
+      if (d->udim[hs.first_player + q] != m_each) return ILQG_ERR_INVALID_ARGUMENT;
     ds.kind = hs.kind;
     ds.x_offset = hs.x_offset;
     ds.first_player = hs.first_player;
     ds.u_offset = d->uoff[hs.first_player];
     ds.u_offset2 = np == 2 ? d->uoff[hs.first_player + 1] : ds.u_offset + 1;
+    ds.nu = np * m_each;
+    for (int q = 0; q < 4; q++) ds.ucol[q] = 0;
+    for (int pl = 0, q = 0; pl < np; pl++)
+      for (int c = 0; c < m_each; c++) ds.ucol[q++] = d->uoff[hs.first_player + pl] + c;
     ds.p0 = hs.params[0];
     ds.p1 = hs.params[1];
   }
@@ -149,6 +181,9 @@ int BuildDeviceDesc(const ilqg_problem_desc& h, DevDesc* d, ilqg_layout* lo, std
     d->seg_start[p] = nseg;
     const int a = h.polyline_start[p], b = h.polyline_start[p + 1];
     if (a < 0 || b > ILQG_MAX_POLYLINE_POINTS || b - a < 2) return ILQG_ERR_INVALID_ARGUMENT;
+    // ranges must not overlap or run backwards, and all segments together must fit the table
+    if (p > 0 && a < h.polyline_start[p]) return ILQG_ERR_INVALID_ARGUMENT;
+    if (nseg + (b - a - 1) > ILQG_MAX_POLYLINE_POINTS) return ILQG_ERR_INVALID_ARGUMENT;
     for (int q = a + 1; q < b; q++) {
       DevSegment& sg = d->seg[nseg++];
       sg.p1x = h.polyline_points[q - 1][0];
@@ -169,10 +204,11 @@ int BuildDeviceDesc(const ilqg_problem_desc& h, DevDesc* d, ilqg_layout* lo, std
   for (int i = 0; i < d->N; i++) has[i][i] = true;
   for (int c = 0; c < h.num_costs; c++) {
     const ilqg_cost_desc& cd = h.costs[c];
-    if (cd.player < 0 || cd.player >= d->N || cd.arg >= d->N) return ILQG_ERR_INVALID_ARGUMENT;
-    // FinalTimeCost's time gate has no device implementation yet (include/ilqg.h: active_from)
-    if (cd.active_from != 0.0) return ILQG_ERR_UNSUPPORTED;
-    if (cd.group != 0) return ILQG_ERR_UNSUPPORTED;  // ExtremeValueCost: oracle only so far
+    if (cd.player < 0 || cd.player >= d->N || cd.arg >= d->N || cd.arg < -1) return ILQG_ERR_INVALID_ARGUMENT;
+    // a constraint cannot be time-gated; a member of an ExtremeValueCost group is a plain cost
+    if (IsConstraintKind(cd.kind) && cd.active_from != 0.0) return ILQG_ERR_INVALID_ARGUMENT;
+    if (cd.group < 0) return ILQG_ERR_INVALID_ARGUMENT;
+    if (cd.group > 0 && (IsConstraintKind(cd.kind) || cd.active_from != 0.0)) return ILQG_ERR_INVALID_ARGUMENT;
     if (cd.arg >= 0) has[cd.player][cd.arg] = true;
   }
   d->num_pairs = 0;
@@ -202,18 +238,25 @@ int BuildDeviceDesc(const ilqg_problem_desc& h, DevDesc* d, ilqg_layout* lo, std
     for (int c = 0; c < h.num_costs; c++) {
       const ilqg_cost_desc& cd = h.costs[c];
       if (cd.player != i) continue;
-      if (cd.kind < ILQG_COST_QUADRATIC || cd.kind > ILQG_CONSTRAINT_SINGLE_DIMENSION)
+      if (cd.kind < ILQG_COST_QUADRATIC || cd.kind > ILQG_COST_QUADRATIC_DIFFERENCE)
         return ILQG_ERR_UNSUPPORTED;
       const int dim = cd.arg < 0 ? d->n : d->udim[cd.arg];
       const bool needs_poly = cd.kind == ILQG_COST_QUADRATIC_POLYLINE2 ||
                               cd.kind == ILQG_COST_SEMIQUADRATIC_POLYLINE2 ||
                               cd.kind == ILQG_COST_POLYLINE2_SIGNED_DISTANCE;
       if (needs_poly && (cd.polyline < 0 || cd.polyline >= h.num_polylines)) return ILQG_ERR_INVALID_ARGUMENT;
-      const int ndims = (cd.kind == ILQG_COST_PROXIMITY || cd.kind == ILQG_CONSTRAINT_PROXIMITY) ? 4
+      const int ndims = (cd.kind == ILQG_COST_PROXIMITY || cd.kind == ILQG_CONSTRAINT_PROXIMITY ||
+                         cd.kind == ILQG_COST_SIGNED_DISTANCE) ? 4
                         : needs_poly ? 2 : 1;
-      for (int q = 0; q < ndims; q++) {
-        const bool all_dims_ok = cd.kind == ILQG_COST_QUADRATIC && q == 0 && cd.dim[0] < 0;
-        if (!all_dims_ok && (cd.dim[q] < 0 || cd.dim[q] >= dim)) return ILQG_ERR_INVALID_ARGUMENT;
+      if (cd.kind == ILQG_COST_QUADRATIC_DIFFERENCE) {  // flag = 1 or 2 pairs (dim[k], dim[2 + k])
+        if (cd.flag < 1 || cd.flag > 2) return ILQG_ERR_INVALID_ARGUMENT;
+        for (int q = 0; q < cd.flag; q++)
+          if (cd.dim[q] < 0 || cd.dim[q] >= dim || cd.dim[2 + q] < 0 || cd.dim[2 + q] >= dim) return ILQG_ERR_INVALID_ARGUMENT;
+      } else {
+        for (int q = 0; q < ndims; q++) {
+          const bool all_dims_ok = cd.kind == ILQG_COST_QUADRATIC && q == 0 && cd.dim[0] < 0;
+          if (!all_dims_ok && (cd.dim[q] < 0 || cd.dim[q] >= dim)) return ILQG_ERR_INVALID_ARGUMENT;
+        }
       }
       DevCost& dc = d->cost[d->num_costs++];
       dc.kind = cd.kind;
@@ -230,9 +273,25 @@ int BuildDeviceDesc(const ilqg_problem_desc& h, DevDesc* d, ilqg_layout* lo, std
       dc.pair = cd.arg >= 0 ? d->pair_of[cd.player][cd.arg] : -1;
       dc.weight = cd.weight;
       dc.value = cd.value;
+      dc.first_step = 0;  // (UpdateCostGates below)
+      dc.active_from = cd.active_from;
+      dc.group = cd.group;
+      dc.group_is_min = cd.group_is_min;
+      dc.group_end = d->num_costs;
     }
   }
   d->cost_begin[d->N] = d->num_costs;
+  // extent of every ExtremeValueCost group: consecutive records of one player and argument with one id
+  for (int c = 0; c < d->num_costs;) {
+    int e = c + 1;
+    if (d->cost[c].group > 0)
+      while (e < d->num_costs && d->cost[e].group == d->cost[c].group && d->cost[e].player == d->cost[c].player &&
+             d->cost[e].arg == d->cost[c].arg)
+        e++;
+    for (int m = c; m < e; m++) d->cost[m].group_end = e;
+    c = e;
+  }
+  UpdateCostGates(d, h.initial_time);
 
   // LQ record layout
   const int n = d->n, M = d->M, N = d->N;
@@ -485,7 +544,9 @@ int MaxRoleEntries(const DevDesc& d) {
       switch (cd.kind) {
         case ILQG_COST_QUADRATIC: e += cd.d0 >= 0 ? 2 : 2 * dim; break;
         case ILQG_COST_PROXIMITY:
-        case ILQG_CONSTRAINT_PROXIMITY: e += 20; break;
+        case ILQG_CONSTRAINT_PROXIMITY:
+        case ILQG_COST_SIGNED_DISTANCE: e += 20; break;
+        case ILQG_COST_QUADRATIC_DIFFERENCE: e += 6 * cd.flag; break;
         case ILQG_COST_SEMIQUADRATIC:
         case ILQG_CONSTRAINT_SINGLE_DIMENSION: e += 2; break;
         default: e += 6; break;  // polyline kinds
@@ -719,8 +780,9 @@ int BuildRecordPattern(SubSolver* h) {
     for (int a = 0; a < mj; a++) tmpl[d.offR + d.pair_Roff[p] + a * mj + a] = d.control_reg[d.pair_i[p]];
   }
   for (GatherItem& it : items) it.base = tmpl[it.off];
-  const size_t smem = klq_smem_bytes(d.n, d.M, d.N, E, d.rec, (int)items.size(), (int)idx.size());
-  if (smem > 110 * 1024) return ILQG_OK;
+  // (K_lq v3 stages NR dense records per block: too much shared memory for the n = 24 problems, which
+  // then produce dense records by expanding compact ones, EnsureDense)
+  h->v3_ok = klq_smem_bytes(d.n, d.M, d.N, E, d.rec, (int)items.size(), (int)idx.size()) <= 110 * 1024;
   GatherItem* d_items = nullptr;
   unsigned short* d_idx = nullptr;
   float* d_tmpl = nullptr;
@@ -750,12 +812,29 @@ int LaunchLqRecords(SubSolver* h, int only_running, Sel sel = Sel{SEL_ALL, nullp
     const long long recs = (long long)h->B * d.T;
     ProfScope prof(h, 0);
     k_linearize_quadraticize_v4<<<(int)((recs + 31) / 32), (d.N + 1) * 32, smem4, h->stream>>>(h->d, h->s, h->pat, h->cp,
-                                                                                             only_running, sel);
+                                                                                             only_running, sel, h->p.linesearch);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     h->compact_valid = true;
     h->dense_valid = false;
     return ILQG_OK;
+  }
+  if (h->pat_ok && h->cp_ok && (!h->v3_ok || !h->p.linesearch)) {  // (v3 has no keep-the-quadraticization mode)
+    // dense records wanted (open-loop solver, ILQG_RECORDS=dense) but K_lq v3 does not fit: v4, then expand
+    const size_t smem4 = klq4_smem_bytes(d.n, d.M, d.N, h->pat.E, h->cp.NIp, h->pat.num_items, h->pat.num_idx);
+    int rc4 = SetSmem(k_linearize_quadraticize_v4, smem4);
+    if (rc4 != ILQG_OK) return rc4;
+    const long long recs = (long long)h->B * d.T;
+    {
+      ProfScope prof(h, 0);
+      k_linearize_quadraticize_v4<<<(int)((recs + 31) / 32), (d.N + 1) * 32, smem4, h->stream>>>(h->d, h->s, h->pat, h->cp,
+                                                                                               only_running, sel, h->p.linesearch);
+      h->launches++;
+      CUDA_TRY(cudaGetLastError());
+    }
+    h->compact_valid = true;
+    h->dense_valid = false;
+    return EnsureDense(h);
   }
   {
     int rca = EnsureDense(h);  // partial launches (only_running / lists) keep the other games' records
@@ -763,7 +842,7 @@ int LaunchLqRecords(SubSolver* h, int only_running, Sel sel = Sel{SEL_ALL, nullp
     h->dense_valid = true;
     h->compact_valid = false;
   }
-  if (h->pat_ok) {
+  if (h->pat_ok && h->v3_ok) {
     const size_t smem3 = klq_smem_bytes(d.n, d.M, d.N, h->pat.E, d.rec, h->pat.num_items, h->pat.num_idx);
     int rc3 = SetSmem(k_linearize_quadraticize_v3, smem3);
     if (rc3 != ILQG_OK) return rc3;
@@ -774,16 +853,7 @@ int LaunchLqRecords(SubSolver* h, int only_running, Sel sel = Sel{SEL_ALL, nullp
     CUDA_TRY(cudaGetLastError());
     return ILQG_OK;
   }
-  const size_t smem = sizeof(float) * KLQ_WARPS * (size_t)(d.rec + ((d.n + d.M + 3) & ~3));
-  int rc = SetSmem(k_linearize_quadraticize, smem);
-  if (rc != ILQG_OK) return rc;
-  const long long warps = (long long)h->B * d.T;
-  const int blocks = (int)((warps + KLQ_WARPS - 1) / KLQ_WARPS);
-  ProfScope prof(h, 0);
-  k_linearize_quadraticize<<<blocks, KLQ_WARPS * 32, smem, h->stream>>>(h->d, h->s, only_running);
-  h->launches++;
-  CUDA_TRY(cudaGetLastError());
-  return ILQG_OK;
+  return ILQG_ERR_UNSUPPORTED;  // no record pattern (never for a descriptor inside the envelope)
 }
 
 // rollout + merit of one linesearch window as two kernels (ilqg_linesearch.cuh, "Split evaluation")
@@ -793,10 +863,17 @@ int LaunchLsSplit(SubSolver* h, int mode, int blocks, int q_offset) {
   const size_t smem_r = sizeof(float) * (size_t)ls_rollout_smem_floats(d.n, S);
   const size_t smem_m = sizeof(float) * (size_t)ls_merit_smem_floats(d.n, d.M, d.N);
   int rc = ILQG_ERR_UNSUPPORTED;
+  int nuq = 2;
+  for (int k = 0; k < S; k++) nuq = std::max(nuq, d.sub[k].nu);
 #define LS_ROLL(SS)                                                                               \
   case SS:                                                                                        \
-    if ((rc = SetSmem(k_ls_rollout<SS>, smem_r)) != ILQG_OK) return rc;                            \
-    k_ls_rollout<SS><<<blocks, SS * 32, smem_r, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset); \
+    if (nuq <= 2) {                                                                               \
+      if ((rc = SetSmem(k_ls_rollout<SS, 2>, smem_r)) != ILQG_OK) return rc;                       \
+      k_ls_rollout<SS, 2><<<blocks, SS * 32, smem_r, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset); \
+    } else {                                                                                      \
+      if ((rc = SetSmem(k_ls_rollout<SS, 4>, smem_r)) != ILQG_OK) return rc;                       \
+      k_ls_rollout<SS, 4><<<blocks, SS * 32, smem_r, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset); \
+    }                                                                                             \
     break;
   switch (S) {
     LS_ROLL(1) LS_ROLL(2) LS_ROLL(3) LS_ROLL(4)
@@ -1828,7 +1905,10 @@ int ilqg_overwrite_solution(ilqg_handle h, int only_successful) {
 }
 int ilqg_reset(ilqg_handle h, int mask) {
   const int rc = ForEach(h, [&](SubSolver* g, int) { return sub::ilqg_reset(g, mask); });
-  if (rc == ILQG_OK && (mask & ILQG_RESET_SOLUTION)) h->op_t0 = h->subs[0]->host_desc.initial_time;  // a fresh OperatingPoint's t0
+  if (rc == ILQG_OK && (mask & ILQG_RESET_SOLUTION)) {
+    h->op_t0 = h->subs[0]->host_desc.initial_time;  // a fresh OperatingPoint's t0
+    for (SubSolver* g : h->subs) UpdateCostGates(&g->d, h->op_t0);
+  }
   return rc;
 }
 
@@ -1877,14 +1957,20 @@ int ilqg_setup_next_receding_horizon(ilqg_handle h, const float* x0, double t0, 
   times.integrate_to = remaining_time_this_step <= planner_runtime ? (int)last_integration_timestep : 0;
   times.dt_half = (float)(kTimeStep / 2.0);
   const int ego_kind = d.sub[0].kind;
-  times.position_distance = ego_kind != ILQG_DYN_AIR3D;
-  times.ego_dim = ego_kind == ILQG_DYN_CAR6D ? 6 : ego_kind == ILQG_DYN_UNICYCLE4D ? 4 : lo.xdim;
+  // MultiPlayerIntegrableSystem::DistanceBetween of the problem's dynamics is positional everywhere: the
+  // concatenated systems look at the first subsystem's (x, y) (src/concatenated_dynamical_system.cpp:109-113;
+  // a Dubins ego has no override: its whole state), Air3D and TwoPlayerUnicycle4D at their first two states
+  // (air_3d.h:151-157, two_player_unicycle_4d.h:141-147)
+  times.position_distance = ego_kind == ILQG_DYN_DUBINS ? 2 : 1;
+  times.ego_dim = (ego_kind == ILQG_DYN_AIR3D || ego_kind == ILQG_DYN_TWO_PLAYER_UNICYCLE4D) ? lo.xdim
+                                                                                            : SubsystemXdim(ego_kind);
   const size_t n = lo.xdim;
   const int rc = ForEach(h, [&](SubSolver* g, int first) {
     return sub::ilqg_setup_next_receding_horizon(g, x0 + (size_t)first * n, times);
   });
   if (rc != ILQG_OK) return rc;
   h->op_t0 = op_t0;
+  for (SubSolver* g : h->subs) UpdateCostGates(&g->d, op_t0);  // RelativeTimeTracker::ResetInitialTime(op.t0), src/problem.cpp:120
   if (new_t0) *new_t0 = op_t0;
   return ILQG_OK;
 }

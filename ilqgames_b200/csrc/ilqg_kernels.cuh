@@ -1,6 +1,6 @@
 // ilqg_kernels.cuh -- the sm_100a kernels of the batched iLQ hot path.
 //
-//   k_linearize_quadraticize  K_lq : one warp per (instance, timestep) LQ record
+//   (K_lq, linearize + quadraticize, lives in ilqg_records.cuh)
 //   k_lq_backward             K_bwd: one warp per instance, coupled Riccati sweep with the
 //                                    running Z_i, zeta_i resident in shared memory, register-tiled
 //                                    F^T Z F, per-lane LU of the stacked S X = Y system,
@@ -75,72 +75,6 @@ __device__ __forceinline__ int sel_instance(const Slab& s, const Sel& sel, int s
     if (sel.mode == SEL_MAIN && s.queued_flag[b]) *live = false;
   }
   return b;
-}
-
-// ===========================================================================
-// K_lq: fused ComputeLinearization + ComputeCostQuadraticization
-// (src/ilq_solver.cpp:437-455, 471-490; PlayerCost::Quadraticize src/player_cost.cpp:194-225)
-// ===========================================================================
-constexpr int KLQ_WARPS = 4;
-
-__global__ void __launch_bounds__(KLQ_WARPS * 32)
-k_linearize_quadraticize(const __grid_constant__ DevDesc d, Slab s, int only_running) {
-  extern __shared__ __align__(16) float smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long w = (long long)blockIdx.x * KLQ_WARPS + warp;
-  const int b = (int)(w / d.T), k = (int)(w % d.T);
-  if (b >= s.B) return;
-  if (only_running && !instance_iterates(s, b)) return;
-  const int n = d.n, M = d.M, N = d.N;
-  float* rec = smem + (size_t)warp * (d.rec + round4(n + M));
-  float* xu = rec + d.rec;
-  const int cur = s.op_cur[b];
-  const float* xs = s.op_xs[cur] + ((size_t)b * d.T + k) * n;
-  const float* us = s.op_us[cur] + ((size_t)b * d.T + k) * M;
-  for (int e = lane; e < n + M; e += 32) xu[e] = e < n ? xs[e] : us[e - n];
-  // LinearDynamicsApproximation ctor: A = I, B = 0 (linear_dynamics_approximation.h:65-70);
-  // QuadraticCostApproximation(xdim, state_reg): reg*I, zero grad (quadratic_cost_approximation.h:80-82)
-  for (int e = lane; e < d.rec; e += 32) rec[e] = 0.f;
-  __syncwarp();
-  for (int a = lane; a < n; a += 32) {
-    rec[d.offA + a * n + a] = 1.f;
-    for (int i = 0; i < N; i++) rec[d.offQ + (i * n + a) * n + a] = d.state_reg[i];
-  }
-  if (lane < d.num_pairs) {
-    const int mj = d.udim[d.pair_j[lane]];
-    for (int a = 0; a < mj; a++) rec[d.offR + d.pair_Roff[lane] + a * mj + a] = d.control_reg[d.pair_i[lane]];
-  }
-  __syncwarp();
-  const float* x = xu;
-  const float* u = xu + n;
-  if (lane < N) {
-    // player `lane`: its records in the reference's accumulation order
-    const int i = lane;
-    const bool full = d.cost_structure[i] == ILQG_COST_SUM || s.te_quad[(size_t)b * N + i] == k;
-    const float mu = s.mu[b];
-    for (int c = d.cost_begin[i]; c < d.cost_begin[i + 1]; c++) {
-      const DevCost& cd = d.cost[c];
-      const bool is_con = cd.slot >= 0;
-      if (!full && (cd.arg < 0 || is_con)) continue;  // QuadraticizeControlCosts
-      const float lambda =
-          is_con ? s.lambdas[((size_t)b * d.num_constraints + cd.slot) * d.T + s.lambda_index[k]] : 0.f;
-      if (cd.arg < 0)
-        quadraticize_record<true>(d, cd, x, n, lambda, mu, rec + d.offQ + i * n * n, n,
-                                  rec + d.offl + i * n);
-      else {
-        const int mj = d.udim[cd.arg];
-        quadraticize_record<true>(d, cd, u + d.uoff[cd.arg], mj, lambda, mu,
-                                  rec + d.offR + d.pair_Roff[cd.pair], mj,
-                                  rec + d.offr + d.pair_roff[cd.pair]);
-      }
-    }
-  } else if (lane - N < d.num_subsystems) {
-    subsystem_linearize(d, d.sub[lane - N], x, u, rec + d.offA, rec + d.offB);
-  }
-  __syncwarp();
-  float4* dst = reinterpret_cast<float4*>(s.rec + ((size_t)b * d.T + k) * d.rec);
-  const float4* src = reinterpret_cast<const float4*>(rec);
-  for (int e = lane; e < d.rec / 4; e += 32) dst[e] = src[e];
 }
 
 // ===========================================================================

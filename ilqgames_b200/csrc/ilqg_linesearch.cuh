@@ -154,7 +154,8 @@ __host__ __device__ inline int ls_rollout_smem_floats(int n, int S) {
   return 2 * n * 32 + S * 32 + S * 2 * 32 * (2 * n + 4);
 }
 
-template <int S>
+// NUQ: control inputs a subsystem can have in this instance (2; 4 only with a TwoPlayerUnicycle4D)
+template <int S, int NUQ>
 __global__ void __launch_bounds__(S * 32)
 k_ls_rollout(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode, int cur_q,
              int q_offset) {
@@ -180,7 +181,7 @@ k_ls_rollout(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScr
 
   const DevSubsystem& sub = d.sub[warp];
   const int xd = subsystem_xdim(sub.kind);
-  const int nu = sub.kind == ILQG_DYN_AIR3D ? 2 : d.udim[sub.first_player];  // own control rows
+  const int nu = sub.nu;  // control inputs of this subsystem (rows of P it evaluates)
   float x[6];
 #pragma unroll
   for (int a = 0; a < 6; a++) x[a] = (valid && a < xd) ? io.x_start[sub.x_offset + a] : 0.f;
@@ -191,7 +192,9 @@ k_ls_rollout(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScr
   const bool vecP = (n & 3) == 0 && nu <= 2;
   const int PST = 2 * n + 4;
   float* pbuf = pbase + (size_t)warp * 2 * 32 * PST;
-  float nref[6], nuref[2] = {0.f, 0.f}, nal[2] = {0.f, 0.f};
+  float nref[6], nuref[NUQ], nal[NUQ];
+#pragma unroll
+  for (int q = 0; q < NUQ; q++) nuref[q] = nal[q] = 0.f;
   bool absorbed = true;
   auto prefetch = [&](int k) {
     if (!valid) return;
@@ -200,9 +203,9 @@ k_ls_rollout(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScr
       if (a < xd)
         nref[a] = k > 0 ? io.last_xs[(size_t)k * n + sub.x_offset + a] : io.x_start[sub.x_offset + a];
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
+    for (int q = 0; q < NUQ; q++) {
       if (q >= nu) break;
-      const int c = q == 0 ? sub.u_offset : sub.u_offset2;
+      const int c = sub.ucol[q];
       nuref[q] = io.last_us[(size_t)k * M + c];
       nal[q] = io.alpha[(size_t)k * M + c];
       if (vecP) {
@@ -221,11 +224,11 @@ k_ls_rollout(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScr
   prefetch(0);
   for (int k = 0; k < T; k++) {
     float* dxs = dxs2 + (k & 1) * n * 32;
-    float ref[6], uref[2], al[2];
+    float ref[6], uref[NUQ], al[NUQ];
 #pragma unroll
     for (int a = 0; a < 6; a++) ref[a] = nref[a];
-    uref[0] = nuref[0]; uref[1] = nuref[1];
-    al[0] = nal[0]; al[1] = nal[1];
+#pragma unroll
+    for (int q = 0; q < NUQ; q++) { uref[q] = nuref[q]; al[q] = nal[q]; }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (k + 1 < T) prefetch(k + 1);
 #pragma unroll
@@ -239,11 +242,11 @@ k_ls_rollout(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScr
     // other half while the others may still be reading this one
     if (S > 1) __syncthreads();
     else __syncwarp();
-    float uu[2] = {0.f, 0.f};
+    float uu[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
+    for (int q = 0; q < NUQ; q++) {
       if (q >= nu) break;
-      const int c = q == 0 ? sub.u_offset : sub.u_offset2;
+      const int c = sub.ucol[q];
       float uv = 0.f;
       if (valid) {
         float acc = 0.f;
@@ -276,7 +279,7 @@ k_ls_rollout(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScr
       }
       uu[q] = uv;
     }
-    if (k < T - 1) subsystem_integrate(sub, dt_half, x, uu[0], uu[1]);
+    if (k < T - 1) subsystem_integrate(sub, dt_half, x, uu);
   }
   // If u_k = (u_ref - P dx) - alpha_k s0 rho^j rounded to (u_ref - P dx) at every step, every
   // deeper candidate (smaller alpha) reproduces this rollout bit for bit: k_ls_decide can run
@@ -355,8 +358,12 @@ k_ls_merit(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScrat
     for (int a = 0; a < n + M; a++) acc[a * 32 + lane] = 0.f;
     const bool full = additive || te == kk;
     float value = 0.f;
-    for (int c = d.cost_begin[i]; c < d.cost_begin[i + 1]; c++) {
+    for (int c0 = d.cost_begin[i]; c0 < d.cost_begin[i + 1];) {
+      // an ExtremeValueCost (group > 0) stands for its extreme member (src/extreme_value_cost.cpp:50-62)
+      const int c = d.cost[c0].group > 0 ? extreme_member<32>(d, c0, slot + lane, slot + n * 32 + lane) : c0;
+      c0 = d.cost[c0].group > 0 ? d.cost[c0].group_end : c0 + 1;
       const DevCost& cd = d.cost[c];
+      if (kk < cd.first_step) continue;  // FinalTimeCost: zero value and derivatives before its threshold
       const bool is_con = cd.slot >= 0;
       // PlayerCost::Quadraticize vs QuadraticizeControlCosts (src/ilq_solver.cpp:483-487): off the
       // extreme timestep of a MAX/MIN player only control COSTS enter the gradient; the cost

@@ -19,7 +19,8 @@ struct RhTimes {
   int integrate_from, integrate_to;  // Integrate(current_timestep + 1, last_integration_timestep, ...)
   float dt_half;           // kTimeStep / 2
   int ego_dim;             // Stitch: leading states taken from the nearest plan state
-  int position_distance;   // 1: ConcatenatedDynamicalSystem::DistanceBetween (first subsystem's x, y)
+  int position_distance;   // 1: DistanceBetween = first subsystem's (x, y) (ConcatenatedDynamicalSystem, Air3D::DistanceBetween
+                           // air_3d.h:151-157); 2: a Dubins ego's whole state; 0: squared 2-norm of the full state
 };
 
 constexpr int KRH_WARPS = 4;
@@ -56,7 +57,10 @@ k_receding_horizon(const __grid_constant__ DevDesc d, Slab s, const float* __res
       float xl[6];
 #pragma unroll
       for (int a = 0; a < 6; a++) xl[a] = a < xd ? from[sub.x_offset + a] : 0.f;
-      subsystem_integrate(sub, dt_half, xl, uu[sub.u_offset], uu[sub.u_offset2]);
+      float us[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) us[q] = q < sub.nu ? uu[sub.ucol[q]] : 0.f;
+      subsystem_integrate(sub, dt_half, xl, us);
 #pragma unroll
       for (int a = 0; a < 6; a++)
         if (a < xd) to[sub.x_offset + a] = xl[a];
@@ -87,10 +91,15 @@ k_receding_horizon(const __grid_constant__ DevDesc d, Slab s, const float* __res
   for (int kk = lane; kk < T; kk += 32) {
     const float* a = pxs + (size_t)kk * n;
     float dist = 0.f;
-    if (r.position_distance) {
+    if (r.position_distance == 1) {
       const int o = d.sub[0].x_offset;
       const float dx = x[o] - a[o], dy = x[o + 1] - a[o + 1];
       dist = dx * dx + dy * dy;
+    } else if (r.position_distance == 2) {
+      // SinglePlayerDubinsCar has no DistanceBetween of its own: the base class's squared 2-norm of the
+      // whole subsystem state, heading included (single_player_dynamical_system.h:68-71)
+      const int o = d.sub[0].x_offset;
+      for (int q = 0; q < 3; q++) dist += (x[o + q] - a[o + q]) * (x[o + q] - a[o + q]);
     } else {
       for (int q = 0; q < n; q++) dist += (x[q] - a[q]) * (x[q] - a[q]);
     }
@@ -180,7 +189,10 @@ k_integrate_plan(const __grid_constant__ DevDesc d, Slab s, float* __restrict__ 
       float xl[6];
 #pragma unroll
       for (int a = 0; a < 6; a++) xl[a] = a < xd ? x[sub.x_offset + a] : 0.f;
-      subsystem_integrate(sub, dt_half, xl, u[sub.u_offset], u[sub.u_offset2], substeps);
+      float us[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) us[q] = q < sub.nu ? u[sub.ucol[q]] : 0.f;
+      subsystem_integrate(sub, dt_half, xl, us, substeps);
 #pragma unroll
       for (int a = 0; a < 6; a++)
         if (a < xd) x[sub.x_offset + a] = xl[a];

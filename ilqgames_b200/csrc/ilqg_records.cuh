@@ -79,10 +79,21 @@ struct LinOffsetSink {
 // the same sequence.  `full` = PlayerCost::Quadraticize, else QuadraticizeControlCosts
 // (src/ilq_solver.cpp:483-487); in the latter case the skipped records still emit (zeros are
 // pushed by the caller through `skip`).
-template <int XS, class PlayerFn, class LinFn>
-__device__ __forceinline__ void walk_role(const DevDesc& d, int role, PlayerFn&& player, LinFn&& lin) {
+template <int XS, class PlayerFn, class LinFn, class ChooseFn>
+__device__ __forceinline__ void walk_role(const DevDesc& d, int role, PlayerFn&& player, LinFn&& lin, ChooseFn&& choose) {
   if (role < d.N) {
-    for (int c = d.cost_begin[role]; c < d.cost_begin[role + 1]; c++) player(d.cost[c]);
+    for (int c = d.cost_begin[role]; c < d.cost_begin[role + 1];) {
+      const DevCost& cd = d.cost[c];
+      if (cd.group > 0) {
+        // an ExtremeValueCost: every member emits its updates, only the extreme one non-zero
+        const int winner = choose(c);
+        for (int m = c; m < cd.group_end; m++) player(d.cost[m], m == winner);
+        c = cd.group_end;
+      } else {
+        player(cd, true);
+        c++;
+      }
+    }
   } else {
     for (int sidx = 0; sidx < d.num_subsystems; sidx++) lin(d.sub[sidx]);
   }
@@ -93,7 +104,9 @@ __device__ __forceinline__ int record_updates(const DevCost& cd, int dim) {
   switch (cd.kind) {
     case ILQG_COST_QUADRATIC: return cd.d0 >= 0 ? 2 : 2 * dim;
     case ILQG_COST_PROXIMITY:
-    case ILQG_CONSTRAINT_PROXIMITY: return 20;
+    case ILQG_CONSTRAINT_PROXIMITY:
+    case ILQG_COST_SIGNED_DISTANCE: return 20;
+    case ILQG_COST_QUADRATIC_DIFFERENCE: return 6 * cd.flag;
     case ILQG_COST_SEMIQUADRATIC:
     case ILQG_CONSTRAINT_SINGLE_DIMENSION: return 2;
     default: return 6;
@@ -114,7 +127,7 @@ __global__ void k_record_pattern(const __grid_constant__ DevDesc d, int* offsets
   const float* u = zeros + d.n;
   walk_role<1>(
       d, role,
-      [&](const DevCost& cd) {
+      [&](const DevCost& cd, bool) {
         if (cd.arg < 0) {
           sink.base_H = d.offQ + role * d.n * d.n;
           sink.ld = d.n;
@@ -131,7 +144,8 @@ __global__ void k_record_pattern(const __grid_constant__ DevDesc d, int* offsets
       [&](const DevSubsystem& sub) {
         LinOffsetSink lin{&sink, d.offA, d.offB, d.n, d.M};
         subsystem_linearize_sink<1>(d, sub, x, u, lin);
-      });
+      },
+      [](int c) { return c; });
   counts[role] = sink.cnt;
 }
 
@@ -206,7 +220,7 @@ k_linearize_quadraticize_v3(const __grid_constant__ DevDesc d, Slab s, RecordPat
                                    (live && s.te_quad[(size_t)b * N + warp] == k));
     walk_role<32>(
         d, warp,
-        [&](const DevCost& cd) {
+        [&](const DevCost& cd, bool chosen) {
           const bool is_con = cd.slot >= 0;
           const int dim = cd.arg < 0 ? n : d.udim[cd.arg];
           if (!full && (cd.arg < 0 || is_con)) {  // QuadraticizeControlCosts: record not visited
@@ -217,12 +231,15 @@ k_linearize_quadraticize_v3(const __grid_constant__ DevDesc d, Slab s, RecordPat
           const float lambda =
               (is_con && live) ? s.lambdas[((size_t)b * d.num_constraints + cd.slot) * T + s.lambda_index[k]] : 0.f;
           const float* in = cd.arg < 0 ? x : u + d.uoff[cd.arg] * 32;
-          quadraticize_record_sink<true, 32, false>(d, cd, in, dim, lambda, mu, sink);
+          // FinalTimeCost: nothing before its threshold; ExtremeValueCost: the extreme member only
+          quadraticize_record_sink<true, 32, false>(d, cd, in, dim, lambda, mu, sink, nullptr,
+                                                    chosen && k >= cd.first_step);
         },
         [&](const DevSubsystem& sub) {
           LinValueSink lin{&sink};
           subsystem_linearize_sink<32>(d, sub, x, u, lin);
-        });
+        },
+        [&](int c) { return extreme_member<32>(d, c, x, u); });
   }
   __syncthreads();
   // xu is dead: reuse its first 32 words as the per-record "assemble me" flags
@@ -299,7 +316,7 @@ __host__ __device__ inline size_t klq4_smem_bytes(int n, int M, int N, int E, in
 
 __global__ void __launch_bounds__(160)
 k_linearize_quadraticize_v4(const __grid_constant__ DevDesc d, Slab s, RecordPattern pat, CompactPattern cp,
-                            int only_running, Sel sel) {
+                            int only_running, Sel sel, int linesearch) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = d.n, M = d.M, N = d.N, T = d.T, NR = N + 1, E = pat.E;
@@ -352,7 +369,7 @@ k_linearize_quadraticize_v4(const __grid_constant__ DevDesc d, Slab s, RecordPat
                                    (live && s.te_quad[(size_t)b * N + warp] == k));
     walk_role<32>(
         d, warp,
-        [&](const DevCost& cd) {
+        [&](const DevCost& cd, bool chosen) {
           const bool is_con = cd.slot >= 0;
           const int dim = cd.arg < 0 ? n : d.udim[cd.arg];
           if (!full && (cd.arg < 0 || is_con)) {
@@ -363,16 +380,26 @@ k_linearize_quadraticize_v4(const __grid_constant__ DevDesc d, Slab s, RecordPat
           const float lambda =
               (is_con && live) ? s.lambdas[((size_t)b * d.num_constraints + cd.slot) * T + s.lambda_index[k]] : 0.f;
           const float* in = cd.arg < 0 ? x : u + d.uoff[cd.arg] * 32;
-          quadraticize_record_sink<true, 32, false>(d, cd, in, dim, lambda, mu, sink);
+          // FinalTimeCost: nothing before its threshold; ExtremeValueCost: the extreme member only
+          quadraticize_record_sink<true, 32, false>(d, cd, in, dim, lambda, mu, sink, nullptr,
+                                                    chosen && k >= cd.first_step);
         },
         [&](const DevSubsystem& sub) {
           LinValueSink lin{&sink};
           subsystem_linearize_sink<32>(d, sub, x, u, lin);
-        });
+        },
+        [&](int c) { return extreme_member<32>(d, c, x, u); });
   }
   __syncthreads();
   int* flags = reinterpret_cast<int*>(xu);
-  if (warp == 0) flags[lane] = live ? b + 1 : 0;
+  // Without a linesearch the reference quadraticizes ONCE, before the first iteration, and only
+  // re-linearizes afterwards (ModifyLQStrategies returns before MeritFunction would refresh the
+  // quadraticization, src/ilq_solver.cpp:114,322): such records keep their cost items.
+  int* keepq = flags + 32;
+  if (warp == 0) {
+    flags[lane] = live ? b + 1 : 0;
+    keepq[lane] = (live && !linesearch && s.iters[b] > 0) ? 1 : 0;
+  }
   __syncthreads();
 
   // ---- phase 2: warp w turns records w, w + NR, ... into item values + g_k ----
@@ -381,12 +408,16 @@ k_linearize_quadraticize_v4(const __grid_constant__ DevDesc d, Slab s, RecordPat
     const long long wr = first + r;
     if (wr >= total) break;
     if (!flags[r]) continue;
+    float* dst = s.crec + ((size_t)(flags[r] - 1) * T + (size_t)(wr % T)) * cp.NIp;
+    const bool keep_quad = keepq[r] != 0;
     for (int g = lane; g < NI; g += 32) {
       const int meta = g_meta[g];
       const int role = meta & 0xff, count = (meta >> 8) & 0xff, start = meta >> 16;
       const float* v = vals + (size_t)role * E * kValStride + r;
       float acc = g_base[g];
-      if (count <= 4) {
+      if (keep_quad && role < N) {
+        acc = dst[g];  // the quadraticization of the solve's first iteration stays
+      } else if (count <= 4) {
         const unsigned e01 = g_e01[g], e23 = g_e23[g];
         if (count > 0) acc += v[(e01 & 0xffff) * kValStride];
         if (count > 1) acc += v[(e01 >> 16) * kValStride];
@@ -414,7 +445,6 @@ k_linearize_quadraticize_v4(const __grid_constant__ DevDesc d, Slab s, RecordPat
       }
       gk += gi;
     }
-    float* dst = s.crec + ((size_t)(flags[r] - 1) * T + (size_t)(wr % T)) * cp.NIp;
     for (int g = lane; g < NI; g += 32) dst[g] = itv[g];
     if (lane < n) dst[NI + lane] = gk;
     if (lane < N) dst[NI + n + lane] = d.state_reg[lane];  // constants the sweep adds to the diagonal of Q_i

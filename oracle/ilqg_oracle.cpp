@@ -2087,7 +2087,9 @@ int ilqg_setup_next_receding_horizon(ilqg_handle h, const float* x0_in, double t
   if (!(std::abs(t0 + planner_runtime - op_t0) <= kTimeStep)) return ILQG_ERR_INVALID_ARGUMENT;  // :123
 
   const ilqg_subsystem_desc& ego = pr.d.subsystems[0];
-  const bool concatenated = ego.kind != ILQG_DYN_AIR3D;  // TwoPlayerUnicycle4D::DistanceBetween is positional too
+  // DistanceBetween is positional for every dynamics class but a Dubins ego: ConcatenatedDynamicalSystem
+  // (first subsystem), TwoPlayerUnicycle4D (two_player_unicycle_4d.h:141-147) and Air3D (head(2), air_3d.h:151-157)
+  const bool concatenated = true;
   for (int b = 0; b < h->batch; b++) {
     Instance& in = h->inst[b];
     real x[ILQG_MAX_XDIM], u[ILQG_MAX_UDIM], ref[ILQG_MAX_XDIM], nx[ILQG_MAX_XDIM];

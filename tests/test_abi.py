@@ -75,56 +75,58 @@ def test_invalid_descriptors_are_rejected(which, product_lib, oracle):
         assert lib.lib.ilqg_destroy(h) == 0
 
 
-def test_time_gated_records_fail_loudly_on_the_cuda_library(product_lib, oracle):
-    """FinalTimeCost records (ilqg_cost_desc::active_from != 0) exist in the oracle only so far: the
-    CUDA library must refuse them rather than ignore the gate."""
-    desc, _ = problems.two_player_collision()
-    assert sum(1 for c in range(desc.num_costs) if desc.costs[c].active_from != 0.0) == 4
-    p = problems.two_player_collision_params()
+def test_widened_descriptors_parse_on_the_cuda_library(product_lib, oracle):
+    """Row f4: FinalTimeCost gates, ExtremeValueCost groups, SinglePlayerCar5D / DubinsCar /
+    PointMass2D, TwoPlayerUnicycle4D, SignedDistanceCost and QuadraticDifferenceCost were oracle-only
+    in round 1 (the CUDA library answered ILQG_ERR_UNSUPPORTED).  The CUDA library's parser now takes
+    them: "no device" (-4) on the CPU-only builder, a handle on a GPU box -- never -2 / -1."""
     h = C.c_void_p()
-    assert product_lib.lib.ilqg_create(C.byref(desc), C.byref(p), 1, 0, C.byref(h)) == -2  # ILQG_ERR_UNSUPPORTED
-    assert oracle.lib.ilqg_create(C.byref(desc), C.byref(p), 1, 0, C.byref(h)) == 0
-    assert oracle.lib.ilqg_destroy(h) == 0
-    # likewise SinglePlayerCar5D / SignedDistanceCost (oracle-only kinds so far)
-    desc5, _ = problems.two_player_collision_avoidance_reachability()
+    p = abi.SolverParams.defaults()
+
+    def accepted(lib, desc, params):
+        rc = lib.lib.ilqg_create(C.byref(desc), C.byref(params), 1, 0, C.byref(h))
+        if rc == 0:
+            assert lib.lib.ilqg_destroy(h) == 0
+        return rc
+
+    desc, _ = problems.two_player_collision()           # FinalTimeCost gates
+    assert sum(1 for c in range(desc.num_costs) if desc.costs[c].active_from != 0.0) == 4
+    assert accepted(product_lib, desc, problems.two_player_collision_params()) in (0, -4)
+    assert accepted(oracle, desc, problems.two_player_collision_params()) == 0
     p5 = problems.two_player_collision_avoidance_reachability_params()
-    assert product_lib.lib.ilqg_create(C.byref(desc5), C.byref(p5), 1, 0, C.byref(h)) == -2
-    assert oracle.lib.ilqg_create(C.byref(desc5), C.byref(p5), 1, 0, C.byref(h)) == 0
-    assert oracle.lib.ilqg_destroy(h) == 0
-    descpm, _ = problems.modified_air_3d()                       # SinglePlayerPointMass2D
-    assert product_lib.lib.ilqg_create(C.byref(descpm), C.byref(p5), 1, 0, C.byref(h)) == -2
-    desc2p, _ = problems.two_player_reachability()               # TwoPlayerUnicycle4D
-    assert product_lib.lib.ilqg_create(C.byref(desc2p), C.byref(p5), 1, 0, C.byref(h)) == -2
-    desc1, _ = problems.one_player_reachability()                # SinglePlayerDubinsCar
-    assert product_lib.lib.ilqg_create(C.byref(desc1), C.byref(p5), 1, 0, C.byref(h)) == -2
-    # ... and ExtremeValueCost groups; a group member that is a constraint or gated is invalid
+    for build in (problems.two_player_collision_avoidance_reachability,    # Car5D, SignedDistanceCost
+                  problems.modified_air_3d,                                  # SinglePlayerPointMass2D
+                  problems.two_player_reachability,                          # TwoPlayerUnicycle4D
+                  problems.one_player_reachability,                          # SinglePlayerDubinsCar
+                  problems.dubins_origin,                                    # QuadraticDifferenceCost
+                  problems.three_player_collision_avoidance_reachability):   # ExtremeValueCost groups
+        d, _ = build()
+        assert accepted(product_lib, d, p5) in (0, -4), build.__name__
+        assert accepted(oracle, d, p5) == 0, build.__name__
     desc3, _ = problems.three_player_collision_avoidance_reachability()
     assert sorted({desc3.costs[c].group for c in range(desc3.num_costs)}) == [0, 1, 2, 3]
-    assert oracle.lib.ilqg_create(C.byref(desc3), C.byref(p5), 1, 0, C.byref(h)) == 0
-    assert oracle.lib.ilqg_destroy(h) == 0
-    for c in range(desc3.num_subsystems):
-        desc3.subsystems[c].kind = abi.DYN_UNICYCLE4D      # leave only the groups for the CUDA parser to object to
-    desc3.xdim = 12
-    for c in range(desc3.num_subsystems):
-        desc3.subsystems[c].x_offset = 4 * c
-    for c in range(desc3.num_costs):
-        if desc3.costs[c].kind == abi.COST_SIGNED_DISTANCE:
-            desc3.costs[c].kind = abi.COST_PROXIMITY
-            for q in range(4):
-                desc3.costs[c].dim[q] = desc3.costs[c].dim[q] // 5 * 4 + desc3.costs[c].dim[q] % 5
-    assert product_lib.lib.ilqg_create(C.byref(desc3), C.byref(p5), 1, 0, C.byref(h)) == -2
-    for c in range(desc3.num_costs):
-        desc3.costs[c].group = 0
-    rc = product_lib.lib.ilqg_create(C.byref(desc3), C.byref(p5), 1, 0, C.byref(h))
-    assert rc in (-4, 0)   # parses: "no device" on the CPU-only builder, a handle on a GPU box
-    if rc == 0:
-        assert product_lib.lib.ilqg_destroy(h) == 0
-    # a gate on a constraint record is not a thing in the reference (FinalTimeCost wraps Costs)
+    # a gate on a constraint record is not a thing in the reference (FinalTimeCost wraps Costs); a group
+    # member that is gated is invalid as well -- both libraries say so
     bad, _ = problems.three_player_intersection()
     for c in range(bad.num_costs):
         if bad.costs[c].kind == abi.CONSTRAINT_PROXIMITY:
             bad.costs[c].active_from = 1.0
     assert oracle.lib.ilqg_create(C.byref(bad), C.byref(p), 1, 0, C.byref(h)) == -1
+    assert product_lib.lib.ilqg_create(C.byref(bad), C.byref(p), 1, 0, C.byref(h)) == -1
+    for c in range(desc3.num_costs):
+        if desc3.costs[c].group > 0:
+            desc3.costs[c].active_from = 1.0
+            break
+    assert oracle.lib.ilqg_create(C.byref(desc3), C.byref(p5), 1, 0, C.byref(h)) == -1
+    assert product_lib.lib.ilqg_create(C.byref(desc3), C.byref(p5), 1, 0, C.byref(h)) == -1
+    # polyline ranges that overlap / overflow the segment table are refused (ADVICE r01)
+    over, _ = problems.three_player_intersection()
+    for q in range(over.num_polylines + 1):
+        over.polyline_start[q] = 0 if q == 0 else 100
+    assert product_lib.lib.ilqg_create(C.byref(over), C.byref(p), 1, 0, C.byref(h)) == -1
+    neg, _ = problems.three_player_intersection()
+    neg.costs[0].arg = -2
+    assert product_lib.lib.ilqg_create(C.byref(neg), C.byref(p), 1, 0, C.byref(h)) == -1
 
 
 def test_descriptor_shapes_of_the_three_configs(oracle):

@@ -54,6 +54,23 @@ CONFIGS = {
 HEADLINE = ["air_3d", "roundabout_merging", "three_player_intersection"]
 
 
+def _fixture_config(name):
+    """The other examples of the reference (row f4): descriptor and parameters as tests/test_ref_pins.py
+    builds them, initial states = the ones the reference fixture was generated on."""
+    from tests.test_ref_pins import CASES
+    build, params = CASES[name]
+    x0 = np.load(os.path.join(GOLDEN, f"ref_{name}.npz"))["x0"]
+    return (lambda num_time_steps=100: build()), params, (lambda b: x0[:b])
+
+
+WIDENED = ["two_player_collision", "two_player_collision_avoidance_reachability",
+           "three_player_collision_avoidance_reachability", "one_player_reachability", "dubins_origin",
+           "two_player_reachability", "modified_air_3d", "modified_three_player_intersection", "skeleton",
+           "three_player_intersection_reachability"]
+for _n in WIDENED:
+    CONFIGS[_n] = _fixture_config(_n)
+
+
 COUNTS = os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out", "parity_counts.jsonl")
 
 
@@ -92,6 +109,8 @@ def close(a, b, tol=STAGE_TOL, what="", atol=1e-5, rows=None, cond=None):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     assert a.shape == b.shape
+    same_nonfinite = (a == b) & ~np.isfinite(b)           # e.g. merit = +inf on both sides
+    a, b = np.where(same_nonfinite, 0.0, a), np.where(same_nonfinite, 0.0, b)
     finite = np.isfinite(b.reshape(len(b), -1)).all(axis=1)
     keep = finite if rows is None else (rows & finite)
     if not keep.any():
@@ -126,9 +145,9 @@ def wellposed(o32, o64, tol=1e-3):
     a = np.asarray(o32, np.float64).reshape(len(o32), -1)
     b = np.asarray(o64, np.float64).reshape(len(o64), -1)
     with np.errstate(invalid="ignore"):
-        err = np.abs(a - b).max(axis=1)
-        scale = np.abs(b).max(axis=1)
-    return np.isfinite(err) & np.isfinite(scale) & (err <= tol * scale + 1e-5)
+        err = np.where(a == b, 0.0, np.abs(a - b)).max(axis=1)   # (inf == inf: the merit with the linesearch off)
+        scale = np.where(np.isfinite(b), np.abs(b), 0.0).max(axis=1)
+    return np.isfinite(err) & (err <= tol * scale + 1e-5)
 
 
 def pair(product, oracle, name, batch, **param_overrides):
@@ -209,7 +228,7 @@ STAGE_CASES = [(n, 100) for n in HEADLINE] + [("roundabout_merging", 150), ("air
 
 
 @pytest.mark.parametrize("name,T", STAGE_CASES)
-def test_stage_parity(product, oracle, oracle64, name, T, iterations=2):
+def test_stage_parity(product, oracle, oracle64, name, T, iterations=2, min_wellposed=None):
     build, params, x0f = CONFIGS[name]
     desc, _ = build(num_time_steps=T)
     x0 = x0f(16)
@@ -234,8 +253,9 @@ def test_stage_parity(product, oracle, oracle64, name, T, iterations=2):
         nonlocal good
         a, b, b64 = c.download(what), o.download(what), o64.download(what)
         good = good & wellposed(b, b64)
-        # the LQ solution is the one stage whose rounding the CUDA path does not share with the oracle
-        cond = row_distance(b, b64) if "LQ" in label else None
+        # conditioning-aware: the LQ solution's rounding is not the oracle's (tensor cores), and every later
+        # stage inherits it -- amplified by the feedback rollout on the ill-conditioned examples
+        cond = None if label.startswith("prologue") or "record" in label else row_distance(b, b64)
         compared.append(close(a, b, tol=tol, rows=good, what=f"{label} field {what}", cond=cond))
 
     for what in (abi.XS, abi.US, abi.TOTAL_COSTS):
@@ -271,6 +291,8 @@ def test_stage_parity(product, oracle, oracle64, name, T, iterations=2):
     # well posed through two iterations at T = 100; RoundaboutMerging at T = 150 (regularisation 0,
     # a 50 % longer Riccati sweep) keeps 7 -- the fp32 and fp64 ORACLES part on the other nine
     floor = 5 if (name, T) == ("roundabout_merging", 150) else B // 2
+    if min_wellposed is not None:
+        floor = min_wellposed
     assert good.sum() >= floor, f"only {good.sum()} of {B} well-posed instances left"
     assert min(compared) >= floor
     for h in hs:
@@ -320,7 +342,7 @@ def test_against_golden_fixture(product, name):
 
 # ------------------------------------------------------------------ reference fixtures
 @pytest.mark.parametrize("name", HEADLINE)
-def test_against_reference_fixture(product, oracle64, name):
+def test_against_reference_fixture(product, oracle64, name, min_compared=6):
     """The CUDA path against outputs of the reference's own sources (tests/golden/ref_*.npz, made
     by tests/golden/make_ref_golden.py; the CPU oracle reproduces them bit for bit in
     tests/test_ref_pins.py).  Log iterate `it` of ILQSolver::Solve = the operating point after
@@ -360,13 +382,16 @@ def test_against_reference_fixture(product, oracle64, name):
                flow_on_stable=flow[stable].mean() if stable.any() else -1.0, rows_compared=ok.sum())
         if stable.any():
             assert flow_ok(flow, stable), f"iterate {it}: CUDA path follows the reference on {flow[stable].mean():.0%}"
-        close(c.download(abi.XS), ref_xs, tol=xs_tol, atol=1e-3, rows=ok, what=f"ref xs_{it}")
-        close(c.download(abi.US), ref_us, tol=xs_tol, atol=1e-3, rows=ok, what=f"ref us_{it}")
+        # (conditioning-aware like the stage tests: 4 x the reference's own distance to the fp64 answer)
+        close(c.download(abi.XS), ref_xs, tol=xs_tol, atol=1e-3, rows=ok, what=f"ref xs_{it}",
+              cond=row_distance(np.where(np.isfinite(ref_xs), ref_xs, 0.0), o64.download(abi.XS)))
+        close(c.download(abi.US), ref_us, tol=xs_tol, atol=1e-3, rows=ok, what=f"ref us_{it}",
+              cond=row_distance(np.where(np.isfinite(ref_us), ref_us, 0.0), o64.download(abi.US)))
         compared += int(ok.sum())
         stable_total += int(stable.sum())
         for h in hs:
             h.close()
-    assert compared >= max(6, int(0.8 * stable_total)), f"only {compared} of {stable_total} stable (instance, iterate) pairs compared"
+    assert compared >= max(min_compared, int(0.8 * stable_total)), f"only {compared} of {stable_total} stable (instance, iterate) pairs compared"
 
 
 # ------------------------------------------------------------------ open-loop LQ solver
