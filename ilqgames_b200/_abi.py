@@ -109,7 +109,7 @@ class Layout(C.Structure):
 
 # every symbol include/ilqg.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
-    "ilqg_create", "ilqg_destroy", "ilqg_strerror", "ilqg_abi_struct_size", "ilqg_get_layout",
+    "ilqg_create", "ilqg_create_multi", "ilqg_destroy", "ilqg_strerror", "ilqg_abi_struct_size", "ilqg_get_layout",
     "ilqg_upload_x0", "ilqg_upload_warmstart", "ilqg_upload", "ilqg_upload_lq",
     "ilqg_solve_begin", "ilqg_linearize_quadraticize", "ilqg_lq_backward", "ilqg_linesearch",
     "ilqg_iterate", "ilqg_al_update", "ilqg_overwrite_solution", "ilqg_al_post_solve",
@@ -138,6 +138,8 @@ class Library:
         self.lib = C.CDLL(path, mode=os.RTLD_LOCAL | os.RTLD_NOW)
         L = self.lib
         vp, ip, fp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)
+        L.ilqg_create_multi.argtypes = [C.POINTER(ProblemDesc), C.POINTER(SolverParams), C.c_int,
+                                        C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
         L.ilqg_create.argtypes = [C.POINTER(ProblemDesc), C.POINTER(SolverParams), C.c_int, C.c_int,
                                   C.POINTER(vp)]
         L.ilqg_destroy.argtypes = [vp]
@@ -204,11 +206,18 @@ class Handle:
     """One ilqg_handle: `batch` independent games on one device."""
 
     def __init__(self, lib: Library, desc: ProblemDesc, params: SolverParams, batch: int,
-                 device: int = 0):
+                 device=0):
+        """device: a CUDA ordinal, or a sequence of them (ilqg_create_multi: the batch sharded over
+        several GPUs of the node behind this one handle)."""
         self.lib = lib
         self._h = C.c_void_p()
-        lib.check(lib.lib.ilqg_create(C.byref(desc), C.byref(params), batch, device,
-                                      C.byref(self._h)), "ilqg_create")
+        if isinstance(device, (list, tuple)):
+            devs = (C.c_int * len(device))(*device)
+            lib.check(lib.lib.ilqg_create_multi(C.byref(desc), C.byref(params), batch, devs, len(device),
+                                                C.byref(self._h)), "ilqg_create_multi")
+        else:
+            lib.check(lib.lib.ilqg_create(C.byref(desc), C.byref(params), batch, device,
+                                          C.byref(self._h)), "ilqg_create")
         self.layout = Layout()
         lib.check(lib.lib.ilqg_get_layout(self._h, C.byref(self.layout)), "ilqg_get_layout")
         lo = self.layout

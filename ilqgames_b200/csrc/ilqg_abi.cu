@@ -864,15 +864,22 @@ int LaunchLsSplit(SubSolver* h, int mode, int blocks, int q_offset) {
   const size_t smem_m = sizeof(float) * (size_t)ls_merit_smem_floats(d.n, d.M, d.N);
   int rc = ILQG_ERR_UNSUPPORTED;
   int nuq = 2;
-  for (int k = 0; k < S; k++) nuq = std::max(nuq, d.sub[k].nu);
+  bool classic = true;  // only the headline examples' subsystem kinds: the lean rollout instance
+  for (int k = 0; k < S; k++) {
+    nuq = std::max(nuq, d.sub[k].nu);
+    classic = classic && (d.sub[k].kind == ILQG_DYN_CAR6D || d.sub[k].kind == ILQG_DYN_UNICYCLE4D || d.sub[k].kind == ILQG_DYN_AIR3D);
+  }
 #define LS_ROLL(SS)                                                                               \
   case SS:                                                                                        \
-    if (nuq <= 2) {                                                                               \
-      if ((rc = SetSmem(k_ls_rollout<SS, 2>, smem_r)) != ILQG_OK) return rc;                       \
-      k_ls_rollout<SS, 2><<<blocks, SS * 32, smem_r, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset); \
+    if (classic) {                                                                                \
+      if ((rc = SetSmem(k_ls_rollout<SS, 2, false>, smem_r)) != ILQG_OK) return rc;                \
+      k_ls_rollout<SS, 2, false><<<blocks, SS * 32, smem_r, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset); \
+    } else if (nuq <= 2) {                                                                        \
+      if ((rc = SetSmem(k_ls_rollout<SS, 2, true>, smem_r)) != ILQG_OK) return rc;                 \
+      k_ls_rollout<SS, 2, true><<<blocks, SS * 32, smem_r, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset); \
     } else {                                                                                      \
-      if ((rc = SetSmem(k_ls_rollout<SS, 4>, smem_r)) != ILQG_OK) return rc;                       \
-      k_ls_rollout<SS, 4><<<blocks, SS * 32, smem_r, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset); \
+      if ((rc = SetSmem(k_ls_rollout<SS, 4, true>, smem_r)) != ILQG_OK) return rc;                 \
+      k_ls_rollout<SS, 4, true><<<blocks, SS * 32, smem_r, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset); \
     }                                                                                             \
     break;
   switch (S) {
@@ -1701,7 +1708,7 @@ struct ilqg_solver {
   int al_max_iterates = 0;
   float al_tolerance = 0.f;
   bool al_first = true;
-  int* al_active_dev = nullptr;
+  std::vector<int*> al_active_dev;  // one counter per group, on the group's device
 };
 
 namespace {
@@ -1716,7 +1723,10 @@ int Fork(ilqg_solver* h) {
 int Join(ilqg_solver* h) {
   if (h->subs.size() == 1 && h->subs[0]->stream == h->stream) return ILQG_OK;
   for (size_t k = 0; k < h->subs.size(); k++) {
-    CUDA_TRY(cudaEventRecord(h->done[k], h->subs[k]->stream));
+    {
+      Guard gd(h->subs[k]->device);  // (a multi-device handle: the event lives on the group's device)
+      CUDA_TRY(cudaEventRecord(h->done[k], h->subs[k]->stream));
+    }
     CUDA_TRY(cudaStreamWaitEvent(h->stream, h->done[k], 0));
   }
   return ILQG_OK;
@@ -1763,40 +1773,37 @@ const char* ilqg_strerror(int code) {
   return "unknown error";
 }
 
-int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params, int batch, int device,
-                ilqg_handle* out) {
-  if (!desc || !params || !out || batch < 1) return ILQG_ERR_INVALID_ARGUMENT;
-  // one group: with the linesearch split into rollout and merit kernels the plain sequence on one
-  // stream is the fastest schedule measured (profiles/r01_schedule_experiments.md)
-  int groups = 1;
-  if (const char* e = std::getenv("ILQG_GROUPS")) groups = std::max(1, std::atoi(e));
-  groups = std::min(groups, batch);
+// groups[k] = (device, instances): the public handle is a list of per-device / per-stream groups over
+// contiguous slices of the batch (independent games, no hot-path exchange)
+static int CreateGroups(const ilqg_problem_desc* desc, const ilqg_solver_params* params, int batch,
+                        const std::vector<std::pair<int, int>>& groups, ilqg_handle* out) {
   ilqg_solver* h = new (std::nothrow) ilqg_solver();
   if (!h) return ILQG_ERR_OUT_OF_MEMORY;
   h->B = batch;
-  h->device = device;
+  h->device = groups[0].first;
   h->stream = nullptr;
   h->own_stream = nullptr;
   h->fork = nullptr;
-  int rc = ILQG_OK;
-  for (int g = 0; g < groups && rc == ILQG_OK; g++) {
-    const int lo = (int)((long long)batch * g / groups), hi = (int)((long long)batch * (g + 1) / groups);
+  int rc = ILQG_OK, lo = 0;
+  for (size_t g = 0; g < groups.size() && rc == ILQG_OK; g++) {
     SubSolver* sh = nullptr;
-    rc = sub::ilqg_create(desc, params, hi - lo, device, &sh);
+    rc = sub::ilqg_create(desc, params, groups[g].second, groups[g].first, &sh);
     if (rc == ILQG_OK) {
       h->subs.push_back(sh);
       h->first.push_back(lo);
+      lo += groups[g].second;
     }
   }
   if (rc == ILQG_OK) {
-    Guard guard(device);
+    Guard guard(h->device);
     if (!guard.ok || cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming) != cudaSuccess)
       rc = ILQG_ERR_CUDA;
     h->stream = h->own_stream;
     for (size_t k = 0; k < h->subs.size() && rc == ILQG_OK; k++) {
+      Guard gd(h->subs[k]->device);
       cudaEvent_t ev;
-      if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) rc = ILQG_ERR_CUDA;
+      if (!gd.ok || cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) rc = ILQG_ERR_CUDA;
       else h->done.push_back(ev);
     }
   }
@@ -1809,6 +1816,36 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
   h->op_t0 = desc->initial_time;
   *out = h;
   return ILQG_OK;
+}
+
+int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params, int batch, int device,
+                ilqg_handle* out) {
+  if (!desc || !params || !out || batch < 1) return ILQG_ERR_INVALID_ARGUMENT;
+  // one group: with the linesearch split into rollout and merit kernels the plain sequence on one
+  // stream is the fastest schedule measured (profiles/r01_schedule_experiments.md)
+  int groups = 1;
+  if (const char* e = std::getenv("ILQG_GROUPS")) groups = std::max(1, std::atoi(e));
+  groups = std::min(groups, batch);
+  std::vector<std::pair<int, int>> g;
+  for (int k = 0; k < groups; k++)
+    g.push_back({device, (int)((long long)batch * (k + 1) / groups) - (int)((long long)batch * k / groups)});
+  return CreateGroups(desc, params, batch, g, out);
+}
+
+// The batch sharded over several GPUs of one node behind ONE handle: device k owns a contiguous slice
+// (sizes differ by at most one game), every entry point fans out to the devices' streams and joins
+// them, uploads / downloads address the global batch.  No data-path collective: the games are
+// independent; the "gather" of converged trajectories is the downloads' device-to-host copies.
+int ilqg_create_multi(const ilqg_problem_desc* desc, const ilqg_solver_params* params, int batch,
+                      const int* devices, int num_devices, ilqg_handle* out) {
+  if (!desc || !params || !out || !devices || num_devices < 1 || batch < num_devices) return ILQG_ERR_INVALID_ARGUMENT;
+  for (int a = 0; a < num_devices; a++)
+    for (int b = a + 1; b < num_devices; b++)
+      if (devices[a] == devices[b]) return ILQG_ERR_INVALID_ARGUMENT;
+  std::vector<std::pair<int, int>> g;
+  const int base = batch / num_devices, rem = batch % num_devices;
+  for (int k = 0; k < num_devices; k++) g.push_back({devices[k], base + (k < rem ? 1 : 0)});
+  return CreateGroups(desc, params, batch, g, out);
 }
 
 int ilqg_destroy(ilqg_handle h) {
@@ -2077,21 +2114,34 @@ int ilqg_al_advance(ilqg_handle h, int* active) {
   if (running > 0) return ILQG_ERR_INVALID_ARGUMENT;  // the inner solve has not finished
   Guard guard(h->device);
   if (!guard.ok) return ILQG_ERR_CUDA;
-  SubSolver* g0 = h->subs[0];
-  if (!h->al_active_dev) {
-    if ((rc = DevAlloc(g0, &h->al_active_dev, 1)) != ILQG_OK) return rc;
+  if (h->al_active_dev.empty()) {
+    for (SubSolver* g : h->subs) {
+      Guard gd(g->device);
+      int* ctr = nullptr;
+      if ((rc = DevAlloc(g, &ctr, 1)) != ILQG_OK) return rc;
+      h->al_active_dev.push_back(ctr);
+    }
   }
-  CUDA_TRY(cudaMemsetAsync(h->al_active_dev, 0, sizeof(int), g0->stream));
-  CUDA_TRY(cudaStreamSynchronize(g0->stream));
+  for (size_t k = 0; k < h->subs.size(); k++) {
+    Guard gd(h->subs[k]->device);
+    CUDA_TRY(cudaMemsetAsync(h->al_active_dev[k], 0, sizeof(int), h->subs[k]->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->subs[k]->stream));
+  }
   const int first = h->al_first ? 1 : 0;
+  size_t which = 0;
   rc = ForEach(h, [&](SubSolver* g, int) {
-    return sub::ilqg_al_advance(g, first, h->al_max_iterates, h->al_tolerance, h->al_active_dev);
+    return sub::ilqg_al_advance(g, first, h->al_max_iterates, h->al_tolerance, h->al_active_dev[which++]);
   });
   if (rc != ILQG_OK) return rc;
   h->al_first = false;
   if ((rc = ilqg_synchronize(h)) != ILQG_OK) return rc;
   int n = 0;
-  CUDA_TRY(cudaMemcpy(&n, h->al_active_dev, sizeof(int), cudaMemcpyDeviceToHost));
+  for (size_t k = 0; k < h->subs.size(); k++) {
+    Guard gd(h->subs[k]->device);
+    int v = 0;
+    CUDA_TRY(cudaMemcpy(&v, h->al_active_dev[k], sizeof(int), cudaMemcpyDeviceToHost));
+    n += v;
+  }
   if (active) *active = n;
   return ILQG_OK;
 }

@@ -155,7 +155,8 @@ __host__ __device__ inline int ls_rollout_smem_floats(int n, int S) {
 }
 
 // NUQ: control inputs a subsystem can have in this instance (2; 4 only with a TwoPlayerUnicycle4D)
-template <int S, int NUQ>
+// WIDE: subsystem kinds beyond Car6D / Unicycle4D / Air3D are compiled in (subsystem_xdot)
+template <int S, int NUQ, bool WIDE>
 __global__ void __launch_bounds__(S * 32)
 k_ls_rollout(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode, int cur_q,
              int q_offset) {
@@ -279,7 +280,7 @@ k_ls_rollout(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScr
       }
       uu[q] = uv;
     }
-    if (k < T - 1) subsystem_integrate(sub, dt_half, x, uu);
+    if (k < T - 1) subsystem_integrate<WIDE>(sub, dt_half, x, uu);
   }
   // If u_k = (u_ref - P dx) - alpha_k s0 rho^j rounded to (u_ref - P dx) at every step, every
   // deeper candidate (smaller alpha) reproduces this rollout bit for bit: k_ls_decide can run

@@ -131,8 +131,7 @@ typedef struct {
   /* FinalTimeCost(cost, threshold_time) (include/ilqgames/cost/final_time_cost.h:55-88): the
    * record counts only at time steps whose RelativeTime(kk) = kk * time_step is
    * >= RelativeTimeTracker::initial_time_ + active_from; 0 = always.  Costs only (not
-   * constraints).  ilqg_create of the CUDA library answers ILQG_ERR_UNSUPPORTED for a nonzero
-   * value (no device implementation yet); the CPU oracle implements it. */
+   * constraints). */
   double active_from;
   /* ExtremeValueCost(costs, is_min) (include/ilqgames/cost/extreme_value_cost.h:54-80,
    * src/extreme_value_cost.cpp:50-84): consecutive records of one player with the same group > 0
@@ -273,6 +272,14 @@ typedef struct ilqg_solver* ilqg_handle;
  * ordinal (ignored by the oracle). */
 int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
                 int batch, int device, ilqg_handle* out);
+/* Additive (the reference is single-threaded, one game per solver): the same handle with the batch
+ * sharded over `num_devices` GPUs of one node -- device devices[k] owns a contiguous slice of the
+ * games (sizes differ by at most one), every entry point fans out to the devices and joins them,
+ * uploads / downloads address the global batch.  The games are independent (each has its own
+ * ILQSolver state: src/ilq_solver.cpp:76-172), so there is no exchange between devices; the gather
+ * of converged trajectories is the downloads.  The oracle ignores the device list. */
+int ilqg_create_multi(const ilqg_problem_desc* desc, const ilqg_solver_params* params, int batch,
+                      const int* devices, int num_devices, ilqg_handle* out);
 int ilqg_destroy(ilqg_handle h);
 const char* ilqg_strerror(int code);
 /* sizeof() of the ABI structs as compiled (0: ilqg_problem_desc, 1:

@@ -188,6 +188,12 @@ class Handle {
     ILQG_CALL(ilqg_create(&desc, &params, batch, device, &h_));
     ILQG_CALL(ilqg_get_layout(h_, &lo_));
   }
+  // the batch sharded over several GPUs of the node (ilqg_create_multi)
+  Handle(const ilqg_problem_desc& desc, const ilqg_solver_params& params, int batch, const std::vector<int>& devices)
+      : h_(nullptr) {
+    ILQG_CALL(ilqg_create_multi(&desc, &params, batch, devices.data(), (int)devices.size(), &h_));
+    ILQG_CALL(ilqg_get_layout(h_, &lo_));
+  }
   ~Handle() { if (h_) ilqg_destroy(h_); }
   Handle(const Handle&) = delete;
   Handle& operator=(const Handle&) = delete;
@@ -388,9 +394,20 @@ class ILQSolver : public GameSolver {
   // Additive: the same Solve() for many initial states at once, one game per x0, all starting
   // from the problem's current operating point and strategies.  The problem is not modified.
   std::vector<BatchSolution> SolveBatch(const std::vector<VectorXf>& x0s, int device = 0) {
+    return SolveBatch(x0s, std::vector<int>{device});
+  }
+
+  // ... and the batch sharded over several GPUs of the node: devices[k] solves a contiguous slice of
+  // the games (no exchange between devices: the games are independent), results come back in order.
+  std::vector<BatchSolution> SolveBatch(const std::vector<VectorXf>& x0s, const std::vector<int>& devices) {
     const int B = (int)x0s.size();
     CHECK_GT(B, 0);
-    if (!batch_ || batch_->B() != B) batch_.reset(new b200::Handle(desc_, abi_params_, B, device));
+    CHECK(!devices.empty());
+    if (!batch_ || batch_->B() != B || batch_devices_ != devices) {
+      if (devices.size() == 1) batch_.reset(new b200::Handle(desc_, abi_params_, B, devices[0]));
+      else batch_.reset(new b200::Handle(desc_, abi_params_, B, devices));
+      batch_devices_ = devices;
+    }
     b200::Handle& h = *batch_;
     std::vector<float> packed((size_t)B * h.n());
     for (int b = 0; b < B; b++) {
@@ -436,6 +453,7 @@ class ILQSolver : public GameSolver {
   ilqg_problem_desc desc_;
   ilqg_solver_params abi_params_;
   std::unique_ptr<b200::Handle> single_, batch_;
+  std::vector<int> batch_devices_;
 };
 
 // ---- include/ilqgames/solver/lq_solver.h:57-81, lq_feedback_solver.h:70-124,

@@ -1763,6 +1763,13 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
   return ILQG_OK;
 }
 
+// ilqg_create_multi (include/ilqg.h): the device list means nothing on the CPU
+int ilqg_create_multi(const ilqg_problem_desc* desc, const ilqg_solver_params* params, int batch,
+                      const int* devices, int num_devices, ilqg_handle* out) {
+  if (!devices || num_devices < 1 || batch < num_devices) return ILQG_ERR_INVALID_ARGUMENT;
+  return ilqg_create(desc, params, batch, 0, out);
+}
+
 int ilqg_destroy(ilqg_handle h) {
   if (!h) return ILQG_ERR_BAD_HANDLE;
   delete h;

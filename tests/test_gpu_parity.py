@@ -761,3 +761,28 @@ def test_ragged_batch_and_horizon(product, oracle, oracle64, batch, T):
     np.testing.assert_array_equal(c.download(abi.XS)[:, 0], x0)
     for h in hs:
         h.close()
+
+
+# ------------------------------------------------------------------ multi-GPU behind the API
+def test_multi_device_handle_equals_single_device(product):
+    """ilqg_create_multi (SURVEY 8e behind the product API, not only under torchrun): the batch sharded
+    over two GPUs of the box by ONE handle reproduces the single-GPU solve bit for bit (the games are
+    independent and every device runs the same kernels).  Skipped on a one-GPU box."""
+    desc, _ = problems.three_player_intersection()
+    params = problems.three_player_intersection_params(max_solver_iters=3, disable_convergence_exit=1)
+    B = 257  # odd on purpose: the shards differ by one game
+    x0 = problems.three_player_intersection_x0_batch(B, 11)
+    try:
+        hm = abi.Handle(product, desc, params, B, [0, 1])
+    except abi.IlqgError as e:
+        pytest.skip(f"needs two GPUs: {e}")
+    outs = []
+    for h in (abi.Handle(product, desc, params, B, 0), hm):
+        h.upload_x0(x0)
+        h.solve_begin()
+        h.solve(chunk=3)
+        outs.append([h.download(w) for w in (abi.XS, abi.US, abi.PS, abi.ALPHAS, abi.STATUS, abi.ITERS, abi.BACKTRACKS,
+                                             abi.LIN_A, abi.QUAD_Q)])
+        h.close()
+    for a, b in zip(*outs):
+        np.testing.assert_array_equal(a, b)

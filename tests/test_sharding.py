@@ -73,3 +73,26 @@ def test_two_rank_gloo_run_matches_single_process(tmp_path, oracle):
     h.iterate(2)
     assert agg["total"] == int(h.download(abi.ITERS).sum())
     np.testing.assert_array_equal(np.load(out), h.download(abi.XS))
+
+
+def test_multi_device_handle_shards_one_batch(oracle):
+    """ilqg_create_multi through the ABI (the oracle ignores the device list): one handle, the global
+    batch addressed as a whole -- the results equal a single-device handle's, row for row."""
+    import numpy as np
+    from ilqgames_b200 import _abi as abi, problems
+    desc, _ = problems.three_player_intersection(num_time_steps=20)
+    params = problems.three_player_intersection_params(max_solver_iters=2)
+    x0 = problems.three_player_intersection_x0_batch(5, 3)
+    out = []
+    for dev in (0, [0, 1]):
+        h = abi.Handle(oracle, desc, params, 5, dev)
+        h.upload_x0(x0)
+        h.solve_begin()
+        h.solve(chunk=2)
+        out.append((h.download(abi.XS), h.download(abi.STATUS)))
+        h.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    import ctypes as C
+    hh = C.c_void_p()
+    devs = (C.c_int * 2)(0, 1)
+    assert oracle.lib.ilqg_create_multi(C.byref(desc), C.byref(params), 1, devs, 2, C.byref(hh)) == -1  # batch < devices
