@@ -389,7 +389,7 @@ class Handle:
     def synchronize(self):
         self.lib.check(self.lib.lib.ilqg_synchronize(self._h), "synchronize")
 
-    RESET_SOLVER, RESET_MULTIPLIERS, RESET_SOLUTION = 1, 2, 4
+    RESET_SOLVER, RESET_MULTIPLIERS, RESET_SOLUTION, RESET_LAMBDAS, RESET_MU = 1, 2, 4, 8, 16
 
     def reset(self, mask: int = 1):
         self.lib.check(self.lib.lib.ilqg_reset(self._h, mask), "reset")

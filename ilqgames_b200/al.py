@@ -52,11 +52,13 @@ def solve_augmented_lagrangian(h: abi.Handle, max_solver_iters: int = DEFAULT_MA
                    h.download(abi.MAX_CONSTRAINT_ERROR), h.download(abi.XS), h.download(abi.US),
                    h.download(abi.PS), h.download(abi.ALPHAS))
     # :192-207 -- the Problem gets its initial solution back and the multipliers their defaults,
-    # unless the caller keeps them (SolverParams::reset_problem / reset_lambdas / reset_mu; the two
-    # multiplier flags travel together here).  ilqg_reset also ends the AL solve.
+    # unless the caller keeps them (SolverParams::reset_problem / reset_lambdas / reset_mu, independent
+    # flags as in the reference).  ilqg_reset also ends the AL solve.
     mask = 0
-    if reset_lambdas and reset_mu:
-        mask |= h.RESET_MULTIPLIERS
+    if reset_lambdas:
+        mask |= h.RESET_LAMBDAS
+    if reset_mu:
+        mask |= h.RESET_MU
     if reset_problem and initial_warmstart is None:
         mask |= h.RESET_SOLUTION      # Problem::Initialize's zero operating point and strategies
     if mask:

@@ -16,7 +16,7 @@ LIB = os.path.join(LIBDIR, "libilqg_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared",
-    "-Xlinker", "-Bsymbolic",
+    "-Xlinker", "-Bsymbolic", "-ldl",
 ]
 
 

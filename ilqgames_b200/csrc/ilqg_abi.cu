@@ -9,6 +9,8 @@
 #include <new>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges around every launch site
+
 #include "ilqg_backward_any.cuh"
 #include "ilqg_backward_tc.cuh"
 #include "ilqg_linesearch.cuh"
@@ -353,12 +355,23 @@ constexpr DimsEntry kDims[] = {
 constexpr int kNumDims = sizeof(kDims) / sizeof(kDims[0]);
 
 
-struct ProfScope {  // brackets one launch with events when profiling is on
+// NVTX range names of the launch sites (the `kind` of a ProfScope)
+static const char* const kRangeNames[8] = {"ilqg/K_lq linearize+quadraticize", "ilqg/K_bwd Riccati sweep", "ilqg/linesearch",
+                                           "ilqg/solve_begin", "ilqg/K_ls first window", "ilqg/K_ls queued window",
+                                           "ilqg/K_ls decide", "ilqg/K_ls prologue rollout"};
+
+struct NvtxRange {  // the launch sites outside the hot loop
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
+struct ProfScope {  // brackets one launch site: an NVTX range always, CUDA events when profiling is on
   SubSolver* h;
   cudaEvent_t a, b;
   int kind;
   bool on;
   ProfScope(SubSolver* hh, int k) : h(hh), a(nullptr), b(nullptr), kind(k), on(hh->profiling) {
+    nvtxRangePushA(kRangeNames[k & 7]);
     if (on) {
       on = cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess;
       if (on) cudaEventRecord(a, h->stream);
@@ -369,6 +382,7 @@ struct ProfScope {  // brackets one launch with events when profiling is on
       cudaEventRecord(b, h->stream);
       h->samples.push_back({a, b, kind});
     }
+    nvtxRangePop();
   }
 };
 
@@ -405,6 +419,7 @@ int EnsureDense(SubSolver* h) {
   int rc = EnsureDenseAlloc(h);
   if (rc != ILQG_OK) return rc;
   if (h->dense_valid || !h->compact_valid) return ILQG_OK;
+  NvtxRange nvtx("ilqg/expand compact records");
   const long long recs = (long long)h->B * h->d.T;
   k_expand_records<<<(int)((recs + 3) / 4), 128, 0, h->stream>>>(h->d, h->s, h->pat, h->cp);
   h->launches++;
@@ -457,7 +472,7 @@ int LaunchOpenLoop(SubSolver* h, int only_running, bool use_lq_x0) {
 // with_dxs: also produce ILQG_DELTA_XS (an optional output of LQFeedbackSolver::Solve that the
 // iLQ loop itself never reads once ExpectedDecrease is fused into the backward sweep)
 template <int NXP, int MUP, int SC, int QA, int MINB>
-int LaunchBackwardTc(SubSolver* h, int only_running, Sel sel) {
+int LaunchBackwardTc(SubSolver* h, int only_running, Sel sel, const float* x0arg) {
   size_t smem = sizeof(float) * (((size_t)h->tc.total_words + 3) / 4 * 4 + 2 * KTC_WARPS + (size_t)KTC_WARPS * h->tc.per_game);
   // ILQG_TC_BLOCKS = k caps the sweep at k resident blocks per SM (by asking for more shared memory than it
   // needs), which leaves registers and shared memory for the side stream's linesearch blocks to run under it
@@ -467,15 +482,15 @@ int LaunchBackwardTc(SubSolver* h, int only_running, Sel sel) {
   if (rc != ILQG_OK) return rc;
   ProfScope prof(h, 1);
   k_lq_backward_tc<NXP, MUP, SC, QA, MINB><<<(h->B + KTC_WARPS - 1) / KTC_WARPS, KTC_WARPS * 32, smem, h->stream>>>(
-      h->d, h->p, h->s, h->tc, only_running, sel);
+      h->d, h->p, h->s, h->tc, only_running, sel, x0arg);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
   return ILQG_OK;
 }
 
-int DispatchBackwardTc(SubSolver* h, int only_running, Sel sel) {
+int DispatchBackwardTc(SubSolver* h, int only_running, Sel sel, const float* x0arg) {
 #define X(NXP, MUP, SC, QA, MINB) \
-  if (h->tc_nxp == NXP && h->tc_mup == MUP) return LaunchBackwardTc<NXP, MUP, SC, QA, MINB>(h, only_running, sel);
+  if (h->tc_nxp == NXP && h->tc_mup == MUP) return LaunchBackwardTc<NXP, MUP, SC, QA, MINB>(h, only_running, sel, x0arg);
   ILQG_TC_INSTANCES(X)
 #undef X
   return ILQG_ERR_UNSUPPORTED;
@@ -485,7 +500,7 @@ int DispatchBackward(SubSolver* h, int only_running, bool with_dxs, Sel sel = Se
   int rc = ILQG_ERR_UNSUPPORTED;
   if (!h->open_loop && h->cp_ok && h->use_compact && h->compact_valid) {
     // the hot path: tensor-core sweep over the compact records
-    if ((rc = DispatchBackwardTc(h, only_running, sel)) != ILQG_OK) return rc;
+    if ((rc = DispatchBackwardTc(h, only_running, sel, with_dxs ? h->s.lq_x0 : nullptr)) != ILQG_OK) return rc;
     if (with_dxs) {
       if ((rc = EnsureDense(h)) != ILQG_OK) return rc;
       k_delta_xs<<<(h->B + 3) / 4, 128, sizeof(float) * 4 * 2 * ILQG_MAX_XDIM, h->stream>>>(h->d, h->s, h->s.lq_x0);
@@ -505,6 +520,10 @@ int DispatchBackward(SubSolver* h, int only_running, bool with_dxs, Sel sel = Se
   if (key == 0 || key == 1)
     for (int i = 0; i < h->d.N; i++)
       if (h->d.udim[i] * h->d.N != h->d.M) key = -1;
+  // a stand-alone LQ solve (with_dxs: it may carry a non-zero x0 argument) on the half-warp kernels' shapes also
+  // goes to the run-time-dimension kernel: the half-warp kernel's adjoint form of ExpectedDecrease assumes
+  // delta_x_0 = 0, the forward sweep of k_lq_backward_any does not
+  if (with_dxs && (key == 0 || key == 1)) key = -1;
   if (key < 0 || (sel.mode != SEL_ALL && (key == 2 || key == 3 || key == 5))) {
     // any other shape (and list / main selections on the warp kernels' shapes never occur: those
     // handles do not pipeline): the run-time-dimension kernel, which writes delta_xs itself
@@ -1373,6 +1392,7 @@ int ilqg_upload_x0(SubHandle h, const float* x0, size_t bytes) {
 int ilqg_upload_warmstart(SubHandle h, const float* xs, const float* us, const float* Ps,
                           const float* alphas) {
   ENTER(h);
+  NvtxRange nvtx("ilqg/upload warm start");
   const size_t B = h->B, T = h->d.T, n = h->d.n, M = h->d.M;
   struct Item {
     float* dst;
@@ -1489,6 +1509,7 @@ int ilqg_count_running(SubHandle h, int* running) {
 
 int ilqg_al_update(SubHandle h) {
   ENTER(h);
+  NvtxRange nvtx("ilqg/AL multiplier sweep");
   k_al_update<<<h->B, ILQG_MAX_COSTS, 0, h->stream>>>(h->d, h->p, h->s, 0);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -1497,6 +1518,7 @@ int ilqg_al_update(SubHandle h) {
 
 int ilqg_overwrite_solution(SubHandle h, int only_successful) {
   ENTER(h);
+  NvtxRange nvtx("ilqg/overwrite solution");
   k_overwrite_solution<<<h->B, 256, 0, h->stream>>>(h->d, h->s, only_successful, 0);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -1506,6 +1528,7 @@ int ilqg_overwrite_solution(SubHandle h, int only_successful) {
 // Problem::SetUpNextRecedingHorizon for this group's games (ilqg_receding.cuh); x_meas is host memory
 int ilqg_setup_next_receding_horizon(SubHandle h, const float* x_meas, const RhTimes& times) {
   ENTER(h);
+  NvtxRange nvtx("ilqg/receding horizon");
   const size_t floats = (size_t)h->B * h->d.n;
   int rc = EnsureStaging(h, floats);
   if (rc != ILQG_OK) return rc;
@@ -1519,6 +1542,7 @@ int ilqg_setup_next_receding_horizon(SubHandle h, const float* x_meas, const RhT
 
 int ilqg_integrate_plan(SubHandle h, const float* x_in, const IpTimes& times, float* x_out) {
   ENTER(h);
+  NvtxRange nvtx("ilqg/integrate plan");
   const size_t floats = (size_t)h->B * h->d.n;
   int rc = EnsureStaging(h, floats);
   if (rc != ILQG_OK) return rc;
@@ -1533,6 +1557,7 @@ int ilqg_integrate_plan(SubHandle h, const float* x_in, const IpTimes& times, fl
 
 int ilqg_al_post_solve(SubHandle h) {
   ENTER(h);
+  NvtxRange nvtx("ilqg/AL post solve");
   k_al_post_solve<<<h->B, 128, 0, h->stream>>>(h->d, h->p, h->s, 0);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -1541,6 +1566,7 @@ int ilqg_al_post_solve(SubHandle h) {
 
 int ilqg_al_begin(SubHandle h) {
   ENTER(h);
+  NvtxRange nvtx("ilqg/AL begin");
   k_al_begin<<<(h->B + 127) / 128, 128, 0, h->stream>>>(h->s);
   h->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -1550,6 +1576,7 @@ int ilqg_al_begin(SubHandle h) {
 // one AugmentedLagrangianSolver::Solve round; *active accumulates (device counter, read by the caller)
 int ilqg_al_advance(SubHandle h, int first, int max_iterates, float tolerance, int* d_active) {
   ENTER(h);
+  NvtxRange nvtx("ilqg/AL advance");
   k_al_account<<<(h->B + 127) / 128, 128, 0, h->stream>>>(h->d, h->s, first, max_iterates, tolerance, d_active);
   k_al_post_solve<<<h->B, 128, 0, h->stream>>>(h->d, h->p, h->s, AL_DO_DOWNSCALE);
   k_al_update<<<h->B, ILQG_MAX_COSTS, 0, h->stream>>>(h->d, h->p, h->s, AL_DO_UPDATE);
@@ -1611,6 +1638,7 @@ int ilqg_synchronize(SubHandle h) {
 
 int ilqg_reset(SubHandle h, int mask) {
   ENTER(h);
+  NvtxRange nvtx("ilqg/reset");
   int rc;
   const size_t B = h->B, T = h->d.T, n = h->d.n, M = h->d.M;
   Slab& s = h->s;
@@ -1619,8 +1647,9 @@ int ilqg_reset(SubHandle h, int mask) {
     if ((rc = Fill(h, s.last_merit, INFINITY, B)) != ILQG_OK) return rc;
     if ((rc = Fill(h, s.expected_decrease, INFINITY, B)) != ILQG_OK) return rc;
   }
-  if (mask & ILQG_RESET_MULTIPLIERS) {
+  if (mask & (ILQG_RESET_MULTIPLIERS | ILQG_RESET_LAMBDAS))
     CUDA_TRY(cudaMemsetAsync(s.lambdas, 0, sizeof(float) * std::max<size_t>(B * h->d.num_constraints * T, 1), h->stream));
+  if (mask & (ILQG_RESET_MULTIPLIERS | ILQG_RESET_MU)) {
     if ((rc = Fill(h, s.mu, 10.0f, B)) != ILQG_OK) return rc;
   }
   if (mask & ILQG_RESET_SOLUTION) {

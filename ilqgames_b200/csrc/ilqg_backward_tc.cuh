@@ -163,7 +163,7 @@ __device__ __noinline__ void lu_solve_pivot(float* Sm /*[MU][MU]*/, float* y /*[
 template <int NXP, int MUP, int SC, int QA, int MINB>
 __global__ void __launch_bounds__(KTC_WARPS * 32, MINB)
 k_lq_backward_tc(const __grid_constant__ DevDesc d, const DevParams p, Slab s, const __grid_constant__ TcTables tb,
-                 int only_running, Sel sel) {
+                 int only_running, Sel sel, const float* x0arg) {
   constexpr TcFixed L = tc_fixed(NXP, MUP);
   constexpr int LD = L.LD;
   constexpr int W = NXP / 4;              // columns per lane in the (control row, column group) mapping
@@ -701,6 +701,14 @@ k_lq_backward_tc(const __grid_constant__ DevDesc d, const DevParams p, Slab s, c
     add_Q();
     if (lane < NXP) pv[lane] = pn[lane];
     __syncwarp();
+  }
+  // a stand-alone solve with delta_x_0 = x0 != 0 (LQFeedbackSolver::Solve's x0 argument): the adjoint sum
+  // lacks  sum_{k >= 1} of the part of delta_x_k driven by x0  =  x0 . (A_0' p_1)  =  x0 . (p_0 - g_0)
+  if (x0arg) {
+    float part = lane < n ? x0arg[(size_t)b * n + lane] * (pv[lane] - vals[NI + lane]) : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    expected_decrease -= part;
   }
   if (lane == 0) s.expected_decrease[b] = expected_decrease;
 }

@@ -411,7 +411,9 @@ int ilqg_synchronize(ilqg_handle h);
  *   ILQG_RESET_MULTIPLIERS  lambda = 0, mu = 10 (augmented_lagrangian_solver.cpp:196-207)
  *   ILQG_RESET_SOLUTION     zero operating point and strategies, t0 back to the descriptor's
  *                           initial time (Problem::Initialize) */
-enum { ILQG_RESET_SOLVER = 1, ILQG_RESET_MULTIPLIERS = 2, ILQG_RESET_SOLUTION = 4 };
+/*   ILQG_RESET_LAMBDAS / ILQG_RESET_MU  the two halves of ILQG_RESET_MULTIPLIERS on their own
+ *                           (SolverParams::reset_lambdas / reset_mu are independent flags, :196-207) */
+enum { ILQG_RESET_SOLVER = 1, ILQG_RESET_MULTIPLIERS = 2, ILQG_RESET_SOLUTION = 4, ILQG_RESET_LAMBDAS = 8, ILQG_RESET_MU = 16 };
 int ilqg_reset(ilqg_handle h, int mask);
 
 /* Run this handle's kernels and copies on the caller's CUDA stream (a cudaStream_t passed as

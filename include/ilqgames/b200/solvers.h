@@ -624,7 +624,9 @@ class AugmentedLagrangianSolver : public GameSolver {
     h.UploadWarmStart(problem_->CurrentOperatingPoint(), problem_->CurrentStrategies());
     ILQG_CALL(ilqg_al_begin(h.get(), (int)params_.max_solver_iters, params_.constraint_error_tolerance));
     int active = 1;
-    while (active > 0 && elapsed() < max_runtime) {
+    bool first_solve = true;  // the reference always runs the first unconstrained solve, whatever max_runtime (:92)
+    while (active > 0 && (first_solve || elapsed() < max_runtime)) {
+      first_solve = false;
       ILQG_CALL(ilqg_solve_begin(h.get()));
       int running = 1;
       while (running > 0) {
@@ -636,9 +638,18 @@ class AugmentedLagrangianSolver : public GameSolver {
     }
     if (success) *success = h.Download<int32_t>(ILQG_AL_SUCCESS, 1)[0] != 0 && active == 0;
     num_iterates_ = h.Download<int32_t>(ILQG_AL_ITERATES, 1)[0];
-    // :192-207.  reset_problem: this solver never wrote into the Problem, so there is nothing to
-    // restore; the multipliers live in the handle.
-    if (params_.reset_lambdas || params_.reset_mu) ILQG_CALL(ilqg_reset(h.get(), ILQG_RESET_MULTIPLIERS));
+    // :192-207.  In the reference `initial_op` / `initial_strategies` are REFERENCES to the Problem's own
+    // members (:77-78), so its reset_problem restore copies the members onto themselves: whatever the loop
+    // last wrote with OverwriteSolution (:159-162) stays.  The device's warm start is exactly that state.
+    if (h.layout().num_constraints > 0) {
+      const size_t T = h.T(), n = h.n(), M = h.M();
+      problem_->OverwriteSolution(
+          h.OperatingPointOf(0, h.Download<float>(ILQG_WARM_XS, T * n), h.Download<float>(ILQG_WARM_US, T * M),
+                             problem_->CurrentOperatingPoint().t0),
+          h.StrategiesOf(0, h.Download<float>(ILQG_WARM_PS, T * M * n), h.Download<float>(ILQG_WARM_ALPHAS, T * M)));
+    }
+    const int mask = (params_.reset_lambdas ? ILQG_RESET_LAMBDAS : 0) | (params_.reset_mu ? ILQG_RESET_MU : 0);
+    if (mask) ILQG_CALL(ilqg_reset(h.get(), mask));
     return log;
   }
 

@@ -2362,10 +2362,8 @@ int ilqg_reset(ilqg_handle h, int mask) {
       in.last_merit = kInfinity;
       in.expected_decrease = kInfinity;
     }
-    if (mask & ILQG_RESET_MULTIPLIERS) {
-      std::fill(in.lambdas.begin(), in.lambdas.end(), (real)0);
-      in.mu = kDefaultMu;
-    }
+    if (mask & (ILQG_RESET_MULTIPLIERS | ILQG_RESET_LAMBDAS)) std::fill(in.lambdas.begin(), in.lambdas.end(), (real)0);
+    if (mask & (ILQG_RESET_MULTIPLIERS | ILQG_RESET_MU)) in.mu = kDefaultMu;
     if (mask & ILQG_RESET_SOLUTION) {
       for (auto* v : {&in.prob_xs, &in.prob_us, &in.prob_Ps, &in.prob_alphas, &in.xs, &in.us, &in.Ps,
                       &in.alphas})

@@ -786,3 +786,37 @@ def test_multi_device_handle_equals_single_device(product):
         h.close()
     for a, b in zip(*outs):
         np.testing.assert_array_equal(a, b)
+
+
+def test_standalone_lq_solve_with_nonzero_x0(product, oracle, oracle64):
+    """LQFeedbackSolver::Solve(lin, quad, x0 != 0) on a (16, 6, 3) handle (ADVICE r01): delta_xs start at
+    x0 and ExpectedDecrease includes the terms x0 drives -- the tensor-core sweep adds them to its
+    adjoint sum, the dense-record path takes the forward sweep."""
+    desc, _ = problems.three_player_intersection()
+    x0 = problems.three_player_intersection_x0_batch(8, 5)
+    lq_x0 = (0.05 * np.random.default_rng(3).normal(size=x0.shape)).astype(np.float32)
+    res = []
+    for lib in (product, oracle, oracle64):
+        h = abi.Handle(lib, desc, problems.three_player_intersection_params(), 8, 0)
+        h.upload_x0(x0)
+        h.solve_begin()
+        h.linearize_quadraticize()
+        h.upload(abi.LQ_X0, lq_x0)
+        h.lq_backward()
+        res.append((h.download(abi.DELTA_XS), h.download(abi.EXPECTED_DECREASE)))
+        h.close()
+    (dc, ec), (do, eo), (d64, e64) = res
+    good = wellposed(do, d64) & wellposed(eo, e64)
+    assert good.sum() >= 4
+    np.testing.assert_array_equal(dc[:, 0], lq_x0)
+    close(dc, do, tol=1e-3, rows=good, what="delta_xs", cond=row_distance(do, d64))
+    close(ec, eo, tol=1e-3, atol=1e-3, rows=good, what="expected decrease", cond=row_distance(eo, e64))
+    # the x0 terms are really there: with x0 = 0 the expected decrease is a different number
+    h = abi.Handle(product, desc, problems.three_player_intersection_params(), 8, 0)
+    h.upload_x0(x0)
+    h.solve_begin()
+    h.linearize_quadraticize()
+    h.lq_backward()
+    e0 = h.download(abi.EXPECTED_DECREASE)
+    h.close()
+    assert np.abs(e0[good] - ec[good]).max() > 1e-3 * np.abs(ec[good]).max()
