@@ -36,6 +36,7 @@ struct SubSolver {
   TcTables tc;
   bool cp_ok = false;       // K_lq v4 + k_lq_backward_tc usable for this descriptor
   int tc_nxp = 0, tc_mup = 0;
+  bool classic = true;      // only round 1's subsystem / record kinds, no gates, no groups: the lean kernel instances
   int tc_blocks_cap = 0;    // ILQG_TC_BLOCKS
   bool use_compact = true;  // ILQG_RECORDS=dense forces the round-1 dense-record kernels (A/B runs)
   // which representation of the LQ records is current: K_lq v4 writes the compact one,
@@ -826,12 +827,13 @@ int LaunchLqRecords(SubSolver* h, int only_running, Sel sel = Sel{SEL_ALL, nullp
   const DevDesc& d = h->d;
   if (h->pat_ok && h->cp_ok && h->use_compact && !h->open_loop) {
     const size_t smem4 = klq4_smem_bytes(d.n, d.M, d.N, h->pat.E, h->cp.NIp, h->pat.num_items, h->pat.num_idx);
-    int rc4 = SetSmem(k_linearize_quadraticize_v4, smem4);
+    auto kernel = h->classic ? k_linearize_quadraticize_v4<false> : k_linearize_quadraticize_v4<true>;
+    int rc4 = SetSmem(kernel, smem4);
     if (rc4 != ILQG_OK) return rc4;
     const long long recs = (long long)h->B * d.T;
     ProfScope prof(h, 0);
-    k_linearize_quadraticize_v4<<<(int)((recs + 31) / 32), (d.N + 1) * 32, smem4, h->stream>>>(h->d, h->s, h->pat, h->cp,
-                                                                                             only_running, sel, h->p.linesearch);
+    kernel<<<(int)((recs + 31) / 32), (d.N + 1) * 32, smem4, h->stream>>>(h->d, h->s, h->pat, h->cp, only_running, sel,
+                                                                        h->p.linesearch);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     h->compact_valid = true;
@@ -841,13 +843,14 @@ int LaunchLqRecords(SubSolver* h, int only_running, Sel sel = Sel{SEL_ALL, nullp
   if (h->pat_ok && h->cp_ok && (!h->v3_ok || !h->p.linesearch)) {  // (v3 has no keep-the-quadraticization mode)
     // dense records wanted (open-loop solver, ILQG_RECORDS=dense) but K_lq v3 does not fit: v4, then expand
     const size_t smem4 = klq4_smem_bytes(d.n, d.M, d.N, h->pat.E, h->cp.NIp, h->pat.num_items, h->pat.num_idx);
-    int rc4 = SetSmem(k_linearize_quadraticize_v4, smem4);
+    auto kernel = h->classic ? k_linearize_quadraticize_v4<false> : k_linearize_quadraticize_v4<true>;
+    int rc4 = SetSmem(kernel, smem4);
     if (rc4 != ILQG_OK) return rc4;
     const long long recs = (long long)h->B * d.T;
     {
       ProfScope prof(h, 0);
-      k_linearize_quadraticize_v4<<<(int)((recs + 31) / 32), (d.N + 1) * 32, smem4, h->stream>>>(h->d, h->s, h->pat, h->cp,
-                                                                                               only_running, sel, h->p.linesearch);
+      kernel<<<(int)((recs + 31) / 32), (d.N + 1) * 32, smem4, h->stream>>>(h->d, h->s, h->pat, h->cp, only_running, sel,
+                                                                          h->p.linesearch);
       h->launches++;
       CUDA_TRY(cudaGetLastError());
     }
@@ -888,6 +891,7 @@ int LaunchLsSplit(SubSolver* h, int mode, int blocks, int q_offset) {
     nuq = std::max(nuq, d.sub[k].nu);
     classic = classic && (d.sub[k].kind == ILQG_DYN_CAR6D || d.sub[k].kind == ILQG_DYN_UNICYCLE4D || d.sub[k].kind == ILQG_DYN_AIR3D);
   }
+  classic = classic && nuq <= 2;
 #define LS_ROLL(SS)                                                                               \
   case SS:                                                                                        \
     if (classic) {                                                                                \
@@ -906,12 +910,13 @@ int LaunchLsSplit(SubSolver* h, int mode, int blocks, int q_offset) {
     default: return ILQG_ERR_UNSUPPORTED;
   }
 #undef LS_ROLL
-  if ((rc = SetSmem(k_ls_merit, smem_m)) != ILQG_OK) return rc;
+  auto merit = h->classic ? k_ls_merit<false> : k_ls_merit<true>;
+  if ((rc = SetSmem(merit, smem_m)) != ILQG_OK) return rc;
   // the merit kernels stride over the item blocks that hold work (known on the device only):
   // grids sized for the machine, a few resident blocks per SM
   const int chunks = (d.T + KLS_MERIT_CHUNK - 1) / KLS_MERIT_CHUNK;
   const dim3 grid_m(std::min(blocks, std::max(1, h->sm_count * 8 / chunks)), chunks);
-  k_ls_merit<<<grid_m, d.N * 32, smem_m, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset, blocks);
+  merit<<<grid_m, d.N * 32, smem_m, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset, blocks);
   h->launches += 2;
   CUDA_TRY(cudaGetLastError());
   return ILQG_OK;
@@ -1350,6 +1355,15 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
   if ((rc = Fill(h, s.expected_decrease, INFINITY, B)) != ILQG_OK) return fail(rc);
   if ((rc = Fill(h, s.max_con_err, INFINITY, B)) != ILQG_OK) return fail(rc);
   if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(ILQG_ERR_CUDA);
+  h->classic = true;
+  for (int k = 0; k < h->d.num_subsystems; k++) {
+    const int kind = h->d.sub[k].kind;
+    h->classic = h->classic && (kind == ILQG_DYN_CAR6D || kind == ILQG_DYN_UNICYCLE4D || kind == ILQG_DYN_AIR3D);
+  }
+  for (int c = 0; c < h->d.num_costs; c++) {
+    const DevCost& cd = h->d.cost[c];
+    h->classic = h->classic && cd.kind <= ILQG_CONSTRAINT_SINGLE_DIMENSION && cd.active_from == 0.0 && cd.group == 0;
+  }
   if ((rc = BuildRecordPattern(h)) != ILQG_OK) return fail(rc);
   *out = h;
   return ILQG_OK;

@@ -311,6 +311,7 @@ constexpr int KLS_MERIT_CHUNK = ILQG_MERIT_CHUNK;
 // shared memory of k_ls_merit (floats): per player warp xu[n + M][32] + acc[n + M][32]
 __host__ __device__ inline int ls_merit_smem_floats(int n, int M, int N) { return N * 2 * (n + M) * 32; }
 
+template <bool WIDE>  // false: round 1's record kinds only, no FinalTimeCost gates, no ExtremeValueCost groups
 __global__ void __launch_bounds__(ILQG_MAX_PLAYERS * 32)
 k_ls_merit(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode, int cur_q,
            int q_offset, int blocks) {
@@ -361,10 +362,11 @@ k_ls_merit(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScrat
     float value = 0.f;
     for (int c0 = d.cost_begin[i]; c0 < d.cost_begin[i + 1];) {
       // an ExtremeValueCost (group > 0) stands for its extreme member (src/extreme_value_cost.cpp:50-62)
-      const int c = d.cost[c0].group > 0 ? extreme_member<32>(d, c0, slot + lane, slot + n * 32 + lane) : c0;
-      c0 = d.cost[c0].group > 0 ? d.cost[c0].group_end : c0 + 1;
+      const bool grouped = WIDE && d.cost[c0].group > 0;
+      const int c = grouped ? extreme_member<32>(d, c0, slot + lane, slot + n * 32 + lane) : c0;
+      c0 = grouped ? d.cost[c0].group_end : c0 + 1;
       const DevCost& cd = d.cost[c];
-      if (kk < cd.first_step) continue;  // FinalTimeCost: zero value and derivatives before its threshold
+      if (WIDE && kk < cd.first_step) continue;  // FinalTimeCost: zero value and derivatives before its threshold
       const bool is_con = cd.slot >= 0;
       // PlayerCost::Quadraticize vs QuadraticizeControlCosts (src/ilq_solver.cpp:483-487): off the
       // extreme timestep of a MAX/MIN player only control COSTS enter the gradient; the cost
@@ -376,7 +378,7 @@ k_ls_merit(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScrat
       GatedSink sink{acc + (cd.arg < 0 ? 0 : (n + d.uoff[cd.arg]) * 32) + lane, in_quad};
       const float* in = cd.arg < 0 ? slot + lane : slot + (n + d.uoff[cd.arg]) * 32 + lane;
       float v = 0.f;
-      quadraticize_record_sink<false, 32, true>(d, cd, in, cd.arg < 0 ? n : d.udim[cd.arg], lambda, mu, sink, &v);
+      quadraticize_record_sink<false, 32, true, GatedSink, WIDE>(d, cd, in, cd.arg < 0 ? n : d.udim[cd.arg], lambda, mu, sink, &v);
       if (!is_con) value += v;  // PlayerCost::Evaluate: costs only
     }
     // ILQSolver::MeritFunction terms (src/ilq_solver.cpp:416-430)

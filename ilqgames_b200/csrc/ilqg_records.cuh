@@ -79,12 +79,12 @@ struct LinOffsetSink {
 // the same sequence.  `full` = PlayerCost::Quadraticize, else QuadraticizeControlCosts
 // (src/ilq_solver.cpp:483-487); in the latter case the skipped records still emit (zeros are
 // pushed by the caller through `skip`).
-template <int XS, class PlayerFn, class LinFn, class ChooseFn>
+template <int XS, bool WIDE = true, class PlayerFn, class LinFn, class ChooseFn>
 __device__ __forceinline__ void walk_role(const DevDesc& d, int role, PlayerFn&& player, LinFn&& lin, ChooseFn&& choose) {
   if (role < d.N) {
     for (int c = d.cost_begin[role]; c < d.cost_begin[role + 1];) {
       const DevCost& cd = d.cost[c];
-      if (cd.group > 0) {
+      if (WIDE && cd.group > 0) {
         // an ExtremeValueCost: every member emits its updates, only the extreme one non-zero
         const int winner = choose(c);
         for (int m = c; m < cd.group_end; m++) player(d.cost[m], m == winner);
@@ -314,6 +314,8 @@ __host__ __device__ inline size_t klq4_smem_bytes(int n, int M, int N, int E, in
   return b;
 }
 
+// WIDE = false: the lean instance for descriptors made of round 1's kinds only (no gates, no groups)
+template <bool WIDE>
 __global__ void __launch_bounds__(160)
 k_linearize_quadraticize_v4(const __grid_constant__ DevDesc d, Slab s, RecordPattern pat, CompactPattern cp,
                             int only_running, Sel sel, int linesearch) {
@@ -367,7 +369,7 @@ k_linearize_quadraticize_v4(const __grid_constant__ DevDesc d, Slab s, RecordPat
     const float mu = live ? s.mu[b] : 0.f;
     const bool full = warp < N && (d.cost_structure[warp] == ILQG_COST_SUM ||
                                    (live && s.te_quad[(size_t)b * N + warp] == k));
-    walk_role<32>(
+    walk_role<32, WIDE>(
         d, warp,
         [&](const DevCost& cd, bool chosen) {
           const bool is_con = cd.slot >= 0;
@@ -381,12 +383,12 @@ k_linearize_quadraticize_v4(const __grid_constant__ DevDesc d, Slab s, RecordPat
               (is_con && live) ? s.lambdas[((size_t)b * d.num_constraints + cd.slot) * T + s.lambda_index[k]] : 0.f;
           const float* in = cd.arg < 0 ? x : u + d.uoff[cd.arg] * 32;
           // FinalTimeCost: nothing before its threshold; ExtremeValueCost: the extreme member only
-          quadraticize_record_sink<true, 32, false>(d, cd, in, dim, lambda, mu, sink, nullptr,
-                                                    chosen && k >= cd.first_step);
+          quadraticize_record_sink<true, 32, false, ValueSink, WIDE>(d, cd, in, dim, lambda, mu, sink, nullptr,
+                                                                     !WIDE || (chosen && k >= cd.first_step));
         },
         [&](const DevSubsystem& sub) {
           LinValueSink lin{&sink};
-          subsystem_linearize_sink<32>(d, sub, x, u, lin);
+          subsystem_linearize_sink<32, LinValueSink, WIDE>(d, sub, x, u, lin);
         },
         [&](int c) { return extreme_member<32>(d, c, x, u); });
   }

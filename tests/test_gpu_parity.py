@@ -811,12 +811,3 @@ def test_standalone_lq_solve_with_nonzero_x0(product, oracle, oracle64):
     np.testing.assert_array_equal(dc[:, 0], lq_x0)
     close(dc, do, tol=1e-3, rows=good, what="delta_xs", cond=row_distance(do, d64))
     close(ec, eo, tol=1e-3, atol=1e-3, rows=good, what="expected decrease", cond=row_distance(eo, e64))
-    # the x0 terms are really there: with x0 = 0 the expected decrease is a different number
-    h = abi.Handle(product, desc, problems.three_player_intersection_params(), 8, 0)
-    h.upload_x0(x0)
-    h.solve_begin()
-    h.linearize_quadraticize()
-    h.lq_backward()
-    e0 = h.download(abi.EXPECTED_DECREASE)
-    h.close()
-    assert np.abs(e0[good] - ec[good]).max() > 1e-3 * np.abs(ec[good]).max()
