@@ -37,6 +37,7 @@ struct SubSolver {
   bool cp_ok = false;       // K_lq v4 + k_lq_backward_tc usable for this descriptor
   int tc_nxp = 0, tc_mup = 0;
   bool classic = true;      // only round 1's subsystem / record kinds, no gates, no groups: the lean kernel instances
+  bool rollout_sp = true;   // ILQG_ROLLOUT=lanes selects round 1's lane-per-item rollout (A/B runs, the bit-identity test)
   int tc_blocks_cap = 0;    // ILQG_TC_BLOCKS
   bool use_compact = true;  // ILQG_RECORDS=dense forces the round-1 dense-record kernels (A/B runs)
   // which representation of the LQ records is current: K_lq v4 writes the compact one,
@@ -892,6 +893,19 @@ int LaunchLsSplit(SubSolver* h, int mode, int blocks, int q_offset) {
     classic = classic && (d.sub[k].kind == ILQG_DYN_CAR6D || d.sub[k].kind == ILQG_DYN_UNICYCLE4D || d.sub[k].kind == ILQG_DYN_AIR3D);
   }
   classic = classic && nuq <= 2;
+  if (h->rollout_sp) {
+    // the stage-parallel rollout: 4 items per block, a grid-stride loop over the item blocks in use
+    const long long nblk = ((long long)blocks * h->ls.lpw + RSP_ITEMS - 1) / RSP_ITEMS;
+    const int grid = (int)std::min<long long>(nblk, (long long)h->sm_count * 16);
+#define LS_SP(NUQ_, WIDE_, N4_) \
+  k_ls_rollout_sp<NUQ_, WIDE_, N4_><<<grid, S * 32, 0, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset, blocks)
+    if (classic && d.n == 16) LS_SP(2, false, 4);
+    else if (classic && d.n == 24) LS_SP(2, false, 6);
+    else if (classic) LS_SP(2, false, 0);
+    else if (nuq <= 2) LS_SP(2, true, 0);
+    else LS_SP(4, true, 0);
+#undef LS_SP
+  } else {
 #define LS_ROLL(SS)                                                                               \
   case SS:                                                                                        \
     if (classic) {                                                                                \
@@ -910,6 +924,7 @@ int LaunchLsSplit(SubSolver* h, int mode, int blocks, int q_offset) {
     default: return ILQG_ERR_UNSUPPORTED;
   }
 #undef LS_ROLL
+  }
   auto merit = h->classic ? k_ls_merit<false> : k_ls_merit<true>;
   if ((rc = SetSmem(merit, smem_m)) != ILQG_OK) return rc;
   // the merit kernels stride over the item blocks that hold work (known on the device only):
@@ -1318,6 +1333,7 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
     // (profiles/r01_schedule_experiments.md)
     h->pipeline = 2;
     if (const char* e = std::getenv("ILQG_PIPELINE")) h->pipeline = std::atoi(e);
+    if (const char* e = std::getenv("ILQG_ROLLOUT")) h->rollout_sp = std::strcmp(e, "lanes") != 0;
     ls.JA = JA;
     ls.JB = JB;
     ls.cap = cap;

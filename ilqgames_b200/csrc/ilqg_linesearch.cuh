@@ -294,6 +294,169 @@ k_ls_rollout(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScr
   }
 }
 
+// ---------------------------------------------------------------------------
+// The stage-parallel rollout (round 2): the same trajectories, bit for bit, from a different
+// decomposition.  k_ls_rollout above gives one lane a whole (item, subsystem): ~1,400 dependent
+// warp instructions per time step on a warp that is alone on its scheduler -- 3.9 us per step,
+// 0.39 ms for the first window of the benchmark with the chip 95 % idle (profiles/r02d).  Here
+// eight lanes share one (item, subsystem): one lane per RK4 stage of the two substeps
+// (subsystem_integrate_sp, ilqg_device.cuh), one lane per control row for u = u_ref - P dx - alpha,
+// one lane per state component for dx and the stores.  A warp is (subsystem, 4 items); a block is
+// the S subsystem warps of those 4 items, exchanging dx through a double-buffered shared tile
+// with one barrier per step as before.  Feedback rows ride in registers, loaded one step ahead.
+// ---------------------------------------------------------------------------
+constexpr int RSP_ITEMS = 4;       // items per block (eight lanes each in every subsystem warp)
+constexpr int RSP_DX_STRIDE = 28;  // floats per item row of the dx tile: n <= 24, and 28 g mod 32 keeps the four
+                                   // items' 128-bit reads on distinct banks
+
+// N4T: n / 4 known at compile time (n = 4 N4T: the feedback row is N4T 128-bit loads, the dot product
+// an unrolled chain), or 0 for any n at run time.
+template <int NUQ, bool WIDE, int N4T>
+__global__ void __launch_bounds__(ILQG_MAX_SUBSYSTEMS * 32, 6)
+k_ls_rollout_sp(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode, int cur_q,
+                int q_offset, int blocks /* item blocks of ls.lpw items the window spans */) {
+  __shared__ __align__(16) float dxs2[2][RSP_ITEMS][RSP_DX_STRIDE];
+  __shared__ int absf[ILQG_MAX_SUBSYSTEMS][RSP_ITEMS];
+  const unsigned full = 0xffffffffu;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 3, t = lane & 7;  // item of the block, stage slot / component / control row
+  const int n = N4T ? 4 * N4T : d.n, M = d.M, T = d.T, S = d.num_subsystems;
+  for (int e = threadIdx.x; e < 2 * RSP_ITEMS * RSP_DX_STRIDE; e += blockDim.x) (&dxs2[0][0][0])[e] = 0.f;
+  long long total_items = (long long)blocks * ls.lpw;
+  if (mode == LS_MODE_QUEUED) {
+    const int live = min(max(ls.counts[cur_q] - q_offset, 0), ls.cap);
+    total_items = min(total_items, (long long)live * ls.JB);
+  }
+  const int nblk = (int)((total_items + RSP_ITEMS - 1) / RSP_ITEMS);
+  const float s0 = p.initial_alpha_scaling, rho = p.geometric_alpha_scaling;
+  const float dt_half = (float)(d.time_step / 2.0);
+  int rho_e;
+  const bool rho_exact = fabsf(frexpf(rho, &rho_e)) == 0.5f;  // (see k_ls_rollout)
+  // the subsystem's constants in registers: the loop below is a latency chain, and an indexed read
+  // of the descriptor (constant bank, register offset) costs more than the arithmetic around it
+  const int kind = d.sub[warp].kind, xoff = d.sub[warp].x_offset, nu = d.sub[warp].nu;
+  const float sp0 = d.sub[warp].p0, sp1 = d.sub[warp].p1;
+  const int xd = subsystem_xdim(kind);
+  const bool vecP = N4T || (n & 3) == 0;
+  const int n4 = N4T ? N4T : (n + 3) >> 2;
+  constexpr int NV = N4T ? N4T : ILQG_MAX_XDIM / 4;
+
+  for (int ib = blockIdx.x; ib < nblk; ib += gridDim.x) {
+    const int item = ib * RSP_ITEMS + g;
+    const LsItem it = ls_decode(p, s, ls, mode, cur_q, q_offset, item / ls.lpw, item % ls.lpw);
+    if (!__syncthreads_or(it.valid)) continue;  // (also fences the tiles against the previous trip)
+    const bool valid = it.valid;
+    const LsIo io = ls_io(s, ls, mode, it, item, T, n, M);
+    float rho_j = 1.0f;
+    for (int jj = 0; jj < it.j; jj++) rho_j *= rho;
+    const bool scaled = io.scaled;
+    const bool rowlane = valid && t < nu && t < NUQ;  // this lane evaluates control row t of the subsystem
+    const int c = rowlane ? d.sub[warp].ucol[t & 3] : 0;
+    const bool complane = valid && t < xd;            // ... and owns state component t
+    float x[6];
+#pragma unroll
+    for (int a = 0; a < 6; a++) x[a] = (valid && a < xd) ? io.x_start[xoff + a] : 0.f;
+    // running pointers (advanced by one time step per trip)
+    const float* ref_p = io.last_xs + xoff + t;
+    float* outx_p = io.out_xs + xoff + t;
+    const float* uref_p = io.last_us + c;
+    const float* al_p = io.alpha + c;
+    const float* P_p = io.P + (size_t)c * n;
+    float* outu_p = io.out_us + c;
+    float* dx_w = &dxs2[0][g][xoff + t];
+    const float* dx_r = &dxs2[0][g][0];
+    const int dx_flip = RSP_ITEMS * RSP_DX_STRIDE;
+    // values of the step ahead: the reference state component and control row this lane owns
+    float ref = complane ? io.x_start[xoff + t] : 0.f;  // last_operating_point.xs[0] is the start state
+    float uref = 0.f, al = 0.f;
+    float pr[4 * NV];
+#pragma unroll
+    for (int a = 0; a < 4 * NV; a++) pr[a] = 0.f;
+    auto fetch_row = [&]() __attribute__((always_inline)) {
+      if (rowlane) {
+        uref = *uref_p;
+        al = *al_p;
+        if (vecP) {
+#pragma unroll
+          for (int a4 = 0; a4 < NV; a4++)
+            if (N4T || a4 < n4) {
+              const float4 v = __ldg(reinterpret_cast<const float4*>(P_p) + a4);
+              pr[4 * a4] = v.x; pr[4 * a4 + 1] = v.y; pr[4 * a4 + 2] = v.z; pr[4 * a4 + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+          for (int a = 0; a < 4 * NV; a++)
+            if (a < n) pr[a] = __ldg(P_p + a);
+        }
+      }
+      uref_p += M;
+      al_p += M;
+      P_p += (size_t)M * n;
+    };
+    fetch_row();
+    bool absorbed = true;
+    for (int k = 0; k < T; k++) {
+      {  // one lane per state component: dx into the tile, x_k into the trajectory
+        const float x01 = (t & 1) ? x[1] : x[0], x23 = (t & 1) ? x[3] : x[2], x45 = (t & 1) ? x[5] : x[4];
+        const float xa = (t & 4) ? x45 : ((t & 2) ? x23 : x01);
+        if (t < xd) *dx_w = xa - ref;
+        if (complane) *outx_p = xa;
+        outx_p += n;
+      }
+      if (S > 1) __syncthreads();
+      else __syncwarp();
+      float acc = 0.f;
+#pragma unroll
+      for (int a4 = 0; a4 < NV; a4++)
+        if (N4T || a4 < n4) {
+          const float4 dv = *reinterpret_cast<const float4*>(dx_r + 4 * a4);
+          acc = fmaf(pr[4 * a4], dv.x, acc);
+          if (N4T || 4 * a4 + 1 < n) acc = fmaf(pr[4 * a4 + 1], dv.y, acc);
+          if (N4T || 4 * a4 + 2 < n) acc = fmaf(pr[4 * a4 + 2], dv.z, acc);
+          if (N4T || 4 * a4 + 3 < n) acc = fmaf(pr[4 * a4 + 3], dv.w, acc);
+        }
+      float alv = al;
+      if (scaled) {
+        alv *= s0;  // ScaleAlphas(initial_alpha_scaling), then geometric_alpha_scaling^j
+        if (rho_exact) {
+          alv *= rho_j;
+        } else {
+#pragma unroll 1
+          for (int jj = 0; jj < it.j; jj++) alv *= rho;
+        }
+      }
+      const float tt = uref - acc;
+      const float uv = tt - alv;  // Strategy::operator(), strategy.h:73-76
+      if (rowlane) {
+        absorbed = absorbed && (uv == tt);
+        *outu_p = uv;
+      }
+      outu_p += M;
+      dx_w += (k & 1) ? -dx_flip : dx_flip;
+      dx_r += (k & 1) ? -dx_flip : dx_flip;
+      if (k + 1 < T) {
+        ref_p += n;
+        if (complane) ref = *ref_p;
+        fetch_row();
+      }
+      float uu[4] = {0.f, 0.f, 0.f, 0.f};
+      const float umine = rowlane ? uv : 0.f;
+#pragma unroll
+      for (int qq = 0; qq < NUQ; qq++) uu[qq] = __shfl_sync(full, umine, (lane & 24) | qq);
+      if (k < T - 1) subsystem_integrate_sp<WIDE>(kind, sp0, sp1, dt_half, x, uu, lane);
+    }
+    // (see k_ls_rollout: a candidate whose alpha terms all vanished in rounding repeats for every deeper j)
+    const unsigned live_rows = __ballot_sync(full, !absorbed);
+    if (t == 0) absf[warp][g] = ((live_rows >> (8 * g)) & 0xffu) == 0u;
+    __syncthreads();
+    if (warp == 0 && t == 0 && valid) {
+      bool all_absorbed = true;
+      for (int w2 = 0; w2 < S; w2++) all_absorbed = all_absorbed && absf[w2][g] != 0;
+      ls.absorbed[item] = all_absorbed ? 1 : 0;
+    }
+  }
+}
+
 // Item blocks of a window launch that can hold valid items.  A queued window is launched for `cap`
 // queue slots without the host knowing how many are filled; the filled ones are a prefix.
 __device__ __forceinline__ int ls_live_blocks(const LsScratch& ls, int mode, int cur_q, int q_offset, int blocks) {

@@ -811,3 +811,39 @@ def test_standalone_lq_solve_with_nonzero_x0(product, oracle, oracle64):
     np.testing.assert_array_equal(dc[:, 0], lq_x0)
     close(dc, do, tol=1e-3, rows=good, what="delta_xs", cond=row_distance(do, d64))
     close(ec, eo, tol=1e-3, atol=1e-3, rows=good, what="expected decrease", cond=row_distance(eo, e64))
+
+
+# ------------------------------------------------------------------ the two rollout kernels
+ROLLOUT_CASES = [("three_player_intersection", 100, 67, 4), ("roundabout_merging", 150, 21, 3), ("air_3d", 50, 64, 4),
+                 ("three_player_overtaking", 100, 9, 2), ("two_player_reachability", 100, 8, 2),
+                 ("dubins_origin", 100, 8, 2), ("modified_air_3d", 100, 8, 2),
+                 ("two_player_collision_avoidance_reachability", 100, 8, 2)]
+
+
+@pytest.mark.parametrize("name,T,batch,iters", ROLLOUT_CASES)
+def test_rollout_kernels_bit_identical(product, name, T, batch, iters):
+    """The stage-parallel rollout (k_ls_rollout_sp: eight lanes per (item, subsystem), one per RK4
+    stage) performs the floating-point operations of the lane-per-item rollout (k_ls_rollout,
+    ILQG_ROLLOUT=lanes) on the same operands: whole solves -- every trajectory, strategy, merit,
+    Armijo decision and counter -- are bit-identical, for every subsystem kind."""
+    build, params, x0f = CONFIGS[name]
+    desc, _ = build(num_time_steps=T) if name in HEADLINE + ["three_player_overtaking"] else build()
+    x0 = x0f(batch)
+    outs = []
+    for kernel in ("lanes", "sp"):
+        os.environ["ILQG_ROLLOUT"] = kernel
+        try:
+            h = abi.Handle(product, desc, params(max_solver_iters=iters, disable_convergence_exit=1), x0.shape[0], 0)
+        finally:
+            del os.environ["ILQG_ROLLOUT"]
+        h.upload_x0(x0)
+        h.solve_begin()
+        first = [h.download(w) for w in (abi.XS, abi.US, abi.MERIT)]
+        h.solve(chunk=iters)
+        outs.append(first + [h.download(w) for w in (abi.XS, abi.US, abi.PS, abi.ALPHAS, abi.MERIT, abi.STATUS, abi.ITERS,
+                                                    abi.BACKTRACKS, abi.TOTAL_COSTS, abi.STEP)])
+        h.close()
+    for a, b in zip(*outs):
+        np.testing.assert_array_equal(a, b)
+    report(f"rollout_bit_identical[{name},T={T}]", batch=x0.shape[0], iterations=iters,
+           backtracks=int(outs[0][-3].sum()))
