@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <string>
 #include <vector>
 
 #include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges around every launch site
@@ -37,6 +38,12 @@ struct SubSolver {
   bool cp_ok = false;       // K_lq v4 + k_lq_backward_tc usable for this descriptor
   int tc_nxp = 0, tc_mup = 0;
   bool classic = true;      // only round 1's subsystem / record kinds, no gates, no groups: the lean kernel instances
+  // ILQG_TRACE=<file>: a device timeline -- a one-thread kernel stamps %globaltimer after every launch site, in
+  // stream order; written to <file> when the handle is destroyed (development aid, off by default)
+  unsigned long long* trace = nullptr;
+  int trace_n = 0, trace_cap = 0;
+  std::vector<int> trace_tags;
+  std::string trace_path;
   bool rollout_sp = true;   // ILQG_ROLLOUT=lanes selects round 1's lane-per-item rollout (A/B runs, the bit-identity test)
   int tc_blocks_cap = 0;    // ILQG_TC_BLOCKS
   bool use_compact = true;  // ILQG_RECORDS=dense forces the round-1 dense-record kernels (A/B runs)
@@ -44,7 +51,8 @@ struct SubSolver {
   // ilqg_upload_lq / K_lq v3 the dense one; EnsureDense expands compact -> dense on demand
   bool compact_valid = false, dense_valid = false;
   int ls_blocks_max;
-  int ls_cur;  // which open-linesearch queue the next pass consumes
+  int ls_cur;  // the open-linesearch queue the next continued window consumes (ilqg_linesearch.cuh: LsScratch::pend)
+  std::vector<int> ls_tiers;  // candidates per continued window, in order (sum = max_backtracking_steps - JA)
   int device;
   int B;
   cudaStream_t stream;      // the stream work is issued on
@@ -366,6 +374,18 @@ struct NvtxRange {  // the launch sites outside the hot loop
   explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
   ~NvtxRange() { nvtxRangePop(); }
 };
+
+__global__ void k_stamp(unsigned long long* slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *slot = t;
+}
+// timeline stamp after a launch site (tag: site * 10 + 0 main / 1 side stream)
+inline void Stamp(SubSolver* h, int site) {
+  if (!h->trace || h->trace_n >= h->trace_cap) return;
+  k_stamp<<<1, 1, 0, h->stream>>>(h->trace + h->trace_n++);
+  h->trace_tags.push_back(site * 10 + (h->stream == h->side ? 1 : 0));
+}
 
 struct ProfScope {  // brackets one launch site: an NVTX range always, CUDA events when profiling is on
   SubSolver* h;
@@ -925,6 +945,7 @@ int LaunchLsSplit(SubSolver* h, int mode, int blocks, int q_offset) {
   }
 #undef LS_ROLL
   }
+  Stamp(h, 3 + mode * 10);  // rollout done
   auto merit = h->classic ? k_ls_merit<false> : k_ls_merit<true>;
   if ((rc = SetSmem(merit, smem_m)) != ILQG_OK) return rc;
   // the merit kernels stride over the item blocks that hold work (known on the device only):
@@ -932,6 +953,7 @@ int LaunchLsSplit(SubSolver* h, int mode, int blocks, int q_offset) {
   const int chunks = (d.T + KLS_MERIT_CHUNK - 1) / KLS_MERIT_CHUNK;
   const dim3 grid_m(std::min(blocks, std::max(1, h->sm_count * 8 / chunks)), chunks);
   merit<<<grid_m, d.N * 32, smem_m, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset, blocks);
+  Stamp(h, 4 + mode * 10);  // merit done
   h->launches += 2;
   CUDA_TRY(cudaGetLastError());
   return ILQG_OK;
@@ -951,14 +973,15 @@ int LaunchLinesearchFresh(SubSolver* h) {
   const int B = h->B;
   int rc;
   const int dec_blocks = (B + KDEC_WARPS - 1) / KDEC_WARPS;
-  CUDA_TRY(cudaMemsetAsync(h->ls.counts + (1 - h->ls_cur), 0, sizeof(int), h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->ls.counts, 0, sizeof(int), h->stream));
+  h->ls_cur = 0;
   if ((rc = LaunchLsEval(h, LS_MODE_FRESH, h->ls.nA_blocks, 0)) != ILQG_OK) return rc;
   {
     ProfScope pd(h, 6);
-    k_ls_decide<<<dec_blocks, KDEC_WARPS * 32, 0, h->stream>>>(h->d, h->p, h->s, h->ls, LS_MODE_FRESH, h->ls_cur, 0);
+    k_ls_decide<<<dec_blocks, KDEC_WARPS * 32, 0, h->stream>>>(h->d, h->p, h->s, h->ls, LS_MODE_FRESH, 0, 0, 0);
   }
+  Stamp(h, 15);  // first-window decide done
   h->launches++;
-  h->ls_cur = 1 - h->ls_cur;  // the queue just filled is now the one to drain
   CUDA_TRY(cudaGetLastError());
   return ILQG_OK;
 }
@@ -969,23 +992,31 @@ int LaunchLinesearchQueued(SubSolver* h) {
   int rc;
   if (h->p.linesearch && h->ls.JB > 0) {
     const int cap = h->ls.cap;
-    const int qblocks = (int)(((long long)cap * h->ls.JB + h->ls.lpw - 1) / h->ls.lpw);
-    const int remaining = std::max(1, h->p.max_backtracking_steps) - h->ls.JA;
-    // instances whose window ended without an accept AND whose last rollout was not "absorbed"
-    // (ilqg_linesearch.cuh) move on to the other queue
-    for (int done = 0; done < remaining; done += h->ls.JB) {
-      CUDA_TRY(cudaMemsetAsync(h->ls.counts + (1 - h->ls_cur), 0, sizeof(int), h->stream));
+    const int widest = h->ls.JB;
+    // Tier after tier (ilqg_linesearch.cuh): a tier evaluates its candidates for every game still in
+    // the queue; games whose tier ended without an accept AND whose last rollout was not "absorbed"
+    // are handed on to the next tier's queue.  Launches over an empty queue exit at once.
+    for (int jb : h->ls_tiers) {
+      const int dst = h->ls_cur == 1 ? 2 : 1;
+      h->ls.JB = jb;  // (kernel arguments are copied at launch)
+      const int qblocks = (int)(((long long)cap * jb + h->ls.lpw - 1) / h->ls.lpw);
+      CUDA_TRY(cudaMemsetAsync(h->ls.counts + dst, 0, sizeof(int), h->stream));
       for (int q0 = 0; q0 < B; q0 += cap) {
-        if ((rc = LaunchLsEval(h, LS_MODE_QUEUED, qblocks, q0)) != ILQG_OK) return rc;
+        if ((rc = LaunchLsEval(h, LS_MODE_QUEUED, qblocks, q0)) != ILQG_OK) {
+          h->ls.JB = widest;
+          return rc;
+        }
         {
           ProfScope pd(h, 6);
           k_ls_decide<<<(cap + KDEC_WARPS - 1) / KDEC_WARPS, KDEC_WARPS * 32, 0, h->stream>>>(
-              h->d, h->p, h->s, h->ls, LS_MODE_QUEUED, h->ls_cur, q0);
+              h->d, h->p, h->s, h->ls, LS_MODE_QUEUED, h->ls_cur, q0, dst);
         }
+        Stamp(h, 25);  // tier decide done
         h->launches++;
       }
-      h->ls_cur = 1 - h->ls_cur;
+      h->ls_cur = dst;
     }
+    h->ls.JB = widest;
   }
   CUDA_TRY(cudaGetLastError());
   return ILQG_OK;
@@ -1008,13 +1039,16 @@ int PipelinedStep(SubSolver* h, int it, int n) {
   const Sel sel = it > 0 ? Sel{SEL_MAIN, nullptr, nullptr} : all;
   const bool bwd_on_side = h->pipeline == 1;
   if (it == 0 && h->stagger_wait) CUDA_TRY(cudaStreamWaitEvent(main, h->stagger_wait, 0));
+  Stamp(h, 0);  // pass begins
   if ((rc = LaunchLqRecords(h, 1, sel)) != ILQG_OK) return rc;
+  Stamp(h, 1);  // K_lq done
   if (!bwd_on_side && h->side_busy) CUDA_TRY(cudaStreamWaitEvent(main, h->ev_side, 0));
   if ((rc = DispatchBackward(h, 1, false, bwd_on_side ? sel : all)) != ILQG_OK) return rc;
+  Stamp(h, 2);  // K_bwd done
   if (it == 0 && h->stagger_signal) CUDA_TRY(cudaEventRecord(h->stagger_signal, main));
   if (bwd_on_side && h->side_busy) CUDA_TRY(cudaStreamWaitEvent(main, h->ev_side, 0));
   if ((rc = LaunchLinesearchFresh(h)) != ILQG_OK) return rc;
-  const int q_first = h->ls_cur;  // the queue the first window just filled
+  const int q_first = 0;  // the queue the first window just filled (left intact by the tiers)
   CUDA_TRY(cudaEventRecord(h->ev_fresh, main));
   CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_fresh, 0));
   h->stream = h->side;
@@ -1022,6 +1056,7 @@ int PipelinedStep(SubSolver* h, int it, int n) {
   if (rc == ILQG_OK && it + 1 < n) {
     const Sel list{SEL_LIST, h->ls.pend[q_first], h->ls.counts + q_first};
     rc = LaunchLqRecords(h, 1, list);
+    Stamp(h, 6);  // K_lq over the queue list done
     if (rc == ILQG_OK && h->pipeline == 1) rc = DispatchBackward(h, 1, false, list);
   }
   h->stream = main;
@@ -1053,14 +1088,13 @@ int IteratePipelined(SubSolver* h, int n) {
 // single queued window; per-kernel profiling wants every kernel alone on the device
 bool CanPipeline(const SubSolver* h, int max_iters) {
   const bool hw = h->dims_key == 0 || h->dims_key == 1 || (h->cp_ok && h->use_compact);
-  const bool one_window = h->ls.JB >= std::max(1, h->p.max_backtracking_steps) - h->ls.JA;
-  return h->pipeline && !h->open_loop && max_iters > 1 && h->pat_ok && hw && one_window && h->p.linesearch && !h->profiling;
+  return h->pipeline && !h->open_loop && max_iters > 1 && h->pat_ok && hw && h->p.linesearch && !h->profiling;
 }
 
 int LaunchSolveBegin(SubSolver* h) {
   int rc;
   ProfScope prof(h, 3);
-  CUDA_TRY(cudaMemsetAsync(h->ls.counts, 0, 2 * sizeof(int), h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->ls.counts, 0, 3 * sizeof(int), h->stream));
   h->ls_cur = 0;
   rc = LaunchLsEval(h, LS_MODE_BEGIN, (h->B + h->ls.lpw - 1) / h->ls.lpw, 0);
   if (rc == ILQG_OK) {
@@ -1322,8 +1356,38 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
     // continued linesearches go on in windows of JB candidates; by default one window covers every
     // remaining candidate (measured best: a second window costs a full rollout latency, and the
     // "absorbed" shortcut of k_ls_decide rarely triggers before j ~ 40)
-    int JB = max_bt - JA;
-    if (const char* e = std::getenv("ILQG_LS_JB")) JB = std::max(0, std::min(max_bt - JA, std::atoi(e)));
+    // Tiers of the continued linesearch (round 2): by default candidates JA .. JA + 38, then the rest.
+    // Measured with the oracle on the three headline problems: a linesearch that rejects j = 0
+    // either accepts by j ~ 36 or fails, and by then alpha * s0 * rho^j has vanished in rounding
+    // (the "absorbed" shortcut of k_ls_decide), so the second tier almost never has work -- the
+    // first tier is 2.5 x narrower than one window over all candidates.  ILQG_LS_TIERS="7,32"
+    // gives tiers of 7, 32 and the remainder; ILQG_LS_JB=n is round 1's equal windows of n.
+    std::vector<int> tiers;
+    {
+      const int remaining = max_bt - JA;
+      const char* e = std::getenv("ILQG_LS_TIERS");
+      std::string spec = e ? e : "39";
+      if (const char* jb = std::getenv("ILQG_LS_JB")) {
+        const int w = std::max(1, std::atoi(jb));
+        spec.clear();
+        for (int done = w; done < remaining; done += w) spec += std::to_string(w) + ",";
+      }
+      int used = 0;
+      for (size_t pos = 0; pos < spec.size() && used < remaining;) {
+        const int w = std::atoi(spec.c_str() + pos);
+        if (w > 0) {
+          tiers.push_back(std::min(w, remaining - used));
+          used += tiers.back();
+        }
+        const size_t comma = spec.find(',', pos);
+        if (comma == std::string::npos) break;
+        pos = comma + 1;
+      }
+      if (used < remaining) tiers.push_back(remaining - used);
+    }
+    h->ls_tiers = tiers;
+    int JB = 0;
+    for (int w : tiers) JB = std::max(JB, w);
     // queue slots one continued-window launch holds candidate trajectories for: the whole batch
     // (one launch, no empty second chunk) while that scratch stays under 8 GiB, else chunks
     const size_t per_slot = (size_t)std::max(1, JB) * T * (n + M) * sizeof(float);
@@ -1334,6 +1398,11 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
     h->pipeline = 2;
     if (const char* e = std::getenv("ILQG_PIPELINE")) h->pipeline = std::atoi(e);
     if (const char* e = std::getenv("ILQG_ROLLOUT")) h->rollout_sp = std::strcmp(e, "lanes") != 0;
+    if (const char* e = std::getenv("ILQG_TRACE")) {
+      h->trace_path = e;
+      h->trace_cap = 1 << 16;
+      if ((rc = DevAlloc(h, &h->trace, (size_t)h->trace_cap, true)) != ILQG_OK) return fail(rc);
+    }
     ls.JA = JA;
     ls.JB = JB;
     ls.cap = cap;
@@ -1356,8 +1425,9 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
 #undef ALLOCNZ
     ALLOC(ls.pend[0], B);
     ALLOC(ls.pend[1], B);
+    ALLOC(ls.pend[2], B);
     ALLOC(ls.slot, B);
-    ALLOC(ls.counts, 2);
+    ALLOC(ls.counts, 3);
     ALLOC(s.ls_next_j, B);
   }
 #undef ALLOC
@@ -1389,6 +1459,15 @@ int ilqg_destroy(SubHandle h) {
   if (!h) return ILQG_ERR_BAD_HANDLE;
   Guard guard(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->trace && h->trace_n > 0) {
+    std::vector<unsigned long long> t(h->trace_n);
+    cudaDeviceSynchronize();
+    if (cudaMemcpy(t.data(), h->trace, sizeof(unsigned long long) * h->trace_n, cudaMemcpyDeviceToHost) == cudaSuccess)
+      if (FILE* f = std::fopen(h->trace_path.c_str(), "w")) {
+        for (int i = 0; i < h->trace_n; i++) std::fprintf(f, "%d %llu\n", h->trace_tags[i], t[i] - t[0]);
+        std::fclose(f);
+      }
+  }
   if (h->side) cudaStreamDestroy(h->side);
   if (h->ev_fresh) cudaEventDestroy(h->ev_fresh);
   if (h->ev_side) cudaEventDestroy(h->ev_side);
@@ -1513,8 +1592,11 @@ int ilqg_iterate(SubHandle h, int max_iters, int* iters_done) {
     if ((rc = IteratePipelined(h, max_iters)) != ILQG_OK) return rc;
   } else {
     for (int it = 0; it < max_iters; it++) {
+      Stamp(h, 0);
       if ((rc = LaunchLqRecords(h, 1)) != ILQG_OK) return rc;
+      Stamp(h, 1);
       if ((rc = DispatchBackward(h, 1, false)) != ILQG_OK) return rc;
+      Stamp(h, 2);
       if ((rc = LaunchLinesearch(h)) != ILQG_OK) return rc;
     }
   }

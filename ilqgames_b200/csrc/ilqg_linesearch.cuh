@@ -31,8 +31,10 @@ struct LsScratch {
   float* terms;     // [blocks][T][2N][32]  merit terms, item = lane of its block
   float* vals;      // [blocks][T][N][32]   per-player cost values
   int* absorbed;    // [items] 1 = every alpha term of this candidate vanished in rounding (see k_ls_rollout)
-  int* pend[2];     // double-buffered queue of instances with an open linesearch
-  int* counts;      // [2] queue lengths
+  int* pend[3];     // queues of instances with an open linesearch: [0] is filled by the first window and
+                    // stays intact for the rest of the pass (the pipelined schedule runs K_lq over it), the
+                    // tiers of the continued linesearch hand the still-open games on between [1] and [2]
+  int* counts;      // [3] queue lengths
   int* slot;        // [B] position of an instance in the queue it is in
   int JA, JB;       // window sizes: fresh linesearch / continued linesearch
   int nA_blocks;    // item blocks of a first-window launch
@@ -349,7 +351,8 @@ k_ls_rollout_sp(const __grid_constant__ DevDesc d, const DevParams p, Slab s, Ls
     const LsIo io = ls_io(s, ls, mode, it, item, T, n, M);
     float rho_j = 1.0f;
     for (int jj = 0; jj < it.j; jj++) rho_j *= rho;
-    const bool scaled = io.scaled;
+    const float m_s0 = io.scaled ? s0 : 1.0f, m_rho = (io.scaled && rho_exact) ? rho_j : 1.0f;
+    const bool slow_rho = io.scaled && !rho_exact;
     const bool rowlane = valid && t < nu && t < NUQ;  // this lane evaluates control row t of the subsystem
     const int c = rowlane ? d.sub[warp].ucol[t & 3] : 0;
     const bool complane = valid && t < xd;            // ... and owns state component t
@@ -415,15 +418,12 @@ k_ls_rollout_sp(const __grid_constant__ DevDesc d, const DevParams p, Slab s, Ls
           if (N4T || 4 * a4 + 2 < n) acc = fmaf(pr[4 * a4 + 2], dv.z, acc);
           if (N4T || 4 * a4 + 3 < n) acc = fmaf(pr[4 * a4 + 3], dv.w, acc);
         }
-      float alv = al;
-      if (scaled) {
-        alv *= s0;  // ScaleAlphas(initial_alpha_scaling), then geometric_alpha_scaling^j
-        if (rho_exact) {
-          alv *= rho_j;
-        } else {
+      // ScaleAlphas(initial_alpha_scaling), then geometric_alpha_scaling^j; an unscaled strategy (the
+      // Solve() prologue) multiplies by 1, which is exact
+      float alv = (al * m_s0) * m_rho;
+      if (slow_rho) {
 #pragma unroll 1
-          for (int jj = 0; jj < it.j; jj++) alv *= rho;
-        }
+        for (int jj = 0; jj < it.j; jj++) alv *= rho;
       }
       const float tt = uref - acc;
       const float uv = tt - alv;  // Strategy::operator(), strategy.h:73-76
@@ -567,6 +567,23 @@ k_ls_merit(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScrat
 // ---------------------------------------------------------------------------
 // decide: one warp per instance
 // ---------------------------------------------------------------------------
+// acc + v[0] + v[1] + ... + v[m - 1] in that order (one fp32 accumulator, as the reference's loops),
+// v[l] held by lane l.  The shuffles do not depend on the running sum: unrolled, they issue back to
+// back and only the additions form the chain (a rolled loop pays a shuffle latency per element).
+__device__ __forceinline__ float ordered_add(float acc, float v, int m) {
+  if (m == 32) {
+#pragma unroll
+    for (int l = 0; l < 32; l++) acc += __shfl_sync(0xffffffffu, v, l);
+  } else {
+#pragma unroll
+    for (int l = 0; l < 32; l++) {
+      const float cur = __shfl_sync(0xffffffffu, v, l);
+      if (l < m) acc += cur;
+    }
+  }
+  return acc;
+}
+
 // ILQSolver::TotalCosts (src/ilq_solver.cpp:220-257) from the per-step values an eval block left
 // behind: ordered over k, first extreme wins.
 __device__ __forceinline__ void ls_total_costs(const DevDesc& d, const Slab& s, int b, const float* vals_block,
@@ -579,19 +596,27 @@ __device__ __forceinline__ void ls_total_costs(const DevDesc& d, const Slab& s, 
     const int cs = d.cost_structure[i];
     float total = cs == ILQG_COST_SUM ? 0.f : cs == ILQG_COST_MAX ? -INFINITY : INFINITY;
     int te = s.te_new[(size_t)b * N + i];
-    for (int k0 = 0; k0 < d.T; k0 += 32) {
-      const float v = k0 + lane < d.T ? vals_block[((size_t)(k0 + lane) * N + i) * 32 + item_lane] : 0.f;
-      const int m = min(32, d.T - k0);
-      for (int l = 0; l < m; l++) {
-        const float cur = __shfl_sync(0xffffffffu, v, l);
-        if (cs == ILQG_COST_SUM)
-          total += cur;
-        else if (cs == ILQG_COST_MAX && cur > total) {
-          total = cur;
-          te = k0 + l;
-        } else if (cs == ILQG_COST_MIN && cur < total) {
-          total = cur;
-          te = k0 + l;
+    for (int k0 = 0; k0 < d.T; k0 += 128) {
+      // four rounds of loads in flight ahead of the scan
+      float v[4];
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+        v[r] = k0 + 32 * r + lane < d.T ? vals_block[((size_t)(k0 + 32 * r + lane) * N + i) * 32 + item_lane] : 0.f;
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int m = min(32, d.T - k0 - 32 * r);
+        if (m <= 0) break;
+        if (cs == ILQG_COST_SUM) {
+          total = ordered_add(total, v[r], m);
+        } else {
+#pragma unroll
+          for (int l = 0; l < 32; l++) {
+            const float cur = __shfl_sync(0xffffffffu, v[r], l);
+            if (l < m && ((cs == ILQG_COST_MAX && cur > total) || (cs == ILQG_COST_MIN && cur < total))) {
+              total = cur;
+              te = k0 + 32 * r + l;
+            }
+          }
         }
       }
     }
@@ -614,7 +639,7 @@ constexpr int KDEC_WARPS = 4;
 
 __global__ void __launch_bounds__(KDEC_WARPS * 32)
 k_ls_decide(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode, int cur_q,
-            int q_offset) {
+            int q_offset, int dst_q /* the queue still-open games are appended to */) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w = blockIdx.x * KDEC_WARPS + warp;
   int b;
@@ -655,10 +680,15 @@ k_ls_decide(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScra
         const size_t item = base;
         const float* terms = ls.terms + (item / ls.lpw) * (size_t)cnt * 32 + item % ls.lpw;
         float acc = 0.f;
-        for (int e0 = 0; e0 < cnt; e0 += 32) {
-          const float v = e0 + lane < cnt ? terms[(size_t)(e0 + lane) * 32] : 0.f;
-          const int m = min(32, cnt - e0);
-          for (int l = 0; l < m; l++) acc += __shfl_sync(0xffffffffu, v, l);
+        for (int e0 = 0; e0 < cnt; e0 += 256) {
+          float v[8];  // eight rounds of loads in flight ahead of the ordered sum
+#pragma unroll
+          for (int r = 0; r < 8; r++) v[r] = e0 + 32 * r + lane < cnt ? terms[(size_t)(e0 + 32 * r + lane) * 32] : 0.f;
+#pragma unroll
+          for (int r = 0; r < 8; r++) {
+            const int m = min(32, cnt - e0 - 32 * r);
+            if (m > 0) acc = ordered_add(acc, v[r], m);
+          }
         }
         merit = 0.5 * acc;
       } else if (c < ncand) {
@@ -712,21 +742,31 @@ k_ls_decide(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScra
       float* dus = s.op_us[1 - cur] + (size_t)b * T * M;
       const float* sus = ls.traj_us + item * T * M;
       if ((T * n) % 4 == 0) {
+#pragma unroll 8
         for (int e = lane; e < T * n / 4; e += 32)
           reinterpret_cast<float4*>(dxs)[e] = reinterpret_cast<const float4*>(sxs)[e];
       } else {
+#pragma unroll 8
         for (int e = lane; e < T * n; e += 32) dxs[e] = sxs[e];
       }
+#pragma unroll 8
       for (int e = lane; e < T * M; e += 32) dus[e] = sus[e];
     }
     ls_total_costs(d, s, b, ls.vals + (item / ls.lpw) * T * d.N * 32, (int)(item % ls.lpw), lane);
     // the scaled LQ strategies become current (ScaleAlphas, src/ilq_solver.cpp:66-72,314,339)
     float* alpha = s.st_a[1 - scur] + (size_t)b * T * M;
     const float s0 = p.initial_alpha_scaling, rho = p.geometric_alpha_scaling;
-    for (int e = lane; e < T * M; e += 32) {
-      float al = alpha[e] * s0;
-      for (int jj = 0; jj < j; jj++) al *= rho;
-      alpha[e] = al;
+    for (int e0 = 0; e0 < T * M; e0 += 256) {
+      float al[8];
+#pragma unroll
+      for (int r = 0; r < 8; r++) al[r] = e0 + 32 * r + lane < T * M ? alpha[e0 + 32 * r + lane] * s0 : 0.f;
+      for (int jj = 0; jj < j; jj++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) al[r] *= rho;
+      }
+#pragma unroll
+      for (int r = 0; r < 8; r++)
+        if (e0 + 32 * r + lane < T * M) alpha[e0 + 32 * r + lane] = al[r];
     }
     __syncwarp();
     if (lane == 0) {
@@ -760,8 +800,8 @@ k_ls_decide(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScra
     } else {
       s.ls_next_j[b] = jn;
       s.queued_flag[b] = 1;
-      const int q = atomicAdd(&ls.counts[1 - cur_q], 1);
-      ls.pend[1 - cur_q][q] = b;
+      const int q = atomicAdd(&ls.counts[dst_q], 1);
+      ls.pend[dst_q][q] = b;
       ls.slot[b] = q;
     }
   }
