@@ -305,10 +305,10 @@ struct CompactPattern {
 
 constexpr unsigned kItemReg = 0xFFF0u;  // item code 0xFFF0 + i: the constant state_reg[i] (template diagonal of Q_i)
 
-// shared memory: xu[n+M][32] | vals[NR][E][33] | itemv[NR][NIp] | gather table SoA | idx (u16)
+// shared memory: xu[n+M][32] | vals[NR][E][33] | itemv[NIp][33] | gather table SoA | idx (u16)
 __host__ __device__ inline size_t klq4_smem_bytes(int n, int M, int N, int E, int NIp, int num_items, int num_idx) {
   const int NR = N + 1;
-  size_t b = sizeof(float) * ((size_t)(n + M) * 32 + (size_t)NR * E * kValStride + (size_t)NR * NIp);
+  size_t b = sizeof(float) * ((size_t)(n + M) * 32 + (size_t)NR * E * kValStride + (size_t)NIp * kValStride);
   b += 4 * sizeof(int) * (size_t)num_items;
   b += sizeof(unsigned short) * (size_t)((num_idx + 7) & ~7);
   return b;
@@ -324,9 +324,9 @@ k_linearize_quadraticize_v4(const __grid_constant__ DevDesc d, Slab s, RecordPat
   const int n = d.n, M = d.M, N = d.N, T = d.T, NR = N + 1, E = pat.E;
   float* xu = smem;                                        // [n+M][32]
   float* vals = xu + (n + M) * 32;                         // [NR][E][33]
-  float* itembuf = vals + (size_t)NR * E * kValStride;     // [NR][NIp]
+  float* itembuf = vals + (size_t)NR * E * kValStride;     // [NIp][33]: the block's 32 compact records, record-minor
   const int NI = pat.num_items;
-  int* g_meta = reinterpret_cast<int*>(itembuf + (size_t)NR * cp.NIp);  // role | count << 8 | start << 16
+  int* g_meta = reinterpret_cast<int*>(itembuf + (size_t)cp.NIp * kValStride);  // role | count << 8 | start << 16
   float* g_base = reinterpret_cast<float*>(g_meta + NI);             // [NI]
   unsigned* g_e01 = reinterpret_cast<unsigned*>(g_base + NI);        // entries 0,1
   unsigned* g_e23 = g_e01 + NI;                                      // entries 2,3
@@ -404,53 +404,60 @@ k_linearize_quadraticize_v4(const __grid_constant__ DevDesc d, Slab s, RecordPat
   }
   __syncthreads();
 
-  // ---- phase 2: warp w turns records w, w + NR, ... into item values + g_k ----
-  float* itv = itembuf + (size_t)warp * cp.NIp;
+  // ---- phase 2: item values + g_k of the block's 32 records, lane = record ----
+  // (Until round 2's last session a warp took one record at a time and its lanes the items: every
+  // lane walked its own gather-table entry, and the g_k rows kept 16 of 32 lanes busy -- 74 % of the
+  // kernel's instructions.  With the record in the lane, the table walk is uniform across the warp:
+  // table words are broadcast reads, the values sit lane-minor in `vals`, nothing diverges.  Same
+  // additions in the same order.)
+  float* itv = itembuf;  // [g][33]
+  const bool keep_quad = keepq[lane] != 0;
+  const float* own = s.crec + ((size_t)(flags[lane] ? flags[lane] - 1 : 0) * T + (size_t)((first + lane) % T)) * cp.NIp;
+  for (int g = warp; g < NI; g += NR) {
+    const int meta = g_meta[g];
+    const int role = meta & 0xff, count = (meta >> 8) & 0xff, start = meta >> 16;
+    const float* v = vals + (size_t)role * E * kValStride + lane;
+    float acc = g_base[g];
+    if (count <= 4) {
+      const unsigned e01 = g_e01[g], e23 = g_e23[g];
+      if (count > 0) acc += v[(e01 & 0xffff) * kValStride];
+      if (count > 1) acc += v[(e01 >> 16) * kValStride];
+      if (count > 2) acc += v[(e23 & 0xffff) * kValStride];
+      if (count > 3) acc += v[(e23 >> 16) * kValStride];
+    } else {
+      for (int t = 0; t < count; t++) acc += v[gidx[start + t] * kValStride];
+    }
+    if (role < N && keep_quad) acc = own[g];  // the quadraticization of the solve's first iteration stays
+    itv[g * kValStride + lane] = acc;
+  }
+  __syncthreads();
+  // g_k[a] = sum_i (sum_c Q_i[a][c] l_i[c]): per-player fma chains over the non-zero terms, in
+  // ascending c (what the dense sweep computed, zeros skipped); warp w takes rows w, w + NR, ...
+  for (int a = warp; a < n; a += NR) {
+    float gk = 0.f, gi = 0.f;
+    int cur = -1;
+    const int e1 = __ldg(cp.gk_start + a + 1);
+    for (int e = __ldg(cp.gk_start + a); e < e1; e++) {
+      const uint2 u = __ldg(cp.gk + e);
+      if ((int)u.y != cur) { gk += gi; gi = 0.f; cur = (int)u.y; }
+      const unsigned qi = u.x & 0xffffu;
+      const float qv = qi >= kItemReg ? d.state_reg[qi - kItemReg] : itv[qi * kValStride + lane];
+      gi = fmaf(qv, itv[(u.x >> 16) * kValStride + lane], gi);
+    }
+    gk += gi;
+    itv[(NI + a) * kValStride + lane] = gk;
+  }
+  __syncthreads();
+  // ---- phase 3: warp w writes records w, w + NR, ... (coalesced; the tile is read along its columns,
+  //      stride 33: conflict-free) ----
   for (int r = warp; r < 32; r += NR) {
     const long long wr = first + r;
     if (wr >= total) break;
     if (!flags[r]) continue;
+    // (the instance need not be slot wr / T: SEL_LIST maps slots through the queue list)
     float* dst = s.crec + ((size_t)(flags[r] - 1) * T + (size_t)(wr % T)) * cp.NIp;
-    const bool keep_quad = keepq[r] != 0;
-    for (int g = lane; g < NI; g += 32) {
-      const int meta = g_meta[g];
-      const int role = meta & 0xff, count = (meta >> 8) & 0xff, start = meta >> 16;
-      const float* v = vals + (size_t)role * E * kValStride + r;
-      float acc = g_base[g];
-      if (keep_quad && role < N) {
-        acc = dst[g];  // the quadraticization of the solve's first iteration stays
-      } else if (count <= 4) {
-        const unsigned e01 = g_e01[g], e23 = g_e23[g];
-        if (count > 0) acc += v[(e01 & 0xffff) * kValStride];
-        if (count > 1) acc += v[(e01 >> 16) * kValStride];
-        if (count > 2) acc += v[(e23 & 0xffff) * kValStride];
-        if (count > 3) acc += v[(e23 >> 16) * kValStride];
-      } else {
-        for (int t = 0; t < count; t++) acc += v[gidx[start + t] * kValStride];
-      }
-      itv[g] = acc;
-    }
-    __syncwarp();
-    // g_k[a] = sum_i (sum_c Q_i[a][c] l_i[c]): per-player fma chains over the non-zero terms, in
-    // ascending c (what the dense sweep computed, zeros skipped)
-    float gk = 0.f;
-    if (lane < n) {
-      int cur = -1;
-      float gi = 0.f;
-      const int e1 = __ldg(cp.gk_start + lane + 1);
-      for (int e = __ldg(cp.gk_start + lane); e < e1; e++) {
-        const uint2 u = __ldg(cp.gk + e);
-        if ((int)u.y != cur) { gk += gi; gi = 0.f; cur = (int)u.y; }
-        const unsigned qi = u.x & 0xffffu;
-        const float qv = qi >= kItemReg ? d.state_reg[qi - kItemReg] : itv[qi];
-        gi = fmaf(qv, itv[u.x >> 16], gi);
-      }
-      gk += gi;
-    }
-    for (int g = lane; g < NI; g += 32) dst[g] = itv[g];
-    if (lane < n) dst[NI + lane] = gk;
+    for (int g = lane; g < NI + n; g += 32) dst[g] = itv[g * kValStride + r];
     if (lane < N) dst[NI + n + lane] = d.state_reg[lane];  // constants the sweep adds to the diagonal of Q_i
-    __syncwarp();
   }
 }
 
