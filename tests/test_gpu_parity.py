@@ -221,6 +221,45 @@ def test_lq_backward_gershgorin_and_batch(product, oracle):
         close(x, y, tol=2e-3, what=nm)  # looser: random indefinite systems are ill-conditioned
 
 
+@pytest.mark.parametrize("n,udims", [(16, (1, 2, 3)), (16, (1, 1, 4)), (24, (3, 1, 2, 2)), (10, (2, 3)), (7, (8,))])
+def test_lq_backward_any_shape_and_nonuniform_controls(product, oracle, n, udims):
+    """an LQ-only handle whose (n, M, N) is one of the shape-keyed kernels' -- (16, 6, 3),
+    (24, 8, 4) -- but whose players do NOT have M / N controls each must not reach the half-warp
+    kernel (it hard-codes m = M / N); like every other shape in the envelope it takes the
+    run-time-dimension sweep.  LQFeedbackSolver::Solve takes any dimensions
+    (src/lq_feedback_solver.cpp:71-244)."""
+    rng = np.random.default_rng(n * 31 + len(udims))
+    B, T, N, M = 6, 20, len(udims), sum(udims)
+    desc = problems.lq_only(T, n, list(udims))
+    A = (np.eye(n) + 0.05 * rng.normal(size=(B, T, n, n))).astype(np.float32)
+    Bs = (0.2 * rng.normal(size=(B, T, n, M))).astype(np.float32)
+    Qh = rng.normal(size=(B, T, N, n, n))
+    Q = (Qh @ np.swapaxes(Qh, -1, -2) * 0.1 + 0.5 * np.eye(n)).astype(np.float32)
+    l = rng.normal(size=(B, T, N, n)).astype(np.float32)
+    res = []
+    for lib in (product, oracle):
+        h = abi.Handle(lib, desc, abi.SolverParams.defaults(), B)
+        lo = h.layout
+        # R_ii = a well-conditioned SPD block per player, r_ii random (the only pairs of this descriptor)
+        R = np.zeros((B, T, lo.R_floats), np.float32)
+        r = np.zeros((B, T, lo.r_floats), np.float32)
+        rr = np.random.default_rng(7)
+        for pidx in range(lo.num_pairs):
+            m = udims[lo.pair_arg[pidx]]
+            Rh = rr.normal(size=(B, T, m, m))
+            blk = Rh @ np.swapaxes(Rh, -1, -2) * 0.1 + np.eye(m)
+            R[..., lo.pair_R_offset[pidx]:lo.pair_R_offset[pidx] + m * m] = blk.reshape(B, T, m * m)
+            r[..., lo.pair_r_offset[pidx]:lo.pair_r_offset[pidx] + m] = rr.normal(size=(B, T, m))
+        h.upload_lq(A, Bs, Q, l, R, r)
+        h.lq_backward()
+        res.append((h.download(abi.LQ_PS), h.download(abi.LQ_ALPHAS), h.download(abi.DELTA_XS),
+                    h.download(abi.EXPECTED_DECREASE)))
+        h.close()
+    for (x, y, nm) in zip(res[0], res[1], ("P", "alpha", "dxs", "expected decrease")):
+        compared = close(x, y, tol=1e-3, what=f"{nm} n={n} udims={udims}")
+        assert compared == B
+
+
 # ------------------------------------------------------------------ stage-by-stage parity
 # BASELINE.json's configs name T = 150 for RoundaboutMerging and T = 50 for Air3D (the reference's
 # own examples use 100): both horizons are run
