@@ -475,7 +475,7 @@ constexpr int KLS_MERIT_CHUNK = ILQG_MERIT_CHUNK;
 __host__ __device__ inline int ls_merit_smem_floats(int n, int M, int N) { return N * 2 * (n + M) * 32; }
 
 template <bool WIDE>  // false: round 1's record kinds only, no FinalTimeCost gates, no ExtremeValueCost groups
-__global__ void __launch_bounds__(ILQG_MAX_PLAYERS * 32)
+__global__ void __launch_bounds__(ILQG_MAX_PLAYERS * 32, 6)  // (<= 85 registers: eight 3-warp blocks per SM)
 k_ls_merit(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode, int cur_q,
            int q_offset, int blocks) {
   extern __shared__ __align__(16) float smem[];
@@ -497,6 +497,7 @@ k_ls_merit(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScrat
   float* vals = ls.vals + (size_t)ib * T * N * 32;
   const float mu = valid ? s.mu[b] : 0.f;
   const int te = valid ? s.te_quad[(size_t)b * N + i] : 0;
+  const float* lam_base = s.lambdas + (size_t)(valid ? b : 0) * d.num_constraints * T;  // this game's multipliers [slot][T]
   const bool additive = d.cost_structure[i] == ILQG_COST_SUM;
   const int mi = d.udim[i];
   const int k0 = blockIdx.y * KLS_MERIT_CHUNK, k1 = min(T, k0 + KLS_MERIT_CHUNK);
@@ -522,6 +523,7 @@ k_ls_merit(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScrat
     }
     for (int a = 0; a < n + M; a++) acc[a * 32 + lane] = 0.f;
     const bool full = additive || te == kk;
+    const int lidx = s.lambda_index[kk];
     float value = 0.f;
     for (int c0 = d.cost_begin[i]; c0 < d.cost_begin[i + 1];) {
       // an ExtremeValueCost (group > 0) stands for its extreme member (src/extreme_value_cost.cpp:50-62)
@@ -536,10 +538,10 @@ k_ls_merit(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScrat
       // VALUE (PlayerCost::Evaluate) always counts every state and control cost.
       const bool in_quad = full || (cd.arg >= 0 && !is_con);
       if (!in_quad && is_con) continue;
-      const float lambda =
-          (is_con && valid) ? s.lambdas[((size_t)b * d.num_constraints + cd.slot) * T + s.lambda_index[kk]] : 0.f;
-      GatedSink sink{acc + (cd.arg < 0 ? 0 : (n + d.uoff[cd.arg]) * 32) + lane, in_quad};
-      const float* in = cd.arg < 0 ? slot + lane : slot + (n + d.uoff[cd.arg]) * 32 + lane;
+      const float lambda = (is_con && valid) ? lam_base[cd.slot * T + lidx] : 0.f;
+      const int aoff = (cd.arg < 0 ? 0 : (n + d.uoff[cd.arg]) * 32) + lane;  // the record's argument in the tiles
+      GatedSink sink{acc + aoff, in_quad};
+      const float* in = slot + aoff;
       float v = 0.f;
       quadraticize_record_sink<false, 32, true, GatedSink, WIDE>(d, cd, in, cd.arg < 0 ? n : d.udim[cd.arg], lambda, mu, sink, &v);
       if (!is_con) value += v;  // PlayerCost::Evaluate: costs only

@@ -76,15 +76,14 @@ enum {
   ILQG_DYN_CAR6D = 1,      /* params[0] = inter-axle distance                  */
   ILQG_DYN_UNICYCLE4D = 2,
   ILQG_DYN_AIR3D = 3,      /* params[0] = evader speed, params[1] = pursuer    */
-  ILQG_DYN_CAR5D = 4,      /* single_player_car_5d.h:102-147; params[0] = inter-axle distance.
-                            * CPU oracle only so far: the CUDA library answers ILQG_ERR_UNSUPPORTED */
+  ILQG_DYN_CAR5D = 4,      /* single_player_car_5d.h:102-147; params[0] = inter-axle distance */
   ILQG_DYN_DUBINS = 5,     /* single_player_dubins_car.h:56-118: (x, y, theta), control = turn rate,
-                            * params[0] = constant speed.  CPU oracle only so far as well */
+                            * params[0] = constant speed */
   ILQG_DYN_TWO_PLAYER_UNICYCLE4D = 6, /* two_player_unicycle_4d.h:60-137: one coupled subsystem
                             * (x, y, theta, v); player first_player steers (omega, a), the next
-                            * one pushes the position (dx, dy).  CPU oracle only so far */
+                            * one pushes the position (dx, dy) */
   ILQG_DYN_POINT_MASS_2D = 7 /* single_player_point_mass_2d.h:56-118: (x, y, vx, vy), controls
-                            * (ax, ay).  CPU oracle only so far */
+                            * (ax, ay) */
 };
 
 typedef struct {
@@ -111,11 +110,9 @@ enum {
   ILQG_CONSTRAINT_PROXIMITY = 7,          /* dim[0..3], value=threshold, flag=keep_within      */
   ILQG_CONSTRAINT_SINGLE_DIMENSION = 8,   /* dim[0], value=threshold, flag=keep_below          */
   ILQG_COST_SIGNED_DISTANCE = 9,          /* src/signed_distance_cost.cpp:50-112: dim[0..3]=x1,y1,x2,y2,
-                                           * value=nominal, flag=less_is_positive (weight unused).
-                                           * CPU oracle only so far (CUDA: ILQG_ERR_UNSUPPORTED) */
+                                           * value=nominal, flag=less_is_positive (weight unused) */
   ILQG_COST_QUADRATIC_DIFFERENCE = 10     /* src/quadratic_difference_cost.cpp:50-91: 0.5 w sum (in[a_k] - in[b_k])^2
-                                           * over flag = 1 or 2 pairs, dim[0..1] = a, dim[2..3] = b.
-                                           * CPU oracle only so far (CUDA: ILQG_ERR_UNSUPPORTED) */
+                                           * over flag = 1 or 2 pairs, dim[0..1] = a, dim[2..3] = b */
 };
 
 typedef struct {
@@ -137,7 +134,7 @@ typedef struct {
    * src/extreme_value_cost.cpp:50-84): consecutive records of one player with the same group > 0
    * are its sub-costs, in order; whenever the cost is evaluated or quadraticized only the member
    * with the largest (group_is_min: smallest) value counts, the first one on ties.  0 = a plain
-   * record.  CPU oracle only so far (CUDA: ILQG_ERR_UNSUPPORTED). */
+   * record. */
   int32_t group;
   int32_t group_is_min;
 } ilqg_cost_desc;
