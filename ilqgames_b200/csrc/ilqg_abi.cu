@@ -44,7 +44,8 @@ struct SubSolver {
   int trace_n = 0, trace_cap = 0;
   std::vector<int> trace_tags;
   std::string trace_path;
-  bool rollout_sp = true;   // ILQG_ROLLOUT=lanes selects round 1's lane-per-item rollout (A/B runs, the bit-identity test)
+  int rollout_mode = 0;     // ILQG_ROLLOUT: 0 auto (by window size, ilqg_linesearch.cuh: LsPick), 1 sp, 2 lanes (A/B runs, the bit-identity test)
+  int cap_sp = 0, cap_lanes = 0;
   int tc_blocks_cap = 0;    // ILQG_TC_BLOCKS
   bool use_compact = true;  // ILQG_RECORDS=dense forces the round-1 dense-record kernels (A/B runs)
   // which representation of the LQ records is current: K_lq v4 writes the compact one,
@@ -913,37 +914,53 @@ int LaunchLsSplit(SubSolver* h, int mode, int blocks, int q_offset) {
     classic = classic && (d.sub[k].kind == ILQG_DYN_CAR6D || d.sub[k].kind == ILQG_DYN_UNICYCLE4D || d.sub[k].kind == ILQG_DYN_AIR3D);
   }
   classic = classic && nuq <= 2;
-  if (h->rollout_sp) {
-    // the stage-parallel rollout: 4 items per block, a grid-stride loop over the item blocks in use
-    const long long nblk = ((long long)blocks * h->ls.lpw + RSP_ITEMS - 1) / RSP_ITEMS;
-    const int grid = (int)std::min<long long>(nblk, (long long)h->sm_count * 16);
-#define LS_SP(NUQ_, WIDE_, N4_) \
-  k_ls_rollout_sp<NUQ_, WIDE_, N4_><<<grid, S * 32, 0, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset, blocks)
-    if (classic && d.n == 16) LS_SP(2, false, 4);
-    else if (classic && d.n == 24) LS_SP(2, false, 6);
-    else if (classic) LS_SP(2, false, 0);
-    else if (nuq <= 2) LS_SP(2, true, 0);
-    else LS_SP(4, true, 0);
-#undef LS_SP
-  } else {
-#define LS_ROLL(SS)                                                                               \
-  case SS:                                                                                        \
-    if (classic) {                                                                                \
-      if ((rc = SetSmem(k_ls_rollout<SS, 2, false>, smem_r)) != ILQG_OK) return rc;                \
-      k_ls_rollout<SS, 2, false><<<blocks, SS * 32, smem_r, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset); \
-    } else if (nuq <= 2) {                                                                        \
-      if ((rc = SetSmem(k_ls_rollout<SS, 2, true>, smem_r)) != ILQG_OK) return rc;                 \
-      k_ls_rollout<SS, 2, true><<<blocks, SS * 32, smem_r, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset); \
-    } else {                                                                                      \
-      if ((rc = SetSmem(k_ls_rollout<SS, 4, true>, smem_r)) != ILQG_OK) return rc;                 \
-      k_ls_rollout<SS, 4, true><<<blocks, SS * 32, smem_r, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset); \
-    }                                                                                             \
+  // the two rollout kernels of this descriptor (ilqg_linesearch.cuh: LsPick)
+  using SpKernel = void (*)(const DevDesc, const DevParams, Slab, LsScratch, int, int, int, int, LsPick);
+  SpKernel k_sp = nullptr, k_lanes = nullptr;
+  if (classic && d.n == 16) k_sp = k_ls_rollout_sp<2, false, 4>;
+  else if (classic && d.n == 24) k_sp = k_ls_rollout_sp<2, false, 6>;
+  else if (classic) k_sp = k_ls_rollout_sp<2, false, 0>;
+  else if (nuq <= 2) k_sp = k_ls_rollout_sp<2, true, 0>;
+  else k_sp = k_ls_rollout_sp<4, true, 0>;
+#define LS_ROLL(SS)                                                                                          \
+  case SS:                                                                                                   \
+    k_lanes = classic ? k_ls_rollout<SS, 2, false> : nuq <= 2 ? k_ls_rollout<SS, 2, true> : k_ls_rollout<SS, 4, true>; \
     break;
   switch (S) {
     LS_ROLL(1) LS_ROLL(2) LS_ROLL(3) LS_ROLL(4)
     default: return ILQG_ERR_UNSUPPORTED;
   }
 #undef LS_ROLL
+  if ((rc = SetSmem(k_lanes, smem_r)) != ILQG_OK) return rc;
+  if (h->cap_sp <= 0) {  // items one resident wave of each kernel holds on this device
+    int occ_sp = 0, occ_lanes = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sp, k_sp, S * 32, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lanes, k_lanes, S * 32, smem_r));
+    h->cap_sp = std::max(1, occ_sp) * h->sm_count * RSP_ITEMS;
+    h->cap_lanes = std::max(1, occ_lanes) * h->sm_count * 32;
+  }
+  // ILQG_ROLLOUT = sp | lanes forces one kernel; auto (default): the first window's size is known here, a
+  // continued window's only on the device -- both kernels are launched and one of them returns at once
+  const long long nblk = ((long long)blocks * h->ls.lpw + RSP_ITEMS - 1) / RSP_ITEMS;
+  const int grid_sp = (int)std::min<long long>(nblk, (long long)h->sm_count * 16);
+  // Measured (profiles/r02_summary.md): with several subsystem warps per block the lane-per-item kernel loses at
+  // every window size (C3: 71 vs 80 k instance-iterations/s); with one (Air3D: a block is a single
+  // warp, so resident blocks per SM, not registers, cap the stage-parallel kernel) it wins on the large
+  // continued windows (C4: 2.23 vs 1.79 M).  auto therefore only considers it when S = 1.
+  int run_sp = h->rollout_mode == 1 || (h->rollout_mode == 0 && S > 1) ? 1 : h->rollout_mode == 2 ? 0 : -1;
+  int run_lanes = run_sp < 0 ? -1 : 1 - run_sp;
+  if (run_sp < 0 && mode != LS_MODE_QUEUED) {
+    run_lanes = ls_prefers_lanes((long long)blocks * h->ls.lpw, h->cap_sp, h->cap_lanes) ? 1 : 0;
+    run_sp = 1 - run_lanes;
+  }
+  if (run_sp != 0) {
+    const LsPick pick{run_sp < 0 ? 1 : 0, h->cap_sp, h->cap_lanes};
+    k_sp<<<grid_sp, S * 32, 0, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset, blocks, pick);
+  }
+  if (run_lanes != 0) {
+    const LsPick pick{run_lanes < 0 ? 2 : 0, h->cap_sp, h->cap_lanes};
+    k_lanes<<<blocks, S * 32, smem_r, h->stream>>>(h->d, h->p, h->s, h->ls, mode, h->ls_cur, q_offset, blocks, pick);
+    h->launches += run_sp != 0 ? 1 : 0;
   }
   Stamp(h, 3 + mode * 10);  // rollout done
   auto merit = h->classic ? k_ls_merit<false> : k_ls_merit<true>;
@@ -1397,7 +1414,7 @@ int ilqg_create(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
     // (profiles/r01_schedule_experiments.md)
     h->pipeline = 2;
     if (const char* e = std::getenv("ILQG_PIPELINE")) h->pipeline = std::atoi(e);
-    if (const char* e = std::getenv("ILQG_ROLLOUT")) h->rollout_sp = std::strcmp(e, "lanes") != 0;
+    if (const char* e = std::getenv("ILQG_ROLLOUT")) h->rollout_mode = !std::strcmp(e, "lanes") ? 2 : !std::strcmp(e, "sp") ? 1 : 0;
     if (const char* e = std::getenv("ILQG_TRACE")) {
       h->trace_path = e;
       h->trace_cap = 1 << 16;

@@ -79,6 +79,32 @@ __device__ __forceinline__ LsItem ls_decode(const DevParams& p, const Slab& s, c
   return it;
 }
 
+// Which rollout kernel a window takes.  The stage-parallel kernel spends eight lanes per (item, subsystem) to cut
+// the latency chain of a time step; the lane-per-item kernel spends one and takes ~2.8 x as long per wave,
+// but a wave of it holds eight times the items.  A window of a few thousand items is latency bound
+// (stage-parallel wins), one of a hundred thousand is throughput bound (lane-per-item wins: half the
+// instructions per item).  The size of a continued window exists only on the device, so both kernels
+// are launched for it and each asks this function whether it is the one to run.
+struct LsPick {
+  int which;      // 0: run unconditionally; 1: "I am the stage-parallel kernel"; 2: "I am the lane-per-item kernel"
+  int cap_sp;     // items one resident wave of the stage-parallel kernel holds on this device
+  int cap_lanes;  // ... of the lane-per-item kernel
+};
+__host__ __device__ inline bool ls_prefers_lanes(long long items, int cap_sp, int cap_lanes) {
+  if (items <= 0 || cap_sp <= 0 || cap_lanes <= 0) return false;
+  const long long w_sp = (items + cap_sp - 1) / cap_sp, w_lanes = (items + cap_lanes - 1) / cap_lanes;
+  return 14 * w_lanes < 5 * w_sp;
+}
+__device__ __forceinline__ bool ls_pick_runs(const LsScratch& ls, int mode, int cur_q, int q_offset, int blocks,
+                                             const LsPick& pick) {
+  if (pick.which == 0) return true;
+  long long items = (long long)blocks * ls.lpw;
+  if (mode == 2 /* LS_MODE_QUEUED */)
+    items = min(items, (long long)min(max(ls.counts[cur_q] - q_offset, 0), ls.cap) * ls.JB);
+  const bool lanes = ls_prefers_lanes(items, pick.cap_sp, pick.cap_lanes);
+  return pick.which == 2 ? lanes : !lanes;
+}
+
 // gradient accumulator in the lane-minor shared tile; `on` = false keeps only the cost value
 struct GatedSink {
   float* grad;  // element idx at grad[idx * 32]
@@ -161,10 +187,11 @@ __host__ __device__ inline int ls_rollout_smem_floats(int n, int S) {
 template <int S, int NUQ, bool WIDE>
 __global__ void __launch_bounds__(S * 32)
 k_ls_rollout(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode, int cur_q,
-             int q_offset) {
+             int q_offset, int blocks, LsPick pick) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = d.n, M = d.M, T = d.T;
+  if (!ls_pick_runs(ls, mode, cur_q, q_offset, blocks, pick)) return;
   const int item = blockIdx.x * ls.lpw + lane;
   const LsItem it = ls_decode(p, s, ls, mode, cur_q, q_offset, blockIdx.x, lane);
   if (!__syncthreads_or(it.valid)) return;
@@ -316,9 +343,10 @@ constexpr int RSP_DX_STRIDE = 28;  // floats per item row of the dx tile: n <= 2
 template <int NUQ, bool WIDE, int N4T>
 __global__ void __launch_bounds__(ILQG_MAX_SUBSYSTEMS * 32, 6)
 k_ls_rollout_sp(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode, int cur_q,
-                int q_offset, int blocks /* item blocks of ls.lpw items the window spans */) {
+                int q_offset, int blocks /* item blocks of ls.lpw items the window spans */, LsPick pick) {
   __shared__ __align__(16) float dxs2[2][RSP_ITEMS][RSP_DX_STRIDE];
   __shared__ int absf[ILQG_MAX_SUBSYSTEMS][RSP_ITEMS];
+  if (!ls_pick_runs(ls, mode, cur_q, q_offset, blocks, pick)) return;
   const unsigned full = 0xffffffffu;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 3, t = lane & 7;  // item of the block, stage slot / component / control row
