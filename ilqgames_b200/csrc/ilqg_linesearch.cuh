@@ -495,7 +495,7 @@ __device__ __forceinline__ int ls_live_blocks(const LsScratch& ls, int mode, int
 
 // time steps one k_ls_merit block covers
 #ifndef ILQG_MERIT_CHUNK
-#define ILQG_MERIT_CHUNK 5
+#define ILQG_MERIT_CHUNK 3
 #endif
 constexpr int KLS_MERIT_CHUNK = ILQG_MERIT_CHUNK;
 
@@ -514,7 +514,8 @@ k_ls_merit(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScrat
   for (int ib = blockIdx.x; ib < live_blocks; ib += gridDim.x) {
   const int item = ib * ls.lpw + lane;
   const LsItem it = ls_decode(p, s, ls, mode, cur_q, q_offset, ib, lane);
-  if (!__syncthreads_or(it.valid)) continue;
+  // (the player warps of a block share nothing -- each has its own tiles -- so there is no block barrier)
+  if (!__any_sync(0xffffffffu, it.valid)) continue;
   const bool valid = it.valid;
   const int b = it.b;
   const LsIo io = ls_io(s, ls, mode, it, item, T, n, M);
@@ -590,7 +591,7 @@ k_ls_merit(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScrat
     terms[((size_t)kk * 2 * N + 2 * i + 1) * 32 + lane] = sq2;
     vals[((size_t)kk * N + i) * 32 + lane] = value;
   }
-  __syncthreads();  // the tiles are reused by the next item block
+  __syncwarp();
   }
 }
 

@@ -886,3 +886,38 @@ def test_rollout_kernels_bit_identical(product, name, T, batch, iters):
         np.testing.assert_array_equal(a, b)
     report(f"rollout_bit_identical[{name},T={T}]", batch=x0.shape[0], iterations=iters,
            backtracks=int(outs[0][-3].sum()))
+
+
+@pytest.mark.parametrize("name,T,batch", [("three_player_intersection", 100, 96), ("air_3d", 50, 128), ("roundabout_merging", 100, 24)])
+def test_tier_splits_and_pipeline_give_identical_solves(product, name, T, batch):
+    """How the continued linesearch is cut into tiers (ILQG_LS_TIERS), which rollout kernel a window
+    takes (ILQG_ROLLOUT) and whether the open linesearches finish on a side stream (ILQG_PIPELINE) are
+    schedules, not algorithms: candidate j's trajectory and merit depend on j alone and the first
+    candidate that passes Armijo wins, so every variant must reproduce the one-window, one-stream
+    solve bit for bit -- trajectories, strategies, merits, statuses, iteration and rollout counts."""
+    build, params, x0f = CONFIGS[name]
+    desc, _ = build(num_time_steps=T)
+    x0 = x0f(batch)
+    variants = [{"ILQG_LS_TIERS": "99", "ILQG_PIPELINE": "0", "ILQG_ROLLOUT": "sp"},
+                {}, {"ILQG_LS_TIERS": "7,32"}, {"ILQG_LS_TIERS": "5"}, {"ILQG_LS_TIERS": "39", "ILQG_PIPELINE": "0"},
+                {"ILQG_ROLLOUT": "lanes"}, {"ILQG_LS_TIERS": "7,32", "ILQG_PIPELINE": "1", "ILQG_ROLLOUT": "auto"}]
+    outs = []
+    for env in variants:
+        os.environ.update(env)
+        try:
+            h = abi.Handle(product, desc, params(max_solver_iters=6, disable_convergence_exit=1), x0.shape[0], 0)
+        finally:
+            for k in env:
+                del os.environ[k]
+        h.upload_x0(x0)
+        h.solve_begin()
+        h.solve(chunk=6)
+        outs.append([h.download(w) for w in (abi.XS, abi.US, abi.PS, abi.ALPHAS, abi.MERIT, abi.STATUS, abi.ITERS,
+                                             abi.BACKTRACKS, abi.TOTAL_COSTS, abi.STEP)])
+        h.close()
+    for v, out in zip(variants[1:], outs[1:]):
+        for a, b in zip(outs[0], out):
+            np.testing.assert_array_equal(a, b, err_msg=str(v))
+    bt = outs[0][7]
+    report(f"tier_splits[{name},T={T}]", batch=x0.shape[0], variants=len(variants), rollouts=int(bt.sum()),
+           failed=int((outs[0][5] == abi.STATUS_LINESEARCH_FAILED).sum()))
