@@ -340,8 +340,11 @@ constexpr int RSP_DX_STRIDE = 28;  // floats per item row of the dx tile: n <= 2
 
 // N4T: n / 4 known at compile time (n = 4 N4T: the feedback row is N4T 128-bit loads, the dot product
 // an unrolled chain), or 0 for any n at run time.
+#ifndef ILQG_RSP_MINB
+#define ILQG_RSP_MINB 6
+#endif
 template <int NUQ, bool WIDE, int N4T>
-__global__ void __launch_bounds__(ILQG_MAX_SUBSYSTEMS * 32, 6)
+__global__ void __launch_bounds__(ILQG_MAX_SUBSYSTEMS * 32, ILQG_RSP_MINB)
 k_ls_rollout_sp(const __grid_constant__ DevDesc d, const DevParams p, Slab s, LsScratch ls, int mode, int cur_q,
                 int q_offset, int blocks /* item blocks of ls.lpw items the window spans */, LsPick pick) {
   __shared__ __align__(16) float dxs2[2][RSP_ITEMS][RSP_DX_STRIDE];

@@ -305,11 +305,11 @@ struct CompactPattern {
 
 constexpr unsigned kItemReg = 0xFFF0u;  // item code 0xFFF0 + i: the constant state_reg[i] (template diagonal of Q_i)
 
-// shared memory: xu[n+M][32] | vals[NR][E][33] | itemv[NIp][33] | gather table SoA | idx (u16)
+// shared memory: xu[n+M][32] | vals[NR][E][33] | itemv[NIp][33] | gather table (byte offsets x4 | base, meta) | idx (u16)
 __host__ __device__ inline size_t klq4_smem_bytes(int n, int M, int N, int E, int NIp, int num_items, int num_idx) {
   const int NR = N + 1;
   size_t b = sizeof(float) * ((size_t)(n + M) * 32 + (size_t)NR * E * kValStride + (size_t)NIp * kValStride);
-  b += 4 * sizeof(int) * (size_t)num_items;
+  b += 6 * sizeof(int) * (size_t)((num_items + 1) & ~1);
   b += sizeof(unsigned short) * (size_t)((num_idx + 7) & ~7);
   return b;
 }
@@ -326,11 +326,13 @@ k_linearize_quadraticize_v4(const __grid_constant__ DevDesc d, Slab s, RecordPat
   float* vals = xu + (n + M) * 32;                         // [NR][E][33]
   float* itembuf = vals + (size_t)NR * E * kValStride;     // [NIp][33]: the block's 32 compact records, record-minor
   const int NI = pat.num_items;
-  int* g_meta = reinterpret_cast<int*>(itembuf + (size_t)cp.NIp * kValStride);  // role | count << 8 | start << 16
-  float* g_base = reinterpret_cast<float*>(g_meta + NI);             // [NI]
-  unsigned* g_e01 = reinterpret_cast<unsigned*>(g_base + NI);        // entries 0,1
-  unsigned* g_e23 = g_e01 + NI;                                      // entries 2,3
-  unsigned short* gidx = reinterpret_cast<unsigned short*>(g_e23 + NI);
+  // gather table, one int4 + one int2 per item: the byte offsets of its first four values inside `vals`
+  // ((role E + entry) 33 floats; the lane's own 4 bytes are added once), then (template value, role | count << 8 |
+  // start << 16) -- two vector loads per item instead of four scalar ones and the index arithmetic
+  const int NI2 = (NI + 1) & ~1;
+  int4* g_off4 = reinterpret_cast<int4*>(itembuf + (size_t)cp.NIp * kValStride);  // [NI2]
+  int2* g_bm = reinterpret_cast<int2*>(g_off4 + NI2);                              // [NI2]
+  unsigned short* gidx = reinterpret_cast<unsigned short*>(g_bm + NI2);
 
   const long long first = (long long)blockIdx.x * 32;
   const long long total = (long long)s.B * T;
@@ -348,10 +350,10 @@ k_linearize_quadraticize_v4(const __grid_constant__ DevDesc d, Slab s, RecordPat
     for (int e = warp; e < n + M; e += NR) xu[e * 32 + lane] = in_range ? (e < n ? xs[e] : us[e - n]) : 0.f;
     for (int e = threadIdx.x; e < NI; e += blockDim.x) {
       const GatherItem it = pat.items[e];
-      g_meta[e] = it.role | (it.count << 8) | (it.start << 16);
-      g_base[e] = it.base;
-      g_e01[e] = (unsigned)it.e[0] | ((unsigned)it.e[1] << 16);
-      g_e23[e] = (unsigned)it.e[2] | ((unsigned)it.e[3] << 16);
+      const int rb = it.role * E;
+      g_off4[e] = make_int4((rb + it.e[0]) * kValStride * 4, (rb + it.e[1]) * kValStride * 4,
+                            (rb + it.e[2]) * kValStride * 4, (rb + it.e[3]) * kValStride * 4);
+      g_bm[e] = make_int2(__float_as_int(it.base), it.role | (it.count << 8) | (it.start << 16));
     }
     for (int e = threadIdx.x; e < pat.num_idx; e += blockDim.x) gidx[e] = pat.idx[e];
   }
@@ -412,22 +414,26 @@ k_linearize_quadraticize_v4(const __grid_constant__ DevDesc d, Slab s, RecordPat
   // additions in the same order.)
   float* itv = itembuf;  // [g][33]
   const bool keep_quad = keepq[lane] != 0;
-  const float* own = s.crec + ((size_t)(flags[lane] ? flags[lane] - 1 : 0) * T + (size_t)((first + lane) % T)) * cp.NIp;
+  const bool any_keep = __any_sync(0xffffffffu, keep_quad);
+  // where this lane's record goes (the instance need not be slot w / T: SEL_LIST maps slots through the queue list)
+  float* own = s.crec + ((size_t)b * T + (size_t)k) * cp.NIp;
+  const char* vl = reinterpret_cast<const char*>(vals + lane);
   for (int g = warp; g < NI; g += NR) {
-    const int meta = g_meta[g];
-    const int role = meta & 0xff, count = (meta >> 8) & 0xff, start = meta >> 16;
-    const float* v = vals + (size_t)role * E * kValStride + lane;
-    float acc = g_base[g];
+    const int4 o = g_off4[g];
+    const int2 bm = g_bm[g];
+    const int role = bm.y & 0xff, count = (bm.y >> 8) & 0xff;
+    float acc = __int_as_float(bm.x);
     if (count <= 4) {
-      const unsigned e01 = g_e01[g], e23 = g_e23[g];
-      if (count > 0) acc += v[(e01 & 0xffff) * kValStride];
-      if (count > 1) acc += v[(e01 >> 16) * kValStride];
-      if (count > 2) acc += v[(e23 & 0xffff) * kValStride];
-      if (count > 3) acc += v[(e23 >> 16) * kValStride];
+      if (count > 0) acc += *reinterpret_cast<const float*>(vl + o.x);
+      if (count > 1) acc += *reinterpret_cast<const float*>(vl + o.y);
+      if (count > 2) acc += *reinterpret_cast<const float*>(vl + o.z);
+      if (count > 3) acc += *reinterpret_cast<const float*>(vl + o.w);
     } else {
+      const float* v = vals + (size_t)role * E * kValStride + lane;
+      const int start = bm.y >> 16;
       for (int t = 0; t < count; t++) acc += v[gidx[start + t] * kValStride];
     }
-    if (role < N && keep_quad) acc = own[g];  // the quadraticization of the solve's first iteration stays
+    if (any_keep && role < N && keep_quad) acc = own[g];  // the quadraticization of the solve's first iteration stays
     itv[g * kValStride + lane] = acc;
   }
   __syncthreads();
@@ -451,11 +457,11 @@ k_linearize_quadraticize_v4(const __grid_constant__ DevDesc d, Slab s, RecordPat
   // ---- phase 3: warp w writes records w, w + NR, ... (coalesced; the tile is read along its columns,
   //      stride 33: conflict-free) ----
   for (int r = warp; r < 32; r += NR) {
-    const long long wr = first + r;
-    if (wr >= total) break;
+    // record r's address is lane r's `own` (no second division by T)
+    const unsigned long long p64 = reinterpret_cast<unsigned long long>(own);
+    float* dst = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, p64, r));
+    if (first + r >= total) break;
     if (!flags[r]) continue;
-    // (the instance need not be slot wr / T: SEL_LIST maps slots through the queue list)
-    float* dst = s.crec + ((size_t)(flags[r] - 1) * T + (size_t)(wr % T)) * cp.NIp;
     for (int g = lane; g < NI + n; g += 32) dst[g] = itv[g * kValStride + r];
     if (lane < N) dst[NI + n + lane] = d.state_reg[lane];  // constants the sweep adds to the diagonal of Q_i
   }
