@@ -75,6 +75,13 @@ class IntersectionProblem : public TopDownRenderableProblem {
       const std::pair<Dimension, Dimension> xy(s, s + 1);
       pc.AddStateCost(std::make_shared<QuadraticPolyline2Cost>(25.0f, Polyline2(agents[i].lane), xy, "LaneCenter"));
       pc.AddStateCost(std::make_shared<QuadraticCost>(100.0f, s + SpeedIdx(agents[i]), agents[i].nominal_speed, "NominalV"));
+      if (WithLaneBoundaries()) {
+        // the lane as a hard constraint: stay within 2.5 m of its centre line on either side (the
+        // reference example constructs these and leaves them commented out,
+        // src/three_player_intersection_example.cpp:214-251)
+        pc.AddStateConstraint(std::make_shared<Polyline2SignedDistanceConstraint>(Polyline2(agents[i].lane), xy, 2.5f, false, "LaneRightBoundary"));
+        pc.AddStateConstraint(std::make_shared<Polyline2SignedDistanceConstraint>(Polyline2(agents[i].lane), xy, -2.5f, true, "LaneLeftBoundary"));
+      }
       // controls: (steering or turn rate, jerk or acceleration), both lightly penalised
       pc.AddControlCost((PlayerIndex)i, std::make_shared<QuadraticCost>(0.1f, 0, 0.0f, "Steering"));
       pc.AddControlCost((PlayerIndex)i, std::make_shared<QuadraticCost>(0.1f, 1, 0.0f, agents[i].is_car ? "Jerk" : "Acceleration"));
@@ -89,6 +96,8 @@ class IntersectionProblem : public TopDownRenderableProblem {
 
   // false: the same game without the proximity constraints (used by the receding-horizon test)
   virtual bool WithProximityConstraints() const { return true; }
+  // true: each player's lane boundaries as Polyline2SignedDistanceConstraints
+  virtual bool WithLaneBoundaries() const { return false; }
 
   std::vector<float> Xs(const VectorXf& x) const override { return Pick(x, 0); }
   std::vector<float> Ys(const VectorXf& x) const override { return Pick(x, 1); }

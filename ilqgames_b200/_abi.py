@@ -30,7 +30,8 @@ MAX_TIME_STEPS = 512
 DYN_NONE, DYN_CAR6D, DYN_UNICYCLE4D, DYN_AIR3D, DYN_CAR5D, DYN_DUBINS, DYN_TWO_PLAYER_UNICYCLE4D, DYN_POINT_MASS_2D = 0, 1, 2, 3, 4, 5, 6, 7
 (COST_QUADRATIC, COST_QUADRATIC_POLYLINE2, COST_PROXIMITY, COST_SEMIQUADRATIC,
  COST_SEMIQUADRATIC_POLYLINE2, COST_POLYLINE2_SIGNED_DISTANCE, CONSTRAINT_PROXIMITY,
- CONSTRAINT_SINGLE_DIMENSION, COST_SIGNED_DISTANCE, COST_QUADRATIC_DIFFERENCE) = range(1, 11)
+ CONSTRAINT_SINGLE_DIMENSION, COST_SIGNED_DISTANCE, COST_QUADRATIC_DIFFERENCE,
+ CONSTRAINT_POLYLINE2_SIGNED_DISTANCE) = range(1, 12)
 COST_SUM, COST_MAX, COST_MIN = 0, 1, 2
 (STATUS_IDLE, STATUS_RUNNING, STATUS_CONVERGED, STATUS_MAX_ITERS,
  STATUS_LINESEARCH_FAILED, STATUS_NONFINITE) = range(6)

@@ -101,7 +101,8 @@ template <typename T>
 int DevAlloc(SubSolver* h, T** out, size_t count, bool zero = true);
 
 inline bool IsConstraintKind(int kind) {
-  return kind == ILQG_CONSTRAINT_PROXIMITY || kind == ILQG_CONSTRAINT_SINGLE_DIMENSION;
+  return kind == ILQG_CONSTRAINT_PROXIMITY || kind == ILQG_CONSTRAINT_SINGLE_DIMENSION ||
+         kind == ILQG_CONSTRAINT_POLYLINE2_SIGNED_DISTANCE;
 }
 
 int SubsystemXdim(int kind) {
@@ -251,12 +252,13 @@ int BuildDeviceDesc(const ilqg_problem_desc& h, DevDesc* d, ilqg_layout* lo, std
     for (int c = 0; c < h.num_costs; c++) {
       const ilqg_cost_desc& cd = h.costs[c];
       if (cd.player != i) continue;
-      if (cd.kind < ILQG_COST_QUADRATIC || cd.kind > ILQG_COST_QUADRATIC_DIFFERENCE)
+      if (cd.kind < ILQG_COST_QUADRATIC || cd.kind > ILQG_CONSTRAINT_POLYLINE2_SIGNED_DISTANCE)
         return ILQG_ERR_UNSUPPORTED;
       const int dim = cd.arg < 0 ? d->n : d->udim[cd.arg];
       const bool needs_poly = cd.kind == ILQG_COST_QUADRATIC_POLYLINE2 ||
                               cd.kind == ILQG_COST_SEMIQUADRATIC_POLYLINE2 ||
-                              cd.kind == ILQG_COST_POLYLINE2_SIGNED_DISTANCE;
+                              cd.kind == ILQG_COST_POLYLINE2_SIGNED_DISTANCE ||
+                              cd.kind == ILQG_CONSTRAINT_POLYLINE2_SIGNED_DISTANCE;
       if (needs_poly && (cd.polyline < 0 || cd.polyline >= h.num_polylines)) return ILQG_ERR_INVALID_ARGUMENT;
       const int ndims = (cd.kind == ILQG_COST_PROXIMITY || cd.kind == ILQG_CONSTRAINT_PROXIMITY ||
                          cd.kind == ILQG_COST_SIGNED_DISTANCE) ? 4

@@ -113,15 +113,19 @@ class DescBuilder:
 # ThreePlayerIntersectionExample, src/three_player_intersection_example.cpp
 # --------------------------------------------------------------------------
 def three_player_intersection(num_time_steps: int = 100, time_step: float = 0.1,
-                              with_constraints: bool = True):
+                              with_constraints: bool = True, lane_constraints: bool = False):
     """Returns (desc, x0).  2x SinglePlayerCar6D + 1x SinglePlayerUnicycle4D, n = 16.
     with_constraints = False drops the proximity constraints (an unconstrained variant used by the
-    receding-horizon tests; the reference example always has them)."""
+    receding-horizon tests; the reference example always has them).
+    lane_constraints = True adds the six Polyline2SignedDistanceConstraints the example constructs
+    and leaves commented out (its lane boundaries, :214-251), in the order the commented lines would
+    add them: each player's right and left boundary ahead of its proximity constraints."""
     b = DescBuilder(num_time_steps, time_step)
     kInterAxleLength = 4.0
     kStateReg, kControlReg = 1.0, 5.0
     kOmegaCostWeight, kJerkCostWeight, kACostWeight = 0.1, 0.1, 0.1
     kNominalVCostWeight, kLaneCostWeight, kMinProximity = 100.0, 25.0, 6.0
+    kLaneHalfWidth, kOrientedRight = 2.5, True  # :99,103
     kP1NominalV, kP2NominalV, kP3NominalV = 8.0, 5.0, 1.5
     kP1InitialX, kP2InitialX, kP3InitialX = -2.0, -10.0, -11.0
     kP1InitialY, kP2InitialY, kP3InitialY = -30.0, 45.0, 16.0
@@ -153,6 +157,11 @@ def three_player_intersection(num_time_steps: int = 100, time_step: float = 0.1,
                      polyline=lanes[i])  # :211-251
         b.state_cost(i, abi.COST_QUADRATIC, dims=(vidx[i],), weight=kNominalVCostWeight,
                      value=nominal_v[i])  # :254-287
+        if lane_constraints:  # :214-221, 229-236, 244-251 (commented out in the reference example)
+            b.state_constraint(i, abi.CONSTRAINT_POLYLINE2_SIGNED_DISTANCE, dims=pos[i], polyline=lanes[i],
+                               value=kLaneHalfWidth, flag=int(not kOrientedRight))
+            b.state_constraint(i, abi.CONSTRAINT_POLYLINE2_SIGNED_DISTANCE, dims=pos[i], polyline=lanes[i],
+                               value=-kLaneHalfWidth, flag=int(kOrientedRight))
     # control costs :289-335 (P3's second control is acceleration)
     b.control_cost(0, 0, abi.COST_QUADRATIC, dims=(0,), weight=kOmegaCostWeight, value=0.0)
     b.control_cost(0, 0, abi.COST_QUADRATIC, dims=(1,), weight=kJerkCostWeight, value=0.0)

@@ -111,8 +111,11 @@ enum {
   ILQG_CONSTRAINT_SINGLE_DIMENSION = 8,   /* dim[0], value=threshold, flag=keep_below          */
   ILQG_COST_SIGNED_DISTANCE = 9,          /* src/signed_distance_cost.cpp:50-112: dim[0..3]=x1,y1,x2,y2,
                                            * value=nominal, flag=less_is_positive (weight unused) */
-  ILQG_COST_QUADRATIC_DIFFERENCE = 10     /* src/quadratic_difference_cost.cpp:50-91: 0.5 w sum (in[a_k] - in[b_k])^2
+  ILQG_COST_QUADRATIC_DIFFERENCE = 10,    /* src/quadratic_difference_cost.cpp:50-91: 0.5 w sum (in[a_k] - in[b_k])^2
                                            * over flag = 1 or 2 pairs, dim[0..1] = a, dim[2..3] = b */
+  ILQG_CONSTRAINT_POLYLINE2_SIGNED_DISTANCE = 11 /* src/polyline2_signed_distance_constraint.cpp:58-145:
+                                           * g = +/-(signed distance to the polyline - value) <= 0, dim[0..1] = x, y,
+                                           * polyline, value = threshold, flag = keep_left */
 };
 
 typedef struct {

@@ -453,14 +453,25 @@ class SingleDimensionConstraint : public TimeInvariantConstraint {
   const bool keep_below_;
 };
 
-// include/ilqgames/constraint/polyline2_signed_distance_constraint.h:58-90: the intersection
-// example constructs six of these and adds none; no device record yet.
+// include/ilqgames/constraint/polyline2_signed_distance_constraint.h:58-90,
+// src/polyline2_signed_distance_constraint.cpp:58-145 (the intersection example constructs six of these
+// -- its lane boundaries -- and adds none: src/three_player_intersection_example.cpp:214-251)
 class Polyline2SignedDistanceConstraint : public TimeInvariantConstraint {
  public:
   Polyline2SignedDistanceConstraint(const Polyline2& polyline, const std::pair<Dimension, Dimension>& dims,
                                     float threshold, bool keep_left, const std::string& name = "")
       : TimeInvariantConstraint(false, name), polyline_(polyline), xidx_(dims.first), yidx_(dims.second),
         threshold_(threshold), keep_left_(keep_left) {}
+  bool Describe(ilqg_cost_desc* out, DescribeContext* ctx) const override {
+    out->kind = ILQG_CONSTRAINT_POLYLINE2_SIGNED_DISTANCE;
+    out->dim[0] = xidx_;
+    out->dim[1] = yidx_;
+    out->value = threshold_;
+    out->flag = keep_left_;
+    out->weight = 1.0f;
+    out->polyline = ctx->AddPolyline(polyline_);
+    return out->polyline >= 0;
+  }
 
  private:
   const Polyline2 polyline_;

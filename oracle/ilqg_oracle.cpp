@@ -204,7 +204,8 @@ void UpdateCostGates(Problem* pr, double tracker_initial_time) {
 }
 
 inline bool IsConstraintKind(int kind) {
-  return kind == ILQG_CONSTRAINT_PROXIMITY || kind == ILQG_CONSTRAINT_SINGLE_DIMENSION;
+  return kind == ILQG_CONSTRAINT_PROXIMITY || kind == ILQG_CONSTRAINT_SINGLE_DIMENSION ||
+         kind == ILQG_CONSTRAINT_POLYLINE2_SIGNED_DISTANCE;
 }
 
 int BuildProblem(const ilqg_problem_desc* desc, const ilqg_solver_params* params,
@@ -664,6 +665,13 @@ real EvaluateRecord(const Problem& pr, const ilqg_cost_desc& cd, const real* in,
     case ILQG_CONSTRAINT_SINGLE_DIMENSION: {  // single_dimension_constraint.h:68-70
       return cd.flag ? in[cd.dim[0]] - cd.value : cd.value - in[cd.dim[0]];
     }
+    case ILQG_CONSTRAINT_POLYLINE2_SIGNED_DISTANCE: {  // src/polyline2_signed_distance_constraint.cpp:58-70
+      real ssd;
+      PolylineClosestPoint(pr.polylines[cd.polyline], {in[cd.dim[0]], in[cd.dim[1]]}, nullptr,
+                           nullptr, &ssd, nullptr);
+      const real value = sgn(ssd) * std::sqrt(std::abs(ssd)) - cd.value;
+      return cd.flag ? value : -value;
+    }
   }
   return 0;
 }
@@ -946,6 +954,58 @@ void QuadraticizeRecord(const Problem& pr, const ilqg_cost_desc& cd, const real*
       ModifyDerivatives(cd, lambda, mu, g, &dx, &ddx, nullptr, nullptr, nullptr);
       grad[dim_] += dx;
       H(dim_, dim_) += ddx;
+      break;
+    }
+    case ILQG_CONSTRAINT_POLYLINE2_SIGNED_DISTANCE: {  // src/polyline2_signed_distance_constraint.cpp:72-145
+      const int xidx_ = cd.dim[0], yidx_ = cd.dim[1];
+      const Polyline& pl = pr.polylines[cd.polyline];
+      const real threshold_ = cd.value;
+      const bool keep_left_ = cd.flag != 0;
+      bool is_vertex;
+      int seg;
+      real signed_distance_sq;
+      const Point2 closest_point =
+          PolylineClosestPoint(pl, {in[xidx_], in[yidx_]}, &is_vertex, &seg, &signed_distance_sq, nullptr);
+      const Segment& closest_segment = pl.segs[seg];
+      const real s = sgn(signed_distance_sq);
+      const real x = in[xidx_];
+      const real y = in[yidx_];
+      real px = closest_segment.p1.x;
+      real py = closest_segment.p1.y;
+      real rx = x - px;
+      real ry = y - py;
+      real d_sq = rx * rx + ry * ry;
+      real d = std::sqrt(d_sq);
+      const real ux = closest_segment.unit.x;
+      const real uy = closest_segment.unit.y;
+      const real sign = (keep_left_) ? 1.0 : -1.0;
+      const real signed_root = sgn(signed_distance_sq) * std::sqrt(std::abs(signed_distance_sq));
+      const real g = (keep_left_) ? signed_root - threshold_ : threshold_ - signed_root;
+      real dx = sign * uy;
+      real ddx = 0.0;
+      real dy = -sign * ux;
+      real ddy = 0.0;
+      real dxdy = 0.0;
+      if (is_vertex) {
+        px = closest_point.x;
+        py = closest_point.y;
+        rx = x - px;
+        ry = y - py;
+        d_sq = (rx * rx + ry * ry);
+        d = std::sqrt(d_sq);
+        dx = sign * s * rx / d;
+        ddx = sign * s * (d_sq - px * px - x * x + 2 * px * x) / (d_sq * d);
+        dxdy = -sign * s * rx * ry / (d_sq * d);
+        dy = sign * s * ry / d;
+        ddy = sign * s * (d_sq - py * py - y * y + 2 * py * y) / (d_sq * d);
+      }
+      ModifyDerivatives(cd, lambda, mu, g, &dx, &ddx, &dy, &ddy, &dxdy);
+      grad[xidx_] += dx;
+      grad[yidx_] += dy;
+      H(xidx_, xidx_) += ddx;
+      H(xidx_, yidx_) += dxdy;
+      H(yidx_, xidx_) += dxdy;
+      H(yidx_, yidx_) += ddy;
       break;
     }
   }

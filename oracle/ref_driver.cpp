@@ -13,6 +13,8 @@
 //   Ps     [T][M][n]              alphas [T][M]            (final strategies)
 //   costs  [N]                                             (final iterate)
 #include <ilqgames/constraint/constraint.h>
+#include <ilqgames/constraint/polyline2_signed_distance_constraint.h>
+#include <ilqgames/geometry/polyline2.h>
 #include <ilqgames/cost/player_cost.h>
 #include <ilqgames/examples/air_3d_example.h>
 #include <ilqgames/examples/dubins_origin_example.h>
@@ -487,6 +489,40 @@ int ilqg_ref_lin_quad(int which, const float* x0, const ilqg_ref_params* q, floa
   }
   ResetMultipliers(*problem);
   return ok ? 0 : 1;
+}
+
+// The reference's own Polyline2SignedDistanceConstraint (src/polyline2_signed_distance_constraint.cpp) at
+// `count` points: no example adds one (the intersection example constructs six and leaves them commented
+// out), so the class itself is the only thing there is to pin the record kind against.
+// `lambda_step` != 0: IncrementLambda(0, lambda_step) first (lambda = max(0, mu lambda_step), constraint.h:96-100).
+// out [count][7] = g, lambda, d/dx, d/dy, d2/dx2, d2/dxdy, d2/dy2 of the augmented Lagrangian terms.
+int ilqg_ref_polyline_constraint(const float* pts, int npts, float threshold, int keep_left, float mu,
+                                 float lambda_step, const float* xy, int count, float* out) {
+  PointList2 points;
+  for (int k = 0; k < npts; k++) points.push_back(Point2(pts[2 * k], pts[2 * k + 1]));
+  const Polyline2 polyline(points);
+  Polyline2SignedDistanceConstraint constraint(polyline, {0, 1}, threshold, keep_left != 0);
+  const float saved_mu = Constraint::GlobalMu();
+  Constraint::GlobalMu() = mu;
+  if (lambda_step != 0.0f) constraint.IncrementLambda(0.0, lambda_step);
+  for (int k = 0; k < count; k++) {
+    VectorXf input(2);
+    input(0) = xy[2 * k];
+    input(1) = xy[2 * k + 1];
+    MatrixXf hess = MatrixXf::Zero(2, 2);
+    VectorXf grad = VectorXf::Zero(2);
+    constraint.Quadraticize(0.0, input, &hess, &grad);
+    float* o = out + 7 * k;
+    o[0] = constraint.Evaluate(input);
+    o[1] = constraint.Lambda(0.0);
+    o[2] = grad(0);
+    o[3] = grad(1);
+    o[4] = hess(0, 0);
+    o[5] = hess(0, 1);
+    o[6] = hess(1, 1);
+  }
+  Constraint::GlobalMu() = saved_mu;
+  return 0;
 }
 
 }  // extern "C"

@@ -278,6 +278,9 @@ void TestILQSolver(const std::shared_ptr<Problem>& problem) {
 class IntersectionWithoutConstraints : public ilqgames_b200_examples::IntersectionProblem {
   bool WithProximityConstraints() const override { return false; }
 };
+class IntersectionWithLaneBoundaries : public ilqgames_b200_examples::IntersectionProblem {
+  bool WithLaneBoundaries() const override { return true; }
+};
 
 void TestRecedingHorizon() {
   const std::shared_ptr<Problem> problem = MakeProblem<IntersectionWithoutConstraints>();
@@ -466,6 +469,8 @@ int main(int argc, char** argv) {
   TestLQOpenLoopIsNash();
   const std::shared_ptr<Problem> problem = MakeProblem<ilqgames_b200_examples::IntersectionProblem>();
   TestProblemDescriptor(problem, "own");
+  // the same game with its lane boundaries as Polyline2SignedDistanceConstraints (24 records)
+  TestProblemDescriptor(MakeProblem<IntersectionWithLaneBoundaries>(), "lanes", 3, 16, 24, 3);
 #ifdef DROPIN_REFERENCE_EXAMPLE
   TestProblemDescriptor(MakeProblem<ThreePlayerIntersectionExample>(), "reference");
   // src/roundabout_merging_example.cpp (+ roundabout_lane_center.cpp, initialize_along_route.cpp) and

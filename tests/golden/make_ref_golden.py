@@ -319,11 +319,45 @@ def check_polylines(ref: R.RefLibrary):
     return out
 
 
+POLYLINE_CONSTRAINT_CASES = [
+    # (polyline, threshold, keep_left, mu, lambda_step): the reference test's polyline and arguments
+    # (test/test_quadraticization.cpp:323-327), its mirror image, a lane boundary of the intersection
+    # example (src/three_player_intersection_example.cpp:229-236: lane2, half width 2.5) with a
+    # non-zero multiplier
+    ([(-2.0, -2.0), (0.5, 1.0), (2.0, 2.0)], 10.0, True, 10.0, 0.0),
+    ([(-2.0, -2.0), (0.5, 1.0), (2.0, 2.0)], -0.5, False, 10.0, 0.0),
+    ([(-10.0, 1000.0), (-10.0, 18.0), (-9.5, 15.0), (-9.0, 14.0), (-7.0, 12.5), (-4.0, 12.0), (1000.0, 12.0)],
+     2.5, False, 10.0, 0.3),
+    ([(-10.0, 1000.0), (-10.0, 18.0), (-9.5, 15.0), (-9.0, 14.0), (-7.0, 12.5), (-4.0, 12.0), (1000.0, 12.0)],
+     -2.5, True, 25.0, 0.07),
+]
+
+
+def run_polyline_constraint(ref: R.RefLibrary):
+    """The reference's own Polyline2SignedDistanceConstraint class (no example adds one) at seeded points
+    around each polyline -- interior closest points, vertices, both sides -- for ILQG_CONSTRAINT_POLYLINE2_SIGNED_DISTANCE."""
+    out = {}
+    rng = np.random.default_rng(11)
+    for c, (pts, threshold, keep_left, mu, lam_step) in enumerate(POLYLINE_CONSTRAINT_CASES):
+        pts = np.asarray(pts, np.float32)
+        inner = pts[np.abs(pts).max(axis=1) < 500.0]
+        centre, spread = inner.mean(axis=0), np.maximum(np.ptp(inner, axis=0), 4.0)
+        xy = (centre + rng.uniform(-1.0, 1.0, size=(64, 2)) * spread).astype(np.float32)
+        out[f"case{c}_pts"] = pts
+        out[f"case{c}_args"] = np.asarray([threshold, float(keep_left), mu, lam_step], np.float32)
+        out[f"case{c}_xy"] = xy
+        out[f"case{c}_out"] = ref.polyline_constraint(pts, threshold, keep_left, mu, lam_step, xy)
+    return out
+
+
 if __name__ == "__main__":
     subprocess.run(["make", "-C", os.path.join(REPO, "oracle"), "ref"], check=True,
                    stdout=subprocess.DEVNULL)
     ref = R.RefLibrary()
     np.savez_compressed(os.path.join(HERE, "ref_polylines.npz"), **check_polylines(ref))
+    np.savez_compressed(os.path.join(HERE, "ref_polyline_constraint.npz"), **run_polyline_constraint(ref))
+    if "--polyline-constraint-only" in sys.argv:
+        sys.exit(0)
     # SolutionSplicer::Splice on synthetic logs (new horizon inside / beyond the keep window / at t0)
     splice = {}
     for c, new_t0 in enumerate(SPLICE_T0S):

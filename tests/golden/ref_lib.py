@@ -154,6 +154,19 @@ class RefLibrary:
                                           num_segments, _ptr(pts), num_segments + 1)
         return pts[:k]
 
+    def polyline_constraint(self, pts, threshold: float, keep_left: bool, mu: float, lambda_step: float, xy):
+        """The reference's own Polyline2SignedDistanceConstraint at the points `xy` [count][2]:
+        rows of (g, lambda, d/dx, d/dy, d2/dx2, d2/dxdy, d2/dy2)."""
+        pts = np.ascontiguousarray(pts, np.float32)
+        xy = np.ascontiguousarray(xy, np.float32)
+        out = np.zeros((len(xy), 7), np.float32)
+        self.lib.ilqg_ref_polyline_constraint.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float,
+                                                          C.c_void_p, C.c_int, C.c_void_p]
+        rc = self.lib.ilqg_ref_polyline_constraint(_ptr(pts), len(pts), threshold, int(keep_left), mu, lambda_step,
+                                                   _ptr(xy), len(xy), _ptr(out))
+        assert rc == 0
+        return out
+
     def _sum_udim_sq(self, which: int) -> int:
         return {INTERSECTION: 12, ROUNDABOUT: 16, AIR3D: 2, OVERTAKING: 12, COLLISION: 8, REACHABILITY2: 8, REACHABILITY3: 12, REACHABILITY1: 1, DUBINS_ORIGIN: 2, REACHABILITY_2P: 8, MODIFIED_AIR3D: 8, MODIFIED_INTERSECTION: 12, SKELETON: 8,
                 INTERSECTION_REACHABILITY: 12}[which]

@@ -921,3 +921,66 @@ def test_tier_splits_and_pipeline_give_identical_solves(product, name, T, batch)
     bt = outs[0][7]
     report(f"tier_splits[{name},T={T}]", batch=x0.shape[0], variants=len(variants), rollouts=int(bt.sum()),
            failed=int((outs[0][5] == abi.STATUS_LINESEARCH_FAILED).sum()))
+
+
+# ------------------------------------------------------------------ lane-boundary constraints
+def test_polyline2_signed_distance_constraint_on_the_device(product, oracle, oracle64):
+    """ILQG_CONSTRAINT_POLYLINE2_SIGNED_DISTANCE (src/polyline2_signed_distance_constraint.cpp:58-145) on the
+    device: ThreePlayerIntersection with the six lane-boundary constraints the reference example
+    constructs and leaves commented out (src/three_player_intersection_example.cpp:214-251), cars
+    started up to 4 m off their lane centres so that boundaries are violated, multipliers made
+    non-zero by one ilqg_al_update sweep.  Records (K_lq), the LQ solve, the linesearch (merit
+    kernel) and the multiplier update are compared with the oracle stage by stage."""
+    desc, _ = problems.three_player_intersection(lane_constraints=True)
+    B = 16
+    x0 = problems.three_player_intersection_x0_batch(B, 77)
+    rng = np.random.default_rng(5)
+    x0[:, 0] += rng.uniform(-4.0, 4.0, B).astype(np.float32)    # P1 across its lane (x)
+    x0[:, 6] += rng.uniform(-4.0, 4.0, B).astype(np.float32)    # P2
+    x0[:, 13] += rng.uniform(-4.0, 4.0, B).astype(np.float32)   # P3 across its lane (y)
+    hs = []
+    for lib in (product, oracle, oracle64):
+        h = abi.Handle(lib, desc, problems.three_player_intersection_params(), B, 0)
+        h.upload_x0(x0)
+        h.solve_begin()
+        hs.append(h)
+    c, o, o64 = hs
+    assert c.layout.num_constraints == 12  # 6 proximity + 6 lane boundaries
+    good = np.ones(B, bool)
+    compared = []
+
+    def check(what, tol=STAGE_TOL, label=""):
+        nonlocal good
+        a, b, b64 = c.download(what), o.download(what), o64.download(what)
+        good = good & wellposed(b, b64)
+        cond = None if "record" in label else row_distance(b, b64)
+        compared.append(close(a, b, tol=tol, rows=good, what=f"{label} field {what}", cond=cond))
+
+    for sweep in range(2):
+        for h in hs:
+            h.linearize_quadraticize()
+        for what in (abi.QUAD_Q, abi.QUAD_L):
+            check(what, label=f"sweep{sweep} record")
+        for h in hs:
+            h.lq_backward()
+        for what in (abi.LQ_PS, abi.LQ_ALPHAS):
+            check(what, tol=1e-3, label=f"sweep{sweep} LQ")
+        for h in hs:
+            h.linesearch()
+        same = np.ones(B, bool)
+        for what in (abi.STATUS, abi.ITERS, abi.BACKTRACKS):
+            same &= c.download(what) == o.download(what)
+        good = good & same & (o.download(abi.BACKTRACKS) == o64.download(abi.BACKTRACKS))
+        for what in (abi.XS, abi.MERIT):
+            check(what, tol=1e-3, label=f"sweep{sweep} linesearch")
+        for h in hs:
+            h.al_update()  # lambda <- max(0, lambda + mu g) at the current operating point
+        lam_c, lam_o = c.download(abi.LAMBDAS), o.download(abi.LAMBDAS)
+        compared.append(close(lam_c, lam_o, tol=1e-3, atol=1e-4, rows=good, what=f"sweep{sweep} lambdas"))
+        # the lane multipliers are really in play: some boundary constraint is violated in most games
+        lanes_active = (lam_o.reshape(B, 12, -1)[:, [0, 1, 4, 5, 8, 9]] > 0).any(axis=(1, 2))
+        assert lanes_active.sum() >= B // 2, lanes_active
+    report("polyline2_signed_distance_constraint", batch=B, wellposed_at_end=good.sum(), min_rows_compared=min(compared))
+    assert good.sum() >= B // 2 and min(compared) >= B // 2
+    for h in hs:
+        h.close()

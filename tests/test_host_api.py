@@ -73,6 +73,9 @@ def _check_against_ctypes(lib, got, exact=True):
     # Problem -> descriptor: byte-identical to the Python builder
     assert np.array_equal(np.frombuffer(bytes(desc), dtype=np.uint32), got["desc_own"].view(np.uint32))
     assert np.array_equal(x0, got["x0_own"])
+    # ... and with the lane boundaries on (Polyline2SignedDistanceConstraint::Describe)
+    desc_l, _ = problems.three_player_intersection(lane_constraints=True)
+    assert np.array_equal(np.frombuffer(bytes(desc_l), dtype=np.uint32), got["desc_lanes"].view(np.uint32))
     same = np.array_equal if exact else (lambda a, b: np.allclose(a, b, rtol=1e-3, atol=1e-3))
 
     # ILQSolver::Solve, max_solver_iters = 4

@@ -289,6 +289,11 @@ COST_CASES = {
                             None, True),
     "SingleDimensionConstraint": (abi.CONSTRAINT_SINGLE_DIMENSION, dict(dims=(0,), value=1.0, flag=1),
                                   None, True),
+    # test/test_quadraticization.cpp:323-327 (threshold 10, keep_left) and its mirror image
+    "Polyline2SignedDistanceConstraint": (abi.CONSTRAINT_POLYLINE2_SIGNED_DISTANCE,
+                                          dict(dims=(0, 1), value=10.0, flag=1), kPolyline, True),
+    "Polyline2SignedDistanceConstraintRight": (abi.CONSTRAINT_POLYLINE2_SIGNED_DISTANCE,
+                                               dict(dims=(0, 1), value=-0.5, flag=0), kPolyline, True),
     # kinds added with the widening of SURVEY 8 f4 (test/test_quadraticization.cpp has the same checks:
     # QuadraticDifferenceCostTest :210-214 with dims {0, 1} / {1, 2}, SignedDistanceCostTest :291-295)
     "SignedDistanceCost": (abi.COST_SIGNED_DISTANCE, dict(dims=(0, 1, 2, 3), value=5.0, flag=1), None, False),

@@ -422,3 +422,33 @@ def test_reset_solution_rewinds_the_receding_horizon_clock(oracle):
     h.reset(h.RESET_SOLUTION)
     assert np.all(h.download(abi.WARM_XS) == 0)
     assert h.setup_next_receding_horizon(x, 0.05, 0.0) > 0.05
+
+
+def test_polyline2_signed_distance_constraint_equals_the_references_class(oracle):
+    """ILQG_CONSTRAINT_POLYLINE2_SIGNED_DISTANCE against the reference's own class
+    (src/polyline2_signed_distance_constraint.cpp:58-145; no example adds one, so the class is what there
+    is to pin against): g and the augmented-Lagrangian derivatives at 64 seeded points per case --
+    interior closest points and vertices, both orientations, with and without a multiplier -- bit for bit."""
+    from tests import oracle_probes as probe
+    g = np.load(os.path.join(GOLDEN, "ref_polyline_constraint.npz"))
+    cases = len([k for k in g.files if k.endswith("_pts")])
+    assert cases == 4
+    vertices = 0
+    for c in range(cases):
+        pts, (threshold, keep_left, mu, _), xy, want = (g[f"case{c}_{k}"] for k in ("pts", "args", "xy", "out"))
+        b = problems.DescBuilder(10, 0.1)
+        b.add_player(1)
+        b.d.xdim = 2
+        b.state_constraint(0, abi.CONSTRAINT_POLYLINE2_SIGNED_DISTANCE, dims=(0, 1), value=float(threshold),
+                           flag=int(keep_left), polyline=b.add_polyline([tuple(p) for p in pts.tolist()]))
+        h = abi.Handle(oracle, b.build(), abi.SolverParams.defaults(), 1)
+        for q, w in zip(xy, want):
+            lam = float(w[1])
+            assert np.float32(probe.evaluate_record(oracle, h, 0, q)) == w[0]
+            hess, grad = probe.quadraticize_record(oracle, h, 0, q, lam, float(mu))
+            got = np.array([grad[0], grad[1], hess[0, 0], hess[0, 1], hess[1, 1]], np.float32)
+            assert np.array_equal(got, w[2:]), (c, q, got, w[2:])
+            assert hess[0, 1] == hess[1, 0]
+            vertices += probe.polyline_closest_point(oracle, h, 0, q)[1]
+        h.close()
+    assert vertices > 20  # (the vertex branch of Quadraticize is exercised, not only the interior one)
