@@ -14,6 +14,9 @@ line; for N > 1 it is launched under torch.distributed.run, one rank per GPU.
               pinned-host -> device and trajectories + status come back device -> pinned-host
   roofline    dominant kernel: algorithmic bytes per launch / mean launch duration (CUDA events)
   cpu_baseline  the CPU oracle (restatement of the reference's Eigen path) on a bounded sample
+  config      the workload, stated identically by both arms (nothing measured, nothing host-dependent)
+  workload_stats  what the run measured about the workload: iterations completed per step, status
+              histogram, how the linesearches ended (first try / backtracked / failed)
 
 `--impl reference` times the reference algorithm's CPU path instead (the oracle port, all host
 cores) on the same workload/metric; no GPU code runs in that arm.
@@ -92,13 +95,32 @@ def usable_cores() -> int:
     return cores
 
 
-def bench_config(config: str, batch: int, world: int, seed: int) -> dict:
-    """The workload description shared by both arms (same `config` keys)."""
+def l2_policy(batch: int, layout):
+    """(need_flush, note): the strategy buffers alone that one iteration rewrites and re-reads
+    (2 x T x M x (n + 1) floats per game) against the 126 MB L2 -- a criterion both arms can evaluate
+    from the problem's shape, so that their `config` objects are the same."""
+    ws_mb = batch * layout.num_time_steps * 4 * 2 * layout.total_udim * (layout.xdim + 1) / 1e6
+    need_flush = ws_mb <= 126
+    note = (f"one iteration streams {ws_mb:.0f} MB of strategies (plus the LQ records) per {batch} instances: "
+            + ("fits the 126 MB L2, so a 256 MB write flushes L2 before every timed step" if need_flush
+               else "exceeds the 126 MB L2, no explicit flush"))
+    return need_flush, note
+
+
+def bench_config(config: str, batch: int, world: int, seed: int, layout) -> dict:
+    """The workload description, IDENTICAL in both arms (`--impl reference` prints the same object;
+    everything measured goes to `workload_stats`, what a CPU step really solves to `cpu_baseline.sample`)."""
     c = CONFIGS[config]
     return {"workload": f"batch {batch} {c['label']}, T={c['T']}, "
                         f"{ITERS_PER_SOLVE} iLQ iterations/solve, lambda=0 mu=10, convergence exit disabled",
             "config": config, "batch_per_gpu": batch, "global_batch": batch * world,
-            "iterations_per_step": ITERS_PER_SOLVE, "seed": seed}
+            "iterations_per_step": ITERS_PER_SOLVE, "seed": seed,
+            "l2": l2_policy(batch, layout)[1],
+            "parallelism": f"dp{world} (independent games, no hot-path collective)",
+            "reference_arm": "--impl reference times the CPU path on a bounded SAMPLE of this workload: each step "
+                             "solves the first min(batch, 16 x host cores) instances of the same seeded batch, one "
+                             "process per core (throughput per instance-iteration does not depend on the batch on "
+                             "the CPU); the exact sample is stated in its cpu_baseline.sample"}
 
 
 def algorithmic_bytes(layout) -> dict:
@@ -287,6 +309,11 @@ def run_reference(args):
     _, _, x0 = workload(args.config, args.batch, args.seed, 0, min(args.batch, cores * per_worker))
     sample = x0
     chunks = [c for c in np.array_split(sample, cores) if len(c)]
+    from ilqgames_b200 import _abi as abi
+    desc_, params_, _ = workload(args.config, 1, 0)
+    h_ = abi.Handle(abi.Library(ORACLE_LIB), desc_, params_, 1)
+    ref_layout = h_.layout
+    h_.close()
     ctx = mp.get_context("fork")
     times = []
     done_total = 0
@@ -306,10 +333,11 @@ def run_reference(args):
         "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         # same workload description as the repo arm; the CPU arm's step is a bounded SAMPLE of it
-        "config": dict(bench_config(args.config, args.batch, 1, args.seed), reference_sample_instances=len(sample),
-                       reference_sample=f"each step solves the first {len(sample)} of the {args.batch} instances "
-                                        f"({len(chunks)} processes x {per_worker}); throughput per instance-iteration "
-                                        "does not depend on the batch on the CPU"),
+        # the repo arm's `config`, key for key; this arm's step is a bounded SAMPLE of that workload
+        "config": bench_config(args.config, args.batch, max(1, args.gpus), args.seed, ref_layout),
+        "workload_stats": {"reference_sample_instances": len(sample),
+                           "reference_sample": f"each step solves the first {len(sample)} of the {args.batch} instances "
+                                               f"({len(chunks)} processes x {per_worker})"},
         "cpu_baseline": {"value": value, "unit": "instance-iterations/s", "cores": len(chunks), "kind": "port",
                          "sample": f"first {len(sample)} instances of the batch x {ITERS_PER_SOLVE} iterations per step, "
                                    f"{len(chunks)} processes; oracle port of the reference's Eigen path: faster than "
@@ -378,10 +406,7 @@ def run_b200(args):
     launches0 = h.kernel_launches()
     # working set of one iteration (records + both strategy buffers): above the 126 MB L2 for every
     # batched configuration; the small ones (c1) get an explicit L2 flush before each timed step
-    lo_ = h.layout
-    ws_mb = args.batch * lo_.num_time_steps * 4 * ((lo_.compact_record_floats or lo_.record_floats)
-                                                   + 2 * lo_.total_udim * (lo_.xdim + 1)) / 1e6
-    need_flush = ws_mb <= 126
+    need_flush, _ = l2_policy(args.batch, h.layout)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if need_flush else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
@@ -504,10 +529,6 @@ def run_b200(args):
                                     if k in per_kernel_bytes else None,
                                     designed_GBps=compact_bytes[k] / (v["ms_per_launch"] * 1e-3) / 1e9
                                     if k in compact_bytes else None) for k, v in kern.items()}}
-    l2_note = (f"one iteration streams {ws_mb:.0f} MB (LQ records + both strategy buffers) per {args.batch} instances: "
-               + ("fits the 126 MB L2, so a 256 MB write flushes L2 before every timed step" if need_flush
-                  else "exceeds the 126 MB L2, no explicit flush"))
-
     # ---- end to end through the C ABI with host buffers ------------------------------
     pin_x0 = torch.from_numpy(x0).pin_memory()
     lo = h.layout
@@ -571,13 +592,11 @@ def run_b200(args):
             "metric": "ilq_instance_iterations_per_second", "value": value, "unit": "instance-iterations/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(bench_config(args.config, args.batch, world, args.seed),
-                           instance_iterations_per_step=total_done_per_step,
-                           mean_rollouts_per_iteration=roll_per_step / max(done_per_step, 1),
-                           status_histogram_rank0=hist,
-                           linesearch_split=ls_split,
-                           l2=l2_note,
-                           parallelism=f"dp{world} (independent games, no hot-path collective)"),
+            "config": bench_config(args.config, args.batch, world, args.seed, h.layout),
+            "workload_stats": {"instance_iterations_per_step": total_done_per_step,
+                               "mean_rollouts_per_iteration": roll_per_step / max(done_per_step, 1),
+                               "status_histogram_rank0": hist,
+                               "linesearch_split": ls_split},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "instance-iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},

@@ -24,6 +24,16 @@ def test_reference_arm_prints_one_json_line():
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0,
                            "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]
+    # the reference arm prints the repo arm's `config`, key for key (the driver compares the two): nothing
+    # measured and nothing that depends on the host lives in it
+    import bench
+    from ilqgames_b200 import _abi as abi
+    desc, params, _ = bench.workload("metric", 1, 0)
+    h = abi.Handle(abi.Library(bench.ORACLE_LIB), desc, params, 1)
+    assert line["config"] == bench.bench_config("metric", 32, 1, 4096, h.layout)
+    assert set(line["config"]) == {"workload", "config", "batch_per_gpu", "global_batch", "iterations_per_step", "seed",
+                                   "l2", "parallelism", "reference_arm"}
+    assert line["workload_stats"]["reference_sample_instances"] >= 16
 
 
 def test_gpu_arm_refuses_to_run_without_a_device():
